@@ -1,0 +1,311 @@
+// Host-side post-processing that follows the GPU seed-and-verify path:
+// reference-window decode, CIGAR refinement (banded affine-gap DP with
+// quality-scaled mismatch penalties), MAPQ, chromosome lookup.  These are the
+// "next" rows of SURVEY.md §8(f)-1 and stay on the host, as in the reference.
+//
+// Behaviour mirrors (results must be identical on identical inputs):
+//   window decode           Schema.cpp:4998-5115 (get_actuall_genome / _rc_genome)
+//   ungapped shortcut       ksw.cpp:2515-2570    (try_cigar_without_path)
+//   CIGAR refinement        ksw.cpp:2578-3148    (fast_recalculate_bs_Cigar)
+//   banded DP + traceback   ksw.cpp:1850-2045    (ksw_semi_global_quality_back)
+//   mismatch penalty        ksw.h:148-162        (MismatchPenaltyByQuality)
+//   MAPQ table              Schema.cpp:168-405   (MAP_Calculation)
+//   coordinate conversion   Schema.cpp:12596-12650, :9188-9244
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace bmbs {
+
+struct Scoring {
+  int mp_max = 6, mp_min = 2, n_pen = 1, gap_open = 5, gap_ext = 3, q_base = 33;
+};
+
+struct ChromTable {
+  std::vector<std::string> name;
+  std::vector<uint64_t> len, start, end;
+  uint64_t N = 0;
+  // <prefix>.index : u64 nChrom; {u64 nameLen; name; u64 len}*; u64 N   (Index.cpp:134-159, :940-980)
+  bool load(const std::string& path) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    uint64_t nc = 0, s = 0;
+    bool ok = fread(&nc, 8, 1, f) == 1;
+    for (uint64_t i = 0; ok && i < nc; ++i) {
+      uint64_t l = 0, cl = 0;
+      ok = fread(&l, 8, 1, f) == 1 && l < (1u << 20);
+      std::string nm(l, '\0');
+      ok = ok && (l == 0 || fread(&nm[0], 1, l, f) == l) && fread(&cl, 8, 1, f) == 1;
+      name.push_back(nm); len.push_back(cl); start.push_back(s); end.push_back(s + cl - 1);
+      s += cl;
+    }
+    ok = ok && fread(&N, 8, 1, f) == 1;
+    fclose(f);
+    return ok;
+  }
+  // linear scan like the reference; returns name.size() when nothing contains pos
+  size_t find(uint64_t pos) const {
+    size_t c = 0;
+    for (; c < name.size(); ++c) if (pos >= start[c] && pos <= end[c]) break;
+    return c;
+  }
+};
+
+// 2-bit genome, four bases per byte, first base in the top bits, A0 C1 G2 T3.
+struct Genome2bit {
+  std::vector<uint8_t> pac;
+  uint64_t N = 0;
+  bool load(const std::string& path, uint64_t n_bases) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    uint64_t nb = 0;
+    bool ok = fread(&nb, 8, 1, f) == 1;
+    pac.assign(nb + 8, 0);
+    ok = ok && fread(pac.data(), 1, nb, f) == nb;
+    pac.resize(nb);
+    fclose(f);
+    N = n_bases;
+    return ok;
+  }
+  inline char base(uint64_t i) const { return "ACGT"[(pac[i >> 2] >> (6 - 2 * (i & 3))) & 3]; }
+  // Forward-strand window [start, start+len); all-zero bytes when it would leave
+  // the genome (such windows can never match).  Arithmetic is modulo 2^64 exactly
+  // like the reference's (Schema.cpp:4998-5050).
+  void window_fwd(uint64_t start, uint64_t len, char* out) const {
+    if (start >= N || start + len > N) { memset(out, 0, len); return; }
+    for (uint64_t i = 0; i < len; ++i) out[i] = base(start + i);
+  }
+  // Reverse-complement window: out[i] = complement(G[N-1-rc_start-i]) (Schema.cpp:5061-5115).
+  void window_rc(uint64_t rc_start, uint64_t len, char* out) const {
+    uint64_t last = N - rc_start - 1;
+    if (last < len - 1 || (last >> 2) >= pac.size()) { memset(out, 0, len); return; }
+    for (uint64_t i = 0; i < len; ++i) out[i] = "TGCA"[(pac[(last - i) >> 2] >> (6 - 2 * ((last - i) & 3))) & 3];
+  }
+  // Double-strand coordinate: [0,N) forward strand, [N,2N) reverse complement.
+  void window(uint64_t site, uint64_t len, char* out) const {
+    if (site < N) window_fwd(site, len, out); else window_rc(site - N, len, out);
+  }
+};
+
+inline int mismatch_penalty(const Scoring& sc, int q) {
+  double phred = q - sc.q_base;
+  if (phred > 40) phred = 40;
+  phred = phred / 40;
+  int p = phred * (sc.mp_max - sc.mp_min);
+  return p + sc.mp_min;
+}
+
+// Bowtie2-like MAPQ from (second-best edit-distance gap, alignment score).
+inline int mapq_from(unsigned second_best_diff, unsigned k, int score, const Scoring& sc) {
+  int worst = std::max(sc.gap_open + sc.gap_ext, sc.mp_max);
+  int score_min = (int)((unsigned)(-worst) * k);
+  int range = -score_min;
+  int sdiff = score - score_min;
+  if (sdiff < 0) { fprintf(stderr, "error best_score: %d, scoreMax: %d\n", score, score_min); sdiff = 0; }
+  int ediff = (int)second_best_diff;
+  if (second_best_diff > k) ediff = (int)(k + 1);
+  double rank = (double)sdiff / (double)range;
+  if ((unsigned)ediff > k) {
+    static const double th[6] = {0.8, 0.7, 0.6, 0.5, 0.4, 0.3};
+    static const int q[6] = {42, 40, 24, 23, 8, 3};
+    for (int i = 0; i < 6; ++i) if (rank >= th[i]) return q[i];
+    return 0;
+  }
+  double re = (double)ediff / (double)k;
+  const bool perfect = score == 0;
+  // rows: error-gap rank >= t ; columns: q(perfect score), then (rank threshold, q) pairs, then fallback
+  struct Row { double t; int q0; double r1; int q1; double r2; int q2; int q3; };
+  static const Row rows[9] = {
+    {0.9, 39, -1, 33, -1, 33, 33}, {0.8, 38, -1, 27, -1, 27, 27}, {0.7, 37, -1, 26, -1, 26, 26},
+    {0.6, 36, -1, 22, -1, 22, 22}, {0.5, 35, 0.84, 25, 0.68, 16, 5}, {0.4, 34, 0.84, 21, 0.68, 14, 4},
+    {0.3, 32, 0.88, 18, 0.67, 15, 3}, {0.2, 31, 0.88, 17, 0.67, 11, 0}, {0.1, 30, 0.88, 12, 0.67, 7, 0}};
+  for (const Row& r : rows) {
+    if (re >= r.t) {
+      if (perfect) return r.q0;
+      if (r.r1 < 0 || rank >= r.r1) return r.q1;
+      if (rank >= r.r2) return r.q2;
+      return r.q3;
+    }
+  }
+  if (ediff == 0) return rank >= 0.67 ? 1 : 0;
+  return rank >= 0.67 ? 6 : 2;
+}
+
+struct Refined {
+  int start_site = 0;        // first window position used by the alignment
+  uint64_t end_site = 0;     // last window position used
+  unsigned err = 0;          // NM
+  int score = 0;
+  std::string cigar;
+};
+
+namespace detail {
+inline int nt4(char c) {
+  switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; }
+}
+// substitution score of read base t against reference base q at a read position
+// whose scaled quality is `phred` in [.,1]; read T on reference C is a match.
+inline int sub_score(int t, int q, double phred, const Scoring& sc) {
+  if (t == 4 || q == 4) return -sc.n_pen;
+  if (t == q || (t == 3 && q == 1)) return 0;
+  return -sc.mp_min - (int)((int8_t)(sc.mp_max - sc.mp_min) * phred);
+}
+}  // namespace detail
+
+// Banded (2k+1) semi-global affine-gap alignment of the read against the
+// window with traceback.  ops: (len<<4)|op with op 0=M, 1=D (reference only),
+// 2=I (read only), in read order.
+inline void banded_affine_align(const char* win, int wlen, const char* read, int rlen, int k,
+                                const char* qual, const Scoring& sc,
+                                int& score, int& qb, int& qe, std::vector<uint32_t>& ops) {
+  const int NEG = -0x40000000;
+  const int band = 2 * k + 1, goe = sc.gap_open + sc.gap_ext, ge = sc.gap_ext;
+  std::vector<int32_t> H(wlen + 2, NEG), E(wlen + 2, NEG);
+  std::vector<uint8_t> dir((size_t)band * rlen);
+  for (int j = 0; j < band; ++j) { H[j] = 0; E[j] = -goe; }
+  int beg = 0, end = 0;
+  for (int i = 0; i < rlen; ++i) {
+    int t = detail::nt4(read[i]);
+    double phred = qual[i] - sc.q_base;
+    if (phred > 40) phred = 40;
+    phred = phred / 40;
+    beg = i; end = i + band;
+    int32_t f = NEG, left = NEG;
+    uint8_t* d_row = &dir[(size_t)i * band];
+    for (int j = beg; j < end; ++j) {
+      int32_t m = H[j], e = E[j];
+      H[j] = left;
+      m += detail::sub_score(t, detail::nt4(win[j]), phred, sc);
+      uint8_t d = m >= e ? 0 : 1;
+      int32_t h = m >= e ? m : e;
+      d = h >= f ? d : 2;
+      h = h >= f ? h : f;
+      left = h;
+      int32_t open = m - goe;
+      e -= ge;
+      if (e > open) d |= 1 << 2; else e = open;
+      E[j] = e;
+      f -= ge;
+      if (f > open) d |= 2 << 4; else f = open;
+      d_row[j - beg] = d;
+    }
+    H[end] = left; E[end] = NEG;
+  }
+  int best = rlen + k;
+  score = H[best];
+  for (int j = end; j > beg; --j) if (H[j] > score) { score = H[j]; best = j; }
+  qe = best - 1;
+  ops.clear();
+  auto push = [&](uint32_t op, uint32_t len) {
+    if (ops.empty() || (ops.back() & 0xf) != op) ops.push_back(len << 4 | op); else ops.back() += len << 4;
+  };
+  int i = rlen - 1, j = best - 1, state = 0;
+  while (i >= 0 && j >= 0) {
+    state = dir[(size_t)i * band + (j - i)] >> (state << 1) & 3;
+    if (state == 0) { push(0, 1); --i; --j; }
+    else if (state == 1) { push(2, 1); --i; }
+    else { push(1, 1); --j; }
+  }
+  if (i >= 0) push(2, i + 1);
+  std::reverse(ops.begin(), ops.end());
+  qb = j + 1;
+}
+
+// CIGAR / NM / score / start / end of the best hit, given the verifier's
+// (end_site, err).  `qual` is the quality string in FASTQ order; mate 2 of a
+// pair is aligned as its reverse complement, so its qualities are reversed
+// (reverse_quality) for the DP and restored.
+inline void refine_alignment(const char* win, int wlen, const char* read, int rlen, int k,
+                             int end_site, unsigned err, bool forward, const char* qual_in,
+                             bool reverse_quality, const Scoring& sc, Refined& out) {
+  out.cigar.clear();
+  if (err == 0) {
+    out.score = 0; out.start_site = end_site - rlen + 1; out.end_site = end_site; out.err = 0;
+    out.cigar = std::to_string(rlen) + "M";
+    return;
+  }
+  std::string qual(qual_in, rlen);
+  if (reverse_quality) std::reverse(qual.begin(), qual.end());
+  {  // ungapped attempt: exactly `err` mismatches on the diagonal ending at end_site
+    int start = end_site - rlen + 1, mism = 0, score = 0;
+    bool ok = start >= 0;
+    for (int i = 0; ok && i < rlen; ++i) {
+      char t = read[i], p = win[i + start];
+      if (t != p && !(t == 'T' && p == 'C')) {
+        if (++mism > (int)err) { ok = false; break; }
+        if (t == 'N' || p == 'N') score -= sc.n_pen; else score -= mismatch_penalty(sc, qual[i]);
+      }
+    }
+    if (ok && mism == (int)err) {
+      out.score = score; out.start_site = start; out.end_site = end_site; out.err = err;
+      out.cigar = std::to_string(rlen) + "M";
+      return;
+    }
+  }
+  int score, qb, qe; std::vector<uint32_t> ops;
+  banded_affine_align(win, wlen, read, rlen, k, qual.data(), sc, score, qb, qe, ops);
+  const int n = (int)ops.size();
+  // leading / trailing insertions become matches (the read is end-to-end)
+  int i = 0, ins = 0;
+  for (; i < n && (ops[i] & 0xf) == 2; ++i) ins += ops[i] >> 4;
+  if (i != 0) {
+    uint32_t op = ops[i] & 0xf, len = ops[i] >> 4;   // (i == n cannot happen for a non-empty read with a match)
+    if (op == 0) len += ins; else { op = 0; len = ins; --i; }
+    ops[i] = len << 4 | op;
+    qb -= ins;
+  }
+  const int cb = i;
+  ins = 0;
+  for (i = n - 1; i >= cb && (ops[i] & 0xf) == 2; --i) ins += ops[i] >> 4;
+  if (i != n - 1) {
+    uint32_t op = ops[i] & 0xf, len = ops[i] >> 4;
+    if (op == 0) len += ins; else { op = 0; len = ins; ++i; }
+    ops[i] = len << 4 | op;
+    qe += ins;
+  }
+  const int ce = i;
+  unsigned nm = 0;
+  char buf[32];
+  auto mismatch = [&](int wi, int ri) { return win[wi] != read[ri] && !(win[wi] == 'C' && read[ri] == 'T'); };
+  if (forward) {
+    int wi = qb, ri = 0;
+    for (i = cb; i <= ce; ++i) {
+      uint32_t op = ops[i] & 0xf, len = ops[i] >> 4;
+      snprintf(buf, sizeof buf, "%u%c", len, "MDISH"[op]); out.cigar += buf;
+      if (op == 0) { for (uint32_t x = 0; x < len; ++x) nm += mismatch(wi++, ri++); }
+      else if (op == 1) { wi += len; nm += len; }
+      else { ri += len; nm += len; }
+    }
+  } else {
+    int wi = qe, ri = rlen - 1;
+    for (i = ce; i >= cb; --i) {
+      uint32_t op = ops[i] & 0xf, len = ops[i] >> 4;
+      snprintf(buf, sizeof buf, "%u%c", len, "MDISH"[op]); out.cigar += buf;
+      if (op == 0) { for (uint32_t x = 0; x < len; ++x) nm += mismatch(wi--, ri--); }
+      else if (op == 1) { wi -= len; nm += len; }
+      else { ri -= len; nm += len; }
+    }
+  }
+  out.score = score; out.start_site = qb; out.end_site = qe; out.err = nm;
+}
+
+// Double-strand window coordinates -> (flag 0/16, chromosome, 1-based POS).
+struct Placed { int flag; size_t chrom; uint64_t pos; bool off_chrom; };
+inline Placed place(const ChromTable& ct, uint64_t site, uint64_t start_site, uint64_t end_site) {
+  Placed p;
+  uint64_t loc = site;
+  if (loc >= ct.N) { loc = ct.N * 2 - (loc + end_site) - 1; p.flag = 16; }
+  else { loc = loc + start_site; p.flag = 0; }
+  p.chrom = ct.find(loc);
+  size_t c = p.chrom < ct.name.size() ? p.chrom : ct.name.size() - 1;  // reference reads past the table here
+  p.chrom = c;
+  p.pos = loc + 1 - ct.start[c];
+  p.off_chrom = p.pos + end_site - start_site > ct.len[c];
+  return p;
+}
+
+}  // namespace bmbs

@@ -1,0 +1,37 @@
+// SAM text records in the reference's exact layout (Schema.cpp:12596-12812 single
+// end; :9453-9700, :10922-11170 paired end) and the --mapstats block
+// (Bitmapper_main.cpp:266-308).
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include "postprocess.hpp"
+
+namespace bmbs {
+
+inline void sam_header(std::string& out, const ChromTable& ct, const std::string& cmdline) {
+  out += "@HD\tVN:1.4\tSO:unsorted\n";
+  for (size_t i = 0; i < ct.name.size(); ++i) out += "@SQ\tSN:" + ct.name[i] + "\tLN:" + std::to_string(ct.len[i]) + "\n";
+  out += "@PG\tID:BitMapperBS\tVN:1.0.2.3\tCL:" + cmdline + "\n";
+}
+
+// Single-end record.  `seq`/`qual` as in the FASTQ; reverse-strand hits print
+// the reverse complement and the reversed qualities.
+inline void sam_record_se(std::string& out, const std::string& name, const std::string& seq, const std::string& qual,
+                          const ChromTable& ct, const Placed& p, int mapq, const std::string& cigar, unsigned nm,
+                          const std::string& rseq) {
+  out += name; out += '\t';
+  out += std::to_string(p.flag); out += '\t';
+  out += ct.name[p.chrom]; out += '\t';
+  out += std::to_string(p.pos); out += '\t';
+  out += std::to_string(mapq); out += '\t';
+  out += cigar; out += "\t*\t0\t0\t";
+  if (p.flag == 0) { out += seq; out += '\t'; out += qual; }
+  else { out += rseq; out += '\t'; out.append(qual.rbegin(), qual.rend()); }
+  out += "\tNM:i:"; out += std::to_string(nm); out += '\n';
+}
+
+struct MapStats { uint64_t reads = 0, unique = 0, ambiguous = 0, bases = 0, err_bases = 0; };
+
+}  // namespace bmbs

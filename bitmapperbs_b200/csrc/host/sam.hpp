@@ -32,6 +32,27 @@ inline void sam_record_se(std::string& out, const std::string& name, const std::
   out += "\tNM:i:"; out += std::to_string(nm); out += '\n';
 }
 
+// Paired-end record (Schema.cpp:9453-9700 mate 1, :10922-11170 mate 2).  `seq` is
+// what was aligned, `rseq` its reverse complement, `qual` the FASTQ-order
+// qualities; for mate 2 `seq` is the reverse complement of the FASTQ record.
+// strand_flag: 0 = aligned sequence lies on the forward strand, 16 = reverse.
+inline void sam_record_pe(std::string& out, bool first, const std::string& name, const std::string& seq, const std::string& rseq,
+                          const std::string& qual, const ChromTable& ct, int strand_flag, size_t chrom, uint64_t pos, int mapq,
+                          const std::string& cigar, uint64_t mate_pos, long long tlen, unsigned nm) {
+  const int flag = first ? (strand_flag == 0 ? 99 : 83) : (strand_flag == 0 ? 147 : 163);
+  out += name; out += '\t'; out += std::to_string(flag); out += '\t'; out += ct.name[chrom]; out += '\t';
+  out += std::to_string(pos); out += '\t'; out += std::to_string(mapq); out += '\t'; out += cigar; out += "\t=\t";
+  out += std::to_string(mate_pos); out += '\t';
+  if (mate_pos < pos || (mate_pos == pos && !first)) out += '-';
+  out += std::to_string((int)tlen); out += '\t';
+  if (first) {
+    if (flag & 32) { out += seq; out += '\t'; out += qual; } else { out += rseq; out += '\t'; out.append(qual.rbegin(), qual.rend()); }
+  } else {
+    if (flag & 16) { out += seq; out += '\t'; out.append(qual.rbegin(), qual.rend()); } else { out += rseq; out += '\t'; out += qual; }
+  }
+  out += "\tNM:i:"; out += std::to_string(nm); out += '\n';
+}
+
 struct MapStats { uint64_t reads = 0, unique = 0, ambiguous = 0, bases = 0, err_bases = 0; };
 
 }  // namespace bmbs

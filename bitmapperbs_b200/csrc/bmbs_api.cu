@@ -1,0 +1,458 @@
+// libbmbs_gpu.so: C ABI (include/bmbs.h) over the kernels in bmbs_kernels.cuh.
+// Index files are read exactly as the reference writes them (bwt.cpp:1704-1835, :2080-2084; Index.cpp:134-159,
+// :827-828) and re-laid out for the GPU at load time; nothing is written back.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "bmbs_kernels.cuh"
+
+using namespace bmbs;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& m) { g_err = m; return code; }
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(BMBS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+template <class T> bool read_vec(FILE* f, std::vector<T>& v, size_t n) { v.resize(n); return n == 0 || fread(v.data(), sizeof(T), n, f) == n; }
+
+struct HostIndex {
+  u64 sa_length = 0, shapline = 0, nacgt[5] = {0, 0, 0, 0, 0}, N = 0;
+  std::vector<u64> bwt, high_occ, sa_flag;
+  std::vector<u32> hash_hi, ssa;
+  std::vector<uint8_t> hash_lo, pac;
+};
+
+int load_files(const std::string& prefix, HostIndex& h) {
+  FILE* f = fopen(prefix.c_str(), "rb");
+  if (!f) return fail(BMBS_ERR_IO, "cannot open " + prefix);
+  u64 nc = 0; bool ok = fread(&nc, 8, 1, f) == 1;
+  for (u64 i = 0; ok && i < nc; ++i) { u64 l = 0, cl = 0; ok = fread(&l, 8, 1, f) == 1 && fseek(f, (long)l, SEEK_CUR) == 0 && fread(&cl, 8, 1, f) == 1; }
+  ok = ok && fread(&h.N, 8, 1, f) == 1; fclose(f);
+  if (!ok) return fail(BMBS_ERR_IO, "short read in " + prefix);
+  f = fopen((prefix + ".bs.pac").c_str(), "rb");
+  if (!f) return fail(BMBS_ERR_IO, "cannot open " + prefix + ".bs.pac");
+  u64 n = 0; ok = fread(&n, 8, 1, f) == 1 && read_vec(f, h.pac, n); fclose(f);
+  if (!ok || n < (h.N + 3) / 4) return fail(BMBS_ERR_IO, "short read in " + prefix + ".bs.pac");
+  const std::string p = prefix + ".bs.index";
+  f = fopen(p.c_str(), "rb");
+  if (!f) return fail(BMBS_ERR_IO, "cannot open " + p);
+  ok = fread(&h.sa_length, 8, 1, f) == 1 && fread(&h.shapline, 8, 1, f) == 1 && fread(h.nacgt, 8, 5, f) == 5; fclose(f);
+  if (!ok) return fail(BMBS_ERR_IO, "short read in " + p);
+  f = fopen((p + ".bwt").c_str(), "rb");
+  if (!f) return fail(BMBS_ERR_IO, "cannot open " + p + ".bwt");
+  ok = fread(&n, 8, 1, f) == 1 && read_vec(f, h.bwt, n);
+  ok = ok && fread(&n, 8, 1, f) == 1 && read_vec(f, h.hash_hi, n) && read_vec(f, h.hash_lo, n); fclose(f);
+  if (!ok) return fail(BMBS_ERR_IO, "short read in " + p + ".bwt");
+  f = fopen((p + ".sa").c_str(), "rb");
+  if (!f) return fail(BMBS_ERR_IO, "cannot open " + p + ".sa");
+  ok = fread(&n, 8, 1, f) == 1 && read_vec(f, h.ssa, n);
+  ok = ok && fread(&n, 8, 1, f) == 1 && read_vec(f, h.sa_flag, n); fclose(f);
+  if (!ok) return fail(BMBS_ERR_IO, "short read in " + p + ".sa");
+  f = fopen((p + ".occ").c_str(), "rb");
+  if (!f) return fail(BMBS_ERR_IO, "cannot open " + p + ".occ");
+  ok = fread(&n, 8, 1, f) == 1 && read_vec(f, h.high_occ, n); fclose(f);
+  if (!ok) return fail(BMBS_ERR_IO, "short read in " + p + ".occ");
+  if (h.sa_length != 2 * h.N + 1) return fail(BMBS_ERR_IO, "index header does not match the genome length");
+  return BMBS_OK;
+}
+
+struct DeviceCopy {
+  int dev = 0; DevIndex view{}; size_t bytes = 0;
+  void *occ = nullptr, *flag = nullptr, *hash = nullptr, *ssa = nullptr, *planes = nullptr;
+};
+
+}  // namespace
+
+struct bmbs_index {
+  u64 N = 0;
+  std::vector<DeviceCopy> copies;
+  const DeviceCopy* on(int dev) const { for (auto& c : copies) if (c.dev == dev) return &c; return nullptr; }
+};
+
+extern "C" const char* bmbs_last_error(void) { return g_err.c_str(); }
+extern "C" void bmbs_params_default(bmbs_params* p) { p->e_rate = 0.08; p->seed_len = 30; p->min_ins = 0; p->max_ins = 500; p->sensitive = 0; }
+extern "C" uint64_t bmbs_index_genome_length(const bmbs_index* idx) { return idx ? idx->N : 0; }
+extern "C" uint64_t bmbs_index_device_bytes(const bmbs_index* idx) { return idx && !idx->copies.empty() ? idx->copies[0].bytes : 0; }
+
+extern "C" void bmbs_index_free(bmbs_index* idx) {
+  if (!idx) return;
+  for (auto& c : idx->copies) { cudaSetDevice(c.dev); cudaFree(c.occ); cudaFree(c.flag); cudaFree(c.hash); cudaFree(c.ssa); cudaFree(c.planes); }
+  delete idx;
+}
+
+extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int n_dev, bmbs_index** out) {
+  if (!index_prefix || !out) return fail(BMBS_ERR_ARG, "null argument");
+  HostIndex h;
+  int rc = load_files(index_prefix, h);
+  if (rc) return rc;
+  const u64 n = 2 * h.N;                       // text length = BWT symbols
+  // ---- occ blocks: fold the 65536-row table and the 16-bit counters into absolute counts
+  const u64 nblk = (n >> 6) + 2;
+  std::vector<u64> occ(nblk * 4, 0);
+  h.bwt.resize(h.bwt.size() + 16, 0);
+  for (u64 b = 0; b < nblk; ++b) {
+    const u64 sb = (b >> 1) * 5, sub = b & 1, w = sb + 1 + 2 * sub, hi_i = ((b << 6) >> 16) * 2;
+    if (w + 1 >= h.bwt.size() || hi_i + 1 >= h.high_occ.size()) break;
+    const u64 hdr = h.bwt[sb];
+    occ[b * 4 + 0] = h.bwt[w];
+    occ[b * 4 + 1] = h.bwt[w + 1];
+    occ[b * 4 + 2] = h.high_occ[hi_i] + ((hdr >> (48 - 32 * sub)) & 0xFFFF);
+    occ[b * 4 + 3] = h.high_occ[hi_i + 1] + ((hdr >> (32 - 32 * sub)) & 0xFFFF);
+  }
+  std::vector<u64>().swap(h.bwt);
+  // ---- flag blocks: 64 rows each, with the rank of the block start
+  const u64 nfb = (h.sa_length >> 6) + 2;
+  std::vector<u64> flag(nfb * 2, 0);
+  h.sa_flag.resize(h.sa_flag.size() + 16, 0);
+  for (u64 b = 0; b < nfb; ++b) {
+    const u64 g = (b >> 2) * 5, in = b & 3;
+    if (g + 1 + in >= h.sa_flag.size()) break;
+    u64 rank = h.sa_flag[g];
+    for (u64 t = 0; t < in; ++t) rank += __builtin_popcountll(h.sa_flag[g + 1 + t]);
+    flag[b * 2] = h.sa_flag[g + 1 + in];
+    flag[b * 2 + 1] = rank;
+  }
+  // the flag file's last word is uninitialised in reference-built indexes (reads past its allocation,
+  // bwt.cpp:1188-1192 vs :1657-1664); it lies beyond the last row and is masked here
+  {
+    const u64 last_row = h.sa_length - 1, b = last_row >> 6, used = (last_row & 63) + 1;
+    if (used < 64) flag[b * 2] &= ~0ull << (64 - used);
+    for (u64 bb = b + 1; bb < nfb; ++bb) flag[bb * 2] = 0;
+  }
+  std::vector<u64>().swap(h.sa_flag);
+  // ---- 16-mer table: one u64 per entry
+  const size_t nh = h.hash_hi.size();
+  std::vector<u64> hash(nh + 2, 0);
+  for (size_t i = 0; i < nh; ++i) hash[i] = ((u64)(h.hash_hi[i] & 0x0FFFFFFFu) << 8) | h.hash_lo[i] | ((u64)(h.hash_hi[i] >> 28) << 60);
+  std::vector<u32>().swap(h.hash_hi); std::vector<uint8_t>().swap(h.hash_lo);
+  // ---- bit-planes of G ++ revcomp(G)
+  const u64 npw = (n + 31) / 32 + 64;
+  std::vector<uint2> planes(npw, make_uint2(0, 0));
+  for (u64 i = 0; i < h.N; ++i) {
+    const u32 c = (h.pac[i >> 2] >> (6 - 2 * (i & 3))) & 3;
+    planes[i >> 5].x |= (c & 1u) << (i & 31); planes[i >> 5].y |= (c >> 1) << (i & 31);
+    const u64 j = n - 1 - i; const u32 rc = 3 - c;
+    planes[j >> 5].x |= (rc & 1u) << (j & 31); planes[j >> 5].y |= (rc >> 1) << (j & 31);
+  }
+  std::vector<uint8_t>().swap(h.pac);
+
+  bmbs_index* idx = new bmbs_index();
+  idx->N = h.N;
+  int dev0 = 0;
+  if (!devices || n_dev <= 0) { devices = &dev0; n_dev = 1; }
+  for (int d = 0; d < n_dev; ++d) {
+    DeviceCopy c; c.dev = devices[d];
+    auto up = [&](void** p, const void* src, size_t bytes) -> cudaError_t {
+      cudaError_t e = cudaMalloc(p, bytes); if (e != cudaSuccess) return e;
+      c.bytes += bytes; return cudaMemcpy(*p, src, bytes, cudaMemcpyHostToDevice);
+    };
+    cudaError_t e = cudaSetDevice(c.dev);
+    if (e == cudaSuccess) e = up(&c.occ, occ.data(), occ.size() * 8);
+    if (e == cudaSuccess) e = up(&c.flag, flag.data(), flag.size() * 8);
+    if (e == cudaSuccess) e = up(&c.hash, hash.data(), hash.size() * 8);
+    if (e == cudaSuccess) e = up(&c.ssa, h.ssa.data(), h.ssa.size() * 4);
+    if (e == cudaSuccess) e = up(&c.planes, planes.data(), planes.size() * 8);
+    idx->copies.push_back(c);
+    if (e != cudaSuccess) { std::string m = std::string("index upload: ") + cudaGetErrorString(e); bmbs_index_free(idx); return fail(BMBS_ERR_CUDA, m); }
+    DevIndex& v = idx->copies.back().view;
+    v.occ = (const ulonglong2*)c.occ; v.flag = (const ulonglong2*)c.flag; v.hash = (const u64*)c.hash;
+    v.ssa = (const u32*)c.ssa; v.planes = (const uint2*)c.planes;
+    v.C[0] = h.nacgt[0]; v.C[1] = h.nacgt[1]; v.C[2] = h.nacgt[2];
+    v.shapline = h.shapline; v.n_rows = h.sa_length; v.N = h.N;
+  }
+  *out = idx;
+  return BMBS_OK;
+}
+
+// ================================================================================================ batch
+struct bmbs_batch {
+  bmbs_index* idx = nullptr; const DeviceCopy* copy = nullptr; int dev = 0;
+  size_t max_reads = 0, max_bases = 0, cand_cap = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<void*> allocs;
+  BatchView v{};
+  char* d_ascii = nullptr; u64* d_offsets = nullptr;
+  u64* d_tile = nullptr;
+  u64* h_small = nullptr;        // pinned: totals[2], status, counters[8]
+  cudaEvent_t ev[8] = {nullptr};
+  int n_reads = 0, pe = 0, max_len = 0, launches = 0, sm_count = 148;
+  bool ran = false;
+};
+
+namespace {
+template <class T> cudaError_t dalloc(bmbs_batch* b, T** p, size_t n) {
+  void* q = nullptr; cudaError_t e = cudaMalloc(&q, n * sizeof(T) + 256);
+  if (e == cudaSuccess) { b->allocs.push_back(q); *p = (T*)q; }
+  return e;
+}
+}  // namespace
+
+extern "C" void bmbs_batch_free(bmbs_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->dev);
+  for (void* p : b->allocs) cudaFree(p);
+  if (b->h_small) cudaFreeHost(b->h_small);
+  for (auto& e : b->ev) if (e) cudaEventDestroy(e);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+extern "C" int bmbs_batch_create(bmbs_index* idx, int dev, size_t max_reads, size_t max_bases, size_t cand_cap, bmbs_batch** out) {
+  if (!idx || !out || max_reads == 0) return fail(BMBS_ERR_ARG, "bad argument");
+  const DeviceCopy* c = idx->on(dev);
+  if (!c) return fail(BMBS_ERR_ARG, "index was not loaded on device " + std::to_string(dev));
+  if (cand_cap >= 0xFFFFFFF0ull || max_reads >= 0x7FFFFFF0ull) return fail(BMBS_ERR_ARG, "capacity too large");
+  CU(cudaSetDevice(dev));
+  bmbs_batch* b = new bmbs_batch();
+  b->idx = idx; b->copy = c; b->dev = dev; b->max_reads = max_reads; b->max_bases = max_bases; b->cand_cap = cand_cap;
+  cudaDeviceProp prop; cudaGetDeviceProperties(&prop, dev); b->sm_count = prop.multiProcessorCount;
+  BatchView& v = b->v;
+  const size_t R = max_reads + 2, S = cand_cap + 64;
+  cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+  auto A = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+  A(dalloc(b, &b->d_ascii, max_bases + 64)); A(dalloc(b, &b->d_offsets, R));
+  A(dalloc(b, &v.codes, max_bases / 8 + R + 64)); A(dalloc(b, &v.len, R)); A(dalloc(b, &v.first_c, R)); A(dalloc(b, &v.kk, R));
+  A(dalloc(b, &v.state, R)); A(dalloc(b, &v.flags, R)); A(dalloc(b, &v.one_mm, R)); A(dalloc(b, &v.site0, R));
+  A(dalloc(b, &v.ntask, R)); A(dalloc(b, &v.ncand, R)); A(dalloc(b, &v.coff, R)); A(dalloc(b, &v.tasks, (size_t)MAX_TASKS * max_reads));
+  A(dalloc(b, &v.slot_row, S)); A(dalloc(b, &v.slot_adj, S)); A(dalloc(b, &v.slot_read, S)); A(dalloc(b, &v.cand, S)); A(dalloc(b, &v.vcnt, S));
+  A(dalloc(b, &v.nv, R)); A(dalloc(b, &v.voff, R)); A(dalloc(b, &v.keep, S));
+  A(dalloc(b, &v.work_site, S)); A(dalloc(b, &v.work_vote, S)); A(dalloc(b, &v.work_read, S)); A(dalloc(b, &v.out_cand, S));
+  A(dalloc(b, &v.out_res, R)); A(dalloc(b, &v.big_list, R)); A(dalloc(b, &v.big_count, 4));
+  v.scratch_cap = 2 * S + 65536;
+  A(dalloc(b, &v.scratch, (size_t)v.scratch_cap)); A(dalloc(b, &v.scratch_used, 4));
+  A(dalloc(b, &v.counters, 16)); A(dalloc(b, &v.totals, 4)); A(dalloc(b, &v.status, 4));
+  A(dalloc(b, &b->d_tile, R / SCAN_TILE + 8));
+  A(cudaMallocHost((void**)&b->h_small, 32 * sizeof(u64)));
+  for (auto& evt : b->ev) A(cudaEventCreate(&evt));
+  if (e != cudaSuccess) { std::string m = std::string("batch allocation: ") + cudaGetErrorString(e); bmbs_batch_free(b); return fail(BMBS_ERR_CUDA, m); }
+  v.slot_cap = cand_cap;
+  // verify_windows may need more than 48 KB of dynamic shared memory for long reads
+  cudaFuncSetAttribute(verify_windows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  *out = b;
+  return BMBS_OK;
+}
+
+extern "C" int bmbs_batch_upload(bmbs_batch* b, const char* seqs, const uint64_t* offsets, int n_reads, int pe) {
+  if (!b || !seqs || !offsets || n_reads < 0) return fail(BMBS_ERR_ARG, "bad argument");
+  if ((size_t)n_reads > b->max_reads) return fail(BMBS_ERR_ARG, "batch has more reads than bmbs_batch_create allowed");
+  if (pe && (n_reads & 1)) return fail(BMBS_ERR_ARG, "paired batch needs an even number of reads");
+  const u64 bases = offsets[n_reads] - offsets[0];
+  if (offsets[0] != 0) return fail(BMBS_ERR_ARG, "offsets[0] must be 0");
+  if (bases > b->max_bases) return fail(BMBS_ERR_ARG, "batch has more bases than bmbs_batch_create allowed");
+  int max_len = 0;
+  for (int i = 0; i < n_reads; ++i) { const u64 l = offsets[i + 1] - offsets[i]; if (l > 1000) return fail(BMBS_ERR_ARG, "read longer than 1000 bases (SEQ_MAX_LENGTH, Auxiliary.h:15)"); if ((int)l > max_len) max_len = (int)l; }
+  CU(cudaSetDevice(b->dev));
+  CU(cudaMemcpyAsync(b->d_ascii, seqs, bases, cudaMemcpyHostToDevice, b->stream));
+  CU(cudaMemcpyAsync(b->d_offsets, offsets, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, b->stream));
+  b->n_reads = n_reads; b->pe = pe; b->max_len = max_len; b->ran = false;
+  return BMBS_OK;
+}
+
+namespace {
+int run_scan(bmbs_batch* b, const u32* in, u32 n, u32* out, u64* total, u64 cap, u32 cap_bit) {
+  const u32 tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  scan_tiles<<<tiles, SCAN_TILE, 0, b->stream>>>(in, n, b->d_tile, b->v.status);
+  scan_tile_sums<<<1, 1024, 0, b->stream>>>(b->d_tile, tiles, total, cap, b->v.status, cap_bit);
+  scan_apply<<<tiles, SCAN_TILE, 0, b->stream>>>(in, n, b->d_tile, out);
+  b->launches += 3;
+  return 0;
+}
+}  // namespace
+
+extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
+  if (!b || !prm) return fail(BMBS_ERR_ARG, "bad argument");
+  if (prm->sensitive) return fail(BMBS_ERR_ARG, "--sensitive pairing is not implemented on the GPU path yet");
+  CU(cudaSetDevice(b->dev));
+  BatchView& v = b->v;
+  const int n = b->n_reads;
+  v.ascii = b->d_ascii; v.offsets = b->d_offsets; v.n_reads = n; v.pe = b->pe;
+  v.e_rate = prm->e_rate; v.seed_len = (u32)prm->seed_len; v.dmax_base = prm->max_ins; v.dmin_base = prm->min_ins;
+  b->launches = 0;
+  cudaStream_t s = b->stream;
+  const DevIndex ix = b->copy->view;
+  CU(cudaMemsetAsync(v.counters, 0, 16 * 8, s)); CU(cudaMemsetAsync(v.totals, 0, 4 * 8, s)); CU(cudaMemsetAsync(v.status, 0, 16, s));
+  CU(cudaMemsetAsync(v.big_count, 0, 16, s)); CU(cudaMemsetAsync(v.scratch_used, 0, 16, s));
+  CU(cudaEventRecord(b->ev[0], s));
+  if (n > 0) {
+    pack_reads<<<(n + 3) / 4, 128, 0, s>>>(v); ++b->launches;
+    CU(cudaEventRecord(b->ev[1], s));
+    seed_reads<<<(n + 127) / 128, 128, 0, s>>>(ix, v); ++b->launches;
+    CU(cudaEventRecord(b->ev[2], s));
+    run_scan(b, v.ncand, (u32)n, v.coff, v.totals, v.slot_cap, 2u);
+    expand_tasks<<<(n + 127) / 128, 128, 0, s>>>(v); ++b->launches;
+    locate_rows<<<b->sm_count * 8, 256, 0, s>>>(ix, v); ++b->launches;
+    CU(cudaEventRecord(b->ev[3], s));
+    votes_small<<<(n + 3) / 4, 128, 0, s>>>(v); ++b->launches;
+    votes_big<<<b->sm_count * 4, 256, 0, s>>>(v); ++b->launches;
+    CU(cudaEventRecord(b->ev[4], s));
+    if (b->pe) { filter_pairs_kernel<<<(n / 2 + 127) / 128, 128, 0, s>>>(v); ++b->launches; }
+    CU(cudaEventRecord(b->ev[5], s));
+    run_scan(b, v.nv, (u32)n, v.voff, v.totals + 1, v.slot_cap, 4u);
+    gather_work<<<b->sm_count * 8, 256, 0, s>>>(v); ++b->launches;
+    const int nch2 = (b->max_len + 31) / 32 + 2;
+    int bd = 128;
+    while (bd > 32 && (size_t)5 * nch2 * bd * 8 > 96 * 1024) bd >>= 1;
+    const size_t smem = (size_t)5 * nch2 * bd * 8;
+    int per_sm = (int)((200 * 1024) / (smem + 1024)); if (per_sm > 12) per_sm = 12; if (per_sm < 1) per_sm = 1;
+    verify_windows<<<b->sm_count * per_sm, bd, smem, s>>>(ix, v, nch2); ++b->launches;
+    CU(cudaEventRecord(b->ev[6], s));
+    finalize_reads<<<(n + 255) / 256, 256, 0, s>>>(v); ++b->launches;
+  } else {
+    for (int i = 1; i <= 6; ++i) CU(cudaEventRecord(b->ev[i], s));
+  }
+  CU(cudaEventRecord(b->ev[7], s));
+  CU(cudaMemcpyAsync(b->h_small, v.totals, 2 * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(b->h_small + 2, v.status, 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(b->h_small + 4, v.counters, 8 * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaGetLastError());
+  b->ran = true;
+  return BMBS_OK;
+}
+
+extern "C" int bmbs_batch_sync(bmbs_batch* b) {
+  if (!b) return fail(BMBS_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(b->dev));
+  CU(cudaStreamSynchronize(b->stream));
+  return BMBS_OK;
+}
+
+namespace {
+int check_status(bmbs_batch* b, size_t* used) {
+  const u32 st = *(const u32*)(b->h_small + 2);
+  if (used) *used = (size_t)b->h_small[1];
+  if (st & 1u) return fail(BMBS_ERR_CAPACITY, "a read produced more seed tasks than the per-read table holds");
+  if (st & 2u) { if (used) *used = (size_t)b->h_small[0]; return fail(BMBS_ERR_CAPACITY, "candidate slots exceed the batch capacity (" + std::to_string(b->h_small[0]) + " needed): create the batch with a larger cand_cap or send fewer reads"); }
+  if (st & 4u) return fail(BMBS_ERR_CAPACITY, "verification work exceeds the batch capacity");
+  if (st & 8u) return fail(BMBS_ERR_CAPACITY, "sort scratch exhausted");
+  return BMBS_OK;
+}
+}  // namespace
+
+extern "C" int bmbs_batch_download(bmbs_batch* b, bmbs_read_result* res, bmbs_cand* cand, size_t cand_cap, size_t* cand_used) {
+  if (!b || !b->ran || !res) return fail(BMBS_ERR_ARG, "bad argument or batch not run");
+  CU(cudaSetDevice(b->dev));
+  CU(cudaStreamSynchronize(b->stream));
+  int rc = check_status(b, cand_used);
+  if (rc) return rc;
+  const size_t work = (size_t)b->h_small[1];
+  if (work > cand_cap) return fail(BMBS_ERR_CAPACITY, "caller's cand[] holds " + std::to_string(cand_cap) + " entries, " + std::to_string(work) + " needed");
+  if (b->n_reads) CU(cudaMemcpyAsync(res, b->v.out_res, (size_t)b->n_reads * sizeof(bmbs_read_result), cudaMemcpyDeviceToHost, b->stream));
+  if (work) { if (!cand) return fail(BMBS_ERR_ARG, "cand is null"); CU(cudaMemcpyAsync(cand, b->v.out_cand, work * sizeof(bmbs_cand), cudaMemcpyDeviceToHost, b->stream)); }
+  CU(cudaStreamSynchronize(b->stream));
+  return BMBS_OK;
+}
+
+extern "C" int bmbs_batch_timings(bmbs_batch* b, float ms[8]) {
+  if (!b || !b->ran || !ms) return fail(BMBS_ERR_ARG, "bad argument or batch not run");
+  CU(cudaSetDevice(b->dev));
+  CU(cudaEventSynchronize(b->ev[7]));
+  CU(cudaEventElapsedTime(&ms[0], b->ev[0], b->ev[7]));
+  for (int i = 1; i <= 6; ++i) CU(cudaEventElapsedTime(&ms[i], b->ev[i - 1], b->ev[i]));
+  ms[7] = 0;
+  return BMBS_OK;
+}
+
+extern "C" int bmbs_batch_counters(bmbs_batch* b, uint64_t c[8]) {
+  if (!b || !b->ran || !c) return fail(BMBS_ERR_ARG, "bad argument or batch not run");
+  CU(cudaSetDevice(b->dev));
+  CU(cudaStreamSynchronize(b->stream));
+  for (int i = 0; i < 8; ++i) c[i] = b->h_small[4 + i];
+  c[CNT_CAND] = b->h_small[0];
+  return BMBS_OK;
+}
+
+extern "C" int bmbs_batch_launches(bmbs_batch* b) { return b ? b->launches : 0; }
+
+// ================================================================================================ one-call forms
+namespace {
+struct Cached { bmbs_index* idx; int dev; bmbs_batch* b; };
+thread_local std::vector<Cached> g_cache;
+
+int cached_batch(bmbs_index* idx, int dev, size_t reads, size_t bases, size_t cand_cap, bmbs_batch** out) {
+  for (auto& c : g_cache)
+    if (c.idx == idx && c.dev == dev) {
+      if (c.b->max_reads >= reads && c.b->max_bases >= bases && c.b->cand_cap >= cand_cap) { *out = c.b; return BMBS_OK; }
+      bmbs_batch_free(c.b); c.b = nullptr;
+      int rc = bmbs_batch_create(idx, dev, reads, bases, cand_cap, &c.b);
+      if (rc) { c.idx = nullptr; return rc; }
+      *out = c.b; return BMBS_OK;
+    }
+  bmbs_batch* b = nullptr;
+  int rc = bmbs_batch_create(idx, dev, reads, bases, cand_cap, &b);
+  if (rc) return rc;
+  g_cache.push_back({idx, dev, b});
+  *out = b; return BMBS_OK;
+}
+
+int map_batch(bmbs_index* idx, int dev, const char* seqs, const uint64_t* offsets, int n_reads, int pe, const bmbs_params* prm,
+              bmbs_read_result* res, bmbs_cand* cand, size_t cand_cap, size_t* cand_used) {
+  if (!idx || !seqs || !offsets || !prm || !res || n_reads < 0) return fail(BMBS_ERR_ARG, "bad argument");
+  bmbs_batch* b = nullptr;
+  size_t cap = cand_cap < 1024 ? 1024 : cand_cap;
+  int rc = cached_batch(idx, dev, (size_t)n_reads + 1, offsets[n_reads] + 64, cap, &b);
+  if (rc) return rc;
+  if ((rc = bmbs_batch_upload(b, seqs, offsets, n_reads, pe))) return rc;
+  if ((rc = bmbs_batch_run(b, prm))) return rc;
+  return bmbs_batch_download(b, res, cand, cand_cap, cand_used);
+}
+}  // namespace
+
+extern "C" int bmbs_map_batch_se(bmbs_index* idx, int dev, const char* seqs, const uint64_t* offsets, int n_reads, const bmbs_params* prm,
+                                 bmbs_read_result* res, bmbs_cand* cand, size_t cand_cap, size_t* cand_used) {
+  return map_batch(idx, dev, seqs, offsets, n_reads, 0, prm, res, cand, cand_cap, cand_used);
+}
+extern "C" int bmbs_map_batch_pe(bmbs_index* idx, int dev, const char* seqs, const uint64_t* offsets, int n_pairs, const bmbs_params* prm,
+                                 bmbs_read_result* res, bmbs_cand* cand, size_t cand_cap, size_t* cand_used) {
+  return map_batch(idx, dev, seqs, offsets, 2 * n_pairs, 1, prm, res, cand, cand_cap, cand_used);
+}
+
+namespace {
+__global__ void verify_setup(BatchView b, const u32* read_idx, const u64* sites, u32 n) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (u32)b.n_reads) b.state[i] = BMBS_VERIFY;
+  if (i < n) { b.work_read[i] = read_idx[i]; b.work_site[i] = sites[i]; b.work_vote[i] = 0; }
+  if (i == 0) b.totals[1] = n;
+}
+}  // namespace
+
+extern "C" int bmbs_verify(bmbs_index* idx, int dev, const char* seqs, const uint64_t* offsets, int n_reads, const uint32_t* read_idx,
+                           const uint64_t* sites, size_t n, double e_rate, int32_t* end_site, uint32_t* err) {
+  if (!idx || !seqs || !offsets || !read_idx || !sites || !end_site || !err) return fail(BMBS_ERR_ARG, "null argument");
+  for (size_t i = 0; i < n; ++i) if (read_idx[i] >= (uint32_t)n_reads) return fail(BMBS_ERR_ARG, "read_idx out of range");
+  bmbs_batch* b = nullptr;
+  int rc = cached_batch(idx, dev, (size_t)n_reads + 1, offsets[n_reads] + 64, n + 1024, &b);
+  if (rc) return rc;
+  if ((rc = bmbs_batch_upload(b, seqs, offsets, n_reads, 0))) return rc;
+  BatchView& v = b->v;
+  v.ascii = b->d_ascii; v.offsets = b->d_offsets; v.n_reads = n_reads; v.pe = 0; v.e_rate = e_rate;
+  cudaStream_t s = b->stream;
+  CU(cudaMemsetAsync(v.counters, 0, 16 * 8, s)); CU(cudaMemsetAsync(v.totals, 0, 4 * 8, s)); CU(cudaMemsetAsync(v.status, 0, 16, s));
+  // stage the work list through cand[] / slot_row[] (free in this mode)
+  CU(cudaMemcpyAsync(v.slot_read, read_idx, n * 4, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(v.slot_row, sites, n * 8, cudaMemcpyHostToDevice, s));
+  b->launches = 0;
+  CU(cudaEventRecord(b->ev[0], s));
+  if (n_reads) { pack_reads<<<(n_reads + 3) / 4, 128, 0, s>>>(v); ++b->launches; }
+  const u32 m = (u32)(n > (size_t)n_reads ? n : (size_t)n_reads);
+  if (m) { verify_setup<<<(m + 255) / 256, 256, 0, s>>>(v, v.slot_read, v.slot_row, (u32)n); ++b->launches; }
+  for (int i = 1; i <= 5; ++i) CU(cudaEventRecord(b->ev[i], s));
+  const int nch2 = (b->max_len + 31) / 32 + 2;
+  int bd = 128;
+  while (bd > 32 && (size_t)5 * nch2 * bd * 8 > 96 * 1024) bd >>= 1;
+  const size_t smem = (size_t)5 * nch2 * bd * 8;
+  int per_sm = (int)((200 * 1024) / (smem + 1024)); if (per_sm > 12) per_sm = 12; if (per_sm < 1) per_sm = 1;
+  verify_windows<<<b->sm_count * per_sm, bd, smem, s>>>(b->copy->view, v, nch2); ++b->launches;
+  CU(cudaEventRecord(b->ev[6], s)); CU(cudaEventRecord(b->ev[7], s));
+  CU(cudaMemcpyAsync(b->h_small + 4, v.counters, 8 * 8, cudaMemcpyDeviceToHost, s));
+  std::vector<bmbs_cand> tmp(n);
+  if (n) CU(cudaMemcpyAsync(tmp.data(), v.out_cand, n * sizeof(bmbs_cand), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  CU(cudaGetLastError());
+  b->h_small[0] = 0; b->h_small[1] = n; *(u32*)(b->h_small + 2) = 0; b->ran = true;
+  for (size_t i = 0; i < n; ++i) { end_site[i] = tmp[i].end_site; err[i] = tmp[i].err == 0xFFFF ? 0xFFFFFFFFu : tmp[i].err; }
+  return BMBS_OK;
+}

@@ -1,0 +1,632 @@
+// CUDA kernels of the seed-and-verify path (sm_100a; integer / bit-vector work, no tensor cores).
+//
+//   pack_reads      ASCII -> nibble codes, first-C position, error threshold k
+//   seed_reads      kernel 1a: per-read seeding state machine (FM backward search with the 16-mer table,
+//                   unique-hit shortcut with direct genome compare, one-mismatch second seed, remaining seeds)
+//   expand_tasks    seed intervals -> one locate work item per row
+//   locate_rows     kernel 1b: LF-walk every row to a sampled suffix, -> candidate site
+//   votes_small/big kernel 2: per-read sort, run-length votes with the site-k shift
+//   filter_pairs    kernel 2b (paired end): distance pre-filter of the two mates' lists
+//   gather_work     compaction of the surviving windows into the verification work list
+//   verify_windows  kernel 3: banded Myers bit-vector edit distance, read T may face reference C
+//   finalize_reads  per-read result records
+#pragma once
+#include "bmbs_device.cuh"
+#include "../../include/bmbs.h"
+
+namespace bmbs {
+
+constexpr int MAX_TASKS = 28;       // 25 seeds + first-seed literal + second seed + slack
+constexpr u32 MAX_SEED_HITS = 1000; // Schema.cpp:26826 max_seed_matches
+constexpr u32 MAX_PE_MULTI = 25000; // Schema.cpp:18854 max_candidates_occ
+
+struct SeedTask { u64 sp; u32 hits; unsigned short mlen, off; };  // hits==0: `sp` is a literal site
+
+// counters (device, u64[16]); indices follow bmbs_batch_counters
+enum { CNT_HASH = 0, CNT_OCC = 1, CNT_ROWS = 2, CNT_LOCATE_LF = 3, CNT_VERIFIED = 4, CNT_CELLS = 5, CNT_CAND = 6, CNT_WINBYTES = 7 };
+
+struct BatchView {
+  // inputs
+  const char* ascii; const u64* offsets; int n_reads; int pe;
+  // per read
+  u32* codes; u32* len; unsigned short* first_c; unsigned char* kk;
+  unsigned char* state; unsigned char* flags;  // flags: bit0 is_multi, bit1 extra==0 (second seed conclusive)
+  short* one_mm; u64* site0;
+  u32* ntask; u32* ncand; u32* coff;           // coff: exclusive scan of ncand, n_reads+1
+  SeedTask* tasks;                              // [MAX_TASKS][n_reads]
+  // per candidate slot
+  u64* slot_row; u32* slot_adj; u32* slot_read; u64* cand; u32* vcnt;
+  u32* nv; u32* voff;                           // votes per read, exclusive scan
+  unsigned char* keep;
+  // work list
+  u64* work_site; u32* work_vote; u32* work_read; bmbs_cand* out_cand;
+  bmbs_read_result* out_res;
+  u32* big_list; u32* big_count; u64* scratch; u32* scratch_used; u64 scratch_cap;
+  u64* counters; u64* totals;   // totals[0] candidate slots, totals[1] verification work items
+  u32* status;                  // bit0 per-read task overflow, bit1 slot capacity, bit2 work capacity, bit3 scratch
+  u64 slot_cap;
+  double e_rate; u32 seed_len; int dmax_base, dmin_base;  // pair distance bounds before the per-pair 2k / length terms
+};
+
+__device__ __forceinline__ u32 code_word_offset(const u64* offsets, int r) { return (u32)(offsets[r] >> 3) + (u32)r; }
+
+// ------------------------------------------------------------------------------------------- pack
+// one warp per read: 8 ASCII bases -> one u32 of nibbles.  Codes: A0 C1 G2 T3 N4 other5.
+__global__ void pack_reads(BatchView b) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= b.n_reads) return;
+  const u64 beg = b.offsets[r];
+  const u32 L = (u32)(b.offsets[r + 1] - beg);
+  const char* s = b.ascii + beg;
+  u32* w = b.codes + code_word_offset(b.offsets, r);
+  u32 first_c = L;
+  for (u32 j = lane; j * 8 < L; j += 32) {
+    u32 word = 0;
+    for (u32 t = 0; t < 8; ++t) {
+      const u32 i = j * 8 + t;
+      u32 c = 0;
+      if (i < L) {
+        const char ch = s[i];
+        c = ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : ch == 'N' ? 4u : 5u;
+        if (c == 1u && i < first_c) first_c = i;
+      }
+      word |= c << (4 * t);
+    }
+    w[j] = word;
+  }
+  for (int o = 16; o; o >>= 1) first_c = min(first_c, __shfl_xor_sync(0xffffffffu, first_c, o));
+  if (lane == 0) {
+    b.len[r] = L;
+    b.first_c[r] = (unsigned short)first_c;
+    u64 k = (u64)(b.e_rate * (double)L);   // Schema.cpp:27121: double product truncated, capped at 31
+    b.kk[r] = (unsigned char)(k >= 31 ? 31 : k);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- seed
+struct SeedHit { u64 hits, sp, ep; u32 mlen; };
+
+// count_backward_as_much_1_terminate (bwt.h:2081-2209) on the reversed, C->T converted read:
+// the seed starts at read[off] and grows to the right; cur = L - off bases are available.
+__device__ __forceinline__ SeedHit seed_until_unique(const DevIndex& ix, const u32* __restrict__ w, u32 off, u32 cur,
+                                                     u64 sp_in, u64 ep_in, u32& n_occ, u32& n_hash) {
+  SeedHit h; h.hits = 0; h.sp = sp_in; h.ep = ep_in; h.mlen = 0;
+  if (cur < 18) return h;
+  u64 key = 0, p3 = 1;
+  for (u32 m = 0; m < 16; ++m) {
+    const int c = fm_code(read_code(w, off + m));
+    if (c > 2) return h;
+    key += p3 * (u64)c; p3 *= 3;
+  }
+  u64 top, bot;
+  hash_query(ix, key, top, bot); ++n_hash;
+  if (bot <= top) return h;
+  u64 ptop = ~0ull, pbot = ~0ull;
+  u32 m = 16;
+  for (; m < cur; ++m) {
+    ptop = top; pbot = bot;
+    if (bot - top == 1) break;
+    const int c = fm_code(read_code(w, off + m));
+    if (c > 2) { bot = top; break; }
+    n_occ += lf_pair(ix, top, bot, c);
+    if (bot <= top) break;
+  }
+  h.mlen = m;
+  if (bot <= top) { h.sp = ptop; h.ep = pbot; } else { h.sp = top; h.ep = bot; }
+  h.hits = h.ep - h.sp;
+  return h;
+}
+
+// count_hash_table (bwt.h:1848-1952): exact interval of read[off .. off+cur)
+__device__ __forceinline__ u64 count_exact(const DevIndex& ix, const u32* __restrict__ w, u32 off, u32 cur, u64& sp, u64& ep,
+                                           u32& n_occ, u32& n_hash) {
+  if (cur < 17) return 0;
+  u64 key = 0, p3 = 1;
+  for (u32 m = 0; m < 16; ++m) {
+    const int c = fm_code(read_code(w, off + m));
+    if (c > 2) return 0;
+    key += p3 * (u64)c; p3 *= 3;
+  }
+  u64 top, bot;
+  hash_query(ix, key, top, bot); ++n_hash;
+  if (bot <= top) return 0;
+  for (u32 m = 16; m < cur; ++m) {
+    if (bot <= top) break;
+    const int c = fm_code(read_code(w, off + m));
+    if (c > 2) return 0;
+    n_occ += lf_pair(ix, top, bot, c);
+  }
+  sp = top; ep = bot;
+  return bot <= top ? 0 : bot - top;
+}
+
+// determine_seed_offset_unmatch, Schema.h:1506-1531 (step 8)
+__device__ __forceinline__ u32 next_offset_unmatched(const u32* __restrict__ w, u32 L, u32 off) {
+  if ((int)L - (int)off < 18) return L;
+  for (u32 i = 0; i < 8; ++i) if (read_code(w, off + i) == 4) return off + i + 1;
+  return off + 8;
+}
+
+__global__ void __launch_bounds__(128) seed_reads(DevIndex ix, BatchView b) {
+  __shared__ u64 s_cnt[4];
+  if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  u32 n_occ = 0, n_hash = 0, n_rows = 0, n_llf = 0;
+  if (r < b.n_reads) {
+    const u32 L = b.len[r];
+    const u32* w = b.codes + code_word_offset(b.offsets, r);
+    const u32 first_c = b.first_c[r];
+    u64 max_seeds = (u64)L / 10 - 1; if (max_seeds > 25) max_seeds = 25;   // u64 wrap for L < 10, as in the reference
+    u32 off = 0, nt = 0, nc = 0, first_len = 0;
+    u64 seed_id = 0, sp = 0, ep = 0, site0 = 0;
+    int state = BMBS_NONE, get_error = -1, one_mm = 0;
+    bool is_multi = false, extra = true, done = false;
+    auto emit = [&](u64 a, u32 hits, u32 mlen, u32 o) {
+      if (nt < MAX_TASKS) { SeedTask t; t.sp = a; t.hits = hits; t.mlen = (unsigned short)mlen; t.off = (unsigned short)o; b.tasks[(size_t)nt * b.n_reads + r] = t; }
+      ++nt; nc += hits ? hits : 1u;
+    };
+    if (seed_id < max_seeds && off < L) {
+      SeedHit h = seed_until_unique(ix, w, off, L - off, sp, ep, n_occ, n_hash);
+      sp = h.sp; ep = h.ep;
+      u32 mlen = h.mlen; first_len = mlen;
+      if (h.hits == 1) {
+        int st; const u64 sa = locate_row(ix, sp, st); n_llf += st; ++n_rows;
+        const u64 site = 2 * ix.N - sa - mlen;
+        emit(site, 0, 0, 0);
+        // try_process_unique_mismatch_end_to_end_*: Schema.cpp:15410-15478, :15661-15715
+        if (mlen > first_c) mlen = first_c;
+        int errors = 0;
+        if (mlen != L) {
+          const bool inside = window_inside(ix, site, L);
+          for (u32 ri = mlen; ri < L; ++ri) {
+            const int rc = read_code(w, ri);
+            bool mism = true;
+            if (inside) { const int g = strand_base(ix, site + ri); mism = rc != g && !(rc == 3 && g == 1); }
+            if (mism) { if (++errors == 1) mlen = ri; else break; }
+          }
+        }
+        get_error = errors;
+        if (errors == 0) { state = BMBS_EXACT_UNIQUE; site0 = site; done = true; }
+      }
+      if (!done) {
+        one_mm = (int)mlen;
+        if (mlen == L && h.hits > 1 && (!b.pe || h.hits <= MAX_PE_MULTI)) {
+          is_multi = true;
+          if (first_c == L) {
+            state = BMBS_MULTI_EXACT; done = true;
+            if (b.pe) emit(sp, (u32)h.hits, mlen, off);
+          }
+        }
+      }
+      if (!done) {
+        if (h.hits != 1 && mlen >= b.seed_len && h.hits <= MAX_SEED_HITS && h.hits != 0) emit(sp, (u32)h.hits, mlen, off);
+        off = mlen == 0 ? next_offset_unmatched(w, L, off) : off + mlen / 2;
+        ++seed_id;
+      }
+    }
+    if (!done && get_error == 1) {
+      const u32 len2 = L - first_len;
+      if (len2 >= 17) {
+        const u64 hits = count_exact(ix, w, first_len, len2, sp, ep, n_occ, n_hash);
+        if (hits <= MAX_SEED_HITS) { if (hits) emit(sp, (u32)hits, len2, first_len); extra = false; }
+      }
+    }
+    if (!done && extra) {
+      while (seed_id < max_seeds && off < L) {
+        const u32 cur = L - off;
+        SeedHit h = seed_until_unique(ix, w, off, cur, sp, ep, n_occ, n_hash);
+        sp = h.sp; ep = h.ep;
+        if (h.hits == 1) emit(sp, 1, h.mlen, off);
+        else if (h.mlen >= b.seed_len && h.hits <= MAX_SEED_HITS) { if (h.hits) emit(sp, (u32)h.hits, h.mlen, off); }
+        else if (cur == h.mlen) break;
+        off = h.mlen == 0 ? next_offset_unmatched(w, L, off) : off + h.mlen / 2;
+        ++seed_id;
+      }
+    }
+    b.state[r] = (unsigned char)state;
+    b.flags[r] = (unsigned char)((is_multi ? 1 : 0) | (extra ? 0 : 2));
+    b.one_mm[r] = (short)one_mm;
+    b.site0[r] = site0;
+    b.ntask[r] = nt < MAX_TASKS ? nt : MAX_TASKS;
+    b.ncand[r] = nt <= MAX_TASKS ? nc : 0xFFFFFFFFu;  // overflow is reported by the host
+  }
+  atomicAdd(&s_cnt[0], (u64)n_hash); atomicAdd(&s_cnt[1], (u64)n_occ); atomicAdd(&s_cnt[2], (u64)n_rows); atomicAdd(&s_cnt[3], (u64)n_llf);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(b.counters + CNT_HASH, s_cnt[0]); atomicAdd(b.counters + CNT_OCC, s_cnt[1]);
+    atomicAdd(b.counters + CNT_ROWS, s_cnt[2]); atomicAdd(b.counters + CNT_LOCATE_LF, s_cnt[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- expand + locate
+__global__ void expand_tasks(BatchView b) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= b.n_reads || *b.status) return;
+  u32 s = b.coff[r];
+  const u32 nt = b.ntask[r];
+  for (u32 t = 0; t < nt; ++t) {
+    const SeedTask k = b.tasks[(size_t)t * b.n_reads + r];
+    if (k.hits == 0) { b.slot_row[s] = k.sp; b.slot_adj[s] = 0xFFFFFFFFu; b.slot_read[s] = r; ++s; }
+    else for (u32 j = 0; j < k.hits; ++j, ++s) { b.slot_row[s] = k.sp + j; b.slot_adj[s] = (u32)k.mlen + (u32)k.off; b.slot_read[s] = r; }
+  }
+}
+
+// site = 2N - SA - seed_len - seed_off, modulo 2^64 (reverse_and_adjust_site, Schema.cpp:4657-4683)
+__global__ void __launch_bounds__(256) locate_rows(DevIndex ix, BatchView b) {
+  __shared__ u64 s_cnt[2];
+  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const u32 total = *b.status ? 0u : (u32)b.totals[0];
+  u64 steps = 0, rows = 0;
+  for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
+    const u32 adj = b.slot_adj[s];
+    u64 v = b.slot_row[s];
+    if (adj != 0xFFFFFFFFu) { int st; const u64 sa = locate_row(ix, v, st); v = 2 * ix.N - sa - (u64)adj; ++rows; steps += st; }
+    b.cand[s] = v;
+  }
+  atomicAdd(&s_cnt[0], rows); atomicAdd(&s_cnt[1], steps);
+  __syncthreads();
+  if (threadIdx.x == 0) { atomicAdd(b.counters + CNT_ROWS, s_cnt[0]); atomicAdd(b.counters + CNT_LOCATE_LF, s_cnt[1]); }
+}
+
+// ------------------------------------------------------------------------------------------- votes
+// What a read's candidates turn into (Schema.cpp:27527-27612, :19885-19915):
+//   conclusive second seed with a single distinct candidate -> ONE_MISMATCH;
+//   otherwise sort + run-length encode into windows {max(c-k,0), votes}  (generate_candidate_votes_shift, :4687-4773).
+// Returns true when the segment still has to be sorted/encoded.
+__device__ __forceinline__ bool classify_read(BatchView& b, int r, u32 beg, u32 n, bool lane0) {
+  const int st = b.state[r];
+  if (st == BMBS_EXACT_UNIQUE) { if (lane0) b.nv[r] = b.pe ? 1u : 0u; return false; }
+  if (st == BMBS_MULTI_EXACT) { if (!b.pe) { if (lane0) b.nv[r] = 0; return false; } return true; }
+  if (n == 0) { if (lane0) b.nv[r] = 0; return false; }
+  if ((b.flags[r] & 2) && (n == 1 || (n == 2 && b.cand[beg] == b.cand[beg + 1]))) {
+    if (lane0) { b.state[r] = BMBS_ONE_MISMATCH; b.site0[r] = b.cand[beg]; b.nv[r] = b.pe ? 1u : 0u; }
+    return false;
+  }
+  if (lane0) b.state[r] = BMBS_VERIFY;
+  return true;
+}
+
+__device__ __forceinline__ u64 window_start(u64 c, u64 k) { return c < k ? 0ull : c - k; }
+
+// one warp per read; segments of up to 32 candidates are sorted in registers (bitonic over shuffles),
+// encoded with a ballot, and written back in place; longer segments are queued for votes_big.
+__global__ void __launch_bounds__(128) votes_small(BatchView b) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= b.n_reads || *b.status) return;
+  const u32 beg = b.coff[r], n = b.coff[r + 1] - beg;
+  const bool multi = b.state[r] == BMBS_MULTI_EXACT;
+  if (n > 32) {
+    // classification needs only the first two candidates, do it here so votes_big sees final states
+    if (!classify_read(b, r, beg, n, lane == 0)) return;
+    if (lane == 0) { const u32 i = atomicAdd(b.big_count, 1u); b.big_list[i] = (u32)r; }
+    return;
+  }
+  if (!classify_read(b, r, beg, n, lane == 0)) return;
+  u64 v = lane < (int)n ? b.cand[beg + lane] : ~0ull;
+  bool pad = lane >= (int)n;   // padding sorts last even against a real ~0 key
+  for (int k = 2; k <= 32; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const u64 o = __shfl_xor_sync(0xffffffffu, v, j);
+      const bool opad = __shfl_xor_sync(0xffffffffu, (int)pad, j) != 0;
+      const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+      const bool o_less = (!opad && pad) || (opad == pad && o < v);
+      const bool v_less = (!pad && opad) || (opad == pad && v < o);
+      const bool take = (lower == up) ? o_less : v_less;
+      if (take) { v = o; pad = opad; }
+    }
+  if (multi) { if (lane < (int)n) { b.cand[beg + lane] = v; b.vcnt[beg + lane] = 0; } if (lane == 0) b.nv[r] = n; return; }
+  const u64 prev = __shfl_up_sync(0xffffffffu, v, 1);
+  const bool head = lane < (int)n && (lane == 0 || prev != v);
+  const u32 heads = __ballot_sync(0xffffffffu, head);
+  const u32 valid = n == 32 ? 0xffffffffu : ((1u << n) - 1u);
+  if (head) {
+    const u32 idx = __popc(heads & ((1u << lane) - 1u));
+    // run length = distance to the next head (or to n)
+    const u32 later = heads & ~((2u << lane) - 1u) & valid;
+    const u32 next = later ? (u32)(__ffs(later) - 1) : n;
+    b.cand[beg + idx] = window_start(v, (u64)b.kk[r]);
+    b.vcnt[beg + idx] = next - lane;
+  }
+  if (lane == 0) b.nv[r] = __popc(heads);
+}
+
+// one CTA per long segment: bitonic sort on a power-of-two padded copy (shared memory when it fits,
+// global scratch otherwise), then a block-wide run-length encode.
+constexpr int BIG_SMEM_ELEMS = 4096;
+__global__ void __launch_bounds__(256) votes_big(BatchView b) {
+  __shared__ u64 s_buf[BIG_SMEM_ELEMS];
+  __shared__ u32 s_warp[8];
+  __shared__ u32 s_base, s_soff;
+  const u32 nbig = *b.status ? 0u : *b.big_count;
+  for (u32 bi = blockIdx.x; bi < nbig; bi += gridDim.x) {
+    const int r = (int)b.big_list[bi];
+    const u32 beg = b.coff[r], n = b.coff[r + 1] - beg;
+    u32 P = 64; while (P < n) P <<= 1;
+    u64* a = s_buf;
+    if (P > BIG_SMEM_ELEMS) {
+      if (threadIdx.x == 0) s_soff = atomicAdd(b.scratch_used, P);
+      __syncthreads();
+      if ((u64)s_soff + P > b.scratch_cap) { if (threadIdx.x == 0) { b.nv[r] = 0; atomicOr(b.status, 8u); } __syncthreads(); continue; }
+      a = b.scratch + s_soff;
+    }
+    for (u32 i = threadIdx.x; i < P; i += blockDim.x) a[i] = i < n ? b.cand[beg + i] : ~0ull;
+    __syncthreads();
+    for (u32 k = 2; k <= P; k <<= 1)
+      for (u32 j = k >> 1; j > 0; j >>= 1) {
+        for (u32 i = threadIdx.x; i < P; i += blockDim.x) {
+          const u32 x = i ^ j;
+          if (x > i) {
+            const u64 vi = a[i], vx = a[x];
+            const bool up = (i & k) == 0;
+            if (up ? vi > vx : vi < vx) { a[i] = vx; a[x] = vi; }
+          }
+        }
+        __syncthreads();
+      }
+    // a real key equal to ~0 is indistinguishable from padding but also equal to it, so the first n entries are right
+    if (b.state[r] == BMBS_MULTI_EXACT) {
+      for (u32 i = threadIdx.x; i < n; i += blockDim.x) { b.cand[beg + i] = a[i]; b.vcnt[beg + i] = 0; }
+      if (threadIdx.x == 0) b.nv[r] = n;
+      __syncthreads();
+      continue;
+    }
+    const u64 k = b.kk[r];
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (u32 c0 = 0; c0 < n; c0 += blockDim.x) {
+      const u32 i = c0 + threadIdx.x;
+      const bool head = i < n && (i == 0 || a[i - 1] != a[i]);
+      const u32 bal = __ballot_sync(0xffffffffu, head);
+      const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+      if (lane == 0) s_warp[wid] = __popc(bal);
+      __syncthreads();
+      u32 before = 0, total = 0;
+      for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) { if (w2 < wid) before += s_warp[w2]; total += s_warp[w2]; }
+      if (head) {
+        u32 e = i + 1; while (e < n && a[e] == a[i]) ++e;      // run length
+        const u32 idx = s_base + before + __popc(bal & ((1u << lane) - 1u));
+        b.cand[beg + idx] = window_start(a[i], k);             // idx <= i and a[] is a copy: in place is safe
+        b.vcnt[beg + idx] = e - i;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) s_base += total;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) b.nv[r] = s_base;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------- pair filter
+// filter_pairs, Schema.cpp:16052-16180, one thread per pair, literal two-pointer walk.
+__global__ void filter_pairs_kernel(BatchView b) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p * 2 + 1 >= b.n_reads || *b.status) return;
+  const int r1 = 2 * p, r2 = r1 + 1;
+  const int s1 = b.state[r1], s2 = b.state[r2];
+  const bool res1 = s1 == BMBS_EXACT_UNIQUE || s1 == BMBS_MULTI_EXACT || s1 == BMBS_ONE_MISMATCH;
+  const bool res2 = s2 == BMBS_EXACT_UNIQUE || s2 == BMBS_MULTI_EXACT || s2 == BMBS_ONE_MISMATCH;
+  u32 n1 = b.nv[r1], n2 = b.nv[r2];
+  if (res1 && res2) return;
+  if (n1 == 0 || n2 == 0) { b.nv[r1] = 0; b.nv[r2] = 0; return; }
+  const u32 b1 = b.coff[r1], b2 = b.coff[r2];
+  const u64 k1 = b.kk[r1], k2 = b.kk[r2], kl = k1 > k2 ? k1 : k2;
+  const u32 L1 = b.len[r1], L2 = b.len[r2];
+  const int dmax = (int)((u64)(long long)b.dmax_base + kl * 2);
+  const int dmin = (int)((u64)(long long)b.dmin_base - kl * 2 - (u64)(L1 > L2 ? L1 : L2));
+  for (u32 i = 0; i < n1; ++i) b.keep[b1 + i] = 0;
+  for (u32 j = 0; j < n2; ++j) b.keep[b2 + j] = 0;
+  long long first = 0;
+  bool any1 = false, any2 = false; u64 last1 = 0, last2 = 0;
+  for (long long i = 0; i < (long long)n1; ++i) {
+    const u64 a = b.cand[b1 + i];
+    for (long long j = first; j < (long long)n2; ++j) {
+      const u64 c = b.cand[b2 + j];
+      bool in = false;
+      if (a > c) { const long long d = (long long)(a - c); if (d > dmax) first = j + 1; else if (d >= dmin) in = true; }
+      else { const long long d = (long long)(c - a); if (d > dmax) break; if (d >= dmin) in = true; }
+      if (in) {
+        if (!any1 || a > last1) { b.keep[b1 + i] = 1; any1 = true; last1 = a; }
+        if (!any2 || c > last2) { b.keep[b2 + j] = 1; any2 = true; last2 = c; }
+      }
+    }
+  }
+  u32 k = 0;
+  for (u32 i = 0; i < n1; ++i) if (b.keep[b1 + i]) { b.cand[b1 + k] = b.cand[b1 + i]; b.vcnt[b1 + k] = b.vcnt[b1 + i]; ++k; }
+  u32 m = 0;
+  for (u32 j = 0; j < n2; ++j) if (b.keep[b2 + j]) { b.cand[b2 + m] = b.cand[b2 + j]; b.vcnt[b2 + m] = b.vcnt[b2 + j]; ++m; }
+  if (k == 0 || m == 0) { k = 0; m = 0; }
+  b.nv[r1] = k; b.nv[r2] = m;
+}
+
+// ------------------------------------------------------------------------------------------- gather
+__global__ void gather_work(BatchView b) {
+  const u32 total = *b.status ? 0u : (u32)b.totals[0];
+  for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
+    const u32 r = b.slot_read[s];
+    const u32 j = s - b.coff[r];
+    if (j >= b.nv[r]) continue;
+    const u32 w = b.voff[r] + j;
+    b.work_site[w] = b.cand[s]; b.work_vote[w] = b.vcnt[s]; b.work_read[w] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- verify
+// BS_Reserve_Banded_BPM (Levenshtein_Cal.h:351-567): Hyyro banded Myers, band 2k+1, "pattern" = reference window of
+// L+2k bases, "text" = read; read T matches reference C or T, N matches nothing, an all-zero (out-of-genome)
+// window matches nothing.  One thread per window; the window's four match bit-planes (A, C, G, T|C) plus a zero
+// plane live in shared memory as overlapping 64-bit chunks (chunk c = window bits [32c, 32c+64)), so a column's
+// Eq word is one LDS.64 + one shift; band state is one W-bit word per thread (W = 32 for k <= 15, 64 for k <= 31;
+// any width >= 2k+2 gives identical results).
+template <typename W>
+__device__ __forceinline__ void bpm_columns(const u64* __restrict__ sm, int stride, int nch2, const u32* __restrict__ rw,
+                                            int L, int k, int& end_out, u32& err_out) {
+  const int band = 2 * k + 1;
+  const W mask = band >= (int)(8 * sizeof(W)) ? ~(W)0 : (((W)1 << band) - 1);
+  W VP = 0, VN = 0;
+  int err = 0;
+  const int limit = 3 * k;   // err - 2k > k can never recover (Levenshtein_Cal.h:455)
+  bool dead = false;
+  for (int i0 = 0; i0 < L && !dead; i0 += 8) {
+    const u32 word = __ldg(rw + (i0 >> 3));
+    const int n = min(8, L - i0);
+    for (int t = 0; t < n; ++t) {
+      const int i = i0 + t;
+      int code = (word >> (4 * t)) & 0xF; code = code > 4 ? 4 : code;
+      const int ch = i >> 5, sh = i & 31;
+      const u64 e0 = sm[(code * nch2 + ch) * stride];
+      W eq;
+      if (sizeof(W) == 4) eq = (W)(e0 >> sh) & mask;
+      else {
+        const u64 e1 = sm[(code * nch2 + ch + 1) * stride];
+        eq = (W)(sh ? (e0 >> sh) | ((e1 >> 32) << (64 - sh)) : e0) & mask;
+      }
+      W X = eq | VN;
+      const W D0 = ((VP + (X & VP)) ^ VP) | X;
+      const W HN = VP & D0, HP = VN | ~(VP | D0);
+      X = D0 >> 1;
+      VN = X & HP; VP = HN | ~(X | HP);
+      err += (int)(~D0 & 1);
+    }
+    if (err > limit) dead = true;
+  }
+  end_out = -1; err_out = 0xFFFFFFFFu;
+  if (dead) return;
+  const int last = L - 1;
+  u32 best = 0xFFFFFFFFu; int site = -1;
+  if (err <= k) { best = (u32)err; site = last; }
+  int ungapped = err;
+  for (int i = 0; i < 2 * k; ++i) {
+    err += (int)((VP >> i) & 1) - (int)((VN >> i) & 1);
+    if (err <= k && (u32)err <= best) { best = (u32)err; site = last + i + 1; }
+    if (i + 1 == k) ungapped = err;
+  }
+  if (k == 0) ungapped = err;
+  if (ungapped >= 0 && ungapped <= k && (u32)ungapped == best) site = last + k;
+  end_out = site; err_out = best;
+}
+
+__global__ void verify_windows(DevIndex ix, BatchView b, int nch2) {
+  extern __shared__ u64 sm_all[];
+  __shared__ u64 s_cnt[3];
+  if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const u32 total_work = *b.status ? 0u : (u32)b.totals[1];
+  const int stride = blockDim.x;
+  u64* sm = sm_all + threadIdx.x;
+  u64 cells = 0, wbytes = 0, verified = 0;
+  for (u32 wi = blockIdx.x * blockDim.x + threadIdx.x; wi < total_work; wi += gridDim.x * blockDim.x) {
+    const u32 r = b.work_read[wi];
+    const u64 site = b.work_site[wi];
+    const int L = (int)b.len[r], k = (int)b.kk[r];
+    const int st = b.state[r];
+    int end = -1; u32 err = 0xFFFFFFFFu;
+    if (st == BMBS_EXACT_UNIQUE || st == BMBS_MULTI_EXACT) { end = L - 1; err = 0; }
+    else if (st == BMBS_ONE_MISMATCH) { end = L - 1; err = 1; }
+    else {
+      const int plen = L + 2 * k;
+      const int nch = (L + 31) >> 5;           // chunks addressed by the column loop (+1 for 64-bit bands)
+      const bool inside = window_inside(ix, site, (u64)plen);
+      if (inside) {
+        const uint2* gp = ix.planes + (site >> 5);
+        const unsigned sh = (unsigned)site & 31u;
+        uint2 w0 = __ldg(gp), w1 = __ldg(gp + 1);
+        u32 lo_prev = __funnelshift_r(w0.x, w1.x, sh), hi_prev = __funnelshift_r(w0.y, w1.y, sh);
+        for (int c = 0; c <= nch; ++c) {
+          const uint2 w2 = __ldg(gp + c + 2);
+          const u32 lo_next = __funnelshift_r(w1.x, w2.x, sh), hi_next = __funnelshift_r(w1.y, w2.y, sh);
+          const u64 lo = (u64)lo_prev | ((u64)lo_next << 32), hi = (u64)hi_prev | ((u64)hi_next << 32);
+          sm[(0 * nch2 + c) * stride] = ~hi & ~lo;   // A
+          sm[(1 * nch2 + c) * stride] = ~hi & lo;    // C
+          sm[(2 * nch2 + c) * stride] = hi & ~lo;    // G
+          sm[(3 * nch2 + c) * stride] = lo;          // T (matches reference C or T)
+          sm[(4 * nch2 + c) * stride] = 0;           // N / other
+          w1 = w2; lo_prev = lo_next; hi_prev = hi_next;
+        }
+        wbytes += (u64)(nch + 3) * 8;
+      } else {
+        for (int c = 0; c <= nch; ++c) for (int p = 0; p < 5; ++p) sm[(p * nch2 + c) * stride] = 0;
+      }
+      const u32* rw = b.codes + code_word_offset(b.offsets, (int)r);
+      if (k <= 15) bpm_columns<u32>(sm, stride, nch2, rw, L, k, end, err);
+      else bpm_columns<u64>(sm, stride, nch2, rw, L, k, end, err);
+      ++verified; cells += (u64)L * (u64)(2 * k + 1);
+    }
+    bmbs_cand o; o.site = site; o.vote = b.work_vote[wi]; o.end_site = (int16_t)end; o.err = err == 0xFFFFFFFFu ? (uint16_t)0xFFFF : (uint16_t)err;
+    b.out_cand[wi] = o;
+  }
+  atomicAdd(&s_cnt[0], verified); atomicAdd(&s_cnt[1], cells); atomicAdd(&s_cnt[2], wbytes);
+  __syncthreads();
+  if (threadIdx.x == 0) { atomicAdd(b.counters + CNT_VERIFIED, s_cnt[0]); atomicAdd(b.counters + CNT_CELLS, s_cnt[1]); atomicAdd(b.counters + CNT_WINBYTES, s_cnt[2]); }
+}
+
+// ------------------------------------------------------------------------------------------- finalize
+__global__ void finalize_reads(BatchView b) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= b.n_reads) return;
+  bmbs_read_result o;
+  o.site = b.site0[r]; o.first_cand = b.voff[r];
+  o.n_cand = b.nv[r];
+  o.one_mismatch_pos = b.one_mm[r]; o.state = b.state[r]; o.is_multiple_map = b.flags[r] & 1; o.reserved = 0;
+  b.out_res[r] = o;
+}
+
+// ------------------------------------------------------------------------------------------- scan
+// exclusive scan of u32 counts into u32 offsets (out[n] = total); 0xFFFFFFFF inputs count as 0 and set *overflow.
+constexpr int SCAN_TILE = 1024;
+__global__ void scan_tiles(const u32* in, u32 n, u64* tile_sum, u32* overflow) {
+  __shared__ u64 s_w[32];
+  const u32 i = blockIdx.x * SCAN_TILE + threadIdx.x;
+  u32 v = i < n ? in[i] : 0u;
+  if (v == 0xFFFFFFFFu) { v = 0; atomicOr(overflow, 1u); }
+  u64 x = v;
+  for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = x;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    u64 y = s_w[threadIdx.x];
+    for (int o = 16; o; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = y;
+  }
+}
+__global__ void scan_tile_sums(u64* tile_sum, u32 ntiles, u64* total, u64 cap, u32* status, u32 cap_bit) {
+  // single block, serial over chunks of blockDim
+  __shared__ u64 s_carry; __shared__ u64 s_w[32];
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (u32 base = 0; base < ntiles; base += blockDim.x) {
+    const u32 i = base + threadIdx.x;
+    const u64 v = i < ntiles ? tile_sum[i] : 0ull;
+    u64 x = v;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) { const u64 y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_w[wid] = x;
+    __syncthreads();
+    u64 wbase = 0; for (int w2 = 0; w2 < wid; ++w2) wbase += s_w[w2];
+    const u64 incl = s_carry + wbase + x;
+    if (i < ntiles) tile_sum[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { *total = s_carry; if (s_carry > cap) atomicOr(status, cap_bit); }
+}
+__global__ void scan_apply(const u32* in, u32 n, const u64* tile_sum, u32* out) {
+  __shared__ u32 s_w[32];
+  const u32 i = blockIdx.x * SCAN_TILE + threadIdx.x;
+  u32 v = i < n ? in[i] : 0u;
+  if (v == 0xFFFFFFFFu) v = 0;
+  u32 x = v;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) s_w[wid] = x;
+  __syncthreads();
+  u32 wbase = 0; for (int w2 = 0; w2 < wid; ++w2) wbase += s_w[w2];
+  const u64 excl = tile_sum[blockIdx.x] + wbase + x - v;
+  if (i < n) out[i] = (u32)(excl > 0xFFFFFFFFull ? 0xFFFFFFFFull : excl);
+  if (i == n - 1) { const u64 t = excl + v; out[n] = (u32)(t > 0xFFFFFFFFull ? 0xFFFFFFFFull : t); }
+}
+
+}  // namespace bmbs

@@ -1,0 +1,209 @@
+// Host side of the GPU mapper: takes the per-read records libbmbs_gpu.so returns
+// (include/bmbs.h) and finishes each read the way the reference's worker does after
+// its verification calls -- vote-ordered reduction, pairing, CIGAR, MAPQ, SAM text.
+//
+//   single end  Schema.cpp:27527-27751 (decision), :7847-8056 / :8325-8745 (reduction in std::sort order)
+//   paired end  Schema.cpp:22014-22382 (Map_Pair_Seq_split_fast after get_candidates + filter_pairs),
+//               :7502-7608 (hit compaction), :16186-16288 (single-side filter), :15773-15959 (pair pick)
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "../../../include/bmbs.h"
+#include "fastq.hpp"
+#include "postprocess.hpp"
+#include "sam.hpp"
+
+namespace bmbs {
+
+struct HostHit { uint64_t site; uint64_t vote; uint32_t err; uint64_t end_site; };  // 32 bytes, the reference's seed_votes shape
+
+inline void unpack_cands(const bmbs_cand* c, uint32_t n, std::vector<HostHit>& v) {
+  v.resize(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    v[i].site = c[i].site; v[i].vote = c[i].vote;
+    v[i].err = c[i].err == 0xFFFF ? 0xFFFFFFFFu : c[i].err;
+    v[i].end_site = (uint64_t)(int64_t)c[i].end_site;
+  }
+}
+
+struct ReadView { const std::string* name; const std::string* seq; const std::string* qual; };
+
+struct HostContext {
+  ChromTable chroms;
+  Genome2bit genome;
+  Scoring sc;
+  bmbs_params prm;
+};
+
+inline uint64_t threshold_k(double e_rate, size_t L) { uint64_t k = (uint64_t)(e_rate * L); return k >= 31 ? 31 : k; }
+
+// ---- single end -------------------------------------------------------------------------------
+inline void finish_single(const HostContext& hc, const ReadView& rd, const bmbs_read_result& res, const bmbs_cand* cand,
+                          std::string& out, MapStats& st, std::vector<HostHit>& hits, std::vector<char>& win) {
+  const std::string& seq = *rd.seq; const std::string& qual = *rd.qual;
+  const int L = (int)seq.size();
+  const uint64_t k = threshold_k(hc.prm.e_rate, L);
+  ++st.reads;
+  auto emit = [&](uint64_t site, uint64_t end_site, int start_site, unsigned nm, const std::string& cigar, int mapq) -> bool {
+    Placed p = place(hc.chroms, site, (uint64_t)(int64_t)start_site, end_site);
+    if (p.off_chrom) return false;
+    sam_record_se(out, *rd.name, seq, qual, hc.chroms, p, mapq, cigar, nm, p.flag ? revcomp(seq) : std::string());
+    return true;
+  };
+  switch (res.state) {
+    case BMBS_EXACT_UNIQUE:
+      if (emit(res.site, L - 1, 0, 0, std::to_string(L) + "M", 42)) { ++st.unique; st.bases += L; }
+      return;
+    case BMBS_MULTI_EXACT: ++st.ambiguous; return;
+    case BMBS_ONE_MISMATCH: {
+      const int pos = res.one_mismatch_pos;
+      int score = 0;
+      if (seq[pos] == 'N') score -= hc.sc.n_pen; else score -= mismatch_penalty(hc.sc, qual[pos]);
+      const int mapq = mapq_from(0xFFFFFFFFu, (unsigned)k, score, hc.sc);
+      if (emit(res.site, L - 1, 0, 1, std::to_string(L) + "M", mapq)) { ++st.unique; st.bases += L; st.err_bases += 1; }
+      return;
+    }
+    case BMBS_VERIFY: break;
+    default: return;
+  }
+  unpack_cands(cand + res.first_cand, res.n_cand, hits);
+  // the reference reduces in the order its (unstable) std::sort by vote leaves; the same call on the same
+  // site-ordered array reproduces that order (Schema.cpp:27612, comparator :560-563)
+  std::sort(hits.begin(), hits.end(), [](const HostHit& a, const HostHit& b) { return a.vote > b.vote; });
+  uint32_t min_err = 0xFFFFFFFEu, sbd = 0; int idx = -1; uint64_t best_end = ~0ull;
+  const bool early = res.is_multiple_map != 0;
+  for (size_t i = 0; i < hits.size(); ++i) {
+    const uint32_t e = hits[i].err; const uint64_t end_abs = hits[i].site + hits[i].end_site;
+    if (!early) {
+      if (e == min_err && best_end != end_abs && idx >= 0) { sbd = 0; idx = -2 - idx; }
+      else if (e < min_err) { sbd = min_err - e; min_err = e; idx = (int)i; best_end = end_abs; }
+    } else {
+      if (e == min_err && best_end != end_abs) { sbd = 0; if (idx >= 0) idx = -2 - idx; if (min_err == 0) break; }
+      else if (e < min_err) { sbd = min_err - e; min_err = e; idx = (int)i; best_end = end_abs; }
+    }
+  }
+  if (idx <= -2) { ++st.ambiguous; return; }
+  if (idx < 0) return;
+  const HostHit& b = hits[idx];
+  Refined rf;
+  if (b.err != 0) {
+    const int plen = L + 2 * (int)k; win.resize(plen + 8);
+    hc.genome.window(b.site, plen, win.data());
+    refine_alignment(win.data(), plen, seq.c_str(), L, (int)k, (int)b.end_site, b.err, b.site < hc.chroms.N, qual.c_str(), false, hc.sc, rf);
+  } else { rf.score = 0; rf.start_site = (int)b.end_site - L + 1; rf.end_site = b.end_site; rf.err = 0; rf.cigar = std::to_string(L) + "M"; }
+  const int mapq = mapq_from(sbd, (unsigned)k, rf.score, hc.sc);
+  if (emit(b.site, rf.end_site, rf.start_site, rf.err, rf.cigar, mapq)) { ++st.unique; st.bases += L; st.err_bases += rf.err; }
+}
+
+// ---- paired end -------------------------------------------------------------------------------
+namespace pe {
+// keep hits (err <= k) whose absolute end differs from the candidate right before them
+inline int keep_hits(std::vector<HostHit>& v, uint64_t k) {
+  int kept = 0; uint64_t prev = ~0ull;
+  for (size_t i = 0; i < v.size(); ++i) {
+    const uint64_t end_abs = v[i].site + v[i].end_site;
+    if (v[i].err <= k && prev != end_abs) { v[kept].site = v[i].site; v[kept].err = v[i].err; v[kept].end_site = v[i].end_site; ++kept; }
+    prev = end_abs;
+  }
+  return kept;
+}
+inline bool in_range(uint64_t a, uint64_t b, int dmax, int dmin, long long j, long long& first, bool& stop) {
+  stop = false;
+  if (a > b) { const long long d = (long long)(a - b); if (d > dmax) { first = j + 1; return false; } return d >= dmin; }
+  const long long d = (long long)(b - a);
+  if (d > dmax) { stop = true; return false; }
+  return d >= dmin;
+}
+inline void single_side(const std::vector<HostHit>& a, int na, std::vector<HostHit>& b, int dmax, int dmin) {
+  long long first = 0; size_t kept = 0;
+  for (long long i = 0; i < na; ++i)
+    for (long long j = first; j < (long long)b.size(); ++j) {
+      bool stop; const bool in = in_range(a[i].site, b[j].site, dmax, dmin, j, first, stop);
+      if (stop) break;
+      if (in) { b[kept].site = b[j].site; b[kept].err = b[j].err; b[kept].end_site = b[j].end_site; ++kept; first = j + 1; }
+    }
+  b.resize(na > 0 ? kept : 0);
+}
+struct Pick { int n = 0; long long i1 = 0, i2 = 0; uint32_t sbd = 0; };
+inline Pick pick(const std::vector<HostHit>& a, int na, const std::vector<HostHit>& b, int nb, int k_large, int dmax, int dmin) {
+  Pick r; int best = 4 * k_large + 2; long long second = 2LL * best, first = 0;
+  if (na > 0 && nb > 0)
+    for (int i = 0; i < na; ++i)
+      for (int j = (int)first; j < nb; ++j) {
+        bool stop; const bool in = in_range(a[i].site, b[j].site, dmax, dmin, j, first, stop);
+        if (stop) break;
+        if (!in) continue;
+        const long long sum = (long long)a[i].err + b[j].err;
+        if (sum < best) { second = best; best = (int)sum; r.i1 = i; r.i2 = j; r.n = 1; }
+        else if (sum == best) { second = best; ++r.n; if (best == 0) { r.sbd = 0; return r; } }
+      }
+  if (r.n) r.sbd = (uint32_t)(second - best);
+  return r;
+}
+struct Mate { int flag = 0; size_t chrom = 0; uint64_t pos = 0; unsigned err = 0; int score = 0, span = 0; std::string cigar; };
+inline void finish_mate(const HostContext& hc, const std::string& seq, const std::string& qual, uint64_t k, const HostHit& h,
+                        bool reverse_quality, Mate& m, std::vector<char>& win) {
+  const int L = (int)seq.size();
+  int start; uint64_t end = h.end_site;
+  m.err = h.err;
+  if (h.err != 0) {
+    const int plen = L + 2 * (int)k; win.resize(plen + 8);
+    hc.genome.window(h.site, plen, win.data());
+    Refined rf;
+    refine_alignment(win.data(), plen, seq.c_str(), L, (int)k, (int)h.end_site, h.err, h.site < hc.chroms.N, qual.c_str(), reverse_quality, hc.sc, rf);
+    end = rf.end_site; m.err = rf.err; m.score = rf.score; m.cigar = rf.cigar; start = rf.start_site;
+    m.span = (int)(end - start + 1);
+  } else { m.score = 0; start = (int)(h.end_site + 1 - L); m.cigar = std::to_string(L) + "M"; m.span = L; }
+  const Placed p = place(hc.chroms, h.site, (uint64_t)(int64_t)start, end);
+  m.flag = p.flag; m.chrom = p.chrom; m.pos = p.pos;
+}
+}  // namespace pe
+
+// seq2 is mate 2 as aligned (reverse complement of the FASTQ record `raw2`), qual2 in FASTQ order.
+inline void finish_pair(const HostContext& hc, const std::string& name1, const std::string& seq1, const std::string& qual1,
+                        const std::string& name2, const std::string& seq2, const std::string& raw2, const std::string& qual2,
+                        const bmbs_read_result& r1, const bmbs_read_result& r2, const bmbs_cand* cand,
+                        std::string& out, MapStats& st, std::vector<HostHit>& v1, std::vector<HostHit>& v2, std::vector<char>& win) {
+  ++st.reads;
+  const int L1 = (int)seq1.size(), L2 = (int)seq2.size();
+  const uint64_t k1 = threshold_k(hc.prm.e_rate, L1), k2 = threshold_k(hc.prm.e_rate, L2), kl = k1 > k2 ? k1 : k2;
+  const int dmax = (int)((uint64_t)(long long)hc.prm.max_ins + kl * 2);
+  const int dmin = (int)((uint64_t)(long long)hc.prm.min_ins - kl * 2 - (uint64_t)(L1 > L2 ? L1 : L2));
+  auto resolved = [](const bmbs_read_result& r) { return r.state == BMBS_EXACT_UNIQUE || r.state == BMBS_MULTI_EXACT || r.state == BMBS_ONE_MISMATCH; };
+  const bool res1 = resolved(r1), res2 = resolved(r2);
+  if (r1.n_cand == 0 || r2.n_cand == 0) return;           // a mate without candidates, or nothing survived the distance filter
+  unpack_cands(cand + r1.first_cand, r1.n_cand, v1);
+  unpack_cands(cand + r2.first_cand, r2.n_cand, v2);
+  int occ1, occ2;
+  if (res1 && res2) { occ1 = (int)v1.size(); occ2 = (int)v2.size(); }
+  else if (!res1 && !res2) {
+    if (v1.size() <= v2.size()) {
+      occ1 = pe::keep_hits(v1, k1); if (occ1 == 0) return;
+      pe::single_side(v1, occ1, v2, dmax, dmin);
+      occ2 = pe::keep_hits(v2, k2);
+    } else {
+      occ2 = pe::keep_hits(v2, k2); if (occ2 == 0) return;
+      pe::single_side(v2, occ2, v1, dmax, dmin);
+      occ1 = pe::keep_hits(v1, k1);
+    }
+  } else if (res1) { occ1 = (int)v1.size(); occ2 = pe::keep_hits(v2, k2); }
+  else { occ2 = (int)v2.size(); occ1 = pe::keep_hits(v1, k1); }
+  const pe::Pick pk = pe::pick(v1, occ1, v2, occ2, (int)kl, dmax, dmin);
+  if (pk.n > 1) { ++st.ambiguous; return; }
+  if (pk.n != 1) return;
+  pe::Mate m1, m2;
+  pe::finish_mate(hc, seq1, qual1, k1, v1[pk.i1], false, m1, win);
+  pe::finish_mate(hc, seq2, qual2, k2, v2[pk.i2], true, m2, win);
+  long long lo = (long long)std::min(m1.pos, m2.pos), hi = std::max((long long)m1.pos + m1.span - 1, (long long)m2.pos + m2.span - 1);
+  const int tlen = (int)(hi - lo + 1);                     // calculate_TLEN, Schema.h:1587-1600
+  if (!(tlen <= hc.prm.max_ins && tlen >= hc.prm.min_ins)) return;
+  if (!(m1.pos + m1.span <= hc.chroms.len[m1.chrom] + 1 && m2.pos + m2.span <= hc.chroms.len[m2.chrom] + 1)) return;
+  ++st.unique; st.bases += L1 + L2; st.err_bases += m1.err + m2.err;
+  const int mapq = mapq_from(pk.sbd, (unsigned)(k1 + k2), m1.score + m2.score, hc.sc);
+  sam_record_pe(out, true, name1, seq1, m1.flag ? revcomp(seq1) : std::string(), qual1, hc.chroms, m1.flag, m1.chrom, m1.pos, mapq, m1.cigar, m2.pos, tlen, m1.err);
+  sam_record_pe(out, false, name2, seq2, raw2, qual2, hc.chroms, m2.flag, m2.chrom, m2.pos, mapq, m2.cigar, m1.pos, tlen, m2.err);
+}
+
+}  // namespace bmbs

@@ -1,0 +1,135 @@
+/* bmbs.h -- C ABI of libbmbs_gpu.so: BitMapperBS's seed-and-verify hot path on B200.
+ *
+ * The reference has no plugin/FFI interface; its worker threads call the hot
+ * functions inline over process globals.  Each entry point below names the
+ * reference seam it replaces (file:line into chhylp123/BitMapperBS v1.0.2.3):
+ *
+ *   bmbs_index_load / _free      Start_Load_Index + Load_Index (Index.cpp:1048, :940) and
+ *                                load_index (bwt.cpp:2458): same six on-disk files, read as-is.
+ *   bmbs_map_batch_se            per-read body of Map_Single_Seq_split (Schema.cpp:27077-27752)
+ *                                up to, not including, the vote-ordered reduction and CIGAR:
+ *                                C_to_T_forward (Schema.h:1534), count_backward_as_much_1_terminate
+ *                                (bwt.h:2081), count_hash_table (bwt.h:1848), locate_muti_thread
+ *                                (bwt.cpp:4986) / locate_one_position_direct (bwt.h:2585),
+ *                                try_process_unique_mismatch_end_to_end_output_buffer
+ *                                (Schema.cpp:15410), std::sort + generate_candidate_votes_shift
+ *                                (Schema.cpp:27599, :4687), get_actuall_genome/_rc_genome
+ *                                (Schema.cpp:4998, :5061) + BS_Reserve_Banded_BPM{,_4_SSE,_8_SSE}
+ *                                (Levenshtein_Cal.h:351, :1678, :2093).
+ *   bmbs_map_batch_pe            the same for Map_Pair_Seq_split_fast (Schema.cpp:21856-22382):
+ *                                get_candidates_muti_thread (:19550) for both mates, filter_pairs
+ *                                (:16052) and verification of every surviving candidate.
+ *   bmbs_verify                  BS_Reserve_Banded_BPM over caller-supplied (read, site) pairs.
+ *
+ * Conventions: plain pointers and sizes, caller-owned in/out buffers (pinned
+ * host memory makes the copies faster but is not required), library-owned device
+ * memory and streams.  Every function returns 0 on success and a negative code
+ * on failure with a message in bmbs_last_error(); nothing calls exit().  One
+ * host thread per device may be inside the library at a time; the index handle
+ * is immutable after load.
+ */
+#ifndef BMBS_H
+#define BMBS_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BMBS_OK 0
+#define BMBS_ERR_IO (-1)        /* index file missing / short                      */
+#define BMBS_ERR_CUDA (-2)      /* CUDA runtime error                              */
+#define BMBS_ERR_ARG (-3)       /* bad argument                                    */
+#define BMBS_ERR_CAPACITY (-4)  /* caller's output buffer too small; see *_used    */
+
+typedef struct bmbs_index bmbs_index; /* opaque: host metadata + one device copy per GPU */
+typedef struct bmbs_batch bmbs_batch; /* opaque: device + pinned staging for one in-flight batch */
+
+/* index_prefix is "<genome.fa>.index" (the name Load_Index opens); devices==NULL means device 0. */
+int bmbs_index_load(const char* index_prefix, const int* devices, int n_dev, bmbs_index** out);
+void bmbs_index_free(bmbs_index* idx);
+uint64_t bmbs_index_genome_length(const bmbs_index* idx);   /* N, bases               */
+uint64_t bmbs_index_device_bytes(const bmbs_index* idx);    /* resident HBM per GPU   */
+const char* bmbs_last_error(void);
+
+typedef struct {
+  double e_rate;      /* -e, default 0.08 (Process_CommandLines.cpp:40)            */
+  int seed_len;       /* --seed, default 30                                        */
+  int min_ins;        /* --min, default 0                                          */
+  int max_ins;        /* --max, default 500                                        */
+  int sensitive;      /* 0 = --fast (default); 1 = --sensitive (not yet on GPU)    */
+} bmbs_params;
+void bmbs_params_default(bmbs_params* p);
+
+/* What seeding decided for one read (one mate). */
+enum {
+  BMBS_NONE = 0,          /* no candidate at all (unmapped)                                        */
+  BMBS_EXACT_UNIQUE = 1,  /* unique first seed + error-free direct compare: site, NM 0, CIGAR <L>M */
+  BMBS_MULTI_EXACT = 2,   /* whole read matches >1 rows and has no C: SE counts it ambiguous;
+                             PE lists all sites as finished hits in cand[]                         */
+  BMBS_ONE_MISMATCH = 3,  /* unique hit with exactly one mismatch: site, NM 1, CIGAR <L>M          */
+  BMBS_VERIFY = 4         /* cand[] holds the site-sorted windows, each verified                   */
+};
+typedef struct {
+  uint64_t site;            /* states 1 and 3: double-strand coordinate of the read start        */
+  uint32_t first_cand;      /* slice of cand[]                                                   */
+  uint32_t n_cand;
+  int16_t one_mismatch_pos; /* state 3: read index of the mismatch (Schema.cpp:27203)            */
+  uint8_t state;
+  uint8_t is_multiple_map;  /* first seed was a full-length multi-hit (selects the reduction
+                               variant, Schema.cpp:27617-27672)                                   */
+  uint32_t reserved;
+} bmbs_read_result;         /* 24 bytes */
+
+/* One candidate window [site, site+L+2k) and its verification. */
+typedef struct {
+  uint64_t site;      /* window start, double-strand coordinate ([0,N) fwd, [N,2N) rc); wraps mod 2^64 like the reference */
+  uint32_t vote;      /* number of seeds that voted for it                                           */
+  int16_t end_site;   /* last window position of the best alignment, -1 if none within k              */
+  uint16_t err;       /* edit distance, 0xFFFF if none within k                                       */
+} bmbs_cand;          /* 16 bytes */
+
+/* ---- one-call form (host buffers in, host buffers out) -------------------------------------------
+ * seqs: concatenated upper-case ASCII reads; read i is seqs[offsets[i] .. offsets[i+1]).
+ * For pairs, reads 2p and 2p+1 are the mates, mate 2 already reverse-complemented
+ * (what Process_Reads.cpp:359-369 stores in Read::seq).
+ * res[n_reads]; cand[cand_cap]; *cand_used receives the number of entries written (or needed,
+ * with BMBS_ERR_CAPACITY). */
+int bmbs_map_batch_se(bmbs_index* idx, int dev, const char* seqs, const uint64_t* offsets, int n_reads,
+                      const bmbs_params* prm, bmbs_read_result* res, bmbs_cand* cand, size_t cand_cap,
+                      size_t* cand_used);
+int bmbs_map_batch_pe(bmbs_index* idx, int dev, const char* seqs, const uint64_t* offsets, int n_pairs,
+                      const bmbs_params* prm, bmbs_read_result* res, bmbs_cand* cand, size_t cand_cap,
+                      size_t* cand_used);
+
+/* Kernel-3 only: verify n (read, site) pairs.  read_idx[i] selects the read, sites[i] the window
+ * start; k = min(31, (uint64)(e_rate*L)) per read.  Writes end_site[i], err[i] (0xFFFFFFFF = none). */
+int bmbs_verify(bmbs_index* idx, int dev, const char* seqs, const uint64_t* offsets, int n_reads,
+                const uint32_t* read_idx, const uint64_t* sites, size_t n, double e_rate,
+                int32_t* end_site, uint32_t* err);
+
+/* ---- staged form (what the mapper and bench.py drive; lets copies overlap kernels) --------------- */
+int bmbs_batch_create(bmbs_index* idx, int dev, size_t max_reads, size_t max_bases, size_t cand_cap, bmbs_batch** out);
+void bmbs_batch_free(bmbs_batch* b);
+/* async H2D of the reads into the batch's device buffers (pe: reads come in mate pairs) */
+int bmbs_batch_upload(bmbs_batch* b, const char* seqs, const uint64_t* offsets, int n_reads, int pe);
+/* enqueue the device pipeline on the batch stream; inputs must have been uploaded */
+int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm);
+/* async D2H of results into the caller's buffers, then wait; returns BMBS_ERR_CAPACITY like above */
+int bmbs_batch_download(bmbs_batch* b, bmbs_read_result* res, bmbs_cand* cand, size_t cand_cap, size_t* cand_used);
+int bmbs_batch_sync(bmbs_batch* b);
+/* device time of the last bmbs_batch_run in ms (CUDA events on the batch stream), per stage:
+ * [0] total [1] pack [2] seed [3] locate [4] votes [5] pair filter [6] verify */
+int bmbs_batch_timings(bmbs_batch* b, float ms[8]);
+/* work counters of the last run, for roofline accounting:
+ * [0] hash queries [1] occ-block lookups (one interval end, one LF step) [2] located rows
+ * [3] locate LF steps [4] verified candidates [5] verified cell updates L*(2k+1) [6] candidates
+ * [7] genome-window bytes fetched */
+int bmbs_batch_counters(bmbs_batch* b, uint64_t c[8]);
+/* number of kernels launched by the last bmbs_batch_run */
+int bmbs_batch_launches(bmbs_batch* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

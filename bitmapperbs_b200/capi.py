@@ -1,0 +1,207 @@
+"""ctypes binding of include/bmbs.h (same names, same argument meaning, same error behaviour)."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+NONE, EXACT_UNIQUE, MULTI_EXACT, ONE_MISMATCH, VERIFY = 0, 1, 2, 3, 4
+
+# numpy views of the C structs
+ReadResult = np.dtype([("site", "<u8"), ("first_cand", "<u4"), ("n_cand", "<u4"), ("one_mismatch_pos", "<i2"),
+                       ("state", "u1"), ("is_multiple_map", "u1"), ("reserved", "<u4")])
+Cand = np.dtype([("site", "<u8"), ("vote", "<u4"), ("end_site", "<i2"), ("err", "<u2")])
+assert ReadResult.itemsize == 24 and Cand.itemsize == 16
+
+
+class Params(C.Structure):
+    _fields_ = [("e_rate", C.c_double), ("seed_len", C.c_int), ("min_ins", C.c_int), ("max_ins", C.c_int), ("sensitive", C.c_int)]
+
+
+class BmbsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"bmbs error {code}: {msg}")
+        self.code = code
+
+
+def lib_path() -> Path:
+    return Path(__file__).resolve().parent / "libbmbs_gpu.so"
+
+
+_lib = None
+
+EXPORTS = ["bmbs_index_load", "bmbs_index_free", "bmbs_index_genome_length", "bmbs_index_device_bytes", "bmbs_last_error",
+           "bmbs_params_default", "bmbs_map_batch_se", "bmbs_map_batch_pe", "bmbs_verify", "bmbs_batch_create", "bmbs_batch_free",
+           "bmbs_batch_upload", "bmbs_batch_run", "bmbs_batch_download", "bmbs_batch_sync", "bmbs_batch_timings",
+           "bmbs_batch_counters", "bmbs_batch_launches"]
+
+
+def load_library():
+    """dlopen libbmbs_gpu.so; raises (no fallback) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not p.exists():
+        raise BmbsError(-1, f"{p} is missing: build it with `python -m bitmapperbs_b200.build` (nvcc, sm_100a); there is no CPU fallback")
+    L = C.CDLL(str(p))
+    vp, u64p = C.c_void_p, C.POINTER(C.c_uint64)
+    L.bmbs_last_error.restype = C.c_char_p
+    L.bmbs_index_load.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    L.bmbs_index_free.argtypes = [vp]
+    L.bmbs_index_genome_length.argtypes = [vp]; L.bmbs_index_genome_length.restype = C.c_uint64
+    L.bmbs_index_device_bytes.argtypes = [vp]; L.bmbs_index_device_bytes.restype = C.c_uint64
+    L.bmbs_params_default.argtypes = [C.POINTER(Params)]
+    for f in (L.bmbs_map_batch_se, L.bmbs_map_batch_pe):
+        f.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.POINTER(Params), vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.bmbs_verify.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_size_t, C.c_double, vp, vp]
+    L.bmbs_batch_create.argtypes = [vp, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(vp)]
+    L.bmbs_batch_free.argtypes = [vp]
+    L.bmbs_batch_upload.argtypes = [vp, vp, vp, C.c_int, C.c_int]
+    L.bmbs_batch_run.argtypes = [vp, C.POINTER(Params)]
+    L.bmbs_batch_download.argtypes = [vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.bmbs_batch_sync.argtypes = [vp]
+    L.bmbs_batch_timings.argtypes = [vp, C.POINTER(C.c_float)]
+    L.bmbs_batch_counters.argtypes = [vp, u64p]
+    L.bmbs_batch_launches.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise BmbsError(rc, load_library().bmbs_last_error().decode(errors="replace"))
+
+
+def default_params(**kw) -> Params:
+    p = Params()
+    load_library().bmbs_params_default(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def flatten(reads):
+    """list of bytes -> (uint8 array, uint64 offsets)"""
+    offs = np.zeros(len(reads) + 1, dtype=np.uint64)
+    if reads:
+        offs[1:] = np.cumsum([len(r) for r in reads], dtype=np.uint64)
+    flat = np.frombuffer(b"".join(reads), dtype=np.uint8).copy() if reads else np.zeros(0, dtype=np.uint8)
+    return flat, offs
+
+
+class Index:
+    """bmbs_index_load / bmbs_index_free (replaces Start_Load_Index + Load_Index + load_index)."""
+
+    def __init__(self, index_prefix: str, devices=(0,)):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        _check(self._L.bmbs_index_load(str(index_prefix).encode(), devs, len(devices), C.byref(self._h)))
+        self.devices = tuple(devices)
+
+    @property
+    def genome_length(self):
+        return int(self._L.bmbs_index_genome_length(self._h))
+
+    @property
+    def device_bytes(self):
+        return int(self._L.bmbs_index_device_bytes(self._h))
+
+    def close(self):
+        if self._h:
+            self._L.bmbs_index_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # one-call forms -------------------------------------------------------------------------
+    def _map(self, fn, reads, n_units, params, dev, cand_cap):
+        flat, offs = reads if isinstance(reads, tuple) else flatten(reads)
+        n_reads = len(offs) - 1
+        params = params or default_params()
+        cand_cap = cand_cap or max(1 << 16, 32 * n_reads)
+        while True:
+            res = np.zeros(n_reads, dtype=ReadResult)
+            cand = np.zeros(cand_cap, dtype=Cand)
+            used = C.c_size_t(0)
+            rc = fn(self._h, dev, flat.ctypes.data, offs.ctypes.data, n_units, C.byref(params), res.ctypes.data, cand.ctypes.data, cand_cap, C.byref(used))
+            if rc == -4 and used.value > cand_cap:
+                cand_cap = int(used.value * 1.25) + 1024
+                continue
+            _check(rc)
+            return res, cand[: used.value]
+
+    def map_batch_se(self, reads, params=None, dev=0, cand_cap=None):
+        n = (len(reads[1]) - 1) if isinstance(reads, tuple) else len(reads)
+        return self._map(self._L.bmbs_map_batch_se, reads, n, params, dev, cand_cap)
+
+    def map_batch_pe(self, mates, params=None, dev=0, cand_cap=None):
+        """mates: [mate1_0, mate2_0(revcomp), mate1_1, ...]"""
+        n = (len(mates[1]) - 1) if isinstance(mates, tuple) else len(mates)
+        return self._map(self._L.bmbs_map_batch_pe, mates, n // 2, params, dev, cand_cap)
+
+    def verify(self, reads, read_idx, sites, e_rate=0.08, dev=0):
+        flat, offs = reads if isinstance(reads, tuple) else flatten(reads)
+        read_idx = np.ascontiguousarray(read_idx, dtype=np.uint32)
+        sites = np.ascontiguousarray(sites, dtype=np.uint64)
+        n = len(sites)
+        end = np.zeros(n, dtype=np.int32); err = np.zeros(n, dtype=np.uint32)
+        _check(self._L.bmbs_verify(self._h, dev, flat.ctypes.data, offs.ctypes.data, len(offs) - 1, read_idx.ctypes.data, sites.ctypes.data, n,
+                                   e_rate, end.ctypes.data, err.ctypes.data))
+        return end, err
+
+
+class Batch:
+    """Staged form: upload / run / download with device timings and work counters."""
+
+    def __init__(self, index: Index, dev, max_reads, max_bases, cand_cap):
+        self._L = load_library(); self._h = C.c_void_p(); self.index = index
+        _check(self._L.bmbs_batch_create(index._h, dev, max_reads, max_bases, cand_cap, C.byref(self._h)))
+        self.cand_cap = cand_cap; self.n_reads = 0
+
+    def upload(self, flat, offs, pe=False):
+        self.n_reads = len(offs) - 1
+        _check(self._L.bmbs_batch_upload(self._h, flat.ctypes.data, offs.ctypes.data, self.n_reads, 1 if pe else 0))
+
+    def run(self, params):
+        _check(self._L.bmbs_batch_run(self._h, C.byref(params)))
+
+    def sync(self):
+        _check(self._L.bmbs_batch_sync(self._h))
+
+    def download(self, res=None, cand=None):
+        res = np.zeros(self.n_reads, dtype=ReadResult) if res is None else res
+        cand = np.zeros(self.cand_cap, dtype=Cand) if cand is None else cand
+        used = C.c_size_t(0)
+        _check(self._L.bmbs_batch_download(self._h, res.ctypes.data, cand.ctypes.data, len(cand), C.byref(used)))
+        return res, cand, used.value
+
+    def timings(self):
+        ms = (C.c_float * 8)()
+        _check(self._L.bmbs_batch_timings(self._h, ms))
+        return dict(zip(["total", "pack", "seed", "locate", "votes", "pair_filter", "verify"], list(ms)[:7]))
+
+    def counters(self):
+        c = (C.c_uint64 * 8)()
+        _check(self._L.bmbs_batch_counters(self._h, c))
+        return dict(zip(["hash_queries", "occ_lookups", "located_rows", "locate_lf_steps", "verified", "cells", "candidates", "window_bytes"], [int(x) for x in c]))
+
+    def launches(self):
+        return int(self._L.bmbs_batch_launches(self._h))
+
+    def close(self):
+        if self._h:
+            self._L.bmbs_batch_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

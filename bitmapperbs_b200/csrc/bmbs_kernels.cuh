@@ -277,11 +277,11 @@ __global__ void __launch_bounds__(256) locate_rows(DevIndex ix, BatchView b) {
 // Returns true when the segment still has to be sorted/encoded.
 __device__ __forceinline__ bool classify_read(BatchView& b, int r, u32 beg, u32 n, bool lane0) {
   const int st = b.state[r];
-  if (st == BMBS_EXACT_UNIQUE) { if (lane0) b.nv[r] = b.pe ? 1u : 0u; return false; }
+  if (st == BMBS_EXACT_UNIQUE) { if (lane0) { b.nv[r] = b.pe ? 1u : 0u; if (n) b.vcnt[beg] = 0; } return false; }
   if (st == BMBS_MULTI_EXACT) { if (!b.pe) { if (lane0) b.nv[r] = 0; return false; } return true; }
   if (n == 0) { if (lane0) b.nv[r] = 0; return false; }
   if ((b.flags[r] & 2) && (n == 1 || (n == 2 && b.cand[beg] == b.cand[beg + 1]))) {
-    if (lane0) { b.state[r] = BMBS_ONE_MISMATCH; b.site0[r] = b.cand[beg]; b.nv[r] = b.pe ? 1u : 0u; }
+    if (lane0) { b.state[r] = BMBS_ONE_MISMATCH; b.site0[r] = b.cand[beg]; b.nv[r] = b.pe ? 1u : 0u; b.vcnt[beg] = 0; }
     return false;
   }
   if (lane0) b.state[r] = BMBS_VERIFY;

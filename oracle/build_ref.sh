@@ -4,6 +4,7 @@
 #
 #   oracle/_ref/bitmapperBS  the reference CLI (SE / PE / PE --sensitive, SAM text)
 #   oracle/_ref/psascan      suffix-sorter stand-in the reference shells out to in --index
+#   oracle/_ref/libref_bpm.so, libref_fm.so   C entry points into the reference's own BPM / FM-index functions
 #
 # Nothing from /root/reference is copied into the repo: sources are copied to a
 # scratch dir under /tmp, the 43 missing-`return` sites (UB that crashes an -O3
@@ -19,7 +20,7 @@ REF="${BMBS_REFERENCE:-/root/reference}"
 OUT="$HERE/_ref"
 [ -d "$REF" ] || { echo "build_ref: $REF absent (GPU box?) - keeping prebuilt $OUT" >&2; exit 0; }
 mkdir -p "$OUT"
-if [ -x "$OUT/bitmapperBS" ] && [ -x "$OUT/psascan" ] && [ "${1:-}" != "--force" ]; then
+if [ -x "$OUT/bitmapperBS" ] && [ -x "$OUT/psascan" ] && [ -f "$OUT/libref_bpm.so" ] && [ -f "$OUT/libref_fm.so" ] && [ "${1:-}" != "--force" ]; then
   echo "build_ref: $OUT up to date"; exit 0
 fi
 TMP="$(mktemp -d /tmp/bmbs_refbuild.XXXXXX)"
@@ -34,4 +35,7 @@ gcc -c -O1 "$HERE/hts_stub.c" -o "$TMP/hts_stub.o"
     hts_stub.o -o bitmapperBS -lm -lz -lpthread )
 cp "$TMP/bitmapperBS" "$OUT/bitmapperBS"
 g++ -O2 -std=c++17 -pthread "$HERE/psascan_shim.cpp" -o "$OUT/psascan"
-echo "build_ref: built $OUT/bitmapperBS and $OUT/psascan"
+# function-level harnesses over the reference's own headers / sources
+g++ -w -O2 -mavx2 -mpopcnt -D__AVX2__ -shared -fPIC -I "$REF" "$HERE/ref_harness_bpm.cpp" -o "$OUT/libref_bpm.so"
+( cd "$TMP" && g++ -w -O2 -mpopcnt -shared -fPIC -I "$TMP" "$HERE/ref_harness_fm.cpp" bwt.cpp saca-k.cpp -o "$OUT/libref_fm.so" )
+echo "build_ref: built $OUT/{bitmapperBS,psascan,libref_bpm.so,libref_fm.so}"

@@ -1,0 +1,112 @@
+// oracle/oracle_capi.cpp -- TEST INFRASTRUCTURE: C entry points (ctypes) into the CPU restatement, shaped like
+// include/bmbs.h so that tests can compare the CUDA path record by record.  Never linked by the product.
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+#include "oracle_core.hpp"
+#include "oracle_pe.hpp"
+#include "../include/bmbs.h"
+
+using namespace oracle;
+
+extern "C" {
+
+void* orc_load(const char* prefix) { Index* ix = new Index(); if (!ix->load(prefix)) { delete ix; return nullptr; } return ix; }
+void orc_free(void* h) { delete (Index*)h; }
+uint64_t orc_genome_length(void* h) { return ((Index*)h)->N; }
+
+int orc_bpm(const char* win, const char* read, int L, unsigned k, uint32_t* err) { return banded_bs_edit(win, read, L, k, *err); }
+void orc_window(void* h, uint64_t site, uint64_t len, char* out) { ((Index*)h)->genome.window(site, len, out); }
+uint64_t orc_lf(void* h, uint64_t row, int c) { return ((Index*)h)->lf(row, c); }
+int orc_locate(void* h, uint64_t row, uint64_t* sa) { return ((Index*)h)->locate_row(row, *sa) ? 1 : 0; }
+uint64_t orc_seed(void* h, const char* pat, uint64_t len, uint64_t* sp, uint64_t* ep, uint64_t* mlen) {
+  SeedHit r = seed_until_unique(*(Index*)h, pat, len, *sp, *ep); *mlen = r.mlen; return r.hits;
+}
+uint64_t orc_count(void* h, const char* pat, uint64_t len, uint64_t* sp, uint64_t* ep) { return count_exact(*(Index*)h, pat, len, *sp, *ep); }
+
+static void put(bmbs_cand& o, const Vote& v) {
+  o.site = v.site; o.vote = (uint32_t)v.vote; o.end_site = (int16_t)(int64_t)v.end_site; o.err = v.err == 0xFFFFFFFFu ? 0xFFFF : (uint16_t)v.err;
+}
+
+// Same record layout and semantics as bmbs_map_batch_se.
+int orc_map_se(void* h, const char* seqs, const uint64_t* offs, int n, double e_rate, int seed_len, bmbs_read_result* res, bmbs_cand* cand,
+               size_t cap, size_t* used) {
+  const Index& ix = *(Index*)h; Params P; P.e_rate = e_rate; P.seed_len = seed_len;
+  size_t w = 0; std::vector<char> win;
+  for (int r = 0; r < n; ++r) {
+    const char* read = seqs + offs[r]; const int L = (int)(offs[r + 1] - offs[r]);
+    const u64 k = u64_k(e_rate, L);
+    SeedTrace t; std::string rd(read, L); seed_read(ix, P, rd.c_str(), L, t);
+    bmbs_read_result& o = res[r]; memset(&o, 0, sizeof o);
+    o.first_cand = (uint32_t)w; o.is_multiple_map = t.is_multi; o.one_mismatch_pos = (int16_t)t.one_mismatch_site;
+    if (t.exact_unique) { o.state = BMBS_EXACT_UNIQUE; o.site = t.cand[0]; continue; }
+    if (t.multi_exact_noC) { o.state = BMBS_MULTI_EXACT; continue; }
+    if (t.cand.empty()) { o.state = BMBS_NONE; continue; }
+    if (!t.extra && (t.cand.size() == 1 || (t.cand.size() == 2 && t.cand[0] == t.cand[1]))) { o.state = BMBS_ONE_MISMATCH; o.site = t.cand[0]; continue; }
+    o.state = BMBS_VERIFY;
+    std::vector<u64> c = t.cand; std::sort(c.begin(), c.end());
+    std::vector<Vote> v; votes_from_sorted(c, k, v);
+    o.n_cand = (uint32_t)v.size();
+    for (auto& x : v) { verify_one(ix, rd.c_str(), L, k, x, win); if (w < cap) put(cand[w], x); ++w; }
+  }
+  *used = w;
+  return w <= cap ? 0 : BMBS_ERR_CAPACITY;
+}
+
+// Same record layout and semantics as bmbs_map_batch_pe: lists after the pair distance filter, every
+// unresolved entry verified.
+int orc_map_pe(void* h, const char* seqs, const uint64_t* offs, int n_pairs, double e_rate, int seed_len, int min_ins, int max_ins,
+               bmbs_read_result* res, bmbs_cand* cand, size_t cap, size_t* used) {
+  const Index& ix = *(Index*)h; Params P; P.e_rate = e_rate; P.seed_len = seed_len; P.min_ins = min_ins; P.max_ins = max_ins;
+  size_t w = 0; std::vector<char> win;
+  for (int p = 0; p < n_pairs; ++p) {
+    MateCands m[2]; std::string rd[2]; int L[2]; u64 k[2];
+    for (int s = 0; s < 2; ++s) {
+      const int r = 2 * p + s; L[s] = (int)(offs[r + 1] - offs[r]); rd[s].assign(seqs + offs[r], L[s]); k[s] = u64_k(e_rate, L[s]);
+      mate_candidates(ix, P, rd[s].c_str(), L[s], k[s], m[s]);
+    }
+    const u64 kl = k[0] > k[1] ? k[0] : k[1];
+    const int dmax = (int)((u64)max_ins + kl * 2), dmin = (int)((u64)min_ins - kl * 2 - (u64)(L[0] > L[1] ? L[0] : L[1]));
+    const bool res0 = m[0].occ > 0, res1 = m[1].occ > 0;
+    if (!(res0 && res1)) {
+      if (m[0].v.empty() || m[1].v.empty()) { m[0].v.clear(); m[1].v.clear(); }
+      else { filter_pairs(m[0].v, m[1].v, dmax, dmin); if (m[0].v.empty() || m[1].v.empty()) { m[0].v.clear(); m[1].v.clear(); } }
+    }
+    for (int s = 0; s < 2; ++s) {
+      bmbs_read_result& o = res[2 * p + s]; memset(&o, 0, sizeof o);
+      const SeedTrace& t = m[s].trace;
+      o.first_cand = (uint32_t)w; o.is_multiple_map = t.is_multi; o.one_mismatch_pos = (int16_t)t.one_mismatch_site;
+      if (t.exact_unique) { o.state = BMBS_EXACT_UNIQUE; o.site = t.cand[0]; }
+      else if (t.multi_exact_noC) o.state = BMBS_MULTI_EXACT;
+      else if (m[s].occ == 1) { o.state = BMBS_ONE_MISMATCH; o.site = t.cand[0]; }
+      else if (m[s].occ == 0) o.state = BMBS_NONE;
+      else o.state = BMBS_VERIFY;
+      o.n_cand = (uint32_t)m[s].v.size();
+      for (auto& x : m[s].v) { if (o.state == BMBS_VERIFY) verify_one(ix, rd[s].c_str(), L[s], k[s], x, win); if (w < cap) put(cand[w], x); ++w; }
+    }
+  }
+  *used = w;
+  return w <= cap ? 0 : BMBS_ERR_CAPACITY;
+}
+
+int orc_verify(void* h, const char* seqs, const uint64_t* offs, int n_reads, const uint32_t* read_idx, const uint64_t* sites, size_t n,
+               double e_rate, int32_t* end_site, uint32_t* err, int threads) {
+  const Index& ix = *(Index*)h;
+  if (threads < 1) threads = 1;
+  auto work = [&](int t) {
+    std::vector<char> win;
+    for (size_t i = t; i < n; i += threads) {
+      const uint32_t r = read_idx[i]; const int L = (int)(offs[r + 1] - offs[r]); const u64 k = u64_k(e_rate, L);
+      std::string rd(seqs + offs[r], L);
+      Vote v{sites[i], 0, 0, 0}; verify_one(ix, rd.c_str(), L, k, v, win);
+      end_site[i] = (int32_t)(int64_t)v.end_site; err[i] = v.err;
+    }
+  };
+  std::vector<std::thread> th; for (int t = 1; t < threads; ++t) th.emplace_back(work, t);
+  work(0); for (auto& x : th) x.join();
+  (void)n_reads;
+  return 0;
+}
+
+}  // extern "C"

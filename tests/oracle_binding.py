@@ -1,0 +1,69 @@
+"""ctypes access to oracle/_build/liboracle.so (the CPU restatement) -- tests only."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from bitmapperbs_b200.capi import Cand, ReadResult, flatten
+
+ROOT = Path(__file__).resolve().parent.parent
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(str(ROOT / "oracle/_build/liboracle.so"))
+        vp = C.c_void_p
+        L.orc_load.restype = vp; L.orc_load.argtypes = [C.c_char_p]
+        L.orc_free.argtypes = [vp]
+        L.orc_genome_length.restype = C.c_uint64; L.orc_genome_length.argtypes = [vp]
+        L.orc_bpm.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_uint, C.POINTER(C.c_uint32)]
+        L.orc_window.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_char_p]
+        L.orc_lf.restype = C.c_uint64; L.orc_lf.argtypes = [vp, C.c_uint64, C.c_int]
+        L.orc_locate.argtypes = [vp, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.orc_seed.restype = C.c_uint64; L.orc_seed.argtypes = [vp, C.c_char_p, C.c_uint64] + [C.POINTER(C.c_uint64)] * 3
+        L.orc_count.restype = C.c_uint64; L.orc_count.argtypes = [vp, C.c_char_p, C.c_uint64] + [C.POINTER(C.c_uint64)] * 2
+        L.orc_map_se.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.orc_map_pe.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.orc_verify.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_size_t, C.c_double, vp, vp, C.c_int]
+        _lib = L
+    return _lib
+
+
+class OracleIndex:
+    def __init__(self, prefix):
+        self.h = lib().orc_load(str(prefix).encode())
+        assert self.h, f"oracle cannot load {prefix}"
+        self.N = lib().orc_genome_length(self.h)
+
+    def window(self, site, n):
+        buf = C.create_string_buffer(n + 8)
+        lib().orc_window(self.h, site, n, buf)
+        return buf.raw[:n]
+
+    def map_se(self, reads, e_rate=0.08, seed_len=30, cap=None):
+        flat, offs = reads if isinstance(reads, tuple) else flatten(reads)
+        n = len(offs) - 1
+        cap = cap or max(1 << 16, 64 * n)
+        res = np.zeros(n, dtype=ReadResult); cand = np.zeros(cap, dtype=Cand); used = C.c_size_t(0)
+        rc = lib().orc_map_se(self.h, flat.ctypes.data, offs.ctypes.data, n, e_rate, seed_len, res.ctypes.data, cand.ctypes.data, cap, C.byref(used))
+        assert rc == 0
+        return res, cand[: used.value]
+
+    def map_pe(self, mates, e_rate=0.08, seed_len=30, min_ins=0, max_ins=500, cap=None):
+        flat, offs = mates if isinstance(mates, tuple) else flatten(mates)
+        n = len(offs) - 1
+        cap = cap or max(1 << 16, 64 * n)
+        res = np.zeros(n, dtype=ReadResult); cand = np.zeros(cap, dtype=Cand); used = C.c_size_t(0)
+        rc = lib().orc_map_pe(self.h, flat.ctypes.data, offs.ctypes.data, n // 2, e_rate, seed_len, min_ins, max_ins, res.ctypes.data, cand.ctypes.data, cap, C.byref(used))
+        assert rc == 0
+        return res, cand[: used.value]
+
+    def verify(self, reads, read_idx, sites, e_rate=0.08, threads=8):
+        flat, offs = reads if isinstance(reads, tuple) else flatten(reads)
+        read_idx = np.ascontiguousarray(read_idx, dtype=np.uint32); sites = np.ascontiguousarray(sites, dtype=np.uint64)
+        n = len(sites)
+        end = np.zeros(n, dtype=np.int32); err = np.zeros(n, dtype=np.uint32)
+        lib().orc_verify(self.h, flat.ctypes.data, offs.ctypes.data, len(offs) - 1, read_idx.ctypes.data, sites.ctypes.data, n, e_rate, end.ctypes.data, err.ctypes.data, threads)
+        return end, err

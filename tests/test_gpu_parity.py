@@ -1,0 +1,201 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle restatement on the same seeded inputs,
+against the committed golden SAM of the real reference, and -- at larger sizes -- through size-independent
+properties.  Integer / index work: everything is compared bit-exactly."""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import bitmapperbs_b200 as B
+from bitmapperbs_b200 import capi, simulate as S
+from conftest import read_fastq, revcomp, sam_body
+from oracle_binding import OracleIndex
+
+pytestmark = pytest.mark.gpu
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+@pytest.fixture(scope="module")
+def gidx(golden):
+    return B.Index(golden / "genome.fa.index")
+
+
+@pytest.fixture(scope="module")
+def oidx(golden):
+    return OracleIndex(golden / "genome.fa.index")
+
+
+def assert_same_records(gres, gcand, ores, ocand, compare_vote=True):
+    for f in ("state", "n_cand", "is_multiple_map"):
+        assert np.array_equal(gres[f], ores[f]), f
+    m = np.isin(gres["state"], [B.EXACT_UNIQUE, B.ONE_MISMATCH])
+    assert np.array_equal(gres["site"][m], ores["site"][m])
+    m3 = gres["state"] == B.ONE_MISMATCH
+    assert np.array_equal(gres["one_mismatch_pos"][m3], ores["one_mismatch_pos"][m3])
+    assert len(gcand) == len(ocand)
+    assert np.array_equal(gres["first_cand"], ores["first_cand"])
+    for f in ("site", "end_site", "err"):
+        assert np.array_equal(gcand[f], ocand[f]), f
+    if compare_vote:
+        assert np.array_equal(gcand["vote"], ocand["vote"])
+
+
+def test_single_end_records_match_oracle(golden, gidx, oidx):
+    reads = [r[1] for r in read_fastq(golden / "se100.fq")] + [r[1] for r in read_fastq(golden / "se250.fq")]
+    gres, gcand = gidx.map_batch_se(reads)
+    ores, ocand = oidx.map_se(reads)
+    assert_same_records(gres, gcand, ores, ocand)
+    assert (gres["state"] == B.VERIFY).sum() > 100 and (gres["state"] == B.EXACT_UNIQUE).sum() > 100
+
+
+def test_paired_end_records_match_oracle(golden, gidx, oidx):
+    m1 = read_fastq(golden / "pe150_1.fq"); m2 = read_fastq(golden / "pe150_2.fq")
+    mates = []
+    for a, b in zip(m1, m2):
+        mates += [a[1], revcomp(b[1])]
+    gres, gcand = gidx.map_batch_pe(mates)
+    ores, ocand = oidx.map_pe(mates)
+    v = np.repeat(gres["state"] == B.VERIFY, gres["n_cand"])
+    assert_same_records(gres, gcand, ores, ocand, compare_vote=False)
+    assert np.array_equal(gcand["vote"][v], ocand["vote"][v])
+
+
+def test_edge_case_reads(golden, gidx, oidx):
+    genome = b"".join(l.strip() for l in open(golden / "genome.fa", "rb") if not l.startswith(b">"))
+    N = len(genome)
+    reads = [
+        b"ACGT" * 4,                                  # 16 bp: never seeds (bwt.h:2089)
+        b"A" * 9,                                     # L < 10: seed budget wraps to 25
+        b"N" * 100,                                   # nothing but N
+        genome[:100], genome[N - 100:],               # first / last bases of the concatenated genome
+        revcomp(genome[:100]), revcomp(genome[N - 100:]),
+        genome[119950:120050],                        # crosses the chr1 / chr2 boundary
+        genome[5000:5100].replace(b"C", b"T"),        # fully converted
+        genome[5000:5050] + b"N" + genome[5051:5100], # N in the middle
+        genome[7000:7017] + b"R" + genome[7018:7100], # IUPAC base other than N
+        b"ACGTTGCA" * 30,                             # junk, 240 bp
+        genome[9000:9999],                            # 999 bp, k capped at 31
+        genome[20000:20018],                          # 18 bp, shortest seedable read
+        b"T" * 60, b"TG" * 40,                        # low complexity, no C
+    ]
+    gres, gcand = gidx.map_batch_se(reads)
+    ores, ocand = oidx.map_se(reads)
+    assert_same_records(gres, gcand, ores, ocand)
+    # empty batch and the argument checks
+    r0, c0 = gidx.map_batch_se([])
+    assert len(r0) == 0 and len(c0) == 0
+    with pytest.raises(B.BmbsError, match="1000"):
+        gidx.map_batch_se([b"A" * 1001])
+
+
+def _verify_cases(rng, oidx, n, L):
+    N = oidx.N
+    k = min(31, int(0.08 * L))
+    reads, sites = [], []
+    for _ in range(n):
+        site = int(rng.integers(0, 2 * N))
+        mode = rng.random()
+        if mode < 0.02:
+            site = int(rng.choice([N - L, N - 3, 2 * N - L - k, 2 * N - 2, 2 * N + 5, (1 << 64) - 7, 0, N]))   # strand ends, wrapped coordinates
+        win = oidx.window(site, L + 2 * k)
+        base = np.frombuffer(win, dtype=np.uint8)[k:k + L].copy()
+        if base[0] == 0 or mode < 0.05:
+            base = ACGT[rng.integers(0, 4, size=L)]                  # decoy / out-of-genome window
+        else:
+            c = (base == ord("C")) & (rng.random(L) < 0.98); base[c] = ord("T")
+            e = rng.choice([0, 0.01, 0.02, 0.04, 0.06, 0.08])
+            for _e in range(rng.binomial(L, e)):
+                p = int(rng.integers(0, len(base))); r = rng.random()
+                if r < 2 / 3:
+                    base[p] = rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8))
+                elif r < 5 / 6 and len(base) > 20:
+                    base = np.delete(base, p)
+                else:
+                    base = np.insert(base, p, ACGT[rng.integers(0, 4)])
+            if len(base) < L:
+                base = np.concatenate([base, ACGT[rng.integers(0, 4, size=L - len(base))]])
+            base = base[:L]
+        reads.append(base.tobytes()); sites.append(site)
+    return reads, np.array(sites, dtype=np.uint64)
+
+
+@pytest.mark.parametrize("L", [30, 100, 150, 200, 250, 640])
+def test_verify_kernel_matches_oracle(gidx, oidx, L):
+    rng = np.random.default_rng(1000 + L)
+    reads, sites = _verify_cases(rng, oidx, 4000, L)
+    idx = np.arange(len(reads), dtype=np.uint32)
+    gend, gerr = gidx.verify(reads, idx, sites)
+    oend, oerr = oidx.verify(reads, idx, sites)
+    assert np.array_equal(gend, oend) and np.array_equal(gerr, oerr)
+    assert (gend >= 0).sum() > 1500 and (gend < 0).sum() > 50
+
+
+def test_verify_error_rate_other_than_default(gidx, oidx):
+    rng = np.random.default_rng(77)
+    reads, sites = _verify_cases(rng, oidx, 2000, 120)
+    idx = np.arange(len(reads), dtype=np.uint32)
+    for e in (0.0, 0.03, 0.2, 0.5):
+        gend, gerr = gidx.verify(reads, idx, sites, e_rate=e)
+        oend, oerr = oidx.verify(reads, idx, sites, e_rate=e)
+        assert np.array_equal(gend, oend) and np.array_equal(gerr, oerr)
+
+
+@pytest.mark.parametrize("name,args", [
+    ("se100", ["--seq", "se100.fq"]),
+    ("se250", ["--seq", "se250.fq"]),
+    ("pe150", ["--seq1", "pe150_1.fq", "--seq2", "pe150_2.fq", "--pe"]),
+])
+def test_mapper_sam_identical_to_reference_golden(golden, built, name, args):
+    """whole program: FASTQ -> GPU seed-and-verify through the C ABI -> host CIGAR/MAPQ -> SAM, vs the reference's SAM"""
+    subprocess.run([str(built["bmbs"]), "--search", "genome.fa", *args, "-t", "4", "-o", "gpu.sam", "--mapstats", "gpu.stats", "--batch", "700"],
+                   cwd=golden, check=True, stderr=subprocess.DEVNULL)
+    assert sam_body(golden / "gpu.sam") == sam_body(golden / f"{name}.sam")
+    assert (golden / "gpu.stats").read_text() == (golden / f"ref_{name}.stats").read_text()
+
+
+def test_live_reference_binary_agrees_on_fresh_data(built, tmp_path):
+    """fresh seeded data, larger than the golden set; compared with the real reference run on this box"""
+    if not built["ref"].exists():
+        pytest.skip("compiled reference absent")
+    chroms = S.random_genome([900000, 600000], seed=99, repeat_fraction=0.4, repeat_copies=(5, 60), repeat_len=(300, 4000))
+    S.write_fasta(tmp_path / "g.fa", chroms)
+    r, _ = S.simulate_reads(chroms, 12000, 125, seed=5, sub=0.025, indel=0.004, n_rate=0.002, random_qual=True, junk_fraction=0.03)
+    S.write_fastq(tmp_path / "r.fq", r)
+    a, b = S.simulate_reads(chroms, 6000, 100, seed=6, paired=True, sub=0.02, indel=0.003, random_qual=True, frag_range=(150, 420))
+    S.write_fastq(tmp_path / "a.fq", a); S.write_fastq(tmp_path / "b.fq", b)
+    subprocess.run([str(built["indexer"]), "g.fa"], cwd=tmp_path, check=True, stderr=subprocess.DEVNULL)
+    for tag, args in (("se", ["--seq", "r.fq"]), ("pe", ["--seq1", "a.fq", "--seq2", "b.fq", "--pe"])):
+        subprocess.run([str(built["ref"]), "--search", "g.fa", *args, "-t", "1", "-o", f"cpu_{tag}.sam", "--mapstats", f"cpu_{tag}.st"],
+                       cwd=tmp_path, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        subprocess.run([str(built["bmbs"]), "--search", "g.fa", *args, "-t", "4", "-o", f"gpu_{tag}.sam", "--mapstats", f"gpu_{tag}.st"],
+                       cwd=tmp_path, check=True, stderr=subprocess.DEVNULL)
+        assert sam_body(tmp_path / f"gpu_{tag}.sam") == sam_body(tmp_path / f"cpu_{tag}.sam")
+        assert (tmp_path / f"gpu_{tag}.st").read_text() == (tmp_path / f"cpu_{tag}.st").read_text()
+
+
+def test_capacity_error_is_reported_with_needed_size(golden, gidx):
+    reads = [r[1] for r in read_fastq(golden / "se100.fq")]
+    flat, offs = capi.flatten(reads)
+    import ctypes as C
+    res = np.zeros(len(reads), dtype=capi.ReadResult); cand = np.zeros(4, dtype=capi.Cand); used = C.c_size_t(0)
+    p = capi.default_params()
+    L = capi.load_library()
+    rc = L.bmbs_map_batch_se(gidx._h, 0, flat.ctypes.data, offs.ctypes.data, len(reads), C.byref(p), res.ctypes.data, cand.ctypes.data, 4, C.byref(used))
+    assert rc == -4 and used.value > 4
+    res2, cand2 = gidx.map_batch_se(reads)
+    assert len(cand2) == used.value
+
+
+def test_staged_batch_counters_and_idempotence(golden, gidx):
+    reads = [r[1] for r in read_fastq(golden / "se100.fq")]
+    flat, offs = capi.flatten(reads)
+    b = B.Batch(gidx, 0, len(reads), len(flat) + 64, 1 << 18)
+    p = capi.default_params()
+    b.upload(flat, offs); b.run(p); r1, c1, u1 = b.download()
+    c = b.counters(); t = b.timings()
+    b.run(p); r2, c2, u2 = b.download()         # same inputs, same outputs
+    assert u1 == u2 and np.array_equal(r1, r2) and np.array_equal(c1[:u1], c2[:u2])
+    assert c["hash_queries"] >= len(reads) * 0.9 and c["occ_lookups"] > 0 and c["verified"] == (r1["n_cand"][r1["state"] == B.VERIFY]).sum()
+    assert c["cells"] == sum(int(n) * len(rd) * (2 * min(31, int(0.08 * len(rd))) + 1) for n, rd, s in zip(r1["n_cand"], reads, r1["state"]) if s == B.VERIFY)
+    assert t["total"] > 0 and b.launches() >= 12

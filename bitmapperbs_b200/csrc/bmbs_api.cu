@@ -339,7 +339,7 @@ extern "C" int bmbs_batch_download(bmbs_batch* b, bmbs_read_result* res, bmbs_ca
   int rc = check_status(b, cand_used);
   if (rc) return rc;
   const size_t work = (size_t)b->h_small[1];
-  if (work > cand_cap) return fail(BMBS_ERR_CAPACITY, "caller's cand[] holds " + std::to_string(cand_cap) + " entries, " + std::to_string(work) + " needed");
+  if (work > cand_cap) { if (cand_used) *cand_used = work; return fail(BMBS_ERR_CAPACITY, "caller's cand[] holds " + std::to_string(cand_cap) + " entries, " + std::to_string(work) + " needed"); }
   if (b->n_reads) CU(cudaMemcpyAsync(res, b->v.out_res, (size_t)b->n_reads * sizeof(bmbs_read_result), cudaMemcpyDeviceToHost, b->stream));
   if (work) { if (!cand) return fail(BMBS_ERR_ARG, "cand is null"); CU(cudaMemcpyAsync(cand, b->v.out_cand, work * sizeof(bmbs_cand), cudaMemcpyDeviceToHost, b->stream)); }
   CU(cudaStreamSynchronize(b->stream));
@@ -391,13 +391,20 @@ int cached_batch(bmbs_index* idx, int dev, size_t reads, size_t bases, size_t ca
 int map_batch(bmbs_index* idx, int dev, const char* seqs, const uint64_t* offsets, int n_reads, int pe, const bmbs_params* prm,
               bmbs_read_result* res, bmbs_cand* cand, size_t cand_cap, size_t* cand_used) {
   if (!idx || !seqs || !offsets || !prm || !res || n_reads < 0) return fail(BMBS_ERR_ARG, "bad argument");
-  bmbs_batch* b = nullptr;
-  size_t cap = cand_cap < 1024 ? 1024 : cand_cap;
-  int rc = cached_batch(idx, dev, (size_t)n_reads + 1, offsets[n_reads] + 64, cap, &b);
-  if (rc) return rc;
-  if ((rc = bmbs_batch_upload(b, seqs, offsets, n_reads, pe))) return rc;
-  if ((rc = bmbs_batch_run(b, prm))) return rc;
-  return bmbs_batch_download(b, res, cand, cand_cap, cand_used);
+  // device-side slot capacity is the library's business: start from a per-read estimate and grow on overflow;
+  // the caller's cand_cap only bounds what is copied back
+  size_t dev_cap = (size_t)n_reads * 16 + (1u << 16);
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    bmbs_batch* b = nullptr;
+    int rc = cached_batch(idx, dev, (size_t)n_reads + 1, offsets[n_reads] + 64, dev_cap, &b);
+    if (rc) return rc;
+    if ((rc = bmbs_batch_upload(b, seqs, offsets, n_reads, pe))) return rc;
+    if ((rc = bmbs_batch_run(b, prm))) return rc;
+    rc = bmbs_batch_download(b, res, cand, cand_cap, cand_used);
+    if (rc == BMBS_ERR_CAPACITY && (*(const u32*)(b->h_small + 2) & 2u)) { dev_cap = (size_t)b->h_small[0] + (size_t)(b->h_small[0] >> 2) + 1024; continue; }
+    return rc;
+  }
+  return fail(BMBS_ERR_CAPACITY, "candidate slots keep exceeding the device capacity");
 }
 }  // namespace
 

@@ -143,3 +143,63 @@ def write_fastq(path, reads):
     with open(path, "wb") as f:
         for name, seq, qual in reads:
             f.write(b"@" + name.encode() + b"\n" + seq + b"\n+\n" + qual + b"\n")
+
+
+# ---------------------------------------------------------------------------------------------
+# vectorised generators for bench.py (millions of reads in seconds)
+def concat_genome(chroms):
+    """-> (uint8 genome, int64 chromosome start offsets incl. the end)"""
+    seq = np.concatenate([s for _, s in chroms])
+    starts = np.zeros(len(chroms) + 1, dtype=np.int64)
+    starts[1:] = np.cumsum([len(s) for _, s in chroms])
+    return seq, starts
+
+
+def _revcomp_rows(m):
+    return _COMP[m[:, ::-1]]
+
+
+def simulate_fast(genome, starts, n, L, seed, paired=True, frag_range=(200, 480), conv=0.98, sub=0.01):
+    """Directional bisulfite reads as uint8 matrices.
+    Returns (mate1 [n,L], mate2 [n,L] or None).  mate2 is in FASTQ orientation (reverse complement of the fragment
+    suffix); pass revcomp rows to the C ABI.  No indels (bench.py uses substitutions only, SURVEY.md §8d cfg 2)."""
+    rng = np.random.default_rng(seed)
+    lens = np.diff(starts)
+    c = rng.choice(len(lens), size=n, p=lens / lens.sum())
+    flen = rng.integers(frag_range[0], frag_range[1] + 1, size=n) if paired else np.full(n, L)
+    flen = np.maximum(flen, L)
+    p = starts[c] + (rng.random(n) * (lens[c] - flen - 1)).astype(np.int64)
+    strand = rng.random(n) < 0.5
+    ar = np.arange(L, dtype=np.int64)
+    left = genome[p[:, None] + ar]                      # G[p : p+L]
+    right = genome[(p + flen - L)[:, None] + ar]        # G[p+flen-L : p+flen]
+    m1 = np.where(strand[:, None], _revcomp_rows(right), left)
+    tail = np.where(strand[:, None], _revcomp_rows(left), right)   # fragment suffix on the sequenced strand
+
+    def damage(m):
+        cc = (m == ord("C")) & (rng.random(m.shape) < conv)
+        m = np.where(cc, ord("T"), m).astype(np.uint8)
+        if sub > 0:
+            e = rng.random(m.shape) < sub
+            k = int(e.sum())
+            m[e] = _ACGT[(np.searchsorted(_ACGT, m[e]) + rng.integers(1, 4, size=k)) % 4]
+        return m
+
+    m1 = damage(m1)
+    if not paired:
+        return m1, None
+    tail = damage(tail)
+    return m1, _revcomp_rows(tail)
+
+
+def write_fastq_matrix(path, m, tag, qual=ord("I")):
+    """fixed-width FASTQ records straight from a read matrix"""
+    n, L = m.shape
+    names = np.char.add(np.char.add("@r", np.char.zfill(np.arange(n).astype(str), 9)), tag)
+    nb = np.frombuffer("".join(names.tolist()).encode(), dtype=np.uint8).reshape(n, -1)
+    w = nb.shape[1]
+    rec = np.empty((n, w + 1 + L + 3 + L + 1), dtype=np.uint8)
+    rec[:, :w] = nb; rec[:, w] = 10
+    rec[:, w + 1:w + 1 + L] = m; rec[:, w + 1 + L] = 10; rec[:, w + 2 + L] = ord("+"); rec[:, w + 3 + L] = 10
+    rec[:, w + 4 + L:w + 4 + 2 * L] = qual; rec[:, -1] = 10
+    rec.tofile(path)

@@ -97,7 +97,8 @@ def _verify_cases(rng, oidx, n, L):
         site = int(rng.integers(0, 2 * N))
         mode = rng.random()
         if mode < 0.02:
-            site = int(rng.choice([N - L, N - 3, 2 * N - L - k, 2 * N - 2, 2 * N + 5, (1 << 64) - 7, 0, N]))   # strand ends, wrapped coordinates
+            edge = [N - L, N - 3, 2 * N - L - k, 2 * N - 2, 2 * N + 5, (1 << 64) - 7, 0, N]   # strand ends, wrapped coordinates
+            site = edge[int(rng.integers(0, len(edge)))]
         win = oidx.window(site, L + 2 * k)
         base = np.frombuffer(win, dtype=np.uint8)[k:k + L].copy()
         if base[0] == 0 or mode < 0.05:

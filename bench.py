@@ -193,7 +193,8 @@ def main():
     d = ensure_dataset(cache, a.scale, rank == 0)
     if dist:
         dist.barrier()
-    m1, m2 = make_reads(d, a.pairs, 2002 + rank)
+    from bitmapperbs_b200 import shard
+    m1, m2 = make_reads(d, a.pairs, shard.rank_seed(2002, rank))
     n_pairs = len(m1); n_reads = 2 * n_pairs
     from bitmapperbs_b200.simulate import _revcomp_rows
     mates = np.empty((n_reads, READ_LEN), dtype=np.uint8)

@@ -44,12 +44,13 @@ __device__ __forceinline__ int read_code(const u32* __restrict__ w, int i) {
 
 struct OccBlock { ulonglong2 planes, cnt; u64 blk; };
 
+// one 32-byte occ block = one 256-bit load (LDG.E.256 on sm_100) = one L1 wavefront and one DRAM sector
 __device__ __forceinline__ OccBlock load_occ(const DevIndex& ix, u64 adj_row) {
   OccBlock b;
   b.blk = adj_row >> 6;
   const ulonglong2* p = ix.occ + b.blk * 2;
-  b.planes = __ldg(p);
-  b.cnt = __ldg(p + 1);
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(b.planes.x), "=l"(b.planes.y), "=l"(b.cnt.x), "=l"(b.cnt.y) : "l"(p));
   return b;
 }
 
@@ -68,12 +69,12 @@ __device__ __forceinline__ u64 adjust_row(const DevIndex& ix, u64 row) { return 
 // Returns the number of distinct occ blocks touched (1 or 2) for the work counters.
 __device__ __forceinline__ int lf_pair(const DevIndex& ix, u64& sp, u64& ep, int c) {
   const u64 a = adjust_row(ix, sp), b = adjust_row(ix, ep);
-  OccBlock ba = load_occ(ix, a);
+  // both ends are issued together (two independent 256-bit loads in flight); when they share a block the second
+  // load hits the same sector
+  const OccBlock ba = load_occ(ix, a), bb = load_occ(ix, b);
   sp = rank_in(ix, ba, a, c);
-  if ((b >> 6) == ba.blk) { ep = rank_in(ix, ba, b, c); return 1; }
-  OccBlock bb = load_occ(ix, b);
   ep = rank_in(ix, bb, b, c);
-  return 2;
+  return ba.blk == bb.blk ? 1 : 2;
 }
 
 __device__ __forceinline__ void hash_query(const DevIndex& ix, u64 key, u64& sp, u64& ep) {

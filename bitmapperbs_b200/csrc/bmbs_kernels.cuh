@@ -29,7 +29,7 @@ struct BatchView {
   // inputs
   const char* ascii; const u64* offsets; int n_reads; int pe;
   // per read
-  u32* codes; u32* len; unsigned short* first_c; unsigned char* kk;
+  u32* codes; uint4* rplanes; u32* len; unsigned short* first_c; unsigned char* kk;   // rplanes: {lo, hi, not-ACGT, is-N} per 32 bases
   unsigned char* state; unsigned char* flags;  // flags: bit0 is_multi, bit1 extra==0 (second seed conclusive)
   short* one_mm; u64* site0;
   u32* ntask; u32* ncand; u32* coff;           // coff: exclusive scan of ncand, n_reads+1
@@ -49,30 +49,50 @@ struct BatchView {
 };
 
 __device__ __forceinline__ u32 code_word_offset(const u64* offsets, int r) { return (u32)(offsets[r] >> 3) + (u32)r; }
+__device__ __forceinline__ u32 plane_chunk_offset(const u64* offsets, int r) { return (u32)(offsets[r] >> 5) + (u32)r; }
 
 // ------------------------------------------------------------------------------------------- pack
-// one warp per read: 8 ASCII bases -> one u32 of nibbles.  Codes: A0 C1 G2 T3 N4 other5.
-__global__ void pack_reads(BatchView b) {
+// One warp per read.  Each lane turns 8 ASCII bases (two aligned 64-bit loads, so the warp reads the read's bytes
+// coalesced) into one u32 of nibble codes (A0 C1 G2 T3 N4 other5, used by verification) and into 8 bits of each
+// bit-plane; four lanes together form one 32-base plane chunk {lo, hi, not-ACGT, is-N} (used by seeding).
+__global__ void __launch_bounds__(128) pack_reads(BatchView b) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= b.n_reads) return;
   const u64 beg = b.offsets[r];
   const u32 L = (u32)(b.offsets[r + 1] - beg);
-  const char* s = b.ascii + beg;
   u32* w = b.codes + code_word_offset(b.offsets, r);
+  uint4* pl = b.rplanes + plane_chunk_offset(b.offsets, r);
   u32 first_c = L;
-  for (u32 j = lane; j * 8 < L; j += 32) {
-    u32 word = 0;
-    for (u32 t = 0; t < 8; ++t) {
-      const u32 i = j * 8 + t;
-      u32 c = 0;
-      if (i < L) {
-        const char ch = s[i];
-        c = ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : ch == 'N' ? 4u : 5u;
-        if (c == 1u && i < first_c) first_c = i;
+  const u32 nwords = (L + 7) >> 3, niter = (nwords + 31) >> 5;
+  for (u32 it = 0; it < niter; ++it) {
+    const u32 j = it * 32 + lane;
+    u32 word = 0, lo = 0, hi = 0, bad = 0, isn = 0;
+    if (j < nwords) {
+      const u64 addr = (u64)(b.ascii) + beg + (u64)j * 8;
+      const u64* q = (const u64*)(addr & ~7ull);
+      const unsigned sh = (unsigned)(addr & 7ull) * 8;
+      u64 x = q[0];
+      if (sh) x = (x >> sh) | (q[1] << (64 - sh));   // staging buffers carry 64 bytes of slack past the last read
+      for (u32 t = 0; t < 8; ++t) {
+        const u32 i = j * 8 + t;
+        if (i < L) {
+          const u32 ch = (u32)(x >> (8 * t)) & 0xFFu;
+          const u32 c = ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : ch == 'N' ? 4u : 5u;
+          if (c == 1u && i < first_c) first_c = i;
+          word |= c << (4 * t);
+          lo |= (c & 1u & (c < 4u ? 1u : 0u)) << t; hi |= ((c >> 1) & (c < 4u ? 1u : 0u)) << t;
+          bad |= (c >= 4u ? 1u : 0u) << t; isn |= (c == 4u ? 1u : 0u) << t;
+        }
       }
-      word |= c << (4 * t);
+      w[j] = word;
     }
-    w[j] = word;
+    const unsigned s8 = 8u * (lane & 3);
+    lo <<= s8; hi <<= s8; bad <<= s8; isn <<= s8;
+    for (int o = 1; o <= 2; o <<= 1) {
+      lo |= __shfl_xor_sync(0xffffffffu, lo, o); hi |= __shfl_xor_sync(0xffffffffu, hi, o);
+      bad |= __shfl_xor_sync(0xffffffffu, bad, o); isn |= __shfl_xor_sync(0xffffffffu, isn, o);
+    }
+    if ((lane & 3) == 0 && (j >> 2) * 32 < L) pl[j >> 2] = make_uint4(lo, hi, bad, isn);   // only the read's own chunks (the next read follows)
   }
   for (int o = 16; o; o >>= 1) first_c = min(first_c, __shfl_xor_sync(0xffffffffu, first_c, o));
   if (lane == 0) {
@@ -86,27 +106,59 @@ __global__ void pack_reads(BatchView b) {
 // ------------------------------------------------------------------------------------------- seed
 struct SeedHit { u64 hits, sp, ep; u32 mlen; };
 
+// Read bases as bit-planes.  FM alphabet of the reversed, C->T converted read: G0 T1 A2, anything else stops a seed;
+// from the planes (A00 C01 G10 T11): fm = lo | ((~lo & ~hi) << 1).
+struct ReadPlanes {
+  const uint4* p;
+  __device__ __forceinline__ void window(u32 pos, u32& lo, u32& hi, u32& bad) const {   // 32 bases starting at pos
+    const uint4 a = __ldg(p + (pos >> 5)), c = __ldg(p + (pos >> 5) + 1);
+    const unsigned s = pos & 31u;
+    lo = __funnelshift_r(a.x, c.x, s); hi = __funnelshift_r(a.y, c.y, s); bad = __funnelshift_r(a.z, c.z, s);
+  }
+};
+
+// base-3 value of 16 FM symbols (first base least significant) through a 4-base table in shared memory
+__device__ __forceinline__ bool key16(const ReadPlanes& rp, const unsigned char* __restrict__ lut, u32 off, u32& key) {
+  u32 lo, hi, bad; rp.window(off, lo, hi, bad);
+  if (bad & 0xFFFFu) return false;
+  const u32 a = (lo & 0xFFFFu) | ((~lo & ~hi) << 16);      // low half: fm bit 0, high half: fm bit 1
+  const u32 i0 = (a & 0xFu) | ((a >> 12) & 0xF0u), i1 = ((a >> 4) & 0xFu) | ((a >> 16) & 0xF0u);
+  const u32 i2 = ((a >> 8) & 0xFu) | ((a >> 20) & 0xF0u), i3 = ((a >> 12) & 0xFu) | ((a >> 24) & 0xF0u);
+  key = (u32)lut[i0] + 81u * (u32)lut[i1] + 6561u * (u32)lut[i2] + 531441u * (u32)lut[i3];
+  return true;
+}
+
+// FM symbols of read[pos ..], 32 at a time, consumed one per LF step
+struct SymbolStream {
+  const ReadPlanes& rp; u32 base, lo, hi, bad;
+  __device__ __forceinline__ SymbolStream(const ReadPlanes& r, u32 pos) : rp(r), base(pos) { rp.window(pos, lo, hi, bad); }
+  __device__ __forceinline__ int at(u32 pos) {       // pos >= base, non-decreasing
+    if (pos - base >= 32u) { base = pos; rp.window(pos, lo, hi, bad); }
+    const unsigned s = pos - base;
+    if ((bad >> s) & 1u) return 3;
+    const u32 l = (lo >> s) & 1u, h = (hi >> s) & 1u;
+    return (int)(l | ((~(l | h) & 1u) << 1));
+  }
+};
+
 // count_backward_as_much_1_terminate (bwt.h:2081-2209) on the reversed, C->T converted read:
 // the seed starts at read[off] and grows to the right; cur = L - off bases are available.
-__device__ __forceinline__ SeedHit seed_until_unique(const DevIndex& ix, const u32* __restrict__ w, u32 off, u32 cur,
+__device__ __forceinline__ SeedHit seed_until_unique(const DevIndex& ix, const ReadPlanes& rp, const unsigned char* lut, u32 off, u32 cur,
                                                      u64 sp_in, u64 ep_in, u32& n_occ, u32& n_hash) {
   SeedHit h; h.hits = 0; h.sp = sp_in; h.ep = ep_in; h.mlen = 0;
   if (cur < 18) return h;
-  u64 key = 0, p3 = 1;
-  for (u32 m = 0; m < 16; ++m) {
-    const int c = fm_code(read_code(w, off + m));
-    if (c > 2) return h;
-    key += p3 * (u64)c; p3 *= 3;
-  }
+  u32 key;
+  if (!key16(rp, lut, off, key)) return h;
   u64 top, bot;
   hash_query(ix, key, top, bot); ++n_hash;
   if (bot <= top) return h;
   u64 ptop = ~0ull, pbot = ~0ull;
   u32 m = 16;
+  SymbolStream ss(rp, off + 16);
   for (; m < cur; ++m) {
     ptop = top; pbot = bot;
     if (bot - top == 1) break;
-    const int c = fm_code(read_code(w, off + m));
+    const int c = ss.at(off + m);
     if (c > 2) { bot = top; break; }
     n_occ += lf_pair(ix, top, bot, c);
     if (bot <= top) break;
@@ -118,21 +170,18 @@ __device__ __forceinline__ SeedHit seed_until_unique(const DevIndex& ix, const u
 }
 
 // count_hash_table (bwt.h:1848-1952): exact interval of read[off .. off+cur)
-__device__ __forceinline__ u64 count_exact(const DevIndex& ix, const u32* __restrict__ w, u32 off, u32 cur, u64& sp, u64& ep,
+__device__ __forceinline__ u64 count_exact(const DevIndex& ix, const ReadPlanes& rp, const unsigned char* lut, u32 off, u32 cur, u64& sp, u64& ep,
                                            u32& n_occ, u32& n_hash) {
   if (cur < 17) return 0;
-  u64 key = 0, p3 = 1;
-  for (u32 m = 0; m < 16; ++m) {
-    const int c = fm_code(read_code(w, off + m));
-    if (c > 2) return 0;
-    key += p3 * (u64)c; p3 *= 3;
-  }
+  u32 key;
+  if (!key16(rp, lut, off, key)) return 0;
   u64 top, bot;
   hash_query(ix, key, top, bot); ++n_hash;
   if (bot <= top) return 0;
+  SymbolStream ss(rp, off + 16);
   for (u32 m = 16; m < cur; ++m) {
     if (bot <= top) break;
-    const int c = fm_code(read_code(w, off + m));
+    const int c = ss.at(off + m);
     if (c > 2) return 0;
     n_occ += lf_pair(ix, top, bot, c);
   }
@@ -140,22 +189,55 @@ __device__ __forceinline__ u64 count_exact(const DevIndex& ix, const u32* __rest
   return bot <= top ? 0 : bot - top;
 }
 
-// determine_seed_offset_unmatch, Schema.h:1506-1531 (step 8)
-__device__ __forceinline__ u32 next_offset_unmatched(const u32* __restrict__ w, u32 L, u32 off) {
+// determine_seed_offset_unmatch, Schema.h:1506-1531 (step 8): skip past an N inside the next 8 bases
+__device__ __forceinline__ u32 next_offset_unmatched(const ReadPlanes& rp, u32 L, u32 off) {
   if ((int)L - (int)off < 18) return L;
-  for (u32 i = 0; i < 8; ++i) if (read_code(w, off + i) == 4) return off + i + 1;
-  return off + 8;
+  const uint4 a = __ldg(rp.p + (off >> 5)), c = __ldg(rp.p + (off >> 5) + 1);
+  const u32 n8 = __funnelshift_r(a.w, c.w, off & 31u) & 0xFFu;
+  return n8 ? off + (u32)__ffs(n8) : off + 8;
+}
+
+// Direct compare of read[from .. L) with the genome at `site` (try_process_unique_mismatch_end_to_end_*,
+// Schema.cpp:15430-15478): read T may face reference C; stops at the second error.  32 bases per step on bit-planes.
+__device__ __forceinline__ int compare_rest(const DevIndex& ix, const ReadPlanes& rp, u64 site, u32 L, u32& mlen) {
+  int errors = 0;
+  const bool inside = window_inside(ix, site, L);
+  const u32 from = mlen;
+  for (u32 c0 = from & ~31u; c0 < L; c0 += 32) {
+    const uint4 r = __ldg(rp.p + (c0 >> 5));
+    u32 mism;
+    if (inside) {
+      const u64 g = site + c0;
+      const uint2 w0 = __ldg(ix.planes + (g >> 5)), w1 = __ldg(ix.planes + (g >> 5) + 1);
+      const unsigned sh = (unsigned)g & 31u;
+      const u32 glo = __funnelshift_r(w0.x, w1.x, sh), ghi = __funnelshift_r(w0.y, w1.y, sh);
+      mism = (((r.x ^ glo) | (r.y ^ ghi)) & ~(r.x & r.y & glo & ~ghi)) | r.z;
+    } else mism = 0xFFFFFFFFu;
+    if (c0 < from) mism &= ~0u << (from - c0);
+    if (L - c0 < 32u) mism &= (1u << (L - c0)) - 1u;
+    if (mism) {
+      if (errors == 0) { mlen = c0 + (u32)__ffs(mism) - 1u; errors = 1; mism &= mism - 1u; }
+      if (mism) { errors = 2; break; }
+    }
+  }
+  return errors;
 }
 
 __global__ void __launch_bounds__(128) seed_reads(DevIndex ix, BatchView b) {
   __shared__ u64 s_cnt[4];
+  __shared__ unsigned char s_lut[256];
   if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+  for (u32 i = threadIdx.x; i < 256; i += blockDim.x) {     // i = fm bit0 of 4 bases | fm bit1 << 4
+    u32 v = 0, p3 = 1;
+    for (u32 t = 0; t < 4; ++t) { v += p3 * (((i >> t) & 1u) | (((i >> (4 + t)) & 1u) << 1)); p3 *= 3; }
+    s_lut[i] = (unsigned char)v;
+  }
   __syncthreads();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   u32 n_occ = 0, n_hash = 0, n_rows = 0, n_llf = 0;
   if (r < b.n_reads) {
     const u32 L = b.len[r];
-    const u32* w = b.codes + code_word_offset(b.offsets, r);
+    ReadPlanes rp; rp.p = b.rplanes + plane_chunk_offset(b.offsets, r);
     const u32 first_c = b.first_c[r];
     u64 max_seeds = (u64)L / 10 - 1; if (max_seeds > 25) max_seeds = 25;   // u64 wrap for L < 10, as in the reference
     u32 off = 0, nt = 0, nc = 0, first_len = 0;
@@ -167,25 +249,16 @@ __global__ void __launch_bounds__(128) seed_reads(DevIndex ix, BatchView b) {
       ++nt; nc += hits ? hits : 1u;
     };
     if (seed_id < max_seeds && off < L) {
-      SeedHit h = seed_until_unique(ix, w, off, L - off, sp, ep, n_occ, n_hash);
+      SeedHit h = seed_until_unique(ix, rp, s_lut, off, L - off, sp, ep, n_occ, n_hash);
       sp = h.sp; ep = h.ep;
       u32 mlen = h.mlen; first_len = mlen;
       if (h.hits == 1) {
         int st; const u64 sa = locate_row(ix, sp, st); n_llf += st; ++n_rows;
         const u64 site = 2 * ix.N - sa - mlen;
         emit(site, 0, 0, 0);
-        // try_process_unique_mismatch_end_to_end_*: Schema.cpp:15410-15478, :15661-15715
         if (mlen > first_c) mlen = first_c;
         int errors = 0;
-        if (mlen != L) {
-          const bool inside = window_inside(ix, site, L);
-          for (u32 ri = mlen; ri < L; ++ri) {
-            const int rc = read_code(w, ri);
-            bool mism = true;
-            if (inside) { const int g = strand_base(ix, site + ri); mism = rc != g && !(rc == 3 && g == 1); }
-            if (mism) { if (++errors == 1) mlen = ri; else break; }
-          }
-        }
+        if (mlen != L) errors = compare_rest(ix, rp, site, L, mlen);
         get_error = errors;
         if (errors == 0) { state = BMBS_EXACT_UNIQUE; site0 = site; done = true; }
       }
@@ -201,26 +274,26 @@ __global__ void __launch_bounds__(128) seed_reads(DevIndex ix, BatchView b) {
       }
       if (!done) {
         if (h.hits != 1 && mlen >= b.seed_len && h.hits <= MAX_SEED_HITS && h.hits != 0) emit(sp, (u32)h.hits, mlen, off);
-        off = mlen == 0 ? next_offset_unmatched(w, L, off) : off + mlen / 2;
+        off = mlen == 0 ? next_offset_unmatched(rp, L, off) : off + mlen / 2;
         ++seed_id;
       }
     }
     if (!done && get_error == 1) {
       const u32 len2 = L - first_len;
       if (len2 >= 17) {
-        const u64 hits = count_exact(ix, w, first_len, len2, sp, ep, n_occ, n_hash);
+        const u64 hits = count_exact(ix, rp, s_lut, first_len, len2, sp, ep, n_occ, n_hash);
         if (hits <= MAX_SEED_HITS) { if (hits) emit(sp, (u32)hits, len2, first_len); extra = false; }
       }
     }
     if (!done && extra) {
       while (seed_id < max_seeds && off < L) {
         const u32 cur = L - off;
-        SeedHit h = seed_until_unique(ix, w, off, cur, sp, ep, n_occ, n_hash);
+        SeedHit h = seed_until_unique(ix, rp, s_lut, off, cur, sp, ep, n_occ, n_hash);
         sp = h.sp; ep = h.ep;
         if (h.hits == 1) emit(sp, 1, h.mlen, off);
         else if (h.mlen >= b.seed_len && h.hits <= MAX_SEED_HITS) { if (h.hits) emit(sp, (u32)h.hits, h.mlen, off); }
         else if (cur == h.mlen) break;
-        off = h.mlen == 0 ? next_offset_unmatched(w, L, off) : off + h.mlen / 2;
+        off = h.mlen == 0 ? next_offset_unmatched(rp, L, off) : off + h.mlen / 2;
         ++seed_id;
       }
     }
@@ -306,7 +379,8 @@ __global__ void __launch_bounds__(128) votes_small(BatchView b) {
   if (!classify_read(b, r, beg, n, lane == 0)) return;
   u64 v = lane < (int)n ? b.cand[beg + lane] : ~0ull;
   bool pad = lane >= (int)n;   // padding sorts last even against a real ~0 key
-  for (int k = 2; k <= 32; k <<= 1)
+  int kmax = 2; while (kmax < (int)n) kmax <<= 1;   // lanes >= n hold padding: stages above nextpow2(n) change nothing
+  for (int k = 2; k <= kmax; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
       const u64 o = __shfl_xor_sync(0xffffffffu, v, j);
       const bool opad = __shfl_xor_sync(0xffffffffu, (int)pad, j) != 0;

@@ -217,6 +217,7 @@ extern "C" int bmbs_batch_create(bmbs_index* idx, int dev, size_t max_reads, siz
   A(dalloc(b, &b->d_ascii, max_bases + 64)); A(dalloc(b, &b->d_offsets, R));
   A(dalloc(b, &v.codes, max_bases / 8 + R + 64)); A(dalloc(b, &v.rplanes, max_bases / 32 + 2 * R + 64)); A(dalloc(b, &v.len, R)); A(dalloc(b, &v.first_c, R)); A(dalloc(b, &v.kk, R));
   A(dalloc(b, &v.state, R)); A(dalloc(b, &v.flags, R)); A(dalloc(b, &v.one_mm, R)); A(dalloc(b, &v.site0, R));
+  A(dalloc(b, &v.ph_off, R)); A(dalloc(b, &v.ph_first_len, R)); A(dalloc(b, &v.ph_seed_id, R)); A(dalloc(b, &v.list2, R)); A(dalloc(b, &v.list3, R)); A(dalloc(b, &v.list_count, 4));
   A(dalloc(b, &v.ntask, R)); A(dalloc(b, &v.ncand, R)); A(dalloc(b, &v.coff, R)); A(dalloc(b, &v.tasks, (size_t)MAX_TASKS * max_reads));
   A(dalloc(b, &v.slot_row, S)); A(dalloc(b, &v.slot_adj, S)); A(dalloc(b, &v.slot_read, S)); A(dalloc(b, &v.cand, S)); A(dalloc(b, &v.vcnt, S));
   A(dalloc(b, &v.nv, R)); A(dalloc(b, &v.voff, R)); A(dalloc(b, &v.keep, S));
@@ -275,12 +276,14 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
   cudaStream_t s = b->stream;
   const DevIndex ix = b->copy->view;
   CU(cudaMemsetAsync(v.counters, 0, 16 * 8, s)); CU(cudaMemsetAsync(v.totals, 0, 4 * 8, s)); CU(cudaMemsetAsync(v.status, 0, 16, s));
-  CU(cudaMemsetAsync(v.big_count, 0, 16, s)); CU(cudaMemsetAsync(v.scratch_used, 0, 16, s));
+  CU(cudaMemsetAsync(v.big_count, 0, 16, s)); CU(cudaMemsetAsync(v.scratch_used, 0, 16, s)); CU(cudaMemsetAsync(v.list_count, 0, 16, s));
   CU(cudaEventRecord(b->ev[0], s));
   if (n > 0) {
     pack_reads<<<(n + 3) / 4, 128, 0, s>>>(v); ++b->launches;
     CU(cudaEventRecord(b->ev[1], s));
-    seed_reads<<<(n + 127) / 128, 128, 0, s>>>(ix, v); ++b->launches;
+    seed_first<<<(n + 127) / 128, 128, 0, s>>>(ix, v); ++b->launches;
+    seed_second<<<b->sm_count * 8, 128, 0, s>>>(ix, v); ++b->launches;
+    seed_rest<<<b->sm_count * 12, 128, 0, s>>>(ix, v); ++b->launches;
     CU(cudaEventRecord(b->ev[2], s));
     run_scan(b, v.ncand, (u32)n, v.coff, v.totals, v.slot_cap, 2u);
     expand_tasks<<<(n + 127) / 128, 128, 0, s>>>(v); ++b->launches;

@@ -32,6 +32,8 @@ struct BatchView {
   u32* codes; uint4* rplanes; u32* len; unsigned short* first_c; unsigned char* kk;   // rplanes: {lo, hi, not-ACGT, is-N} per 32 bases
   unsigned char* state; unsigned char* flags;  // flags: bit0 is_multi, bit1 extra==0 (second seed conclusive)
   short* one_mm; u64* site0;
+  unsigned short* ph_off; unsigned short* ph_first_len; unsigned char* ph_seed_id;   // seeding state carried between the phase kernels
+  u32* list2; u32* list3; u32* list_count;        // reads needing the one-mismatch second seed / the remaining seeds
   u32* ntask; u32* ncand; u32* coff;           // coff: exclusive scan of ncand, n_reads+1
   SeedTask* tasks;                              // [MAX_TASKS][n_reads]
   // per candidate slot
@@ -55,6 +57,27 @@ __device__ __forceinline__ u32 plane_chunk_offset(const u64* offsets, int r) { r
 // One warp per read.  Each lane turns 8 ASCII bases (two aligned 64-bit loads, so the warp reads the read's bytes
 // coalesced) into one u32 of nibble codes (A0 C1 G2 T3 N4 other5, used by verification) and into 8 bits of each
 // bit-plane; four lanes together form one 32-base plane chunk {lo, hi, not-ACGT, is-N} (used by seeding).
+// The ASCII -> code conversion works on 4 bytes at a time (SWAR).
+__device__ __forceinline__ u32 gather4(u32 m01) { return ((m01 * 0x01020408u) >> 24) & 0xFu; }   // byte t bit 0 -> bit t
+__device__ __forceinline__ u32 nonzero_bytes(u32 d) { return ((((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) >> 7) & 0x01010101u; }
+
+struct Packed4 { u32 nib, lo, hi, bad, isn, isc; };
+__device__ __forceinline__ Packed4 pack4(u32 x, u32 nvalid) {
+  const u32 keep = nvalid >= 4 ? 0x01010101u : (((1u << (8 * nvalid)) - 1u) & 0x01010101u);
+  const u32 y = (x >> 1) & 0x03030303u;
+  const u32 code = y ^ ((y >> 1) & 0x01010101u);                  // A0 C1 G2 T3 when the byte is one of ACGT
+  u32 b0 = code & 0x01010101u, b1 = (code >> 1) & 0x01010101u;
+  const u32 expect = 0x41414141u + 2u * b0 + 6u * b1 + 11u * (b0 & b1);   // 'A' 'C' 'G' 'T' for codes 0..3
+  const u32 bad = nonzero_bytes(x ^ expect) & keep;
+  const u32 isn = (~nonzero_bytes(x ^ 0x4E4E4E4Eu)) & 0x01010101u & keep;
+  b0 &= keep & ~bad; b1 &= keep & ~bad;
+  const u32 cb = b0 | (b1 << 1) | (bad * 5u - isn);                // per byte: 0..3, N 4, other 5
+  Packed4 o;
+  o.nib = (cb & 0xFu) | ((cb >> 4) & 0xF0u) | ((cb >> 8) & 0xF00u) | ((cb >> 12) & 0xF000u);
+  o.lo = gather4(b0); o.hi = gather4(b1); o.bad = gather4(bad); o.isn = gather4(isn); o.isc = gather4(b0 & ~b1);
+  return o;
+}
+
 __global__ void __launch_bounds__(128) pack_reads(BatchView b) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= b.n_reads) return;
@@ -66,25 +89,19 @@ __global__ void __launch_bounds__(128) pack_reads(BatchView b) {
   const u32 nwords = (L + 7) >> 3, niter = (nwords + 31) >> 5;
   for (u32 it = 0; it < niter; ++it) {
     const u32 j = it * 32 + lane;
-    u32 word = 0, lo = 0, hi = 0, bad = 0, isn = 0;
+    u32 lo = 0, hi = 0, bad = 0, isn = 0;
     if (j < nwords) {
       const u64 addr = (u64)(b.ascii) + beg + (u64)j * 8;
       const u64* q = (const u64*)(addr & ~7ull);
       const unsigned sh = (unsigned)(addr & 7ull) * 8;
       u64 x = q[0];
       if (sh) x = (x >> sh) | (q[1] << (64 - sh));   // staging buffers carry 64 bytes of slack past the last read
-      for (u32 t = 0; t < 8; ++t) {
-        const u32 i = j * 8 + t;
-        if (i < L) {
-          const u32 ch = (u32)(x >> (8 * t)) & 0xFFu;
-          const u32 c = ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : ch == 'N' ? 4u : 5u;
-          if (c == 1u && i < first_c) first_c = i;
-          word |= c << (4 * t);
-          lo |= (c & 1u & (c < 4u ? 1u : 0u)) << t; hi |= ((c >> 1) & (c < 4u ? 1u : 0u)) << t;
-          bad |= (c >= 4u ? 1u : 0u) << t; isn |= (c == 4u ? 1u : 0u) << t;
-        }
-      }
-      w[j] = word;
+      const u32 left = L - j * 8;                     // >= 1
+      const Packed4 a = pack4((u32)x, left), c = pack4((u32)(x >> 32), left > 4 ? left - 4 : 0);
+      w[j] = a.nib | (c.nib << 16);
+      lo = a.lo | (c.lo << 4); hi = a.hi | (c.hi << 4); bad = a.bad | (c.bad << 4); isn = a.isn | (c.isn << 4);
+      const u32 isc = a.isc | (c.isc << 4);
+      if (isc) first_c = min(first_c, j * 8 + (u32)__ffs(isc) - 1u);
     }
     const unsigned s8 = 8u * (lane & 3);
     lo <<= s8; hi <<= s8; bad <<= s8; isn <<= s8;
@@ -169,9 +186,15 @@ __device__ __forceinline__ SeedHit seed_until_unique(const DevIndex& ix, const R
   return h;
 }
 
-// count_hash_table (bwt.h:1848-1952): exact interval of read[off .. off+cur)
+// count_hash_table (bwt.h:1848-1952): exact interval of read[off .. off+cur).
+// Once a single row is left the remaining LF steps can only keep that row or empty the interval, i.e. they compare
+// the rest of the pattern with the text to the left of that one suffix.  So the row is located and the rest of
+// the read is compared with the (C->T converted) double-strand sequence 32 bases at a time -- the same hits
+// (1 or 0) and, via site = 2N - SA - len - off with SA(final) = SA(row) - (cur - m), the same site, without a
+// chain of up to L dependent occ lookups.  hits >= 2 leave the interval in [sp, ep) for the locate kernel.
 __device__ __forceinline__ u64 count_exact(const DevIndex& ix, const ReadPlanes& rp, const unsigned char* lut, u32 off, u32 cur, u64& sp, u64& ep,
-                                           u32& n_occ, u32& n_hash) {
+                                           bool& have_site, u64& site, u32& n_occ, u32& n_hash, u32& n_rows, u32& n_llf) {
+  have_site = false;
   if (cur < 17) return 0;
   u32 key;
   if (!key16(rp, lut, off, key)) return 0;
@@ -181,6 +204,24 @@ __device__ __forceinline__ u64 count_exact(const DevIndex& ix, const ReadPlanes&
   SymbolStream ss(rp, off + 16);
   for (u32 m = 16; m < cur; ++m) {
     if (bot <= top) break;
+    if (bot - top == 1) {
+      int st; const u64 sa = locate_row(ix, top, st); n_llf += st; ++n_rows;
+      const u64 s0 = 2 * ix.N - sa - m;                 // double-strand coordinate of read[off]
+      if (s0 + cur > 2 * ix.N) return 0;                // the text ends before the pattern does
+      for (u32 p = off + m; p < off + cur; p += 32) {
+        u32 rlo, rhi, rbad; rp.window(p, rlo, rhi, rbad);
+        const u64 g = s0 + (p - off);
+        const uint2 w0 = __ldg(ix.planes + (g >> 5)), w1 = __ldg(ix.planes + (g >> 5) + 1);
+        const unsigned sh = (unsigned)g & 31u;
+        const u32 glo = __funnelshift_r(w0.x, w1.x, sh), ghi = __funnelshift_r(w0.y, w1.y, sh);
+        u32 mism = (rlo ^ glo) | (~rlo & (rhi ^ ghi)) | rbad;   // 3-letter equality: lo set (C/T) ignores hi
+        const u32 left = off + cur - p;
+        if (left < 32u) mism &= (1u << left) - 1u;
+        if (mism) return 0;
+      }
+      have_site = true; site = s0 - off;
+      return 1;
+    }
     const int c = ss.at(off + m);
     if (c > 2) return 0;
     n_occ += lf_pair(ix, top, bot, c);
@@ -223,39 +264,76 @@ __device__ __forceinline__ int compare_rest(const DevIndex& ix, const ReadPlanes
   return errors;
 }
 
-__global__ void __launch_bounds__(128) seed_reads(DevIndex ix, BatchView b) {
-  __shared__ u64 s_cnt[4];
-  __shared__ unsigned char s_lut[256];
-  if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+// ---- the seeding state machine of one read (Schema.cpp:27151-27515 / :19586-19906), cut into three kernels so
+// that the lanes of a warp do the same kind of work: (1) first seed + unique-hit shortcut for every read,
+// (2) the one-mismatch second seed, (3) the remaining seeds.  Reads move between them through compacted lists.
+struct SeedCounters { u32 n_occ = 0, n_hash = 0, n_rows = 0, n_llf = 0; };
+
+__device__ __forceinline__ void build_key_lut(unsigned char* lut) {
   for (u32 i = threadIdx.x; i < 256; i += blockDim.x) {     // i = fm bit0 of 4 bases | fm bit1 << 4
     u32 v = 0, p3 = 1;
     for (u32 t = 0; t < 4; ++t) { v += p3 * (((i >> t) & 1u) | (((i >> (4 + t)) & 1u) << 1)); p3 *= 3; }
-    s_lut[i] = (unsigned char)v;
+    lut[i] = (unsigned char)v;
   }
+}
+
+__device__ __forceinline__ void flush_counters(u64* s_cnt, const SeedCounters& c, u64* counters) {
+  atomicAdd(&s_cnt[0], (u64)c.n_hash); atomicAdd(&s_cnt[1], (u64)c.n_occ); atomicAdd(&s_cnt[2], (u64)c.n_rows); atomicAdd(&s_cnt[3], (u64)c.n_llf);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(counters + CNT_HASH, s_cnt[0]); atomicAdd(counters + CNT_OCC, s_cnt[1]);
+    atomicAdd(counters + CNT_ROWS, s_cnt[2]); atomicAdd(counters + CNT_LOCATE_LF, s_cnt[3]);
+  }
+}
+
+// warp-aggregated append of read r to a list (order is irrelevant: results are indexed by read)
+__device__ __forceinline__ void list_append(u32* list, u32* count, bool pred, u32 r) {
+  const u32 active = __activemask();
+  const u32 m = __ballot_sync(active, pred);
+  if (!m) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  u32 base = 0;
+  if (lane == leader) base = atomicAdd(count, (u32)__popc(m));
+  base = __shfl_sync(active, base, leader);
+  if (pred) list[base + __popc(m & ((1u << lane) - 1u))] = r;
+}
+
+struct TaskWriter {
+  BatchView& b; int r; u32 nt, nc;
+  __device__ __forceinline__ void emit(u64 a, u32 hits, u32 mlen, u32 o) {
+    if (nt < MAX_TASKS) { SeedTask t; t.sp = a; t.hits = hits; t.mlen = (unsigned short)mlen; t.off = (unsigned short)o; b.tasks[(size_t)nt * b.n_reads + r] = t; }
+    ++nt; nc += hits ? hits : 1u;
+  }
+  __device__ __forceinline__ void store() { b.ntask[r] = nt < MAX_TASKS ? nt : MAX_TASKS; b.ncand[r] = nt <= MAX_TASKS ? nc : 0xFFFFFFFFu; }
+};
+
+__global__ void __launch_bounds__(128) seed_first(DevIndex ix, BatchView b) {
+  __shared__ u64 s_cnt[4];
+  __shared__ unsigned char s_lut[256];
+  if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+  build_key_lut(s_lut);
   __syncthreads();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  u32 n_occ = 0, n_hash = 0, n_rows = 0, n_llf = 0;
+  SeedCounters cn;
+  bool to2 = false, to3 = false;
   if (r < b.n_reads) {
     const u32 L = b.len[r];
     ReadPlanes rp; rp.p = b.rplanes + plane_chunk_offset(b.offsets, r);
     const u32 first_c = b.first_c[r];
     u64 max_seeds = (u64)L / 10 - 1; if (max_seeds > 25) max_seeds = 25;   // u64 wrap for L < 10, as in the reference
-    u32 off = 0, nt = 0, nc = 0, first_len = 0;
-    u64 seed_id = 0, sp = 0, ep = 0, site0 = 0;
+    TaskWriter tw{b, r, 0, 0};
+    u32 off = 0, first_len = 0, seed_id = 0;
+    u64 sp = 0, ep = 0, site0 = 0;
     int state = BMBS_NONE, get_error = -1, one_mm = 0;
-    bool is_multi = false, extra = true, done = false;
-    auto emit = [&](u64 a, u32 hits, u32 mlen, u32 o) {
-      if (nt < MAX_TASKS) { SeedTask t; t.sp = a; t.hits = hits; t.mlen = (unsigned short)mlen; t.off = (unsigned short)o; b.tasks[(size_t)nt * b.n_reads + r] = t; }
-      ++nt; nc += hits ? hits : 1u;
-    };
-    if (seed_id < max_seeds && off < L) {
-      SeedHit h = seed_until_unique(ix, rp, s_lut, off, L - off, sp, ep, n_occ, n_hash);
+    bool is_multi = false, done = false;
+    if (max_seeds > 0 && L > 0) {
+      SeedHit h = seed_until_unique(ix, rp, s_lut, 0, L, sp, ep, cn.n_occ, cn.n_hash);
       sp = h.sp; ep = h.ep;
       u32 mlen = h.mlen; first_len = mlen;
       if (h.hits == 1) {
-        int st; const u64 sa = locate_row(ix, sp, st); n_llf += st; ++n_rows;
+        int st; const u64 sa = locate_row(ix, sp, st); cn.n_llf += st; ++cn.n_rows;
         const u64 site = 2 * ix.N - sa - mlen;
-        emit(site, 0, 0, 0);
+        tw.emit(site, 0, 0, 0);
         if (mlen > first_c) mlen = first_c;
         int errors = 0;
         if (mlen != L) errors = compare_rest(ix, rp, site, L, mlen);
@@ -268,48 +346,94 @@ __global__ void __launch_bounds__(128) seed_reads(DevIndex ix, BatchView b) {
           is_multi = true;
           if (first_c == L) {
             state = BMBS_MULTI_EXACT; done = true;
-            if (b.pe) emit(sp, (u32)h.hits, mlen, off);
+            if (b.pe) tw.emit(sp, (u32)h.hits, mlen, 0);
           }
         }
       }
       if (!done) {
-        if (h.hits != 1 && mlen >= b.seed_len && h.hits <= MAX_SEED_HITS && h.hits != 0) emit(sp, (u32)h.hits, mlen, off);
-        off = mlen == 0 ? next_offset_unmatched(rp, L, off) : off + mlen / 2;
-        ++seed_id;
+        if (h.hits != 1 && mlen >= b.seed_len && h.hits <= MAX_SEED_HITS && h.hits != 0) tw.emit(sp, (u32)h.hits, mlen, 0);
+        off = mlen == 0 ? next_offset_unmatched(rp, L, 0) : mlen / 2;
+        seed_id = 1;
       }
     }
-    if (!done && get_error == 1) {
-      const u32 len2 = L - first_len;
-      if (len2 >= 17) {
-        const u64 hits = count_exact(ix, rp, s_lut, first_len, len2, sp, ep, n_occ, n_hash);
-        if (hits <= MAX_SEED_HITS) { if (hits) emit(sp, (u32)hits, len2, first_len); extra = false; }
-      }
-    }
-    if (!done && extra) {
-      while (seed_id < max_seeds && off < L) {
-        const u32 cur = L - off;
-        SeedHit h = seed_until_unique(ix, rp, s_lut, off, cur, sp, ep, n_occ, n_hash);
-        sp = h.sp; ep = h.ep;
-        if (h.hits == 1) emit(sp, 1, h.mlen, off);
-        else if (h.mlen >= b.seed_len && h.hits <= MAX_SEED_HITS) { if (h.hits) emit(sp, (u32)h.hits, h.mlen, off); }
-        else if (cur == h.mlen) break;
-        off = h.mlen == 0 ? next_offset_unmatched(rp, L, off) : off + h.mlen / 2;
-        ++seed_id;
-      }
-    }
+    if (!done) { to2 = get_error == 1; to3 = !to2; }
     b.state[r] = (unsigned char)state;
-    b.flags[r] = (unsigned char)((is_multi ? 1 : 0) | (extra ? 0 : 2));
+    b.flags[r] = (unsigned char)(is_multi ? 1 : 0);
     b.one_mm[r] = (short)one_mm;
     b.site0[r] = site0;
-    b.ntask[r] = nt < MAX_TASKS ? nt : MAX_TASKS;
-    b.ncand[r] = nt <= MAX_TASKS ? nc : 0xFFFFFFFFu;  // overflow is reported by the host
+    b.ph_off[r] = (unsigned short)off; b.ph_first_len[r] = (unsigned short)first_len; b.ph_seed_id[r] = (unsigned char)seed_id;
+    tw.store();
   }
-  atomicAdd(&s_cnt[0], (u64)n_hash); atomicAdd(&s_cnt[1], (u64)n_occ); atomicAdd(&s_cnt[2], (u64)n_rows); atomicAdd(&s_cnt[3], (u64)n_llf);
+  list_append(b.list2, b.list_count, to2, (u32)r);
+  list_append(b.list3, b.list_count + 1, to3, (u32)r);
+  flush_counters(s_cnt, cn, b.counters);
+}
+
+// one-mismatch rule: a single second seed covering read[first_len .. L)  (Schema.cpp:27334-27401)
+__global__ void __launch_bounds__(128) seed_second(DevIndex ix, BatchView b) {
+  __shared__ u64 s_cnt[4];
+  __shared__ unsigned char s_lut[256];
+  if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+  build_key_lut(s_lut);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    atomicAdd(b.counters + CNT_HASH, s_cnt[0]); atomicAdd(b.counters + CNT_OCC, s_cnt[1]);
-    atomicAdd(b.counters + CNT_ROWS, s_cnt[2]); atomicAdd(b.counters + CNT_LOCATE_LF, s_cnt[3]);
+  const u32 n2 = b.list_count[0];
+  SeedCounters cn;
+  for (u32 base = blockIdx.x * blockDim.x; base < n2; base += gridDim.x * blockDim.x) {
+    const u32 i = base + threadIdx.x;
+    bool to3 = false; u32 r = 0;
+    if (i < n2) {
+      r = b.list2[i];
+      const u32 L = b.len[r], first_len = b.ph_first_len[r];
+      ReadPlanes rp; rp.p = b.rplanes + plane_chunk_offset(b.offsets, (int)r);
+      TaskWriter tw{b, (int)r, b.ntask[r], b.ncand[r]};
+      const u32 len2 = L - first_len;
+      bool extra = true;
+      if (len2 >= 17) {
+        u64 sp = 0, ep = 0, site = 0; bool have_site = false;
+        const u64 hits = count_exact(ix, rp, s_lut, first_len, len2, sp, ep, have_site, site, cn.n_occ, cn.n_hash, cn.n_rows, cn.n_llf);
+        if (hits <= MAX_SEED_HITS) {
+          if (have_site) tw.emit(site, 0, 0, 0); else if (hits) tw.emit(sp, (u32)hits, len2, first_len);
+          extra = false;
+        }
+      }
+      if (!extra) b.flags[r] |= 2;
+      to3 = extra;
+      tw.store();
+    }
+    list_append(b.list3, b.list_count + 1, to3, r);
   }
+  flush_counters(s_cnt, cn, b.counters);
+}
+
+// the remaining seeds (Schema.cpp:27434-27515)
+__global__ void __launch_bounds__(128) seed_rest(DevIndex ix, BatchView b) {
+  __shared__ u64 s_cnt[4];
+  __shared__ unsigned char s_lut[256];
+  if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+  build_key_lut(s_lut);
+  __syncthreads();
+  const u32 n3 = b.list_count[1];
+  SeedCounters cn;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += gridDim.x * blockDim.x) {
+    const u32 r = b.list3[i];
+    const u32 L = b.len[r];
+    ReadPlanes rp; rp.p = b.rplanes + plane_chunk_offset(b.offsets, (int)r);
+    u64 max_seeds = (u64)L / 10 - 1; if (max_seeds > 25) max_seeds = 25;
+    TaskWriter tw{b, (int)r, b.ntask[r], b.ncand[r]};
+    u32 off = b.ph_off[r]; u64 seed_id = b.ph_seed_id[r], sp = 0, ep = 0;
+    while (seed_id < max_seeds && off < L) {
+      const u32 cur = L - off;
+      SeedHit h = seed_until_unique(ix, rp, s_lut, off, cur, sp, ep, cn.n_occ, cn.n_hash);
+      sp = h.sp; ep = h.ep;
+      if (h.hits == 1) tw.emit(sp, 1, h.mlen, off);
+      else if (h.mlen >= b.seed_len && h.hits <= MAX_SEED_HITS) { if (h.hits) tw.emit(sp, (u32)h.hits, h.mlen, off); }
+      else if (cur == h.mlen) break;
+      off = h.mlen == 0 ? next_offset_unmatched(rp, L, off) : off + h.mlen / 2;
+      ++seed_id;
+    }
+    tw.store();
+  }
+  flush_counters(s_cnt, cn, b.counters);
 }
 
 // ------------------------------------------------------------------------------------------- expand + locate

@@ -94,13 +94,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=0.0, t1=1e30):
+        """samples taken inside [t0, t1] (the timed region); if the region was shorter than the sampling period,
+        every sample since start() -- the sampler is started before the warm-up, so those are under load too"""
         if self.p:
             self.p.terminate()
+        inside = [r for t, r in self.rows if t0 <= t <= t1]
+        rows = inside if len(inside) >= 2 else [r for _, r in self.rows]
         sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             try:
                 sm.append(float(f[0])); mx = max(mx, float(f[1]))
@@ -109,7 +113,8 @@ class ClockSampler:
             for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm),
+                "window": "timed region" if len(inside) >= 2 else "warm-up + timed region"}
 
 
 # ------------------------------------------------------------------------------------------------ reference CPU arm
@@ -139,7 +144,7 @@ def run_reference(d: Path, m1, m2, sample_pairs: int, threads: int, repeats: int
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU per step")
@@ -225,9 +230,18 @@ def main():
                 raise
             batch.close(); cand_cap *= 2
     states = np.bincount(res["state"], minlength=5)
+    # second in-flight batch for the end-to-end loop: copies of one batch overlap the kernels of the other
+    batch2 = B.Batch(index, dev, n_reads, bases + 64, cand_cap)
+    h_res2 = torch.empty(n_reads * capi.ReadResult.itemsize, dtype=torch.uint8, pin_memory=True)
+    h_cand2 = torch.empty(cand_cap * capi.Cand.itemsize, dtype=torch.uint8, pin_memory=True)
+    outs = [(batch, res, cand), (batch2, h_res2.numpy().view(capi.ReadResult), h_cand2.numpy().view(capi.Cand))]
+    clocks = ClockSampler(dev); clocks.start()
     for _ in range(max(0, a.warmup - 1)):
         batch.run(prm)
     batch.sync()
+    for i in range(a.warmup):
+        bb, rr, cc = outs[i & 1]
+        bb.upload(flat, offs, pe=True); bb.run(prm); bb.download(rr, cc)
 
     def barrier():
         torch.cuda.synchronize()
@@ -236,8 +250,8 @@ def main():
         torch.cuda.synchronize()
 
     # ---- timed: device-resident steps
-    clocks = ClockSampler(dev); clocks.start()
     barrier()
+    t_begin = time.time()
     stage = {}
     dev_ms = 0.0
     w0 = time.perf_counter()
@@ -253,13 +267,22 @@ def main():
     counters = batch.counters()
     launches = batch.launches() * a.steps
     # ---- timed: end to end through the C ABI, host buffers in / out
+    # (every step: H2D of the step's reads from pinned host memory, kernels, D2H of its records; two batches in
+    # flight on two streams, as the host mapper drives them)
     barrier()
     e0 = time.perf_counter()
-    for _ in range(a.steps):
-        batch.upload(flat, offs, pe=True); batch.run(prm); _, _, used = batch.download(res, cand)
+    for i in range(a.steps):
+        bb, rr, cc = outs[i & 1]
+        bb.upload(flat, offs, pe=True); bb.run(prm)
+        if i > 0:
+            pb, pr, pc = outs[(i - 1) & 1]
+            _, _, used = pb.download(pr, pc)
+    pb, pr, pc = outs[(a.steps - 1) & 1]
+    _, _, used = pb.download(pr, pc)
     e2e_ms = (time.perf_counter() - e0) * 1000
     barrier()
-    clk = clocks.stop()
+    clk = clocks.stop(t_begin, time.time())
+    assert np.array_equal(outs[0][1]["state"], outs[1][1]["state"])
     h2d = int(bases + 8 * (n_reads + 1)); d2h = int(n_reads * capi.ReadResult.itemsize + used * capi.Cand.itemsize)
 
     if dist:
@@ -283,7 +306,8 @@ def main():
     per_step = {k: v / a.steps for k, v in stage.items()}
     seed_bytes = 10 * counters["hash_queries"] + 40 * counters["occ_lookups"]
     # rows located inside the seed kernel (unique first seeds) are counted with it; the rest belongs to locate_rows
-    loc_bytes = counters["locate_lf_steps"] * 80 + counters["located_rows"] * 44
+    # sampled suffix array: 80 B per LF step + 44 B per row; dense suffix array (default): one 4-byte entry per row
+    loc_bytes = counters["locate_lf_steps"] * 80 + counters["located_rows"] * (44 if counters["locate_lf_steps"] else 4)
     ver_bytes = counters["window_bytes"]
     kernels = {"seed_first+second+rest": (per_step["seed"], seed_bytes), "locate_rows": (per_step["locate"], loc_bytes), "verify_windows": (per_step["verify"], ver_bytes)}
     dom = max(kernels, key=lambda k: kernels[k][0])

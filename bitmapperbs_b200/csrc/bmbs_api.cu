@@ -62,8 +62,17 @@ int load_files(const std::string& prefix, HostIndex& h) {
 
 struct DeviceCopy {
   int dev = 0; DevIndex view{}; size_t bytes = 0;
-  void *occ = nullptr, *flag = nullptr, *hash = nullptr, *ssa = nullptr, *planes = nullptr;
+  void *occ = nullptr, *flag = nullptr, *hash = nullptr, *ssa = nullptr, *planes = nullptr, *dsa_lo = nullptr, *dsa_hi = nullptr;
 };
+
+// every row's suffix-array value from the sampled one, once per index load (the same walk the reference does per hit)
+__global__ void __launch_bounds__(256) densify_sa(DevIndex ix, u32* lo, unsigned char* hi) {
+  for (u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x; row < ix.n_rows; row += (u64)gridDim.x * blockDim.x) {
+    int st; const u64 sa = locate_row_walk(ix, row, st);
+    lo[row] = (u32)sa;
+    if (hi) hi[row] = (unsigned char)(sa >> 32);
+  }
+}
 
 }  // namespace
 
@@ -80,7 +89,7 @@ extern "C" uint64_t bmbs_index_device_bytes(const bmbs_index* idx) { return idx 
 
 extern "C" void bmbs_index_free(bmbs_index* idx) {
   if (!idx) return;
-  for (auto& c : idx->copies) { cudaSetDevice(c.dev); cudaFree(c.occ); cudaFree(c.flag); cudaFree(c.hash); cudaFree(c.ssa); cudaFree(c.planes); }
+  for (auto& c : idx->copies) { cudaSetDevice(c.dev); cudaFree(c.occ); cudaFree(c.flag); cudaFree(c.hash); cudaFree(c.ssa); cudaFree(c.planes); cudaFree(c.dsa_lo); cudaFree(c.dsa_hi); }
   delete idx;
 }
 
@@ -163,6 +172,27 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
     v.ssa = (const u32*)c.ssa; v.planes = (const uint2*)c.planes;
     v.C[0] = h.nacgt[0]; v.C[1] = h.nacgt[1]; v.C[2] = h.nacgt[2];
     v.shapline = h.shapline; v.n_rows = h.sa_length; v.N = h.N;
+    v.dsa_lo = nullptr; v.dsa_hi = nullptr;
+    // ---- dense suffix array (BMBS_SA=sampled keeps the on-disk 1/8 sampling; default: dense when it fits with room to spare)
+    const char* mode = getenv("BMBS_SA");
+    const bool wide = h.sa_length > 0xFFFFFFFFull;
+    const size_t need = (size_t)h.sa_length * (wide ? 5 : 4);
+    size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
+    const bool want = mode ? strcmp(mode, "sampled") != 0 : need + (total_b >> 2) < free_b;
+    if (want) {
+      DeviceCopy& cc = idx->copies.back();
+      e = cudaMalloc(&cc.dsa_lo, (size_t)h.sa_length * 4 + 256);
+      if (e == cudaSuccess && wide) e = cudaMalloc(&cc.dsa_hi, (size_t)h.sa_length + 256);
+      if (e == cudaSuccess) {
+        cudaDeviceProp prop; cudaGetDeviceProperties(&prop, cc.dev);
+        densify_sa<<<prop.multiProcessorCount * 8, 256>>>(v, (u32*)cc.dsa_lo, (unsigned char*)cc.dsa_hi);
+        e = cudaDeviceSynchronize();
+      }
+      if (e != cudaSuccess) { std::string m = std::string("dense suffix array: ") + cudaGetErrorString(e); bmbs_index_free(idx); return fail(BMBS_ERR_CUDA, m); }
+      v.dsa_lo = (const u32*)cc.dsa_lo; v.dsa_hi = (const unsigned char*)cc.dsa_hi;
+      cudaFree(cc.flag); cudaFree(cc.ssa); cc.flag = nullptr; cc.ssa = nullptr; v.flag = nullptr; v.ssa = nullptr;
+      cc.bytes += need; cc.bytes -= flag.size() * 8 + h.ssa.size() * 4;
+    }
   }
   *out = idx;
   return BMBS_OK;

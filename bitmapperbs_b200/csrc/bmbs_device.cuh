@@ -9,7 +9,8 @@
 //   flag   : one 16-byte block per 64 rows: { u64 sampled-row flags, u64 rank
 //            before the block } (reference: 5 words per 256 rows, bwt.h:2449-2560).
 //   hash   : u64 per 16-mer: 36-bit first row | 4-bit gap << 60 (bwt.h:284-306).
-//   ssa    : u32 sampled suffix array, unchanged (top two bits masked on use).
+//   ssa    : u32 sampled suffix array, unchanged (top two bits masked on use); replaced at load by the
+//            dense array dsa (u32 per row, +u8 above 2^32 rows) when HBM allows: see locate_row.
 //   planes : the 2N-base double-strand sequence  G ++ revcomp(G)  as interleaved
 //            bit-planes {lo, hi} per 32 bases, LSB = first base, so that any
 //            window is two funnel shifts away (reference: 2-bit bytes decoded
@@ -28,7 +29,9 @@ struct DevIndex {
   const ulonglong2* flag;
   const u64* hash;
   const u32* ssa;
-  const uint2* planes;
+ const uint2* planes;
+  const u32* dsa_lo;          // dense suffix array (one entry per row), low 32 bits; null = walk to a sampled row
+  const unsigned char* dsa_hi; // bits 32..39 when the text is longer than 2^32
   u64 C[3];        // first row of symbols G(0), T(1), A(2)   (nacgt[c], bwt.cpp:1715-1729)
   u64 shapline;    // row whose BWT symbol is '$' (omitted from the planes)
   u64 n_rows;      // text length + 1
@@ -84,7 +87,7 @@ __device__ __forceinline__ void hash_query(const DevIndex& ix, u64 key, u64& sp,
 }
 
 // Single-row locate: walk LF until a sampled row.  bwt.h:2449-2560.  `steps_out` counts LF steps.
-__device__ __forceinline__ u64 locate_row(const DevIndex& ix, u64 row, int& steps_out) {
+__device__ __forceinline__ u64 locate_row_walk(const DevIndex& ix, u64 row, int& steps_out) {
   int steps = 0;
   u64 sa;
   for (;;) {
@@ -105,6 +108,19 @@ __device__ __forceinline__ u64 locate_row(const DevIndex& ix, u64 row, int& step
   }
   steps_out = steps;
   return sa;
+}
+
+// Single-row locate.  With 180 GB of HBM the suffix array does not have to stay sampled: at load every row's
+// value is computed once on the device (densify_sa) and locate becomes one 4-byte (5-byte) gather instead of
+// up to 7 dependent LF steps of two sectors each.  Same value as the walk by construction.
+__device__ __forceinline__ u64 locate_row(const DevIndex& ix, u64 row, int& steps_out) {
+  if (ix.dsa_lo) {
+    steps_out = 0;
+    u64 sa = __ldg(ix.dsa_lo + row);
+    if (ix.dsa_hi) sa |= (u64)__ldg(ix.dsa_hi + row) << 32;
+    return sa;
+  }
+  return locate_row_walk(ix, row, steps_out);
 }
 
 // 2-bit code (A0 C1 G2 T3) of base `pos` of the double-strand sequence.

@@ -196,7 +196,8 @@ inline void map_pair_fast(const Index& ix, const Params& P, const char* read1, c
   } else if (o.n_pairs > 1) ++st.ambiguous;
 }
 
-bool run_pe_sensitive_pair(const Index&, const Params&, const char*, const char*, int, const char*, const char*, int, PairOutcome&, Stats&);
+struct SensDebug;
+bool run_pe_sensitive_pair(const Index&, const Params&, const char*, const char*, int, const char*, const char*, int, PairOutcome&, Stats&, SensDebug* dbg = nullptr);
 
 }  // namespace oracle
 
@@ -221,8 +222,5 @@ inline bool run_pe(const Index& ix, const Params& P, const char* f1, const char*
   }
   fwrite(out.data(), 1, out.size(), fo); fclose(fo);
   return true;
-}
-inline bool run_pe_sensitive_pair(const Index&, const Params&, const char*, const char*, int, const char*, const char*, int, PairOutcome& o, Stats&) {
-  o = PairOutcome(); fprintf(stderr, "oracle: --sensitive restatement not built yet\n"); return false;
 }
 }  // namespace oracle

@@ -6,6 +6,7 @@
 #include <vector>
 #include "oracle_core.hpp"
 #include "oracle_pe.hpp"
+#include "oracle_pe_sensitive.hpp"
 #include "../include/bmbs.h"
 
 using namespace oracle;

@@ -8,6 +8,7 @@
 #include <string>
 #include "oracle_core.hpp"
 #include "oracle_pe.hpp"
+#include "oracle_pe_sensitive.hpp"
 #include "../bitmapperbs_b200/csrc/host/fastq.hpp"
 #include "../bitmapperbs_b200/csrc/host/sam.hpp"
 

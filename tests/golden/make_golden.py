@@ -7,6 +7,9 @@
   se250.fq.gz  -> se250.sam.gz      600 x 250 bp single end (k = 20: 64-bit bands)
   pe150_[12].fq.gz -> pe150.sam.gz  1500 pairs x 150 bp, --pe (fast mode)
   pe150s.sam.gz                     same pairs, --pe --sensitive
+  pe100h_[12].fq.gz -> pe100h.sam.gz (--pe) and pe100hs.sam.gz (--pe --sensitive): 2500 pairs x 100 bp with 5 % substitutions,
+                                    0.8 % indels, 3 % junk -- hard enough that the sensitive mode's mate filter and
+                                    re-seeding change the outcome of several hundred pairs
   *.stats                           the five --mapstats lines of each run
   index_sha256.json                 sha256 of every file `--index` wrote (the .sa hash skips its last 8 bytes,
                                     which the reference leaves uninitialised)
@@ -50,6 +53,8 @@ def main():
         p1, p2 = S.simulate_reads(chroms, 1500, 150, seed=3, paired=True, sub=0.015, indel=0.002, n_rate=0.001, random_qual=True, junk_fraction=0.01)
         S.write_fastq(w / "se100.fq", se100); S.write_fastq(w / "se250.fq", se250)
         S.write_fastq(w / "pe150_1.fq", p1); S.write_fastq(w / "pe150_2.fq", p2)
+        h1, h2 = S.simulate_reads(chroms, 2500, 100, seed=16, paired=True, sub=0.05, indel=0.008, n_rate=0.003, random_qual=True, frag_range=(150, 420), junk_fraction=0.03)
+        S.write_fastq(w / "pe100h_1.fq", h1); S.write_fastq(w / "pe100h_2.fq", h2)
         shutil.copy(SHIM, w / "psascan")
         run = lambda *a: subprocess.run([str(REF), *a], cwd=w, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         run("--index", "genome.fa")
@@ -57,9 +62,11 @@ def main():
         run("--search", "genome.fa", "--seq", "se250.fq", "-t", "1", "-o", "se250.sam", "--mapstats", "se250.stats")
         run("--search", "genome.fa", "--seq1", "pe150_1.fq", "--seq2", "pe150_2.fq", "--pe", "-t", "1", "-o", "pe150.sam", "--mapstats", "pe150.stats")
         run("--search", "genome.fa", "--seq1", "pe150_1.fq", "--seq2", "pe150_2.fq", "--pe", "--sensitive", "-t", "1", "-o", "pe150s.sam", "--mapstats", "pe150s.stats")
-        for f in ["genome.fa", "se100.fq", "se250.fq", "pe150_1.fq", "pe150_2.fq"]:
+        run("--search", "genome.fa", "--seq1", "pe100h_1.fq", "--seq2", "pe100h_2.fq", "--pe", "-t", "1", "-o", "pe100h.sam", "--mapstats", "pe100h.stats")
+        run("--search", "genome.fa", "--seq1", "pe100h_1.fq", "--seq2", "pe100h_2.fq", "--pe", "--sensitive", "-t", "1", "-o", "pe100hs.sam", "--mapstats", "pe100hs.stats")
+        for f in ["genome.fa", "se100.fq", "se250.fq", "pe150_1.fq", "pe150_2.fq", "pe100h_1.fq", "pe100h_2.fq"]:
             gz_write(HERE / (f + ".gz"), (w / f).read_bytes())
-        for f in ["se100", "se250", "pe150", "pe150s"]:
+        for f in ["se100", "se250", "pe150", "pe150s", "pe100h", "pe100hs"]:
             gz_write(HERE / (f + ".sam.gz"), body(w / (f + ".sam")))
             shutil.copy(w / (f + ".stats"), HERE / (f + ".stats"))
         hashes = {}

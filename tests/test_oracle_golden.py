@@ -22,6 +22,9 @@ def test_index_files_identical_to_reference(golden):
     ("se100", ["se", "genome.fa", "se100.fq", "out.sam"]),
     ("se250", ["se", "genome.fa", "se250.fq", "out.sam"]),
     ("pe150", ["pe", "genome.fa", "pe150_1.fq", "pe150_2.fq", "out.sam"]),
+    ("pe150s", ["pe", "genome.fa", "pe150_1.fq", "pe150_2.fq", "out.sam", "1"]),     # --pe --sensitive
+    ("pe100h", ["pe", "genome.fa", "pe100h_1.fq", "pe100h_2.fq", "out.sam"]),
+    ("pe100hs", ["pe", "genome.fa", "pe100h_1.fq", "pe100h_2.fq", "out.sam", "1"]),  # --pe --sensitive, mate filter + re-seeding matter
 ])
 def test_oracle_sam_identical_to_reference(golden, built, name, args):
     r = subprocess.run([str(built["oracle_cli"]), *args], cwd=golden, stderr=subprocess.PIPE, check=True)

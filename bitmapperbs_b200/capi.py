@@ -185,7 +185,7 @@ class Batch:
     def timings(self):
         ms = (C.c_float * 8)()
         _check(self._L.bmbs_batch_timings(self._h, ms))
-        return dict(zip(["total", "pack", "seed", "locate", "votes", "pair_filter", "verify"], list(ms)[:7]))
+        return dict(zip(["total", "pack", "seed", "locate", "votes", "pair_filter", "verify", "sensitive"], list(ms)[:8]))
 
     def counters(self):
         c = (C.c_uint64 * 8)()

@@ -208,7 +208,7 @@ struct bmbs_batch {
   char* d_ascii = nullptr; u64* d_offsets = nullptr;
   u64* d_tile = nullptr;
   u64* h_small = nullptr;        // pinned: totals[2], status, counters[8]
-  cudaEvent_t ev[8] = {nullptr};
+  cudaEvent_t ev[9] = {nullptr};
   int n_reads = 0, pe = 0, max_len = 0, launches = 0, sm_count = 148;
   bool ran = false;
 };
@@ -248,6 +248,7 @@ extern "C" int bmbs_batch_create(bmbs_index* idx, int dev, size_t max_reads, siz
   A(dalloc(b, &v.codes, max_bases / 8 + R + 64)); A(dalloc(b, &v.rplanes, max_bases / 32 + 2 * R + 64)); A(dalloc(b, &v.len, R)); A(dalloc(b, &v.first_c, R)); A(dalloc(b, &v.kk, R));
   A(dalloc(b, &v.state, R)); A(dalloc(b, &v.flags, R)); A(dalloc(b, &v.one_mm, R)); A(dalloc(b, &v.site0, R));
   A(dalloc(b, &v.ph_off, R)); A(dalloc(b, &v.ph_first_len, R)); A(dalloc(b, &v.ph_seed_id, R)); A(dalloc(b, &v.list2, R)); A(dalloc(b, &v.list3, R)); A(dalloc(b, &v.list_count, 4));
+  A(dalloc(b, &v.bk, 5 * R)); A(dalloc(b, &v.first_cands, R)); A(dalloc(b, &v.list4, R)); A(dalloc(b, &v.res_first, R)); A(dalloc(b, &v.res_n, R));
   A(dalloc(b, &v.ntask, R)); A(dalloc(b, &v.ncand, R)); A(dalloc(b, &v.coff, R)); A(dalloc(b, &v.tasks, (size_t)MAX_TASKS * max_reads));
   A(dalloc(b, &v.slot_row, S)); A(dalloc(b, &v.slot_adj, S)); A(dalloc(b, &v.slot_read, S)); A(dalloc(b, &v.cand, S)); A(dalloc(b, &v.vcnt, S));
   A(dalloc(b, &v.nv, R)); A(dalloc(b, &v.voff, R)); A(dalloc(b, &v.keep, S));
@@ -284,10 +285,10 @@ extern "C" int bmbs_batch_upload(bmbs_batch* b, const char* seqs, const uint64_t
 }
 
 namespace {
-int run_scan(bmbs_batch* b, const u32* in, u32 n, u32* out, u64* total, u64 cap, u32 cap_bit) {
+int run_scan(bmbs_batch* b, const u32* in, u32 n, u32* out, u64* total, u64 cap, u32 cap_bit, const u64* base = nullptr) {
   const u32 tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
   scan_tiles<<<tiles, SCAN_TILE, 0, b->stream>>>(in, n, b->d_tile, b->v.status);
-  scan_tile_sums<<<1, 1024, 0, b->stream>>>(b->d_tile, tiles, total, cap, b->v.status, cap_bit);
+  scan_tile_sums<<<1, 1024, 0, b->stream>>>(b->d_tile, tiles, total, cap, b->v.status, cap_bit, base);
   scan_apply<<<tiles, SCAN_TILE, 0, b->stream>>>(in, n, b->d_tile, out);
   b->launches += 3;
   return 0;
@@ -296,12 +297,13 @@ int run_scan(bmbs_batch* b, const u32* in, u32 n, u32* out, u64* total, u64 cap,
 
 extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
   if (!b || !prm) return fail(BMBS_ERR_ARG, "bad argument");
-  if (prm->sensitive) return fail(BMBS_ERR_ARG, "--sensitive pairing is not implemented on the GPU path yet");
+  if (prm->sensitive && !b->pe) return fail(BMBS_ERR_ARG, "sensitive=1 only applies to paired batches (Process_CommandLines.cpp: --sensitive is a --pe mode)");
   CU(cudaSetDevice(b->dev));
   BatchView& v = b->v;
   const int n = b->n_reads;
   v.ascii = b->d_ascii; v.offsets = b->d_offsets; v.n_reads = n; v.pe = b->pe;
   v.e_rate = prm->e_rate; v.seed_len = (u32)prm->seed_len; v.dmax_base = prm->max_ins; v.dmin_base = prm->min_ins;
+  v.sensitive = prm->sensitive ? 1 : 0; v.round = 0; v.multi_cap = prm->sensitive ? MAX_PE_MULTI_SENSITIVE : MAX_PE_MULTI;
   b->launches = 0;
   cudaStream_t s = b->stream;
   const DevIndex ix = b->copy->view;
@@ -322,23 +324,42 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
     votes_small<<<(n + 3) / 4, 128, 0, s>>>(v); ++b->launches;
     votes_big<<<b->sm_count * 4, 256, 0, s>>>(v); ++b->launches;
     CU(cudaEventRecord(b->ev[4], s));
-    if (b->pe) { filter_pairs_kernel<<<(n / 2 + 127) / 128, 128, 0, s>>>(v); ++b->launches; }
+    if (b->pe && !v.sensitive) { filter_pairs_kernel<<<(n / 2 + 127) / 128, 128, 0, s>>>(v); ++b->launches; }
     CU(cudaEventRecord(b->ev[5], s));
-    run_scan(b, v.nv, (u32)n, v.voff, v.totals + 1, v.slot_cap, 4u);
-    gather_work<<<b->sm_count * 8, 256, 0, s>>>(v); ++b->launches;
     const int nch2 = (b->max_len + 31) / 32 + 2;
     int bd = 128;
     while (bd > 32 && (size_t)5 * nch2 * bd * 8 > 96 * 1024) bd >>= 1;
     const size_t smem = (size_t)5 * nch2 * bd * 8;
     int per_sm = (int)((200 * 1024) / (smem + 1024)); if (per_sm > 12) per_sm = 12; if (per_sm < 1) per_sm = 1;
+    run_scan(b, v.nv, (u32)n, v.voff, v.totals + 1, v.slot_cap, 4u);
+    gather_work<<<b->sm_count * 8, 256, 0, s>>>(v); ++b->launches;
     verify_windows<<<b->sm_count * per_sm, bd, smem, s>>>(ix, v, nch2); ++b->launches;
     CU(cudaEventRecord(b->ev[6], s));
+    if (v.sensitive) {
+      // --pe --sensitive: pair logic on the verified lists, then one re-seeding round for the mates left without a hit
+      sens_pair<<<(n / 2 + 127) / 128, 128, 0, s>>>(v); ++b->launches;
+      reseed_clear<<<(n + 255) / 256, 256, 0, s>>>(v); ++b->launches;
+      BatchView w = v; w.round = 1;
+      seed_reseed<<<b->sm_count * 8, 128, 0, s>>>(ix, w); ++b->launches;
+      run_scan(b, w.ncand, (u32)n, w.coff, w.totals, w.slot_cap, 2u);
+      expand_tasks<<<(n + 127) / 128, 128, 0, s>>>(w); ++b->launches;
+      locate_rows<<<b->sm_count * 8, 256, 0, s>>>(ix, w); ++b->launches;
+      votes_small<<<(n + 3) / 4, 128, 0, s>>>(w); ++b->launches;
+      votes_big<<<b->sm_count * 4, 256, 0, s>>>(w); ++b->launches;
+      sens_reseed_filter<<<b->sm_count * 4, 128, 0, s>>>(w); ++b->launches;
+      run_scan(b, w.nv, (u32)n, w.voff, w.totals + 1, w.slot_cap, 4u, w.totals + 2);
+      gather_work<<<b->sm_count * 8, 256, 0, s>>>(w); ++b->launches;
+      verify_windows<<<b->sm_count * per_sm, bd, smem, s>>>(ix, w, nch2); ++b->launches;
+      sens_reseed_finish<<<b->sm_count * 4, 128, 0, s>>>(w); ++b->launches;
+    }
+    CU(cudaEventRecord(b->ev[7], s));
     finalize_reads<<<(n + 255) / 256, 256, 0, s>>>(v); ++b->launches;
   } else {
-    for (int i = 1; i <= 6; ++i) CU(cudaEventRecord(b->ev[i], s));
+    for (int i = 1; i <= 7; ++i) CU(cudaEventRecord(b->ev[i], s));
   }
-  CU(cudaEventRecord(b->ev[7], s));
+  CU(cudaEventRecord(b->ev[8], s));
   CU(cudaMemcpyAsync(b->h_small, v.totals, 2 * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(b->h_small + 12, v.totals + 3, 8, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(b->h_small + 2, v.status, 4, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(b->h_small + 4, v.counters, 8 * 8, cudaMemcpyDeviceToHost, s));
   CU(cudaGetLastError());
@@ -356,7 +377,7 @@ extern "C" int bmbs_batch_sync(bmbs_batch* b) {
 namespace {
 int check_status(bmbs_batch* b, size_t* used) {
   const u32 st = *(const u32*)(b->h_small + 2);
-  if (used) *used = (size_t)b->h_small[1];
+  if (used) *used = (size_t)b->h_small[12];
   if (st & 1u) return fail(BMBS_ERR_CAPACITY, "a read produced more seed tasks than the per-read table holds");
   if (st & 2u) { if (used) *used = (size_t)b->h_small[0]; return fail(BMBS_ERR_CAPACITY, "candidate slots exceed the batch capacity (" + std::to_string(b->h_small[0]) + " needed): create the batch with a larger cand_cap or send fewer reads"); }
   if (st & 4u) return fail(BMBS_ERR_CAPACITY, "verification work exceeds the batch capacity");
@@ -371,7 +392,7 @@ extern "C" int bmbs_batch_download(bmbs_batch* b, bmbs_read_result* res, bmbs_ca
   CU(cudaStreamSynchronize(b->stream));
   int rc = check_status(b, cand_used);
   if (rc) return rc;
-  const size_t work = (size_t)b->h_small[1];
+  const size_t work = (size_t)b->h_small[12];     // out_cand entries of all rounds
   if (work > cand_cap) { if (cand_used) *cand_used = work; return fail(BMBS_ERR_CAPACITY, "caller's cand[] holds " + std::to_string(cand_cap) + " entries, " + std::to_string(work) + " needed"); }
   if (b->n_reads) CU(cudaMemcpyAsync(res, b->v.out_res, (size_t)b->n_reads * sizeof(bmbs_read_result), cudaMemcpyDeviceToHost, b->stream));
   if (work) { if (!cand) return fail(BMBS_ERR_ARG, "cand is null"); CU(cudaMemcpyAsync(cand, b->v.out_cand, work * sizeof(bmbs_cand), cudaMemcpyDeviceToHost, b->stream)); }
@@ -382,10 +403,9 @@ extern "C" int bmbs_batch_download(bmbs_batch* b, bmbs_read_result* res, bmbs_ca
 extern "C" int bmbs_batch_timings(bmbs_batch* b, float ms[8]) {
   if (!b || !b->ran || !ms) return fail(BMBS_ERR_ARG, "bad argument or batch not run");
   CU(cudaSetDevice(b->dev));
-  CU(cudaEventSynchronize(b->ev[7]));
-  CU(cudaEventElapsedTime(&ms[0], b->ev[0], b->ev[7]));
-  for (int i = 1; i <= 6; ++i) CU(cudaEventElapsedTime(&ms[i], b->ev[i - 1], b->ev[i]));
-  ms[7] = 0;
+  CU(cudaEventSynchronize(b->ev[8]));
+  CU(cudaEventElapsedTime(&ms[0], b->ev[0], b->ev[8]));
+  for (int i = 1; i <= 7; ++i) CU(cudaEventElapsedTime(&ms[i], b->ev[i - 1], b->ev[i]));
   return BMBS_OK;
 }
 
@@ -486,13 +506,13 @@ extern "C" int bmbs_verify(bmbs_index* idx, int dev, const char* seqs, const uin
   const size_t smem = (size_t)5 * nch2 * bd * 8;
   int per_sm = (int)((200 * 1024) / (smem + 1024)); if (per_sm > 12) per_sm = 12; if (per_sm < 1) per_sm = 1;
   verify_windows<<<b->sm_count * per_sm, bd, smem, s>>>(b->copy->view, v, nch2); ++b->launches;
-  CU(cudaEventRecord(b->ev[6], s)); CU(cudaEventRecord(b->ev[7], s));
+  CU(cudaEventRecord(b->ev[6], s)); CU(cudaEventRecord(b->ev[7], s)); CU(cudaEventRecord(b->ev[8], s));
   CU(cudaMemcpyAsync(b->h_small + 4, v.counters, 8 * 8, cudaMemcpyDeviceToHost, s));
   std::vector<bmbs_cand> tmp(n);
   if (n) CU(cudaMemcpyAsync(tmp.data(), v.out_cand, n * sizeof(bmbs_cand), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   CU(cudaGetLastError());
-  b->h_small[0] = 0; b->h_small[1] = n; *(u32*)(b->h_small + 2) = 0; b->ran = true;
+  b->h_small[0] = 0; b->h_small[1] = n; b->h_small[12] = n; *(u32*)(b->h_small + 2) = 0; b->ran = true;
   for (size_t i = 0; i < n; ++i) { end_site[i] = tmp[i].end_site; err[i] = tmp[i].err == 0xFFFF ? 0xFFFFFFFFu : tmp[i].err; }
   return BMBS_OK;
 }

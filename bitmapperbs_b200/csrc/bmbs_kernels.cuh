@@ -18,7 +18,8 @@ namespace bmbs {
 
 constexpr int MAX_TASKS = 28;       // 25 seeds + first-seed literal + second seed + slack
 constexpr u32 MAX_SEED_HITS = 1000; // Schema.cpp:26826 max_seed_matches
-constexpr u32 MAX_PE_MULTI = 25000; // Schema.cpp:18854 max_candidates_occ
+constexpr u32 MAX_PE_MULTI = 25000; // Schema.cpp:18854 max_candidates_occ (fast pair mode)
+constexpr u32 MAX_PE_MULTI_SENSITIVE = 10000; // Schema.cpp:22713-22716 (sensitive pair mode)
 
 struct SeedTask { u64 sp; u32 hits; unsigned short mlen, off; };  // hits==0: `sp` is a literal site
 
@@ -34,6 +35,13 @@ struct BatchView {
   short* one_mm; u64* site0;
   unsigned short* ph_off; unsigned short* ph_first_len; unsigned char* ph_seed_id;   // seeding state carried between the phase kernels
   u32* list2; u32* list3; u32* list_count;        // reads needing the one-mismatch second seed / the remaining seeds
+  // --pe --sensitive (Map_Pair_Seq_split, Schema.cpp:22450): bookkeeping of the seeds that were used
+  // {count, start[0], start[1], end of the one before last, end of the last} (select_best_seeds, :16630), the
+  // number of candidates after the first seed (decides which mate goes first, :23326), the list of mates to
+  // re-seed, and each read's final slice of out_cand
+  unsigned short* bk; unsigned short* first_cands; u32* list4; u32* res_first; u32* res_n;
+  int sensitive; int round;                     // round 1 = the re-seeding pass
+  u32 multi_cap;
   u32* ntask; u32* ncand; u32* coff;           // coff: exclusive scan of ncand, n_reads+1
   SeedTask* tasks;                              // [MAX_TASKS][n_reads]
   // per candidate slot
@@ -44,7 +52,7 @@ struct BatchView {
   u64* work_site; u32* work_vote; u32* work_read; bmbs_cand* out_cand;
   bmbs_read_result* out_res;
   u32* big_list; u32* big_count; u64* scratch; u32* scratch_used; u64 scratch_cap;
-  u64* counters; u64* totals;   // totals[0] candidate slots, totals[1] verification work items
+  u64* counters; u64* totals;   // totals[0] candidate slots, [1] verification work items of this round, [2] out_cand base of this round, [3] out_cand entries in all
   u32* status;                  // bit0 per-read task overflow, bit1 slot capacity, bit2 work capacity, bit3 scratch
   u64 slot_cap;
   double e_rate; u32 seed_len; int dmax_base, dmin_base;  // pair distance bounds before the per-pair 2k / length terms
@@ -342,7 +350,7 @@ __global__ void __launch_bounds__(128) seed_first(DevIndex ix, BatchView b) {
       }
       if (!done) {
         one_mm = (int)mlen;
-        if (mlen == L && h.hits > 1 && (!b.pe || h.hits <= MAX_PE_MULTI)) {
+        if (mlen == L && h.hits > 1 && (!b.pe || h.hits <= b.multi_cap)) {
           is_multi = true;
           if (first_c == L) {
             state = BMBS_MULTI_EXACT; done = true;
@@ -352,10 +360,17 @@ __global__ void __launch_bounds__(128) seed_first(DevIndex ix, BatchView b) {
       }
       if (!done) {
         if (h.hits != 1 && mlen >= b.seed_len && h.hits <= MAX_SEED_HITS && h.hits != 0) tw.emit(sp, (u32)h.hits, mlen, 0);
+        if (b.sensitive) {
+          const bool used = h.hits == 1 || (h.mlen >= b.seed_len && h.hits <= MAX_SEED_HITS);
+          unsigned short* k5 = b.bk + (size_t)r * 5;
+          k5[0] = used ? 1 : 0; k5[1] = 0; k5[2] = 0; k5[3] = 0; k5[4] = (unsigned short)(used ? first_len : 0);
+          b.first_cands[r] = (unsigned short)tw.nc;
+        }
         off = mlen == 0 ? next_offset_unmatched(rp, L, 0) : mlen / 2;
         seed_id = 1;
       }
     }
+    if (b.sensitive && (done || !(max_seeds > 0 && L > 0))) { b.first_cands[r] = 0; b.bk[(size_t)r * 5] = 0; b.bk[(size_t)r * 5 + 4] = 0; }
     if (!done) { to2 = get_error == 1; to3 = !to2; }
     b.state[r] = (unsigned char)state;
     b.flags[r] = (unsigned char)(is_multi ? 1 : 0);
@@ -421,16 +436,21 @@ __global__ void __launch_bounds__(128) seed_rest(DevIndex ix, BatchView b) {
     u64 max_seeds = (u64)L / 10 - 1; if (max_seeds > 25) max_seeds = 25;
     TaskWriter tw{b, (int)r, b.ntask[r], b.ncand[r]};
     u32 off = b.ph_off[r]; u64 seed_id = b.ph_seed_id[r], sp = 0, ep = 0;
+    u32 bn = 0, bs0 = 0, bs1 = 0, bep = 0, bel = 0;
+    if (b.sensitive) { const unsigned short* k5 = b.bk + (size_t)r * 5; bn = k5[0]; bs0 = k5[1]; bs1 = k5[2]; bep = k5[3]; bel = k5[4]; }
     while (seed_id < max_seeds && off < L) {
       const u32 cur = L - off;
       SeedHit h = seed_until_unique(ix, rp, s_lut, off, cur, sp, ep, cn.n_occ, cn.n_hash);
       sp = h.sp; ep = h.ep;
+      bool used = true;
       if (h.hits == 1) tw.emit(sp, 1, h.mlen, off);
       else if (h.mlen >= b.seed_len && h.hits <= MAX_SEED_HITS) { if (h.hits) tw.emit(sp, (u32)h.hits, h.mlen, off); }
-      else if (cur == h.mlen) break;
+      else { used = false; if (cur == h.mlen) break; }
+      if (used) { if (bn == 0) bs0 = off; else if (bn == 1) bs1 = off; bep = bel; bel = off + h.mlen; ++bn; }
       off = h.mlen == 0 ? next_offset_unmatched(rp, L, off) : off + h.mlen / 2;
       ++seed_id;
     }
+    if (b.sensitive) { unsigned short* k5 = b.bk + (size_t)r * 5; k5[0] = (unsigned short)bn; k5[1] = (unsigned short)bs0; k5[2] = (unsigned short)bs1; k5[3] = (unsigned short)bep; k5[4] = (unsigned short)bel; }
     tw.store();
   }
   flush_counters(s_cnt, cn, b.counters);
@@ -473,6 +493,7 @@ __global__ void __launch_bounds__(256) locate_rows(DevIndex ix, BatchView b) {
 //   otherwise sort + run-length encode into windows {max(c-k,0), votes}  (generate_candidate_votes_shift, :4687-4773).
 // Returns true when the segment still has to be sorted/encoded.
 __device__ __forceinline__ bool classify_read(BatchView& b, int r, u32 beg, u32 n, bool lane0) {
+  if (b.round == 1) { if (n == 0) { if (lane0) b.nv[r] = 0; return false; } return true; }   // re-seeded mates: always sort + encode
   const int st = b.state[r];
   if (st == BMBS_EXACT_UNIQUE) { if (lane0) { b.nv[r] = b.pe ? 1u : 0u; if (n) b.vcnt[beg] = 0; } return false; }
   if (st == BMBS_MULTI_EXACT) { if (!b.pe) { if (lane0) b.nv[r] = 0; return false; } return true; }
@@ -493,7 +514,7 @@ __global__ void __launch_bounds__(128) votes_small(BatchView b) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= b.n_reads || *b.status) return;
   const u32 beg = b.coff[r], n = b.coff[r + 1] - beg;
-  const bool multi = b.state[r] == BMBS_MULTI_EXACT;
+  const bool multi = b.round == 0 && b.state[r] == BMBS_MULTI_EXACT;
   if (n > 32) {
     // classification needs only the first two candidates, do it here so votes_big sees final states
     if (!classify_read(b, r, beg, n, lane == 0)) return;
@@ -564,7 +585,7 @@ __global__ void __launch_bounds__(256) votes_big(BatchView b) {
         __syncthreads();
       }
     // a real key equal to ~0 is indistinguishable from padding but also equal to it, so the first n entries are right
-    if (b.state[r] == BMBS_MULTI_EXACT) {
+    if (b.round == 0 && b.state[r] == BMBS_MULTI_EXACT) {
       for (u32 i = threadIdx.x; i < n; i += blockDim.x) { b.cand[beg + i] = a[i]; b.vcnt[beg + i] = 0; }
       if (threadIdx.x == 0) b.nv[r] = n;
       __syncthreads();
@@ -712,6 +733,7 @@ __global__ void verify_windows(DevIndex ix, BatchView b, int nch2) {
   if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   const u32 total_work = *b.status ? 0u : (u32)b.totals[1];
+  const u64 out_base = b.totals[2];
   const int stride = blockDim.x;
   u64* sm = sm_all + threadIdx.x;
   u64 cells = 0, wbytes = 0, verified = 0;
@@ -719,7 +741,7 @@ __global__ void verify_windows(DevIndex ix, BatchView b, int nch2) {
     const u32 r = b.work_read[wi];
     const u64 site = b.work_site[wi];
     const int L = (int)b.len[r], k = (int)b.kk[r];
-    const int st = b.state[r];
+    const int st = b.round == 0 ? b.state[r] : BMBS_VERIFY;
     int end = -1; u32 err = 0xFFFFFFFFu;
     if (st == BMBS_EXACT_UNIQUE || st == BMBS_MULTI_EXACT) { end = L - 1; err = 0; }
     else if (st == BMBS_ONE_MISMATCH) { end = L - 1; err = 1; }
@@ -753,11 +775,166 @@ __global__ void verify_windows(DevIndex ix, BatchView b, int nch2) {
       ++verified; cells += (u64)L * (u64)(2 * k + 1);
     }
     bmbs_cand o; o.site = site; o.vote = b.work_vote[wi]; o.end_site = (int16_t)end; o.err = err == 0xFFFFFFFFu ? (uint16_t)0xFFFF : (uint16_t)err;
-    b.out_cand[wi] = o;
+    b.out_cand[out_base + wi] = o;
   }
   atomicAdd(&s_cnt[0], verified); atomicAdd(&s_cnt[1], cells); atomicAdd(&s_cnt[2], wbytes);
   __syncthreads();
   if (threadIdx.x == 0) { atomicAdd(b.counters + CNT_VERIFIED, s_cnt[0]); atomicAdd(b.counters + CNT_CELLS, s_cnt[1]); atomicAdd(b.counters + CNT_WINBYTES, s_cnt[2]); }
+}
+
+
+// ------------------------------------------------------------------------------------------- sensitive pairing
+// select_suit_candidates (Schema.cpp:4775-4824): a verified hit of the mate within [dmin, dmax] of `site`?
+__device__ __forceinline__ bool mate_in_range(u64 site, const bmbs_cand* hits, int nh, int dmax, int dmin, int& next) {
+  for (int i = next; i < nh; ++i) {
+    const u64 h = hits[i].site;
+    if (h > site) {
+      const long long d = (long long)(h - site);
+      if (d > dmax) return false;
+      if (d >= dmin) return true;
+    } else {
+      const long long d = (long long)(site - h);
+      if (d > dmax) next = i + 1;
+      else if (d >= dmin) return true;
+    }
+  }
+  return false;
+}
+
+__device__ __forceinline__ void pair_bounds(const BatchView& b, int r1, int r2, int& dmax, int& dmin) {
+  const u64 k1 = b.kk[r1], k2 = b.kk[r2], kl = k1 > k2 ? k1 : k2;
+  const u32 L1 = b.len[r1], L2 = b.len[r2];
+  dmax = (int)((u64)(long long)b.dmax_base + kl * 2);
+  dmin = (int)((u64)(long long)b.dmin_base - kl * 2 - (u64)(L1 > L2 ? L1 : L2));
+}
+
+// hits (err <= k) whose absolute end differs from that of the entry verified just before them, compacted to the
+// front of the slice (map_candidate_votes_mutiple_cut_end_to_end_*_for_paired_end, Schema.cpp:7502-7512); with
+// `mate` set only entries within range of a mate hit take part (the reference verifies only those,
+// generate_candidate_votes_shift_filter, :4884-4992)
+__device__ __forceinline__ u32 keep_hits_inplace(bmbs_cand* c, u32 n, u32 k, const bmbs_cand* mate, int nmate, int dmax, int dmin) {
+  u32 kept = 0; u64 prev_end = ~0ull; int next = 0;
+  for (u32 i = 0; i < n; ++i) {
+    const bmbs_cand x = c[i];
+    if (mate && !mate_in_range(x.site, mate, nmate, dmax, dmin, next)) continue;
+    const u64 end_abs = x.site + (u64)(long long)x.end_site;
+    const u32 err = x.err == 0xFFFF ? 0xFFFFFFFFu : x.err;
+    if (err <= k && prev_end != end_abs) c[kept++] = x;
+    prev_end = end_abs;
+  }
+  return kept;
+}
+
+__device__ __forceinline__ bool is_resolved(int st) { return st == BMBS_EXACT_UNIQUE || st == BMBS_MULTI_EXACT || st == BMBS_ONE_MISMATCH; }
+
+// After every window of both mates has been verified: the mate with fewer first-seed candidates is the primary
+// (Schema.cpp:23326); its hits are final; the other mate keeps only windows near a primary hit; a secondary left
+// without a hit goes to the re-seeding list (:23562-23640).  One thread per pair, literal walks.
+__global__ void sens_pair(BatchView b) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  bool reseed = false; u32 rs = 0;
+  if (p * 2 + 1 < b.n_reads && !*b.status) {
+    const int r1 = 2 * p, r2 = r1 + 1;
+    const bool first_is_1 = b.first_cands[r1] <= b.first_cands[r2];
+    const int pri = first_is_1 ? r1 : r2, sec = first_is_1 ? r2 : r1;
+    int dmax, dmin; pair_bounds(b, r1, r2, dmax, dmin);
+    bmbs_cand* cp = b.out_cand + b.voff[pri]; bmbs_cand* cs = b.out_cand + b.voff[sec];
+    u32 occp = b.nv[pri], occs = 0;
+    if (!is_resolved(b.state[pri])) occp = keep_hits_inplace(cp, occp, b.kk[pri], nullptr, 0, 0, 0);
+    if (occp) {
+      occs = b.nv[sec];
+      if (!is_resolved(b.state[sec])) {
+        occs = keep_hits_inplace(cs, occs, b.kk[sec], cp, (int)occp, dmax, dmin);
+        if (occs == 0) { reseed = true; rs = (u32)sec; }
+      }
+    }
+    b.res_first[pri] = b.voff[pri]; b.res_n[pri] = occp;
+    b.res_first[sec] = b.voff[sec]; b.res_n[sec] = occs;
+  }
+  list_append(b.list4, b.list_count + 2, reseed, rs);
+}
+
+__global__ void reseed_clear(BatchView b) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < b.n_reads) { b.ntask[r] = 0; b.ncand[r] = 0; b.nv[r] = 0; }
+  if (r == 0) b.totals[2] = b.totals[1];       // the re-seeding round appends to out_cand
+}
+
+// reseed_filter_muti_thread, Schema.cpp:16998-17240: up to three exact seeds chosen from the gaps of the seeds used so
+// far (select_best_seeds, :16630-16670), then a greedy seed every 8 bases; a multi-hit seed counts from 20 bases.
+__global__ void __launch_bounds__(128) seed_reseed(DevIndex ix, BatchView b) {
+  __shared__ u64 s_cnt[4];
+  __shared__ unsigned char s_lut[256];
+  if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+  build_key_lut(s_lut);
+  __syncthreads();
+  const u32 n4 = *b.status ? 0u : b.list_count[2];
+  SeedCounters cn;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const u32 r = b.list4[i];
+    const u32 L = b.len[r];
+    ReadPlanes rp; rp.p = b.rplanes + plane_chunk_offset(b.offsets, (int)r);
+    u64 max_seeds = (u64)L / 10 - 1; if (max_seeds > 25) max_seeds = 25;
+    TaskWriter tw{b, (int)r, 0, 0};
+    const unsigned short* k5 = b.bk + (size_t)r * 5;
+    const u32 bn = k5[0], s0 = k5[1], s1 = k5[2], e_prev = k5[3], e_last = k5[4];
+    u32 rs[3], rl[3]; u32 nsel = 0;
+    if (bn >= 2) { rs[0] = s0; rl[0] = s1 - s0; rs[1] = e_prev; rl[1] = L - e_prev; nsel = 2; }
+    else if (bn == 1) { rs[0] = s0; rl[0] = L / 2; rs[1] = s0 + L / 2; rl[1] = L - rs[1]; nsel = 2; }
+    // with no seed used the reference reads element [-1] of two malloc'ed int arrays: 0 with glibc -> the whole read
+    const u32 last_end = bn ? e_last : 0;
+    if (last_end < L) { rs[nsel] = last_end; rl[nsel] = L - last_end; ++nsel; }
+    u64 seed_id = 0, sp = 0, ep = 0;
+    for (; seed_id < nsel; ++seed_id) {
+      const u32 off = rs[seed_id], cur = L - off, mlen = rl[seed_id];
+      u64 site = 0; bool have_site = false;
+      const u64 hits = count_exact(ix, rp, s_lut, off, mlen, sp, ep, have_site, site, cn.n_occ, cn.n_hash, cn.n_rows, cn.n_llf);
+      if (hits == 1) { if (have_site) tw.emit(site, 0, 0, 0); else tw.emit(sp, 1, mlen, off); }
+      else if (mlen >= 20 && hits <= MAX_SEED_HITS) { if (hits) tw.emit(sp, (u32)hits, mlen, off); }
+      else if (cur == mlen) break;
+    }
+    u32 off = bn > 1 ? (s0 + s1) / 2 : 4u;
+    while (seed_id < max_seeds && off < L) {
+      const u32 cur = L - off;
+      SeedHit h = seed_until_unique(ix, rp, s_lut, off, cur, sp, ep, cn.n_occ, cn.n_hash);
+      sp = h.sp; ep = h.ep;
+      if (h.hits == 1) tw.emit(sp, 1, h.mlen, off);
+      else if (h.mlen >= 20 && h.hits <= MAX_SEED_HITS) { if (h.hits) tw.emit(sp, (u32)h.hits, h.mlen, off); }
+      else if (cur == h.mlen) break;
+      off += 8;
+      ++seed_id;
+    }
+    tw.store();
+  }
+  flush_counters(s_cnt, cn, b.counters);
+}
+
+// re-seeded mates: keep the windows near a hit of the (final) primary before verifying them
+__global__ void sens_reseed_filter(BatchView b) {
+  const u32 n4 = *b.status ? 0u : b.list_count[2];
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const int r = (int)b.list4[i], mate = r ^ 1;
+    int dmax, dmin; pair_bounds(b, r & ~1, r | 1, dmax, dmin);
+    const bmbs_cand* hits = b.out_cand + b.res_first[mate]; const int nh = (int)b.res_n[mate];
+    const u32 beg = b.coff[r], n = b.nv[r];
+    u32 kept = 0; int next = 0;
+    for (u32 j = 0; j < n; ++j) {
+      const u64 site = b.cand[beg + j];
+      if (mate_in_range(site, hits, nh, dmax, dmin, next)) { b.cand[beg + kept] = site; b.vcnt[beg + kept] = b.vcnt[beg + j]; ++kept; }
+    }
+    b.nv[r] = kept;
+  }
+}
+
+__global__ void sens_reseed_finish(BatchView b) {
+  const u32 n4 = *b.status ? 0u : b.list_count[2];
+  const u64 base = b.totals[2];
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const int r = (int)b.list4[i];
+    const u32 first = (u32)(base + b.voff[r]);
+    b.res_first[r] = first;
+    b.res_n[r] = keep_hits_inplace(b.out_cand + first, b.nv[r], b.kk[r], nullptr, 0, 0, 0);
+  }
 }
 
 // ------------------------------------------------------------------------------------------- finalize
@@ -765,8 +942,9 @@ __global__ void finalize_reads(BatchView b) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= b.n_reads) return;
   bmbs_read_result o;
-  o.site = b.site0[r]; o.first_cand = b.voff[r];
-  o.n_cand = b.nv[r];
+  o.site = b.site0[r]; o.first_cand = b.sensitive ? b.res_first[r] : b.voff[r];
+  o.n_cand = b.sensitive ? b.res_n[r] : b.nv[r];
+  if (r == 0) b.totals[3] = b.totals[2] + b.totals[1];
   o.one_mismatch_pos = b.one_mm[r]; o.state = b.state[r]; o.is_multiple_map = b.flags[r] & 1; o.reserved = 0;
   b.out_res[r] = o;
 }
@@ -789,7 +967,7 @@ __global__ void scan_tiles(const u32* in, u32 n, u64* tile_sum, u32* overflow) {
     if (threadIdx.x == 0) tile_sum[blockIdx.x] = y;
   }
 }
-__global__ void scan_tile_sums(u64* tile_sum, u32 ntiles, u64* total, u64 cap, u32* status, u32 cap_bit) {
+__global__ void scan_tile_sums(u64* tile_sum, u32 ntiles, u64* total, u64 cap, u32* status, u32 cap_bit, const u64* base) {
   // single block, serial over chunks of blockDim
   __shared__ u64 s_carry; __shared__ u64 s_w[32];
   if (threadIdx.x == 0) s_carry = 0;
@@ -809,7 +987,7 @@ __global__ void scan_tile_sums(u64* tile_sum, u32 ntiles, u64* total, u64 cap, u
     if (threadIdx.x == blockDim.x - 1) s_carry = incl;
     __syncthreads();
   }
-  if (threadIdx.x == 0) { *total = s_carry; if (s_carry > cap) atomicOr(status, cap_bit); }
+  if (threadIdx.x == 0) { *total = s_carry; if (s_carry + (base ? *base : 0ull) > cap) atomicOr(status, cap_bit); }
 }
 __global__ void scan_apply(const u32* in, u32 n, const u64* tile_sum, u32* out) {
   __shared__ u32 s_w[32];

@@ -89,14 +89,14 @@ void parse(int argc, char** argv, Options& o) {
     else if (a == "--phred64") o.sc.q_base = 64;
     else if (a == "-g" || a == "--gpus") o.gpus = atoi(val().c_str());
     else if (a == "--batch") o.batch_reads = (size_t)atoll(val().c_str());
-    else die("unknown or unsupported option " + a + " (supported: --index --search --seq --seq1 --seq2 --pe --fast -o -t -e --seed --min --max --mapstats scoring flags --phred33/64 --gpus --batch)");
+    else die("unknown or unsupported option " + a + " (supported: --index --search --seq --seq1 --seq2 --pe --fast --sensitive -o -t -e --seed --min --max --mapstats scoring flags --phred33/64 --gpus --batch)");
   }
   if (!o.seq1.empty() && !o.seq2.empty()) o.pe = true;   // Process_CommandLines.cpp:314-317
   if (o.threads < 1) o.threads = 1;
   unsigned hw = std::thread::hardware_concurrency();
   if (hw && (unsigned)o.threads > hw) o.threads = (int)hw;  // the reference caps -t at the online CPUs (:254-258)
   if (o.gpus < 1) o.gpus = 1;
-  o.prm.sensitive = o.sensitive ? 1 : 0;
+  o.prm.sensitive = (o.sensitive && o.pe) ? 1 : 0;      // --sensitive only selects the pair worker (Bitmapper_main.cpp)
 }
 
 void finish_batch(const HostContext& hc, Batch& b, bool pe, int threads) {
@@ -148,7 +148,6 @@ int search(const Options& o, const std::string& cmdline) {
   bmbs_index* idx = nullptr;
   if (bmbs_index_load(prefix.c_str(), devs.data(), (int)devs.size(), &idx)) die(std::string("index load failed: ") + bmbs_last_error());
   const double t_load = now() - t0;
-  if (o.sensitive && o.pe) die("--sensitive pairing is not available on the GPU path yet; use --fast");
 
   FastqReader q1, q2;
   const bool pe = o.pe;

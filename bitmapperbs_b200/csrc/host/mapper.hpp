@@ -177,7 +177,8 @@ inline void finish_pair(const HostContext& hc, const std::string& name1, const s
   unpack_cands(cand + r1.first_cand, r1.n_cand, v1);
   unpack_cands(cand + r2.first_cand, r2.n_cand, v2);
   int occ1, occ2;
-  if (res1 && res2) { occ1 = (int)v1.size(); occ2 = (int)v2.size(); }
+  // --pe --sensitive (Map_Pair_Seq_split, Schema.cpp:22450): the library already returns each mate's final hits
+  if (hc.prm.sensitive || (res1 && res2)) { occ1 = (int)v1.size(); occ2 = (int)v2.size(); }
   else if (!res1 && !res2) {
     if (v1.size() <= v2.size()) {
       occ1 = pe::keep_hits(v1, k1); if (occ1 == 0) return;

@@ -57,7 +57,7 @@ typedef struct {
   int seed_len;       /* --seed, default 30                                        */
   int min_ins;        /* --min, default 0                                          */
   int max_ins;        /* --max, default 500                                        */
-  int sensitive;      /* 0 = --fast (default); 1 = --sensitive (not yet on GPU)    */
+  int sensitive;      /* 0 = --fast (default); 1 = --sensitive (paired batches)     */
 } bmbs_params;
 void bmbs_params_default(bmbs_params* p);
 
@@ -119,7 +119,7 @@ int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm);
 int bmbs_batch_download(bmbs_batch* b, bmbs_read_result* res, bmbs_cand* cand, size_t cand_cap, size_t* cand_used);
 int bmbs_batch_sync(bmbs_batch* b);
 /* device time of the last bmbs_batch_run in ms (CUDA events on the batch stream), per stage:
- * [0] total [1] pack [2] seed [3] locate [4] votes [5] pair filter [6] verify */
+ * [0] total [1] pack [2] seed [3] locate [4] votes [5] pair filter [6] verify [7] sensitive pairing + re-seeding round */
 int bmbs_batch_timings(bmbs_batch* b, float ms[8]);
 /* work counters of the last run, for roofline accounting:
  * [0] hash queries [1] occ-block lookups (one interval end, one LF step) [2] located rows

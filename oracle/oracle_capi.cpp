@@ -91,6 +91,39 @@ int orc_map_pe(void* h, const char* seqs, const uint64_t* offs, int n_pairs, dou
   return w <= cap ? 0 : BMBS_ERR_CAPACITY;
 }
 
+// Same record layout and semantics as bmbs_map_batch_pe with sensitive=1: every read's slice holds its FINAL hits
+// (primary: verified hits; secondary: hits near a primary hit, after re-seeding when there were none).
+int orc_map_pe_sensitive(void* h, const char* seqs, const uint64_t* offs, int n_pairs, double e_rate, int seed_len, int min_ins, int max_ins,
+                         bmbs_read_result* res, bmbs_cand* cand, size_t cap, size_t* used, uint8_t* reseeded) {
+  const Index& ix = *(Index*)h; Params P; P.e_rate = e_rate; P.seed_len = seed_len; P.min_ins = min_ins; P.max_ins = max_ins; P.sensitive = true;
+  size_t w = 0;
+  for (int p = 0; p < n_pairs; ++p) {
+    std::string rd[2]; int L[2];
+    for (int s = 0; s < 2; ++s) { const int r = 2 * p + s; L[s] = (int)(offs[r + 1] - offs[r]); rd[s].assign(seqs + offs[r], L[s]); }
+    PairOutcome o; Stats st; SensDebug d;
+    std::string q0(L[0], 'I'), q1(L[1], 'I');
+    run_pe_sensitive_pair(ix, P, rd[0].c_str(), q0.c_str(), L[0], rd[1].c_str(), q1.c_str(), L[1], o, st, &d);
+    const SensMate* m[2] = {&d.a, &d.b};
+    const bool dead = m[d.primary]->occ == 0;
+    for (int s = 0; s < 2; ++s) {
+      bmbs_read_result& r = res[2 * p + s]; memset(&r, 0, sizeof r);
+      const SeedTrace& t = m[s]->t;
+      r.first_cand = (uint32_t)w; r.is_multiple_map = t.is_multi; r.one_mismatch_pos = (int16_t)t.one_mismatch_site;
+      if (t.exact_unique) { r.state = BMBS_EXACT_UNIQUE; r.site = t.cand[0]; }
+      else if (t.multi_exact_noC) r.state = BMBS_MULTI_EXACT;
+      else if (t.cand.empty()) r.state = BMBS_NONE;
+      else if (!t.extra && (t.cand.size() == 1 || (t.cand.size() == 2 && t.cand[0] == t.cand[1]))) { r.state = BMBS_ONE_MISMATCH; r.site = t.cand[0]; }
+      else r.state = BMBS_VERIFY;
+      const int occ = dead ? 0 : m[s]->occ;
+      r.n_cand = (uint32_t)occ;
+      if (reseeded) reseeded[2 * p + s] = m[s]->reseeded ? 1 : 0;
+      for (int i = 0; i < occ; ++i) { if (w < cap) put(cand[w], m[s]->v[i]); ++w; }
+    }
+  }
+  *used = w;
+  return w <= cap ? 0 : BMBS_ERR_CAPACITY;
+}
+
 int orc_verify(void* h, const char* seqs, const uint64_t* offs, int n_reads, const uint32_t* read_idx, const uint64_t* sites, size_t n,
                double e_rate, int32_t* end_site, uint32_t* err, int threads) {
   const Index& ix = *(Index*)h;

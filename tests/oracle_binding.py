@@ -26,6 +26,7 @@ def lib():
         L.orc_count.restype = C.c_uint64; L.orc_count.argtypes = [vp, C.c_char_p, C.c_uint64] + [C.POINTER(C.c_uint64)] * 2
         L.orc_map_se.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.orc_map_pe.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.orc_map_pe_sensitive.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_size_t), vp]
         L.orc_verify.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_size_t, C.c_double, vp, vp, C.c_int]
         _lib = L
     return _lib
@@ -59,6 +60,17 @@ class OracleIndex:
         rc = lib().orc_map_pe(self.h, flat.ctypes.data, offs.ctypes.data, n // 2, e_rate, seed_len, min_ins, max_ins, res.ctypes.data, cand.ctypes.data, cap, C.byref(used))
         assert rc == 0
         return res, cand[: used.value]
+
+    def map_pe_sensitive(self, mates, e_rate=0.08, seed_len=30, min_ins=0, max_ins=500, cap=None):
+        """-> (records, final hit lists, per-read flag: went through the re-seeding round)"""
+        flat, offs = mates if isinstance(mates, tuple) else flatten(mates)
+        n = len(offs) - 1
+        cap = cap or max(1 << 16, 64 * n)
+        res = np.zeros(n, dtype=ReadResult); cand = np.zeros(cap, dtype=Cand); used = C.c_size_t(0); reseeded = np.zeros(n, dtype=np.uint8)
+        rc = lib().orc_map_pe_sensitive(self.h, flat.ctypes.data, offs.ctypes.data, n // 2, e_rate, seed_len, min_ins, max_ins, res.ctypes.data,
+                                        cand.ctypes.data, cap, C.byref(used), reseeded.ctypes.data)
+        assert rc == 0
+        return res, cand[: used.value], reseeded
 
     def verify(self, reads, read_idx, sites, e_rate=0.08, threads=8):
         flat, offs = reads if isinstance(reads, tuple) else flatten(reads)

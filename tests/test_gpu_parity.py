@@ -61,6 +61,32 @@ def test_paired_end_records_match_oracle(golden, gidx, oidx):
     assert np.array_equal(gcand["vote"][v], ocand["vote"][v])
 
 
+def _slices(res, cand):
+    """per-read slices of cand[] laid end to end (offsets differ between implementations, contents must not)"""
+    idx = np.concatenate([np.arange(f, f + n) for f, n in zip(res["first_cand"].astype(np.int64), res["n_cand"].astype(np.int64))] or [np.zeros(0, np.int64)])
+    return cand[idx]
+
+
+@pytest.mark.parametrize("name", ["pe150", "pe100h"])
+def test_sensitive_pairing_records_match_oracle(golden, gidx, oidx, name):
+    """--pe --sensitive: final hit lists of both mates (primary hits, mate-filtered secondary hits, re-seeded secondaries)"""
+    m1 = read_fastq(golden / f"{name}_1.fq"); m2 = read_fastq(golden / f"{name}_2.fq")
+    mates = []
+    for a, b in zip(m1, m2):
+        mates += [a[1], revcomp(b[1])]
+    gres, gcand = gidx.map_batch_pe(mates, params=capi.default_params(sensitive=1))
+    ores, ocand, reseeded = oidx.map_pe_sensitive(mates)
+    for f in ("state", "n_cand", "is_multiple_map"):
+        assert np.array_equal(gres[f], ores[f]), f
+    m = np.isin(gres["state"], [B.EXACT_UNIQUE, B.ONE_MISMATCH])
+    assert np.array_equal(gres["site"][m], ores["site"][m])
+    gs, os_ = _slices(gres, gcand), _slices(ores, ocand)
+    for f in ("site", "end_site", "err"):
+        assert np.array_equal(gs[f], os_[f]), f
+    if name == "pe100h":
+        assert reseeded.sum() > 100 and (ores["n_cand"][reseeded == 1] > 0).sum() > 3   # the re-seeding round is exercised and finds hits
+
+
 def test_edge_case_reads(golden, gidx, oidx):
     genome = b"".join(l.strip() for l in open(golden / "genome.fa", "rb") if not l.startswith(b">"))
     N = len(genome)
@@ -146,6 +172,9 @@ def test_verify_error_rate_other_than_default(gidx, oidx):
     ("se100", ["--seq", "se100.fq"]),
     ("se250", ["--seq", "se250.fq"]),
     ("pe150", ["--seq1", "pe150_1.fq", "--seq2", "pe150_2.fq", "--pe"]),
+    ("pe150s", ["--seq1", "pe150_1.fq", "--seq2", "pe150_2.fq", "--pe", "--sensitive"]),
+    ("pe100h", ["--seq1", "pe100h_1.fq", "--seq2", "pe100h_2.fq", "--pe"]),
+    ("pe100hs", ["--seq1", "pe100h_1.fq", "--seq2", "pe100h_2.fq", "--pe", "--sensitive"]),
 ])
 def test_mapper_sam_identical_to_reference_golden(golden, built, name, args):
     """whole program: FASTQ -> GPU seed-and-verify through the C ABI -> host CIGAR/MAPQ -> SAM, vs the reference's SAM"""
@@ -165,8 +194,13 @@ def test_live_reference_binary_agrees_on_fresh_data(built, tmp_path):
     S.write_fastq(tmp_path / "r.fq", r)
     a, b = S.simulate_reads(chroms, 6000, 100, seed=6, paired=True, sub=0.02, indel=0.003, random_qual=True, frag_range=(150, 420))
     S.write_fastq(tmp_path / "a.fq", a); S.write_fastq(tmp_path / "b.fq", b)
+    c, d = S.simulate_reads(chroms, 8000, 120, seed=7, paired=True, sub=0.06, indel=0.008, n_rate=0.003, random_qual=True, frag_range=(150, 450), junk_fraction=0.03)
+    S.write_fastq(tmp_path / "c.fq", c); S.write_fastq(tmp_path / "d.fq", d)
     subprocess.run([str(built["indexer"]), "g.fa"], cwd=tmp_path, check=True, stderr=subprocess.DEVNULL)
-    for tag, args in (("se", ["--seq", "r.fq"]), ("pe", ["--seq1", "a.fq", "--seq2", "b.fq", "--pe"])):
+    for tag, args in (("se", ["--seq", "r.fq"]), ("pe", ["--seq1", "a.fq", "--seq2", "b.fq", "--pe"]),
+                      ("pes", ["--seq1", "a.fq", "--seq2", "b.fq", "--pe", "--sensitive"]),
+                      ("hard", ["--seq1", "c.fq", "--seq2", "d.fq", "--pe"]),
+                      ("hards", ["--seq1", "c.fq", "--seq2", "d.fq", "--pe", "--sensitive"])):
         subprocess.run([str(built["ref"]), "--search", "g.fa", *args, "-t", "1", "-o", f"cpu_{tag}.sam", "--mapstats", f"cpu_{tag}.st"],
                        cwd=tmp_path, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         subprocess.run([str(built["bmbs"]), "--search", "g.fa", *args, "-t", "4", "-o", f"gpu_{tag}.sam", "--mapstats", f"gpu_{tag}.st"],

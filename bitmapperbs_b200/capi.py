@@ -34,7 +34,7 @@ _lib = None
 EXPORTS = ["bmbs_index_load", "bmbs_index_free", "bmbs_index_genome_length", "bmbs_index_device_bytes", "bmbs_last_error",
            "bmbs_params_default", "bmbs_map_batch_se", "bmbs_map_batch_pe", "bmbs_verify", "bmbs_batch_create", "bmbs_batch_free",
            "bmbs_batch_upload", "bmbs_batch_run", "bmbs_batch_download", "bmbs_batch_sync", "bmbs_batch_timings",
-           "bmbs_batch_counters", "bmbs_batch_launches"]
+           "bmbs_batch_counters", "bmbs_batch_launches", "bmbs_batch_verify", "bmbs_batch_download_verify", "bmbs_ubench_int_pipe"]
 
 
 def load_library():
@@ -65,6 +65,9 @@ def load_library():
     L.bmbs_batch_timings.argtypes = [vp, C.POINTER(C.c_float)]
     L.bmbs_batch_counters.argtypes = [vp, u64p]
     L.bmbs_batch_launches.argtypes = [vp]
+    L.bmbs_batch_verify.argtypes = [vp, vp, vp, C.c_size_t, C.c_double]
+    L.bmbs_batch_download_verify.argtypes = [vp, vp, vp, C.c_size_t]
+    L.bmbs_ubench_int_pipe.argtypes = [C.c_int, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -72,6 +75,13 @@ def load_library():
 def _check(rc):
     if rc != 0:
         raise BmbsError(rc, load_library().bmbs_last_error().decode(errors="replace"))
+
+
+def int_pipe_peak(dev=0) -> float:
+    """measured LOP3+IADD3 throughput of the device, 32-bit integer ops per second"""
+    v = C.c_double(0)
+    _check(load_library().bmbs_ubench_int_pipe(dev, C.byref(v)))
+    return v.value
 
 
 def default_params(**kw) -> Params:
@@ -181,6 +191,17 @@ class Batch:
         used = C.c_size_t(0)
         _check(self._L.bmbs_batch_download(self._h, res.ctypes.data, cand.ctypes.data, len(cand), C.byref(used)))
         return res, cand, used.value
+
+    def verify(self, read_idx, sites, e_rate=0.08):
+        """kernel 3 alone over the uploaded reads (async); results via download_verify"""
+        self._vn = len(sites)
+        _check(self._L.bmbs_batch_verify(self._h, read_idx.ctypes.data, sites.ctypes.data, self._vn, e_rate))
+
+    def download_verify(self, end=None, err=None):
+        end = np.zeros(self._vn, dtype=np.int32) if end is None else end
+        err = np.zeros(self._vn, dtype=np.uint32) if err is None else err
+        _check(self._L.bmbs_batch_download_verify(self._h, end.ctypes.data, err.ctypes.data, self._vn))
+        return end, err
 
     def timings(self):
         ms = (C.c_float * 8)()

@@ -252,7 +252,7 @@ extern "C" int bmbs_batch_create(bmbs_index* idx, int dev, size_t max_reads, siz
   A(dalloc(b, &v.ntask, R)); A(dalloc(b, &v.ncand, R)); A(dalloc(b, &v.coff, R)); A(dalloc(b, &v.tasks, (size_t)MAX_TASKS * max_reads));
   A(dalloc(b, &v.slot_row, S)); A(dalloc(b, &v.slot_adj, S)); A(dalloc(b, &v.slot_read, S)); A(dalloc(b, &v.cand, S)); A(dalloc(b, &v.vcnt, S));
   A(dalloc(b, &v.nv, R)); A(dalloc(b, &v.voff, R)); A(dalloc(b, &v.keep, S));
-  A(dalloc(b, &v.work_site, S)); A(dalloc(b, &v.work_vote, S)); A(dalloc(b, &v.work_read, S)); A(dalloc(b, &v.out_cand, S));
+  A(dalloc(b, &v.vlist, S)); A(dalloc(b, &v.work_site, S)); A(dalloc(b, &v.work_vote, S)); A(dalloc(b, &v.work_read, S)); A(dalloc(b, &v.out_cand, S));
   A(dalloc(b, &v.out_res, R)); A(dalloc(b, &v.big_list, R)); A(dalloc(b, &v.big_count, 4));
   v.scratch_cap = 2 * S + 65536;
   A(dalloc(b, &v.scratch, (size_t)v.scratch_cap)); A(dalloc(b, &v.scratch_used, 4));
@@ -474,26 +474,29 @@ namespace {
 __global__ void verify_setup(BatchView b, const u32* read_idx, const u64* sites, u32 n) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < (u32)b.n_reads) b.state[i] = BMBS_VERIFY;
-  if (i < n) { b.work_read[i] = read_idx[i]; b.work_site[i] = sites[i]; b.work_vote[i] = 0; }
-  if (i == 0) b.totals[1] = n;
+  if (i < n) { b.work_read[i] = read_idx[i]; b.work_site[i] = sites[i]; b.work_vote[i] = 0; b.vlist[i] = i; }
+  if (i == 0) { b.totals[1] = n; b.totals[3] = n; b.list_count[3] = n; }
+}
+__global__ void verify_unpack(const bmbs_cand* c, u32 n, int* end_site, u32* err) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { end_site[i] = c[i].end_site; err[i] = c[i].err == 0xFFFF ? 0xFFFFFFFFu : c[i].err; }
 }
 }  // namespace
 
-extern "C" int bmbs_verify(bmbs_index* idx, int dev, const char* seqs, const uint64_t* offsets, int n_reads, const uint32_t* read_idx,
-                           const uint64_t* sites, size_t n, double e_rate, int32_t* end_site, uint32_t* err) {
-  if (!idx || !seqs || !offsets || !read_idx || !sites || !end_site || !err) return fail(BMBS_ERR_ARG, "null argument");
+// Kernel 3 alone over the reads of the last bmbs_batch_upload: pack, then one verify_windows launch over n (read, site) items.
+extern "C" int bmbs_batch_verify(bmbs_batch* b, const uint32_t* read_idx, const uint64_t* sites, size_t n, double e_rate) {
+  if (!b || (n && (!read_idx || !sites))) return fail(BMBS_ERR_ARG, "bad argument");
+  if (n > b->cand_cap) return fail(BMBS_ERR_CAPACITY, "more work items than the batch's cand_cap");
+  const int n_reads = b->n_reads;
   for (size_t i = 0; i < n; ++i) if (read_idx[i] >= (uint32_t)n_reads) return fail(BMBS_ERR_ARG, "read_idx out of range");
-  bmbs_batch* b = nullptr;
-  int rc = cached_batch(idx, dev, (size_t)n_reads + 1, offsets[n_reads] + 64, n + 1024, &b);
-  if (rc) return rc;
-  if ((rc = bmbs_batch_upload(b, seqs, offsets, n_reads, 0))) return rc;
+  CU(cudaSetDevice(b->dev));
   BatchView& v = b->v;
-  v.ascii = b->d_ascii; v.offsets = b->d_offsets; v.n_reads = n_reads; v.pe = 0; v.e_rate = e_rate;
+  v.ascii = b->d_ascii; v.offsets = b->d_offsets; v.n_reads = n_reads; v.pe = 0; v.e_rate = e_rate; v.sensitive = 0; v.round = 0;
   cudaStream_t s = b->stream;
   CU(cudaMemsetAsync(v.counters, 0, 16 * 8, s)); CU(cudaMemsetAsync(v.totals, 0, 4 * 8, s)); CU(cudaMemsetAsync(v.status, 0, 16, s));
-  // stage the work list through cand[] / slot_row[] (free in this mode)
-  CU(cudaMemcpyAsync(v.slot_read, read_idx, n * 4, cudaMemcpyHostToDevice, s));
-  CU(cudaMemcpyAsync(v.slot_row, sites, n * 8, cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(v.list_count, 0, 16, s));
+  // stage the work list through slot_read[] / slot_row[] (free in this mode)
+  if (n) { CU(cudaMemcpyAsync(v.slot_read, read_idx, n * 4, cudaMemcpyHostToDevice, s)); CU(cudaMemcpyAsync(v.slot_row, sites, n * 8, cudaMemcpyHostToDevice, s)); }
   b->launches = 0;
   CU(cudaEventRecord(b->ev[0], s));
   if (n_reads) { pack_reads<<<(n_reads + 3) / 4, 128, 0, s>>>(v); ++b->launches; }
@@ -508,11 +511,80 @@ extern "C" int bmbs_verify(bmbs_index* idx, int dev, const char* seqs, const uin
   verify_windows<<<b->sm_count * per_sm, bd, smem, s>>>(b->copy->view, v, nch2); ++b->launches;
   CU(cudaEventRecord(b->ev[6], s)); CU(cudaEventRecord(b->ev[7], s)); CU(cudaEventRecord(b->ev[8], s));
   CU(cudaMemcpyAsync(b->h_small + 4, v.counters, 8 * 8, cudaMemcpyDeviceToHost, s));
-  std::vector<bmbs_cand> tmp(n);
-  if (n) CU(cudaMemcpyAsync(tmp.data(), v.out_cand, n * sizeof(bmbs_cand), cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
   CU(cudaGetLastError());
   b->h_small[0] = 0; b->h_small[1] = n; b->h_small[12] = n; *(u32*)(b->h_small + 2) = 0; b->ran = true;
-  for (size_t i = 0; i < n; ++i) { end_site[i] = tmp[i].end_site; err[i] = tmp[i].err == 0xFFFF ? 0xFFFFFFFFu : tmp[i].err; }
+  return BMBS_OK;
+}
+
+extern "C" int bmbs_batch_download_verify(bmbs_batch* b, int32_t* end_site, uint32_t* err, size_t n) {
+  if (!b || !b->ran || (n && (!end_site || !err))) return fail(BMBS_ERR_ARG, "bad argument or batch not run");
+  if (n > b->cand_cap) return fail(BMBS_ERR_ARG, "n exceeds the batch capacity");
+  CU(cudaSetDevice(b->dev));
+  cudaStream_t s = b->stream;
+  // unpack on the device into the (now free) work arrays, then two plain copies
+  int* d_end = (int*)b->v.work_vote; u32* d_err = b->v.slot_adj;
+  if (n) {
+    verify_unpack<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(b->v.out_cand, (u32)n, d_end, d_err);
+    CU(cudaMemcpyAsync(end_site, d_end, n * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(err, d_err, n * 4, cudaMemcpyDeviceToHost, s));
+  }
+  CU(cudaStreamSynchronize(s));
+  CU(cudaGetLastError());
+  return BMBS_OK;
+}
+
+extern "C" int bmbs_verify(bmbs_index* idx, int dev, const char* seqs, const uint64_t* offsets, int n_reads, const uint32_t* read_idx,
+                           const uint64_t* sites, size_t n, double e_rate, int32_t* end_site, uint32_t* err) {
+  if (!idx || !seqs || !offsets || !read_idx || !sites || !end_site || !err) return fail(BMBS_ERR_ARG, "null argument");
+  bmbs_batch* b = nullptr;
+  int rc = cached_batch(idx, dev, (size_t)n_reads + 1, offsets[n_reads] + 64, n + 1024, &b);
+  if (rc) return rc;
+  if ((rc = bmbs_batch_upload(b, seqs, offsets, n_reads, 0))) return rc;
+  if ((rc = bmbs_batch_verify(b, read_idx, sites, n, e_rate))) return rc;
+  return bmbs_batch_download_verify(b, end_site, err, n);
+}
+
+// ================================================================================================ integer-pipe peak
+// Denominator of the verification roofline: dependent-free LOP3 + IADD3 streams, 8 independent
+// chains per thread, every SM full.  Returns 32-bit integer ALU operations per second.
+namespace {
+__global__ void __launch_bounds__(256) int_pipe_ubench(u32* out, int iters) {
+  u32 a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = threadIdx.x * (i + 1) + blockIdx.x;
+  const u32 x = out[0], y = out[1];
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(x), "r"(y));
+      asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(y));
+    }
+  }
+  u32 s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s ^= a[i];
+  if (s == 0x12345678u) out[2] = s;
+}
+}  // namespace
+
+extern "C" int bmbs_ubench_int_pipe(int dev, double* ops_per_second) {
+  if (!ops_per_second) return fail(BMBS_ERR_ARG, "null argument");
+  CU(cudaSetDevice(dev));
+  cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, dev));
+  u32* d = nullptr; CU(cudaMalloc(&d, 64)); CU(cudaMemset(d, 0, 64));
+  cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  const int blocks = prop.multiProcessorCount * 8, iters = 1 << 14;
+  int_pipe_ubench<<<blocks, 256>>>(d, 256);
+  double best = 0;
+  for (int rep = 0; rep < 3; ++rep) {
+    CU(cudaEventRecord(e0));
+    int_pipe_ubench<<<blocks, 256>>>(d, iters);
+    CU(cudaEventRecord(e1)); CU(cudaEventSynchronize(e1));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double ops = (double)blocks * 256 * (double)iters * 16 / (ms / 1000.0);
+    if (ops > best) best = ops;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  *ops_per_second = best;
   return BMBS_OK;
 }

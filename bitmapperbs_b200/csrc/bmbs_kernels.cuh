@@ -50,6 +50,7 @@ struct BatchView {
   unsigned char* keep;
   // work list
   u64* work_site; u32* work_vote; u32* work_read; bmbs_cand* out_cand;
+  u32* vlist;                                   // dense list of the work items that need the bit-vector kernel (count: list_count[3])
   bmbs_read_result* out_res;
   u32* big_list; u32* big_count; u64* scratch; u32* scratch_used; u64 scratch_cap;
   u64* counters; u64* totals;   // totals[0] candidate slots, [1] verification work items of this round, [2] out_cand base of this round, [3] out_cand entries in all
@@ -661,14 +662,44 @@ __global__ void filter_pairs_kernel(BatchView b) {
 }
 
 // ------------------------------------------------------------------------------------------- gather
-__global__ void gather_work(BatchView b) {
+// Work item w = voff[r] + j for every surviving window.  Windows of reads that seeding already resolved get their
+// record here (end L-1, err 0 or 1); the others are appended to a dense list, so that every lane of the
+// bit-vector kernel has a window to verify.
+__global__ void __launch_bounds__(256) gather_work(BatchView b) {
+  __shared__ u32 s_n, s_base;
   const u32 total = *b.status ? 0u : (u32)b.totals[0];
-  for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
-    const u32 r = b.slot_read[s];
-    const u32 j = s - b.coff[r];
-    if (j >= b.nv[r]) continue;
-    const u32 w = b.voff[r] + j;
-    b.work_site[w] = b.cand[s]; b.work_vote[w] = b.vcnt[s]; b.work_read[w] = r;
+  const u64 out_base = b.totals[2];
+  const u32 rounds = (total + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
+  for (u32 it = 0; it < rounds; ++it) {
+    const u32 s = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    bool verify = false; u32 w = 0;
+    if (s < total) {
+      const u32 r = b.slot_read[s];
+      const u32 j = s - b.coff[r];
+      if (j < b.nv[r]) {
+        w = b.voff[r] + j;
+        const int st = b.round == 0 ? b.state[r] : BMBS_VERIFY;
+        if (st == BMBS_VERIFY || st == BMBS_NONE) {
+          b.work_site[w] = b.cand[s]; b.work_vote[w] = b.vcnt[s]; b.work_read[w] = r; verify = true;
+        } else {
+          bmbs_cand o; o.site = b.cand[s]; o.vote = b.vcnt[s]; o.end_site = (int16_t)(b.len[r] - 1); o.err = st == BMBS_ONE_MISMATCH ? 1 : 0;
+          b.out_cand[out_base + w] = o;
+        }
+      }
+    }
+    // block-aggregated append: one global atomic per block and round
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const u32 bal = __ballot_sync(0xffffffffu, verify);
+    const int lane = threadIdx.x & 31;
+    u32 wbase = 0;
+    if (lane == 0 && bal) wbase = atomicAdd(&s_n, (u32)__popc(bal));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_n) s_base = atomicAdd(b.list_count + 3, s_n);
+    __syncthreads();
+    if (verify) b.vlist[s_base + wbase + __popc(bal & ((1u << lane) - 1u))] = w;
+    __syncthreads();
   }
 }
 
@@ -732,20 +763,18 @@ __global__ void verify_windows(DevIndex ix, BatchView b, int nch2) {
   __shared__ u64 s_cnt[3];
   if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
   __syncthreads();
-  const u32 total_work = *b.status ? 0u : (u32)b.totals[1];
+  const u32 total_work = *b.status ? 0u : b.list_count[3];
   const u64 out_base = b.totals[2];
   const int stride = blockDim.x;
   u64* sm = sm_all + threadIdx.x;
   u64 cells = 0, wbytes = 0, verified = 0;
-  for (u32 wi = blockIdx.x * blockDim.x + threadIdx.x; wi < total_work; wi += gridDim.x * blockDim.x) {
+  for (u32 vi = blockIdx.x * blockDim.x + threadIdx.x; vi < total_work; vi += gridDim.x * blockDim.x) {
+    const u32 wi = b.vlist[vi];
     const u32 r = b.work_read[wi];
     const u64 site = b.work_site[wi];
     const int L = (int)b.len[r], k = (int)b.kk[r];
-    const int st = b.round == 0 ? b.state[r] : BMBS_VERIFY;
     int end = -1; u32 err = 0xFFFFFFFFu;
-    if (st == BMBS_EXACT_UNIQUE || st == BMBS_MULTI_EXACT) { end = L - 1; err = 0; }
-    else if (st == BMBS_ONE_MISMATCH) { end = L - 1; err = 1; }
-    else {
+    {
       const int plen = L + 2 * k;
       const int nch = (L + 31) >> 5;           // chunks addressed by the column loop (+1 for 64-bit bands)
       const bool inside = window_inside(ix, site, (u64)plen);
@@ -857,7 +886,7 @@ __global__ void sens_pair(BatchView b) {
 __global__ void reseed_clear(BatchView b) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < b.n_reads) { b.ntask[r] = 0; b.ncand[r] = 0; b.nv[r] = 0; }
-  if (r == 0) b.totals[2] = b.totals[1];       // the re-seeding round appends to out_cand
+  if (r == 0) { b.totals[2] = b.totals[1]; b.list_count[3] = 0; }      // the re-seeding round appends to out_cand
 }
 
 // reseed_filter_muti_thread, Schema.cpp:16998-17240: up to three exact seeds chosen from the gaps of the seeds used so

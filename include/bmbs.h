@@ -126,6 +126,14 @@ int bmbs_batch_timings(bmbs_batch* b, float ms[8]);
  * [3] locate LF steps [4] verified candidates [5] verified cell updates L*(2k+1) [6] candidates
  * [7] genome-window bytes fetched */
 int bmbs_batch_counters(bmbs_batch* b, uint64_t c[8]);
+/* Kernel 3 alone (what bmbs_verify does, staged; BASELINE.json config 5): verify n (read, site) items over the
+ * reads of the last bmbs_batch_upload; results stay on the device until bmbs_batch_download_verify.
+ * bmbs_batch_timings()[6] is the verify_windows launch, bmbs_batch_counters()[5] its cell updates. */
+int bmbs_batch_verify(bmbs_batch* b, const uint32_t* read_idx, const uint64_t* sites, size_t n, double e_rate);
+int bmbs_batch_download_verify(bmbs_batch* b, int32_t* end_site, uint32_t* err, size_t n);
+/* measured peak of the integer ALU pipe on `dev` (LOP3 + IADD3, no dependencies between chains), 32-bit ops/s:
+ * the roofline kernel 3 is reported against (SURVEY.md §8d asks for it to be measured, not assumed) */
+int bmbs_ubench_int_pipe(int dev, double* ops_per_second);
 /* number of kernels launched by the last bmbs_batch_run */
 int bmbs_batch_launches(bmbs_batch* b);
 

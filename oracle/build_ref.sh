@@ -36,6 +36,6 @@ gcc -c -O1 "$HERE/hts_stub.c" -o "$TMP/hts_stub.o"
 cp "$TMP/bitmapperBS" "$OUT/bitmapperBS"
 g++ -O2 -std=c++17 -pthread "$HERE/psascan_shim.cpp" -o "$OUT/psascan"
 # function-level harnesses over the reference's own headers / sources
-g++ -w -O2 -mavx2 -mpopcnt -D__AVX2__ -shared -fPIC -I "$REF" "$HERE/ref_harness_bpm.cpp" -o "$OUT/libref_bpm.so"
+g++ -w -O3 -mavx2 -mpopcnt -D__AVX2__ -shared -fPIC -pthread -I "$REF" "$HERE/ref_harness_bpm.cpp" -o "$OUT/libref_bpm.so"
 ( cd "$TMP" && g++ -w -O2 -mpopcnt -shared -fPIC -I "$TMP" "$HERE/ref_harness_fm.cpp" bwt.cpp saca-k.cpp -o "$OUT/libref_fm.so" )
 echo "build_ref: built $OUT/{bitmapperBS,psascan,libref_bpm.so,libref_fm.so}"

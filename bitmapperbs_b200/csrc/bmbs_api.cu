@@ -62,8 +62,38 @@ int load_files(const std::string& prefix, HostIndex& h) {
 
 struct DeviceCopy {
   int dev = 0; DevIndex view{}; size_t bytes = 0;
-  void *occ = nullptr, *flag = nullptr, *hash = nullptr, *ssa = nullptr, *planes = nullptr, *dsa_lo = nullptr, *dsa_hi = nullptr;
+  void *occ = nullptr, *flag = nullptr, *hash = nullptr, *ssa = nullptr, *planes = nullptr, *dsa_lo = nullptr, *dsa_hi = nullptr, *ktab = nullptr;
 };
+
+// ---- deep seed table (kmer_entry, bmbs_device.cuh): one thread per 16-mer walks the <= 3^D extensions depth first, sharing
+// the LF steps of common prefixes and stopping where the reference's greedy loop would stop
+__device__ __forceinline__ void ktab_fill(u64* t, u32 first, u32 stride, u32 count, u64 e) {
+  for (u32 i = 0; i < count; ++i) t[first + i * stride] = e;
+}
+template <int LEFT>
+__device__ void ktab_node(const DevIndex& ix, u64* t, u32 prefix, u32 stride, u32 m, u64 top, u64 bot) {
+  // node: symbols 16..m-1 fixed (extension value `prefix`, next digit weighs `stride`), interval [top, bot) not empty
+  constexpr u32 below = LEFT == 0 ? 1 : LEFT == 1 ? 3 : LEFT == 2 ? 9 : LEFT == 3 ? 27 : 81;
+  if (bot - top == 1 || LEFT == 0) { ktab_fill(t, prefix, stride, below, kmer_entry(m, top, bot)); return; }
+  if constexpr (LEFT > 0) {
+    for (int c = 0; c < 3; ++c) {
+      u64 a = top, b = bot;
+      lf_pair(ix, a, b, c);
+      if (b <= a) ktab_fill(t, prefix + c * stride, stride * 3, below / 3, kmer_entry(m, top, bot));
+      else ktab_node<LEFT - 1>(ix, t, prefix + c * stride, stride * 3, m + 1, a, b);
+    }
+  }
+}
+template <int D>
+__global__ void __launch_bounds__(128) build_ktab(DevIndex ix, u64* table, u32 n_keys) {
+  constexpr u32 leaves = D == 1 ? 3 : D == 2 ? 9 : D == 3 ? 27 : 81;
+  for (u32 key = blockIdx.x * blockDim.x + threadIdx.x; key < n_keys; key += gridDim.x * blockDim.x) {
+    u64* t = table + (u64)key * leaves;
+    u64 top, bot; hash_query(ix, key, top, bot);
+    if (bot <= top) ktab_fill(t, 0, 1, leaves, 0ull);
+    else ktab_node<D>(ix, t, 0, 1, 16, top, bot);
+  }
+}
 
 // every row's suffix-array value from the sampled one, once per index load (the same walk the reference does per hit)
 __global__ void __launch_bounds__(256) densify_sa(DevIndex ix, u32* lo, unsigned char* hi) {
@@ -89,7 +119,7 @@ extern "C" uint64_t bmbs_index_device_bytes(const bmbs_index* idx) { return idx 
 
 extern "C" void bmbs_index_free(bmbs_index* idx) {
   if (!idx) return;
-  for (auto& c : idx->copies) { cudaSetDevice(c.dev); cudaFree(c.occ); cudaFree(c.flag); cudaFree(c.hash); cudaFree(c.ssa); cudaFree(c.planes); cudaFree(c.dsa_lo); cudaFree(c.dsa_hi); }
+  for (auto& c : idx->copies) { cudaSetDevice(c.dev); cudaFree(c.occ); cudaFree(c.flag); cudaFree(c.hash); cudaFree(c.ssa); cudaFree(c.planes); cudaFree(c.dsa_lo); cudaFree(c.dsa_hi); cudaFree(c.ktab); }
   delete idx;
 }
 
@@ -172,7 +202,35 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
     v.ssa = (const u32*)c.ssa; v.planes = (const uint2*)c.planes;
     v.C[0] = h.nacgt[0]; v.C[1] = h.nacgt[1]; v.C[2] = h.nacgt[2];
     v.shapline = h.shapline; v.n_rows = h.sa_length; v.N = h.N;
-    v.dsa_lo = nullptr; v.dsa_hi = nullptr;
+    v.dsa_lo = nullptr; v.dsa_hi = nullptr; v.ktab = nullptr; v.kdepth = 0; v.kpow = 1;
+    // ---- deep seed table: K = 16..20 (BMBS_KMER); default: the smallest K whose 3^K exceeds 8 x the text length -- a
+    // random K-mer then rarely has a second occurrence, so most seeds end on their first lookup -- if it fits in a quarter of HBM
+    {
+      int K = 16;
+      if (const char* ks = getenv("BMBS_KMER")) K = atoi(ks);
+      else { double p = 43046721.0; while (K < 20 && p < 8.0 * (double)n) { p *= 3; ++K; } }
+      if (K > 20) K = 20;
+      size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
+      auto bytes_of = [&](int k) { size_t x = nh ? nh - 1 : 0; for (int i = 16; i < k; ++i) x *= 3; return x * 8; };
+      if (!getenv("BMBS_KMER")) while (K > 16 && bytes_of(K) > total_b / 4) --K;
+      if (K > 16 && nh > 1) {
+        DeviceCopy& cc = idx->copies.back();
+        const int D = K - 16; const size_t kb = bytes_of(K);
+        e = cudaMalloc(&cc.ktab, kb + 256);
+        if (e == cudaSuccess) {
+          cudaDeviceProp prop; cudaGetDeviceProperties(&prop, cc.dev);
+          const u32 n_keys = (u32)(nh - 1); const int grid = prop.multiProcessorCount * 16;
+          if (D == 1) build_ktab<1><<<grid, 128>>>(v, (u64*)cc.ktab, n_keys);
+          else if (D == 2) build_ktab<2><<<grid, 128>>>(v, (u64*)cc.ktab, n_keys);
+          else if (D == 3) build_ktab<3><<<grid, 128>>>(v, (u64*)cc.ktab, n_keys);
+          else build_ktab<4><<<grid, 128>>>(v, (u64*)cc.ktab, n_keys);
+          e = cudaDeviceSynchronize();
+        }
+        if (e != cudaSuccess) { std::string m = std::string("deep seed table: ") + cudaGetErrorString(e); bmbs_index_free(idx); return fail(BMBS_ERR_CUDA, m); }
+        v.ktab = (const u64*)cc.ktab; v.kdepth = (u32)D; v.kpow = D == 1 ? 3 : D == 2 ? 9 : D == 3 ? 27 : 81;
+        cc.bytes += kb;
+      }
+    }
     // ---- dense suffix array (BMBS_SA=sampled keeps the on-disk 1/8 sampling; default: dense when it fits with room to spare)
     const char* mode = getenv("BMBS_SA");
     const bool wide = h.sa_length > 0xFFFFFFFFull;

@@ -30,6 +30,8 @@ struct DevIndex {
   const u64* hash;
   const u32* ssa;
  const uint2* planes;
+  const u64* ktab;            // deep seed table over K-mers, K = 16 + kdepth (null: only the 16-mer table); see kmer_entry
+  u32 kdepth, kpow;           // K - 16 (1..4), 3^(K-16)
   const u32* dsa_lo;          // dense suffix array (one entry per row), low 32 bits; null = walk to a sampled row
   const unsigned char* dsa_hi; // bits 32..39 when the text is longer than 2^32
   u64 C[3];        // first row of symbols G(0), T(1), A(2)   (nacgt[c], bwt.cpp:1715-1729)
@@ -84,6 +86,18 @@ __device__ __forceinline__ void hash_query(const DevIndex& ix, u64 key, u64& sp,
   const u64 a = __ldg(ix.hash + key), b = __ldg(ix.hash + key + 1);
   sp = a & 0xFFFFFFFFFull;
   ep = (b & 0xFFFFFFFFFull) - (b >> 60);
+}
+
+// Deep seed table (built on the device at load): entry of the K-mer whose first 16 symbols have table key
+// `key16` and whose symbols 16..K-1 have base-3 value `ext` (symbol 16 least significant) records where the greedy seed
+// loop of count_backward_as_much_1_terminate (bwt.h:2081-2209) stands after at most K symbols:
+//   bits 0..35  first row of the interval I_m          bits 36..38  0: the 16-mer does not occur; else m - 15 (m = 16..K)
+//   bits 39..63 rows in I_m (KTAB_SAT: too many to store, fall back to the 16-mer table)
+// m < K means the loop stopped there (one row left, or the next symbol empties the interval); m = K means it goes on.
+constexpr u64 KTAB_SAT = (1ull << 25) - 1;
+__device__ __forceinline__ u64 kmer_entry(u32 m, u64 top, u64 bot) {
+  const u64 size = bot - top;
+  return (top & 0xFFFFFFFFFull) | ((u64)(m ? m - 15 : 0) << 36) | ((size >= KTAB_SAT ? KTAB_SAT : size) << 39);
 }
 
 // Single-row locate: walk LF until a sampled row.  bwt.h:2449-2560.  `steps_out` counts LF steps.

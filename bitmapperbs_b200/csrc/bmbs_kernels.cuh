@@ -169,18 +169,44 @@ struct SymbolStream {
 
 // count_backward_as_much_1_terminate (bwt.h:2081-2209) on the reversed, C->T converted read:
 // the seed starts at read[off] and grows to the right; cur = L - off bases are available.
+// symbols 16..K-1 of the seed at `off` as the extension index of the deep table; false when one of them is not A/C/G/T
+__device__ __forceinline__ bool kmer_ext(const DevIndex& ix, const unsigned char* __restrict__ lut, u32 lo, u32 hi, u32 bad, u32& ext) {
+  const u32 mask = (1u << ix.kdepth) - 1u;
+  if (bad & mask) return false;
+  ext = lut[(lo & mask) | (((~lo & ~hi) & mask) << 4)];
+  return true;
+}
+
+// count_backward_as_much_1_terminate (bwt.h:2081-2209) on the reversed, C->T converted read:
+// the seed starts at read[off] and grows to the right; cur = L - off bases are available.
 __device__ __forceinline__ SeedHit seed_until_unique(const DevIndex& ix, const ReadPlanes& rp, const unsigned char* lut, u32 off, u32 cur,
                                                      u64 sp_in, u64 ep_in, u32& n_occ, u32& n_hash) {
   SeedHit h; h.hits = 0; h.sp = sp_in; h.ep = ep_in; h.mlen = 0;
   if (cur < 18) return h;
   u32 key;
   if (!key16(rp, lut, off, key)) return h;
-  u64 top, bot;
-  hash_query(ix, key, top, bot); ++n_hash;
-  if (bot <= top) return h;
-  u64 ptop = ~0ull, pbot = ~0ull;
+  u64 top = 0, bot = 0;
   u32 m = 16;
   SymbolStream ss(rp, off + 16);
+  bool deep = false;
+  if (ix.ktab && cur >= 16 + ix.kdepth) {
+    u32 ext;
+    if (kmer_ext(ix, lut, ss.lo, ss.hi, ss.bad, ext)) {
+      const u64 e = __ldg(ix.ktab + (u64)key * ix.kpow + ext); ++n_hash;
+      const u64 size = e >> 39; const u32 code = (u32)(e >> 36) & 7u;
+      if (size != KTAB_SAT) {
+        if (code == 0) return h;
+        m = 15 + code; top = e & 0xFFFFFFFFFull; bot = top + size;
+        if (m < 16 + ix.kdepth) { h.mlen = m; h.sp = top; h.ep = bot; h.hits = size; return h; }
+        deep = true;
+      }
+    }
+  }
+  if (!deep) {
+    hash_query(ix, key, top, bot); ++n_hash;
+    if (bot <= top) return h;
+  }
+  u64 ptop = ~0ull, pbot = ~0ull;
   for (; m < cur; ++m) {
     ptop = top; pbot = bot;
     if (bot - top == 1) break;
@@ -207,11 +233,28 @@ __device__ __forceinline__ u64 count_exact(const DevIndex& ix, const ReadPlanes&
   if (cur < 17) return 0;
   u32 key;
   if (!key16(rp, lut, off, key)) return 0;
-  u64 top, bot;
-  hash_query(ix, key, top, bot); ++n_hash;
-  if (bot <= top) return 0;
+  u64 top = 0, bot = 0;
+  u32 m = 16;
   SymbolStream ss(rp, off + 16);
-  for (u32 m = 16; m < cur; ++m) {
+  bool deep = false;
+  if (ix.ktab && cur >= 16 + ix.kdepth) {
+    u32 ext;
+    if (kmer_ext(ix, lut, ss.lo, ss.hi, ss.bad, ext)) {
+      const u64 e = __ldg(ix.ktab + (u64)key * ix.kpow + ext); ++n_hash;
+      const u64 size = e >> 39; const u32 code = (u32)(e >> 36) & 7u;
+      if (size != KTAB_SAT) {
+        if (code == 0) return 0;
+        m = 15 + code; top = e & 0xFFFFFFFFFull; bot = top + size;
+        if (m < 16 + ix.kdepth && size >= 2) return 0;   // the next symbol empties the interval
+        deep = true;
+      }
+    }
+  }
+  if (!deep) {
+    hash_query(ix, key, top, bot); ++n_hash;
+    if (bot <= top) return 0;
+  }
+  for (; m < cur; ++m) {
     if (bot <= top) break;
     if (bot - top == 1) {
       int st; const u64 sa = locate_row(ix, top, st); n_llf += st; ++n_rows;

@@ -16,9 +16,24 @@ pytestmark = pytest.mark.gpu
 ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
 
 
-@pytest.fixture(scope="module")
-def gidx(golden):
-    return B.Index(golden / "genome.fa.index")
+# index residency variants: what the loader picks for a genome this small (dense suffix array, 16-mer table
+# only), the on-disk 1/8 suffix-array sampling with an 18-mer deep seed table, and the 20-mer table a 100 Mbp genome gets
+@pytest.fixture(scope="module", params=["default", "sampled_sa+18mer", "20mer"])
+def gidx(golden, request):
+    import os
+    env = {"default": {}, "sampled_sa+18mer": {"BMBS_SA": "sampled", "BMBS_KMER": "18"}, "20mer": {"BMBS_KMER": "20"}}[request.param]
+    old = {k: os.environ.get(k) for k in ("BMBS_SA", "BMBS_KMER")}
+    os.environ.update(env)
+    try:
+        ix = B.Index(golden / "genome.fa.index")
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    yield ix
+    ix.close()
 
 
 @pytest.fixture(scope="module")

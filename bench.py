@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--cache", default=os.environ.get("BMBS_BENCH_CACHE", "/tmp/bmbs_bench"))
     ap.add_argument("--ref-sample", type=int, default=250_000, help="pairs per reference-CPU run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=3, help="batches in flight in the end-to-end loop")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
 
@@ -230,17 +231,22 @@ def main():
                 raise
             batch.close(); cand_cap *= 2
     states = np.bincount(res["state"], minlength=5)
-    # second in-flight batch for the end-to-end loop: copies of one batch overlap the kernels of the other
-    batch2 = B.Batch(index, dev, n_reads, bases + 64, cand_cap)
-    h_res2 = torch.empty(n_reads * capi.ReadResult.itemsize, dtype=torch.uint8, pin_memory=True)
-    h_cand2 = torch.empty(cand_cap * capi.Cand.itemsize, dtype=torch.uint8, pin_memory=True)
-    outs = [(batch, res, cand), (batch2, h_res2.numpy().view(capi.ReadResult), h_cand2.numpy().view(capi.Cand))]
+    # more in-flight batches for the end-to-end loop (each with its own stream and pinned result buffers): the H2D copy of
+    # one batch overlaps the kernels of the previous one and the D2H copy of the one before
+    outs = [(batch, res, cand)]
+    keep = [h_res, h_cand]
+    for _ in range(a.inflight - 1):
+        hr = torch.empty(n_reads * capi.ReadResult.itemsize, dtype=torch.uint8, pin_memory=True)
+        hc = torch.empty(cand_cap * capi.Cand.itemsize, dtype=torch.uint8, pin_memory=True)
+        keep += [hr, hc]
+        outs.append((B.Batch(index, dev, n_reads, bases + 64, cand_cap), hr.numpy().view(capi.ReadResult), hc.numpy().view(capi.Cand)))
+    NB = len(outs)
     clocks = ClockSampler(dev); clocks.start()
     for _ in range(max(0, a.warmup - 1)):
         batch.run(prm)
     batch.sync()
-    for i in range(a.warmup):
-        bb, rr, cc = outs[i & 1]
+    for i in range(max(a.warmup, NB)):
+        bb, rr, cc = outs[i % NB]
         bb.upload(flat, offs, pe=True); bb.run(prm); bb.download(rr, cc)
 
     def barrier():
@@ -272,17 +278,18 @@ def main():
     barrier()
     e0 = time.perf_counter()
     for i in range(a.steps):
-        bb, rr, cc = outs[i & 1]
+        bb, rr, cc = outs[i % NB]
         bb.upload(flat, offs, pe=True); bb.run(prm)
-        if i > 0:
-            pb, pr, pc = outs[(i - 1) & 1]
+        if i >= NB - 1:
+            pb, pr, pc = outs[(i - (NB - 1)) % NB]
             _, _, used = pb.download(pr, pc)
-    pb, pr, pc = outs[(a.steps - 1) & 1]
-    _, _, used = pb.download(pr, pc)
+    for i in range(max(0, a.steps - (NB - 1)), a.steps):
+        pb, pr, pc = outs[i % NB]
+        _, _, used = pb.download(pr, pc)
     e2e_ms = (time.perf_counter() - e0) * 1000
     barrier()
     clk = clocks.stop(t_begin, time.time())
-    assert np.array_equal(outs[0][1]["state"], outs[1][1]["state"])
+    assert all(np.array_equal(outs[0][1]["state"], o[1]["state"]) for o in outs[1:])
     h2d = int(bases + 8 * (n_reads + 1)); d2h = int(n_reads * capi.ReadResult.itemsize + used * capi.Cand.itemsize)
 
     if dist:
@@ -320,7 +327,7 @@ def main():
         "config": {"workload": workload, "reads_per_step_per_gpu": n_reads, "l2": "inputs (300 MB of reads, 0.6 GB index) exceed the 126 MB L2; no flush needed",
                    "read_states": {"none": int(states[0]), "exact_unique": int(states[1]), "multi_exact": int(states[2]), "one_mismatch": int(states[3]), "verify": int(states[4])},
                    "index_hbm_bytes": index.device_bytes},
-        "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps},
+        "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps, "batches_in_flight": NB},
         "gpu_launches": launches,
         "clocks": clk,
         "stage_ms_per_step": per_step,

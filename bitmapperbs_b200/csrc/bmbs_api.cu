@@ -311,7 +311,7 @@ extern "C" int bmbs_batch_create(bmbs_index* idx, int dev, size_t max_reads, siz
   A(dalloc(b, &v.slot_row, S)); A(dalloc(b, &v.slot_adj, S)); A(dalloc(b, &v.slot_read, S)); A(dalloc(b, &v.cand, S)); A(dalloc(b, &v.vcnt, S));
   A(dalloc(b, &v.nv, R)); A(dalloc(b, &v.voff, R)); A(dalloc(b, &v.keep, S));
   A(dalloc(b, &v.vlist, S)); A(dalloc(b, &v.work_site, S)); A(dalloc(b, &v.work_vote, S)); A(dalloc(b, &v.work_read, S)); A(dalloc(b, &v.out_cand, S));
-  A(dalloc(b, &v.out_res, R)); A(dalloc(b, &v.big_list, R)); A(dalloc(b, &v.big_count, 4));
+  A(dalloc(b, &v.out_res, R)); A(dalloc(b, &v.big_list, R)); A(dalloc(b, &v.big_count, 4)); A(dalloc(b, &v.sort16, R)); A(dalloc(b, &v.sort32, R)); A(dalloc(b, &v.sort_count, 4));
   v.scratch_cap = 2 * S + 65536;
   A(dalloc(b, &v.scratch, (size_t)v.scratch_cap)); A(dalloc(b, &v.scratch_used, 4));
   A(dalloc(b, &v.counters, 16)); A(dalloc(b, &v.totals, 4)); A(dalloc(b, &v.status, 4));
@@ -367,9 +367,10 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
   const DevIndex ix = b->copy->view;
   CU(cudaMemsetAsync(v.counters, 0, 16 * 8, s)); CU(cudaMemsetAsync(v.totals, 0, 4 * 8, s)); CU(cudaMemsetAsync(v.status, 0, 16, s));
   CU(cudaMemsetAsync(v.big_count, 0, 16, s)); CU(cudaMemsetAsync(v.scratch_used, 0, 16, s)); CU(cudaMemsetAsync(v.list_count, 0, 16, s));
+  CU(cudaMemsetAsync(v.sort_count, 0, 16, s));
   CU(cudaEventRecord(b->ev[0], s));
   if (n > 0) {
-    pack_reads<<<(n + 3) / 4, 128, 0, s>>>(v); ++b->launches;
+    pack_reads<<<(n + 15) / 16, 128, 0, s>>>(v); ++b->launches;
     CU(cudaEventRecord(b->ev[1], s));
     seed_first<<<(n + 127) / 128, 128, 0, s>>>(ix, v); ++b->launches;
     seed_second<<<b->sm_count * 8, 128, 0, s>>>(ix, v); ++b->launches;
@@ -379,7 +380,9 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
     expand_tasks<<<(n + 127) / 128, 128, 0, s>>>(v); ++b->launches;
     locate_rows<<<b->sm_count * 8, 256, 0, s>>>(ix, v); ++b->launches;
     CU(cudaEventRecord(b->ev[3], s));
-    votes_small<<<(n + 3) / 4, 128, 0, s>>>(v); ++b->launches;
+    votes_classify<<<(n + 255) / 256, 256, 0, s>>>(v); ++b->launches;
+    votes_sort<16><<<b->sm_count * 16, 128, 0, s>>>(v); ++b->launches;
+    votes_sort<32><<<b->sm_count * 4, 128, 0, s>>>(v); ++b->launches;
     votes_big<<<b->sm_count * 4, 256, 0, s>>>(v); ++b->launches;
     CU(cudaEventRecord(b->ev[4], s));
     if (b->pe && !v.sensitive) { filter_pairs_kernel<<<(n / 2 + 127) / 128, 128, 0, s>>>(v); ++b->launches; }
@@ -402,7 +405,9 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
       run_scan(b, w.ncand, (u32)n, w.coff, w.totals, w.slot_cap, 2u);
       expand_tasks<<<(n + 127) / 128, 128, 0, s>>>(w); ++b->launches;
       locate_rows<<<b->sm_count * 8, 256, 0, s>>>(ix, w); ++b->launches;
-      votes_small<<<(n + 3) / 4, 128, 0, s>>>(w); ++b->launches;
+      votes_classify<<<(n + 255) / 256, 256, 0, s>>>(w); ++b->launches;
+      votes_sort<16><<<b->sm_count * 16, 128, 0, s>>>(w); ++b->launches;
+      votes_sort<32><<<b->sm_count * 4, 128, 0, s>>>(w); ++b->launches;
       votes_big<<<b->sm_count * 4, 256, 0, s>>>(w); ++b->launches;
       sens_reseed_filter<<<b->sm_count * 4, 128, 0, s>>>(w); ++b->launches;
       run_scan(b, w.nv, (u32)n, w.voff, w.totals + 1, w.slot_cap, 4u, w.totals + 2);
@@ -557,7 +562,7 @@ extern "C" int bmbs_batch_verify(bmbs_batch* b, const uint32_t* read_idx, const 
   if (n) { CU(cudaMemcpyAsync(v.slot_read, read_idx, n * 4, cudaMemcpyHostToDevice, s)); CU(cudaMemcpyAsync(v.slot_row, sites, n * 8, cudaMemcpyHostToDevice, s)); }
   b->launches = 0;
   CU(cudaEventRecord(b->ev[0], s));
-  if (n_reads) { pack_reads<<<(n_reads + 3) / 4, 128, 0, s>>>(v); ++b->launches; }
+  if (n_reads) { pack_reads<<<(n_reads + 15) / 16, 128, 0, s>>>(v); ++b->launches; }
   const u32 m = (u32)(n > (size_t)n_reads ? n : (size_t)n_reads);
   if (m) { verify_setup<<<(m + 255) / 256, 256, 0, s>>>(v, v.slot_read, v.slot_row, (u32)n); ++b->launches; }
   for (int i = 1; i <= 5; ++i) CU(cudaEventRecord(b->ev[i], s));

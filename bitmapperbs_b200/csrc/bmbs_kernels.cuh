@@ -52,6 +52,7 @@ struct BatchView {
   u64* work_site; u32* work_vote; u32* work_read; bmbs_cand* out_cand;
   u32* vlist;                                   // dense list of the work items that need the bit-vector kernel (count: list_count[3])
   bmbs_read_result* out_res;
+  u32* sort16; u32* sort32; u32* sort_count;     // reads whose candidate segment (<= 16 / <= 32 entries) has to be sorted
   u32* big_list; u32* big_count; u64* scratch; u32* scratch_used; u64 scratch_cap;
   u64* counters; u64* totals;   // totals[0] candidate slots, [1] verification work items of this round, [2] out_cand base of this round, [3] out_cand entries in all
   u32* status;                  // bit0 per-read task overflow, bit1 slot capacity, bit2 work capacity, bit3 scratch
@@ -63,65 +64,73 @@ __device__ __forceinline__ u32 code_word_offset(const u64* offsets, int r) { ret
 __device__ __forceinline__ u32 plane_chunk_offset(const u64* offsets, int r) { return (u32)(offsets[r] >> 5) + (u32)r; }
 
 // ------------------------------------------------------------------------------------------- pack
-// One warp per read.  Each lane turns 8 ASCII bases (two aligned 64-bit loads, so the warp reads the read's bytes
-// coalesced) into one u32 of nibble codes (A0 C1 G2 T3 N4 other5, used by verification) and into 8 bits of each
-// bit-plane; four lanes together form one 32-base plane chunk {lo, hi, not-ACGT, is-N} (used by seeding).
-// The ASCII -> code conversion works on 4 bytes at a time (SWAR).
+// Eight lanes per read, one 32-base chunk per lane and pass: 32 ASCII bytes (aligned 64-bit loads + funnel shifts) become
+// four u32 of nibble codes (A0 C1 G2 T3, anything else 4; used by verification) and one bit-plane chunk {lo, hi, not-ACGT,
+// is-N} (used by seeding).  Four bases at a time (SWAR): code = bits 1-2 of the byte, folded; a byte is valid when it equals
+// "ACGT"[code] (one PRMT); planes are gathered with a multiply.  Anything that is not A/C/G/T takes the rare slow path.
 __device__ __forceinline__ u32 gather4(u32 m01) { return ((m01 * 0x01020408u) >> 24) & 0xFu; }   // byte t bit 0 -> bit t
 __device__ __forceinline__ u32 nonzero_bytes(u32 d) { return ((((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) >> 7) & 0x01010101u; }
 
-struct Packed4 { u32 nib, lo, hi, bad, isn, isc; };
+struct Packed4 { u32 nib, lo, hi, bad, isn; };
 __device__ __forceinline__ Packed4 pack4(u32 x, u32 nvalid) {
-  const u32 keep = nvalid >= 4 ? 0x01010101u : (((1u << (8 * nvalid)) - 1u) & 0x01010101u);
   const u32 y = (x >> 1) & 0x03030303u;
   const u32 code = y ^ ((y >> 1) & 0x01010101u);                  // A0 C1 G2 T3 when the byte is one of ACGT
+  const u32 t = (code & 0x00030003u) | ((code >> 4) & 0x00300030u);
+  u32 nib = (t | (t >> 8)) & 0xFFFFu;
   u32 b0 = code & 0x01010101u, b1 = (code >> 1) & 0x01010101u;
-  const u32 expect = 0x41414141u + 2u * b0 + 6u * b1 + 11u * (b0 & b1);   // 'A' 'C' 'G' 'T' for codes 0..3
-  const u32 bad = nonzero_bytes(x ^ expect) & keep;
-  const u32 isn = (~nonzero_bytes(x ^ 0x4E4E4E4Eu)) & 0x01010101u & keep;
-  b0 &= keep & ~bad; b1 &= keep & ~bad;
-  const u32 cb = b0 | (b1 << 1) | (bad * 5u - isn);                // per byte: 0..3, N 4, other 5
-  Packed4 o;
-  o.nib = (cb & 0xFu) | ((cb >> 4) & 0xF0u) | ((cb >> 8) & 0xF00u) | ((cb >> 12) & 0xF000u);
-  o.lo = gather4(b0); o.hi = gather4(b1); o.bad = gather4(bad); o.isn = gather4(isn); o.isc = gather4(b0 & ~b1);
+  const u32 diff = x ^ __byte_perm(0x54474341u, 0u, nib);          // "ACGT"[code] per byte
+  Packed4 o; o.bad = 0; o.isn = 0;
+  if (diff != 0 || nvalid < 4) {
+    const u32 keep = nvalid >= 4 ? 0x01010101u : (((1u << (8 * nvalid)) - 1u) & 0x01010101u);
+    const u32 bad = nonzero_bytes(diff) & keep;
+    const u32 isn = (~nonzero_bytes(x ^ 0x4E4E4E4Eu)) & 0x01010101u & keep;
+    b0 &= keep & ~bad; b1 &= keep & ~bad;
+    const u32 cb = b0 | (b1 << 1) | (bad << 2);                     // per byte: 0..3, anything else 4
+    nib = (cb & 0xFu) | ((cb >> 4) & 0xF0u) | ((cb >> 8) & 0xF00u) | ((cb >> 12) & 0xF000u);
+    o.bad = gather4(bad); o.isn = gather4(isn);
+  }
+  o.nib = nib; o.lo = gather4(b0); o.hi = gather4(b1);
   return o;
 }
 
 __global__ void __launch_bounds__(128) pack_reads(BatchView b) {
-  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (r >= b.n_reads) return;
-  const u64 beg = b.offsets[r];
-  const u32 L = (u32)(b.offsets[r + 1] - beg);
-  u32* w = b.codes + code_word_offset(b.offsets, r);
-  uint4* pl = b.rplanes + plane_chunk_offset(b.offsets, r);
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, sub = threadIdx.x & 7;
+  const bool live = r < b.n_reads;
+  u64 beg = 0; u32 L = 0;
+  if (live) { beg = b.offsets[r]; L = (u32)(b.offsets[r + 1] - beg); }
+  u32* w = b.codes + (live ? code_word_offset(b.offsets, r) : 0);
+  uint4* pl = b.rplanes + (live ? plane_chunk_offset(b.offsets, r) : 0);
   u32 first_c = L;
-  const u32 nwords = (L + 7) >> 3, niter = (nwords + 31) >> 5;
-  for (u32 it = 0; it < niter; ++it) {
-    const u32 j = it * 32 + lane;
+  for (u32 c = sub; c * 32 < L; c += 8) {
+    const u64 addr = (u64)(b.ascii) + beg + (u64)c * 32;
+    const u64* q = (const u64*)(addr & ~7ull);
+    const unsigned sh = (unsigned)(addr & 7ull) * 8;
+    u64 x[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) x[i] = __ldg(q + i);            // staging buffers carry 64 bytes of slack past the last read
+    if (sh) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] = (x[i] >> sh) | (x[i + 1] << (64 - sh));
+    }
+    const u32 left = L - c * 32;                                // >= 1
     u32 lo = 0, hi = 0, bad = 0, isn = 0;
-    if (j < nwords) {
-      const u64 addr = (u64)(b.ascii) + beg + (u64)j * 8;
-      const u64* q = (const u64*)(addr & ~7ull);
-      const unsigned sh = (unsigned)(addr & 7ull) * 8;
-      u64 x = q[0];
-      if (sh) x = (x >> sh) | (q[1] << (64 - sh));   // staging buffers carry 64 bytes of slack past the last read
-      const u32 left = L - j * 8;                     // >= 1
-      const Packed4 a = pack4((u32)x, left), c = pack4((u32)(x >> 32), left > 4 ? left - 4 : 0);
-      w[j] = a.nib | (c.nib << 16);
-      lo = a.lo | (c.lo << 4); hi = a.hi | (c.hi << 4); bad = a.bad | (c.bad << 4); isn = a.isn | (c.isn << 4);
-      const u32 isc = a.isc | (c.isc << 4);
-      if (isc) first_c = min(first_c, j * 8 + (u32)__ffs(isc) - 1u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const u32 base = 8 * i;
+      if (base < left) {
+        const Packed4 a = pack4((u32)x[i], left - base);
+        const Packed4 d = pack4((u32)(x[i] >> 32), left > base + 4 ? left - base - 4 : 0);
+        w[c * 4 + i] = a.nib | (d.nib << 16);
+        lo |= (a.lo | (d.lo << 4)) << base; hi |= (a.hi | (d.hi << 4)) << base;
+        bad |= (a.bad | (d.bad << 4)) << base; isn |= (a.isn | (d.isn << 4)) << base;
+      }
     }
-    const unsigned s8 = 8u * (lane & 3);
-    lo <<= s8; hi <<= s8; bad <<= s8; isn <<= s8;
-    for (int o = 1; o <= 2; o <<= 1) {
-      lo |= __shfl_xor_sync(0xffffffffu, lo, o); hi |= __shfl_xor_sync(0xffffffffu, hi, o);
-      bad |= __shfl_xor_sync(0xffffffffu, bad, o); isn |= __shfl_xor_sync(0xffffffffu, isn, o);
-    }
-    if ((lane & 3) == 0 && (j >> 2) * 32 < L) pl[j >> 2] = make_uint4(lo, hi, bad, isn);   // only the read's own chunks (the next read follows)
+    pl[c] = make_uint4(lo, hi, bad, isn);
+    const u32 isc = lo & ~hi & ~bad;
+    if (isc) first_c = min(first_c, c * 32 + (u32)__ffs(isc) - 1u);
   }
-  for (int o = 16; o; o >>= 1) first_c = min(first_c, __shfl_xor_sync(0xffffffffu, first_c, o));
-  if (lane == 0) {
+  for (int o = 4; o; o >>= 1) first_c = min(first_c, __shfl_xor_sync(0xffffffffu, first_c, o));
+  if (live && sub == 0) {
     b.len[r] = L;
     b.first_c[r] = (unsigned short)first_c;
     u64 k = (u64)(b.e_rate * (double)L);   // Schema.cpp:27121: double product truncated, capped at 31
@@ -552,47 +561,58 @@ __device__ __forceinline__ bool classify_read(BatchView& b, int r, u32 beg, u32 
 
 __device__ __forceinline__ u64 window_start(u64 c, u64 k) { return c < k ? 0ull : c - k; }
 
-// one warp per read; segments of up to 32 candidates are sorted in registers (bitonic over shuffles),
-// encoded with a ballot, and written back in place; longer segments are queued for votes_big.
-__global__ void __launch_bounds__(128) votes_small(BatchView b) {
-  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (r >= b.n_reads || *b.status) return;
-  const u32 beg = b.coff[r], n = b.coff[r + 1] - beg;
-  const bool multi = b.round == 0 && b.state[r] == BMBS_MULTI_EXACT;
-  if (n > 32) {
-    // classification needs only the first two candidates, do it here so votes_big sees final states
-    if (!classify_read(b, r, beg, n, lane == 0)) return;
-    if (lane == 0) { const u32 i = atomicAdd(b.big_count, 1u); b.big_list[i] = (u32)r; }
-    return;
+// One thread per read decides what the candidates turn into; reads whose candidates have to be sorted go to one of three
+// lists by segment length (<= 16: half a warp sorts them, <= 32: a warp, longer: a CTA).
+__global__ void votes_classify(BatchView b) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  int which = -1;
+  if (r < b.n_reads && !*b.status) {
+    const u32 beg = b.coff[r], n = b.coff[r + 1] - beg;
+    if (classify_read(b, r, beg, n, true)) which = n <= 16 ? 0 : n <= 32 ? 1 : 2;
   }
-  if (!classify_read(b, r, beg, n, lane == 0)) return;
-  u64 v = lane < (int)n ? b.cand[beg + lane] : ~0ull;
-  bool pad = lane >= (int)n;   // padding sorts last even against a real ~0 key
-  int kmax = 2; while (kmax < (int)n) kmax <<= 1;   // lanes >= n hold padding: stages above nextpow2(n) change nothing
-  for (int k = 2; k <= kmax; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      const u64 o = __shfl_xor_sync(0xffffffffu, v, j);
-      const bool opad = __shfl_xor_sync(0xffffffffu, (int)pad, j) != 0;
-      const bool up = (lane & k) == 0, lower = (lane & j) == 0;
-      const bool o_less = (!opad && pad) || (opad == pad && o < v);
-      const bool v_less = (!pad && opad) || (opad == pad && v < o);
-      const bool take = (lower == up) ? o_less : v_less;
-      if (take) { v = o; pad = opad; }
+  list_append(b.sort16, b.sort_count, which == 0, (u32)r);
+  list_append(b.sort32, b.sort_count + 1, which == 1, (u32)r);
+  list_append(b.big_list, b.big_count, which == 2, (u32)r);
+}
+
+// W lanes per read (16 or 32): bitonic sort in registers over shuffles, run-length encode with a ballot, written back in
+// place.  Padding is ~0: a real candidate equal to it sorts next to the padding, so the first n entries are still right.
+template <int W>
+__global__ void __launch_bounds__(128) votes_sort(BatchView b) {
+  const u32 nlist = *b.status ? 0u : b.sort_count[W == 16 ? 0 : 1];
+  const u32* list = W == 16 ? b.sort16 : b.sort32;
+  const int lane = threadIdx.x & 31, sub = lane & (W - 1), half_shift = lane & ~(W - 1);
+  const u32 groups = gridDim.x * blockDim.x / W;
+  for (u32 g0 = 0; g0 < nlist; g0 += groups) {
+    const u32 g = g0 + (blockIdx.x * blockDim.x + threadIdx.x) / W;
+    const bool live = g < nlist;
+    int r = 0; u32 beg = 0, n = 0;
+    if (live) { r = (int)list[g]; beg = b.coff[r]; n = b.coff[r + 1] - beg; }
+    u64 v = sub < (int)n ? b.cand[beg + sub] : ~0ull;
+#pragma unroll
+    for (int k = 2; k <= W; k <<= 1)
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        const u64 o = __shfl_xor_sync(0xffffffffu, v, j);
+        const bool take_min = ((sub & k) == 0) == ((sub & j) == 0);
+        v = take_min ? (o < v ? o : v) : (o > v ? o : v);
+      }
+    const bool multi = live && b.round == 0 && b.state[r] == BMBS_MULTI_EXACT;
+    const u64 prev = __shfl_up_sync(0xffffffffu, v, 1);
+    const bool head = live && !multi && sub < (int)n && (sub == 0 || prev != v);
+    const u32 heads = (__ballot_sync(0xffffffffu, head) >> half_shift) & (W == 32 ? 0xffffffffu : 0xffffu);
+    if (multi) { if (sub < (int)n) { b.cand[beg + sub] = v; b.vcnt[beg + sub] = 0; } if (sub == 0) b.nv[r] = n; }
+    else if (live) {
+      if (head) {
+        const u32 idx = __popc(heads & ((1u << sub) - 1u));
+        const u32 later = heads & ~((2u << sub) - 1u);       // run length = distance to the next head (or to n)
+        const u32 next = later ? (u32)(__ffs(later) - 1) : n;
+        b.cand[beg + idx] = window_start(v, (u64)b.kk[r]);
+        b.vcnt[beg + idx] = next - sub;
+      }
+      if (sub == 0) b.nv[r] = __popc(heads);
     }
-  if (multi) { if (lane < (int)n) { b.cand[beg + lane] = v; b.vcnt[beg + lane] = 0; } if (lane == 0) b.nv[r] = n; return; }
-  const u64 prev = __shfl_up_sync(0xffffffffu, v, 1);
-  const bool head = lane < (int)n && (lane == 0 || prev != v);
-  const u32 heads = __ballot_sync(0xffffffffu, head);
-  const u32 valid = n == 32 ? 0xffffffffu : ((1u << n) - 1u);
-  if (head) {
-    const u32 idx = __popc(heads & ((1u << lane) - 1u));
-    // run length = distance to the next head (or to n)
-    const u32 later = heads & ~((2u << lane) - 1u) & valid;
-    const u32 next = later ? (u32)(__ffs(later) - 1) : n;
-    b.cand[beg + idx] = window_start(v, (u64)b.kk[r]);
-    b.vcnt[beg + idx] = next - lane;
   }
-  if (lane == 0) b.nv[r] = __popc(heads);
 }
 
 // one CTA per long segment: bitonic sort on a power-of-two padded copy (shared memory when it fits,
@@ -929,7 +949,7 @@ __global__ void sens_pair(BatchView b) {
 __global__ void reseed_clear(BatchView b) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < b.n_reads) { b.ntask[r] = 0; b.ncand[r] = 0; b.nv[r] = 0; }
-  if (r == 0) { b.totals[2] = b.totals[1]; b.list_count[3] = 0; }      // the re-seeding round appends to out_cand
+  if (r == 0) { b.totals[2] = b.totals[1]; b.list_count[3] = 0; b.sort_count[0] = 0; b.sort_count[1] = 0; b.big_count[0] = 0; b.scratch_used[0] = 0; }      // the re-seeding round appends to out_cand
 }
 
 // reseed_filter_muti_thread, Schema.cpp:16998-17240: up to three exact seeds chosen from the gaps of the seeds used so

@@ -4,7 +4,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 #include "bmbs_kernels.cuh"
 
@@ -16,6 +19,16 @@ thread_local std::string g_err;
 int fail(int code, const std::string& m) { g_err = m; return code; }
 
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(BMBS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+// splits [0, n) over a few host threads (index re-layout at load)
+template <class F> void parallel_for(u64 n, F fn) {
+  unsigned hw = std::thread::hardware_concurrency();
+  const u64 T = std::max<u64>(1, std::min<u64>(hw ? hw : 4, 16));
+  std::vector<std::thread> th;
+  for (u64 t = 1; t < T; ++t) th.emplace_back([=] { fn(n * t / T, n * (t + 1) / T); });
+  fn(0, n / T);
+  for (auto& x : th) x.join();
+}
 
 template <class T> bool read_vec(FILE* f, std::vector<T>& v, size_t n) { v.resize(n); return n == 0 || fread(v.data(), sizeof(T), n, f) == n; }
 
@@ -74,7 +87,8 @@ template <int LEFT>
 __device__ void ktab_node(const DevIndex& ix, u64* t, u32 prefix, u32 stride, u32 m, u64 top, u64 bot) {
   // node: symbols 16..m-1 fixed (extension value `prefix`, next digit weighs `stride`), interval [top, bot) not empty
   constexpr u32 below = LEFT == 0 ? 1 : LEFT == 1 ? 3 : LEFT == 2 ? 9 : LEFT == 3 ? 27 : 81;
-  if (bot - top == 1 || LEFT == 0) { ktab_fill(t, prefix, stride, below, kmer_entry(m, top, bot)); return; }
+  if (bot - top == 1) { int st; const u64 sa = locate_row(ix, top, st); ktab_fill(t, prefix, stride, below, kmer_entry(m, sa, sa + 1)); return; }   // one row: store its SA value
+  if (LEFT == 0) { ktab_fill(t, prefix, stride, below, kmer_entry(m, top, bot)); return; }
   if constexpr (LEFT > 0) {
     for (int c = 0; c < 3; ++c) {
       u64 a = top, b = bot;
@@ -126,35 +140,48 @@ extern "C" void bmbs_index_free(bmbs_index* idx) {
 extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int n_dev, bmbs_index** out) {
   if (!index_prefix || !out) return fail(BMBS_ERR_ARG, "null argument");
   HostIndex h;
+  const bool verbose = getenv("BMBS_VERBOSE") != nullptr;
+  auto tnow = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; };
+  double t_prev = tnow();
+  auto lap = [&](const char* what) { if (verbose) { const double t = tnow(); fprintf(stderr, "[bmbs load] %-28s %.3f s\n", what, t - t_prev); t_prev = t; } };
+  // CUDA context creation overlaps the file reads and the host re-layout
+  int dev0 = 0;
+  if (!devices || n_dev <= 0) { devices = &dev0; n_dev = 1; }
+  std::thread warm([=] { for (int d = 0; d < n_dev; ++d) { cudaSetDevice(devices[d]); cudaFree(0); } });
   int rc = load_files(index_prefix, h);
-  if (rc) return rc;
+  if (rc) { warm.join(); return rc; }
+  lap("read index files");
   const u64 n = 2 * h.N;                       // text length = BWT symbols
   // ---- occ blocks: fold the 65536-row table and the 16-bit counters into absolute counts
   const u64 nblk = (n >> 6) + 2;
   std::vector<u64> occ(nblk * 4, 0);
   h.bwt.resize(h.bwt.size() + 16, 0);
-  for (u64 b = 0; b < nblk; ++b) {
-    const u64 sb = (b >> 1) * 5, sub = b & 1, w = sb + 1 + 2 * sub, hi_i = ((b << 6) >> 16) * 2;
-    if (w + 1 >= h.bwt.size() || hi_i + 1 >= h.high_occ.size()) break;
-    const u64 hdr = h.bwt[sb];
-    occ[b * 4 + 0] = h.bwt[w];
-    occ[b * 4 + 1] = h.bwt[w + 1];
-    occ[b * 4 + 2] = h.high_occ[hi_i] + ((hdr >> (48 - 32 * sub)) & 0xFFFF);
-    occ[b * 4 + 3] = h.high_occ[hi_i + 1] + ((hdr >> (32 - 32 * sub)) & 0xFFFF);
-  }
+  parallel_for(nblk, [&](u64 lo, u64 hi) {
+    for (u64 b = lo; b < hi; ++b) {
+      const u64 sb = (b >> 1) * 5, sub = b & 1, w = sb + 1 + 2 * sub, hi_i = ((b << 6) >> 16) * 2;
+      if (w + 1 >= h.bwt.size() || hi_i + 1 >= h.high_occ.size()) break;
+      const u64 hdr = h.bwt[sb];
+      occ[b * 4 + 0] = h.bwt[w];
+      occ[b * 4 + 1] = h.bwt[w + 1];
+      occ[b * 4 + 2] = h.high_occ[hi_i] + ((hdr >> (48 - 32 * sub)) & 0xFFFF);
+      occ[b * 4 + 3] = h.high_occ[hi_i + 1] + ((hdr >> (32 - 32 * sub)) & 0xFFFF);
+    }
+  });
   std::vector<u64>().swap(h.bwt);
   // ---- flag blocks: 64 rows each, with the rank of the block start
   const u64 nfb = (h.sa_length >> 6) + 2;
   std::vector<u64> flag(nfb * 2, 0);
   h.sa_flag.resize(h.sa_flag.size() + 16, 0);
-  for (u64 b = 0; b < nfb; ++b) {
-    const u64 g = (b >> 2) * 5, in = b & 3;
-    if (g + 1 + in >= h.sa_flag.size()) break;
-    u64 rank = h.sa_flag[g];
-    for (u64 t = 0; t < in; ++t) rank += __builtin_popcountll(h.sa_flag[g + 1 + t]);
-    flag[b * 2] = h.sa_flag[g + 1 + in];
-    flag[b * 2 + 1] = rank;
-  }
+  parallel_for(nfb, [&](u64 lo, u64 hi) {
+    for (u64 b = lo; b < hi; ++b) {
+      const u64 g = (b >> 2) * 5, in = b & 3;
+      if (g + 1 + in >= h.sa_flag.size()) break;
+      u64 rank = h.sa_flag[g];
+      for (u64 t = 0; t < in; ++t) rank += __builtin_popcountll(h.sa_flag[g + 1 + t]);
+      flag[b * 2] = h.sa_flag[g + 1 + in];
+      flag[b * 2 + 1] = rank;
+    }
+  });
   // the flag file's last word is uninitialised in reference-built indexes (reads past its allocation,
   // bwt.cpp:1188-1192 vs :1657-1664); it lies beyond the last row and is masked here
   {
@@ -166,23 +193,34 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
   // ---- 16-mer table: one u64 per entry
   const size_t nh = h.hash_hi.size();
   std::vector<u64> hash(nh + 2, 0);
-  for (size_t i = 0; i < nh; ++i) hash[i] = ((u64)(h.hash_hi[i] & 0x0FFFFFFFu) << 8) | h.hash_lo[i] | ((u64)(h.hash_hi[i] >> 28) << 60);
+  parallel_for(nh, [&](u64 lo, u64 hi) {
+    for (u64 i = lo; i < hi; ++i) hash[i] = ((u64)(h.hash_hi[i] & 0x0FFFFFFFu) << 8) | h.hash_lo[i] | ((u64)(h.hash_hi[i] >> 28) << 60);
+  });
   std::vector<u32>().swap(h.hash_hi); std::vector<uint8_t>().swap(h.hash_lo);
   // ---- bit-planes of G ++ revcomp(G)
   const u64 npw = (n + 31) / 32 + 64;
   std::vector<uint2> planes(npw, make_uint2(0, 0));
-  for (u64 i = 0; i < h.N; ++i) {
-    const u32 c = (h.pac[i >> 2] >> (6 - 2 * (i & 3))) & 3;
-    planes[i >> 5].x |= (c & 1u) << (i & 31); planes[i >> 5].y |= (c >> 1) << (i & 31);
-    const u64 j = n - 1 - i; const u32 rc = 3 - c;
-    planes[j >> 5].x |= (rc & 1u) << (j & 31); planes[j >> 5].y |= (rc >> 1) << (j & 31);
-  }
+  parallel_for((n + 31) / 32, [&](u64 lo, u64 hi) {        // one 32-base word at a time: forward strand, then the reverse complement
+    for (u64 w = lo; w < hi; ++w) {
+      u32 x = 0, y = 0;
+      for (u32 t = 0; t < 32; ++t) {
+        const u64 pos = w * 32 + t;
+        if (pos >= n) break;
+        u32 c;
+        if (pos < h.N) c = (h.pac[pos >> 2] >> (6 - 2 * (pos & 3))) & 3;
+        else { const u64 i = n - 1 - pos; c = 3 - ((h.pac[i >> 2] >> (6 - 2 * (i & 3))) & 3); }
+        x |= (c & 1u) << t; y |= (c >> 1) << t;
+      }
+      planes[w] = make_uint2(x, y);
+    }
+  });
   std::vector<uint8_t>().swap(h.pac);
+  lap("host re-layout");
 
   bmbs_index* idx = new bmbs_index();
   idx->N = h.N;
-  int dev0 = 0;
-  if (!devices || n_dev <= 0) { devices = &dev0; n_dev = 1; }
+  warm.join();
+  lap("(wait for the CUDA context)");
   for (int d = 0; d < n_dev; ++d) {
     DeviceCopy c; c.dev = devices[d];
     auto up = [&](void** p, const void* src, size_t bytes) -> cudaError_t {
@@ -203,6 +241,28 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
     v.C[0] = h.nacgt[0]; v.C[1] = h.nacgt[1]; v.C[2] = h.nacgt[2];
     v.shapline = h.shapline; v.n_rows = h.sa_length; v.N = h.N;
     v.dsa_lo = nullptr; v.dsa_hi = nullptr; v.ktab = nullptr; v.kdepth = 0; v.kpow = 1;
+    lap("cuda init + upload");
+    // ---- dense suffix array (BMBS_SA=sampled keeps the on-disk 1/8 sampling; default: dense when it fits with room to spare)
+    const char* mode = getenv("BMBS_SA");
+    const bool wide = h.sa_length > 0xFFFFFFFFull;
+    const size_t need = (size_t)h.sa_length * (wide ? 5 : 4);
+    size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
+    const bool want = mode ? strcmp(mode, "sampled") != 0 : need + (total_b >> 2) < free_b;
+    if (want) {
+      DeviceCopy& cc = idx->copies.back();
+      e = cudaMalloc(&cc.dsa_lo, (size_t)h.sa_length * 4 + 256);
+      if (e == cudaSuccess && wide) e = cudaMalloc(&cc.dsa_hi, (size_t)h.sa_length + 256);
+      if (e == cudaSuccess) {
+        cudaDeviceProp prop; cudaGetDeviceProperties(&prop, cc.dev);
+        densify_sa<<<prop.multiProcessorCount * 8, 256>>>(v, (u32*)cc.dsa_lo, (unsigned char*)cc.dsa_hi);
+        e = cudaDeviceSynchronize();
+      }
+      if (e != cudaSuccess) { std::string m = std::string("dense suffix array: ") + cudaGetErrorString(e); bmbs_index_free(idx); return fail(BMBS_ERR_CUDA, m); }
+      v.dsa_lo = (const u32*)cc.dsa_lo; v.dsa_hi = (const unsigned char*)cc.dsa_hi;
+      cudaFree(cc.flag); cudaFree(cc.ssa); cc.flag = nullptr; cc.ssa = nullptr; v.flag = nullptr; v.ssa = nullptr;
+      cc.bytes += need; cc.bytes -= flag.size() * 8 + h.ssa.size() * 4;
+    }
+    lap("dense suffix array");
     // ---- deep seed table: K = 16..20 (BMBS_KMER); default: the smallest K whose 3^K exceeds 8 x the text length -- a
     // random K-mer then rarely has a second occurrence, so most seeds end on their first lookup -- if it fits in a quarter of HBM
     {
@@ -231,26 +291,7 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
         cc.bytes += kb;
       }
     }
-    // ---- dense suffix array (BMBS_SA=sampled keeps the on-disk 1/8 sampling; default: dense when it fits with room to spare)
-    const char* mode = getenv("BMBS_SA");
-    const bool wide = h.sa_length > 0xFFFFFFFFull;
-    const size_t need = (size_t)h.sa_length * (wide ? 5 : 4);
-    size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
-    const bool want = mode ? strcmp(mode, "sampled") != 0 : need + (total_b >> 2) < free_b;
-    if (want) {
-      DeviceCopy& cc = idx->copies.back();
-      e = cudaMalloc(&cc.dsa_lo, (size_t)h.sa_length * 4 + 256);
-      if (e == cudaSuccess && wide) e = cudaMalloc(&cc.dsa_hi, (size_t)h.sa_length + 256);
-      if (e == cudaSuccess) {
-        cudaDeviceProp prop; cudaGetDeviceProperties(&prop, cc.dev);
-        densify_sa<<<prop.multiProcessorCount * 8, 256>>>(v, (u32*)cc.dsa_lo, (unsigned char*)cc.dsa_hi);
-        e = cudaDeviceSynchronize();
-      }
-      if (e != cudaSuccess) { std::string m = std::string("dense suffix array: ") + cudaGetErrorString(e); bmbs_index_free(idx); return fail(BMBS_ERR_CUDA, m); }
-      v.dsa_lo = (const u32*)cc.dsa_lo; v.dsa_hi = (const unsigned char*)cc.dsa_hi;
-      cudaFree(cc.flag); cudaFree(cc.ssa); cc.flag = nullptr; cc.ssa = nullptr; v.flag = nullptr; v.ssa = nullptr;
-      cc.bytes += need; cc.bytes -= flag.size() * 8 + h.ssa.size() * 4;
-    }
+    lap("deep seed table");
   }
   *out = idx;
   return BMBS_OK;
@@ -272,9 +313,22 @@ struct bmbs_batch {
 };
 
 namespace {
-template <class T> cudaError_t dalloc(bmbs_batch* b, T** p, size_t n) {
-  void* q = nullptr; cudaError_t e = cudaMalloc(&q, n * sizeof(T) + 256);
-  if (e == cudaSuccess) { b->allocs.push_back(q); *p = (T*)q; }
+// device arrays of a batch are carved out of one slab (one cudaMalloc per batch context): requests are recorded first
+struct SlabRequest { void** slot; size_t bytes; };
+thread_local std::vector<SlabRequest> g_slab;
+template <class T> cudaError_t dalloc(bmbs_batch*, T** p, size_t n) {
+  g_slab.push_back({(void**)p, ((n * sizeof(T) + 256) + 255) & ~(size_t)255});
+  return cudaSuccess;
+}
+cudaError_t slab_commit(bmbs_batch* b) {
+  size_t total = 0; for (auto& r : g_slab) total += r.bytes;
+  void* base = nullptr; cudaError_t e = cudaMalloc(&base, total + 256);
+  if (e == cudaSuccess) {
+    b->allocs.push_back(base);
+    char* p = (char*)base;
+    for (auto& r : g_slab) { *r.slot = p; p += r.bytes; }
+  }
+  g_slab.clear();
   return e;
 }
 }  // namespace
@@ -300,6 +354,7 @@ extern "C" int bmbs_batch_create(bmbs_index* idx, int dev, size_t max_reads, siz
   cudaDeviceProp prop; cudaGetDeviceProperties(&prop, dev); b->sm_count = prop.multiProcessorCount;
   BatchView& v = b->v;
   const size_t R = max_reads + 2, S = cand_cap + 64;
+  g_slab.clear();
   cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
   auto A = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
   A(dalloc(b, &b->d_ascii, max_bases + 64)); A(dalloc(b, &b->d_offsets, R));
@@ -316,6 +371,7 @@ extern "C" int bmbs_batch_create(bmbs_index* idx, int dev, size_t max_reads, siz
   A(dalloc(b, &v.scratch, (size_t)v.scratch_cap)); A(dalloc(b, &v.scratch_used, 4));
   A(dalloc(b, &v.counters, 16)); A(dalloc(b, &v.totals, 4)); A(dalloc(b, &v.status, 4));
   A(dalloc(b, &b->d_tile, R / SCAN_TILE + 8));
+  A(slab_commit(b));
   A(cudaMallocHost((void**)&b->h_small, 32 * sizeof(u64)));
   for (auto& evt : b->ev) A(cudaEventCreate(&evt));
   if (e != cudaSuccess) { std::string m = std::string("batch allocation: ") + cudaGetErrorString(e); bmbs_batch_free(b); return fail(BMBS_ERR_CUDA, m); }
@@ -482,6 +538,9 @@ extern "C" int bmbs_batch_counters(bmbs_batch* b, uint64_t c[8]) {
 }
 
 extern "C" int bmbs_batch_launches(bmbs_batch* b) { return b ? b->launches : 0; }
+
+extern "C" void* bmbs_pinned_alloc(size_t bytes) { void* p = nullptr; return cudaMallocHost(&p, bytes ? bytes : 1) == cudaSuccess ? p : nullptr; }
+extern "C" void bmbs_pinned_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ================================================================================================ one-call forms
 namespace {

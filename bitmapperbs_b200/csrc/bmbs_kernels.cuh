@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(128) pack_reads(BatchView b) {
 }
 
 // ------------------------------------------------------------------------------------------- seed
-struct SeedHit { u64 hits, sp, ep; u32 mlen; };
+struct SeedHit { u64 hits, sp, ep; u32 mlen; bool has_sa; u64 sa; };   // has_sa: one row left and its suffix-array value is already known
 
 // Read bases as bit-planes.  FM alphabet of the reversed, C->T converted read: G0 T1 A2, anything else stops a seed;
 // from the planes (A00 C01 G10 T11): fm = lo | ((~lo & ~hi) << 1).
@@ -190,7 +190,7 @@ __device__ __forceinline__ bool kmer_ext(const DevIndex& ix, const unsigned char
 // the seed starts at read[off] and grows to the right; cur = L - off bases are available.
 __device__ __forceinline__ SeedHit seed_until_unique(const DevIndex& ix, const ReadPlanes& rp, const unsigned char* lut, u32 off, u32 cur,
                                                      u64 sp_in, u64 ep_in, u32& n_occ, u32& n_hash) {
-  SeedHit h; h.hits = 0; h.sp = sp_in; h.ep = ep_in; h.mlen = 0;
+  SeedHit h; h.hits = 0; h.sp = sp_in; h.ep = ep_in; h.mlen = 0; h.has_sa = false; h.sa = 0;
   if (cur < 18) return h;
   u32 key;
   if (!key16(rp, lut, off, key)) return h;
@@ -206,6 +206,7 @@ __device__ __forceinline__ SeedHit seed_until_unique(const DevIndex& ix, const R
       if (size != KTAB_SAT) {
         if (code == 0) return h;
         m = 15 + code; top = e & 0xFFFFFFFFFull; bot = top + size;
+        if (size == 1) { h.mlen = m; h.hits = 1; h.has_sa = true; h.sa = top; return h; }   // one row: the entry holds its SA value
         if (m < 16 + ix.kdepth) { h.mlen = m; h.sp = top; h.ep = bot; h.hits = size; return h; }
         deep = true;
       }
@@ -245,7 +246,7 @@ __device__ __forceinline__ u64 count_exact(const DevIndex& ix, const ReadPlanes&
   u64 top = 0, bot = 0;
   u32 m = 16;
   SymbolStream ss(rp, off + 16);
-  bool deep = false;
+  bool deep = false, known_sa = false; u64 sa_known = 0;
   if (ix.ktab && cur >= 16 + ix.kdepth) {
     u32 ext;
     if (kmer_ext(ix, lut, ss.lo, ss.hi, ss.bad, ext)) {
@@ -255,6 +256,7 @@ __device__ __forceinline__ u64 count_exact(const DevIndex& ix, const ReadPlanes&
         if (code == 0) return 0;
         m = 15 + code; top = e & 0xFFFFFFFFFull; bot = top + size;
         if (m < 16 + ix.kdepth && size >= 2) return 0;   // the next symbol empties the interval
+        if (size == 1) { known_sa = true; sa_known = top; }   // one row: the entry holds its SA value
         deep = true;
       }
     }
@@ -266,7 +268,7 @@ __device__ __forceinline__ u64 count_exact(const DevIndex& ix, const ReadPlanes&
   for (; m < cur; ++m) {
     if (bot <= top) break;
     if (bot - top == 1) {
-      int st; const u64 sa = locate_row(ix, top, st); n_llf += st; ++n_rows;
+      int st = 0; const u64 sa = known_sa ? sa_known : locate_row(ix, top, st); n_llf += st; ++n_rows;
       const u64 s0 = 2 * ix.N - sa - m;                 // double-strand coordinate of read[off]
       if (s0 + cur > 2 * ix.N) return 0;                // the text ends before the pattern does
       for (u32 p = off + m; p < off + cur; p += 32) {
@@ -286,6 +288,11 @@ __device__ __forceinline__ u64 count_exact(const DevIndex& ix, const ReadPlanes&
     const int c = ss.at(off + m);
     if (c > 2) return 0;
     n_occ += lf_pair(ix, top, bot, c);
+  }
+  if (known_sa) {                                     // the pattern ends exactly where the table entry stands
+    const u64 s0 = 2 * ix.N - sa_known - m;
+    have_site = true; site = s0 - off;
+    return 1;
   }
   sp = top; ep = bot;
   return bot <= top ? 0 : bot - top;
@@ -392,7 +399,7 @@ __global__ void __launch_bounds__(128) seed_first(DevIndex ix, BatchView b) {
       sp = h.sp; ep = h.ep;
       u32 mlen = h.mlen; first_len = mlen;
       if (h.hits == 1) {
-        int st; const u64 sa = locate_row(ix, sp, st); cn.n_llf += st; ++cn.n_rows;
+        int st = 0; const u64 sa = h.has_sa ? h.sa : locate_row(ix, sp, st); cn.n_llf += st; ++cn.n_rows;
         const u64 site = 2 * ix.N - sa - mlen;
         tw.emit(site, 0, 0, 0);
         if (mlen > first_c) mlen = first_c;
@@ -496,7 +503,7 @@ __global__ void __launch_bounds__(128) seed_rest(DevIndex ix, BatchView b) {
       SeedHit h = seed_until_unique(ix, rp, s_lut, off, cur, sp, ep, cn.n_occ, cn.n_hash);
       sp = h.sp; ep = h.ep;
       bool used = true;
-      if (h.hits == 1) tw.emit(sp, 1, h.mlen, off);
+      if (h.hits == 1) { if (h.has_sa) tw.emit(2 * ix.N - h.sa - h.mlen - off, 0, 0, 0); else tw.emit(sp, 1, h.mlen, off); }
       else if (h.mlen >= b.seed_len && h.hits <= MAX_SEED_HITS) { if (h.hits) tw.emit(sp, (u32)h.hits, h.mlen, off); }
       else { used = false; if (cur == h.mlen) break; }
       if (used) { if (bn == 0) bs0 = off; else if (bn == 1) bs1 = off; bep = bel; bel = off + h.mlen; ++bn; }
@@ -517,7 +524,7 @@ __global__ void expand_tasks(BatchView b) {
   const u32 nt = b.ntask[r];
   for (u32 t = 0; t < nt; ++t) {
     const SeedTask k = b.tasks[(size_t)t * b.n_reads + r];
-    if (k.hits == 0) { b.slot_row[s] = k.sp; b.slot_adj[s] = 0xFFFFFFFFu; b.slot_read[s] = r; ++s; }
+    if (k.hits == 0) { b.cand[s] = k.sp; b.slot_adj[s] = 0xFFFFFFFFu; b.slot_read[s] = r; ++s; }     // already a site
     else for (u32 j = 0; j < k.hits; ++j, ++s) { b.slot_row[s] = k.sp + j; b.slot_adj[s] = (u32)k.mlen + (u32)k.off; b.slot_read[s] = r; }
   }
 }
@@ -531,9 +538,7 @@ __global__ void __launch_bounds__(256) locate_rows(DevIndex ix, BatchView b) {
   u64 steps = 0, rows = 0;
   for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
     const u32 adj = b.slot_adj[s];
-    u64 v = b.slot_row[s];
-    if (adj != 0xFFFFFFFFu) { int st; const u64 sa = locate_row(ix, v, st); v = 2 * ix.N - sa - (u64)adj; ++rows; steps += st; }
-    b.cand[s] = v;
+    if (adj != 0xFFFFFFFFu) { int st; const u64 sa = locate_row(ix, b.slot_row[s], st); b.cand[s] = 2 * ix.N - sa - (u64)adj; ++rows; steps += st; }
   }
   atomicAdd(&s_cnt[0], rows); atomicAdd(&s_cnt[1], steps);
   __syncthreads();
@@ -990,7 +995,7 @@ __global__ void __launch_bounds__(128) seed_reseed(DevIndex ix, BatchView b) {
       const u32 cur = L - off;
       SeedHit h = seed_until_unique(ix, rp, s_lut, off, cur, sp, ep, cn.n_occ, cn.n_hash);
       sp = h.sp; ep = h.ep;
-      if (h.hits == 1) tw.emit(sp, 1, h.mlen, off);
+      if (h.hits == 1) { if (h.has_sa) tw.emit(2 * ix.N - h.sa - h.mlen - off, 0, 0, 0); else tw.emit(sp, 1, h.mlen, off); }
       else if (h.mlen >= 20 && h.hits <= MAX_SEED_HITS) { if (h.hits) tw.emit(sp, (u32)h.hits, h.mlen, off); }
       else if (cur == h.mlen) break;
       off += 8;

@@ -7,8 +7,8 @@
 //   -o <out.sam>  -t <host threads>  -e <rate>  --seed <len>  --min/--max <insert>  --mapstats <file>
 //   --mp_max/--mp_min/--np/--gap_open/--gap_extension  --phred33/--phred64   -g/--gpus <n>
 // Records are written in input order (the reference's `-t 1` order).
-// Pipeline: reader thread -> per-GPU worker (H2D, kernels, D2H through include/bmbs.h) ->
-// host finishing threads (reduction, CIGAR, MAPQ, SAM text) -> ordered writer.
+// Pipeline: block splitter -> FASTQ parse workers -> GPU threads (two batches in flight per device: H2D, kernels,
+// D2H through include/bmbs.h) -> host finishing workers (reduction, CIGAR, MAPQ, SAM text) -> ordered writer.
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -34,16 +34,20 @@ struct Options {
   std::string mode, genome, seq, seq1, seq2, out = "output", mapstats;
   bool pe = false, sensitive = false;
   int threads = 1, gpus = 1;
-  size_t batch_reads = 1 << 18;
+  size_t batch_reads = 1 << 15;                      // reads (pairs) per batch
   bmbs_params prm; Scoring sc;
 };
 
+struct RawBatch { size_t seq_no = 0; size_t n_rec = 0; std::string raw1, raw2; };
+
 struct Batch {
   size_t seq_no = 0; int n = 0;                      // n reads (SE) or mates (PE, even)
-  std::vector<std::string> name, seq, qual, raw;     // raw: mate-2 FASTQ record (PE)
-  std::string flat; std::vector<uint64_t> offsets;
+  std::string raw1, raw2;                            // FASTQ text the views below point into (bases upper-cased in place)
+  std::vector<std::string_view> name, qual, fq_seq;  // per read / mate; fq_seq: the sequence as it stands in the FASTQ record
+  std::string flat; std::vector<uint64_t> offsets;   // sequences as aligned (mate 2 reverse-complemented), back to back
   std::vector<bmbs_read_result> res; std::vector<bmbs_cand> cand;
   std::string sam; MapStats st;
+  std::string_view seq(int i) const { return std::string_view(flat.data() + offsets[i], (size_t)(offsets[i + 1] - offsets[i])); }
 };
 
 template <class T> class Channel {
@@ -99,33 +103,62 @@ void parse(int argc, char** argv, Options& o) {
   o.prm.sensitive = (o.sensitive && o.pe) ? 1 : 0;      // --sensitive only selects the pair worker (Bitmapper_main.cpp)
 }
 
-void finish_batch(const HostContext& hc, Batch& b, bool pe, int threads) {
-  const int units = pe ? b.n / 2 : b.n;
-  const int T = std::max(1, std::min(threads, units / 256 + 1));
-  std::vector<std::string> out(T); std::vector<MapStats> st(T);
-  auto work = [&](int t) {
-    std::vector<HostHit> v1, v2; std::vector<char> win;
-    const int lo = (int)((long long)units * t / T), hi = (int)((long long)units * (t + 1) / T);
-    out[t].reserve((size_t)(hi - lo) * (pe ? 900 : 400));
-    for (int u = lo; u < hi; ++u) {
-      if (!pe) {
-        ReadView rv{&b.name[u], &b.seq[u], &b.qual[u]};
-        finish_single(hc, rv, b.res[u], b.cand.data(), out[t], st[t], v1, win);
-      } else {
-        finish_pair(hc, b.name[2 * u], b.seq[2 * u], b.qual[2 * u], b.name[2 * u + 1], b.seq[2 * u + 1], b.raw[u], b.qual[2 * u + 1],
-                    b.res[2 * u], b.res[2 * u + 1], b.cand.data(), out[t], st[t], v1, v2, win);
-      }
-    }
+inline void upper_in_place(std::string_view v) {
+  char* p = const_cast<char*>(v.data());
+  for (size_t i = 0; i < v.size(); ++i) { const char c = p[i]; if (c >= 'a' && c <= 'z') p[i] = (char)(c - 32); }
+}
+
+// FASTQ text -> batch (names cut, bases upper-cased, mate 2 reverse-complemented for alignment): Process_Reads.cpp:62-90, :321-472
+void parse_batch(RawBatch& rb, bool pe, Batch& b) {
+  b.seq_no = rb.seq_no;
+  b.raw1 = std::move(rb.raw1); b.raw2 = std::move(rb.raw2);
+  const size_t n = rb.n_rec * (pe ? 2 : 1);
+  b.n = (int)n;
+  b.name.resize(n); b.qual.resize(n); b.fq_seq.resize(n);
+  b.offsets.resize(n + 1); b.offsets[0] = 0;
+  b.flat.clear(); b.flat.reserve((pe ? b.raw1.size() + b.raw2.size() : b.raw1.size()) / 2 + 64);
+  const char* p1 = b.raw1.data(); const char* e1 = p1 + b.raw1.size();
+  const char* p2 = b.raw2.data(); const char* e2 = p2 + b.raw2.size();
+  auto record = [](const char*& p, const char* e, std::string_view& name, std::string_view& seq, std::string_view& qual) {
+    name = next_line(p, e); seq = next_line(p, e); next_line(p, e); qual = next_line(p, e);
+    if (!name.empty() && name[0] == '@') name.remove_prefix(1);
+    upper_in_place(seq);
+    if (qual.size() > seq.size()) qual = qual.substr(0, seq.size());
   };
-  std::vector<std::thread> th;
-  for (int t = 1; t < T; ++t) th.emplace_back(work, t);
-  work(0);
-  for (auto& x : th) x.join();
-  size_t total = 0; for (auto& s : out) total += s.size();
-  b.sam.clear(); b.sam.reserve(total);
-  for (int t = 0; t < T; ++t) {
-    b.sam += out[t];
-    b.st.reads += st[t].reads; b.st.unique += st[t].unique; b.st.ambiguous += st[t].ambiguous; b.st.bases += st[t].bases; b.st.err_bases += st[t].err_bases;
+  for (size_t u = 0; u < rb.n_rec; ++u) {
+    if (!pe) {
+      record(p1, e1, b.name[u], b.fq_seq[u], b.qual[u]);
+      cut_name_se(b.name[u]);
+      b.flat.append(b.fq_seq[u]); b.offsets[u + 1] = b.flat.size();
+    } else {
+      const size_t i = 2 * u, k = i + 1;
+      record(p1, e1, b.name[i], b.fq_seq[i], b.qual[i]);
+      record(p2, e2, b.name[k], b.fq_seq[k], b.qual[k]);
+      cut_name_pe(b.name[i], b.name[k]);
+      b.flat.append(b.fq_seq[i]); b.offsets[i + 1] = b.flat.size();
+      const std::string_view s2 = b.fq_seq[k];
+      const size_t at = b.flat.size(); b.flat.resize(at + s2.size());
+      for (size_t t = 0; t < s2.size(); ++t) {
+        const char c = s2[s2.size() - 1 - t];
+        b.flat[at + t] = c == 'A' ? 'T' : c == 'T' ? 'A' : c == 'C' ? 'G' : c == 'G' ? 'C' : c;
+      }
+      b.offsets[k + 1] = b.flat.size();
+    }
+  }
+}
+
+void finish_batch(const HostContext& hc, Batch& b, bool pe) {
+  const int units = pe ? b.n / 2 : b.n;
+  std::vector<HostHit> v1, v2; std::vector<char> win;
+  b.sam.clear(); b.sam.reserve((size_t)units * (pe ? 900 : 400));
+  for (int u = 0; u < units; ++u) {
+    if (!pe) {
+      ReadView rv{b.name[u], b.seq(u), b.qual[u]};
+      finish_single(hc, rv, b.res[u], b.cand.data(), b.sam, b.st, v1, win);
+    } else {
+      finish_pair(hc, b.name[2 * u], b.seq(2 * u), b.qual[2 * u], b.name[2 * u + 1], b.seq(2 * u + 1), b.fq_seq[2 * u + 1], b.qual[2 * u + 1],
+                  b.res[2 * u], b.res[2 * u + 1], b.cand.data(), b.sam, b.st, v1, v2, win);
+    }
   }
 }
 
@@ -149,7 +182,7 @@ int search(const Options& o, const std::string& cmdline) {
   if (bmbs_index_load(prefix.c_str(), devs.data(), (int)devs.size(), &idx)) die(std::string("index load failed: ") + bmbs_last_error());
   const double t_load = now() - t0;
 
-  FastqReader q1, q2;
+  FastqBlockReader q1, q2;
   const bool pe = o.pe;
   if (pe) { if (!q1.open(o.seq1) || !q2.open(o.seq2)) die("cannot open read files"); }
   else if (!q1.open(o.seq)) die("cannot open " + o.seq);
@@ -157,87 +190,116 @@ int search(const Options& o, const std::string& cmdline) {
   if (!fo) die("cannot write " + o.out);
   { std::string h; sam_header(h, hc.chroms, cmdline); fwrite(h.data(), 1, h.size(), fo); }
 
+  // splitter -> parse workers -> GPU threads (two batches in flight per device) -> finish workers -> ordered writer
   const double t1 = now();
-  Channel<std::unique_ptr<Batch>> to_gpu(2 * devs.size()), to_writer(4 * devs.size());
-  std::thread reader([&] {
+  const int n_parse = std::max(1, o.threads / 2), n_finish = std::max(1, o.threads), n_gpu = 2 * (int)devs.size();
+  std::atomic<long long> us_split(0), us_parse(0), us_gpu(0), us_finish(0), us_write(0), n_retry(0), n_batches(0), us_dev(0), us_up(0), us_run(0), us_down(0), us_prep(0);
+  std::atomic<long long> us_stage[8] = {};
+  auto us = [](double a, double b) { return (long long)((b - a) * 1e6); };
+  Channel<std::unique_ptr<RawBatch>> raw_q(2 * n_parse);
+  Channel<std::unique_ptr<Batch>> gpu_q(2 * n_gpu), fin_q(2 * n_finish), out_q(4 * n_finish);
+  std::thread splitter([&] {
     size_t seq_no = 0;
     for (;;) {
-      std::unique_ptr<Batch> b(new Batch()); b->seq_no = seq_no++;
-      FastqRecord a, c;
-      const size_t want = o.batch_reads;
-      b->offsets.push_back(0);
-      while ((size_t)(pe ? b->n / 2 : b->n) < want && q1.next(a)) {
-        if (pe) {
-          if (!q2.next(c)) break;
-          cut_name_pe(a.name, c.name);
-          std::string rc2 = revcomp(c.seq);
-          b->flat += a.seq; b->offsets.push_back(b->flat.size());
-          b->flat += rc2; b->offsets.push_back(b->flat.size());
-          b->name.push_back(a.name); b->name.push_back(c.name);
-          b->seq.push_back(std::move(a.seq)); b->seq.push_back(std::move(rc2));
-          b->qual.push_back(std::move(a.qual)); b->qual.push_back(std::move(c.qual));
-          b->raw.push_back(std::move(c.seq));
-          b->n += 2;
-        } else {
-          cut_name_se(a.name);
-          b->flat += a.seq; b->offsets.push_back(b->flat.size());
-          b->name.push_back(std::move(a.name)); b->seq.push_back(std::move(a.seq)); b->qual.push_back(std::move(a.qual));
-          b->n += 1;
-        }
-      }
-      if (b->n == 0) break;
-      to_gpu.push(std::move(b));
+      std::unique_ptr<RawBatch> rb(new RawBatch()); rb->seq_no = seq_no++;
+      const double ts = now();
+      size_t n2 = 0;
+      std::thread second;                              // the two files of a pair are split side by side
+      if (pe) second = std::thread([&] { n2 = q2.next(o.batch_reads, rb->raw2); });
+      rb->n_rec = q1.next(o.batch_reads, rb->raw1);
+      if (pe) { second.join(); if (n2 < rb->n_rec) rb->n_rec = n2; }   // the shorter file ends the run, as in the reference's paired reader
+      us_split += us(ts, now());
+      if (rb->n_rec == 0) break;
+      raw_q.push(std::move(rb));
     }
-    to_gpu.close();
+    raw_q.close();
   });
-
-  std::atomic<int> live((int)devs.size());
-  std::vector<std::thread> workers;
-  const int finish_threads = std::max(1, o.threads / (int)devs.size());
-  for (int dev : devs) workers.emplace_back([&, dev] {
+  std::atomic<int> live_parse(n_parse), live_gpu(n_gpu), live_finish(n_finish);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < n_parse; ++t) pool.emplace_back([&] {
+    std::unique_ptr<RawBatch> rb;
+    while (raw_q.pop(rb)) { const double ts = now(); std::unique_ptr<Batch> b(new Batch()); parse_batch(*rb, pe, *b); us_parse += us(ts, now()); gpu_q.push(std::move(b)); }
+    if (--live_parse == 0) gpu_q.close();
+  });
+  for (int g = 0; g < n_gpu; ++g) pool.emplace_back([&, g] {
+    const int dev = devs[g % devs.size()];
+    // one batch context and one set of page-locked result buffers per GPU thread, grown on demand
     bmbs_batch* ctx = nullptr; size_t cap_reads = 0, cap_bases = 0, cap_cand = 0;
+    bmbs_read_result* h_res = nullptr; bmbs_cand* h_cand = nullptr; size_t h_res_cap = 0, h_cand_cap = 0;
+    auto ensure = [&](size_t reads, size_t bases, size_t cands) {
+      if (!ctx || reads > cap_reads || bases > cap_bases || cands > cap_cand) {
+        if (ctx) bmbs_batch_free(ctx);
+        cap_reads = std::max(cap_reads, reads); cap_bases = std::max(cap_bases, bases); cap_cand = std::max(cap_cand, cands);
+        if (bmbs_batch_create(idx, dev, cap_reads, cap_bases, cap_cand, &ctx)) die(std::string("batch create: ") + bmbs_last_error());
+      }
+      if (cap_reads > h_res_cap) { bmbs_pinned_free(h_res); h_res_cap = cap_reads; h_res = (bmbs_read_result*)bmbs_pinned_alloc(h_res_cap * sizeof(bmbs_read_result)); }
+      if (cap_cand > h_cand_cap) { bmbs_pinned_free(h_cand); h_cand_cap = cap_cand; h_cand = (bmbs_cand*)bmbs_pinned_alloc(h_cand_cap * sizeof(bmbs_cand)); }
+      if (!h_res || !h_cand) die("cannot allocate page-locked result buffers");
+    };
+    {   // sized for a full batch of typical reads before the first one arrives
+      const size_t r0 = o.batch_reads * (pe ? 2 : 1);
+      ensure(r0, r0 * 160 + 64, r0 * 24 + (1u << 20));
+    }
     std::unique_ptr<Batch> b;
-    while (to_gpu.pop(b)) {
+    while (gpu_q.pop(b)) {
+      const double ts = now(); ++n_batches;
       const size_t bases = b->flat.size() + 64;
       size_t want_cand = std::max<size_t>(cap_cand, (size_t)b->n * 24 + (1u << 20));
       for (;;) {
-        if (!ctx || (size_t)b->n > cap_reads || bases > cap_bases || want_cand > cap_cand) {
-          if (ctx) bmbs_batch_free(ctx);
-          cap_reads = std::max(cap_reads, (size_t)b->n); cap_bases = std::max(cap_bases, bases); cap_cand = want_cand;
-          if (bmbs_batch_create(idx, dev, cap_reads, cap_bases, cap_cand, &ctx)) die(std::string("batch create: ") + bmbs_last_error());
-        }
-        b->res.resize(b->n); b->cand.resize(cap_cand);
+        const double t_a = now();
+        ensure((size_t)b->n, bases, want_cand);
         size_t used = 0;
+        const double t_b = now();
         int rc = bmbs_batch_upload(ctx, b->flat.data(), b->offsets.data(), b->n, pe ? 1 : 0);
+        const double t_c = now();
         if (!rc) rc = bmbs_batch_run(ctx, &o.prm);
-        if (!rc) rc = bmbs_batch_download(ctx, b->res.data(), b->cand.data(), b->cand.size(), &used);
-        if (rc == BMBS_ERR_CAPACITY) { want_cand = std::max(cap_cand * 2, used + (used >> 2) + 1024); continue; }
+        const double t_d = now();
+        if (!rc) rc = bmbs_batch_download(ctx, h_res, h_cand, h_cand_cap, &used);
+        const double t_e = now();
+        us_prep += us(t_a, t_b); us_up += us(t_b, t_c); us_run += us(t_c, t_d); us_down += us(t_d, t_e);
+        if (!rc) { float ms[8]; if (!bmbs_batch_timings(ctx, ms)) { us_dev += (long long)(ms[0] * 1000); for (int q = 1; q < 8; ++q) us_stage[q] += (long long)(ms[q] * 1000); } }
+        if (rc == BMBS_ERR_CAPACITY) { want_cand = std::max(cap_cand * 2, used + (used >> 2) + 1024); ++n_retry; continue; }
         if (rc) die(std::string("gpu batch failed: ") + bmbs_last_error());
-        b->cand.resize(used);
+        b->res.assign(h_res, h_res + b->n); b->cand.assign(h_cand, h_cand + used);
         break;
       }
-      finish_batch(hc, *b, pe, finish_threads);
-      to_writer.push(std::move(b));
+      us_gpu += us(ts, now());
+      fin_q.push(std::move(b));
     }
     if (ctx) bmbs_batch_free(ctx);
-    if (--live == 0) to_writer.close();
+    bmbs_pinned_free(h_res); bmbs_pinned_free(h_cand);
+    if (--live_gpu == 0) fin_q.close();
+  });
+  for (int t = 0; t < n_finish; ++t) pool.emplace_back([&] {
+    std::unique_ptr<Batch> b;
+    while (fin_q.pop(b)) { const double ts = now(); finish_batch(hc, *b, pe); us_finish += us(ts, now()); out_q.push(std::move(b)); }
+    if (--live_finish == 0) out_q.close();
   });
 
   MapStats total;
   {
     std::map<size_t, std::unique_ptr<Batch>> pending; size_t next = 0;
     std::unique_ptr<Batch> b;
-    while (to_writer.pop(b)) {
+    while (out_q.pop(b)) {
       pending[b->seq_no] = std::move(b);
       while (!pending.empty() && pending.begin()->first == next) {
         Batch& x = *pending.begin()->second;
+        const double ts = now();
         fwrite(x.sam.data(), 1, x.sam.size(), fo);
+        us_write += us(ts, now());
         total.reads += x.st.reads; total.unique += x.st.unique; total.ambiguous += x.st.ambiguous; total.bases += x.st.bases; total.err_bases += x.st.err_bases;
         pending.erase(pending.begin()); ++next;
       }
     }
   }
-  reader.join(); for (auto& w : workers) w.join();
+  splitter.join(); for (auto& w : pool) w.join();
+  if (getenv("BMBS_TIMING")) {
+    fprintf(stderr, "[bmbs timing] gpu threads: prepare %.2f  upload %.2f  run(enqueue) %.2f  download(wait+copy) %.2f  | device %.3f s: pack %.3f seed %.3f locate %.3f votes %.3f pairfilter %.3f verify %.3f sensitive %.3f\n",
+            us_prep / 1e6, us_up / 1e6, us_run / 1e6, us_down / 1e6, us_dev / 1e6, us_stage[1] / 1e6, us_stage[2] / 1e6, us_stage[3] / 1e6, us_stage[4] / 1e6, us_stage[5] / 1e6, us_stage[6] / 1e6, us_stage[7] / 1e6);
+  }
+  if (getenv("BMBS_TIMING"))
+    fprintf(stderr, "[bmbs timing] busy seconds summed over threads: split %.2f  parse %.2f (%d thr)  gpu %.2f (%d thr, %lld batches, %lld capacity retries)  finish %.2f (%d thr)  write %.2f\n",
+            us_split / 1e6, us_parse / 1e6, n_parse, us_gpu / 1e6, n_gpu, (long long)n_batches, (long long)n_retry, us_finish / 1e6, n_finish, us_write / 1e6);
   fclose(fo);
   const double t_map = now() - t1;
   bmbs_index_free(idx);

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <string>
+#include <string_view>
 #include <vector>
 #include "../../../include/bmbs.h"
 #include "fastq.hpp"
@@ -28,7 +29,7 @@ inline void unpack_cands(const bmbs_cand* c, uint32_t n, std::vector<HostHit>& v
   }
 }
 
-struct ReadView { const std::string* name; const std::string* seq; const std::string* qual; };
+struct ReadView { std::string_view name, seq, qual; };
 
 struct HostContext {
   ChromTable chroms;
@@ -42,14 +43,14 @@ inline uint64_t threshold_k(double e_rate, size_t L) { uint64_t k = (uint64_t)(e
 // ---- single end -------------------------------------------------------------------------------
 inline void finish_single(const HostContext& hc, const ReadView& rd, const bmbs_read_result& res, const bmbs_cand* cand,
                           std::string& out, MapStats& st, std::vector<HostHit>& hits, std::vector<char>& win) {
-  const std::string& seq = *rd.seq; const std::string& qual = *rd.qual;
+  const std::string_view seq = rd.seq, qual = rd.qual;
   const int L = (int)seq.size();
   const uint64_t k = threshold_k(hc.prm.e_rate, L);
   ++st.reads;
   auto emit = [&](uint64_t site, uint64_t end_site, int start_site, unsigned nm, const std::string& cigar, int mapq) -> bool {
     Placed p = place(hc.chroms, site, (uint64_t)(int64_t)start_site, end_site);
     if (p.off_chrom) return false;
-    sam_record_se(out, *rd.name, seq, qual, hc.chroms, p, mapq, cigar, nm, p.flag ? revcomp(seq) : std::string());
+    sam_record_se(out, rd.name, seq, qual, hc.chroms, p, mapq, cigar, nm, p.flag ? revcomp(seq) : std::string());
     return true;
   };
   switch (res.state) {
@@ -91,7 +92,7 @@ inline void finish_single(const HostContext& hc, const ReadView& rd, const bmbs_
   if (b.err != 0) {
     const int plen = L + 2 * (int)k; win.resize(plen + 8);
     hc.genome.window(b.site, plen, win.data());
-    refine_alignment(win.data(), plen, seq.c_str(), L, (int)k, (int)b.end_site, b.err, b.site < hc.chroms.N, qual.c_str(), false, hc.sc, rf);
+    refine_alignment(win.data(), plen, seq.data(), L, (int)k, (int)b.end_site, b.err, b.site < hc.chroms.N, qual.data(), false, hc.sc, rf);
   } else { rf.score = 0; rf.start_site = (int)b.end_site - L + 1; rf.end_site = b.end_site; rf.err = 0; rf.cigar = std::to_string(L) + "M"; }
   const int mapq = mapq_from(sbd, (unsigned)k, rf.score, hc.sc);
   if (emit(b.site, rf.end_site, rf.start_site, rf.err, rf.cigar, mapq)) { ++st.unique; st.bases += L; st.err_bases += rf.err; }
@@ -143,7 +144,7 @@ inline Pick pick(const std::vector<HostHit>& a, int na, const std::vector<HostHi
   return r;
 }
 struct Mate { int flag = 0; size_t chrom = 0; uint64_t pos = 0; unsigned err = 0; int score = 0, span = 0; std::string cigar; };
-inline void finish_mate(const HostContext& hc, const std::string& seq, const std::string& qual, uint64_t k, const HostHit& h,
+inline void finish_mate(const HostContext& hc, std::string_view seq, std::string_view qual, uint64_t k, const HostHit& h,
                         bool reverse_quality, Mate& m, std::vector<char>& win) {
   const int L = (int)seq.size();
   int start; uint64_t end = h.end_site;
@@ -152,7 +153,7 @@ inline void finish_mate(const HostContext& hc, const std::string& seq, const std
     const int plen = L + 2 * (int)k; win.resize(plen + 8);
     hc.genome.window(h.site, plen, win.data());
     Refined rf;
-    refine_alignment(win.data(), plen, seq.c_str(), L, (int)k, (int)h.end_site, h.err, h.site < hc.chroms.N, qual.c_str(), reverse_quality, hc.sc, rf);
+    refine_alignment(win.data(), plen, seq.data(), L, (int)k, (int)h.end_site, h.err, h.site < hc.chroms.N, qual.data(), reverse_quality, hc.sc, rf);
     end = rf.end_site; m.err = rf.err; m.score = rf.score; m.cigar = rf.cigar; start = rf.start_site;
     m.span = (int)(end - start + 1);
   } else { m.score = 0; start = (int)(h.end_site + 1 - L); m.cigar = std::to_string(L) + "M"; m.span = L; }
@@ -162,8 +163,8 @@ inline void finish_mate(const HostContext& hc, const std::string& seq, const std
 }  // namespace pe
 
 // seq2 is mate 2 as aligned (reverse complement of the FASTQ record `raw2`), qual2 in FASTQ order.
-inline void finish_pair(const HostContext& hc, const std::string& name1, const std::string& seq1, const std::string& qual1,
-                        const std::string& name2, const std::string& seq2, const std::string& raw2, const std::string& qual2,
+inline void finish_pair(const HostContext& hc, std::string_view name1, std::string_view seq1, std::string_view qual1,
+                        std::string_view name2, std::string_view seq2, std::string_view raw2, std::string_view qual2,
                         const bmbs_read_result& r1, const bmbs_read_result& r2, const bmbs_cand* cand,
                         std::string& out, MapStats& st, std::vector<HostHit>& v1, std::vector<HostHit>& v2, std::vector<char>& win) {
   ++st.reads;

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <string_view>
 #include "postprocess.hpp"
 
 namespace bmbs {
@@ -18,9 +19,9 @@ inline void sam_header(std::string& out, const ChromTable& ct, const std::string
 
 // Single-end record.  `seq`/`qual` as in the FASTQ; reverse-strand hits print
 // the reverse complement and the reversed qualities.
-inline void sam_record_se(std::string& out, const std::string& name, const std::string& seq, const std::string& qual,
+inline void sam_record_se(std::string& out, std::string_view name, std::string_view seq, std::string_view qual,
                           const ChromTable& ct, const Placed& p, int mapq, const std::string& cigar, unsigned nm,
-                          const std::string& rseq) {
+                          std::string_view rseq) {
   out += name; out += '\t';
   out += std::to_string(p.flag); out += '\t';
   out += ct.name[p.chrom]; out += '\t';
@@ -36,8 +37,8 @@ inline void sam_record_se(std::string& out, const std::string& name, const std::
 // what was aligned, `rseq` its reverse complement, `qual` the FASTQ-order
 // qualities; for mate 2 `seq` is the reverse complement of the FASTQ record.
 // strand_flag: 0 = aligned sequence lies on the forward strand, 16 = reverse.
-inline void sam_record_pe(std::string& out, bool first, const std::string& name, const std::string& seq, const std::string& rseq,
-                          const std::string& qual, const ChromTable& ct, int strand_flag, size_t chrom, uint64_t pos, int mapq,
+inline void sam_record_pe(std::string& out, bool first, std::string_view name, std::string_view seq, std::string_view rseq,
+                          std::string_view qual, const ChromTable& ct, int strand_flag, size_t chrom, uint64_t pos, int mapq,
                           const std::string& cigar, uint64_t mate_pos, long long tlen, unsigned nm) {
   const int flag = first ? (strand_flag == 0 ? 99 : 83) : (strand_flag == 0 ? 147 : 163);
   out += name; out += '\t'; out += std::to_string(flag); out += '\t'; out += ct.name[chrom]; out += '\t';

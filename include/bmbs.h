@@ -134,6 +134,9 @@ int bmbs_batch_download_verify(bmbs_batch* b, int32_t* end_site, uint32_t* err, 
 /* measured peak of the integer ALU pipe on `dev` (LOP3 + IADD3, no dependencies between chains), 32-bit ops/s:
  * the roofline kernel 3 is reported against (SURVEY.md §8d asks for it to be measured, not assumed) */
 int bmbs_ubench_int_pipe(int dev, double* ops_per_second);
+/* page-locked host memory for the caller's in/out buffers (copies from and to it are asynchronous and run at link speed) */
+void* bmbs_pinned_alloc(size_t bytes);
+void bmbs_pinned_free(void* p);
 /* number of kernels launched by the last bmbs_batch_run */
 int bmbs_batch_launches(bmbs_batch* b);
 

@@ -186,6 +186,9 @@ def main():
         return 0
 
     # ---------------------------------------------------------------- our arm
+    # libraries (NCCL's version banner) may write to stdout: keep fd 1 for the one JSON line
+    sys.stdout.flush()
+    json_fd = os.dup(1); os.dup2(2, 1)
     import torch
     import bitmapperbs_b200 as B
     from bitmapperbs_b200 import capi
@@ -348,7 +351,8 @@ def main():
                                    "wall_s": runs[-1][1]}
         else:
             out["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref/bitmapperBS unavailable"}
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(out) + "\n").encode())
     if dist:
         dist.destroy_process_group()
     return 0

@@ -429,8 +429,8 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
     pack_reads<<<(n + 15) / 16, 128, 0, s>>>(v); ++b->launches;
     CU(cudaEventRecord(b->ev[1], s));
     seed_first<<<(n + 127) / 128, 128, 0, s>>>(ix, v); ++b->launches;
-    seed_second<<<b->sm_count * 8, 128, 0, s>>>(ix, v); ++b->launches;
-    seed_rest<<<b->sm_count * 12, 128, 0, s>>>(ix, v); ++b->launches;
+    seed_second<<<(n + 127) / 128, 128, 0, s>>>(ix, v); ++b->launches;
+    seed_rest<<<(n + 127) / 128, 128, 0, s>>>(ix, v); ++b->launches;
     CU(cudaEventRecord(b->ev[2], s));
     run_scan(b, v.ncand, (u32)n, v.coff, v.totals, v.slot_cap, 2u);
     expand_tasks<<<(n + 127) / 128, 128, 0, s>>>(v); ++b->launches;

@@ -448,6 +448,7 @@ __global__ void __launch_bounds__(128) seed_first(DevIndex ix, BatchView b) {
 __global__ void __launch_bounds__(128) seed_second(DevIndex ix, BatchView b) {
   __shared__ u64 s_cnt[4];
   __shared__ unsigned char s_lut[256];
+  if (blockIdx.x * blockDim.x >= b.list_count[0]) return;     // launched with one thread per read: the hardware balances the blocks
   if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
   build_key_lut(s_lut);
   __syncthreads();
@@ -484,6 +485,7 @@ __global__ void __launch_bounds__(128) seed_second(DevIndex ix, BatchView b) {
 __global__ void __launch_bounds__(128) seed_rest(DevIndex ix, BatchView b) {
   __shared__ u64 s_cnt[4];
   __shared__ unsigned char s_lut[256];
+  if (blockIdx.x * blockDim.x >= b.list_count[1]) return;
   if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
   build_key_lut(s_lut);
   __syncthreads();
@@ -778,37 +780,59 @@ __global__ void __launch_bounds__(256) gather_work(BatchView b) {
 // plane live in shared memory as overlapping 64-bit chunks (chunk c = window bits [32c, 32c+64)), so a column's
 // Eq word is one LDS.64 + one shift; band state is one W-bit word per thread (W = 32 for k <= 15, 64 for k <= 31;
 // any width >= 2k+2 gives identical results).
+// One column of the band (Levenshtein_Cal.h:436-445).  Bit 0 of D0 (1 = the diagonal cell matched) is shifted into `dbits`,
+// newest on top, so that the diagonal error count costs one funnel shift per column and one POPC per eight columns.
+template <typename W>
+__device__ __forceinline__ void bpm_step(W eq, W& VP, W& VN, u32& dbits) {
+  W X = eq | VN;
+  const W D0 = ((VP + (X & VP)) ^ VP) | X;
+  const W HN = VP & D0, HP = VN | ~(VP | D0);
+  X = D0 >> 1;
+  VN = X & HP; VP = HN | ~(X | HP);
+  dbits = __funnelshift_r(dbits, (u32)D0, 1);
+}
+
+// Eq word of column 32*ch + t for read symbol `code`: bits [t, t + band) of the window's match plane.  cb points at the
+// thread's chunk ch of plane 0; planes are `pstride` words apart, chunks `stride` words.
+template <typename W>
+__device__ __forceinline__ W eq_word(const u64* __restrict__ cb, u32 pstride, int stride, u32 code, int t, W mask) {
+  const u64 e0 = cb[code * pstride];
+  if (sizeof(W) == 4) return (W)(e0 >> t) & mask;
+  const u32 e1hi = (u32)(cb[code * pstride + stride] >> 32);
+  const u32 lo = __funnelshift_r((u32)e0, (u32)(e0 >> 32), t), hi = __funnelshift_r((u32)(e0 >> 32), e1hi, t);
+  return (W)(((u64)hi << 32) | lo) & mask;
+}
+
 template <typename W>
 __device__ __forceinline__ void bpm_columns(const u64* __restrict__ sm, int stride, int nch2, const u32* __restrict__ rw,
                                             int L, int k, int& end_out, u32& err_out) {
   const int band = 2 * k + 1;
   const W mask = band >= (int)(8 * sizeof(W)) ? ~(W)0 : (((W)1 << band) - 1);
+  const u32 pstride = (u32)(nch2 * stride);
   W VP = 0, VN = 0;
   int err = 0;
-  const int limit = 3 * k;   // err - 2k > k can never recover (Levenshtein_Cal.h:455)
+  const int limit = 3 * k;   // err - 2k > k can never recover (Levenshtein_Cal.h:455); checked every eight columns
   bool dead = false;
-  for (int i0 = 0; i0 < L && !dead; i0 += 8) {
-    const u32 word = __ldg(rw + (i0 >> 3));
-    const int n = min(8, L - i0);
-    for (int t = 0; t < n; ++t) {
-      const int i = i0 + t;
-      int code = (word >> (4 * t)) & 0xF; code = code > 4 ? 4 : code;
-      const int ch = i >> 5, sh = i & 31;
-      const u64 e0 = sm[(code * nch2 + ch) * stride];
-      W eq;
-      if (sizeof(W) == 4) eq = (W)(e0 >> sh) & mask;
-      else {
-        const u64 e1 = sm[(code * nch2 + ch + 1) * stride];
-        eq = (W)(sh ? (e0 >> sh) | ((e1 >> 32) << (64 - sh)) : e0) & mask;
+  u32 dbits = 0;
+  for (int ch = 0; ch * 32 < L && !dead; ++ch) {
+    const u64* cb = sm + ch * stride;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int i0 = ch * 32 + g * 8;
+      if (i0 < L && !dead) {
+        const u32 word = __ldg(rw + (i0 >> 3));
+        if (i0 + 8 <= L) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bpm_step<W>(eq_word<W>(cb, pstride, stride, (word >> (4 * j)) & 0xFu, g * 8 + j, mask), VP, VN, dbits);
+          err += 8 - __popc(dbits >> 24);
+        } else {
+          const int n = L - i0;
+          for (int j = 0; j < n; ++j) bpm_step<W>(eq_word<W>(cb, pstride, stride, (word >> (4 * j)) & 0xFu, g * 8 + j, mask), VP, VN, dbits);
+          err += n - __popc(dbits >> (32 - n));
+        }
+        if (err > limit) dead = true;
       }
-      W X = eq | VN;
-      const W D0 = ((VP + (X & VP)) ^ VP) | X;
-      const W HN = VP & D0, HP = VN | ~(VP | D0);
-      X = D0 >> 1;
-      VN = X & HP; VP = HN | ~(X | HP);
-      err += (int)(~D0 & 1);
     }
-    if (err > limit) dead = true;
   }
   end_out = -1; err_out = 0xFFFFFFFFu;
   if (dead) return;

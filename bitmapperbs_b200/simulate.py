@@ -159,10 +159,11 @@ def _revcomp_rows(m):
     return _COMP[m[:, ::-1]]
 
 
-def simulate_fast(genome, starts, n, L, seed, paired=True, frag_range=(200, 480), conv=0.98, sub=0.01):
+def simulate_fast(genome, starts, n, L, seed, paired=True, frag_range=(200, 480), conv=0.98, sub=0.01, indel_reads=0.0):
     """Directional bisulfite reads as uint8 matrices.
     Returns (mate1 [n,L], mate2 [n,L] or None).  mate2 is in FASTQ orientation (reverse complement of the fragment
-    suffix); pass revcomp rows to the C ABI.  No indels (bench.py uses substitutions only, SURVEY.md §8d cfg 2)."""
+    suffix); pass revcomp rows to the C ABI.  `indel_reads` (single end only): fraction of reads that carry one
+    single-base insertion or deletion (0.001 indels per base over 150 bases ~ 0.14)."""
     rng = np.random.default_rng(seed)
     lens = np.diff(starts)
     c = rng.choice(len(lens), size=n, p=lens / lens.sum())
@@ -186,6 +187,21 @@ def simulate_fast(genome, starts, n, L, seed, paired=True, frag_range=(200, 480)
         return m
 
     m1 = damage(m1)
+    if not paired and indel_reads > 0:
+        # one indel per chosen read: deletion = skip one fragment base (the read takes the next genome base at its end),
+        # insertion = one random base pushed in (the last base falls off); both by index arithmetic on the forward read
+        pick = np.flatnonzero(rng.random(n) < indel_reads)
+        pos = rng.integers(5, L - 5, size=len(pick))
+        is_del = rng.random(len(pick)) < 0.5
+        sub_m = m1[pick]
+        ar2 = np.arange(L)[None, :]
+        src_del = np.minimum(ar2 + (ar2 >= pos[:, None]), L - 1)
+        src_ins = ar2 - (ar2 > pos[:, None])
+        src = np.where(is_del[:, None], src_del, src_ins)
+        out = np.take_along_axis(sub_m, src, axis=1)
+        ins_rows = np.flatnonzero(~is_del)
+        out[ins_rows, pos[ins_rows]] = _ACGT[rng.integers(0, 4, size=len(ins_rows))]
+        m1[pick] = out
     if not paired:
         return m1, None
     tail = damage(tail)

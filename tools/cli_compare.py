@@ -71,6 +71,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=1_000_000)
     ap.add_argument("--cache", default=os.environ.get("BMBS_BENCH_CACHE", "/tmp/bmbs_bench"))
     ap.add_argument("--out", default="")
+    ap.add_argument("--genome-scale", type=float, default=1.0, help="cfg3: fraction of the 3.1 Gbp genome")
     a = ap.parse_args()
     cache = Path(a.cache); cores = os.cpu_count() or 1
     results = []
@@ -98,9 +99,30 @@ def main():
                 r1, _ = S.simulate_reads(chroms, n_slow, 150, seed=2003, sub=0.01, indel=0.001)
                 S.write_fastq(f, r1)
             args = ["--seq", f.name]; n_reads = min(a.pairs, 200_000)
+        elif cfg == "cfg3":
+            # BASELINE.json configs[2]: 3.1 Gbp, 24 chromosomes, half of it repeat families; 10 M x 150 bp single-end reads
+            mbp = [250, 243, 198, 190, 181, 171, 159, 145, 138, 134, 135, 133, 114, 107, 102, 90, 83, 80, 59, 64, 47, 51, 156, 57]
+            scale = a.genome_scale
+            t0 = time.time()
+            d, g, st = dataset(cache, f"cfg3_s1003_x{scale:g}", [int(x * 1_000_000 * scale) for x in mbp], 1003,
+                               repeat_fraction=0.5, repeat_len=(1000, 10000), repeat_copies=(10, 10000), repeat_div=(0.01, 0.15))
+            out_extra = {"genome_bases": int(len(g)), "dataset_s": time.time() - t0}
+            f = d / f"se_{a.pairs}.fq"
+            if not f.exists():
+                with open(f, "wb") as fo:
+                    done = 0
+                    while done < a.pairs:
+                        m = min(1_000_000, a.pairs - done)
+                        m1, _ = S.simulate_fast(g, st, m, 150, 2003 + done, paired=False, indel_reads=0.14)
+                        tmp = d / ".chunk.fq"
+                        S.write_fastq_matrix(tmp, m1, f"_{done // 1_000_000}")
+                        fo.write(tmp.read_bytes()); done += m
+            args = ["--seq", f.name]; n_reads = a.pairs
         else:
             raise SystemExit(f"unknown config {cfg}")
         out = {"config": cfg, "reads": n_reads, "host_cores": cores}
+        if cfg == "cfg3":
+            out.update(out_extra)
         run([BMBS, "--search", "g.fa", *args, "-t", cores, "-o", "warm.sam"], d)        # page cache + CUDA context warm-up
         w, (load, mp) = run([BMBS, "--search", "g.fa", *args, "-t", cores, "-o", "gpu.sam", "--mapstats", "gpu.st"], d)
         out["gpu"] = {"wall_s": w, "load_s": load, "map_s": mp, "reads_per_s_map": n_reads / mp if mp else None}

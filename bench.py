@@ -330,6 +330,13 @@ def main():
     except Exception:
         pass
     gcups = counters["cells"] / (per_step["verify"] / 1000) / 1e9 if per_step["verify"] > 0 else 0.0
+    # the bound that applies to the seeding kernels: independent random 32-byte sectors per second (measured live)
+    try:
+        rs_peak = capi.random_sector_peak(dev)
+    except Exception:
+        rs_peak = None
+    seed_sectors = counters["hash_queries"] + counters["occ_lookups"] + counters["located_rows"]
+    seed_sector_rate = seed_sectors / (per_step["seed"] / 1000) if per_step["seed"] > 0 else 0.0
     out = {
         "metric": "mapped_reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -345,6 +352,8 @@ def main():
         "work_per_step": counters,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": dbytes, "kernel_ms": dms,
+                     "random_sector_peak_gbs": rs_peak * 32 / 1e9 if rs_peak else None, "seed_random_sector_gbs": seed_sector_rate * 32 / 1e9,
+                     "frac_of_random_sector_peak": seed_sector_rate / rs_peak if rs_peak else None,
                      "note": "after the deep seed table a seed is one 8-byte entry: the seed kernels are bound by dependent random sectors and instruction issue, not by bytes (DESIGN.md 7)",
                      "all_kernels": {k: {"ms": v[0], "algorithmic_bytes": v[1], "GBps": (v[1] / (v[0] / 1000) / 1e9 if v[0] > 0 else 0.0)} for k, v in kernels.items()}},
     }

@@ -34,7 +34,7 @@ _lib = None
 EXPORTS = ["bmbs_index_load", "bmbs_index_free", "bmbs_index_genome_length", "bmbs_index_device_bytes", "bmbs_last_error",
            "bmbs_params_default", "bmbs_map_batch_se", "bmbs_map_batch_pe", "bmbs_verify", "bmbs_batch_create", "bmbs_batch_free",
            "bmbs_batch_upload", "bmbs_batch_run", "bmbs_batch_download", "bmbs_batch_sync", "bmbs_batch_timings",
-           "bmbs_batch_counters", "bmbs_batch_launches", "bmbs_batch_verify", "bmbs_batch_download_verify", "bmbs_ubench_int_pipe", "bmbs_pinned_alloc", "bmbs_pinned_free"]
+           "bmbs_batch_counters", "bmbs_batch_launches", "bmbs_batch_verify", "bmbs_batch_download_verify", "bmbs_ubench_int_pipe", "bmbs_pinned_alloc", "bmbs_pinned_free", "bmbs_ubench_random_sectors"]
 
 
 def load_library():
@@ -68,6 +68,7 @@ def load_library():
     L.bmbs_batch_verify.argtypes = [vp, vp, vp, C.c_size_t, C.c_double]
     L.bmbs_batch_download_verify.argtypes = [vp, vp, vp, C.c_size_t]
     L.bmbs_ubench_int_pipe.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    L.bmbs_ubench_random_sectors.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -81,6 +82,13 @@ def int_pipe_peak(dev=0) -> float:
     """measured LOP3+IADD3 throughput of the device, 32-bit integer ops per second"""
     v = C.c_double(0)
     _check(load_library().bmbs_ubench_int_pipe(dev, C.byref(v)))
+    return v.value
+
+
+def random_sector_peak(dev=0, nbytes=8 << 30) -> float:
+    """measured rate of independent random 32-byte sector loads, sectors per second"""
+    v = C.c_double(0)
+    _check(load_library().bmbs_ubench_random_sectors(dev, nbytes, C.byref(v)))
     return v.value
 
 

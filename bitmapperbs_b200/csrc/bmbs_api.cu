@@ -447,7 +447,7 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
     int bd = 128;
     while (bd > 32 && (size_t)5 * nch2 * bd * 8 > 96 * 1024) bd >>= 1;
     const size_t smem = (size_t)5 * nch2 * bd * 8;
-    int per_sm = (int)((200 * 1024) / (smem + 1024)); if (per_sm > 12) per_sm = 12; if (per_sm < 1) per_sm = 1;
+    int per_sm = (int)((226 * 1024) / (smem + 1024)); if (per_sm > 12) per_sm = 12; if (per_sm < 1) per_sm = 1;
     run_scan(b, v.nv, (u32)n, v.voff, v.totals + 1, v.slot_cap, 4u);
     gather_work<<<b->sm_count * 8, 256, 0, s>>>(v); ++b->launches;
     verify_windows<<<b->sm_count * per_sm, bd, smem, s>>>(ix, v, nch2); ++b->launches;
@@ -629,7 +629,7 @@ extern "C" int bmbs_batch_verify(bmbs_batch* b, const uint32_t* read_idx, const 
   int bd = 128;
   while (bd > 32 && (size_t)5 * nch2 * bd * 8 > 96 * 1024) bd >>= 1;
   const size_t smem = (size_t)5 * nch2 * bd * 8;
-  int per_sm = (int)((200 * 1024) / (smem + 1024)); if (per_sm > 12) per_sm = 12; if (per_sm < 1) per_sm = 1;
+  int per_sm = (int)((226 * 1024) / (smem + 1024)); if (per_sm > 12) per_sm = 12; if (per_sm < 1) per_sm = 1;
   verify_windows<<<b->sm_count * per_sm, bd, smem, s>>>(b->copy->view, v, nch2); ++b->launches;
   CU(cudaEventRecord(b->ev[6], s)); CU(cudaEventRecord(b->ev[7], s)); CU(cudaEventRecord(b->ev[8], s));
   CU(cudaMemcpyAsync(b->h_small + 4, v.counters, 8 * 8, cudaMemcpyDeviceToHost, s));
@@ -708,5 +708,52 @@ extern "C" int bmbs_ubench_int_pipe(int dev, double* ops_per_second) {
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
   *ops_per_second = best;
+  return BMBS_OK;
+}
+
+// ================================================================================================ random-sector peak
+// What bounds the seeding kernels is not streaming bandwidth but how many independent 32-byte sectors HBM delivers per
+// second at random addresses (table entries, occ blocks, suffix-array entries).  This measures that rate: every thread
+// keeps 8 independent 256-bit loads in flight at hashed addresses over `bytes` of device memory.
+namespace {
+__global__ void __launch_bounds__(256) random_sector_ubench(const ulonglong4* __restrict__ buf, u64 n_sectors, int iters, u64* sink) {
+  u64 x = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+  u64 acc = 0;
+  for (int it = 0; it < iters; ++it) {
+    u64 a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; a[i] = x % n_sectors; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      u64 v0, v1, v2, v3;
+      asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v0), "=l"(v1), "=l"(v2), "=l"(v3) : "l"(buf + a[i]));
+      acc += v0 ^ v3;
+    }
+  }
+  if (acc == 0x1234567ull) *sink = acc;
+}
+}  // namespace
+
+extern "C" int bmbs_ubench_random_sectors(int dev, size_t bytes, double* sectors_per_second) {
+  if (!sectors_per_second || bytes < (1u << 20)) return fail(BMBS_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(dev));
+  cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, dev));
+  void* d = nullptr; CU(cudaMalloc(&d, bytes + 64)); CU(cudaMemset(d, 1, bytes));
+  u64* sink = (u64*)d;
+  cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  const int blocks = prop.multiProcessorCount * 8, iters = 64;
+  const u64 n_sectors = bytes / 32;
+  random_sector_ubench<<<blocks, 256>>>((const ulonglong4*)d, n_sectors, 4, sink);
+  double best = 0;
+  for (int rep = 0; rep < 3; ++rep) {
+    CU(cudaEventRecord(e0));
+    random_sector_ubench<<<blocks, 256>>>((const ulonglong4*)d, n_sectors, iters, sink);
+    CU(cudaEventRecord(e1)); CU(cudaEventSynchronize(e1));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double rate = (double)blocks * 256 * iters * 8 / (ms / 1000.0);
+    if (rate > best) best = rate;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  *sectors_per_second = best;
   return BMBS_OK;
 }

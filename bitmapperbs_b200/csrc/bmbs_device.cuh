@@ -72,14 +72,25 @@ __device__ __forceinline__ u64 adjust_row(const DevIndex& ix, u64 row) { return 
 
 // one backward-extension step on [sp, ep): find_occ_fm_index_combine, bwt.h:1473-1596.
 // Returns the number of distinct occ blocks touched (1 or 2) for the work counters.
+// Both ends extend by the same symbol; when they fall into the same 64-row block (the usual case once an interval is
+// narrow) the second end is the first plus the symbol's count between them: one load, one plane select, two POPCs.
 __device__ __forceinline__ int lf_pair(const DevIndex& ix, u64& sp, u64& ep, int c) {
   const u64 a = adjust_row(ix, sp), b = adjust_row(ix, ep);
-  // both ends are issued together (two independent 256-bit loads in flight); when they share a block the second
-  // load hits the same sector
-  const OccBlock ba = load_occ(ix, a), bb = load_occ(ix, b);
-  sp = rank_in(ix, ba, a, c);
-  ep = rank_in(ix, bb, b, c);
-  return ba.blk == bb.blk ? 1 : 2;
+  const OccBlock ba = load_occ(ix, a);
+  if ((b >> 6) != ba.blk) {
+    const OccBlock bb = load_occ(ix, b);
+    sp = rank_in(ix, ba, a, c);
+    ep = rank_in(ix, bb, b, c);
+    return 2;
+  }
+  const unsigned pa = (unsigned)a & 63u, pb = (unsigned)b & 63u;
+  const u64 plane = c == 1 ? ba.planes.x : c == 2 ? ba.planes.y : ~(ba.planes.x | ba.planes.y);
+  const u64 base = c == 1 ? ba.cnt.x : c == 2 ? ba.cnt.y : (ba.blk << 6) - ba.cnt.x - ba.cnt.y;
+  const u64 top = ix.C[c] + base + (u64)(pa ? __popcll(plane >> (64 - pa)) : 0);
+  u64 between = 0;
+  if (pb > pa) between = (u64)__popcll((plane << pa) >> (64 - (pb - pa)));    // rows a .. b-1, row i at bit 63-i
+  sp = top; ep = top + between;
+  return 1;
 }
 
 __device__ __forceinline__ void hash_query(const DevIndex& ix, u64 key, u64& sp, u64& ep) {

@@ -137,6 +137,9 @@ int bmbs_ubench_int_pipe(int dev, double* ops_per_second);
 /* page-locked host memory for the caller's in/out buffers (copies from and to it are asynchronous and run at link speed) */
 void* bmbs_pinned_alloc(size_t bytes);
 void bmbs_pinned_free(void* p);
+/* measured rate of independent 32-byte sector loads at random addresses over `bytes` of device memory, sectors/s: the
+ * bound of the seeding kernels, whose work is one table entry / occ block / suffix-array entry per dependent step */
+int bmbs_ubench_random_sectors(int dev, size_t bytes, double* sectors_per_second);
 /* number of kernels launched by the last bmbs_batch_run */
 int bmbs_batch_launches(bmbs_batch* b);
 

@@ -102,6 +102,61 @@ def test_sensitive_pairing_records_match_oracle(golden, gidx, oidx, name):
         assert reseeded.sum() > 100 and (ores["n_cand"][reseeded == 1] > 0).sum() > 3   # the re-seeding round is exercised and finds hits
 
 
+@pytest.mark.parametrize("e_rate,seed_len,min_ins,max_ins", [(0.04, 20, 0, 500), (0.12, 40, 100, 1000), (0.2, 30, 0, 300)])
+def test_non_default_parameters_match_oracle(golden, gidx, oidx, e_rate, seed_len, min_ins, max_ins):
+    """-e / --seed / --min / --max other than the defaults, single end, pairs and sensitive pairs"""
+    se = [r[1] for r in read_fastq(golden / "se100.fq")][:1500] + [r[1] for r in read_fastq(golden / "se250.fq")][:300]
+    prm = capi.default_params(e_rate=e_rate, seed_len=seed_len, min_ins=min_ins, max_ins=max_ins)
+    gres, gcand = gidx.map_batch_se(se, params=prm)
+    ores, ocand = oidx.map_se(se, e_rate=e_rate, seed_len=seed_len)
+    assert_same_records(gres, gcand, ores, ocand)
+    m1 = read_fastq(golden / "pe100h_1.fq")[:1200]; m2 = read_fastq(golden / "pe100h_2.fq")[:1200]
+    mates = []
+    for a, b in zip(m1, m2):
+        mates += [a[1], revcomp(b[1])]
+    gres, gcand = gidx.map_batch_pe(mates, params=prm)
+    ores, ocand = oidx.map_pe(mates, e_rate=e_rate, seed_len=seed_len, min_ins=min_ins, max_ins=max_ins)
+    v = np.repeat(gres["state"] == B.VERIFY, gres["n_cand"])
+    assert_same_records(gres, gcand, ores, ocand, compare_vote=False)
+    assert np.array_equal(gcand["vote"][v], ocand["vote"][v])
+    prm.sensitive = 1
+    gres, gcand = gidx.map_batch_pe(mates, params=prm)
+    ores, ocand, _ = oidx.map_pe_sensitive(mates, e_rate=e_rate, seed_len=seed_len, min_ins=min_ins, max_ins=max_ins)
+    for f in ("state", "n_cand", "is_multiple_map"):
+        assert np.array_equal(gres[f], ores[f]), f
+    gs, os_ = _slices(gres, gcand), _slices(ores, ocand)
+    for f in ("site", "end_site", "err"):
+        assert np.array_equal(gs[f], os_[f]), f
+
+
+def test_mixed_lengths_and_unequal_mates(golden, gidx, oidx):
+    """reads of many lengths in one batch (ragged input); mates of different lengths in a pair"""
+    rng = np.random.default_rng(11)
+    se = []
+    for r in read_fastq(golden / "se250.fq")[:400]:
+        se.append(r[1][: int(rng.integers(18, 251))])
+    se += [r[1][: int(rng.integers(30, 101))] for r in read_fastq(golden / "se100.fq")[:800]]
+    gres, gcand = gidx.map_batch_se(se)
+    ores, ocand = oidx.map_se(se)
+    assert_same_records(gres, gcand, ores, ocand)
+    m1 = read_fastq(golden / "pe150_1.fq")[:800]; m2 = read_fastq(golden / "pe150_2.fq")[:800]
+    mates = []
+    for a, b in zip(m1, m2):
+        la, lb = int(rng.integers(40, 151)), int(rng.integers(40, 151))
+        mates += [a[1][:la], revcomp(b[1][:lb])]
+    for sens in (0, 1):
+        gres, gcand = gidx.map_batch_pe(mates, params=capi.default_params(sensitive=sens))
+        if sens:
+            ores, ocand, _ = oidx.map_pe_sensitive(mates)
+        else:
+            ores, ocand = oidx.map_pe(mates)
+        for f in ("state", "n_cand", "is_multiple_map"):
+            assert np.array_equal(gres[f], ores[f]), (sens, f)
+        gs, os_ = _slices(gres, gcand), _slices(ores, ocand)
+        for f in ("site", "end_site", "err"):
+            assert np.array_equal(gs[f], os_[f]), (sens, f)
+
+
 def test_edge_case_reads(golden, gidx, oidx):
     genome = b"".join(l.strip() for l in open(golden / "genome.fa", "rb") if not l.startswith(b">"))
     N = len(genome)
@@ -215,7 +270,10 @@ def test_live_reference_binary_agrees_on_fresh_data(built, tmp_path):
     for tag, args in (("se", ["--seq", "r.fq"]), ("pe", ["--seq1", "a.fq", "--seq2", "b.fq", "--pe"]),
                       ("pes", ["--seq1", "a.fq", "--seq2", "b.fq", "--pe", "--sensitive"]),
                       ("hard", ["--seq1", "c.fq", "--seq2", "d.fq", "--pe"]),
-                      ("hards", ["--seq1", "c.fq", "--seq2", "d.fq", "--pe", "--sensitive"])):
+                      ("hards", ["--seq1", "c.fq", "--seq2", "d.fq", "--pe", "--sensitive"]),
+                      ("se_e", ["--seq", "r.fq", "-e", "0.12", "--seed", "25"]),
+                      ("hard_flags", ["--seq1", "c.fq", "--seq2", "d.fq", "--pe", "-e", "0.05", "--seed", "25", "--min", "50", "--max", "600"]),
+                      ("hards_flags", ["--seq1", "c.fq", "--seq2", "d.fq", "--pe", "--sensitive", "-e", "0.1", "--min", "100", "--max", "450"])):
         subprocess.run([str(built["ref"]), "--search", "g.fa", *args, "-t", "1", "-o", f"cpu_{tag}.sam", "--mapstats", f"cpu_{tag}.st"],
                        cwd=tmp_path, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         subprocess.run([str(built["bmbs"]), "--search", "g.fa", *args, "-t", "4", "-o", f"gpu_{tag}.sam", "--mapstats", f"gpu_{tag}.st"],

@@ -6,8 +6,10 @@ the GPU mapper (bitmapperbs_b200/_build/bmbs) on the same FASTQ files and index,
   cfg1   10 Mbp genome, 100 k x 100 bp single-end reads                       (BASELINE.json configs[0])
   cfg2   100 Mbp genome, 1 M x 2 x 150 bp pairs, --pe                         (configs[1])
   cfg2s  same pairs, --pe --sensitive
-  cfg3r  reduced stand-in for configs[2]: 100 Mbp genome with 50 % repeat families, 1 M x 150 bp single-end reads with
-         1 % substitutions and 0.1 % indels (the 3.1 Gbp index itself is out of reach of the CPU index writer in a bench run)
+  cfg3r  reduced stand-in for configs[2]: 100 Mbp genome with 50 % repeat families, 200 k x 150 bp single-end reads with
+         1 % substitutions and 0.1 % indels
+  cfg3   configs[2] itself: 3.1 Gbp genome (24 chromosomes, half repeat families), 10 M x 150 bp single-end reads (--pairs)
+  cfg4   configs[3]: the same genome, 10 M x 2 x 150 bp pairs, --pe --sensitive (cfg4f: --pe fast)
 
   python tools/cli_compare.py [cfg1 cfg2 cfg2s cfg3r] [--pairs N] [--out profiles/rNN_cli_compare.json]
 """
@@ -99,6 +101,26 @@ def main():
                 r1, _ = S.simulate_reads(chroms, n_slow, 150, seed=2003, sub=0.01, indel=0.001)
                 S.write_fastq(f, r1)
             args = ["--seq", f.name]; n_reads = min(a.pairs, 200_000)
+        elif cfg in ("cfg4", "cfg4f"):
+            # BASELINE.json configs[3]: the 3.1 Gbp genome of cfg3, 10 M x 2 x 150 bp pairs, --pe --sensitive (cfg4f: --pe fast)
+            mbp = [250, 243, 198, 190, 181, 171, 159, 145, 138, 134, 135, 133, 114, 107, 102, 90, 83, 80, 59, 64, 47, 51, 156, 57]
+            scale = a.genome_scale
+            t0 = time.time()
+            d, g, st = dataset(cache, f"cfg3_s1003_x{scale:g}", [int(x * 1_000_000 * scale) for x in mbp], 1003,
+                               repeat_fraction=0.5, repeat_len=(1000, 10000), repeat_copies=(10, 10000), repeat_div=(0.01, 0.15))
+            out_extra = {"genome_bases": int(len(g)), "dataset_s": time.time() - t0}
+            fa, fb = d / f"pe_{a.pairs}_1.fq", d / f"pe_{a.pairs}_2.fq"
+            if not fa.exists():
+                with open(fa, "wb") as f1, open(fb, "wb") as f2:
+                    done = 0
+                    while done < a.pairs:
+                        m = min(1_000_000, a.pairs - done)
+                        m1, m2 = S.simulate_fast(g, st, m, 150, 2004 + done)
+                        t1, t2 = d / ".chunk1.fq", d / ".chunk2.fq"
+                        S.write_fastq_matrix(t1, m1, f"_{done // 1_000_000}/1"); S.write_fastq_matrix(t2, m2, f"_{done // 1_000_000}/2")
+                        f1.write(t1.read_bytes()); f2.write(t2.read_bytes()); done += m
+            args = ["--seq1", fa.name, "--seq2", fb.name, "--pe"] + (["--sensitive"] if cfg == "cfg4" else [])
+            n_reads = 2 * a.pairs
         elif cfg == "cfg3":
             # BASELINE.json configs[2]: 3.1 Gbp, 24 chromosomes, half of it repeat families; 10 M x 150 bp single-end reads
             mbp = [250, 243, 198, 190, 181, 171, 159, 145, 138, 134, 135, 133, 114, 107, 102, 90, 83, 80, 59, 64, 47, 51, 156, 57]
@@ -121,9 +143,10 @@ def main():
         else:
             raise SystemExit(f"unknown config {cfg}")
         out = {"config": cfg, "reads": n_reads, "host_cores": cores}
-        if cfg == "cfg3":
+        if cfg in ("cfg3", "cfg4", "cfg4f"):
             out.update(out_extra)
-        run([BMBS, "--search", "g.fa", *args, "-t", cores, "-o", "warm.sam"], d)        # page cache + CUDA context warm-up
+        if n_reads <= 4_000_000:
+            run([BMBS, "--search", "g.fa", *args, "-t", cores, "-o", "warm.sam"], d)    # page cache + CUDA context warm-up
         w, (load, mp) = run([BMBS, "--search", "g.fa", *args, "-t", cores, "-o", "gpu.sam", "--mapstats", "gpu.st"], d)
         out["gpu"] = {"wall_s": w, "load_s": load, "map_s": mp, "reads_per_s_map": n_reads / mp if mp else None}
         if REF.exists():

@@ -1,0 +1,32 @@
+#!/usr/bin/env bash
+# One gpurun call's worth of evidence: GPU parity tests, the bench line, the ncu launch list of the same command and
+# one `ncu --set full` capture of the main kernels.  Everything lands in gpurun_out/ (copied into profiles/ by hand).
+#   gpurun --timeout 1700 -- 'bash tools/gpu_round.sh [tag] [what...]'      what: tests bench launches full verify
+set -u
+TAG=${1:-run}; shift || true
+WHAT=${*:-tests bench launches full}
+O=gpurun_out; mkdir -p $O
+KERNELS='regex:^(pack_reads|seed_first|seed_second|seed_rest|expand_tasks|locate_rows|votes_classify|votes_sort|filter_pairs_kernel|gather_work|verify_windows)'
+for w in $WHAT; do
+  case $w in
+    tests)
+      timeout 900 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest.log 2>&1; echo "pytest exit $?" | tee -a $O/${TAG}_pytest.log; tail -3 $O/${TAG}_pytest.log ;;
+    bench)
+      timeout 600 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.log; echo "bench exit $?"; cat $O/${TAG}_bench.json ;;
+    refarm)
+      timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_bench_reference.json 2>> $O/${TAG}_bench.log; cat $O/${TAG}_bench_reference.json ;;
+    launches)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv \
+        python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_launches_bench.log 2>&1; echo "launch list exit $?" ;;
+    full)
+      timeout 900 ncu --set full --clock-control none --import-source on -k "$KERNELS" --launch-skip 36 --launch-count 12 -f -o $O/${TAG}_full \
+        python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_full_bench.log 2>&1; echo "ncu full exit $?" ;;
+    verify)
+      timeout 900 python tools/bench_verify.py > $O/${TAG}_verify.json 2> $O/${TAG}_verify.log; echo "bench_verify exit $?"; tail -c 1500 $O/${TAG}_verify.json ;;
+    scale2)
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 \
+        > $O/${TAG}_scale2.json 2> $O/${TAG}_scale2.log; cat $O/${TAG}_scale2.json ;;
+  esac
+done
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/${TAG}_smi.txt 2>&1
+ls -la $O | tail -20

@@ -319,7 +319,7 @@ def main():
     # sampled suffix array: 80 B per LF step + 44 B per row; dense suffix array (default): one 4-byte entry per row
     loc_bytes = counters["locate_lf_steps"] * 80 + counters["located_rows"] * (44 if counters["locate_lf_steps"] else 4)
     ver_bytes = counters["window_bytes"]
-    kernels = {"seed_first+second+rest": (per_step["seed"], seed_bytes), "locate_rows": (per_step["locate"], loc_bytes), "verify_windows": (per_step["verify"], ver_bytes)}
+    kernels = {"seed_first+second+rest": (per_step["seed"], seed_bytes), "expand_locate": (per_step["locate"], loc_bytes), "verify_windows": (per_step["verify"], ver_bytes)}
     dom = max(kernels, key=lambda k: kernels[k][0])
     dms, dbytes = kernels[dom]
     achieved = dbytes / (dms / 1000) / 1e9 if dms > 0 else 0.0

@@ -433,8 +433,7 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
     seed_rest<<<(n + 127) / 128, 128, 0, s>>>(ix, v); ++b->launches;
     CU(cudaEventRecord(b->ev[2], s));
     run_scan(b, v.ncand, (u32)n, v.coff, v.totals, v.slot_cap, 2u);
-    expand_tasks<<<(n + 127) / 128, 128, 0, s>>>(v); ++b->launches;
-    locate_rows<<<b->sm_count * 8, 256, 0, s>>>(ix, v); ++b->launches;
+    expand_locate<<<(n + 127) / 128, 128, 0, s>>>(ix, v); ++b->launches;
     CU(cudaEventRecord(b->ev[3], s));
     votes_classify<<<(n + 255) / 256, 256, 0, s>>>(v); ++b->launches;
     votes_sort<16><<<b->sm_count * 16, 128, 0, s>>>(v); ++b->launches;
@@ -459,8 +458,7 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
       BatchView w = v; w.round = 1;
       seed_reseed<<<b->sm_count * 8, 128, 0, s>>>(ix, w); ++b->launches;
       run_scan(b, w.ncand, (u32)n, w.coff, w.totals, w.slot_cap, 2u);
-      expand_tasks<<<(n + 127) / 128, 128, 0, s>>>(w); ++b->launches;
-      locate_rows<<<b->sm_count * 8, 256, 0, s>>>(ix, w); ++b->launches;
+      expand_locate<<<(n + 127) / 128, 128, 0, s>>>(ix, w); ++b->launches;
       votes_classify<<<(n + 255) / 256, 256, 0, s>>>(w); ++b->launches;
       votes_sort<16><<<b->sm_count * 16, 128, 0, s>>>(w); ++b->launches;
       votes_sort<32><<<b->sm_count * 4, 128, 0, s>>>(w); ++b->launches;

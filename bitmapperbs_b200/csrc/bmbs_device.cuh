@@ -59,13 +59,16 @@ __device__ __forceinline__ OccBlock load_occ(const DevIndex& ix, u64 adj_row) {
   return b;
 }
 
+// C[c] by selects: a run-time index into the by-value kernel parameter would make the compiler copy the whole struct to local memory
+__device__ __forceinline__ u64 first_row_of(const DevIndex& ix, int c) { return c == 0 ? ix.C[0] : c == 1 ? ix.C[1] : ix.C[2]; }
+
 // C[c] + occ(c, row) for a row already adjusted for the '$' row.  bwt.h:1373-1465.
 __device__ __forceinline__ u64 rank_in(const DevIndex& ix, const OccBlock& b, u64 adj_row, int c) {
   const unsigned part = (unsigned)adj_row & 63u;
   const u64 plane = c == 1 ? b.planes.x : c == 2 ? b.planes.y : ~(b.planes.x | b.planes.y);
   const u64 base = c == 1 ? b.cnt.x : c == 2 ? b.cnt.y : (b.blk << 6) - b.cnt.x - b.cnt.y;
   const u64 head = part ? plane >> (64 - part) : 0ull;
-  return ix.C[c] + base + (u64)__popcll(head);
+  return first_row_of(ix, c) + base + (u64)__popcll(head);
 }
 
 __device__ __forceinline__ u64 adjust_row(const DevIndex& ix, u64 row) { return row > ix.shapline ? row - 1 : row; }
@@ -86,7 +89,7 @@ __device__ __forceinline__ int lf_pair(const DevIndex& ix, u64& sp, u64& ep, int
   const unsigned pa = (unsigned)a & 63u, pb = (unsigned)b & 63u;
   const u64 plane = c == 1 ? ba.planes.x : c == 2 ? ba.planes.y : ~(ba.planes.x | ba.planes.y);
   const u64 base = c == 1 ? ba.cnt.x : c == 2 ? ba.cnt.y : (ba.blk << 6) - ba.cnt.x - ba.cnt.y;
-  const u64 top = ix.C[c] + base + (u64)(pa ? __popcll(plane >> (64 - pa)) : 0);
+  const u64 top = first_row_of(ix, c) + base + (u64)(pa ? __popcll(plane >> (64 - pa)) : 0);
   u64 between = 0;
   if (pb > pa) between = (u64)__popcll((plane << pa) >> (64 - (pb - pa)));    // rows a .. b-1, row i at bit 63-i
   sp = top; ep = top + between;

@@ -3,8 +3,7 @@
 //   pack_reads      ASCII -> nibble codes, first-C position, error threshold k
 //   seed_reads      kernel 1a: per-read seeding state machine (FM backward search with the 16-mer table,
 //                   unique-hit shortcut with direct genome compare, one-mismatch second seed, remaining seeds)
-//   expand_tasks    seed intervals -> one locate work item per row
-//   locate_rows     kernel 1b: LF-walk every row to a sampled suffix, -> candidate site
+//   expand_locate   kernel 1b: seed intervals -> one candidate site per row (dense suffix array gather, or LF-walk to a sampled row)
 //   votes_small/big kernel 2: per-read sort, run-length votes with the site-k shift
 //   filter_pairs    kernel 2b (paired end): distance pre-filter of the two mates' lists
 //   gather_work     compaction of the surviving windows into the verification work list
@@ -519,28 +518,67 @@ __global__ void __launch_bounds__(128) seed_rest(DevIndex ix, BatchView b) {
 }
 
 // ------------------------------------------------------------------------------------------- expand + locate
-__global__ void expand_tasks(BatchView b) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= b.n_reads || *b.status) return;
-  u32 s = b.coff[r];
-  const u32 nt = b.ntask[r];
-  for (u32 t = 0; t < nt; ++t) {
-    const SeedTask k = b.tasks[(size_t)t * b.n_reads + r];
-    if (k.hits == 0) { b.cand[s] = k.sp; b.slot_adj[s] = 0xFFFFFFFFu; b.slot_read[s] = r; ++s; }     // already a site
-    else for (u32 j = 0; j < k.hits; ++j, ++s) { b.slot_row[s] = k.sp + j; b.slot_adj[s] = (u32)k.mlen + (u32)k.off; b.slot_read[s] = r; }
-  }
-}
+// Seed tasks -> candidate sites, one kernel.  A warp owns 32 consecutive reads, i.e. one contiguous range of candidate
+// slots [coff[r0], coff[r0+32]).  Its lanes first lay the reads' tasks out as a table of segments {first slot, first row or
+// literal site, seed length + offset, owner} in shared memory (in slot order), then walk the slot range with consecutive
+// lanes on consecutive slots: a binary search over the segment starts finds a slot's task, the row is located (one gather
+// from the dense suffix array) and turned into a site, and cand[] / slot_read[] are written coalesced.
+//   site = 2N - SA - seed_len - seed_off, modulo 2^64 (reverse_and_adjust_site, Schema.cpp:4657-4683)
+constexpr int SEG_CAP = 256;                      // segments per warp and pass; a read has at most MAX_TASKS = 28
+struct Seg { u64 sp; u32 start; u32 info; };      // info: seed_len + seed_off | owner lane << 16 | literal site << 31
 
-// site = 2N - SA - seed_len - seed_off, modulo 2^64 (reverse_and_adjust_site, Schema.cpp:4657-4683)
-__global__ void __launch_bounds__(256) locate_rows(DevIndex ix, BatchView b) {
+__global__ void __launch_bounds__(128) expand_locate(DevIndex ix, BatchView b) {
+  __shared__ Seg s_seg[4][SEG_CAP];
   __shared__ u64 s_cnt[2];
   if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
   __syncthreads();
-  const u32 total = *b.status ? 0u : (u32)b.totals[0];
+  const int lane = threadIdx.x & 31;
+  Seg* seg = s_seg[threadIdx.x >> 5];
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool ok = !*b.status, live = ok && r < b.n_reads;
+  const u32 nt = live ? b.ntask[r] : 0u;
+  // lanes past the last read own the empty range at the end, so that a pass's slot range is [c0 of its first lane, c1 of its last)
+  const u32 c0 = ok ? b.coff[min(r, b.n_reads)] : 0u, c1 = ok ? b.coff[min(r + 1, b.n_reads)] : 0u;
+  u32 incl = nt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  const u32 excl = incl - nt;
   u64 steps = 0, rows = 0;
-  for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
-    const u32 adj = b.slot_adj[s];
-    if (adj != 0xFFFFFFFFu) { int st; const u64 sa = locate_row(ix, b.slot_row[s], st); b.cand[s] = 2 * ix.N - sa - (u64)adj; ++rows; steps += st; }
+  int lo_lane = 0;
+  while (lo_lane < 32) {
+    // lanes [lo_lane, hi_lane) whose tasks fit into the table together (incl is monotonic, so they are contiguous)
+    const u32 base = __shfl_sync(0xffffffffu, excl, lo_lane);
+    const bool fits = lane >= lo_lane && incl - base <= (u32)SEG_CAP;
+    const int hi_lane = lo_lane + __popc(__ballot_sync(0xffffffffu, fits));
+    if (fits) {
+      u32 s = c0;
+      for (u32 t = 0; t < nt; ++t) {
+        const SeedTask k = b.tasks[(size_t)t * b.n_reads + r];
+        Seg g; g.sp = k.sp; g.start = s;
+        g.info = (k.hits ? (u32)k.mlen + (u32)k.off : 0x80000000u) | ((u32)lane << 16);
+        seg[excl - base + t] = g;
+        s += k.hits ? k.hits : 1u;
+      }
+    }
+    __syncwarp();
+    const u32 n_seg = __shfl_sync(0xffffffffu, incl, hi_lane - 1) - base;
+    const u32 s_begin = __shfl_sync(0xffffffffu, c0, lo_lane), s_end = __shfl_sync(0xffffffffu, c1, hi_lane - 1);
+    if (n_seg) {
+      for (u32 s = s_begin + lane; s < s_end; s += 32) {
+        u32 lo = 0, hi = n_seg;                              // seg[lo].start <= s < seg[hi].start
+        while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (seg[mid].start <= s) lo = mid; else hi = mid; }
+        const Seg g = seg[lo];
+        u64 site = g.sp;
+        if (!(g.info >> 31)) {
+          int st; const u64 sa = locate_row(ix, g.sp + (u64)(s - g.start), st);
+          site = 2 * ix.N - sa - (u64)(g.info & 0xFFFFu); ++rows; steps += st;
+        }
+        b.cand[s] = site;
+        b.slot_read[s] = (u32)(r - lane) + ((g.info >> 16) & 31u);
+      }
+    }
+    __syncwarp();
+    lo_lane = hi_lane;
   }
   atomicAdd(&s_cnt[0], rows); atomicAdd(&s_cnt[1], steps);
   __syncthreads();

@@ -6,7 +6,7 @@ set -u
 TAG=${1:-run}; shift || true
 WHAT=${*:-tests bench launches full}
 O=gpurun_out; mkdir -p $O
-KERNELS='regex:^(pack_reads|seed_first|seed_second|seed_rest|expand_tasks|locate_rows|votes_classify|votes_sort|filter_pairs_kernel|gather_work|verify_windows)'
+KERNELS='regex:^(pack_reads|seed_first|seed_second|seed_rest|expand_locate|votes_classify|votes_sort|filter_pairs_kernel|gather_work|verify_windows)'
 for w in $WHAT; do
   case $w in
     tests)

@@ -79,42 +79,66 @@ def make_reads(d: Path, pairs: int, seed: int):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons every 5 ms from a thread (NVML); `nvidia-smi -lms` as the fallback."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu):
-        self.rows = []; self.p = None; self.gpu = gpu
+        self.rows = []; self.p = None; self.gpu = gpu; self.run = False; self.max_mhz = None; self.src = None
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            import pynvml as N
+            N.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.gpu
+            h = N.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            reasons_fn = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM); reasons_fn(h)
+            self.run = True; self.src = "nvml"
+
+            def loop():
+                while self.run:
+                    try:
+                        mhz = float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)); r = int(reasons_fn(h))
+                        self.rows.append((time.time(), mhz, [k for k, b in bits.items() if r & b]))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+            threading.Thread(target=loop, daemon=True).start()
+            return
+        except Exception:
+            self.run = False
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.src = "nvidia-smi"
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.p = None
 
     def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.p.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t0=0.0, t1=1e30):
-        """samples taken inside [t0, t1] (the timed region); if the region was shorter than the sampling period,
-        every sample since start() -- the sampler is started before the warm-up, so those are under load too"""
-        if self.p:
-            self.p.terminate()
-        inside = [r for t, r in self.rows if t0 <= t <= t1]
-        rows = inside if len(inside) >= 2 else [r for _, r in self.rows]
-        sm, mx, reasons = [], 0, set()
-        for r in rows:
-            f = [x.strip() for x in r.split(",")]
+            f = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+                self.max_mhz = max(self.max_mhz or 0.0, float(f[1]))
+                self.rows.append((time.time(), float(f[0]), [n for n, v in zip(names, f[2:6]) if v.lower().startswith("active")]))
             except Exception:
                 continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm),
-                "window": "timed region" if len(inside) >= 2 else "warm-up + timed region"}
+
+    def stop(self, t0=0.0, t1=1e30):
+        """samples taken inside [t0, t1] (the timed region); if the region was shorter than a few sampling periods,
+        every sample since start() -- the sampler is started before the warm-up, so those are under load too"""
+        self.run = False
+        if self.p:
+            self.p.terminate()
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        rows = inside if len(inside) >= 3 else self.rows
+        sm = [r[1] for r in rows]; reasons = sorted({x for r in rows for x in r[2]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm), "source": self.src,
+                "window": "timed region" if len(inside) >= 3 else "warm-up + timed region"}
 
 
 # ------------------------------------------------------------------------------------------------ reference CPU arm
@@ -144,7 +168,7 @@ def run_reference(d: Path, m1, m2, sample_pairs: int, threads: int, repeats: int
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU per step")

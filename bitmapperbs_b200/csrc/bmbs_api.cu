@@ -365,7 +365,7 @@ extern "C" int bmbs_batch_create(bmbs_index* idx, int dev, size_t max_reads, siz
   A(dalloc(b, &v.ntask, R)); A(dalloc(b, &v.ncand, R)); A(dalloc(b, &v.coff, R)); A(dalloc(b, &v.tasks, (size_t)MAX_TASKS * max_reads));
   A(dalloc(b, &v.slot_row, S)); A(dalloc(b, &v.slot_adj, S)); A(dalloc(b, &v.slot_read, S)); A(dalloc(b, &v.cand, S)); A(dalloc(b, &v.vcnt, S));
   A(dalloc(b, &v.nv, R)); A(dalloc(b, &v.voff, R)); A(dalloc(b, &v.keep, S));
-  A(dalloc(b, &v.vlist, S)); A(dalloc(b, &v.work_site, S)); A(dalloc(b, &v.work_vote, S)); A(dalloc(b, &v.work_read, S)); A(dalloc(b, &v.out_cand, S));
+  A(dalloc(b, &v.vitems, S)); A(dalloc(b, &v.out_cand, S));
   A(dalloc(b, &v.out_res, R)); A(dalloc(b, &v.big_list, R)); A(dalloc(b, &v.big_count, 4)); A(dalloc(b, &v.sort16, R)); A(dalloc(b, &v.sort32, R)); A(dalloc(b, &v.sort_count, 4));
   v.scratch_cap = 2 * S + 65536;
   A(dalloc(b, &v.scratch, (size_t)v.scratch_cap)); A(dalloc(b, &v.scratch_used, 4));
@@ -594,7 +594,11 @@ namespace {
 __global__ void verify_setup(BatchView b, const u32* read_idx, const u64* sites, u32 n) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < (u32)b.n_reads) b.state[i] = BMBS_VERIFY;
-  if (i < n) { b.work_read[i] = read_idx[i]; b.work_site[i] = sites[i]; b.work_vote[i] = 0; b.vlist[i] = i; }
+  if (i < n) {
+    const u32 r = read_idx[i];
+    VerifyItem it; it.site = sites[i]; it.wi = i; it.vote = 0; it.code_off = code_word_offset(b.offsets, (int)r); it.L = b.len[r]; it.k = b.kk[r]; it.pad = 0;
+    b.vitems[i] = it;
+  }
   if (i == 0) { b.totals[1] = n; b.totals[3] = n; b.list_count[3] = n; }
 }
 __global__ void verify_unpack(const bmbs_cand* c, u32 n, int* end_site, u32* err) {
@@ -642,7 +646,7 @@ extern "C" int bmbs_batch_download_verify(bmbs_batch* b, int32_t* end_site, uint
   CU(cudaSetDevice(b->dev));
   cudaStream_t s = b->stream;
   // unpack on the device into the (now free) work arrays, then two plain copies
-  int* d_end = (int*)b->v.work_vote; u32* d_err = b->v.slot_adj;
+  int* d_end = (int*)b->v.slot_read; u32* d_err = b->v.slot_adj;
   if (n) {
     verify_unpack<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(b->v.out_cand, (u32)n, d_end, d_err);
     CU(cudaMemcpyAsync(end_site, d_end, n * 4, cudaMemcpyDeviceToHost, s));

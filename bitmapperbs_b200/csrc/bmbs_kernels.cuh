@@ -25,6 +25,11 @@ struct SeedTask { u64 sp; u32 hits; unsigned short mlen, off; };  // hits==0: `s
 // counters (device, u64[16]); indices follow bmbs_batch_counters
 enum { CNT_HASH = 0, CNT_OCC = 1, CNT_ROWS = 2, CNT_LOCATE_LF = 3, CNT_VERIFIED = 4, CNT_CELLS = 5, CNT_CAND = 6, CNT_WINBYTES = 7 };
 
+// One window for the bit-vector kernel, everything it needs in one 32-byte record (one load instead of a chain of
+// dependent gathers through the read tables): window start, slot in out_cand, votes, where the read's nibble codes start,
+// read length and error threshold.
+struct __align__(16) VerifyItem { u64 site; u32 wi, vote, code_off, L, k, pad; };
+
 struct BatchView {
   // inputs
   const char* ascii; const u64* offsets; int n_reads; int pe;
@@ -48,8 +53,7 @@ struct BatchView {
   u32* nv; u32* voff;                           // votes per read, exclusive scan
   unsigned char* keep;
   // work list
-  u64* work_site; u32* work_vote; u32* work_read; bmbs_cand* out_cand;
-  u32* vlist;                                   // dense list of the work items that need the bit-vector kernel (count: list_count[3])
+  VerifyItem* vitems; bmbs_cand* out_cand;      // dense list of the windows that need the bit-vector kernel (count: list_count[3])
   bmbs_read_result* out_res;
   u32* sort16; u32* sort32; u32* sort_count;     // reads whose candidate segment (<= 16 / <= 32 entries) has to be sorted
   u32* big_list; u32* big_count; u64* scratch; u32* scratch_used; u64 scratch_cap;
@@ -781,6 +785,7 @@ __global__ void __launch_bounds__(256) gather_work(BatchView b) {
   for (u32 it = 0; it < rounds; ++it) {
     const u32 s = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
     bool verify = false; u32 w = 0;
+    VerifyItem item;
     if (s < total) {
       const u32 r = b.slot_read[s];
       const u32 j = s - b.coff[r];
@@ -788,7 +793,8 @@ __global__ void __launch_bounds__(256) gather_work(BatchView b) {
         w = b.voff[r] + j;
         const int st = b.round == 0 ? b.state[r] : BMBS_VERIFY;
         if (st == BMBS_VERIFY || st == BMBS_NONE) {
-          b.work_site[w] = b.cand[s]; b.work_vote[w] = b.vcnt[s]; b.work_read[w] = r; verify = true;
+          item.site = b.cand[s]; item.wi = w; item.vote = b.vcnt[s]; item.code_off = code_word_offset(b.offsets, (int)r);
+          item.L = b.len[r]; item.k = b.kk[r]; item.pad = 0; verify = true;
         } else {
           bmbs_cand o; o.site = b.cand[s]; o.vote = b.vcnt[s]; o.end_site = (int16_t)(b.len[r] - 1); o.err = st == BMBS_ONE_MISMATCH ? 1 : 0;
           b.out_cand[out_base + w] = o;
@@ -806,7 +812,7 @@ __global__ void __launch_bounds__(256) gather_work(BatchView b) {
     __syncthreads();
     if (threadIdx.x == 0 && s_n) s_base = atomicAdd(b.list_count + 3, s_n);
     __syncthreads();
-    if (verify) b.vlist[s_base + wbase + __popc(bal & ((1u << lane) - 1u))] = w;
+    if (verify) b.vitems[s_base + wbase + __popc(bal & ((1u << lane) - 1u))] = item;
     __syncthreads();
   }
 }
@@ -852,13 +858,15 @@ __device__ __forceinline__ void bpm_columns(const u64* __restrict__ sm, int stri
   const int limit = 3 * k;   // err - 2k > k can never recover (Levenshtein_Cal.h:455); checked every eight columns
   bool dead = false;
   u32 dbits = 0;
+  u32 next_word = L > 0 ? __ldg(rw) : 0u;     // the read's code words are fetched one group of eight columns ahead
   for (int ch = 0; ch * 32 < L && !dead; ++ch) {
     const u64* cb = sm + ch * stride;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const int i0 = ch * 32 + g * 8;
       if (i0 < L && !dead) {
-        const u32 word = __ldg(rw + (i0 >> 3));
+        const u32 word = next_word;
+        if (i0 + 8 < L) next_word = __ldg(rw + (i0 >> 3) + 1);
         if (i0 + 8 <= L) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) bpm_step<W>(eq_word<W>(cb, pstride, stride, (word >> (4 * j)) & 0xFu, g * 8 + j, mask), VP, VN, dbits);
@@ -899,41 +907,50 @@ __global__ void verify_windows(DevIndex ix, BatchView b, int nch2) {
   u64* sm = sm_all + threadIdx.x;
   u64 cells = 0, wbytes = 0, verified = 0;
   for (u32 vi = blockIdx.x * blockDim.x + threadIdx.x; vi < total_work; vi += gridDim.x * blockDim.x) {
-    const u32 wi = b.vlist[vi];
-    const u32 r = b.work_read[wi];
-    const u64 site = b.work_site[wi];
-    const int L = (int)b.len[r], k = (int)b.kk[r];
+    const uint4* ip = (const uint4*)(b.vitems + vi);
+    const uint4 i0 = __ldg(ip), i1 = __ldg(ip + 1);
+    const u64 site = (u64)i0.x | ((u64)i0.y << 32);
+    const u32 wi = i0.z, vote = i0.w;
+    const int L = (int)i1.y, k = (int)i1.z;
     int end = -1; u32 err = 0xFFFFFFFFu;
     {
       const int plen = L + 2 * k;
       const int nch = (L + 31) >> 5;           // chunks addressed by the column loop (+1 for 64-bit bands)
       const bool inside = window_inside(ix, site, (u64)plen);
       if (inside) {
+        // window words gp[0 .. nch+2]: eight chunks per pass, their ten words loaded back to back (independent loads in
+        // flight together instead of one dependent round trip per chunk)
         const uint2* gp = ix.planes + (site >> 5);
         const unsigned sh = (unsigned)site & 31u;
-        uint2 w0 = __ldg(gp), w1 = __ldg(gp + 1);
-        u32 lo_prev = __funnelshift_r(w0.x, w1.x, sh), hi_prev = __funnelshift_r(w0.y, w1.y, sh);
-        for (int c = 0; c <= nch; ++c) {
-          const uint2 w2 = __ldg(gp + c + 2);
-          const u32 lo_next = __funnelshift_r(w1.x, w2.x, sh), hi_next = __funnelshift_r(w1.y, w2.y, sh);
-          const u64 lo = (u64)lo_prev | ((u64)lo_next << 32), hi = (u64)hi_prev | ((u64)hi_next << 32);
-          sm[(0 * nch2 + c) * stride] = ~hi & ~lo;   // A
-          sm[(1 * nch2 + c) * stride] = ~hi & lo;    // C
-          sm[(2 * nch2 + c) * stride] = hi & ~lo;    // G
-          sm[(3 * nch2 + c) * stride] = lo;          // T (matches reference C or T)
-          sm[(4 * nch2 + c) * stride] = 0;           // N / other
-          w1 = w2; lo_prev = lo_next; hi_prev = hi_next;
+        for (int c0 = 0; c0 <= nch; c0 += 8) {
+          uint2 w[10];
+#pragma unroll
+          for (int j = 0; j < 10; ++j) w[j] = c0 + j <= nch + 2 ? __ldg(gp + c0 + j) : make_uint2(0u, 0u);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            if (c <= nch) {
+              const u32 lo0 = __funnelshift_r(w[j].x, w[j + 1].x, sh), hi0 = __funnelshift_r(w[j].y, w[j + 1].y, sh);
+              const u32 lo1 = __funnelshift_r(w[j + 1].x, w[j + 2].x, sh), hi1 = __funnelshift_r(w[j + 1].y, w[j + 2].y, sh);
+              const u64 lo = (u64)lo0 | ((u64)lo1 << 32), hi = (u64)hi0 | ((u64)hi1 << 32);
+              sm[(0 * nch2 + c) * stride] = ~hi & ~lo;   // A
+              sm[(1 * nch2 + c) * stride] = ~hi & lo;    // C
+              sm[(2 * nch2 + c) * stride] = hi & ~lo;    // G
+              sm[(3 * nch2 + c) * stride] = lo;          // T (matches reference C or T)
+              sm[(4 * nch2 + c) * stride] = 0;           // N / other
+            }
+          }
         }
         wbytes += (u64)(nch + 3) * 8;
       } else {
         for (int c = 0; c <= nch; ++c) for (int p = 0; p < 5; ++p) sm[(p * nch2 + c) * stride] = 0;
       }
-      const u32* rw = b.codes + code_word_offset(b.offsets, (int)r);
+      const u32* rw = b.codes + i1.x;
       if (k <= 15) bpm_columns<u32>(sm, stride, nch2, rw, L, k, end, err);
       else bpm_columns<u64>(sm, stride, nch2, rw, L, k, end, err);
       ++verified; cells += (u64)L * (u64)(2 * k + 1);
     }
-    bmbs_cand o; o.site = site; o.vote = b.work_vote[wi]; o.end_site = (int16_t)end; o.err = err == 0xFFFFFFFFu ? (uint16_t)0xFFFF : (uint16_t)err;
+    bmbs_cand o; o.site = site; o.vote = vote; o.end_site = (int16_t)end; o.err = err == 0xFFFFFFFFu ? (uint16_t)0xFFFF : (uint16_t)err;
     b.out_cand[out_base + wi] = o;
   }
   atomicAdd(&s_cnt[0], verified); atomicAdd(&s_cnt[1], cells); atomicAdd(&s_cnt[2], wbytes);

@@ -22,6 +22,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <unistd.h>
 #include "../../../include/bmbs.h"
 #include "../../indexer/build_index.hpp"
 #include "mapper.hpp"
@@ -38,11 +39,11 @@ struct Options {
   bmbs_params prm; Scoring sc;
 };
 
-struct RawBatch { size_t seq_no = 0; size_t n_rec = 0; std::string raw1, raw2; };
+struct RawBatch { size_t seq_no = 0; size_t n_rec = 0; std::string_view raw1, raw2; std::string own1, own2; };   // views into the mapped files (own*: gzip input)
 
 struct Batch {
   size_t seq_no = 0; int n = 0;                      // n reads (SE) or mates (PE, even)
-  std::string raw1, raw2;                            // FASTQ text the views below point into (bases upper-cased in place)
+  std::string_view raw1, raw2; std::string own1, own2; // FASTQ text the views below point into (bases upper-cased in place)
   std::vector<std::string_view> name, qual, fq_seq;  // per read / mate; fq_seq: the sequence as it stands in the FASTQ record
   std::string flat; std::vector<uint64_t> offsets;   // sequences as aligned (mate 2 reverse-complemented), back to back
   std::vector<bmbs_read_result> res; std::vector<bmbs_cand> cand;
@@ -103,15 +104,27 @@ void parse(int argc, char** argv, Options& o) {
   o.prm.sensitive = (o.sensitive && o.pe) ? 1 : 0;      // --sensitive only selects the pair worker (Bitmapper_main.cpp)
 }
 
+// Bases are upper-cased in place (Process_Reads.cpp:321-472).  Lower-case letters have bit 5 set and A/C/G/T/N do not, so
+// eight bytes at a time are skipped unless one of them could be lower case; nothing is written to clean input (the
+// mapped file stays shared with the page cache).
 inline void upper_in_place(std::string_view v) {
   char* p = const_cast<char*>(v.data());
-  for (size_t i = 0; i < v.size(); ++i) { const char c = p[i]; if (c >= 'a' && c <= 'z') p[i] = (char)(c - 32); }
+  const size_t n = v.size(); size_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    unsigned long long x; memcpy(&x, p + i, 8);
+    if (!(x & 0x2020202020202020ull)) continue;
+    for (size_t j = i; j < i + 8; ++j) { const char c = p[j]; if (c >= 'a' && c <= 'z') p[j] = (char)(c - 32); }
+  }
+  for (; i < n; ++i) { const char c = p[i]; if (c >= 'a' && c <= 'z') p[i] = (char)(c - 32); }
 }
 
 // FASTQ text -> batch (names cut, bases upper-cased, mate 2 reverse-complemented for alignment): Process_Reads.cpp:62-90, :321-472
 void parse_batch(RawBatch& rb, bool pe, Batch& b) {
   b.seq_no = rb.seq_no;
-  b.raw1 = std::move(rb.raw1); b.raw2 = std::move(rb.raw2);
+  // moving a std::string keeps its heap buffer, so views into own* stay valid; short strings live inside the object: re-point
+  const bool o1 = rb.raw1.data() == rb.own1.data(), o2 = rb.raw2.data() == rb.own2.data();
+  b.own1 = std::move(rb.own1); b.own2 = std::move(rb.own2);
+  b.raw1 = o1 ? std::string_view(b.own1) : rb.raw1; b.raw2 = o2 ? std::string_view(b.own2) : rb.raw2;
   const size_t n = rb.n_rec * (pe ? 2 : 1);
   b.n = (int)n;
   b.name.resize(n); b.qual.resize(n); b.fq_seq.resize(n);
@@ -138,10 +151,8 @@ void parse_batch(RawBatch& rb, bool pe, Batch& b) {
       b.flat.append(b.fq_seq[i]); b.offsets[i + 1] = b.flat.size();
       const std::string_view s2 = b.fq_seq[k];
       const size_t at = b.flat.size(); b.flat.resize(at + s2.size());
-      for (size_t t = 0; t < s2.size(); ++t) {
-        const char c = s2[s2.size() - 1 - t];
-        b.flat[at + t] = c == 'A' ? 'T' : c == 'T' ? 'A' : c == 'C' ? 'G' : c == 'G' ? 'C' : c;
-      }
+      const char* comp = complement_table();
+      for (size_t t = 0; t < s2.size(); ++t) b.flat[at + t] = comp[(unsigned char)s2[s2.size() - 1 - t]];
       b.offsets[k + 1] = b.flat.size();
     }
   }
@@ -188,7 +199,11 @@ int search(const Options& o, const std::string& cmdline) {
   else if (!q1.open(o.seq)) die("cannot open " + o.seq);
   FILE* fo = fopen(o.out.c_str(), "w");
   if (!fo) die("cannot write " + o.out);
-  { std::string h; sam_header(h, hc.chroms, cmdline); fwrite(h.data(), 1, h.size(), fo); }
+  { std::string h; sam_header(h, hc.chroms, cmdline); fwrite(h.data(), 1, h.size(), fo); fflush(fo); }
+  // batches of SAM text go straight to the descriptor: no second copy through the stdio buffer
+  auto write_all = [&](const char* p, size_t n) {
+    while (n) { const ssize_t w = ::write(fileno(fo), p, n); if (w <= 0) die("write failed on " + o.out); p += w; n -= (size_t)w; }
+  };
 
   // splitter -> parse workers -> GPU threads (two batches in flight per device) -> finish workers -> ordered writer
   const double t1 = now();
@@ -205,8 +220,8 @@ int search(const Options& o, const std::string& cmdline) {
       const double ts = now();
       size_t n2 = 0;
       std::thread second;                              // the two files of a pair are split side by side
-      if (pe) second = std::thread([&] { n2 = q2.next(o.batch_reads, rb->raw2); });
-      rb->n_rec = q1.next(o.batch_reads, rb->raw1);
+      if (pe) second = std::thread([&] { n2 = q2.next(o.batch_reads, rb->raw2, rb->own2); });
+      rb->n_rec = q1.next(o.batch_reads, rb->raw1, rb->own1);
       if (pe) { second.join(); if (n2 < rb->n_rec) rb->n_rec = n2; }   // the shorter file ends the run, as in the reference's paired reader
       us_split += us(ts, now());
       if (rb->n_rec == 0) break;
@@ -285,7 +300,7 @@ int search(const Options& o, const std::string& cmdline) {
       while (!pending.empty() && pending.begin()->first == next) {
         Batch& x = *pending.begin()->second;
         const double ts = now();
-        fwrite(x.sam.data(), 1, x.sam.size(), fo);
+        write_all(x.sam.data(), x.sam.size());
         us_write += us(ts, now());
         total.reads += x.st.reads; total.unique += x.st.unique; total.ambiguous += x.st.ambiguous; total.bases += x.st.bases; total.err_bases += x.st.err_bases;
         pending.erase(pending.begin()); ++next;

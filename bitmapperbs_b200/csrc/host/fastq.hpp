@@ -3,7 +3,15 @@
 // the first ' ' or '/', bases are upper-cased; mate 2 of a pair is additionally
 // cut where the two names first differ.  Every record must end with '\n'.
 #pragma once
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+#include <algorithm>
 #include <cctype>
 #include <cstdio>
 #include <cstring>
@@ -42,14 +50,82 @@ class FastqReader {
   gzFile gz_ = nullptr;
 };
 
+// number of '\n' in [p, p+n): 16 bytes per step with SSE2 (part of x86-64), SWAR elsewhere
+inline size_t count_newlines(const char* p, size_t n) {
+  size_t c = 0, i = 0;
+#if defined(__SSE2__)
+  const __m128i nl = _mm_set1_epi8('\n');
+  for (; i + 64 <= n; i += 64) {
+    const unsigned m0 = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)(p + i)), nl));
+    const unsigned m1 = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)(p + i + 16)), nl));
+    const unsigned m2 = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)(p + i + 32)), nl));
+    const unsigned m3 = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)(p + i + 48)), nl));
+    c += (size_t)__builtin_popcountll((unsigned long long)m0 | ((unsigned long long)m1 << 16) | ((unsigned long long)m2 << 32) | ((unsigned long long)m3 << 48));
+  }
+#else
+  for (; i + 8 <= n; i += 8) {
+    unsigned long long x; memcpy(&x, p + i, 8); x ^= 0x0A0A0A0A0A0A0A0Aull;
+    const unsigned long long t = ~(((x & 0x7F7F7F7F7F7F7F7Full) + 0x7F7F7F7F7F7F7F7Full) | x | 0x7F7F7F7F7F7F7F7Full);
+    c += (size_t)__builtin_popcountll(t);
+  }
+#endif
+  for (; i < n; ++i) c += p[i] == '\n';
+  return c;
+}
+
 // Block reader for the mapper: hands out raw FASTQ text holding a whole number of 4-line records, so that parsing can run
-// in worker threads.  Plain and gzip input (gzread passes plain files through).
+// in worker threads.  A plain file is mapped into memory and handed out as views (no copy; the mapping is private and
+// writable because parsing upper-cases bases in place -- only pages that really hold lower-case bases get copied); gzip
+// input goes through gzread into an owned buffer.
 class FastqBlockReader {
  public:
-  bool open(const std::string& path) { gz_ = gzopen(path.c_str(), "rb"); if (gz_) gzbuffer(gz_, 1 << 22); return gz_ != nullptr; }
-  ~FastqBlockReader() { if (gz_) gzclose(gz_); }
-  // up to max_rec records -> out (ends with '\n'); returns the number of records, 0 at end of input
-  size_t next(size_t max_rec, std::string& out) {
+  bool open(const std::string& path) {
+    const int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    unsigned char magic[2] = {0, 0};
+    const ssize_t got = ::pread(fd, magic, 2, 0);
+    struct stat st;
+    if (got == 2 && !(magic[0] == 0x1f && magic[1] == 0x8b) && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+      void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ | PROT_WRITE, MAP_PRIVATE, fd, 0);
+      if (m != MAP_FAILED) {
+        map_ = (char*)m; map_size_ = (size_t)st.st_size;
+        madvise(map_, map_size_, MADV_SEQUENTIAL);
+        ::close(fd);
+        return true;
+      }
+    }
+    ::close(fd);
+    gz_ = gzopen(path.c_str(), "rb"); if (gz_) gzbuffer(gz_, 1 << 22); return gz_ != nullptr;
+  }
+  ~FastqBlockReader() { if (gz_) gzclose(gz_); if (map_) munmap(map_, map_size_); }
+  // up to max_rec records -> view (whole records; the last line of the input may lack its '\n'); `owned` backs the view for
+  // gzip input.  Returns the number of records, 0 at end of input.
+  size_t next(size_t max_rec, std::string_view& view, std::string& owned) {
+    if (!map_) { const size_t n = next_copy(max_rec, owned); view = owned; return n; }
+    const size_t want = max_rec * 4;
+    size_t lines = 0, at = pos_;
+    constexpr size_t BLK = 4096;
+    while (lines < want && at < map_size_) {
+      const size_t n = std::min(BLK, map_size_ - at);
+      const size_t c = count_newlines(map_ + at, n);
+      if (lines + c < want) { lines += c; at += n; continue; }
+      while (lines < want) { at = (size_t)((const char*)memchr(map_ + at, '\n', map_size_ - at) - map_) + 1; ++lines; }   // the want-th newline is inside this block
+    }
+    if (lines < want && at == map_size_ && map_size_ > pos_ && map_[map_size_ - 1] != '\n') ++lines;   // last line without a newline
+    const size_t rec = lines / 4;
+    if (rec == 0) { pos_ = map_size_; return 0; }
+    size_t end = at;
+    if (lines != rec * 4) {      // trailing partial record: stop after the last whole one
+      end = pos_;
+      for (size_t l = 0; l < rec * 4; ++l) end = (size_t)((const char*)memchr(map_ + end, '\n', map_size_ - end) - map_) + 1;
+    }
+    view = std::string_view(map_ + pos_, end - pos_);
+    pos_ = end;
+    return rec;
+  }
+ private:
+  // gzip path: up to max_rec records -> out (ends with '\n')
+  size_t next_copy(size_t max_rec, std::string& out) {
     out.clear();
     size_t lines = 0, scan = pos_;
     const size_t want = max_rec * 4;
@@ -79,8 +155,8 @@ class FastqBlockReader {
     pos_ = end;
     return rec;
   }
- private:
   gzFile gz_ = nullptr; std::string buf_; size_t pos_ = 0; bool eof_ = false;
+  char* map_ = nullptr; size_t map_size_ = 0;
 };
 
 // one line of a raw block, without the line end ('\n' or "\r\n"); advances p

@@ -50,7 +50,7 @@ inline void finish_single(const HostContext& hc, const ReadView& rd, const bmbs_
   auto emit = [&](uint64_t site, uint64_t end_site, int start_site, unsigned nm, const std::string& cigar, int mapq) -> bool {
     Placed p = place(hc.chroms, site, (uint64_t)(int64_t)start_site, end_site);
     if (p.off_chrom) return false;
-    sam_record_se(out, rd.name, seq, qual, hc.chroms, p, mapq, cigar, nm, p.flag ? revcomp(seq) : std::string());
+    sam_record_se(out, rd.name, seq, qual, hc.chroms, p, mapq, cigar, nm);
     return true;
   };
   switch (res.state) {
@@ -204,7 +204,7 @@ inline void finish_pair(const HostContext& hc, std::string_view name1, std::stri
   if (!(m1.pos + m1.span <= hc.chroms.len[m1.chrom] + 1 && m2.pos + m2.span <= hc.chroms.len[m2.chrom] + 1)) return;
   ++st.unique; st.bases += L1 + L2; st.err_bases += m1.err + m2.err;
   const int mapq = mapq_from(pk.sbd, (unsigned)(k1 + k2), m1.score + m2.score, hc.sc);
-  sam_record_pe(out, true, name1, seq1, m1.flag ? revcomp(seq1) : std::string(), qual1, hc.chroms, m1.flag, m1.chrom, m1.pos, mapq, m1.cigar, m2.pos, tlen, m1.err);
+  sam_record_pe(out, true, name1, seq1, std::string_view(), qual1, hc.chroms, m1.flag, m1.chrom, m1.pos, mapq, m1.cigar, m2.pos, tlen, m1.err);
   sam_record_pe(out, false, name2, seq2, raw2, qual2, hc.chroms, m2.flag, m2.chrom, m2.pos, mapq, m2.cigar, m1.pos, tlen, m2.err);
 }
 

@@ -11,6 +11,27 @@
 
 namespace bmbs {
 
+// decimal text of v appended to out (std::to_string allocates a temporary per field)
+inline void append_uint(std::string& out, uint64_t v) {
+  char buf[24]; int n = 0;
+  do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+  const size_t at = out.size(); out.resize(at + (size_t)n);
+  for (int i = 0; i < n; ++i) out[at + (size_t)i] = buf[n - 1 - i];
+}
+inline void append_int(std::string& out, long long v) { if (v < 0) { out += '-'; append_uint(out, (uint64_t)(-(v + 1)) + 1u); } else append_uint(out, (uint64_t)v); }
+inline void append_reversed(std::string& out, std::string_view s) {
+  const size_t at = out.size(), n = s.size(); out.resize(at + n);
+  for (size_t i = 0; i < n; ++i) out[at + i] = s[n - 1 - i];
+}
+inline char complement_base(char c) { return c == 'A' ? 'T' : c == 'T' ? 'A' : c == 'C' ? 'G' : c == 'G' ? 'C' : c; }
+struct ComplementTable { char t[256]; ComplementTable() { for (int i = 0; i < 256; ++i) t[i] = complement_base((char)i); } };
+inline const char* complement_table() { static const ComplementTable c; return c.t; }
+inline void append_revcomp(std::string& out, std::string_view s) {
+  const char* t = complement_table();
+  const size_t at = out.size(), n = s.size(); out.resize(at + n);
+  for (size_t i = 0; i < n; ++i) out[at + i] = t[(unsigned char)s[n - 1 - i]];
+}
+
 inline void sam_header(std::string& out, const ChromTable& ct, const std::string& cmdline) {
   out += "@HD\tVN:1.4\tSO:unsorted\n";
   for (size_t i = 0; i < ct.name.size(); ++i) out += "@SQ\tSN:" + ct.name[i] + "\tLN:" + std::to_string(ct.len[i]) + "\n";
@@ -20,38 +41,38 @@ inline void sam_header(std::string& out, const ChromTable& ct, const std::string
 // Single-end record.  `seq`/`qual` as in the FASTQ; reverse-strand hits print
 // the reverse complement and the reversed qualities.
 inline void sam_record_se(std::string& out, std::string_view name, std::string_view seq, std::string_view qual,
-                          const ChromTable& ct, const Placed& p, int mapq, const std::string& cigar, unsigned nm,
-                          std::string_view rseq) {
+                          const ChromTable& ct, const Placed& p, int mapq, const std::string& cigar, unsigned nm) {
   out += name; out += '\t';
-  out += std::to_string(p.flag); out += '\t';
+  append_uint(out, (uint64_t)p.flag); out += '\t';
   out += ct.name[p.chrom]; out += '\t';
-  out += std::to_string(p.pos); out += '\t';
-  out += std::to_string(mapq); out += '\t';
+  append_uint(out, p.pos); out += '\t';
+  append_int(out, mapq); out += '\t';
   out += cigar; out += "\t*\t0\t0\t";
   if (p.flag == 0) { out += seq; out += '\t'; out += qual; }
-  else { out += rseq; out += '\t'; out.append(qual.rbegin(), qual.rend()); }
-  out += "\tNM:i:"; out += std::to_string(nm); out += '\n';
+  else { append_revcomp(out, seq); out += '\t'; append_reversed(out, qual); }
+  out += "\tNM:i:"; append_uint(out, nm); out += '\n';
 }
 
 // Paired-end record (Schema.cpp:9453-9700 mate 1, :10922-11170 mate 2).  `seq` is
-// what was aligned, `rseq` its reverse complement, `qual` the FASTQ-order
+// what was aligned, `rseq` its reverse complement (empty: computed here), `qual` the FASTQ-order
 // qualities; for mate 2 `seq` is the reverse complement of the FASTQ record.
 // strand_flag: 0 = aligned sequence lies on the forward strand, 16 = reverse.
 inline void sam_record_pe(std::string& out, bool first, std::string_view name, std::string_view seq, std::string_view rseq,
                           std::string_view qual, const ChromTable& ct, int strand_flag, size_t chrom, uint64_t pos, int mapq,
                           const std::string& cigar, uint64_t mate_pos, long long tlen, unsigned nm) {
   const int flag = first ? (strand_flag == 0 ? 99 : 83) : (strand_flag == 0 ? 147 : 163);
-  out += name; out += '\t'; out += std::to_string(flag); out += '\t'; out += ct.name[chrom]; out += '\t';
-  out += std::to_string(pos); out += '\t'; out += std::to_string(mapq); out += '\t'; out += cigar; out += "\t=\t";
-  out += std::to_string(mate_pos); out += '\t';
+  out += name; out += '\t'; append_uint(out, (uint64_t)flag); out += '\t'; out += ct.name[chrom]; out += '\t';
+  append_uint(out, pos); out += '\t'; append_int(out, mapq); out += '\t'; out += cigar; out += "\t=\t";
+  append_uint(out, mate_pos); out += '\t';
   if (mate_pos < pos || (mate_pos == pos && !first)) out += '-';
-  out += std::to_string((int)tlen); out += '\t';
+  append_int(out, (int)tlen); out += '\t';
+  auto put_rseq = [&] { if (rseq.empty()) append_revcomp(out, seq); else out += rseq; };
   if (first) {
-    if (flag & 32) { out += seq; out += '\t'; out += qual; } else { out += rseq; out += '\t'; out.append(qual.rbegin(), qual.rend()); }
+    if (flag & 32) { out += seq; out += '\t'; out += qual; } else { put_rseq(); out += '\t'; append_reversed(out, qual); }
   } else {
-    if (flag & 16) { out += seq; out += '\t'; out.append(qual.rbegin(), qual.rend()); } else { out += rseq; out += '\t'; out += qual; }
+    if (flag & 16) { out += seq; out += '\t'; append_reversed(out, qual); } else { put_rseq(); out += '\t'; out += qual; }
   }
-  out += "\tNM:i:"; out += std::to_string(nm); out += '\n';
+  out += "\tNM:i:"; append_uint(out, nm); out += '\n';
 }
 
 struct MapStats { uint64_t reads = 0, unique = 0, ambiguous = 0, bases = 0, err_bases = 0; };

@@ -35,7 +35,7 @@ int main(int argc, char** argv) {
       bmbs::cut_name_se(r.name);
       oracle::map_single(ix, P, r.seq.c_str(), r.qual.c_str(), (int)r.seq.size(), o, st, carry);
       if (o.kind == oracle::SeOutcome::UNIQUE && !o.dropped_off_chrom)
-        bmbs::sam_record_se(out, r.name, r.seq, r.qual, ix.chroms, o.placed, o.mapq, o.cigar, o.err, bmbs::revcomp(r.seq));
+        bmbs::sam_record_se(out, r.name, r.seq, r.qual, ix.chroms, o.placed, o.mapq, o.cigar, o.err);
       if (out.size() > (1u << 20)) { fwrite(out.data(), 1, out.size(), fo); out.clear(); }
     }
     fwrite(out.data(), 1, out.size(), fo); fclose(fo);

@@ -23,6 +23,11 @@ for w in $WHAT; do
         python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_full_bench.log 2>&1; echo "ncu full exit $?" ;;
     verify)
       timeout 900 python tools/bench_verify.py > $O/${TAG}_verify.json 2> $O/${TAG}_verify.log; echo "bench_verify exit $?"; tail -c 1500 $O/${TAG}_verify.json ;;
+    fullverify)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:verify_windows --launch-skip 3 --launch-count 1 -f -o $O/${TAG}_fullverify150 \
+        python tools/bench_verify.py --lengths 150 --rates 0.02 --reps 2 --no-oracle --cpu-sample-log2 10 > $O/${TAG}_fullverify.log 2>&1; echo "ncu verify150 exit $?"
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:verify_windows --launch-skip 3 --launch-count 1 -f -o $O/${TAG}_fullverify250 \
+        python tools/bench_verify.py --lengths 250 --rates 0.02 --reps 2 --no-oracle --cpu-sample-log2 10 >> $O/${TAG}_fullverify.log 2>&1; echo "ncu verify250 exit $?" ;;
     scale2)
       timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 \
         > $O/${TAG}_scale2.json 2> $O/${TAG}_scale2.log; cat $O/${TAG}_scale2.json ;;

@@ -376,6 +376,10 @@ def main():
         "work_per_step": counters,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": dbytes, "kernel_ms": dms,
+                     # DRAM bytes the kernels really move (ncu, profiles/ncu_traffic.json) over the live kernel time: random 8-byte table entries and
+                     # 32-byte occ blocks cost a 64-byte DRAM access each, so this -- not the algorithmic figure -- is what loads HBM
+                     "traffic_gbs": traffic / (dms / 1000) / 1e9 if traffic and dms > 0 else None,
+                     "traffic_frac_of_peak": traffic / (dms / 1000) / 1e9 / peak if traffic and dms > 0 and peak else None,
                      "random_sector_peak_gbs": rs_peak * 32 / 1e9 if rs_peak else None, "seed_random_sector_gbs": seed_sector_rate * 32 / 1e9,
                      "frac_of_random_sector_peak": seed_sector_rate / rs_peak if rs_peak else None,
                      "note": "after the deep seed table a seed is one 8-byte entry: the seed kernels are bound by dependent random sectors and instruction issue, not by bytes (DESIGN.md 7)",

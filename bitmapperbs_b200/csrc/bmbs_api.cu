@@ -428,9 +428,12 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
   if (n > 0) {
     pack_reads<<<(n + 15) / 16, 128, 0, s>>>(v); ++b->launches;
     CU(cudaEventRecord(b->ev[1], s));
-    seed_first<<<(n + 127) / 128, 128, 0, s>>>(ix, v); ++b->launches;
-    seed_second<<<(n + 127) / 128, 128, 0, s>>>(ix, v); ++b->launches;
-    seed_rest<<<(n + 127) / 128, 128, 0, s>>>(ix, v); ++b->launches;
+    // read chunks staged per thread in shared memory: max_len/32 + 2 chunks of 16 bytes, at most 12 (longer reads: the rest from global memory)
+    const u32 plane_cap = (u32)std::min(b->max_len / 32 + 2, 12);
+    const size_t seed_smem = (size_t)plane_cap * SEED_BLOCK * sizeof(uint4);
+    seed_first<<<(n + 127) / 128, SEED_BLOCK, seed_smem, s>>>(ix, v, plane_cap); ++b->launches;
+    seed_second<<<(n + 127) / 128, SEED_BLOCK, seed_smem, s>>>(ix, v, plane_cap); ++b->launches;
+    seed_rest<<<(n + 127) / 128, SEED_BLOCK, seed_smem, s>>>(ix, v, plane_cap); ++b->launches;
     CU(cudaEventRecord(b->ev[2], s));
     run_scan(b, v.ncand, (u32)n, v.coff, v.totals, v.slot_cap, 2u);
     expand_locate<<<(n + 127) / 128, 128, 0, s>>>(ix, v); ++b->launches;
@@ -448,7 +451,7 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
     const size_t smem = (size_t)5 * nch2 * bd * 8;
     int per_sm = (int)((226 * 1024) / (smem + 1024)); if (per_sm > 12) per_sm = 12; if (per_sm < 1) per_sm = 1;
     run_scan(b, v.nv, (u32)n, v.voff, v.totals + 1, v.slot_cap, 4u);
-    gather_work<<<b->sm_count * 8, 256, 0, s>>>(v); ++b->launches;
+    gather_work<<<(n + 127) / 128, 128, 0, s>>>(v); ++b->launches;
     verify_windows<<<b->sm_count * per_sm, bd, smem, s>>>(ix, v, nch2); ++b->launches;
     CU(cudaEventRecord(b->ev[6], s));
     if (v.sensitive) {
@@ -456,7 +459,7 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
       sens_pair<<<(n / 2 + 127) / 128, 128, 0, s>>>(v); ++b->launches;
       reseed_clear<<<(n + 255) / 256, 256, 0, s>>>(v); ++b->launches;
       BatchView w = v; w.round = 1;
-      seed_reseed<<<b->sm_count * 8, 128, 0, s>>>(ix, w); ++b->launches;
+      seed_reseed<<<b->sm_count * 8, SEED_BLOCK, seed_smem, s>>>(ix, w, plane_cap); ++b->launches;
       run_scan(b, w.ncand, (u32)n, w.coff, w.totals, w.slot_cap, 2u);
       expand_locate<<<(n + 127) / 128, 128, 0, s>>>(ix, w); ++b->launches;
       votes_classify<<<(n + 255) / 256, 256, 0, s>>>(w); ++b->launches;
@@ -465,7 +468,7 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
       votes_big<<<b->sm_count * 4, 256, 0, s>>>(w); ++b->launches;
       sens_reseed_filter<<<b->sm_count * 4, 128, 0, s>>>(w); ++b->launches;
       run_scan(b, w.nv, (u32)n, w.voff, w.totals + 1, w.slot_cap, 4u, w.totals + 2);
-      gather_work<<<b->sm_count * 8, 256, 0, s>>>(w); ++b->launches;
+      gather_work<<<(n + 127) / 128, 128, 0, s>>>(w); ++b->launches;
       verify_windows<<<b->sm_count * per_sm, bd, smem, s>>>(ix, w, nch2); ++b->launches;
       sens_reseed_finish<<<b->sm_count * 4, 128, 0, s>>>(w); ++b->launches;
     }

@@ -146,10 +146,20 @@ struct SeedHit { u64 hits, sp, ep; u32 mlen; bool has_sa; u64 sa; };   // has_sa
 
 // Read bases as bit-planes.  FM alphabet of the reversed, C->T converted read: G0 T1 A2, anything else stops a seed;
 // from the planes (A00 C01 G10 T11): fm = lo | ((~lo & ~hi) << 1).
+// A seeding thread looks at its read many times (every seed, every 32 symbols of an extension); between two looks the
+// random table / occ sectors of the whole SM have flushed L1 and much of L2, so the chunks are staged once per read in
+// shared memory (column `threadIdx.x` of s[chunk][blockDim.x]; `ns` chunks, longer reads fall back to global memory).
+constexpr int SEED_BLOCK = 128;
 struct ReadPlanes {
-  const uint4* p;
+  const uint4* p; const uint4* s; u32 ns;
+  __device__ __forceinline__ void stage(const uint4* src, u32 L, uint4* smem_col, u32 cap) {
+    p = src; s = smem_col;
+    ns = (L >> 5) + 2; if (ns > cap) ns = cap;           // chunks 0 .. L/32 hold bases, +1 for the look-ahead of window()
+    for (u32 i = 0; i < ns; ++i) smem_col[i * SEED_BLOCK] = __ldg(src + i);
+  }
+  __device__ __forceinline__ uint4 chunk(u32 i) const { return i < ns ? s[i * SEED_BLOCK] : __ldg(p + i); }
   __device__ __forceinline__ void window(u32 pos, u32& lo, u32& hi, u32& bad) const {   // 32 bases starting at pos
-    const uint4 a = __ldg(p + (pos >> 5)), c = __ldg(p + (pos >> 5) + 1);
+    const uint4 a = chunk(pos >> 5), c = chunk((pos >> 5) + 1);
     const unsigned s = pos & 31u;
     lo = __funnelshift_r(a.x, c.x, s); hi = __funnelshift_r(a.y, c.y, s); bad = __funnelshift_r(a.z, c.z, s);
   }
@@ -304,7 +314,7 @@ __device__ __forceinline__ u64 count_exact(const DevIndex& ix, const ReadPlanes&
 // determine_seed_offset_unmatch, Schema.h:1506-1531 (step 8): skip past an N inside the next 8 bases
 __device__ __forceinline__ u32 next_offset_unmatched(const ReadPlanes& rp, u32 L, u32 off) {
   if ((int)L - (int)off < 18) return L;
-  const uint4 a = __ldg(rp.p + (off >> 5)), c = __ldg(rp.p + (off >> 5) + 1);
+  const uint4 a = rp.chunk(off >> 5), c = rp.chunk((off >> 5) + 1);
   const u32 n8 = __funnelshift_r(a.w, c.w, off & 31u) & 0xFFu;
   return n8 ? off + (u32)__ffs(n8) : off + 8;
 }
@@ -316,7 +326,7 @@ __device__ __forceinline__ int compare_rest(const DevIndex& ix, const ReadPlanes
   const bool inside = window_inside(ix, site, L);
   const u32 from = mlen;
   for (u32 c0 = from & ~31u; c0 < L; c0 += 32) {
-    const uint4 r = __ldg(rp.p + (c0 >> 5));
+    const uint4 r = rp.chunk(c0 >> 5);
     u32 mism;
     if (inside) {
       const u64 g = site + c0;
@@ -378,7 +388,8 @@ struct TaskWriter {
   __device__ __forceinline__ void store() { b.ntask[r] = nt < MAX_TASKS ? nt : MAX_TASKS; b.ncand[r] = nt <= MAX_TASKS ? nc : 0xFFFFFFFFu; }
 };
 
-__global__ void __launch_bounds__(128) seed_first(DevIndex ix, BatchView b) {
+__global__ void __launch_bounds__(128) seed_first(DevIndex ix, BatchView b, u32 plane_cap) {
+  extern __shared__ uint4 s_planes[];      // [plane_cap][SEED_BLOCK] staged read chunks
   __shared__ u64 s_cnt[4];
   __shared__ unsigned char s_lut[256];
   if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
@@ -389,7 +400,7 @@ __global__ void __launch_bounds__(128) seed_first(DevIndex ix, BatchView b) {
   bool to2 = false, to3 = false;
   if (r < b.n_reads) {
     const u32 L = b.len[r];
-    ReadPlanes rp; rp.p = b.rplanes + plane_chunk_offset(b.offsets, r);
+    ReadPlanes rp; rp.stage(b.rplanes + plane_chunk_offset(b.offsets, r), L, s_planes + threadIdx.x, plane_cap);
     const u32 first_c = b.first_c[r];
     u64 max_seeds = (u64)L / 10 - 1; if (max_seeds > 25) max_seeds = 25;   // u64 wrap for L < 10, as in the reference
     TaskWriter tw{b, r, 0, 0};
@@ -448,7 +459,8 @@ __global__ void __launch_bounds__(128) seed_first(DevIndex ix, BatchView b) {
 }
 
 // one-mismatch rule: a single second seed covering read[first_len .. L)  (Schema.cpp:27334-27401)
-__global__ void __launch_bounds__(128) seed_second(DevIndex ix, BatchView b) {
+__global__ void __launch_bounds__(128) seed_second(DevIndex ix, BatchView b, u32 plane_cap) {
+  extern __shared__ uint4 s_planes[];      // [plane_cap][SEED_BLOCK] staged read chunks
   __shared__ u64 s_cnt[4];
   __shared__ unsigned char s_lut[256];
   if (blockIdx.x * blockDim.x >= b.list_count[0]) return;     // launched with one thread per read: the hardware balances the blocks
@@ -463,7 +475,7 @@ __global__ void __launch_bounds__(128) seed_second(DevIndex ix, BatchView b) {
     if (i < n2) {
       r = b.list2[i];
       const u32 L = b.len[r], first_len = b.ph_first_len[r];
-      ReadPlanes rp; rp.p = b.rplanes + plane_chunk_offset(b.offsets, (int)r);
+      ReadPlanes rp; rp.stage(b.rplanes + plane_chunk_offset(b.offsets, (int)r), L, s_planes + threadIdx.x, plane_cap);
       TaskWriter tw{b, (int)r, b.ntask[r], b.ncand[r]};
       const u32 len2 = L - first_len;
       bool extra = true;
@@ -484,8 +496,10 @@ __global__ void __launch_bounds__(128) seed_second(DevIndex ix, BatchView b) {
   flush_counters(s_cnt, cn, b.counters);
 }
 
-// the remaining seeds (Schema.cpp:27434-27515)
-__global__ void __launch_bounds__(128) seed_rest(DevIndex ix, BatchView b) {
+// the remaining seeds (Schema.cpp:27434-27515).  62 registers = 8 resident blocks; bounding it for 10 or 12 blocks spills and
+// measures slower (1.10 / 1.17 ms against 1.07 ms for the seeding stage)
+__global__ void __launch_bounds__(128) seed_rest(DevIndex ix, BatchView b, u32 plane_cap) {
+  extern __shared__ uint4 s_planes[];      // [plane_cap][SEED_BLOCK] staged read chunks
   __shared__ u64 s_cnt[4];
   __shared__ unsigned char s_lut[256];
   if (blockIdx.x * blockDim.x >= b.list_count[1]) return;
@@ -497,7 +511,7 @@ __global__ void __launch_bounds__(128) seed_rest(DevIndex ix, BatchView b) {
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += gridDim.x * blockDim.x) {
     const u32 r = b.list3[i];
     const u32 L = b.len[r];
-    ReadPlanes rp; rp.p = b.rplanes + plane_chunk_offset(b.offsets, (int)r);
+    ReadPlanes rp; rp.stage(b.rplanes + plane_chunk_offset(b.offsets, (int)r), L, s_planes + threadIdx.x, plane_cap);
     u64 max_seeds = (u64)L / 10 - 1; if (max_seeds > 25) max_seeds = 25;
     TaskWriter tw{b, (int)r, b.ntask[r], b.ncand[r]};
     u32 off = b.ph_off[r]; u64 seed_id = b.ph_seed_id[r], sp = 0, ep = 0;
@@ -529,7 +543,7 @@ __global__ void __launch_bounds__(128) seed_rest(DevIndex ix, BatchView b) {
 // from the dense suffix array) and turned into a site, and cand[] / slot_read[] are written coalesced.
 //   site = 2N - SA - seed_len - seed_off, modulo 2^64 (reverse_and_adjust_site, Schema.cpp:4657-4683)
 constexpr int SEG_CAP = 256;                      // segments per warp and pass; a read has at most MAX_TASKS = 28
-struct Seg { u64 sp; u32 start; u32 info; };      // info: seed_len + seed_off | owner lane << 16 | literal site << 31
+struct Seg { u64 sp; u32 start; u32 info; };      // info: seed_len + seed_off | literal site << 31
 
 __global__ void __launch_bounds__(128) expand_locate(DevIndex ix, BatchView b) {
   __shared__ Seg s_seg[4][SEG_CAP];
@@ -559,7 +573,7 @@ __global__ void __launch_bounds__(128) expand_locate(DevIndex ix, BatchView b) {
       for (u32 t = 0; t < nt; ++t) {
         const SeedTask k = b.tasks[(size_t)t * b.n_reads + r];
         Seg g; g.sp = k.sp; g.start = s;
-        g.info = (k.hits ? (u32)k.mlen + (u32)k.off : 0x80000000u) | ((u32)lane << 16);
+        g.info = k.hits ? (u32)k.mlen + (u32)k.off : 0x80000000u;
         seg[excl - base + t] = g;
         s += k.hits ? k.hits : 1u;
       }
@@ -578,7 +592,6 @@ __global__ void __launch_bounds__(128) expand_locate(DevIndex ix, BatchView b) {
           site = 2 * ix.N - sa - (u64)(g.info & 0xFFFFu); ++rows; steps += st;
         }
         b.cand[s] = site;
-        b.slot_read[s] = (u32)(r - lane) + ((g.info >> 16) & 31u);
       }
     }
     __syncwarp();
@@ -774,46 +787,54 @@ __global__ void filter_pairs_kernel(BatchView b) {
 }
 
 // ------------------------------------------------------------------------------------------- gather
-// Work item w = voff[r] + j for every surviving window.  Windows of reads that seeding already resolved get their
-// record here (end L-1, err 0 or 1); the others are appended to a dense list, so that every lane of the
-// bit-vector kernel has a window to verify.
-__global__ void __launch_bounds__(256) gather_work(BatchView b) {
-  __shared__ u32 s_n, s_base;
-  const u32 total = *b.status ? 0u : (u32)b.totals[0];
+// Work item w = voff[r] + j for every surviving window j < nv[r] of read r.  Windows of reads that seeding already resolved
+// get their record here (end L-1, err 0 or 1); the others become one VerifyItem each in a dense list, so that every lane of
+// the bit-vector kernel has a window to verify.  A warp owns 32 consecutive reads: one scan over their window counts, one
+// atomic for the warp's share of the list, then consecutive lanes take consecutive windows (owner found by a binary search
+// over the scanned counts through shuffles); the list stays grouped by read.
+__global__ void __launch_bounds__(128) gather_work(BatchView b) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool ok = !*b.status, live = ok && r < b.n_reads;
   const u64 out_base = b.totals[2];
-  const u32 rounds = (total + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
-  for (u32 it = 0; it < rounds; ++it) {
-    const u32 s = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
-    bool verify = false; u32 w = 0;
-    VerifyItem item;
-    if (s < total) {
-      const u32 r = b.slot_read[s];
-      const u32 j = s - b.coff[r];
-      if (j < b.nv[r]) {
-        w = b.voff[r] + j;
-        const int st = b.round == 0 ? b.state[r] : BMBS_VERIFY;
-        if (st == BMBS_VERIFY || st == BMBS_NONE) {
-          item.site = b.cand[s]; item.wi = w; item.vote = b.vcnt[s]; item.code_off = code_word_offset(b.offsets, (int)r);
-          item.L = b.len[r]; item.k = b.kk[r]; item.pad = 0; verify = true;
-        } else {
-          bmbs_cand o; o.site = b.cand[s]; o.vote = b.vcnt[s]; o.end_site = (int16_t)(b.len[r] - 1); o.err = st == BMBS_ONE_MISMATCH ? 1 : 0;
-          b.out_cand[out_base + w] = o;
-        }
+  u32 nvr = 0, c0 = 0, w0 = 0, L = 0, k = 0, code_off = 0; int st = BMBS_NONE;
+  if (live) {
+    nvr = b.nv[r];
+    if (nvr) { c0 = b.coff[r]; w0 = b.voff[r]; L = b.len[r]; k = b.kk[r]; code_off = code_word_offset(b.offsets, r); st = b.round == 0 ? b.state[r] : BMBS_VERIFY; }
+  }
+  const bool is_ver = st == BMBS_VERIFY || st == BMBS_NONE;
+  u32 incl = nvr, vincl = is_ver ? nvr : 0u;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 t = __shfl_up_sync(0xffffffffu, incl, o), tv = __shfl_up_sync(0xffffffffu, vincl, o);
+    if (lane >= o) { incl += t; vincl += tv; }
+  }
+  const u32 total = __shfl_sync(0xffffffffu, incl, 31), vtotal = __shfl_sync(0xffffffffu, vincl, 31);
+  const u32 excl = incl - nvr, vexcl = vincl - (is_ver ? nvr : 0u);
+  u32 vbase = 0;
+  if (lane == 0 && vtotal) vbase = atomicAdd(b.list_count + 3, vtotal);
+  vbase = __shfl_sync(0xffffffffu, vbase, 0);
+  for (u32 i0 = 0; i0 < total; i0 += 32) {
+    const u32 i = i0 + lane;
+    int o = 0;                                                    // owner: the lane with excl <= i < incl
+#pragma unroll
+    for (int step = 16; step; step >>= 1) { const u32 t = __shfl_sync(0xffffffffu, incl, o + step - 1); if (t <= i) o += step; }
+    o &= 31;
+    const u32 j = i - __shfl_sync(0xffffffffu, excl, o);
+    const u32 s = __shfl_sync(0xffffffffu, c0, o) + j, w = __shfl_sync(0xffffffffu, w0, o) + j;
+    const u32 oL = __shfl_sync(0xffffffffu, L, o), ok_ = __shfl_sync(0xffffffffu, k, o), ocode = __shfl_sync(0xffffffffu, code_off, o);
+    const int ost = __shfl_sync(0xffffffffu, st, o);
+    const u32 ovex = __shfl_sync(0xffffffffu, vexcl, o);
+    if (i < total) {
+      const u64 site = b.cand[s]; const u32 vote = b.vcnt[s];
+      if (ost == BMBS_VERIFY || ost == BMBS_NONE) {
+        VerifyItem it; it.site = site; it.wi = w; it.vote = vote; it.code_off = ocode; it.L = oL; it.k = ok_; it.pad = 0;
+        b.vitems[vbase + ovex + j] = it;
+      } else {
+        bmbs_cand c; c.site = site; c.vote = vote; c.end_site = (int16_t)(oL - 1); c.err = ost == BMBS_ONE_MISMATCH ? 1 : 0;
+        b.out_cand[out_base + w] = c;
       }
     }
-    // block-aggregated append: one global atomic per block and round
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    const u32 bal = __ballot_sync(0xffffffffu, verify);
-    const int lane = threadIdx.x & 31;
-    u32 wbase = 0;
-    if (lane == 0 && bal) wbase = atomicAdd(&s_n, (u32)__popc(bal));
-    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_n) s_base = atomicAdd(b.list_count + 3, s_n);
-    __syncthreads();
-    if (verify) b.vitems[s_base + wbase + __popc(bal & ((1u << lane) - 1u))] = item;
-    __syncthreads();
   }
 }
 
@@ -1038,7 +1059,8 @@ __global__ void reseed_clear(BatchView b) {
 
 // reseed_filter_muti_thread, Schema.cpp:16998-17240: up to three exact seeds chosen from the gaps of the seeds used so
 // far (select_best_seeds, :16630-16670), then a greedy seed every 8 bases; a multi-hit seed counts from 20 bases.
-__global__ void __launch_bounds__(128) seed_reseed(DevIndex ix, BatchView b) {
+__global__ void __launch_bounds__(128) seed_reseed(DevIndex ix, BatchView b, u32 plane_cap) {
+  extern __shared__ uint4 s_planes[];      // [plane_cap][SEED_BLOCK] staged read chunks
   __shared__ u64 s_cnt[4];
   __shared__ unsigned char s_lut[256];
   if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
@@ -1049,7 +1071,7 @@ __global__ void __launch_bounds__(128) seed_reseed(DevIndex ix, BatchView b) {
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
     const u32 r = b.list4[i];
     const u32 L = b.len[r];
-    ReadPlanes rp; rp.p = b.rplanes + plane_chunk_offset(b.offsets, (int)r);
+    ReadPlanes rp; rp.stage(b.rplanes + plane_chunk_offset(b.offsets, (int)r), L, s_planes + threadIdx.x, plane_cap);
     u64 max_seeds = (u64)L / 10 - 1; if (max_seeds > 25) max_seeds = 25;
     TaskWriter tw{b, (int)r, 0, 0};
     const unsigned short* k5 = b.bk + (size_t)r * 5;

@@ -5,5 +5,5 @@ host mapper `_build/bmbs`; this package is the thin Python host mirror used by t
 tests and bench.py (ctypes over the same C ABI).  There is no CPU fallback: loading
 fails loudly when the CUDA library has not been built.
 """
-from .capi import (BmbsError, Index, Batch, Params, ReadResult, Cand, lib_path, load_library,  # noqa: F401
+from .capi import (BmbsError, Index, Batch, Refiner, Params, ReadResult, Cand, lib_path, load_library,  # noqa: F401
                    NONE, EXACT_UNIQUE, MULTI_EXACT, ONE_MISMATCH, VERIFY)

@@ -19,6 +19,15 @@ class Params(C.Structure):
     _fields_ = [("e_rate", C.c_double), ("seed_len", C.c_int), ("min_ins", C.c_int), ("max_ins", C.c_int), ("sensitive", C.c_int)]
 
 
+class Scoring(C.Structure):
+    """bmbs_scoring (include/bmbs.h): --mp_max --mp_min --np --gap_open --gap_extension, quality base"""
+    _fields_ = [("mp_max", C.c_int), ("mp_min", C.c_int), ("n_pen", C.c_int), ("gap_open", C.c_int), ("gap_ext", C.c_int), ("q_base", C.c_int)]
+
+
+RefineItem = np.dtype([("site", "<u8"), ("seq_off", "<u4"), ("len", "<u2"), ("k", "u1"), ("pad", "u1")])
+RefineResult = np.dtype([("score", "<i4"), ("qb", "<i4"), ("qe", "<i4"), ("n_ops", "<u4"), ("ops_off", "<u4")])
+
+
 class BmbsError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"bmbs error {code}: {msg}")
@@ -34,7 +43,8 @@ _lib = None
 EXPORTS = ["bmbs_index_load", "bmbs_index_free", "bmbs_index_genome_length", "bmbs_index_device_bytes", "bmbs_last_error",
            "bmbs_params_default", "bmbs_map_batch_se", "bmbs_map_batch_pe", "bmbs_verify", "bmbs_batch_create", "bmbs_batch_free",
            "bmbs_batch_upload", "bmbs_batch_run", "bmbs_batch_download", "bmbs_batch_sync", "bmbs_batch_timings",
-           "bmbs_batch_counters", "bmbs_batch_launches", "bmbs_batch_verify", "bmbs_batch_download_verify", "bmbs_ubench_int_pipe", "bmbs_pinned_alloc", "bmbs_pinned_free", "bmbs_ubench_random_sectors"]
+           "bmbs_batch_counters", "bmbs_batch_launches", "bmbs_batch_verify", "bmbs_batch_download_verify", "bmbs_ubench_int_pipe", "bmbs_pinned_alloc", "bmbs_pinned_free", "bmbs_ubench_random_sectors",
+           "bmbs_refiner_create", "bmbs_refiner_free", "bmbs_refine"]
 
 
 def load_library():
@@ -69,6 +79,9 @@ def load_library():
     L.bmbs_batch_download_verify.argtypes = [vp, vp, vp, C.c_size_t]
     L.bmbs_ubench_int_pipe.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.bmbs_ubench_random_sectors.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_double)]
+    L.bmbs_refiner_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.bmbs_refiner_free.argtypes = [vp]
+    L.bmbs_refine.argtypes = [vp, vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(Scoring), vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     _lib = L
     return L
 
@@ -228,6 +241,36 @@ class Batch:
         if self._h:
             self._L.bmbs_batch_free(self._h)
             self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Refiner:
+    """bmbs_refiner: the banded affine-gap DP with traceback of the CIGAR refinement on the device"""
+
+    def __init__(self, index: Index, dev=0):
+        self.L = load_library(); self.h = C.c_void_p()
+        _check(self.L.bmbs_refiner_create(index._h, dev, C.byref(self.h)))
+
+    def refine(self, seqs: bytes, quals: bytes, items: np.ndarray, scoring=(6, 2, 1, 5, 3, 33)):
+        """items: RefineItem array; returns (RefineResult array, ops u32 array)"""
+        assert items.dtype == RefineItem and len(seqs) == len(quals)
+        n = len(items)
+        res = np.zeros(n, dtype=RefineResult)
+        cap = int((2 * items["len"].astype(np.int64) + 2 * items["k"].astype(np.int64) + 2).sum()) + 1
+        ops = np.zeros(cap, dtype=np.uint32); used = C.c_size_t(0)
+        sc = Scoring(*scoring)
+        items = np.ascontiguousarray(items)
+        _check(self.L.bmbs_refine(self.h, seqs, quals, len(seqs), items.ctypes.data, n, C.byref(sc), res.ctypes.data, ops.ctypes.data, cap, C.byref(used)))
+        return res, ops[: used.value]
+
+    def close(self):
+        if self.h:
+            self.L.bmbs_refiner_free(self.h); self.h = C.c_void_p()
 
     def __del__(self):
         try:

@@ -671,6 +671,104 @@ extern "C" int bmbs_verify(bmbs_index* idx, int dev, const char* seqs, const uin
   return bmbs_batch_download_verify(b, end_site, err, n);
 }
 
+// ================================================================================================ CIGAR refinement
+struct bmbs_refiner {
+  bmbs_index* idx = nullptr; const DeviceCopy* copy = nullptr; int dev = 0;
+  cudaStream_t stream = nullptr;
+  // device buffers, grown on demand
+  char* d_seq = nullptr; char* d_qual = nullptr; size_t cap_bytes = 0;
+  bmbs_refine_item* d_items = nullptr; bmbs_refine_result* d_res = nullptr; u64* d_dir_off = nullptr; u64* d_ops_off = nullptr; size_t cap_items = 0;
+  unsigned char* d_dir = nullptr; size_t cap_dir = 0;
+  u32* d_ops_scratch = nullptr; u32* d_ops_out = nullptr; size_t cap_ops = 0;
+  unsigned long long* d_total = nullptr;
+  // page-locked staging for the offsets and the counter
+  u64* h_off = nullptr; size_t cap_h_off = 0; unsigned long long* h_total = nullptr;
+};
+
+extern "C" int bmbs_refiner_create(bmbs_index* idx, int dev, bmbs_refiner** out) {
+  if (!idx || !out) return fail(BMBS_ERR_ARG, "null argument");
+  const DeviceCopy* copy = nullptr;
+  for (auto& c : idx->copies) if (c.dev == dev) copy = &c;
+  if (!copy) return fail(BMBS_ERR_ARG, "the index is not resident on device " + std::to_string(dev));
+  CU(cudaSetDevice(dev));
+  bmbs_refiner* r = new bmbs_refiner();
+  r->idx = idx; r->copy = copy; r->dev = dev;
+  CU(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+  CU(cudaMalloc(&r->d_total, 8));
+  CU(cudaMallocHost(&r->h_total, 8));
+  *out = r;
+  return BMBS_OK;
+}
+
+extern "C" void bmbs_refiner_free(bmbs_refiner* r) {
+  if (!r) return;
+  cudaSetDevice(r->dev);
+  cudaStreamSynchronize(r->stream);
+  cudaFree(r->d_seq); cudaFree(r->d_qual); cudaFree(r->d_items); cudaFree(r->d_res); cudaFree(r->d_dir_off); cudaFree(r->d_ops_off);
+  cudaFree(r->d_dir); cudaFree(r->d_ops_scratch); cudaFree(r->d_ops_out); cudaFree(r->d_total);
+  cudaFreeHost(r->h_off); cudaFreeHost(r->h_total);
+  cudaStreamDestroy(r->stream);
+  delete r;
+}
+
+extern "C" int bmbs_refine(bmbs_refiner* r, const char* seqs, const char* quals, size_t bytes, const bmbs_refine_item* items, size_t n,
+                           const bmbs_scoring* sc, bmbs_refine_result* res, uint32_t* ops, size_t ops_cap, size_t* ops_used) {
+  if (!r || !sc || (n && (!seqs || !quals || !items || !res))) return fail(BMBS_ERR_ARG, "null argument");
+  if (ops_used) *ops_used = 0;
+  if (n == 0) return BMBS_OK;
+  CU(cudaSetDevice(r->dev));
+  // per-item scratch: band x L direction bytes and 2L + 2k + 2 ops (the longest possible traceback)
+  if (2 * (n + 1) > r->cap_h_off) { cudaFreeHost(r->h_off); r->cap_h_off = 2 * (n + 1) + 1024; CU(cudaMallocHost(&r->h_off, r->cap_h_off * 8)); }
+  u64* dir_off = r->h_off; u64* ops_off = r->h_off + (n + 1);
+  u64 dir_total = 0, ops_total = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const bmbs_refine_item& q = items[i];
+    if (q.k > 31) return fail(BMBS_ERR_ARG, "k > 31");
+    if ((size_t)q.seq_off + q.len > bytes) return fail(BMBS_ERR_ARG, "item reaches past the end of seqs[]");
+    dir_off[i] = dir_total; ops_off[i] = ops_total;
+    dir_total += (u64)(2 * q.k + 1) * q.len; ops_total += 2ull * q.len + 2ull * q.k + 2;
+  }
+  dir_off[n] = dir_total; ops_off[n] = ops_total;
+  if (ops_total > 0xFFFFFFFFull) return fail(BMBS_ERR_CAPACITY, "too many alignments in one bmbs_refine call");
+  auto grow = [&](void** p, size_t& cap, size_t need, size_t elem) -> cudaError_t {
+    if (need <= cap) return cudaSuccess;
+    cudaFree(*p); *p = nullptr; cap = need + need / 2 + 1024;
+    return cudaMalloc(p, cap * elem);
+  };
+  if (bytes > r->cap_bytes) { cudaFree(r->d_seq); cudaFree(r->d_qual); r->d_seq = r->d_qual = nullptr; r->cap_bytes = bytes + bytes / 2 + 4096; CU(cudaMalloc(&r->d_seq, r->cap_bytes)); CU(cudaMalloc(&r->d_qual, r->cap_bytes)); }
+  if (n + 1 > r->cap_items) {
+    cudaFree(r->d_items); cudaFree(r->d_res); cudaFree(r->d_dir_off); cudaFree(r->d_ops_off);
+    r->cap_items = n + n / 2 + 1024;
+    CU(cudaMalloc(&r->d_items, r->cap_items * sizeof(bmbs_refine_item))); CU(cudaMalloc(&r->d_res, r->cap_items * sizeof(bmbs_refine_result)));
+    CU(cudaMalloc(&r->d_dir_off, r->cap_items * 8)); CU(cudaMalloc(&r->d_ops_off, r->cap_items * 8));
+  }
+  CU(grow((void**)&r->d_dir, r->cap_dir, (size_t)dir_total + 64, 1));
+  if (ops_total > r->cap_ops) {
+    cudaFree(r->d_ops_scratch); cudaFree(r->d_ops_out); r->d_ops_scratch = r->d_ops_out = nullptr;
+    r->cap_ops = (size_t)ops_total + (size_t)ops_total / 2 + 1024;
+    CU(cudaMalloc(&r->d_ops_scratch, r->cap_ops * 4)); CU(cudaMalloc(&r->d_ops_out, r->cap_ops * 4));
+  }
+  cudaStream_t s = r->stream;
+  CU(cudaMemcpyAsync(r->d_seq, seqs, bytes, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(r->d_qual, quals, bytes, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(r->d_items, items, n * sizeof(bmbs_refine_item), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(r->d_dir_off, dir_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(r->d_ops_off, ops_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(r->d_total, 0, 8, s));
+  RefineScoring rs{sc->mp_max, sc->mp_min, sc->n_pen, sc->gap_open, sc->gap_ext, sc->q_base};
+  refine_dp<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(r->copy->view, r->d_items, (u32)n, r->d_seq, r->d_qual, rs, r->d_dir, r->d_dir_off,
+                                                      r->d_ops_scratch, r->d_ops_off, r->d_res, r->d_ops_out, r->d_total, (u64)r->cap_ops);
+  CU(cudaMemcpyAsync(r->h_total, r->d_total, 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(res, r->d_res, n * sizeof(bmbs_refine_result), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  CU(cudaGetLastError());
+  const size_t used = (size_t)*r->h_total;
+  if (ops_used) *ops_used = used;
+  if (used > ops_cap) return fail(BMBS_ERR_CAPACITY, "ops[] holds " + std::to_string(ops_cap) + " entries, " + std::to_string(used) + " needed");
+  if (used) { if (!ops) return fail(BMBS_ERR_ARG, "ops is null"); CU(cudaMemcpyAsync(ops, r->d_ops_out, used * 4, cudaMemcpyDeviceToHost, s)); CU(cudaStreamSynchronize(s)); }
+  return BMBS_OK;
+}
+
 // ================================================================================================ integer-pipe peak
 // Denominator of the verification roofline: dependent-free LOP3 + IADD3 streams, 8 independent
 // chains per thread, every SM full.  Returns 32-bit integer ALU operations per second.

@@ -980,6 +980,104 @@ __global__ void verify_windows(DevIndex ix, BatchView b, int nch2) {
 }
 
 
+// ------------------------------------------------------------------------------------------- CIGAR refinement
+// ksw_semi_global_quality_back (ksw.cpp:1850-2045) as fast_recalculate_bs_Cigar uses it: semi-global banded (2k+1)
+// affine-gap alignment of the read against its window with traceback.  One thread per alignment -- the row recurrence
+// is a serial chain (h -> f -> h), alignments are independent, and a sub-block sends thousands of them; the H / E rows
+// live in a 128-entry ring per thread, the direction bytes (band x L) in global scratch.  Values and tie-breaks are the
+// reference's, cell by cell (every comparison below is written as it is there).
+struct RefineScoring { int mp_max, mp_min, n_pen, gap_open, gap_ext, q_base; };
+
+__device__ __forceinline__ int refine_nt4(char c) {
+  switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; }
+}
+
+__global__ void __launch_bounds__(64) refine_dp(DevIndex ix, const bmbs_refine_item* __restrict__ items, u32 n, const char* __restrict__ seqs,
+                                                const char* __restrict__ quals, RefineScoring sc, unsigned char* __restrict__ dir_all,
+                                                const u64* __restrict__ dir_off, u32* __restrict__ ops_scratch, const u64* __restrict__ ops_off,
+                                                bmbs_refine_result* __restrict__ res, u32* __restrict__ ops_out, unsigned long long* ops_total, u64 ops_cap) {
+  const u32 it = blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= n) return;
+  const bmbs_refine_item q = items[it];
+  const int rlen = q.len, k = q.k, band = 2 * k + 1, wlen = rlen + 2 * k;
+  const char* read = seqs + q.seq_off; const char* qual = quals + q.seq_off;
+  const int NEG = -0x40000000, goe = sc.gap_open + sc.gap_ext, ge = sc.gap_ext;
+  const bool inside = window_inside(ix, q.site, (u64)wlen);
+  int H[128], E[128];                                  // ring over window positions: row i touches j in [i, i + band], band <= 63
+  for (int j = 0; j < 128; ++j) { H[j] = NEG; E[j] = NEG; }
+  for (int j = 0; j < band; ++j) { H[j] = 0; E[j] = -goe; }
+  unsigned char* dir = dir_all + dir_off[it];
+  const uint2* gp = ix.planes + (q.site >> 5);
+  const unsigned sh0 = (unsigned)q.site & 31u;
+  int beg = 0, end = 0;
+  for (int i = 0; i < rlen; ++i) {
+    const int t = refine_nt4(read[i]);
+    double phred = (double)((int)qual[i] - sc.q_base);
+    if (phred > 40) phred = 40;
+    phred = phred / 40;
+    const int mism = -sc.mp_min - (int)((double)(signed char)(sc.mp_max - sc.mp_min) * phred);
+    beg = i; end = i + band;
+    // window bases [i, i + 64) as two 64-bit planes (code = lo | hi << 1: A0 C1 G2 T3)
+    u64 wlo = 0, whi = 0;
+    if (inside) {
+      const unsigned bit = sh0 + (unsigned)i;
+      const uint2* wp = gp + (bit >> 5); const unsigned s = bit & 31u;
+      const uint2 a = __ldg(wp), b2 = __ldg(wp + 1), c = __ldg(wp + 2);
+      wlo = (u64)__funnelshift_r(a.x, b2.x, s) | ((u64)__funnelshift_r(b2.x, c.x, s) << 32);
+      whi = (u64)__funnelshift_r(a.y, b2.y, s) | ((u64)__funnelshift_r(b2.y, c.y, s) << 32);
+    }
+    int f = NEG, left = NEG;
+    unsigned char* d_row = dir + (size_t)i * band;
+    for (int j = beg; j < end; ++j) {
+      const int jj = j - beg;
+      int m = H[j & 127], e = E[j & 127];
+      H[j & 127] = left;
+      const int qb = inside ? (int)(((wlo >> jj) & 1ull) | (((whi >> jj) & 1ull) << 1)) : 4;
+      int s;
+      if (t == 4 || qb == 4) s = -sc.n_pen;
+      else if (t == qb || (t == 3 && qb == 1)) s = 0;
+      else s = mism;
+      m += s;
+      unsigned char d = m >= e ? 0 : 1;
+      int h = m >= e ? m : e;
+      d = h >= f ? d : 2;
+      h = h >= f ? h : f;
+      left = h;
+      const int open = m - goe;
+      e -= ge;
+      if (e > open) d |= 1 << 2; else e = open;
+      E[j & 127] = e;
+      f -= ge;
+      if (f > open) d |= 2 << 4; else f = open;
+      d_row[jj] = d;
+    }
+    H[end & 127] = left; E[end & 127] = NEG;
+  }
+  int best = rlen + k;
+  int score = H[best & 127];
+  for (int j = end; j > beg; --j) if (H[j & 127] > score) { score = H[j & 127]; best = j; }
+  // traceback, ops pushed from the alignment end; written backwards so that they read in read order
+  u32* ops = ops_scratch + ops_off[it];
+  const u32 cap = (u32)(ops_off[it + 1] - ops_off[it]);
+  u32 n_ops = 0, cur = 0;                               // cur: the run being built, (len << 4) | op
+  auto push = [&](u32 op, u32 len) {
+    if (n_ops == 0 || (cur & 0xfu) != op) { if (n_ops) ops[cap - n_ops] = cur; cur = len << 4 | op; ++n_ops; } else cur += len << 4;
+  };
+  int i = rlen - 1, j = best - 1, state = 0;
+  while (i >= 0 && j >= 0) {
+    state = dir[(size_t)i * band + (j - i)] >> (state << 1) & 3;
+    if (state == 0) { push(0, 1); --i; --j; }
+    else if (state == 1) { push(2, 1); --i; }
+    else { push(1, 1); --j; }
+  }
+  if (i >= 0) push(2, (u32)(i + 1));
+  if (n_ops) ops[cap - n_ops] = cur;
+  const u64 at = atomicAdd(ops_total, (unsigned long long)n_ops);
+  if (at + n_ops <= ops_cap) for (u32 x = 0; x < n_ops; ++x) ops_out[at + x] = ops[cap - n_ops + x];
+  bmbs_refine_result r; r.score = score; r.qb = j + 1; r.qe = best - 1; r.n_ops = n_ops; r.ops_off = (u32)at;
+  res[it] = r;
+}
+
 // ------------------------------------------------------------------------------------------- sensitive pairing
 // select_suit_candidates (Schema.cpp:4775-4824): a verified hit of the mate within [dmin, dmax] of `site`?
 __device__ __forceinline__ bool mate_in_range(u64 site, const bmbs_cand* hits, int nh, int dmax, int dmin, int& next) {

@@ -158,19 +158,50 @@ void parse_batch(RawBatch& rb, bool pe, Batch& b) {
   }
 }
 
-void finish_batch(const HostContext& hc, Batch& b, bool pe) {
+// Finishing of one sub-block.  The banded DPs (alignments with indels) of the whole sub-block run on the GPU in one
+// bmbs_refine call: the first pass writes the SAM text of every unit that needs none and collects the requests of the
+// others, the second pass redoes only those units with the results, and their text is spliced back in input order.
+struct FinishScratch { std::vector<HostHit> v1, v2; std::vector<char> win; DpQueue dq; std::string side; std::vector<uint32_t> unit; std::vector<size_t> at, side_end; };
+
+void finish_batch(const HostContext& hc, Batch& b, bool pe, bmbs_refiner* refiner, FinishScratch& fs, long long& n_dp) {
   const int units = pe ? b.n / 2 : b.n;
-  std::vector<HostHit> v1, v2; std::vector<char> win;
   b.sam.clear(); b.sam.reserve((size_t)units * (pe ? 900 : 400));
-  for (int u = 0; u < units; ++u) {
+  DpQueue& dq = fs.dq; dq.clear();
+  fs.unit.clear(); fs.at.clear();
+  auto one = [&](int u, std::string& out, MapStats& st) {
     if (!pe) {
       ReadView rv{b.name[u], b.seq(u), b.qual[u]};
-      finish_single(hc, rv, b.res[u], b.cand.data(), b.sam, b.st, v1, win);
+      finish_single(hc, rv, b.res[u], b.cand.data(), out, st, fs.v1, fs.win, &dq);
     } else {
       finish_pair(hc, b.name[2 * u], b.seq(2 * u), b.qual[2 * u], b.name[2 * u + 1], b.seq(2 * u + 1), b.fq_seq[2 * u + 1], b.qual[2 * u + 1],
-                  b.res[2 * u], b.res[2 * u + 1], b.cand.data(), b.sam, b.st, v1, v2, win);
+                  b.res[2 * u], b.res[2 * u + 1], b.cand.data(), out, st, fs.v1, fs.v2, fs.win, &dq);
     }
+  };
+  auto add = [&](const MapStats& t) { b.st.reads += t.reads; b.st.unique += t.unique; b.st.ambiguous += t.ambiguous; b.st.bases += t.bases; b.st.err_bases += t.err_bases; };
+  for (int u = 0; u < units; ++u) {
+    const size_t mark = b.sam.size();
+    MapStats t; dq.pending = false;
+    one(u, b.sam, t);
+    if (dq.pending) { b.sam.resize(mark); fs.unit.push_back((uint32_t)u); fs.at.push_back(mark); } else add(t);
   }
+  if (fs.unit.empty()) return;
+  n_dp += (long long)dq.items.size();
+  dq.res.resize(dq.items.size()); dq.ops.resize(dq.ops_bound);
+  const bmbs_scoring sc{hc.sc.mp_max, hc.sc.mp_min, hc.sc.n_pen, hc.sc.gap_open, hc.sc.gap_ext, hc.sc.q_base};
+  size_t used = 0;
+  if (bmbs_refine(refiner, dq.seqs.data(), dq.quals.data(), dq.seqs.size(), dq.items.data(), dq.items.size(), &sc, dq.res.data(), dq.ops.data(), dq.ops.size(), &used))
+    die(std::string("gpu CIGAR refinement failed: ") + bmbs_last_error());
+  dq.mode = DpQueue::REPLAY; dq.next = 0;
+  fs.side.clear(); fs.side_end.clear();
+  for (uint32_t u : fs.unit) { MapStats t; one((int)u, fs.side, t); add(t); fs.side_end.push_back(fs.side.size()); }
+  std::string merged; merged.reserve(b.sam.size() + fs.side.size());
+  size_t from = 0, sfrom = 0;
+  for (size_t i = 0; i < fs.unit.size(); ++i) {
+    merged.append(b.sam, from, fs.at[i] - from); from = fs.at[i];
+    merged.append(fs.side, sfrom, fs.side_end[i] - sfrom); sfrom = fs.side_end[i];
+  }
+  merged.append(b.sam, from, std::string::npos);
+  b.sam.swap(merged);
 }
 
 void print_stats(FILE* f, const MapStats& st) {
@@ -285,9 +316,16 @@ int search(const Options& o, const std::string& cmdline) {
     bmbs_pinned_free(h_res); bmbs_pinned_free(h_cand);
     if (--live_gpu == 0) fin_q.close();
   });
-  for (int t = 0; t < n_finish; ++t) pool.emplace_back([&] {
+  std::atomic<long long> n_dp_total(0);
+  for (int t = 0; t < n_finish; ++t) pool.emplace_back([&, t] {
+    // each finishing thread owns a refiner (stream + device buffers) on one of the GPUs
+    bmbs_refiner* refiner = nullptr;
+    if (bmbs_refiner_create(idx, devs[t % devs.size()], &refiner)) die(std::string("refiner create: ") + bmbs_last_error());
+    FinishScratch fs; long long n_dp = 0;
     std::unique_ptr<Batch> b;
-    while (fin_q.pop(b)) { const double ts = now(); finish_batch(hc, *b, pe); us_finish += us(ts, now()); out_q.push(std::move(b)); }
+    while (fin_q.pop(b)) { const double ts = now(); finish_batch(hc, *b, pe, refiner, fs, n_dp); us_finish += us(ts, now()); out_q.push(std::move(b)); }
+    bmbs_refiner_free(refiner);
+    n_dp_total += n_dp;
     if (--live_finish == 0) out_q.close();
   });
 
@@ -313,8 +351,8 @@ int search(const Options& o, const std::string& cmdline) {
             us_prep / 1e6, us_up / 1e6, us_run / 1e6, us_down / 1e6, us_dev / 1e6, us_stage[1] / 1e6, us_stage[2] / 1e6, us_stage[3] / 1e6, us_stage[4] / 1e6, us_stage[5] / 1e6, us_stage[6] / 1e6, us_stage[7] / 1e6);
   }
   if (getenv("BMBS_TIMING"))
-    fprintf(stderr, "[bmbs timing] busy seconds summed over threads: split %.2f  parse %.2f (%d thr)  gpu %.2f (%d thr, %lld batches, %lld capacity retries)  finish %.2f (%d thr)  write %.2f\n",
-            us_split / 1e6, us_parse / 1e6, n_parse, us_gpu / 1e6, n_gpu, (long long)n_batches, (long long)n_retry, us_finish / 1e6, n_finish, us_write / 1e6);
+    fprintf(stderr, "[bmbs timing] busy seconds summed over threads: split %.2f  parse %.2f (%d thr)  gpu %.2f (%d thr, %lld batches, %lld capacity retries)  finish %.2f (%d thr, %lld banded DPs on the GPU)  write %.2f\n",
+            us_split / 1e6, us_parse / 1e6, n_parse, us_gpu / 1e6, n_gpu, (long long)n_batches, (long long)n_retry, us_finish / 1e6, n_finish, (long long)n_dp_total, us_write / 1e6);
   fclose(fo);
   const double t_map = now() - t1;
   bmbs_index_free(idx);

@@ -42,7 +42,7 @@ inline uint64_t threshold_k(double e_rate, size_t L) { uint64_t k = (uint64_t)(e
 
 // ---- single end -------------------------------------------------------------------------------
 inline void finish_single(const HostContext& hc, const ReadView& rd, const bmbs_read_result& res, const bmbs_cand* cand,
-                          std::string& out, MapStats& st, std::vector<HostHit>& hits, std::vector<char>& win) {
+                          std::string& out, MapStats& st, std::vector<HostHit>& hits, std::vector<char>& win, DpQueue* dq = nullptr) {
   const std::string_view seq = rd.seq, qual = rd.qual;
   const int L = (int)seq.size();
   const uint64_t k = threshold_k(hc.prm.e_rate, L);
@@ -92,7 +92,7 @@ inline void finish_single(const HostContext& hc, const ReadView& rd, const bmbs_
   if (b.err != 0) {
     const int plen = L + 2 * (int)k; win.resize(plen + 8);
     hc.genome.window(b.site, plen, win.data());
-    refine_alignment(win.data(), plen, seq.data(), L, (int)k, (int)b.end_site, b.err, b.site < hc.chroms.N, qual.data(), false, hc.sc, rf);
+    refine_alignment(win.data(), plen, seq.data(), L, (int)k, (int)b.end_site, b.err, b.site < hc.chroms.N, qual.data(), false, hc.sc, rf, b.site, dq);
   } else { rf.score = 0; rf.start_site = (int)b.end_site - L + 1; rf.end_site = b.end_site; rf.err = 0; rf.cigar = std::to_string(L) + "M"; }
   const int mapq = mapq_from(sbd, (unsigned)k, rf.score, hc.sc);
   if (emit(b.site, rf.end_site, rf.start_site, rf.err, rf.cigar, mapq)) { ++st.unique; st.bases += L; st.err_bases += rf.err; }
@@ -145,7 +145,7 @@ inline Pick pick(const std::vector<HostHit>& a, int na, const std::vector<HostHi
 }
 struct Mate { int flag = 0; size_t chrom = 0; uint64_t pos = 0; unsigned err = 0; int score = 0, span = 0; std::string cigar; };
 inline void finish_mate(const HostContext& hc, std::string_view seq, std::string_view qual, uint64_t k, const HostHit& h,
-                        bool reverse_quality, Mate& m, std::vector<char>& win) {
+                        bool reverse_quality, Mate& m, std::vector<char>& win, DpQueue* dq) {
   const int L = (int)seq.size();
   int start; uint64_t end = h.end_site;
   m.err = h.err;
@@ -153,7 +153,7 @@ inline void finish_mate(const HostContext& hc, std::string_view seq, std::string
     const int plen = L + 2 * (int)k; win.resize(plen + 8);
     hc.genome.window(h.site, plen, win.data());
     Refined rf;
-    refine_alignment(win.data(), plen, seq.data(), L, (int)k, (int)h.end_site, h.err, h.site < hc.chroms.N, qual.data(), reverse_quality, hc.sc, rf);
+    refine_alignment(win.data(), plen, seq.data(), L, (int)k, (int)h.end_site, h.err, h.site < hc.chroms.N, qual.data(), reverse_quality, hc.sc, rf, h.site, dq);
     end = rf.end_site; m.err = rf.err; m.score = rf.score; m.cigar = rf.cigar; start = rf.start_site;
     m.span = (int)(end - start + 1);
   } else { m.score = 0; start = (int)(h.end_site + 1 - L); m.cigar = std::to_string(L) + "M"; m.span = L; }
@@ -166,7 +166,7 @@ inline void finish_mate(const HostContext& hc, std::string_view seq, std::string
 inline void finish_pair(const HostContext& hc, std::string_view name1, std::string_view seq1, std::string_view qual1,
                         std::string_view name2, std::string_view seq2, std::string_view raw2, std::string_view qual2,
                         const bmbs_read_result& r1, const bmbs_read_result& r2, const bmbs_cand* cand,
-                        std::string& out, MapStats& st, std::vector<HostHit>& v1, std::vector<HostHit>& v2, std::vector<char>& win) {
+                        std::string& out, MapStats& st, std::vector<HostHit>& v1, std::vector<HostHit>& v2, std::vector<char>& win, DpQueue* dq = nullptr) {
   ++st.reads;
   const int L1 = (int)seq1.size(), L2 = (int)seq2.size();
   const uint64_t k1 = threshold_k(hc.prm.e_rate, L1), k2 = threshold_k(hc.prm.e_rate, L2), kl = k1 > k2 ? k1 : k2;
@@ -196,8 +196,8 @@ inline void finish_pair(const HostContext& hc, std::string_view name1, std::stri
   if (pk.n > 1) { ++st.ambiguous; return; }
   if (pk.n != 1) return;
   pe::Mate m1, m2;
-  pe::finish_mate(hc, seq1, qual1, k1, v1[pk.i1], false, m1, win);
-  pe::finish_mate(hc, seq2, qual2, k2, v2[pk.i2], true, m2, win);
+  pe::finish_mate(hc, seq1, qual1, k1, v1[pk.i1], false, m1, win, dq);
+  pe::finish_mate(hc, seq2, qual2, k2, v2[pk.i2], true, m2, win, dq);
   long long lo = (long long)std::min(m1.pos, m2.pos), hi = std::max((long long)m1.pos + m1.span - 1, (long long)m2.pos + m2.span - 1);
   const int tlen = (int)(hi - lo + 1);                     // calculate_TLEN, Schema.h:1587-1600
   if (!(tlen <= hc.prm.max_ins && tlen >= hc.prm.min_ins)) return;

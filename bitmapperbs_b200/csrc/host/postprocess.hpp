@@ -18,6 +18,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include "../../../include/bmbs.h"
 
 namespace bmbs {
 
@@ -215,13 +216,25 @@ inline void banded_affine_align(const char* win, int wlen, const char* read, int
   qb = j + 1;
 }
 
+// Where the banded DP of refine_alignment runs.  The mapper sends a whole sub-block's DPs to the GPU in one bmbs_refine
+// call: a first pass over the sub-block COLLECTs the requests (the unit that asked is marked pending and re-done later),
+// a second pass REPLAYs the results in the same order.  Without a queue the DP runs here on the CPU (oracle, tests).
+struct DpQueue {
+  enum Mode { COLLECT = 1, REPLAY = 2 };
+  int mode = COLLECT;
+  bool pending = false;                                 // COLLECT: the current unit asked for a DP
+  std::string seqs, quals; std::vector<bmbs_refine_item> items; size_t ops_bound = 0;
+  std::vector<bmbs_refine_result> res; std::vector<uint32_t> ops; size_t next = 0;   // REPLAY
+  void clear() { mode = COLLECT; pending = false; seqs.clear(); quals.clear(); items.clear(); ops_bound = 0; res.clear(); ops.clear(); next = 0; }
+};
+
 // CIGAR / NM / score / start / end of the best hit, given the verifier's
 // (end_site, err).  `qual` is the quality string in FASTQ order; mate 2 of a
 // pair is aligned as its reverse complement, so its qualities are reversed
 // (reverse_quality) for the DP and restored.
 inline void refine_alignment(const char* win, int wlen, const char* read, int rlen, int k,
                              int end_site, unsigned err, bool forward, const char* qual_in,
-                             bool reverse_quality, const Scoring& sc, Refined& out) {
+                             bool reverse_quality, const Scoring& sc, Refined& out, uint64_t site = 0, DpQueue* dq = nullptr) {
   out.cigar.clear();
   if (err == 0) {
     out.score = 0; out.start_site = end_site - rlen + 1; out.end_site = end_site; out.err = 0;
@@ -247,7 +260,18 @@ inline void refine_alignment(const char* win, int wlen, const char* read, int rl
     }
   }
   int score, qb, qe; std::vector<uint32_t> ops;
-  banded_affine_align(win, wlen, read, rlen, k, qual.data(), sc, score, qb, qe, ops);
+  if (!dq) banded_affine_align(win, wlen, read, rlen, k, qual.data(), sc, score, qb, qe, ops);
+  else if (dq->mode == DpQueue::COLLECT) {
+    bmbs_refine_item it; it.site = site; it.seq_off = (uint32_t)dq->seqs.size(); it.len = (uint16_t)rlen; it.k = (uint8_t)k; it.pad = 0;
+    dq->seqs.append(read, (size_t)rlen); dq->quals.append(qual.data(), (size_t)rlen); dq->items.push_back(it);
+    dq->ops_bound += 2 * (size_t)rlen + 2 * (size_t)k + 2;
+    dq->pending = true;
+    out.score = 0; out.start_site = end_site - rlen + 1; out.end_site = end_site; out.err = err; out.cigar = "*";   // placeholder, the unit is redone
+    return;
+  } else {
+    const bmbs_refine_result& r = dq->res[dq->next++];
+    score = r.score; qb = r.qb; qe = r.qe; ops.assign(dq->ops.begin() + r.ops_off, dq->ops.begin() + r.ops_off + r.n_ops);
+  }
   const int n = (int)ops.size();
   // leading / trailing insertions become matches (the read is end-to-end)
   int i = 0, ins = 0;

@@ -4,7 +4,7 @@
 #
 #   oracle/_ref/bitmapperBS  the reference CLI (SE / PE / PE --sensitive, SAM text)
 #   oracle/_ref/psascan      suffix-sorter stand-in the reference shells out to in --index
-#   oracle/_ref/libref_bpm.so, libref_fm.so   C entry points into the reference's own BPM / FM-index functions
+#   oracle/_ref/libref_bpm.so, libref_fm.so, libref_ksw.so   C entry points into the reference's own BPM / FM-index / CIGAR functions
 #
 # Nothing from /root/reference is copied into the repo: sources are copied to a
 # scratch dir under /tmp, the 43 missing-`return` sites (UB that crashes an -O3
@@ -20,7 +20,7 @@ REF="${BMBS_REFERENCE:-/root/reference}"
 OUT="$HERE/_ref"
 [ -d "$REF" ] || { echo "build_ref: $REF absent (GPU box?) - keeping prebuilt $OUT" >&2; exit 0; }
 mkdir -p "$OUT"
-if [ -x "$OUT/bitmapperBS" ] && [ -x "$OUT/psascan" ] && [ -f "$OUT/libref_bpm.so" ] && [ -f "$OUT/libref_fm.so" ] && [ "${1:-}" != "--force" ]; then
+if [ -x "$OUT/bitmapperBS" ] && [ -x "$OUT/psascan" ] && [ -f "$OUT/libref_bpm.so" ] && [ -f "$OUT/libref_fm.so" ] && [ -f "$OUT/libref_ksw.so" ] && [ "${1:-}" != "--force" ]; then
   echo "build_ref: $OUT up to date"; exit 0
 fi
 TMP="$(mktemp -d /tmp/bmbs_refbuild.XXXXXX)"
@@ -38,4 +38,5 @@ g++ -O2 -std=c++17 -pthread "$HERE/psascan_shim.cpp" -o "$OUT/psascan"
 # function-level harnesses over the reference's own headers / sources
 g++ -w -O3 -mavx2 -mpopcnt -D__AVX2__ -shared -fPIC -pthread -I "$REF" "$HERE/ref_harness_bpm.cpp" -o "$OUT/libref_bpm.so"
 ( cd "$TMP" && g++ -w -O2 -mpopcnt -shared -fPIC -I "$TMP" "$HERE/ref_harness_fm.cpp" bwt.cpp saca-k.cpp -o "$OUT/libref_fm.so" )
-echo "build_ref: built $OUT/{bitmapperBS,psascan,libref_bpm.so,libref_fm.so}"
+( cd "$TMP" && g++ -w -O2 -msse4.1 -mpopcnt -shared -fPIC -I "$TMP" "$HERE/ref_harness_ksw.cpp" ksw.cpp -o "$OUT/libref_ksw.so" )
+echo "build_ref: built $OUT/{bitmapperBS,psascan,libref_bpm.so,libref_fm.so,libref_ksw.so}"

@@ -143,4 +143,31 @@ int orc_verify(void* h, const char* seqs, const uint64_t* offs, int n_reads, con
   return 0;
 }
 
+// CIGAR refinement of one alignment on the CPU (host/postprocess.hpp refine_alignment, the restatement of
+// fast_recalculate_bs_Cigar, ksw.cpp:2578-3148); window given as decoded characters
+int orc_refine(const char* win, int wlen, const char* read, int rlen, int k, int end_site, unsigned err, int forward, const char* qual,
+               int reverse_quality, int mp_max, int mp_min, int n_pen, int gap_open, int gap_ext, int q_base,
+               int* start_site, uint64_t* out_end, unsigned* out_err, int* score, char* cigar, int cigar_cap) {
+  bmbs::Scoring sc; sc.mp_max = mp_max; sc.mp_min = mp_min; sc.n_pen = n_pen; sc.gap_open = gap_open; sc.gap_ext = gap_ext; sc.q_base = q_base;
+  bmbs::Refined rf;
+  bmbs::refine_alignment(win, wlen, read, rlen, k, end_site, err, forward != 0, qual, reverse_quality != 0, sc, rf);
+  *start_site = rf.start_site; *out_end = rf.end_site; *out_err = rf.err; *score = rf.score;
+  snprintf(cigar, (size_t)cigar_cap, "%s", rf.cigar.c_str());
+  return 0;
+}
+// the banded DP alone (banded_affine_align = ksw_semi_global_quality_back, ksw.cpp:1850-2045) on the window at `site`:
+// what the refine_dp kernel must reproduce value for value
+int orc_banded_align(void* h, uint64_t site, const char* read, const char* qual, int rlen, int k, int mp_max, int mp_min, int n_pen, int gap_open,
+                     int gap_ext, int q_base, int* score, int* qb, int* qe, uint32_t* ops, int ops_cap) {
+  bmbs::Scoring sc; sc.mp_max = mp_max; sc.mp_min = mp_min; sc.n_pen = n_pen; sc.gap_open = gap_open; sc.gap_ext = gap_ext; sc.q_base = q_base;
+  const int wlen = rlen + 2 * k;
+  std::vector<char> win((size_t)wlen + 8);
+  ((Index*)h)->genome.window(site, (uint64_t)wlen, win.data());
+  std::vector<uint32_t> o;
+  bmbs::banded_affine_align(win.data(), wlen, read, rlen, k, qual, sc, *score, *qb, *qe, o);
+  if ((int)o.size() > ops_cap) return -1;
+  for (size_t i = 0; i < o.size(); ++i) ops[i] = o[i];
+  return (int)o.size();
+}
+
 }  // extern "C"

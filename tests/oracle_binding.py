@@ -28,6 +28,7 @@ def lib():
         L.orc_map_pe.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.orc_map_pe_sensitive.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_size_t), vp]
         L.orc_verify.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_size_t, C.c_double, vp, vp, C.c_int]
+        L.orc_banded_align.argtypes = [vp, C.c_uint64, C.c_char_p, C.c_char_p] + [C.c_int] * 8 + [C.POINTER(C.c_int)] * 3 + [vp, C.c_int]
         _lib = L
     return _lib
 
@@ -79,3 +80,13 @@ class OracleIndex:
         end = np.zeros(n, dtype=np.int32); err = np.zeros(n, dtype=np.uint32)
         lib().orc_verify(self.h, flat.ctypes.data, offs.ctypes.data, len(offs) - 1, read_idx.ctypes.data, sites.ctypes.data, n, e_rate, end.ctypes.data, err.ctypes.data, threads)
         return end, err
+
+
+def banded_align(oidx, site, read: bytes, qual: bytes, k, scoring=(6, 2, 1, 5, 3, 33)):
+    """CPU banded affine-gap DP with traceback (host/postprocess.hpp banded_affine_align) on the window at `site`:
+    (score, qb, qe, ops) -- what bmbs_refine must return value for value"""
+    score, qb, qe = C.c_int(), C.c_int(), C.c_int()
+    ops = np.zeros(2 * len(read) + 2 * k + 2, dtype=np.uint32)
+    n = lib().orc_banded_align(oidx.h, int(site), read, qual, len(read), int(k), *scoring, C.byref(score), C.byref(qb), C.byref(qe), ops.ctypes.data, len(ops))
+    assert n >= 0
+    return score.value, qb.value, qe.value, ops[:n].copy()

@@ -5,7 +5,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <algorithm>
+#include <atomic>
 #include <string>
 #include <thread>
 #include <vector>
@@ -30,14 +35,42 @@ template <class F> void parallel_for(u64 n, F fn) {
   for (auto& x : th) x.join();
 }
 
-template <class T> bool read_vec(FILE* f, std::vector<T>& v, size_t n) { v.resize(n); return n == 0 || fread(v.data(), sizeof(T), n, f) == n; }
+// The index files are mapped, not read: the arrays go from the page cache straight to the device, where they are
+// re-laid out; nothing is copied or converted on the host.
+struct MappedFile {
+  char* p = nullptr; size_t size = 0;
+  bool open(const std::string& path) {
+    const int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size <= 0) { ::close(fd); return false; }
+    void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd);
+    if (m == MAP_FAILED) return false;
+    p = (char*)m; size = (size_t)st.st_size;
+    madvise(p, size, MADV_WILLNEED);
+    return true;
+  }
+  ~MappedFile() { if (p) munmap(p, size); }
+};
+template <class T> struct Span { const T* p = nullptr; size_t n = 0; size_t bytes() const { return n * sizeof(T); } };
 
 struct HostIndex {
   u64 sa_length = 0, shapline = 0, nacgt[5] = {0, 0, 0, 0, 0}, N = 0;
-  std::vector<u64> bwt, high_occ, sa_flag;
-  std::vector<u32> hash_hi, ssa;
-  std::vector<uint8_t> hash_lo, pac;
+  MappedFile f_pac, f_bwt, f_sa, f_occ;
+  Span<u64> bwt, high_occ, sa_flag;
+  Span<u32> hash_hi, ssa;
+  Span<uint8_t> hash_lo, pac;
 };
+
+// u64 count followed by `count` elements at `off`; advances off
+template <class T> bool take(const MappedFile& f, size_t& off, Span<T>& out) {
+  if (off + 8 > f.size) return false;
+  u64 n; memcpy(&n, f.p + off, 8); off += 8;
+  if (n > (f.size - off) / sizeof(T)) return false;
+  out.p = (const T*)(f.p + off); out.n = (size_t)n; off += (size_t)n * sizeof(T);
+  return true;
+}
 
 int load_files(const std::string& prefix, HostIndex& h) {
   FILE* f = fopen(prefix.c_str(), "rb");
@@ -46,30 +79,38 @@ int load_files(const std::string& prefix, HostIndex& h) {
   for (u64 i = 0; ok && i < nc; ++i) { u64 l = 0, cl = 0; ok = fread(&l, 8, 1, f) == 1 && fseek(f, (long)l, SEEK_CUR) == 0 && fread(&cl, 8, 1, f) == 1; }
   ok = ok && fread(&h.N, 8, 1, f) == 1; fclose(f);
   if (!ok) return fail(BMBS_ERR_IO, "short read in " + prefix);
-  f = fopen((prefix + ".bs.pac").c_str(), "rb");
-  if (!f) return fail(BMBS_ERR_IO, "cannot open " + prefix + ".bs.pac");
-  u64 n = 0; ok = fread(&n, 8, 1, f) == 1 && read_vec(f, h.pac, n); fclose(f);
-  if (!ok || n < (h.N + 3) / 4) return fail(BMBS_ERR_IO, "short read in " + prefix + ".bs.pac");
+  if (!h.f_pac.open(prefix + ".bs.pac")) return fail(BMBS_ERR_IO, "cannot open " + prefix + ".bs.pac");
+  size_t off = 0;
+  if (!take(h.f_pac, off, h.pac) || h.pac.n < (h.N + 3) / 4) return fail(BMBS_ERR_IO, "short read in " + prefix + ".bs.pac");
   const std::string p = prefix + ".bs.index";
   f = fopen(p.c_str(), "rb");
   if (!f) return fail(BMBS_ERR_IO, "cannot open " + p);
   ok = fread(&h.sa_length, 8, 1, f) == 1 && fread(&h.shapline, 8, 1, f) == 1 && fread(h.nacgt, 8, 5, f) == 5; fclose(f);
   if (!ok) return fail(BMBS_ERR_IO, "short read in " + p);
-  f = fopen((p + ".bwt").c_str(), "rb");
-  if (!f) return fail(BMBS_ERR_IO, "cannot open " + p + ".bwt");
-  ok = fread(&n, 8, 1, f) == 1 && read_vec(f, h.bwt, n);
-  ok = ok && fread(&n, 8, 1, f) == 1 && read_vec(f, h.hash_hi, n) && read_vec(f, h.hash_lo, n); fclose(f);
-  if (!ok) return fail(BMBS_ERR_IO, "short read in " + p + ".bwt");
-  f = fopen((p + ".sa").c_str(), "rb");
-  if (!f) return fail(BMBS_ERR_IO, "cannot open " + p + ".sa");
-  ok = fread(&n, 8, 1, f) == 1 && read_vec(f, h.ssa, n);
-  ok = ok && fread(&n, 8, 1, f) == 1 && read_vec(f, h.sa_flag, n); fclose(f);
-  if (!ok) return fail(BMBS_ERR_IO, "short read in " + p + ".sa");
-  f = fopen((p + ".occ").c_str(), "rb");
-  if (!f) return fail(BMBS_ERR_IO, "cannot open " + p + ".occ");
-  ok = fread(&n, 8, 1, f) == 1 && read_vec(f, h.high_occ, n); fclose(f);
-  if (!ok) return fail(BMBS_ERR_IO, "short read in " + p + ".occ");
+  if (!h.f_bwt.open(p + ".bwt")) return fail(BMBS_ERR_IO, "cannot open " + p + ".bwt");
+  off = 0;
+  if (!take(h.f_bwt, off, h.bwt)) return fail(BMBS_ERR_IO, "short read in " + p + ".bwt");
+  {   // u64 n; u32 hi[n]; u8 lo[n]
+    if (off + 8 > h.f_bwt.size) return fail(BMBS_ERR_IO, "short read in " + p + ".bwt");
+    u64 n; memcpy(&n, h.f_bwt.p + off, 8); off += 8;
+    if (n > (h.f_bwt.size - off) / 5) return fail(BMBS_ERR_IO, "short read in " + p + ".bwt");
+    h.hash_hi.p = (const u32*)(h.f_bwt.p + off); h.hash_hi.n = (size_t)n; off += (size_t)n * 4;
+    h.hash_lo.p = (const uint8_t*)(h.f_bwt.p + off); h.hash_lo.n = (size_t)n;
+  }
+  if (!h.f_sa.open(p + ".sa")) return fail(BMBS_ERR_IO, "cannot open " + p + ".sa");
+  off = 0;
+  if (!take(h.f_sa, off, h.ssa) || !take(h.f_sa, off, h.sa_flag)) return fail(BMBS_ERR_IO, "short read in " + p + ".sa");
+  if (!h.f_occ.open(p + ".occ")) return fail(BMBS_ERR_IO, "cannot open " + p + ".occ");
+  off = 0;
+  if (!take(h.f_occ, off, h.high_occ)) return fail(BMBS_ERR_IO, "short read in " + p + ".occ");
   if (h.sa_length != 2 * h.N + 1) return fail(BMBS_ERR_IO, "index header does not match the genome length");
+  // fault the mappings in with a few threads (the driver's pageable copy would otherwise take the page faults one by one)
+  const MappedFile* files[4] = {&h.f_pac, &h.f_bwt, &h.f_sa, &h.f_occ};
+  for (const MappedFile* mf : files) {
+    const size_t pages = (mf->size + 4095) / 4096;
+    std::atomic<unsigned> sink(0);
+    parallel_for(pages, [&](u64 lo, u64 hi) { unsigned x = 0; for (u64 i = lo; i < hi; ++i) x += (unsigned char)mf->p[i * 4096]; sink += x; });
+  }
   return BMBS_OK;
 }
 
@@ -106,6 +147,60 @@ __global__ void __launch_bounds__(128) build_ktab(DevIndex ix, u64* table, u32 n
     u64 top, bot; hash_query(ix, key, top, bot);
     if (bot <= top) ktab_fill(t, 0, 1, leaves, 0ull);
     else ktab_node<D>(ix, t, 0, 1, 16, top, bot);
+  }
+}
+
+// ---- re-layout of the on-disk arrays, on the device (formats: SURVEY.md 8a D1-D7)
+// occ blocks: fold the 65536-row table and the 16-bit counters of the 40-byte superblocks (bwt.h:1007-1058) into absolute counts
+__global__ void relayout_occ(const u64* __restrict__ bwt, u64 bwt_words, const u64* __restrict__ high_occ, u64 high_words, u64 nblk, u64* __restrict__ occ) {
+  for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < nblk; b += (u64)gridDim.x * blockDim.x) {
+    const u64 sb = (b >> 1) * 5, sub = b & 1, w = sb + 1 + 2 * sub, hi_i = ((b << 6) >> 16) * 2;
+    u64 o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+    if (w + 1 < bwt_words && hi_i + 1 < high_words) {
+      const u64 hdr = bwt[sb];
+      o0 = bwt[w]; o1 = bwt[w + 1];
+      o2 = high_occ[hi_i] + ((hdr >> (48 - 32 * sub)) & 0xFFFF);
+      o3 = high_occ[hi_i + 1] + ((hdr >> (32 - 32 * sub)) & 0xFFFF);
+    }
+    occ[b * 4] = o0; occ[b * 4 + 1] = o1; occ[b * 4 + 2] = o2; occ[b * 4 + 3] = o3;
+  }
+}
+// flag blocks of 64 rows with the rank of the block start (reference: 5 words per 256 rows, bwt.h:2449-2560).  The flag file's
+// last word is uninitialised in reference-built indexes (bwt.cpp:1188-1192 vs :1657-1664): bits beyond the last row are masked.
+__global__ void relayout_flag(const u64* __restrict__ sa_flag, u64 flag_words, u64 nfb, u64 last_row, u64* __restrict__ flag) {
+  for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < nfb; b += (u64)gridDim.x * blockDim.x) {
+    const u64 g = (b >> 2) * 5, in = b & 3;
+    u64 bits = 0, rank = 0;
+    if (g + 1 + in < flag_words) {
+      rank = sa_flag[g];
+      for (u64 t = 0; t < in; ++t) rank += (u64)__popcll(sa_flag[g + 1 + t]);
+      bits = sa_flag[g + 1 + in];
+    }
+    const u64 lb = last_row >> 6, used = (last_row & 63) + 1;
+    if (b == lb && used < 64) bits &= ~0ull << (64 - used);
+    if (b > lb) bits = 0;
+    flag[b * 2] = bits; flag[b * 2 + 1] = rank;
+  }
+}
+// 16-mer table: u32 + u8 per entry (bwt.h:284-306) -> one u64
+__global__ void relayout_hash(const u32* __restrict__ hi, const unsigned char* __restrict__ lo, u64 n, u64* __restrict__ hash) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+    hash[i] = ((u64)(hi[i] & 0x0FFFFFFFu) << 8) | lo[i] | ((u64)(hi[i] >> 28) << 60);
+}
+// bit-planes of G ++ revcomp(G) from the 2-bit genome (Index.cpp:734-831: four bases per byte, first base in the top bits)
+__global__ void relayout_planes(const unsigned char* __restrict__ pac, u64 N, u64 n_words, uint2* __restrict__ planes) {
+  const u64 n = 2 * N;
+  for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (u64)gridDim.x * blockDim.x) {
+    u32 x = 0, y = 0;
+    for (u32 t = 0; t < 32; ++t) {
+      const u64 pos = w * 32 + t;
+      if (pos >= n) break;
+      u32 c;
+      if (pos < N) c = (pac[pos >> 2] >> (6 - 2 * (pos & 3))) & 3;
+      else { const u64 i = n - 1 - pos; c = 3 - ((pac[i >> 2] >> (6 - 2 * (i & 3))) & 3); }
+      x |= (c & 1u) << t; y |= (c >> 1) << t;
+    }
+    planes[w] = make_uint2(x, y);
   }
 }
 
@@ -150,72 +245,10 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
   std::thread warm([=] { for (int d = 0; d < n_dev; ++d) { cudaSetDevice(devices[d]); cudaFree(0); } });
   int rc = load_files(index_prefix, h);
   if (rc) { warm.join(); return rc; }
-  lap("read index files");
+  lap("map index files");
   const u64 n = 2 * h.N;                       // text length = BWT symbols
-  // ---- occ blocks: fold the 65536-row table and the 16-bit counters into absolute counts
-  const u64 nblk = (n >> 6) + 2;
-  std::vector<u64> occ(nblk * 4, 0);
-  h.bwt.resize(h.bwt.size() + 16, 0);
-  parallel_for(nblk, [&](u64 lo, u64 hi) {
-    for (u64 b = lo; b < hi; ++b) {
-      const u64 sb = (b >> 1) * 5, sub = b & 1, w = sb + 1 + 2 * sub, hi_i = ((b << 6) >> 16) * 2;
-      if (w + 1 >= h.bwt.size() || hi_i + 1 >= h.high_occ.size()) break;
-      const u64 hdr = h.bwt[sb];
-      occ[b * 4 + 0] = h.bwt[w];
-      occ[b * 4 + 1] = h.bwt[w + 1];
-      occ[b * 4 + 2] = h.high_occ[hi_i] + ((hdr >> (48 - 32 * sub)) & 0xFFFF);
-      occ[b * 4 + 3] = h.high_occ[hi_i + 1] + ((hdr >> (32 - 32 * sub)) & 0xFFFF);
-    }
-  });
-  std::vector<u64>().swap(h.bwt);
-  // ---- flag blocks: 64 rows each, with the rank of the block start
-  const u64 nfb = (h.sa_length >> 6) + 2;
-  std::vector<u64> flag(nfb * 2, 0);
-  h.sa_flag.resize(h.sa_flag.size() + 16, 0);
-  parallel_for(nfb, [&](u64 lo, u64 hi) {
-    for (u64 b = lo; b < hi; ++b) {
-      const u64 g = (b >> 2) * 5, in = b & 3;
-      if (g + 1 + in >= h.sa_flag.size()) break;
-      u64 rank = h.sa_flag[g];
-      for (u64 t = 0; t < in; ++t) rank += __builtin_popcountll(h.sa_flag[g + 1 + t]);
-      flag[b * 2] = h.sa_flag[g + 1 + in];
-      flag[b * 2 + 1] = rank;
-    }
-  });
-  // the flag file's last word is uninitialised in reference-built indexes (reads past its allocation,
-  // bwt.cpp:1188-1192 vs :1657-1664); it lies beyond the last row and is masked here
-  {
-    const u64 last_row = h.sa_length - 1, b = last_row >> 6, used = (last_row & 63) + 1;
-    if (used < 64) flag[b * 2] &= ~0ull << (64 - used);
-    for (u64 bb = b + 1; bb < nfb; ++bb) flag[bb * 2] = 0;
-  }
-  std::vector<u64>().swap(h.sa_flag);
-  // ---- 16-mer table: one u64 per entry
-  const size_t nh = h.hash_hi.size();
-  std::vector<u64> hash(nh + 2, 0);
-  parallel_for(nh, [&](u64 lo, u64 hi) {
-    for (u64 i = lo; i < hi; ++i) hash[i] = ((u64)(h.hash_hi[i] & 0x0FFFFFFFu) << 8) | h.hash_lo[i] | ((u64)(h.hash_hi[i] >> 28) << 60);
-  });
-  std::vector<u32>().swap(h.hash_hi); std::vector<uint8_t>().swap(h.hash_lo);
-  // ---- bit-planes of G ++ revcomp(G)
-  const u64 npw = (n + 31) / 32 + 64;
-  std::vector<uint2> planes(npw, make_uint2(0, 0));
-  parallel_for((n + 31) / 32, [&](u64 lo, u64 hi) {        // one 32-base word at a time: forward strand, then the reverse complement
-    for (u64 w = lo; w < hi; ++w) {
-      u32 x = 0, y = 0;
-      for (u32 t = 0; t < 32; ++t) {
-        const u64 pos = w * 32 + t;
-        if (pos >= n) break;
-        u32 c;
-        if (pos < h.N) c = (h.pac[pos >> 2] >> (6 - 2 * (pos & 3))) & 3;
-        else { const u64 i = n - 1 - pos; c = 3 - ((h.pac[i >> 2] >> (6 - 2 * (i & 3))) & 3); }
-        x |= (c & 1u) << t; y |= (c >> 1) << t;
-      }
-      planes[w] = make_uint2(x, y);
-    }
-  });
-  std::vector<uint8_t>().swap(h.pac);
-  lap("host re-layout");
+  const u64 nblk = (n >> 6) + 2, nfb = (h.sa_length >> 6) + 2, npw = (n + 31) / 32 + 64;
+  const size_t nh = h.hash_hi.n;
 
   bmbs_index* idx = new bmbs_index();
   idx->N = h.N;
@@ -223,16 +256,37 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
   lap("(wait for the CUDA context)");
   for (int d = 0; d < n_dev; ++d) {
     DeviceCopy c; c.dev = devices[d];
-    auto up = [&](void** p, const void* src, size_t bytes) -> cudaError_t {
-      cudaError_t e = cudaMalloc(p, bytes); if (e != cudaSuccess) return e;
-      c.bytes += bytes; return cudaMemcpy(*p, src, bytes, cudaMemcpyHostToDevice);
-    };
     cudaError_t e = cudaSetDevice(c.dev);
-    if (e == cudaSuccess) e = up(&c.occ, occ.data(), occ.size() * 8);
-    if (e == cudaSuccess) e = up(&c.flag, flag.data(), flag.size() * 8);
-    if (e == cudaSuccess) e = up(&c.hash, hash.data(), hash.size() * 8);
-    if (e == cudaSuccess) e = up(&c.ssa, h.ssa.data(), h.ssa.size() * 4);
-    if (e == cudaSuccess) e = up(&c.planes, planes.data(), planes.size() * 8);
+    cudaDeviceProp prop; if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, c.dev);
+    const int grid = e == cudaSuccess ? prop.multiProcessorCount * 16 : 1;
+    // raw file arrays -> device (16 zero words of slack behind bwt and sa_flag, as the re-layout reads a little past the end)
+    void *r_bwt = nullptr, *r_high = nullptr, *r_flag = nullptr, *r_hi = nullptr, *r_lo = nullptr, *r_pac = nullptr;
+    auto raw = [&](void** p, const void* src, size_t bytes, size_t slack) -> cudaError_t {
+      cudaError_t x = cudaMalloc(p, bytes + slack + 16); if (x != cudaSuccess) return x;
+      if (slack) { x = cudaMemset((char*)*p + bytes, 0, slack); if (x != cudaSuccess) return x; }
+      return bytes ? cudaMemcpy(*p, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
+    };
+    auto dev_alloc = [&](void** p, size_t bytes) -> cudaError_t { c.bytes += bytes; return cudaMalloc(p, bytes); };
+    if (e == cudaSuccess) e = raw(&r_bwt, h.bwt.p, h.bwt.bytes(), 128);
+    if (e == cudaSuccess) e = raw(&r_high, h.high_occ.p, h.high_occ.bytes(), 0);
+    if (e == cudaSuccess) e = dev_alloc(&c.occ, nblk * 32);
+    if (e == cudaSuccess) { relayout_occ<<<grid, 256>>>((const u64*)r_bwt, h.bwt.n + 16, (const u64*)r_high, h.high_occ.n, nblk, (u64*)c.occ); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = raw(&r_flag, h.sa_flag.p, h.sa_flag.bytes(), 128);
+    if (e == cudaSuccess) e = dev_alloc(&c.flag, nfb * 16);
+    if (e == cudaSuccess) { relayout_flag<<<grid, 256>>>((const u64*)r_flag, h.sa_flag.n + 16, nfb, h.sa_length - 1, (u64*)c.flag); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = raw(&r_hi, h.hash_hi.p, h.hash_hi.bytes(), 0);
+    if (e == cudaSuccess) e = raw(&r_lo, h.hash_lo.p, h.hash_lo.bytes(), 0);
+    if (e == cudaSuccess) e = dev_alloc(&c.hash, (nh + 2) * 8);
+    if (e == cudaSuccess) e = cudaMemset(c.hash, 0, (nh + 2) * 8);
+    if (e == cudaSuccess) { relayout_hash<<<grid, 256>>>((const u32*)r_hi, (const unsigned char*)r_lo, nh, (u64*)c.hash); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = raw(&r_pac, h.pac.p, h.pac.bytes(), 16);
+    if (e == cudaSuccess) e = dev_alloc(&c.planes, npw * 8);
+    if (e == cudaSuccess) e = cudaMemset(c.planes, 0, npw * 8);
+    if (e == cudaSuccess) { relayout_planes<<<grid, 256>>>((const unsigned char*)r_pac, h.N, (n + 31) / 32, (uint2*)c.planes); e = cudaGetLastError(); }
+    if (e == cudaSuccess) { c.bytes += h.ssa.bytes(); e = cudaMalloc(&c.ssa, h.ssa.bytes() + 16); }
+    if (e == cudaSuccess) e = cudaMemcpy(c.ssa, h.ssa.p, h.ssa.bytes(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(r_bwt); cudaFree(r_high); cudaFree(r_flag); cudaFree(r_hi); cudaFree(r_lo); cudaFree(r_pac);
     idx->copies.push_back(c);
     if (e != cudaSuccess) { std::string m = std::string("index upload: ") + cudaGetErrorString(e); bmbs_index_free(idx); return fail(BMBS_ERR_CUDA, m); }
     DevIndex& v = idx->copies.back().view;
@@ -241,7 +295,7 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
     v.C[0] = h.nacgt[0]; v.C[1] = h.nacgt[1]; v.C[2] = h.nacgt[2];
     v.shapline = h.shapline; v.n_rows = h.sa_length; v.N = h.N;
     v.dsa_lo = nullptr; v.dsa_hi = nullptr; v.ktab = nullptr; v.kdepth = 0; v.kpow = 1;
-    lap("cuda init + upload");
+    lap("upload + device re-layout");
     // ---- dense suffix array (BMBS_SA=sampled keeps the on-disk 1/8 sampling; default: dense when it fits with room to spare)
     const char* mode = getenv("BMBS_SA");
     const bool wide = h.sa_length > 0xFFFFFFFFull;
@@ -260,7 +314,7 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
       if (e != cudaSuccess) { std::string m = std::string("dense suffix array: ") + cudaGetErrorString(e); bmbs_index_free(idx); return fail(BMBS_ERR_CUDA, m); }
       v.dsa_lo = (const u32*)cc.dsa_lo; v.dsa_hi = (const unsigned char*)cc.dsa_hi;
       cudaFree(cc.flag); cudaFree(cc.ssa); cc.flag = nullptr; cc.ssa = nullptr; v.flag = nullptr; v.ssa = nullptr;
-      cc.bytes += need; cc.bytes -= flag.size() * 8 + h.ssa.size() * 4;
+      cc.bytes += need; cc.bytes -= nfb * 16 + h.ssa.bytes();
     }
     lap("dense suffix array");
     // ---- deep seed table: K = 16..20 (BMBS_KMER); default: the smallest K whose 3^K exceeds 8 x the text length -- a

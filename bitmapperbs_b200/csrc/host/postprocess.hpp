@@ -12,6 +12,10 @@
 //   MAPQ table              Schema.cpp:168-405   (MAP_Calculation)
 //   coordinate conversion   Schema.cpp:12596-12650, :9188-9244
 #pragma once
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
@@ -58,19 +62,28 @@ struct ChromTable {
 
 // 2-bit genome, four bases per byte, first base in the top bits, A0 C1 G2 T3.
 struct Genome2bit {
-  std::vector<uint8_t> pac;
+  // <prefix>.index.bs.pac: u64 nBytes; u8[] -- mapped, not read (only the windows of refined alignments are ever touched)
+  struct Bytes {
+    const uint8_t* p = nullptr; size_t n = 0; void* map = nullptr; size_t map_size = 0;
+    Bytes() = default; Bytes(const Bytes&) = delete; Bytes& operator=(const Bytes&) = delete;
+    uint8_t operator[](size_t i) const { return p[i]; }
+    size_t size() const { return n; }
+    ~Bytes() { if (map) munmap(map, map_size); }
+  } pac;
   uint64_t N = 0;
   bool load(const std::string& path, uint64_t n_bases) {
-    FILE* f = fopen(path.c_str(), "rb");
-    if (!f) return false;
-    uint64_t nb = 0;
-    bool ok = fread(&nb, 8, 1, f) == 1;
-    pac.assign(nb + 8, 0);
-    ok = ok && fread(pac.data(), 1, nb, f) == nb;
-    pac.resize(nb);
-    fclose(f);
+    const int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size < 8) { ::close(fd); return false; }
+    void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd);
+    if (m == MAP_FAILED) return false;
+    uint64_t nb = 0; memcpy(&nb, m, 8);
+    if (nb > (uint64_t)st.st_size - 8) { munmap(m, (size_t)st.st_size); return false; }
+    pac.map = m; pac.map_size = (size_t)st.st_size; pac.p = (const uint8_t*)m + 8; pac.n = (size_t)nb;
     N = n_bases;
-    return ok;
+    return true;
   }
   inline char base(uint64_t i) const { return "ACGT"[(pac[i >> 2] >> (6 - 2 * (i & 3))) & 3]; }
   // Forward-strand window [start, start+len); all-zero bytes when it would leave

@@ -873,6 +873,8 @@ extern "C" int bmbs_ubench_int_pipe(int dev, double* ops_per_second) {
 // second at random addresses (table entries, occ blocks, suffix-array entries).  This measures that rate: every thread
 // keeps 8 independent 256-bit loads in flight at hashed addresses over `bytes` of device memory.
 namespace {
+// V selects the load instruction (BMBS_UBENCH_VARIANT, experiments on how much DRAM traffic one random sector costs)
+template <int V>
 __global__ void __launch_bounds__(256) random_sector_ubench(const ulonglong4* __restrict__ buf, u64 n_sectors, int iters, u64* sink) {
   u64 x = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
   u64 acc = 0;
@@ -882,8 +884,16 @@ __global__ void __launch_bounds__(256) random_sector_ubench(const ulonglong4* __
     for (int i = 0; i < 8; ++i) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; a[i] = x % n_sectors; }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      u64 v0, v1, v2, v3;
-      asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v0), "=l"(v1), "=l"(v2), "=l"(v3) : "l"(buf + a[i]));
+      u64 v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+      if (V == 0) asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v0), "=l"(v1), "=l"(v2), "=l"(v3) : "l"(buf + a[i]));
+      if (V == 1) asm volatile("ld.global.nc.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v0), "=l"(v1), "=l"(v2), "=l"(v3) : "l"(buf + a[i]));
+      if (V == 2) asm volatile("ld.global.nc.L2::128B.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v0), "=l"(v1), "=l"(v2), "=l"(v3) : "l"(buf + a[i]));
+      if (V == 3) asm volatile("ld.global.cv.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v0), "=l"(v1), "=l"(v2), "=l"(v3) : "l"(buf + a[i]));
+      if (V == 4) asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v0), "=l"(v1), "=l"(v2), "=l"(v3) : "l"(buf + a[i]));
+      if (V == 5) asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v0), "=l"(v1), "=l"(v2), "=l"(v3) : "l"(buf + a[i]));
+      if (V == 6) asm volatile("ld.global.lu.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v0), "=l"(v1), "=l"(v2), "=l"(v3) : "l"(buf + a[i]));
+      if (V == 7) asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v0) : "l"(buf + a[i]));
+      if (V == 8) asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v0), "=l"(v1), "=l"(v2), "=l"(v3) : "l"(buf + a[i]));
       acc += v0 ^ v3;
     }
   }
@@ -900,11 +910,26 @@ extern "C" int bmbs_ubench_random_sectors(int dev, size_t bytes, double* sectors
   cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
   const int blocks = prop.multiProcessorCount * 8, iters = 64;
   const u64 n_sectors = bytes / 32;
-  random_sector_ubench<<<blocks, 256>>>((const ulonglong4*)d, n_sectors, 4, sink);
+  const int variant = getenv("BMBS_UBENCH_VARIANT") ? atoi(getenv("BMBS_UBENCH_VARIANT")) : 0;
+  auto launch = [&](int it) {
+    const ulonglong4* q = (const ulonglong4*)d;
+    switch (variant) {
+      case 1: random_sector_ubench<1><<<blocks, 256>>>(q, n_sectors, it, sink); break;
+      case 2: random_sector_ubench<2><<<blocks, 256>>>(q, n_sectors, it, sink); break;
+      case 3: random_sector_ubench<3><<<blocks, 256>>>(q, n_sectors, it, sink); break;
+      case 4: random_sector_ubench<4><<<blocks, 256>>>(q, n_sectors, it, sink); break;
+      case 5: random_sector_ubench<5><<<blocks, 256>>>(q, n_sectors, it, sink); break;
+      case 6: random_sector_ubench<6><<<blocks, 256>>>(q, n_sectors, it, sink); break;
+      case 7: random_sector_ubench<7><<<blocks, 256>>>(q, n_sectors, it, sink); break;
+      case 8: random_sector_ubench<8><<<blocks, 256>>>(q, n_sectors, it, sink); break;
+      default: random_sector_ubench<0><<<blocks, 256>>>(q, n_sectors, it, sink); break;
+    }
+  };
+  launch(4);
   double best = 0;
   for (int rep = 0; rep < 3; ++rep) {
     CU(cudaEventRecord(e0));
-    random_sector_ubench<<<blocks, 256>>>((const ulonglong4*)d, n_sectors, iters, sink);
+    launch(iters);
     CU(cudaEventRecord(e1)); CU(cudaEventSynchronize(e1));
     float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
     const double rate = (double)blocks * 256 * iters * 8 / (ms / 1000.0);

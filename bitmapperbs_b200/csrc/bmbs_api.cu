@@ -412,7 +412,7 @@ extern "C" int bmbs_batch_create(bmbs_index* idx, int dev, size_t max_reads, siz
   cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
   auto A = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
   A(dalloc(b, &b->d_ascii, max_bases + 64)); A(dalloc(b, &b->d_offsets, R));
-  A(dalloc(b, &v.codes, max_bases / 8 + R + 64)); A(dalloc(b, &v.rplanes, max_bases / 32 + 2 * R + 64)); A(dalloc(b, &v.len, R)); A(dalloc(b, &v.first_c, R)); A(dalloc(b, &v.kk, R));
+  A(dalloc(b, &v.codes, 4 * (max_bases / 32 + 2 * R + 64))); A(dalloc(b, &v.rplanes, max_bases / 32 + 2 * R + 64)); A(dalloc(b, &v.len, R)); A(dalloc(b, &v.first_c, R)); A(dalloc(b, &v.kk, R));
   A(dalloc(b, &v.state, R)); A(dalloc(b, &v.flags, R)); A(dalloc(b, &v.one_mm, R)); A(dalloc(b, &v.site0, R));
   A(dalloc(b, &v.ph_off, R)); A(dalloc(b, &v.ph_first_len, R)); A(dalloc(b, &v.ph_seed_id, R)); A(dalloc(b, &v.list2, R)); A(dalloc(b, &v.list3, R)); A(dalloc(b, &v.list_count, 4));
   A(dalloc(b, &v.bk, 5 * R)); A(dalloc(b, &v.first_cands, R)); A(dalloc(b, &v.list4, R)); A(dalloc(b, &v.res_first, R)); A(dalloc(b, &v.res_n, R));
@@ -492,8 +492,7 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
     run_scan(b, v.ncand, (u32)n, v.coff, v.totals, v.slot_cap, 2u);
     expand_locate<<<(n + 127) / 128, 128, 0, s>>>(ix, v); ++b->launches;
     CU(cudaEventRecord(b->ev[3], s));
-    votes_classify<<<(n + 255) / 256, 256, 0, s>>>(v); ++b->launches;
-    votes_sort<16><<<b->sm_count * 16, 128, 0, s>>>(v); ++b->launches;
+    votes_classify<<<(n + 127) / 128, 128, 0, s>>>(v); ++b->launches;
     votes_sort<32><<<b->sm_count * 4, 128, 0, s>>>(v); ++b->launches;
     votes_big<<<b->sm_count * 4, 256, 0, s>>>(v); ++b->launches;
     CU(cudaEventRecord(b->ev[4], s));
@@ -516,8 +515,7 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
       seed_reseed<<<b->sm_count * 8, SEED_BLOCK, seed_smem, s>>>(ix, w, plane_cap); ++b->launches;
       run_scan(b, w.ncand, (u32)n, w.coff, w.totals, w.slot_cap, 2u);
       expand_locate<<<(n + 127) / 128, 128, 0, s>>>(ix, w); ++b->launches;
-      votes_classify<<<(n + 255) / 256, 256, 0, s>>>(w); ++b->launches;
-      votes_sort<16><<<b->sm_count * 16, 128, 0, s>>>(w); ++b->launches;
+      votes_classify<<<(n + 127) / 128, 128, 0, s>>>(w); ++b->launches;
       votes_sort<32><<<b->sm_count * 4, 128, 0, s>>>(w); ++b->launches;
       votes_big<<<b->sm_count * 4, 256, 0, s>>>(w); ++b->launches;
       sens_reseed_filter<<<b->sm_count * 4, 128, 0, s>>>(w); ++b->launches;

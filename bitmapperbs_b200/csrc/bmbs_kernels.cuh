@@ -63,8 +63,9 @@ struct BatchView {
   double e_rate; u32 seed_len; int dmax_base, dmin_base;  // pair distance bounds before the per-pair 2k / length terms
 };
 
-__device__ __forceinline__ u32 code_word_offset(const u64* offsets, int r) { return (u32)(offsets[r] >> 3) + (u32)r; }
+// a read owns (L >> 5) + 1 chunks of 32 bases: one uint4 of bit-planes and four code words (16-byte aligned) per chunk
 __device__ __forceinline__ u32 plane_chunk_offset(const u64* offsets, int r) { return (u32)(offsets[r] >> 5) + (u32)r; }
+__device__ __forceinline__ u32 code_word_offset(const u64* offsets, int r) { return 4u * plane_chunk_offset(offsets, r); }
 
 // ------------------------------------------------------------------------------------------- pack
 // Eight lanes per read, one 32-base chunk per lane and pass: 32 ASCII bytes (aligned 64-bit loads + funnel shifts) become
@@ -75,6 +76,7 @@ __device__ __forceinline__ u32 gather4(u32 m01) { return ((m01 * 0x01020408u) >>
 __device__ __forceinline__ u32 nonzero_bytes(u32 d) { return ((((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) >> 7) & 0x01010101u; }
 
 struct Packed4 { u32 nib, lo, hi, bad, isn; };
+// General path, four bases: handles anything that is not A/C/G/T and the ragged end of a read.
 __device__ __forceinline__ Packed4 pack4(u32 x, u32 nvalid) {
   const u32 y = (x >> 1) & 0x03030303u;
   const u32 code = y ^ ((y >> 1) & 0x01010101u);                  // A0 C1 G2 T3 when the byte is one of ACGT
@@ -94,6 +96,26 @@ __device__ __forceinline__ Packed4 pack4(u32 x, u32 nvalid) {
   }
   o.nib = nib; o.lo = gather4(b0); o.hi = gather4(b1);
   return o;
+}
+
+// Fast path, eight bases that are all A/C/G/T (checked; false = take the general path).  For A 0x41, C 0x43, G 0x47, T 0x54
+// the code (A0 C1 G2 T3) is in the byte: high bit = bit 2, low bit = bit 1 ^ bit 2.  Each plane's eight bits are gathered
+// with one multiply (no two partial products meet, so no carries), the nibble codes are spread back out of the planes with
+// three multiply-and-mask steps, the bytes are checked against "ACGT"[code] (PRMT).  Half of the work is IMADs, which run
+// on the FMA pipe this ALU-bound kernel otherwise leaves idle.
+__device__ __forceinline__ u32 spread8(u32 v) {                   // bit i of an 8-bit value -> bit 4i
+  u32 t = (v * 0x1001u) & 0x000F000Fu;
+  t = (t * 0x41u) & 0x03030303u;
+  return (t * 9u) & 0x11111111u;
+}
+__device__ __forceinline__ bool pack8(u32 x0, u32 x1, u32& nib, u32& lo8, u32& hi8) {
+  const u32 a1 = x0 >> 1, a2 = x0 >> 2, c1 = x1 >> 1, c2 = x1 >> 2;
+  const u32 l0 = (a1 ^ a2) & 0x01010101u, h0 = a2 & 0x01010101u, l1 = (c1 ^ c2) & 0x01010101u, h1 = c2 & 0x01010101u;
+  lo8 = ((l1 * 16u + l0) * 0x01020408u) >> 24;                    // bases 0-3 in bits 0-3, bases 4-7 in bits 4-7
+  hi8 = ((h1 * 16u + h0) * 0x01020408u) >> 24;
+  nib = spread8(hi8) * 2u + spread8(lo8);
+  const u32 d0 = x0 ^ __byte_perm(0x54474341u, 0u, nib), d1 = x1 ^ __byte_perm(0x54474341u, 0u, nib >> 16);
+  return (d0 | d1) == 0;
 }
 
 __global__ void __launch_bounds__(128) pack_reads(BatchView b) {
@@ -117,17 +139,27 @@ __global__ void __launch_bounds__(128) pack_reads(BatchView b) {
     }
     const u32 left = L - c * 32;                                // >= 1
     u32 lo = 0, hi = 0, bad = 0, isn = 0;
+    u32 nw[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const u32 base = 8 * i;
-      if (base < left) {
+      u32 n8, l8, h8;
+      // the bytes behind a ragged end are the next read's bases (or slack): when they happen to be A/C/G/T too the group
+      // still takes the fast path and its results are cut to the bases that belong to this read
+      if (base < left && pack8((u32)x[i], (u32)(x[i] >> 32), n8, l8, h8)) {
+        const u32 nb = left - base;
+        if (nb < 8) { n8 &= (1u << (4 * nb)) - 1u; l8 &= (1u << nb) - 1u; h8 &= (1u << nb) - 1u; }
+        nw[i] = n8;
+        lo |= l8 << base; hi |= h8 << base;
+      } else if (base < left) {
         const Packed4 a = pack4((u32)x[i], left - base);
         const Packed4 d = pack4((u32)(x[i] >> 32), left > base + 4 ? left - base - 4 : 0);
-        w[c * 4 + i] = a.nib | (d.nib << 16);
+        nw[i] = a.nib | (d.nib << 16);
         lo |= (a.lo | (d.lo << 4)) << base; hi |= (a.hi | (d.hi << 4)) << base;
         bad |= (a.bad | (d.bad << 4)) << base; isn |= (a.isn | (d.isn << 4)) << base;
       }
     }
+    *reinterpret_cast<uint4*>(w + c * 4) = make_uint4(nw[0], nw[1], nw[2], nw[3]);
     pl[c] = make_uint4(lo, hi, bad, isn);
     const u32 isc = lo & ~hi & ~bad;
     if (isc) first_c = min(first_c, c * 32 + (u32)__ffs(isc) - 1u);
@@ -623,16 +655,68 @@ __device__ __forceinline__ bool classify_read(BatchView& b, int r, u32 beg, u32 
 
 __device__ __forceinline__ u64 window_start(u64 c, u64 k) { return c < k ? 0ull : c - k; }
 
-// One thread per read decides what the candidates turn into; reads whose candidates have to be sorted go to one of three
-// lists by segment length (<= 16: half a warp sorts them, <= 32: a warp, longer: a CTA).
-__global__ void votes_classify(BatchView b) {
+// Sorting network over N registers (bitonic; every index is a compile-time constant after unrolling), ascending.
+template <int N>
+__device__ __forceinline__ void sort_regs(u64 (&v)[N]) {
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1)
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1)
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int l = i ^ j;
+        if (l > i) {
+          const u64 a = v[i], c = v[l];
+          const bool sw = ((i & k) == 0) ? (a > c) : (a < c);
+          v[i] = sw ? c : a; v[l] = sw ? a : c;
+        }
+      }
+}
+
+// sort + run-length encode a segment of n <= N candidates held by one thread, in place (generate_candidate_votes_shift,
+// Schema.cpp:4687-4773: equal sites merge into {max(site - k, 0), votes}; distinct small sites that clamp to 0 stay apart)
+template <int N>
+__device__ __forceinline__ void sort_encode_small(BatchView& b, int r, u32 beg, u32 n, bool live, bool multi) {
+  u64 v[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = (live && (u32)i < n) ? b.cand[beg + i] : ~0ull;   // padding ~0 sorts last (a real ~0 is equal to it)
+  sort_regs<N>(v);
+  if (!live) return;
+  if (multi) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) if ((u32)i < n) { b.cand[beg + i] = v[i]; b.vcnt[beg + i] = 0; }
+    b.nv[r] = n;
+    return;
+  }
+  const u64 k = b.kk[r];
+  u32 out = 0, run = 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    if ((u32)i < n) {
+      ++run;
+      const bool last = (u32)(i + 1) == n || (i + 1 < N && v[i + 1] != v[i]);
+      if (last) { b.cand[beg + out] = window_start(v[i], k); b.vcnt[beg + out] = run; ++out; run = 0; }
+    }
+  }
+  b.nv[r] = out;
+}
+
+// One thread per read decides what the candidates turn into and, for the usual short segment (<= 16 candidates), sorts and
+// encodes it on the spot with a sorting network in registers (8 wide when the whole warp fits); longer segments go to the
+// warp kernel (<= 32) or the CTA kernel.
+__global__ void __launch_bounds__(128) votes_classify(BatchView b) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  int which = -1;
+  int which = -1; u32 beg = 0, n = 0;
   if (r < b.n_reads && !*b.status) {
-    const u32 beg = b.coff[r], n = b.coff[r + 1] - beg;
+    beg = b.coff[r]; n = b.coff[r + 1] - beg;
     if (classify_read(b, r, beg, n, true)) which = n <= 16 ? 0 : n <= 32 ? 1 : 2;
   }
-  list_append(b.sort16, b.sort_count, which == 0, (u32)r);
+  const bool small = which == 0;
+  if (__any_sync(0xffffffffu, small)) {
+    const bool multi = small && b.round == 0 && b.state[r] == BMBS_MULTI_EXACT;
+    if (__all_sync(0xffffffffu, !small || n <= 8)) sort_encode_small<8>(b, r, beg, n, small, multi);
+    else sort_encode_small<16>(b, r, beg, n, small, multi);
+  }
   list_append(b.sort32, b.sort_count + 1, which == 1, (u32)r);
   list_append(b.big_list, b.big_count, which == 2, (u32)r);
 }

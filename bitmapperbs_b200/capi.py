@@ -16,7 +16,7 @@ assert ReadResult.itemsize == 24 and Cand.itemsize == 16
 
 
 class Params(C.Structure):
-    _fields_ = [("e_rate", C.c_double), ("seed_len", C.c_int), ("min_ins", C.c_int), ("max_ins", C.c_int), ("sensitive", C.c_int)]
+    _fields_ = [("e_rate", C.c_double), ("seed_len", C.c_int), ("min_ins", C.c_int), ("max_ins", C.c_int), ("sensitive", C.c_int), ("ambiguous_out", C.c_int)]
 
 
 class Scoring(C.Structure):

@@ -222,7 +222,7 @@ struct bmbs_index {
 };
 
 extern "C" const char* bmbs_last_error(void) { return g_err.c_str(); }
-extern "C" void bmbs_params_default(bmbs_params* p) { p->e_rate = 0.08; p->seed_len = 30; p->min_ins = 0; p->max_ins = 500; p->sensitive = 0; }
+extern "C" void bmbs_params_default(bmbs_params* p) { p->e_rate = 0.08; p->seed_len = 30; p->min_ins = 0; p->max_ins = 500; p->sensitive = 0; p->ambiguous_out = 0; }
 extern "C" uint64_t bmbs_index_genome_length(const bmbs_index* idx) { return idx ? idx->N : 0; }
 extern "C" uint64_t bmbs_index_device_bytes(const bmbs_index* idx) { return idx && !idx->copies.empty() ? idx->copies[0].bytes : 0; }
 
@@ -471,7 +471,7 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
   const int n = b->n_reads;
   v.ascii = b->d_ascii; v.offsets = b->d_offsets; v.n_reads = n; v.pe = b->pe;
   v.e_rate = prm->e_rate; v.seed_len = (u32)prm->seed_len; v.dmax_base = prm->max_ins; v.dmin_base = prm->min_ins;
-  v.sensitive = prm->sensitive ? 1 : 0; v.round = 0; v.multi_cap = prm->sensitive ? MAX_PE_MULTI_SENSITIVE : MAX_PE_MULTI;
+  v.sensitive = prm->sensitive ? 1 : 0; v.amb_out = prm->ambiguous_out ? 1 : 0; v.round = 0; v.multi_cap = prm->sensitive ? MAX_PE_MULTI_SENSITIVE : MAX_PE_MULTI;
   b->launches = 0;
   cudaStream_t s = b->stream;
   const DevIndex ix = b->copy->view;

@@ -45,6 +45,7 @@ struct BatchView {
   // re-seed, and each read's final slice of out_cand
   unsigned short* bk; unsigned short* first_cands; u32* list4; u32* res_first; u32* res_n;
   int sensitive; int round;                     // round 1 = the re-seeding pass
+  int amb_out;                                  // --ambiguous_out: single-end multi-exact reads keep their located rows, in row order
   u32 multi_cap;
   u32* ntask; u32* ncand; u32* coff;           // coff: exclusive scan of ncand, n_reads+1
   SeedTask* tasks;                              // [MAX_TASKS][n_reads]
@@ -461,6 +462,7 @@ __global__ void __launch_bounds__(128) seed_first(DevIndex ix, BatchView b, u32 
           if (first_c == L) {
             state = BMBS_MULTI_EXACT; done = true;
             if (b.pe) tw.emit(sp, (u32)h.hits, mlen, 0);
+            else if (b.amb_out) tw.emit(sp, (u32)(h.hits > MAX_SEED_HITS ? MAX_SEED_HITS : h.hits), mlen, 0);   // output_ambiguous_exact_map_output_buffer walks at most 1000 rows
           }
         }
       }
@@ -643,7 +645,13 @@ __device__ __forceinline__ bool classify_read(BatchView& b, int r, u32 beg, u32 
   if (b.round == 1) { if (n == 0) { if (lane0) b.nv[r] = 0; return false; } return true; }   // re-seeded mates: always sort + encode
   const int st = b.state[r];
   if (st == BMBS_EXACT_UNIQUE) { if (lane0) { b.nv[r] = b.pe ? 1u : 0u; if (n) b.vcnt[beg] = 0; } return false; }
-  if (st == BMBS_MULTI_EXACT) { if (!b.pe) { if (lane0) b.nv[r] = 0; return false; } return true; }
+  if (st == BMBS_MULTI_EXACT) {
+    if (!b.pe) {      // single end: nothing to verify; with --ambiguous_out the located rows stay as they are (row order)
+      if (lane0) { const u32 keep = b.amb_out ? n : 0u; for (u32 i = 0; i < keep; ++i) b.vcnt[beg + i] = 0; b.nv[r] = keep; }
+      return false;
+    }
+    return true;
+  }
   if (n == 0) { if (lane0) b.nv[r] = 0; return false; }
   if ((b.flags[r] & 2) && (n == 1 || (n == 2 && b.cand[beg] == b.cand[beg + 1]))) {
     if (lane0) { b.state[r] = BMBS_ONE_MISMATCH; b.site0[r] = b.cand[beg]; b.nv[r] = b.pe ? 1u : 0u; b.vcnt[beg] = 0; }

@@ -5,6 +5,7 @@
 //   --search <genome.fa> --seq <r.fq[.gz]>       single-end mapping
 //   --search <genome.fa> --seq1 <a> --seq2 <b> --pe   paired-end mapping (fast mode)
 //   -o <out.sam>  -t <host threads>  -e <rate>  --seed <len>  --min/--max <insert>  --mapstats <file>
+//   --unmapped_out  --ambiguous_out
 //   --mp_max/--mp_min/--np/--gap_open/--gap_extension  --phred33/--phred64   -g/--gpus <n>
 // Records are written in input order (the reference's `-t 1` order).
 // Pipeline: block splitter -> FASTQ parse workers -> GPU threads (two batches in flight per device: H2D, kernels,
@@ -33,7 +34,7 @@ namespace {
 
 struct Options {
   std::string mode, genome, seq, seq1, seq2, out = "output", mapstats;
-  bool pe = false, sensitive = false;
+  bool pe = false, sensitive = false, unmapped_out = false, ambiguous_out = false;
   int threads = 1, gpus = 1;
   size_t batch_reads = 1 << 15;                      // reads (pairs) per batch
   bmbs_params prm; Scoring sc;
@@ -78,6 +79,8 @@ void parse(int argc, char** argv, Options& o) {
     else if (a == "--pe") o.pe = true;
     else if (a == "--sensitive") o.sensitive = true;
     else if (a == "--fast") o.sensitive = false;
+    else if (a == "--unmapped_out") o.unmapped_out = true;
+    else if (a == "--ambiguous_out") o.ambiguous_out = true;
     else if (a == "-o") o.out = val();
     else if (a == "-t" || a == "--threads") o.threads = atoi(val().c_str());
     else if (a == "-e") o.prm.e_rate = atof(val().c_str());
@@ -94,14 +97,15 @@ void parse(int argc, char** argv, Options& o) {
     else if (a == "--phred64") o.sc.q_base = 64;
     else if (a == "-g" || a == "--gpus") o.gpus = atoi(val().c_str());
     else if (a == "--batch") o.batch_reads = (size_t)atoll(val().c_str());
-    else die("unknown or unsupported option " + a + " (supported: --index --search --seq --seq1 --seq2 --pe --fast --sensitive -o -t -e --seed --min --max --mapstats scoring flags --phred33/64 --gpus --batch)");
+    else die("unknown or unsupported option " + a + " (supported: --index --search --seq --seq1 --seq2 --pe --fast --sensitive --unmapped_out --ambiguous_out -o -t -e --seed --min --max --mapstats scoring flags --phred33/64 --gpus --batch)");
   }
   if (!o.seq1.empty() && !o.seq2.empty()) o.pe = true;   // Process_CommandLines.cpp:314-317
   if (o.threads < 1) o.threads = 1;
   unsigned hw = std::thread::hardware_concurrency();
   if (hw && (unsigned)o.threads > hw) o.threads = (int)hw;  // the reference caps -t at the online CPUs (:254-258)
   if (o.gpus < 1) o.gpus = 1;
-  o.prm.sensitive = (o.sensitive && o.pe) ? 1 : 0;      // --sensitive only selects the pair worker (Bitmapper_main.cpp)
+  o.prm.sensitive = (o.sensitive && o.pe) ? 1 : 0;
+  o.prm.ambiguous_out = o.ambiguous_out ? 1 : 0;      // --sensitive only selects the pair worker (Bitmapper_main.cpp)
 }
 
 // Bases are upper-cased in place (Process_Reads.cpp:321-472).  Lower-case letters have bit 5 set and A/C/G/T/N do not, so
@@ -163,7 +167,7 @@ void parse_batch(RawBatch& rb, bool pe, Batch& b) {
 // others, the second pass redoes only those units with the results, and their text is spliced back in input order.
 struct FinishScratch { std::vector<HostHit> v1, v2; std::vector<char> win; DpQueue dq; std::string side; std::vector<uint32_t> unit; std::vector<size_t> at, side_end; };
 
-void finish_batch(const HostContext& hc, Batch& b, bool pe, bmbs_refiner* refiner, FinishScratch& fs, long long& n_dp) {
+void finish_batch(const HostContext& hc, Batch& b, bool pe, bool unmapped_out, bmbs_refiner* refiner, FinishScratch& fs, long long& n_dp) {
   const int units = pe ? b.n / 2 : b.n;
   b.sam.clear(); b.sam.reserve((size_t)units * (pe ? 900 : 400));
   DpQueue& dq = fs.dq; dq.clear();
@@ -177,12 +181,20 @@ void finish_batch(const HostContext& hc, Batch& b, bool pe, bmbs_refiner* refine
                   b.res[2 * u], b.res[2 * u + 1], b.cand.data(), out, st, fs.v1, fs.v2, fs.win, &dq);
     }
   };
+  // --unmapped_out: a read (pair) that was counted neither as unique nor as ambiguous gets flag-4 (77 / 141) records where its
+  // alignment would have stood (Schema.cpp:27087-27096 / :13041 single end, :21864-21880 / :10392 paired end; this includes
+  // unique hits dropped because they run over a chromosome end)
+  auto unmapped = [&](int u, std::string& out, const MapStats& t) {
+    if (!unmapped_out || t.unique || t.ambiguous) return;
+    if (!pe) sam_record_unmapped(out, b.name[u], 4, b.fq_seq[u], b.qual[u]);
+    else { sam_record_unmapped(out, b.name[2 * u], 77, b.fq_seq[2 * u], b.qual[2 * u]); sam_record_unmapped(out, b.name[2 * u + 1], 141, b.fq_seq[2 * u + 1], b.qual[2 * u + 1]); }
+  };
   auto add = [&](const MapStats& t) { b.st.reads += t.reads; b.st.unique += t.unique; b.st.ambiguous += t.ambiguous; b.st.bases += t.bases; b.st.err_bases += t.err_bases; };
   for (int u = 0; u < units; ++u) {
     const size_t mark = b.sam.size();
     MapStats t; dq.pending = false;
     one(u, b.sam, t);
-    if (dq.pending) { b.sam.resize(mark); fs.unit.push_back((uint32_t)u); fs.at.push_back(mark); } else add(t);
+    if (dq.pending) { b.sam.resize(mark); fs.unit.push_back((uint32_t)u); fs.at.push_back(mark); } else { add(t); unmapped(u, b.sam, t); }
   }
   if (fs.unit.empty()) return;
   n_dp += (long long)dq.items.size();
@@ -193,7 +205,7 @@ void finish_batch(const HostContext& hc, Batch& b, bool pe, bmbs_refiner* refine
     die(std::string("gpu CIGAR refinement failed: ") + bmbs_last_error());
   dq.mode = DpQueue::REPLAY; dq.next = 0;
   fs.side.clear(); fs.side_end.clear();
-  for (uint32_t u : fs.unit) { MapStats t; one((int)u, fs.side, t); add(t); fs.side_end.push_back(fs.side.size()); }
+  for (uint32_t u : fs.unit) { MapStats t; one((int)u, fs.side, t); add(t); unmapped((int)u, fs.side, t); fs.side_end.push_back(fs.side.size()); }
   std::string merged; merged.reserve(b.sam.size() + fs.side.size());
   size_t from = 0, sfrom = 0;
   for (size_t i = 0; i < fs.unit.size(); ++i) {
@@ -215,7 +227,7 @@ void print_stats(FILE* f, const MapStats& st) {
 
 int search(const Options& o, const std::string& cmdline) {
   const double t0 = now();
-  HostContext hc; hc.sc = o.sc; hc.prm = o.prm;
+  HostContext hc; hc.sc = o.sc; hc.prm = o.prm; hc.ambiguous_out = o.ambiguous_out;
   const std::string prefix = o.genome + ".index";
   if (!hc.chroms.load(prefix)) die("cannot open " + prefix);
   if (!hc.genome.load(prefix + ".bs.pac", hc.chroms.N)) die("cannot open " + prefix + ".bs.pac");
@@ -323,7 +335,7 @@ int search(const Options& o, const std::string& cmdline) {
     if (bmbs_refiner_create(idx, devs[t % devs.size()], &refiner)) die(std::string("refiner create: ") + bmbs_last_error());
     FinishScratch fs; long long n_dp = 0;
     std::unique_ptr<Batch> b;
-    while (fin_q.pop(b)) { const double ts = now(); finish_batch(hc, *b, pe, refiner, fs, n_dp); us_finish += us(ts, now()); out_q.push(std::move(b)); }
+    while (fin_q.pop(b)) { const double ts = now(); finish_batch(hc, *b, pe, o.unmapped_out, refiner, fs, n_dp); us_finish += us(ts, now()); out_q.push(std::move(b)); }
     bmbs_refiner_free(refiner);
     n_dp_total += n_dp;
     if (--live_finish == 0) out_q.close();

@@ -36,6 +36,7 @@ struct HostContext {
   Genome2bit genome;
   Scoring sc;
   bmbs_params prm;
+  bool ambiguous_out = false;   // --ambiguous_out: report the first hit of an ambiguously mapped read (pair)
 };
 
 inline uint64_t threshold_k(double e_rate, size_t L) { uint64_t k = (uint64_t)(e_rate * L); return k >= 31 ? 31 : k; }
@@ -57,7 +58,13 @@ inline void finish_single(const HostContext& hc, const ReadView& rd, const bmbs_
     case BMBS_EXACT_UNIQUE:
       if (emit(res.site, L - 1, 0, 0, std::to_string(L) + "M", 42)) { ++st.unique; st.bases += L; }
       return;
-    case BMBS_MULTI_EXACT: ++st.ambiguous; return;
+    case BMBS_MULTI_EXACT:
+      // several exact hits of a read without C.  --ambiguous_out: the first located row (suffix-array order, at most 1000)
+      // that stays inside a chromosome, MAPQ 1; counted only when one was written (Schema.cpp:27216-27245, :26704-26758)
+      if (!hc.ambiguous_out) { ++st.ambiguous; return; }
+      for (uint32_t i = 0; i < res.n_cand; ++i)
+        if (emit(cand[res.first_cand + i].site, L - 1, 0, 0, std::to_string(L) + "M", 1)) { ++st.ambiguous; return; }
+      return;
     case BMBS_ONE_MISMATCH: {
       const int pos = res.one_mismatch_pos;
       int score = 0;
@@ -85,7 +92,11 @@ inline void finish_single(const HostContext& hc, const ReadView& rd, const bmbs_
       else if (e < min_err) { sbd = min_err - e; min_err = e; idx = (int)i; best_end = end_abs; }
     }
   }
-  if (idx <= -2) { ++st.ambiguous; return; }
+  const bool ambiguous = idx <= -2;
+  if (ambiguous) {                       // --ambiguous_out reports the first of the equally good hits (Schema.cpp:27707-27733)
+    if (!hc.ambiguous_out) { ++st.ambiguous; return; }
+    idx = -2 - idx;
+  }
   if (idx < 0) return;
   const HostHit& b = hits[idx];
   Refined rf;
@@ -95,7 +106,9 @@ inline void finish_single(const HostContext& hc, const ReadView& rd, const bmbs_
     refine_alignment(win.data(), plen, seq.data(), L, (int)k, (int)b.end_site, b.err, b.site < hc.chroms.N, qual.data(), false, hc.sc, rf, b.site, dq);
   } else { rf.score = 0; rf.start_site = (int)b.end_site - L + 1; rf.end_site = b.end_site; rf.err = 0; rf.cigar = std::to_string(L) + "M"; }
   const int mapq = mapq_from(sbd, (unsigned)k, rf.score, hc.sc);
-  if (emit(b.site, rf.end_site, rf.start_site, rf.err, rf.cigar, mapq)) { ++st.unique; st.bases += L; st.err_bases += rf.err; }
+  if (emit(b.site, rf.end_site, rf.start_site, rf.err, rf.cigar, mapq)) {
+    if (ambiguous) ++st.ambiguous; else { ++st.unique; st.bases += L; st.err_bases += rf.err; }
+  }
 }
 
 // ---- paired end -------------------------------------------------------------------------------
@@ -193,8 +206,8 @@ inline void finish_pair(const HostContext& hc, std::string_view name1, std::stri
   } else if (res1) { occ1 = (int)v1.size(); occ2 = pe::keep_hits(v2, k2); }
   else { occ2 = (int)v2.size(); occ1 = pe::keep_hits(v1, k1); }
   const pe::Pick pk = pe::pick(v1, occ1, v2, occ2, (int)kl, dmax, dmin);
-  if (pk.n > 1) { ++st.ambiguous; return; }
-  if (pk.n != 1) return;
+  if (pk.n > 1 && !hc.ambiguous_out) { ++st.ambiguous; return; }   // --ambiguous_out: the first best pair is reported (Schema.cpp:22218-22222)
+  if (pk.n < 1) return;
   pe::Mate m1, m2;
   pe::finish_mate(hc, seq1, qual1, k1, v1[pk.i1], false, m1, win, dq);
   pe::finish_mate(hc, seq2, qual2, k2, v2[pk.i2], true, m2, win, dq);
@@ -202,7 +215,8 @@ inline void finish_pair(const HostContext& hc, std::string_view name1, std::stri
   const int tlen = (int)(hi - lo + 1);                     // calculate_TLEN, Schema.h:1587-1600
   if (!(tlen <= hc.prm.max_ins && tlen >= hc.prm.min_ins)) return;
   if (!(m1.pos + m1.span <= hc.chroms.len[m1.chrom] + 1 && m2.pos + m2.span <= hc.chroms.len[m2.chrom] + 1)) return;
-  ++st.unique; st.bases += L1 + L2; st.err_bases += m1.err + m2.err;
+  if (pk.n == 1) ++st.unique; else ++st.ambiguous;
+  st.bases += L1 + L2; st.err_bases += m1.err + m2.err;
   const int mapq = mapq_from(pk.sbd, (unsigned)(k1 + k2), m1.score + m2.score, hc.sc);
   sam_record_pe(out, true, name1, seq1, std::string_view(), qual1, hc.chroms, m1.flag, m1.chrom, m1.pos, mapq, m1.cigar, m2.pos, tlen, m1.err);
   sam_record_pe(out, false, name2, seq2, raw2, qual2, hc.chroms, m2.flag, m2.chrom, m2.pos, mapq, m2.cigar, m1.pos, tlen, m2.err);

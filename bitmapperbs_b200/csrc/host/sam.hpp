@@ -75,6 +75,11 @@ inline void sam_record_pe(std::string& out, bool first, std::string_view name, s
   out += "\tNM:i:"; append_uint(out, nm); out += '\n';
 }
 
+// --unmapped_out record (Schema.cpp:13041-13110; paired end :10392-10520 with flags 77 / 141): the read as it stands in the FASTQ
+inline void sam_record_unmapped(std::string& out, std::string_view name, int flag, std::string_view seq, std::string_view qual) {
+  out += name; out += '\t'; append_uint(out, (uint64_t)flag); out += "\t*\t0\t0\t*\t*\t0\t0\t"; out += seq; out += '\t'; out += qual; out += '\n';
+}
+
 struct MapStats { uint64_t reads = 0, unique = 0, ambiguous = 0, bases = 0, err_bases = 0; };
 
 }  // namespace bmbs

@@ -58,6 +58,8 @@ typedef struct {
   int min_ins;        /* --min, default 0                                          */
   int max_ins;        /* --max, default 500                                        */
   int sensitive;      /* 0 = --fast (default); 1 = --sensitive (paired batches)     */
+  int ambiguous_out;  /* --ambiguous_out: single-end reads that match exactly at several places (state 2) also get
+                         their rows located, in suffix-array row order, at most 1000 (Schema.cpp:26704-26758)  */
 } bmbs_params;
 void bmbs_params_default(bmbs_params* p);
 

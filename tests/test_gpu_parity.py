@@ -273,7 +273,14 @@ def test_live_reference_binary_agrees_on_fresh_data(built, tmp_path):
                       ("hards", ["--seq1", "c.fq", "--seq2", "d.fq", "--pe", "--sensitive"]),
                       ("se_e", ["--seq", "r.fq", "-e", "0.12", "--seed", "25"]),
                       ("hard_flags", ["--seq1", "c.fq", "--seq2", "d.fq", "--pe", "-e", "0.05", "--seed", "25", "--min", "50", "--max", "600"]),
-                      ("hards_flags", ["--seq1", "c.fq", "--seq2", "d.fq", "--pe", "--sensitive", "-e", "0.1", "--min", "100", "--max", "450"])):
+                      ("hards_flags", ["--seq1", "c.fq", "--seq2", "d.fq", "--pe", "--sensitive", "-e", "0.1", "--min", "100", "--max", "450"]),
+                      ("se_unmapped", ["--seq", "r.fq", "--unmapped_out"]),
+                      ("hard_unmapped", ["--seq1", "c.fq", "--seq2", "d.fq", "--pe", "--unmapped_out"]),
+                      ("hards_unmapped", ["--seq1", "c.fq", "--seq2", "d.fq", "--pe", "--sensitive", "--unmapped_out"]),
+                      ("se_ambiguous", ["--seq", "r.fq", "--ambiguous_out"]),
+                      ("se_both", ["--seq", "r.fq", "--ambiguous_out", "--unmapped_out"]),
+                      ("hard_ambiguous", ["--seq1", "c.fq", "--seq2", "d.fq", "--pe", "--ambiguous_out", "--unmapped_out"]),
+                      ("hards_ambiguous", ["--seq1", "c.fq", "--seq2", "d.fq", "--pe", "--sensitive", "--ambiguous_out"])):
         subprocess.run([str(built["ref"]), "--search", "g.fa", *args, "-t", "1", "-o", f"cpu_{tag}.sam", "--mapstats", f"cpu_{tag}.st"],
                        cwd=tmp_path, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         subprocess.run([str(built["bmbs"]), "--search", "g.fa", *args, "-t", "4", "-o", f"gpu_{tag}.sam", "--mapstats", f"gpu_{tag}.st"],

@@ -509,7 +509,7 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
     CU(cudaEventRecord(b->ev[6], s));
     if (v.sensitive) {
       // --pe --sensitive: pair logic on the verified lists, then one re-seeding round for the mates left without a hit
-      sens_pair<<<(n / 2 + 127) / 128, 128, 0, s>>>(v); ++b->launches;
+      sens_pair<<<(n / 2 + 3) / 4, 128, 0, s>>>(v); ++b->launches;      // one warp per pair
       reseed_clear<<<(n + 255) / 256, 256, 0, s>>>(v); ++b->launches;
       BatchView w = v; w.round = 1;
       seed_reseed<<<b->sm_count * 8, SEED_BLOCK, seed_smem, s>>>(ix, w, plane_cap); ++b->launches;

@@ -1212,13 +1212,79 @@ __device__ __forceinline__ u32 keep_hits_inplace(bmbs_cand* c, u32 n, u32 k, con
   return kept;
 }
 
+// ---- warp-cooperative forms of the two walks above (one warp per pair: the lists of a pair in a repeat are thousands of
+// entries long, and a single thread pays an L2 round trip per entry).  Both walks are pure per entry once "the previous
+// entry that passed the mate filter" is known, as long as no coordinate has wrapped: with every site below 2^62,
+// mate_in_range(site) == "a hit h with dmin <= |h - site| <= dmax exists" (the skip pointer only saves time on ascending
+// sites), answered by binary searches over the site-sorted hits.  Lists with a wrapped coordinate (windows that start
+// before the text; never hits) take the literal single-thread walk.
+constexpr u64 SITE_SANE = 1ull << 62;
+__device__ __forceinline__ int lower_bound_site(const bmbs_cand* hits, int nh, u64 v) {   // first i with hits[i].site >= v
+  int lo = 0, hi = nh;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (hits[mid].site < v) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+__device__ __forceinline__ bool hit_between(const bmbs_cand* hits, int nh, long long lo, long long hi) {   // a hit with lo <= site <= hi
+  if (hi < 0 || lo > hi) return false;
+  const int i = lower_bound_site(hits, nh, (u64)(lo < 0 ? 0 : lo));
+  return i < nh && hits[i].site <= (u64)hi;
+}
+__device__ __forceinline__ bool in_range_pure(u64 site, const bmbs_cand* hits, int nh, int dmax, int dmin) {
+  const long long s = (long long)site;
+  if (dmax < 0) return false;
+  const long long lo0 = dmin > 0 ? dmin : 0;                          // h <= s: dmin <= s - h <= dmax
+  if (hit_between(hits, nh, s - dmax, s - lo0)) return true;
+  const long long lo1 = dmin > 1 ? dmin : 1;                          // h > s: dmin <= h - s <= dmax
+  return hit_between(hits, nh, s + lo1, s + dmax);
+}
+// are all coordinates of c[0..n) sane?  (warp-wide answer)
+__device__ __forceinline__ bool warp_all_sane(const bmbs_cand* c, u32 n, int lane) {
+  bool ok = true;
+  for (u32 i = lane; i < n; i += 32) ok = ok && c[i].site < SITE_SANE;
+  return __all_sync(0xffffffffu, ok);
+}
+// keep_hits_inplace by a warp; every lane returns the count
+__device__ __forceinline__ u32 warp_keep_hits(bmbs_cand* c, u32 n, u32 k, const bmbs_cand* mate, int nmate, int dmax, int dmin, int lane) {
+  const bool sane = warp_all_sane(c, n, lane) && (!mate || warp_all_sane(mate, (u32)nmate, lane));
+  if (!sane) {
+    u32 kept = 0;
+    if (lane == 0) kept = keep_hits_inplace(c, n, k, mate, nmate, dmax, dmin);
+    __syncwarp();
+    return __shfl_sync(0xffffffffu, kept, 0);
+  }
+  u32 kept = 0; u64 carry_end = ~0ull;                                  // absolute end of the last entry that passed the mate filter
+  for (u32 base = 0; base < n; base += 32) {
+    const u32 i = base + lane;
+    const bool valid = i < n;
+    bmbs_cand x; x.site = 0; x.vote = 0; x.end_site = 0; x.err = 0;
+    if (valid) x = c[i];
+    const bool pass = valid && (!mate || in_range_pure(x.site, mate, nmate, dmax, dmin));
+    const u64 end_abs = x.site + (u64)(long long)x.end_site;
+    const u32 pm = __ballot_sync(0xffffffffu, pass);
+    const u32 below = pm & ((1u << lane) - 1u);
+    const int src = below ? 31 - __clz(below) : 0;
+    const u64 prev_in_chunk = __shfl_sync(0xffffffffu, end_abs, src);
+    const u64 prev_end = below ? prev_in_chunk : carry_end;
+    const u32 err = x.err == 0xFFFF ? 0xFFFFFFFFu : x.err;
+    const bool keep = pass && err <= k && prev_end != end_abs;
+    const u32 km = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();
+    if (keep) c[kept + __popc(km & ((1u << lane) - 1u))] = x;           // kept + rank <= i: never ahead of the entries still to be read
+    kept += __popc(km);
+    if (pm) carry_end = __shfl_sync(0xffffffffu, end_abs, 31 - __clz(pm));
+    __syncwarp();
+  }
+  return kept;
+}
+
 __device__ __forceinline__ bool is_resolved(int st) { return st == BMBS_EXACT_UNIQUE || st == BMBS_MULTI_EXACT || st == BMBS_ONE_MISMATCH; }
 
 // After every window of both mates has been verified: the mate with fewer first-seed candidates is the primary
 // (Schema.cpp:23326); its hits are final; the other mate keeps only windows near a primary hit; a secondary left
 // without a hit goes to the re-seeding list (:23562-23640).  One thread per pair, literal walks.
-__global__ void sens_pair(BatchView b) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) sens_pair(BatchView b) {
+  const int lane = threadIdx.x & 31;
+  const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;           // one warp per pair
   bool reseed = false; u32 rs = 0;
   if (p * 2 + 1 < b.n_reads && !*b.status) {
     const int r1 = 2 * p, r2 = r1 + 1;
@@ -1227,18 +1293,21 @@ __global__ void sens_pair(BatchView b) {
     int dmax, dmin; pair_bounds(b, r1, r2, dmax, dmin);
     bmbs_cand* cp = b.out_cand + b.voff[pri]; bmbs_cand* cs = b.out_cand + b.voff[sec];
     u32 occp = b.nv[pri], occs = 0;
-    if (!is_resolved(b.state[pri])) occp = keep_hits_inplace(cp, occp, b.kk[pri], nullptr, 0, 0, 0);
+    if (!is_resolved(b.state[pri])) occp = warp_keep_hits(cp, occp, b.kk[pri], nullptr, 0, 0, 0, lane);
+    __syncwarp();
     if (occp) {
       occs = b.nv[sec];
       if (!is_resolved(b.state[sec])) {
-        occs = keep_hits_inplace(cs, occs, b.kk[sec], cp, (int)occp, dmax, dmin);
+        occs = warp_keep_hits(cs, occs, b.kk[sec], cp, (int)occp, dmax, dmin, lane);
         if (occs == 0) { reseed = true; rs = (u32)sec; }
       }
     }
-    b.res_first[pri] = b.voff[pri]; b.res_n[pri] = occp;
-    b.res_first[sec] = b.voff[sec]; b.res_n[sec] = occs;
+    if (lane == 0) {
+      b.res_first[pri] = b.voff[pri]; b.res_n[pri] = occp;
+      b.res_first[sec] = b.voff[sec]; b.res_n[sec] = occs;
+    }
   }
-  list_append(b.list4, b.list_count + 2, reseed, rs);
+  list_append(b.list4, b.list_count + 2, reseed && lane == 0, rs);
 }
 
 __global__ void reseed_clear(BatchView b) {
@@ -1249,21 +1318,33 @@ __global__ void reseed_clear(BatchView b) {
 
 // reseed_filter_muti_thread, Schema.cpp:16998-17240: up to three exact seeds chosen from the gaps of the seeds used so
 // far (select_best_seeds, :16630-16670), then a greedy seed every 8 bases; a multi-hit seed counts from 20 bases.
+// One warp per read.  Where a seed starts does not depend on the seeds before it (fixed positions, then a fixed step of 8),
+// only whether it is still looked at does (the seed budget, and the loops stop at an unusable seed that reaches the read
+// end).  So the lanes compute the seeds side by side -- each one a chain of dependent table / occ lookups, long in
+// repeats -- and lane 0 then replays the reference's loop over the finished results.
+struct ReseedResult { u64 sp, val; u32 hits, mlen; u32 off, flags; };   // flags bit0: val is a site, bit1: val is a suffix-array value
 __global__ void __launch_bounds__(128) seed_reseed(DevIndex ix, BatchView b, u32 plane_cap) {
-  extern __shared__ uint4 s_planes[];      // [plane_cap][SEED_BLOCK] staged read chunks
+  extern __shared__ uint4 s_planes[];      // [plane_cap][SEED_BLOCK]: column (warp's first thread) holds the warp's read
   __shared__ u64 s_cnt[4];
   __shared__ unsigned char s_lut[256];
+  __shared__ ReseedResult s_res[4][32];
   if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
   build_key_lut(s_lut);
   __syncthreads();
   const u32 n4 = *b.status ? 0u : b.list_count[2];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const u32 warps = gridDim.x * (blockDim.x >> 5);
   SeedCounters cn;
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+  for (u32 i = blockIdx.x * (blockDim.x >> 5) + wid; i < n4; i += warps) {
     const u32 r = b.list4[i];
     const u32 L = b.len[r];
-    ReadPlanes rp; rp.stage(b.rplanes + plane_chunk_offset(b.offsets, (int)r), L, s_planes + threadIdx.x, plane_cap);
+    // the read's chunks, staged once for the warp
+    ReadPlanes rp; rp.p = b.rplanes + plane_chunk_offset(b.offsets, (int)r); rp.s = s_planes + (threadIdx.x & ~31u);
+    rp.ns = (L >> 5) + 2; if (rp.ns > plane_cap) rp.ns = plane_cap;
+    __syncwarp();
+    for (u32 c = lane; c < rp.ns; c += 32) s_planes[c * SEED_BLOCK + (threadIdx.x & ~31u)] = __ldg(rp.p + c);
+    __syncwarp();
     u64 max_seeds = (u64)L / 10 - 1; if (max_seeds > 25) max_seeds = 25;
-    TaskWriter tw{b, (int)r, 0, 0};
     const unsigned short* k5 = b.bk + (size_t)r * 5;
     const u32 bn = k5[0], s0 = k5[1], s1 = k5[2], e_prev = k5[3], e_last = k5[4];
     u32 rs[3], rl[3]; u32 nsel = 0;
@@ -1272,56 +1353,100 @@ __global__ void __launch_bounds__(128) seed_reseed(DevIndex ix, BatchView b, u32
     // with no seed used the reference reads element [-1] of two malloc'ed int arrays: 0 with glibc -> the whole read
     const u32 last_end = bn ? e_last : 0;
     if (last_end < L) { rs[nsel] = last_end; rl[nsel] = L - last_end; ++nsel; }
-    u64 seed_id = 0, sp = 0, ep = 0;
-    for (; seed_id < nsel; ++seed_id) {
-      const u32 off = rs[seed_id], cur = L - off, mlen = rl[seed_id];
-      u64 site = 0; bool have_site = false;
+    const u32 goff0 = bn > 1 ? (s0 + s1) / 2 : 4u;
+    // lane j < nsel: exact seed j; lane nsel + g: greedy seed at goff0 + 8 g (at most 25 of them are ever looked at)
+    ReseedResult me; me.sp = 0; me.val = 0; me.hits = 0; me.mlen = 0; me.off = 0; me.flags = 0;
+    if ((u32)lane < nsel) {
+      const u32 off = lane == 0 ? rs[0] : lane == 1 ? rs[1] : rs[2], mlen = lane == 0 ? rl[0] : lane == 1 ? rl[1] : rl[2];
+      u64 sp = 0, ep = 0, site = 0; bool have_site = false;
       const u64 hits = count_exact(ix, rp, s_lut, off, mlen, sp, ep, have_site, site, cn.n_occ, cn.n_hash, cn.n_rows, cn.n_llf);
-      if (hits == 1) { if (have_site) tw.emit(site, 0, 0, 0); else tw.emit(sp, 1, mlen, off); }
-      else if (mlen >= 20 && hits <= MAX_SEED_HITS) { if (hits) tw.emit(sp, (u32)hits, mlen, off); }
-      else if (cur == mlen) break;
+      me.sp = sp; me.val = site; me.hits = (u32)(hits > 0xFFFFFFFFull ? 0xFFFFFFFFull : hits); me.mlen = mlen; me.off = off; me.flags = have_site ? 1u : 0u;
+    } else {
+      const u32 off = goff0 + 8u * ((u32)lane - nsel);
+      if (off < L && (u64)((u32)lane - nsel) < max_seeds) {
+        u64 sp = 0, ep = 0;
+        const SeedHit h = seed_until_unique(ix, rp, s_lut, off, L - off, sp, ep, cn.n_occ, cn.n_hash);
+        me.sp = h.sp; me.val = h.sa; me.hits = (u32)(h.hits > 0xFFFFFFFFull ? 0xFFFFFFFFull : h.hits); me.mlen = h.mlen; me.off = off; me.flags = h.has_sa ? 2u : 0u;
+      }
     }
-    u32 off = bn > 1 ? (s0 + s1) / 2 : 4u;
-    while (seed_id < max_seeds && off < L) {
-      const u32 cur = L - off;
-      SeedHit h = seed_until_unique(ix, rp, s_lut, off, cur, sp, ep, cn.n_occ, cn.n_hash);
-      sp = h.sp; ep = h.ep;
-      if (h.hits == 1) { if (h.has_sa) tw.emit(2 * ix.N - h.sa - h.mlen - off, 0, 0, 0); else tw.emit(sp, 1, h.mlen, off); }
-      else if (h.mlen >= 20 && h.hits <= MAX_SEED_HITS) { if (h.hits) tw.emit(sp, (u32)h.hits, h.mlen, off); }
-      else if (cur == h.mlen) break;
-      off += 8;
-      ++seed_id;
+    s_res[wid][lane] = me;
+    __syncwarp();
+    if (lane == 0) {
+      TaskWriter tw{b, (int)r, 0, 0};
+      u64 seed_id = 0;
+      for (; seed_id < nsel; ++seed_id) {
+        const ReseedResult& q = s_res[wid][seed_id];
+        const u32 cur = L - q.off;
+        if (q.hits == 1) { if (q.flags & 1u) tw.emit(q.val, 0, 0, 0); else tw.emit(q.sp, 1, q.mlen, q.off); }
+        else if (q.mlen >= 20 && q.hits <= MAX_SEED_HITS) { if (q.hits) tw.emit(q.sp, q.hits, q.mlen, q.off); }
+        else if (cur == q.mlen) break;
+      }
+      u32 g = 0;
+      for (u32 off = goff0; seed_id < max_seeds && off < L; off += 8, ++seed_id, ++g) {
+        const ReseedResult& q = s_res[wid][nsel + g];
+        const u32 cur = L - off;
+        if (q.hits == 1) { if (q.flags & 2u) tw.emit(2 * ix.N - q.val - q.mlen - off, 0, 0, 0); else tw.emit(q.sp, 1, q.mlen, off); }
+        else if (q.mlen >= 20 && q.hits <= MAX_SEED_HITS) { if (q.hits) tw.emit(q.sp, q.hits, q.mlen, off); }
+        else if (cur == q.mlen) break;
+      }
+      tw.store();
     }
-    tw.store();
+    __syncwarp();
   }
   flush_counters(s_cnt, cn, b.counters);
 }
 
+
 // re-seeded mates: keep the windows near a hit of the (final) primary before verifying them
-__global__ void sens_reseed_filter(BatchView b) {
+__global__ void __launch_bounds__(128) sens_reseed_filter(BatchView b) {
   const u32 n4 = *b.status ? 0u : b.list_count[2];
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const u32 warps = gridDim.x * (blockDim.x >> 5);
+  for (u32 i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n4; i += warps) {      // one warp per re-seeded mate
     const int r = (int)b.list4[i], mate = r ^ 1;
     int dmax, dmin; pair_bounds(b, r & ~1, r | 1, dmax, dmin);
     const bmbs_cand* hits = b.out_cand + b.res_first[mate]; const int nh = (int)b.res_n[mate];
     const u32 beg = b.coff[r], n = b.nv[r];
-    u32 kept = 0; int next = 0;
-    for (u32 j = 0; j < n; ++j) {
-      const u64 site = b.cand[beg + j];
-      if (mate_in_range(site, hits, nh, dmax, dmin, next)) { b.cand[beg + kept] = site; b.vcnt[beg + kept] = b.vcnt[beg + j]; ++kept; }
+    bool ok = true;
+    for (u32 j = lane; j < n; j += 32) ok = ok && b.cand[beg + j] < SITE_SANE;
+    const bool sane = __all_sync(0xffffffffu, ok) && warp_all_sane(hits, (u32)nh, lane);
+    u32 kept = 0;
+    if (!sane) {
+      if (lane == 0) {
+        int next = 0;
+        for (u32 j = 0; j < n; ++j) {
+          const u64 site = b.cand[beg + j];
+          if (mate_in_range(site, hits, nh, dmax, dmin, next)) { b.cand[beg + kept] = site; b.vcnt[beg + kept] = b.vcnt[beg + j]; ++kept; }
+        }
+      }
+    } else {
+      for (u32 base = 0; base < n; base += 32) {
+        const u32 j = base + lane;
+        u64 site = 0; u32 vote = 0;
+        if (j < n) { site = b.cand[beg + j]; vote = b.vcnt[beg + j]; }
+        const bool keep = j < n && in_range_pure(site, hits, nh, dmax, dmin);
+        const u32 km = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();
+        if (keep) { const u32 at = beg + kept + __popc(km & ((1u << lane) - 1u)); b.cand[at] = site; b.vcnt[at] = vote; }
+        kept += __popc(km);
+        __syncwarp();
+      }
     }
-    b.nv[r] = kept;
+    if (lane == 0) b.nv[r] = kept;
+    __syncwarp();
   }
 }
 
-__global__ void sens_reseed_finish(BatchView b) {
+__global__ void __launch_bounds__(128) sens_reseed_finish(BatchView b) {
   const u32 n4 = *b.status ? 0u : b.list_count[2];
   const u64 base = b.totals[2];
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const u32 warps = gridDim.x * (blockDim.x >> 5);
+  for (u32 i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n4; i += warps) {
     const int r = (int)b.list4[i];
     const u32 first = (u32)(base + b.voff[r]);
-    b.res_first[r] = first;
-    b.res_n[r] = keep_hits_inplace(b.out_cand + first, b.nv[r], b.kk[r], nullptr, 0, 0, 0);
+    const u32 kept = warp_keep_hits(b.out_cand + first, b.nv[r], b.kk[r], nullptr, 0, 0, 0, lane);
+    if (lane == 0) { b.res_first[r] = first; b.res_n[r] = kept; }
   }
 }
 

@@ -8,7 +8,7 @@
 //   --unmapped_out  --ambiguous_out
 //   --mp_max/--mp_min/--np/--gap_open/--gap_extension  --phred33/--phred64   -g/--gpus <n>
 // Records are written in input order (the reference's `-t 1` order).
-// Pipeline: block splitter -> FASTQ parse workers -> GPU threads (two batches in flight per device: H2D, kernels,
+// Pipeline: block splitter -> FASTQ parse workers -> GPU threads (three batches in flight per device: H2D, kernels,
 // D2H through include/bmbs.h) -> host finishing workers (reduction, CIGAR, MAPQ, SAM text) -> ordered writer.
 #include <atomic>
 #include <chrono>
@@ -250,7 +250,10 @@ int search(const Options& o, const std::string& cmdline) {
 
   // splitter -> parse workers -> GPU threads (two batches in flight per device) -> finish workers -> ordered writer
   const double t1 = now();
-  const int n_parse = std::max(1, o.threads / 2), n_finish = std::max(1, o.threads), n_gpu = 2 * (int)devs.size();
+  // batches in flight per device: a sub-block of 32 k reads does not fill a B200 (and its slowest reads set the pace of
+  // every kernel), so three of them share the device on their own streams while their copies overlap (BMBS_INFLIGHT to change)
+  const int inflight = getenv("BMBS_INFLIGHT") ? std::max(1, atoi(getenv("BMBS_INFLIGHT"))) : 3;
+  const int n_parse = std::max(1, o.threads / 2), n_finish = std::max(1, o.threads), n_gpu = inflight * (int)devs.size();
   std::atomic<long long> us_split(0), us_parse(0), us_gpu(0), us_finish(0), us_write(0), n_retry(0), n_batches(0), us_dev(0), us_up(0), us_run(0), us_down(0), us_prep(0);
   std::atomic<long long> us_stage[8] = {};
   auto us = [](double a, double b) { return (long long)((b - a) * 1e6); };

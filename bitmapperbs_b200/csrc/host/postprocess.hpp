@@ -91,13 +91,30 @@ struct Genome2bit {
   // like the reference's (Schema.cpp:4998-5050).
   void window_fwd(uint64_t start, uint64_t len, char* out) const {
     if (start >= N || start + len > N) { memset(out, 0, len); return; }
-    for (uint64_t i = 0; i < len; ++i) out[i] = base(start + i);
+    uint64_t i = 0, pos = start;
+    for (; i < len && (pos & 3); ++i, ++pos) out[i] = base(pos);                       // up to the next byte boundary
+    const uint32_t* lut = fwd_lut();
+    for (; i + 4 <= len; i += 4, pos += 4) memcpy(out + i, &lut[pac[pos >> 2]], 4);     // four bases per byte
+    for (; i < len; ++i, ++pos) out[i] = base(pos);
   }
   // Reverse-complement window: out[i] = complement(G[N-1-rc_start-i]) (Schema.cpp:5061-5115).
   void window_rc(uint64_t rc_start, uint64_t len, char* out) const {
     uint64_t last = N - rc_start - 1;
     if (last < len - 1 || (last >> 2) >= pac.size()) { memset(out, 0, len); return; }
-    for (uint64_t i = 0; i < len; ++i) out[i] = "TGCA"[(pac[(last - i) >> 2] >> (6 - 2 * ((last - i) & 3))) & 3];
+    uint64_t i = 0, pos = last;                                                         // walks down the genome
+    for (; i < len && (pos & 3) != 3; ++i, --pos) out[i] = "TGCA"[(pac[pos >> 2] >> (6 - 2 * (pos & 3))) & 3];
+    const uint32_t* lut = rc_lut();
+    for (; i + 4 <= len; i += 4, pos -= 4) memcpy(out + i, &lut[pac[pos >> 2]], 4);     // a whole byte, last base first, complemented
+    for (; i < len; ++i, --pos) out[i] = "TGCA"[(pac[pos >> 2] >> (6 - 2 * (pos & 3))) & 3];
+  }
+  // byte -> its four bases as characters (first base in the low byte of the word), and reversed + complemented
+  static const uint32_t* fwd_lut() {
+    static const struct T { uint32_t v[256]; T() { for (int b = 0; b < 256; ++b) { char c[4]; for (int t = 0; t < 4; ++t) c[t] = "ACGT"[(b >> (6 - 2 * t)) & 3]; memcpy(&v[b], c, 4); } } } t;
+    return t.v;
+  }
+  static const uint32_t* rc_lut() {
+    static const struct T { uint32_t v[256]; T() { for (int b = 0; b < 256; ++b) { char c[4]; for (int t = 0; t < 4; ++t) c[t] = "TGCA"[(b >> (2 * t)) & 3]; memcpy(&v[b], c, 4); } } } t;
+    return t.v;
   }
   // Double-strand coordinate: [0,N) forward strand, [N,2N) reverse complement.
   void window(uint64_t site, uint64_t len, char* out) const {

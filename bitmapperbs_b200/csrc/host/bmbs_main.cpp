@@ -5,7 +5,7 @@
 //   --search <genome.fa> --seq <r.fq[.gz]>       single-end mapping
 //   --search <genome.fa> --seq1 <a> --seq2 <b> --pe   paired-end mapping (fast mode)
 //   -o <out.sam>  -t <host threads>  -e <rate>  --seed <len>  --min/--max <insert>  --mapstats <file>
-//   --unmapped_out  --ambiguous_out
+//   --unmapped_out  --ambiguous_out  --bam
 //   --mp_max/--mp_min/--np/--gap_open/--gap_extension  --phred33/--phred64   -g/--gpus <n>
 // Records are written in input order (the reference's `-t 1` order).
 // Pipeline: block splitter -> FASTQ parse workers -> GPU threads (three batches in flight per device: H2D, kernels,
@@ -26,6 +26,7 @@
 #include <unistd.h>
 #include "../../../include/bmbs.h"
 #include "../../indexer/build_index.hpp"
+#include "bam.hpp"
 #include "mapper.hpp"
 
 using namespace bmbs;
@@ -34,7 +35,7 @@ namespace {
 
 struct Options {
   std::string mode, genome, seq, seq1, seq2, out = "output", mapstats;
-  bool pe = false, sensitive = false, unmapped_out = false, ambiguous_out = false;
+  bool pe = false, sensitive = false, unmapped_out = false, ambiguous_out = false, bam = false;
   int threads = 1, gpus = 1;
   size_t batch_reads = 1 << 15;                      // reads (pairs) per batch
   bmbs_params prm; Scoring sc;
@@ -80,6 +81,8 @@ void parse(int argc, char** argv, Options& o) {
     else if (a == "--sensitive") o.sensitive = true;
     else if (a == "--fast") o.sensitive = false;
     else if (a == "--unmapped_out") o.unmapped_out = true;
+    else if (a == "--bam") o.bam = true;
+    else if (a == "--sam") o.bam = false;
     else if (a == "--ambiguous_out") o.ambiguous_out = true;
     else if (a == "-o") o.out = val();
     else if (a == "-t" || a == "--threads") o.threads = atoi(val().c_str());
@@ -97,7 +100,7 @@ void parse(int argc, char** argv, Options& o) {
     else if (a == "--phred64") o.sc.q_base = 64;
     else if (a == "-g" || a == "--gpus") o.gpus = atoi(val().c_str());
     else if (a == "--batch") o.batch_reads = (size_t)atoll(val().c_str());
-    else die("unknown or unsupported option " + a + " (supported: --index --search --seq --seq1 --seq2 --pe --fast --sensitive --unmapped_out --ambiguous_out -o -t -e --seed --min --max --mapstats scoring flags --phred33/64 --gpus --batch)");
+    else die("unknown or unsupported option " + a + " (supported: --index --search --seq --seq1 --seq2 --pe --fast --sensitive --unmapped_out --ambiguous_out --bam --sam -o -t -e --seed --min --max --mapstats scoring flags --phred33/64 --gpus --batch)");
   }
   if (!o.seq1.empty() && !o.seq2.empty()) o.pe = true;   // Process_CommandLines.cpp:314-317
   if (o.threads < 1) o.threads = 1;
@@ -242,7 +245,12 @@ int search(const Options& o, const std::string& cmdline) {
   else if (!q1.open(o.seq)) die("cannot open " + o.seq);
   FILE* fo = fopen(o.out.c_str(), "w");
   if (!fo) die("cannot write " + o.out);
-  { std::string h; sam_header(h, hc.chroms, cmdline); fwrite(h.data(), 1, h.size(), fo); fflush(fo); }
+  BamWriter bam;
+  {
+    std::string h; sam_header(h, hc.chroms, cmdline);
+    if (o.bam) { std::string raw, z; bam.header(hc.chroms, h, raw); if (!BamWriter::bgzf(raw, z)) die("BGZF compression failed"); h.swap(z); }
+    fwrite(h.data(), 1, h.size(), fo); fflush(fo);
+  }
   // batches of SAM text go straight to the descriptor: no second copy through the stdio buffer
   auto write_all = [&](const char* p, size_t n) {
     while (n) { const ssize_t w = ::write(fileno(fo), p, n); if (w <= 0) die("write failed on " + o.out); p += w; n -= (size_t)w; }
@@ -338,7 +346,18 @@ int search(const Options& o, const std::string& cmdline) {
     if (bmbs_refiner_create(idx, devs[t % devs.size()], &refiner)) die(std::string("refiner create: ") + bmbs_last_error());
     FinishScratch fs; long long n_dp = 0;
     std::unique_ptr<Batch> b;
-    while (fin_q.pop(b)) { const double ts = now(); finish_batch(hc, *b, pe, o.unmapped_out, refiner, fs, n_dp); us_finish += us(ts, now()); out_q.push(std::move(b)); }
+    std::string raw;
+    while (fin_q.pop(b)) {
+      const double ts = now();
+      finish_batch(hc, *b, pe, o.unmapped_out, refiner, fs, n_dp);
+      if (o.bam) {      // --bam: the sub-block's records as BGZF members (bam_prase.cpp:248-274 does this per line through htslib)
+        raw.clear(); bam.records(b->sam, raw);
+        std::string z; z.reserve(raw.size() / 3 + 64);
+        if (!BamWriter::bgzf(raw, z)) die("BGZF compression failed");
+        b->sam.swap(z);
+      }
+      us_finish += us(ts, now()); out_q.push(std::move(b));
+    }
     bmbs_refiner_free(refiner);
     n_dp_total += n_dp;
     if (--live_finish == 0) out_q.close();
@@ -360,6 +379,7 @@ int search(const Options& o, const std::string& cmdline) {
       }
     }
   }
+  if (o.bam) { std::string z; BamWriter::eof_marker(z); write_all(z.data(), z.size()); }
   splitter.join(); for (auto& w : pool) w.join();
   if (getenv("BMBS_TIMING")) {
     fprintf(stderr, "[bmbs timing] gpu threads: prepare %.2f  upload %.2f  run(enqueue) %.2f  download(wait+copy) %.2f  | device %.3f s: pack %.3f seed %.3f locate %.3f votes %.3f pairfilter %.3f verify %.3f sensitive %.3f\n",

@@ -314,3 +314,20 @@ def test_staged_batch_counters_and_idempotence(golden, gidx):
     assert c["hash_queries"] >= len(reads) * 0.9 and c["occ_lookups"] > 0 and c["verified"] == (r1["n_cand"][r1["state"] == B.VERIFY]).sum()
     assert c["cells"] == sum(int(n) * len(rd) * (2 * min(31, int(0.08 * len(rd))) + 1) for n, rd, s in zip(r1["n_cand"], reads, r1["state"]) if s == B.VERIFY)
     assert t["total"] > 0 and b.launches() >= 12
+
+
+@pytest.mark.parametrize("name,args", [("se100", ["--seq", "se100.fq"]), ("pe100hs", ["--seq1", "pe100h_1.fq", "--seq2", "pe100h_2.fq", "--pe", "--sensitive"])])
+def test_mapper_bam_output_holds_the_same_records(golden, built, name, args):
+    """--bam: the BGZF/BAM container written by the mapper decodes (gzip + struct only) to the records of the reference's SAM"""
+    from test_host_bam import decode_bam
+    subprocess.run([str(built["bmbs"]), "--search", "genome.fa", *args, "-t", "4", "--bam", "-o", "gpu.bam", "--batch", "700"],
+                   cwd=golden, check=True, stderr=subprocess.DEVNULL)
+    text, refs, recs, n_members = decode_bam(golden / "gpu.bam")
+    assert text.startswith("@HD") and [r[0] for r in refs] == [l.split("\t")[1][3:] for l in text.splitlines() if l.startswith("@SQ")]
+    lines = [l.decode().rstrip("\n").split("\t") for l in sam_body(golden / f"{name}.sam")]
+    assert len(recs) == len(lines) and n_members > 3
+    rid = {n: i for i, (n, _) in enumerate(refs)}
+    for f, r in zip(lines, recs):
+        assert (r["name"], r["flag"], r["rid"], r["pos"], r["mapq"], r["cigar"], r["seq"], r["qual"], r["tags"]) == \
+               (f[0], int(f[1]), rid[f[2]], int(f[3]) - 1, int(f[4]), f[5], f[9], f[10], f[11:])
+        assert r["npos"] == int(f[7]) - 1 and r["tlen"] == int(f[8])

@@ -1,14 +1,18 @@
 // CUDA kernels of the seed-and-verify path (sm_100a; integer / bit-vector work, no tensor cores).
 //
-//   pack_reads      ASCII -> nibble codes, first-C position, error threshold k
-//   seed_reads      kernel 1a: per-read seeding state machine (FM backward search with the 16-mer table,
-//                   unique-hit shortcut with direct genome compare, one-mismatch second seed, remaining seeds)
-//   expand_locate   kernel 1b: seed intervals -> one candidate site per row (dense suffix array gather, or LF-walk to a sampled row)
-//   votes_small/big kernel 2: per-read sort, run-length votes with the site-k shift
-//   filter_pairs    kernel 2b (paired end): distance pre-filter of the two mates' lists
-//   gather_work     compaction of the surviving windows into the verification work list
-//   verify_windows  kernel 3: banded Myers bit-vector edit distance, read T may face reference C
-//   finalize_reads  per-read result records
+//   pack_reads       ASCII -> nibble codes + bit-plane chunks, first-C position, error threshold k
+//   seed_first       kernel 1a, phase 1: first seed of every read (deep K-mer table), unique-hit shortcut with direct genome compare
+//   seed_second      kernel 1a, phase 2: the one-mismatch second seed
+//   seed_rest        kernel 1a, phase 3: the remaining greedy seeds
+//   expand_locate    kernel 1b: seed intervals -> one candidate site per row (dense suffix array gather, or LF-walk to a sampled row)
+//   votes_classify   kernel 2: what a read's candidates turn into; short segments sorted + run-length encoded in registers
+//   votes_sort<32>, votes_big   kernel 2 for segments of 17..32 (a warp) and longer (a CTA)
+//   filter_pairs_kernel         kernel 2b (paired end): distance pre-filter of the two mates' lists
+//   gather_work      the surviving windows as one VerifyItem each (resolved reads get their record directly)
+//   verify_windows   kernel 3: banded Myers bit-vector edit distance, read T may face reference C
+//   sens_pair, seed_reseed, sens_reseed_filter, sens_reseed_finish   --pe --sensitive: pair logic and the re-seeding round
+//   refine_dp        CIGAR refinement: banded affine-gap DP with traceback
+//   finalize_reads   per-read result records
 #pragma once
 #include "bmbs_device.cuh"
 #include "../../include/bmbs.h"
@@ -56,7 +60,7 @@ struct BatchView {
   // work list
   VerifyItem* vitems; bmbs_cand* out_cand;      // dense list of the windows that need the bit-vector kernel (count: list_count[3])
   bmbs_read_result* out_res;
-  u32* sort16; u32* sort32; u32* sort_count;     // reads whose candidate segment (<= 16 / <= 32 entries) has to be sorted
+  u32* sort32; u32* sort_count;                  // reads whose candidate segment (17..32 entries) is sorted by a warp; count in sort_count[1]
   u32* big_list; u32* big_count; u64* scratch; u32* scratch_used; u64 scratch_cap;
   u64* counters; u64* totals;   // totals[0] candidate slots, [1] verification work items of this round, [2] out_cand base of this round, [3] out_cand entries in all
   u32* status;                  // bit0 per-read task overflow, bit1 slot capacity, bit2 work capacity, bit3 scratch
@@ -729,12 +733,12 @@ __global__ void __launch_bounds__(128) votes_classify(BatchView b) {
   list_append(b.big_list, b.big_count, which == 2, (u32)r);
 }
 
-// W lanes per read (16 or 32): bitonic sort in registers over shuffles, run-length encode with a ballot, written back in
+// W lanes per read (32; segments up to 16 are sorted by their own thread in votes_classify): bitonic sort in registers over shuffles, run-length encode with a ballot, written back in
 // place.  Padding is ~0: a real candidate equal to it sorts next to the padding, so the first n entries are still right.
 template <int W>
 __global__ void __launch_bounds__(128) votes_sort(BatchView b) {
-  const u32 nlist = *b.status ? 0u : b.sort_count[W == 16 ? 0 : 1];
-  const u32* list = W == 16 ? b.sort16 : b.sort32;
+  const u32 nlist = *b.status ? 0u : b.sort_count[1];
+  const u32* list = b.sort32;
   const int lane = threadIdx.x & 31, sub = lane & (W - 1), half_shift = lane & ~(W - 1);
   const u32 groups = gridDim.x * blockDim.x / W;
   for (u32 g0 = 0; g0 < nlist; g0 += groups) {

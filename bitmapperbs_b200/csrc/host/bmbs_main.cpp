@@ -5,7 +5,7 @@
 //   --search <genome.fa> --seq <r.fq[.gz]>       single-end mapping
 //   --search <genome.fa> --seq1 <a> --seq2 <b> --pe   paired-end mapping (fast mode)
 //   -o <out.sam>  -t <host threads>  -e <rate>  --seed <len>  --min/--max <insert>  --mapstats <file>
-//   --unmapped_out  --ambiguous_out  --bam
+//   --unmapped_out  --ambiguous_out  --bam  --pbat
 //   --mp_max/--mp_min/--np/--gap_open/--gap_extension  --phred33/--phred64   -g/--gpus <n>
 // Records are written in input order (the reference's `-t 1` order).
 // Pipeline: block splitter -> FASTQ parse workers -> GPU threads (three batches in flight per device: H2D, kernels,
@@ -35,7 +35,7 @@ namespace {
 
 struct Options {
   std::string mode, genome, seq, seq1, seq2, out = "output", mapstats;
-  bool pe = false, sensitive = false, unmapped_out = false, ambiguous_out = false, bam = false;
+  bool pe = false, sensitive = false, unmapped_out = false, ambiguous_out = false, bam = false, pbat = false;
   int threads = 1, gpus = 1;
   size_t batch_reads = 1 << 15;                      // reads (pairs) per batch
   bmbs_params prm; Scoring sc;
@@ -82,6 +82,7 @@ void parse(int argc, char** argv, Options& o) {
     else if (a == "--fast") o.sensitive = false;
     else if (a == "--unmapped_out") o.unmapped_out = true;
     else if (a == "--bam") o.bam = true;
+    else if (a == "--pbat") o.pbat = true;
     else if (a == "--sam") o.bam = false;
     else if (a == "--ambiguous_out") o.ambiguous_out = true;
     else if (a == "-o") o.out = val();
@@ -100,9 +101,10 @@ void parse(int argc, char** argv, Options& o) {
     else if (a == "--phred64") o.sc.q_base = 64;
     else if (a == "-g" || a == "--gpus") o.gpus = atoi(val().c_str());
     else if (a == "--batch") o.batch_reads = (size_t)atoll(val().c_str());
-    else die("unknown or unsupported option " + a + " (supported: --index --search --seq --seq1 --seq2 --pe --fast --sensitive --unmapped_out --ambiguous_out --bam --sam -o -t -e --seed --min --max --mapstats scoring flags --phred33/64 --gpus --batch)");
+    else die("unknown or unsupported option " + a + " (supported: --index --search --seq --seq1 --seq2 --pe --fast --sensitive --unmapped_out --ambiguous_out --bam --sam --pbat -o -t -e --seed --min --max --mapstats scoring flags --phred33/64 --gpus --batch)");
   }
   if (!o.seq1.empty() && !o.seq2.empty()) o.pe = true;   // Process_CommandLines.cpp:314-317
+  if (o.pbat && o.pe) std::swap(o.seq1, o.seq2);           // exchange_two_reads, Bitmapper_main.cpp:169-172
   if (o.threads < 1) o.threads = 1;
   unsigned hw = std::thread::hardware_concurrency();
   if (hw && (unsigned)o.threads > hw) o.threads = (int)hw;  // the reference caps -t at the online CPUs (:254-258)
@@ -126,7 +128,7 @@ inline void upper_in_place(std::string_view v) {
 }
 
 // FASTQ text -> batch (names cut, bases upper-cased, mate 2 reverse-complemented for alignment): Process_Reads.cpp:62-90, :321-472
-void parse_batch(RawBatch& rb, bool pe, Batch& b) {
+void parse_batch(RawBatch& rb, bool pe, bool pbat_se, Batch& b) {
   b.seq_no = rb.seq_no;
   // moving a std::string keeps its heap buffer, so views into own* stay valid; short strings live inside the object: re-point
   const bool o1 = rb.raw1.data() == rb.own1.data(), o2 = rb.raw2.data() == rb.own2.data();
@@ -149,7 +151,13 @@ void parse_batch(RawBatch& rb, bool pe, Batch& b) {
     if (!pe) {
       record(p1, e1, b.name[u], b.fq_seq[u], b.qual[u]);
       cut_name_se(b.name[u]);
-      b.flat.append(b.fq_seq[u]); b.offsets[u + 1] = b.flat.size();
+      if (!pbat_se) b.flat.append(b.fq_seq[u]);
+      else {      // --pbat: the reverse complement is aligned (post_process_single_reads_pbat, Process_Reads.cpp:476)
+        const std::string_view s1 = b.fq_seq[u]; const size_t at = b.flat.size(); b.flat.resize(at + s1.size());
+        const char* comp = complement_table();
+        for (size_t t = 0; t < s1.size(); ++t) b.flat[at + t] = comp[(unsigned char)s1[s1.size() - 1 - t]];
+      }
+      b.offsets[u + 1] = b.flat.size();
     } else {
       const size_t i = 2 * u, k = i + 1;
       record(p1, e1, b.name[i], b.fq_seq[i], b.qual[i]);
@@ -177,7 +185,7 @@ void finish_batch(const HostContext& hc, Batch& b, bool pe, bool unmapped_out, b
   fs.unit.clear(); fs.at.clear();
   auto one = [&](int u, std::string& out, MapStats& st) {
     if (!pe) {
-      ReadView rv{b.name[u], b.seq(u), b.qual[u]};
+      ReadView rv{b.name[u], b.seq(u), b.qual[u], b.fq_seq[u]};
       finish_single(hc, rv, b.res[u], b.cand.data(), out, st, fs.v1, fs.win, &dq);
     } else {
       finish_pair(hc, b.name[2 * u], b.seq(2 * u), b.qual[2 * u], b.name[2 * u + 1], b.seq(2 * u + 1), b.fq_seq[2 * u + 1], b.qual[2 * u + 1],
@@ -230,7 +238,7 @@ void print_stats(FILE* f, const MapStats& st) {
 
 int search(const Options& o, const std::string& cmdline) {
   const double t0 = now();
-  HostContext hc; hc.sc = o.sc; hc.prm = o.prm; hc.ambiguous_out = o.ambiguous_out;
+  HostContext hc; hc.sc = o.sc; hc.prm = o.prm; hc.ambiguous_out = o.ambiguous_out; hc.pbat = o.pbat && !o.pe;
   const std::string prefix = o.genome + ".index";
   if (!hc.chroms.load(prefix)) die("cannot open " + prefix);
   if (!hc.genome.load(prefix + ".bs.pac", hc.chroms.N)) die("cannot open " + prefix + ".bs.pac");
@@ -287,7 +295,7 @@ int search(const Options& o, const std::string& cmdline) {
   std::vector<std::thread> pool;
   for (int t = 0; t < n_parse; ++t) pool.emplace_back([&] {
     std::unique_ptr<RawBatch> rb;
-    while (raw_q.pop(rb)) { const double ts = now(); std::unique_ptr<Batch> b(new Batch()); parse_batch(*rb, pe, *b); us_parse += us(ts, now()); gpu_q.push(std::move(b)); }
+    while (raw_q.pop(rb)) { const double ts = now(); std::unique_ptr<Batch> b(new Batch()); parse_batch(*rb, pe, o.pbat && !pe, *b); us_parse += us(ts, now()); gpu_q.push(std::move(b)); }
     if (--live_parse == 0) gpu_q.close();
   });
   for (int g = 0; g < n_gpu; ++g) pool.emplace_back([&, g] {

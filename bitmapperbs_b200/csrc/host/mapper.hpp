@@ -29,7 +29,7 @@ inline void unpack_cands(const bmbs_cand* c, uint32_t n, std::vector<HostHit>& v
   }
 }
 
-struct ReadView { std::string_view name, seq, qual; };
+struct ReadView { std::string_view name, seq, qual, raw; };   // seq: as aligned; raw: as it stands in the FASTQ (differs with --pbat)
 
 struct HostContext {
   ChromTable chroms;
@@ -37,6 +37,11 @@ struct HostContext {
   Scoring sc;
   bmbs_params prm;
   bool ambiguous_out = false;   // --ambiguous_out: report the first hit of an ambiguously mapped read (pair)
+  // --pbat, single end (Map_Single_Seq_split_pbat, Schema.cpp:27879; reads stored by post_process_single_reads_pbat,
+  // Process_Reads.cpp:476): the reverse complement of the FASTQ record is what gets aligned -- the treatment mate 2 of a pair
+  // gets -- so qualities are taken in reverse for scoring and the record itself is printed for reverse-strand hits
+  // (output_sam_end_to_end_pbat_output_buffer, :13215).  Paired end: the two input files change places (exchange_two_reads).
+  bool pbat = false;
 };
 
 inline uint64_t threshold_k(double e_rate, size_t L) { uint64_t k = (uint64_t)(e_rate * L); return k >= 31 ? 31 : k; }
@@ -51,7 +56,8 @@ inline void finish_single(const HostContext& hc, const ReadView& rd, const bmbs_
   auto emit = [&](uint64_t site, uint64_t end_site, int start_site, unsigned nm, const std::string& cigar, int mapq) -> bool {
     Placed p = place(hc.chroms, site, (uint64_t)(int64_t)start_site, end_site);
     if (p.off_chrom) return false;
-    sam_record_se(out, rd.name, seq, qual, hc.chroms, p, mapq, cigar, nm);
+    if (!hc.pbat) sam_record_se(out, rd.name, seq, qual, hc.chroms, p, mapq, cigar, nm);
+    else sam_record_se_pbat(out, rd.name, seq, rd.raw, qual, hc.chroms, p, mapq, cigar, nm);
     return true;
   };
   switch (res.state) {
@@ -68,7 +74,7 @@ inline void finish_single(const HostContext& hc, const ReadView& rd, const bmbs_
     case BMBS_ONE_MISMATCH: {
       const int pos = res.one_mismatch_pos;
       int score = 0;
-      if (seq[pos] == 'N') score -= hc.sc.n_pen; else score -= mismatch_penalty(hc.sc, qual[pos]);
+      if (seq[pos] == 'N') score -= hc.sc.n_pen; else score -= mismatch_penalty(hc.sc, qual[hc.pbat ? L - 1 - pos : pos]);   // :28703 pbat reads the quality from the other end
       const int mapq = mapq_from(0xFFFFFFFFu, (unsigned)k, score, hc.sc);
       if (emit(res.site, L - 1, 0, 1, std::to_string(L) + "M", mapq)) { ++st.unique; st.bases += L; st.err_bases += 1; }
       return;
@@ -103,7 +109,7 @@ inline void finish_single(const HostContext& hc, const ReadView& rd, const bmbs_
   if (b.err != 0) {
     const int plen = L + 2 * (int)k; win.resize(plen + 8);
     hc.genome.window(b.site, plen, win.data());
-    refine_alignment(win.data(), plen, seq.data(), L, (int)k, (int)b.end_site, b.err, b.site < hc.chroms.N, qual.data(), false, hc.sc, rf, b.site, dq);
+    refine_alignment(win.data(), plen, seq.data(), L, (int)k, (int)b.end_site, b.err, b.site < hc.chroms.N, qual.data(), hc.pbat, hc.sc, rf, b.site, dq);
   } else { rf.score = 0; rf.start_site = (int)b.end_site - L + 1; rf.end_site = b.end_site; rf.err = 0; rf.cigar = std::to_string(L) + "M"; }
   const int mapq = mapq_from(sbd, (unsigned)k, rf.score, hc.sc);
   if (emit(b.site, rf.end_site, rf.start_site, rf.err, rf.cigar, mapq)) {

@@ -53,6 +53,21 @@ inline void sam_record_se(std::string& out, std::string_view name, std::string_v
   out += "\tNM:i:"; append_uint(out, nm); out += '\n';
 }
 
+// --pbat single-end record (output_sam_end_to_end_pbat_output_buffer, Schema.cpp:13215-13450): `seq` is what was aligned (the
+// reverse complement of the FASTQ record `raw`), `qual` in FASTQ order
+inline void sam_record_se_pbat(std::string& out, std::string_view name, std::string_view seq, std::string_view raw, std::string_view qual,
+                               const ChromTable& ct, const Placed& p, int mapq, const std::string& cigar, unsigned nm) {
+  out += name; out += '\t';
+  append_uint(out, (uint64_t)p.flag); out += '\t';
+  out += ct.name[p.chrom]; out += '\t';
+  append_uint(out, p.pos); out += '\t';
+  append_int(out, mapq); out += '\t';
+  out += cigar; out += "\t*\t0\t0\t";
+  if (p.flag == 0) { out += seq; out += '\t'; append_reversed(out, qual); }
+  else { out += raw; out += '\t'; out += qual; }
+  out += "\tNM:i:"; append_uint(out, nm); out += '\n';
+}
+
 // Paired-end record (Schema.cpp:9453-9700 mate 1, :10922-11170 mate 2).  `seq` is
 // what was aligned, `rseq` its reverse complement (empty: computed here), `qual` the FASTQ-order
 // qualities; for mate 2 `seq` is the reverse complement of the FASTQ record.

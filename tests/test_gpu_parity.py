@@ -266,6 +266,12 @@ def test_live_reference_binary_agrees_on_fresh_data(built, tmp_path):
     S.write_fastq(tmp_path / "a.fq", a); S.write_fastq(tmp_path / "b.fq", b)
     c, d = S.simulate_reads(chroms, 8000, 120, seed=7, paired=True, sub=0.06, indel=0.008, n_rate=0.003, random_qual=True, frag_range=(150, 450), junk_fraction=0.03)
     S.write_fastq(tmp_path / "c.fq", c); S.write_fastq(tmp_path / "d.fq", d)
+    # --pbat data: the reverse complements of directional reads (qualities reversed with them)
+    comp = bytes.maketrans(b"ACGTacgt", b"TGCAtgca")
+    with open(tmp_path / "r.fq", "rb") as f, open(tmp_path / "r_rc.fq", "wb") as o:
+        ls = f.read().split(b"\n")
+        for i in range(0, len(ls) - 1, 4):
+            o.write(ls[i] + b"\n" + ls[i + 1].translate(comp)[::-1] + b"\n+\n" + ls[i + 3][::-1] + b"\n")
     subprocess.run([str(built["indexer"]), "g.fa"], cwd=tmp_path, check=True, stderr=subprocess.DEVNULL)
     for tag, args in (("se", ["--seq", "r.fq"]), ("pe", ["--seq1", "a.fq", "--seq2", "b.fq", "--pe"]),
                       ("pes", ["--seq1", "a.fq", "--seq2", "b.fq", "--pe", "--sensitive"]),
@@ -280,7 +286,11 @@ def test_live_reference_binary_agrees_on_fresh_data(built, tmp_path):
                       ("se_ambiguous", ["--seq", "r.fq", "--ambiguous_out"]),
                       ("se_both", ["--seq", "r.fq", "--ambiguous_out", "--unmapped_out"]),
                       ("hard_ambiguous", ["--seq1", "c.fq", "--seq2", "d.fq", "--pe", "--ambiguous_out", "--unmapped_out"]),
-                      ("hards_ambiguous", ["--seq1", "c.fq", "--seq2", "d.fq", "--pe", "--sensitive", "--ambiguous_out"])):
+                      ("hards_ambiguous", ["--seq1", "c.fq", "--seq2", "d.fq", "--pe", "--sensitive", "--ambiguous_out"]),
+                      ("se_pbat", ["--seq", "r_rc.fq", "--pbat", "--unmapped_out", "--ambiguous_out"]),
+                      ("se_pbat_directional", ["--seq", "r.fq", "--pbat", "--unmapped_out"]),
+                      ("pe_pbat", ["--seq1", "b.fq", "--seq2", "a.fq", "--pe", "--pbat"]),
+                      ("hards_pbat", ["--seq1", "d.fq", "--seq2", "c.fq", "--pe", "--sensitive", "--pbat", "--unmapped_out"])):
         subprocess.run([str(built["ref"]), "--search", "g.fa", *args, "-t", "1", "-o", f"cpu_{tag}.sam", "--mapstats", f"cpu_{tag}.st"],
                        cwd=tmp_path, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         subprocess.run([str(built["bmbs"]), "--search", "g.fa", *args, "-t", "4", "-o", f"gpu_{tag}.sam", "--mapstats", f"gpu_{tag}.st"],

@@ -2,8 +2,11 @@
 // pair pick, CIGAR refinement with the DP on the CPU, MAPQ, SAM text) fed with the per-read records of the ORACLE instead of
 // the GPU library -- both produce the same bmbs_read_result / bmbs_cand arrays (tests/test_gpu_parity.py checks that on the
 // GPU box).  The SAM it writes must equal the reference's golden SAM: that pins the host glue without a GPU.
-//   host_finish_harness se|pe|pes <genome.fa> <out.sam> <reads.fq> [<mates.fq>] [--unmapped_out]
+//   host_finish_harness se|pe|pes <genome.fa> <out.sam> <reads.fq> [<mates.fq>] [--unmapped_out] [--ambiguous_out] [--pbat]
+// (--ambiguous_out: paired end only here -- the single-end multi-exact case needs the located rows in row order, which only the
+// device path returns; --pbat as in bmbs_main.cpp: single end aligns the reverse complement, paired end swaps the files)
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -14,11 +17,12 @@ int main(int argc, char** argv) {
   if (argc < 5) return 2;
   const std::string mode = argv[1], fa = argv[2], out_path = argv[3];
   const bool pe = mode != "se", sens = mode == "pes";
-  bool unmapped_out = false;
+  bool unmapped_out = false, ambiguous_out = false, pbat = false;
   std::vector<std::string> files;
-  for (int i = 4; i < argc; ++i) { if (!strcmp(argv[i], "--unmapped_out")) unmapped_out = true; else files.push_back(argv[i]); }
+  for (int i = 4; i < argc; ++i) { if (!strcmp(argv[i], "--unmapped_out")) unmapped_out = true; else if (!strcmp(argv[i], "--ambiguous_out")) ambiguous_out = true; else if (!strcmp(argv[i], "--pbat")) pbat = true; else files.push_back(argv[i]); }
+  if (pbat && pe) std::swap(files[0], files[1]);
   bmbs::HostContext hc;
-  hc.prm.e_rate = 0.08; hc.prm.seed_len = 30; hc.prm.min_ins = 0; hc.prm.max_ins = 500; hc.prm.sensitive = sens ? 1 : 0; hc.prm.ambiguous_out = 0;
+  hc.prm.e_rate = 0.08; hc.prm.seed_len = 30; hc.prm.min_ins = 0; hc.prm.max_ins = 500; hc.prm.sensitive = sens ? 1 : 0; hc.prm.ambiguous_out = 0; hc.ambiguous_out = ambiguous_out; hc.pbat = pbat && !pe;
   const std::string prefix = fa + ".index";
   if (!hc.chroms.load(prefix) || !hc.genome.load(prefix + ".bs.pac", hc.chroms.N)) { fprintf(stderr, "cannot load %s\n", prefix.c_str()); return 1; }
   void* h = orc_load(prefix.c_str());
@@ -27,7 +31,8 @@ int main(int argc, char** argv) {
   if (!f1.open(files[0]) || (pe && !f2.open(files[1]))) return 1;
   std::vector<bmbs::FastqRecord> recs; bmbs::FastqRecord r;
   std::string flat; std::vector<uint64_t> offs(1, 0); std::vector<std::string> raw2;
-  if (!pe) { while (f1.next(r)) { bmbs::cut_name_se(r.name); flat += r.seq; offs.push_back(flat.size()); recs.push_back(r); } }
+  std::vector<std::string> raw1;
+  if (!pe) { while (f1.next(r)) { bmbs::cut_name_se(r.name); raw1.push_back(r.seq); flat += hc.pbat ? bmbs::revcomp(r.seq) : r.seq; offs.push_back(flat.size()); recs.push_back(r); } }
   else {
     bmbs::FastqRecord a, b;
     while (f1.next(a) && f2.next(b)) {
@@ -51,17 +56,19 @@ int main(int argc, char** argv) {
   bmbs::MapStats st; std::vector<bmbs::HostHit> v1, v2; std::vector<char> win;
   auto seq = [&](int i) { return std::string_view(flat.data() + offs[i], (size_t)(offs[i + 1] - offs[i])); };
   const int units = pe ? n / 2 : n;
+  const auto t_begin = std::chrono::steady_clock::now();
   for (int u = 0; u < units; ++u) {
     bmbs::MapStats t;
-    if (!pe) { bmbs::ReadView rv{recs[u].name, seq(u), recs[u].qual, seq(u)}; bmbs::finish_single(hc, rv, res[u], cand.data(), out, t, v1, win); }
+    if (!pe) { bmbs::ReadView rv{recs[u].name, seq(u), recs[u].qual, raw1[u]}; bmbs::finish_single(hc, rv, res[u], cand.data(), out, t, v1, win); }
     else bmbs::finish_pair(hc, recs[2 * u].name, seq(2 * u), recs[2 * u].qual, recs[2 * u + 1].name, seq(2 * u + 1), raw2[u], recs[2 * u + 1].qual,
                            res[2 * u], res[2 * u + 1], cand.data(), out, t, v1, v2, win);
     if (unmapped_out && !t.unique && !t.ambiguous) {
-      if (!pe) bmbs::sam_record_unmapped(out, recs[u].name, 4, seq(u), recs[u].qual);
+      if (!pe) bmbs::sam_record_unmapped(out, recs[u].name, 4, raw1[u], recs[u].qual);
       else { bmbs::sam_record_unmapped(out, recs[2 * u].name, 77, seq(2 * u), recs[2 * u].qual); bmbs::sam_record_unmapped(out, recs[2 * u + 1].name, 141, raw2[u], recs[2 * u + 1].qual); }
     }
     st.reads += t.reads; st.unique += t.unique; st.ambiguous += t.ambiguous; st.bases += t.bases; st.err_bases += t.err_bases;
   }
+  fprintf(stderr, "finish: %.3f s for %d units\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count(), units);
   FILE* fo = fopen(out_path.c_str(), "w"); fwrite(out.data(), 1, out.size(), fo); fclose(fo);
   const long long nn = (long long)st.reads, uq = (long long)st.unique, am = (long long)st.ambiguous;
   printf("%lld %lld %lld %.2f\n", nn, uq, am, st.bases ? (double)st.err_bases / (double)st.bases * 100 : 0.0);

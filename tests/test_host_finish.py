@@ -43,3 +43,26 @@ def test_unmapped_out_matches_live_reference(golden, built, harness, mode, files
                    cwd=golden, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     subprocess.run([str(harness), mode, "genome.fa", f"hf_un_{mode}.sam", *files, "--unmapped_out"], cwd=golden, check=True, capture_output=True)
     assert sam_body(golden / f"hf_un_{mode}.sam") == sam_body(golden / f"ref_un_{mode}.sam")
+
+
+@pytest.mark.parametrize("mode,files,flags", [("pe", ["pe100h_1.fq", "pe100h_2.fq"], ["--ambiguous_out"]), ("pes", ["pe100h_1.fq", "pe100h_2.fq"], ["--ambiguous_out", "--unmapped_out"]),
+                                              ("pe", ["pe150_2.fq", "pe150_1.fq"], ["--pbat"]), ("pes", ["pe100h_2.fq", "pe100h_1.fq"], ["--pbat", "--unmapped_out"]),
+                                              ("se", ["se100_rc.fq"], ["--pbat", "--unmapped_out"]), ("se", ["se100.fq"], ["--pbat", "--unmapped_out"])])
+def test_flag_rows_match_live_reference(golden, built, harness, mode, files, flags):
+    """--ambiguous_out (paired end), --pbat (single end on reverse-complemented reads and on directional ones; paired end with
+    the files swapped so that pairs still map) and --unmapped_out with them, against the live reference"""
+    if not built["ref"].exists():
+        pytest.skip("compiled reference absent")
+    if not (golden / "se100_rc.fq").exists():
+        comp = bytes.maketrans(b"ACGTacgt", b"TGCAtgca")
+        ls = (golden / "se100.fq").read_bytes().split(b"\n")
+        with open(golden / "se100_rc.fq", "wb") as o:
+            for i in range(0, len(ls) - 1, 4):
+                o.write(ls[i] + b"\n" + ls[i + 1].translate(comp)[::-1] + b"\n+\n" + ls[i + 3][::-1] + b"\n")
+    tag = mode + "_" + "_".join(f.strip("-") for f in flags) + "_" + files[0].split(".")[0]
+    args = ["--seq", files[0]] if mode == "se" else ["--seq1", files[0], "--seq2", files[1], "--pe"] + (["--sensitive"] if mode == "pes" else [])
+    subprocess.run([str(built["ref"]), "--search", "genome.fa", *args, *flags, "-t", "1", "-o", f"ref_{tag}.sam"],
+                   cwd=golden, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([str(harness), mode, "genome.fa", f"hf_{tag}.sam", *files, *flags], cwd=golden, check=True, capture_output=True)
+    ref = sam_body(golden / f"ref_{tag}.sam")
+    assert len(ref) > 100 and sam_body(golden / f"hf_{tag}.sam") == ref

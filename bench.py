@@ -1,20 +1,27 @@
 #!/usr/bin/env python3
 """bench.py -- throughput of the seed-and-verify hot path on B200, next to the reference CPU mapper.
 
-Workload (BASELINE.json configs[1], SURVEY.md §8d cfg 2): synthetic 100 Mbp genome (4 chromosomes, uniform,
-seed 1002), 1 M simulated 150 bp paired-end directional bisulfite reads (fragments U[200,480], 98 % C->T,
-1 % substitutions, seed 2002 + rank), `--pe` fast mode.  A "step" is one pass of the whole device pipeline
-(pack -> seed -> locate -> votes -> pair filter -> verify) over the batch of 1 M pairs = 2 M reads.
+Default workload = BASELINE.json configs[2] (SURVEY.md §8d cfg 3, the one the metric is quoted on): human-like synthetic genome
+(24 chromosomes, half of it repeat families of 1-10 kbp elements copied 10-10^4 times at 1-15 % divergence, seed 1003),
+150 bp single-end directional bisulfite reads (98 % C->T, 1 % substitutions, 14 % of the reads with one indel, seed 2003 +
+rank), default -e 0.08.  `--scale` is the fraction of the 3.087 Gbp genome that is built (stated in config.workload); the
+index is built once per box under --cache.  `--workload cfg2` (100 Mbp uniform, --pe) and `cfg4` (cfg3's genome, --pe
+--sensitive) are kept for profiling.  A "step" is one pass of the whole device pipeline (pack -> seed -> locate -> votes ->
+[pair filter] -> verify [-> sensitive pairing]) over one batch of `--reads` reads per GPU.
 
-  value  reads/s (mates, 2 per pair), inputs already resident in HBM, CUDA-event time on the library's stream
-  e2e    the same through the C ABI with pinned HOST buffers: H2D of the reads and D2H of the per-read records
-         and verified candidate lists inside the timed region (what the host mapper calls per batch)
-  roofline      dominant kernel of the step against the measured HBM peak (MEASURED_PEAKS.json)
-  cpu_baseline  the REAL reference (oracle/_ref/bitmapperBS, compiled from /root/reference) with -t <host cores>
-                on a bounded sample of the same reads, its own mapping timer (Bitmapper_main.cpp:262)
+  value         reads/s, inputs already resident in HBM, CUDA-event time on the library's stream
+  e2e           the same through the C ABI with pinned HOST buffers: H2D of the reads and D2H of the per-read records and
+                verified candidate lists inside the timed region (what the host mapper calls per batch)
+  roofline      dominant kernel group of the step against the measured HBM peak (MEASURED_PEAKS.json), algorithmic bytes in
+                SURVEY.md §8d's units (10 B per table query, 40 B per occ lookup) and in this layout's own (8 B / 32 B)
+  roofline_int  verify_windows against the measured integer-ALU peak: GCUPS and 14 word-ops per column per band word
+  whole_program FASTQ -> SAM through the command line (bitmapperbs_b200/_build/bmbs) next to the reference's own `Total:`
+                timers on the same file: the like-for-like number for the reference arm, whose timer covers its whole mapping
+  cpu_baseline  the REAL reference (oracle/_ref/bitmapperBS, compiled from /root/reference) with -t <host cores> on a
+                bounded sample of the same reads, its own mapping timer (Bitmapper_main.cpp:262)
 
-`--impl reference` times only that CPU run.  Multi-GPU (torchrun, one rank per GPU): read batches are sharded,
-the index is replicated, no collective on the data path; per-GPU work is fixed ("weak").
+`--impl reference` times only that CPU run.  Multi-GPU (torchrun, one rank per GPU): read batches are sharded, the index is
+replicated, no collective on the data path; per-GPU work is fixed ("weak").
 """
 from __future__ import annotations
 
@@ -33,48 +40,122 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-GENOME_CHROMS = [40_000_000, 30_000_000, 20_000_000, 10_000_000]
 READ_LEN = 150
+HUMAN_MBP = [250, 243, 198, 190, 181, 171, 159, 145, 138, 134, 135, 133, 114, 107, 102, 90, 83, 80, 59, 64, 47, 51, 156, 57]
+REPEATS = dict(repeat_fraction=0.5, repeat_len=(1000, 10000), repeat_copies=(10, 10000), repeat_div=(0.01, 0.15))
+DEFAULT_SCALE = {"cfg3": 0.1, "cfg4": 0.1, "cfg2": 1.0}
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-# ------------------------------------------------------------------------------------------------ dataset
-def ensure_dataset(cache: Path, scale: float, build: bool):
-    """genome + index under `cache`; built once per box (rank 0), reused by every later run"""
+# ------------------------------------------------------------------------------------------------ workloads
+class Workload:
+    """what is mapped: genome recipe, read recipe, mapper flags"""
+
+    def __init__(self, name: str, scale: float):
+        self.name, self.scale = name, scale
+        if name == "cfg2":
+            self.chroms = [int(c * scale) for c in (40_000_000, 30_000_000, 20_000_000, 10_000_000)]
+            self.genome_seed, self.repeat, self.dir = 1002, {}, f"cfg2_s1002_x{scale:g}"
+            self.pe, self.sensitive, self.read_seed = True, False, 2002
+        elif name in ("cfg3", "cfg4"):
+            self.chroms = [int(x * 1_000_000 * scale) for x in HUMAN_MBP]
+            self.genome_seed, self.repeat, self.dir = 1003, REPEATS, f"cfg3_s1003_x{scale:g}"
+            self.pe, self.sensitive, self.read_seed = name == "cfg4", name == "cfg4", 2003 if name == "cfg3" else 2004
+        else:
+            raise SystemExit(f"unknown workload {name}")
+        self.mbp = sum(self.chroms) / 1e6
+
+    def describe(self, units: int) -> str:
+        if self.name == "cfg2":
+            return (f"cfg2: synthetic {self.mbp:g} Mbp genome (4 chr, uniform, seed 1002), {units} x 2 x {READ_LEN} bp paired-end directional "
+                    f"bisulfite reads per GPU per step, --pe fast mode")
+        g = (f"synthetic {self.mbp / 1000:.3f} Gbp genome = {self.scale:g} x BASELINE's 3.087 Gbp (24 chr, 50 % repeat families of 1-10 kbp "
+             f"elements x 10-10^4 copies at 1-15 % divergence, seed 1003)")
+        if self.name == "cfg3":
+            return f"cfg3: {g}, {units} x {READ_LEN} bp single-end directional bisulfite reads per GPU per step (1 % substitutions, 14 % of reads with one indel), -e 0.08"
+        return f"cfg4: {g}, {units} x 2 x {READ_LEN} bp paired-end reads per GPU per step, --pe --sensitive"
+
+    def simulate(self, genome, starts, units, seed):
+        """-> (mate1 [n, L], mate2 [n, L] in FASTQ orientation or None)"""
+        from bitmapperbs_b200 import simulate as S
+        if self.pe:
+            return S.simulate_fast(genome, starts, units, READ_LEN, seed)
+        return S.simulate_fast(genome, starts, units, READ_LEN, seed, paired=False, indel_reads=0.14 if self.name == "cfg3" else 0.0)
+
+    def cli_flags(self):
+        return (["--pe"] if self.pe else []) + (["--sensitive"] if self.sensitive else [])
+
+
+def build_index(fa: Path):
+    """index files next to `fa`: the device builder when this box has a GPU and the tool is built, else the CPU writer (data prep)"""
+    from bitmapperbs_b200 import build as B
+    idx, _ = B.build_tools()
+    gpu_tool = ROOT / "bitmapperbs_b200/_build/bmbs-index-gpu"
+    if gpu_tool.exists() and os.environ.get("BMBS_INDEXER", "gpu") != "cpu":
+        r = subprocess.run([str(gpu_tool), str(fa)], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+        if r.returncode == 0:
+            return "gpu"
+        log(f"[bench] device index builder failed ({r.stderr.strip()[-300:]}); using the CPU writer")
+    subprocess.run([str(idx), str(fa)], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return "cpu"
+
+
+def ensure_dataset(cache: Path, wl, build: bool = True):
+    """genome + index under `cache`; built once per box (rank 0), reused by every later run.
+    (tools/ call this as ensure_dataset(cache, scale, build) for the cfg2 genome.)"""
+    if not isinstance(wl, Workload):
+        wl = Workload("cfg2", float(wl))
     from bitmapperbs_b200 import simulate as S
-    d = cache / f"cfg2_s1002_x{scale:g}"
+    d = cache / wl.dir
     done = d / ".done"
     if build and not done.exists():
         d.mkdir(parents=True, exist_ok=True)
         t = time.time()
-        chroms = S.random_genome([int(c * scale) for c in GENOME_CHROMS], seed=1002)
+        chroms = S.random_genome(wl.chroms, seed=wl.genome_seed, **wl.repeat)
         S.write_fasta(d / "g.fa", chroms)
         g, st = S.concat_genome(chroms)
         np.save(d / "genome.npy", g); np.save(d / "starts.npy", st)
-        from bitmapperbs_b200 import build as B
-        idx, _ = B.build_tools()
-        subprocess.run([str(idx), str(d / "g.fa")], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-        done.write_text("ok")
-        log(f"[bench] dataset + index built in {time.time() - t:.1f}s at {d}")
+        del chroms, g
+        t1 = time.time()
+        how = build_index(d / "g.fa")
+        done.write_text(how)
+        log(f"[bench] genome written in {t1 - t:.1f}s, index built ({how}) in {time.time() - t1:.1f}s at {d}")
     while not done.exists():
         time.sleep(0.5)
     return d
 
 
-def make_reads(d: Path, pairs: int, seed: int):
-    from bitmapperbs_b200 import simulate as S
-    f = d / f"reads_p{pairs}_s{seed}.npz"
+def make_reads(d: Path, wl: Workload, units: int, seed: int):
+    f = d / f"reads_{wl.name}_n{units}_s{seed}.npz"
     if f.exists():
         z = np.load(f)
-        return z["m1"], z["m2"]
-    g = np.load(d / "genome.npy"); st = np.load(d / "starts.npy")
-    m1, m2 = S.simulate_fast(g, st, pairs, READ_LEN, seed)
+        return z["m1"], (z["m2"] if "m2" in z.files else None)
+    g = np.load(d / "genome.npy", mmap_mode="r"); st = np.load(d / "starts.npy")
+    m1, m2 = wl.simulate(g, st, units, seed)
     tmp = d / f".tmp_{os.getpid()}_{seed}.npz"
-    np.savez(tmp, m1=m1, m2=m2); os.replace(tmp, f)
+    if m2 is None:
+        np.savez(tmp, m1=m1)
+    else:
+        np.savez(tmp, m1=m1, m2=m2)
+    os.replace(tmp, f)
     return m1, m2
+
+
+def write_fastq_files(d: Path, wl: Workload, m1, m2, n: int, tag: str):
+    from bitmapperbs_b200 import simulate as S
+    n = min(n, len(m1))
+    if wl.pe:
+        fa, fb = d / f"{tag}_{wl.name}_{n}_1.fq", d / f"{tag}_{wl.name}_{n}_2.fq"
+        if not fa.exists() or not fb.exists():
+            S.write_fastq_matrix(fa, m1[:n], "/1"); S.write_fastq_matrix(fb, m2[:n], "/2")
+        return n, ["--seq1", fa.name, "--seq2", fb.name]
+    f = d / f"{tag}_{wl.name}_{n}.fq"
+    if not f.exists():
+        S.write_fastq_matrix(f, m1[:n], "")
+    return n, ["--seq", f.name]
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -141,72 +222,74 @@ class ClockSampler:
                 "window": "timed region" if len(inside) >= 3 else "warm-up + timed region"}
 
 
-# ------------------------------------------------------------------------------------------------ reference CPU arm
-def run_reference(d: Path, m1, m2, sample_pairs: int, threads: int, repeats: int):
-    """oracle/_ref/bitmapperBS --search --pe -t threads on the first `sample_pairs` pairs; returns list of (map_s, wall_s)"""
-    from bitmapperbs_b200 import simulate as S
-    ref = ROOT / "oracle/_ref/bitmapperBS"
-    if not ref.exists():
+# ------------------------------------------------------------------------------------------------ command-line runs
+def run_cli(exe: Path, d: Path, wl: Workload, seq_args, threads: int, out: str, extra=()):
+    """`exe --search g.fa <reads> -t threads -o out`; returns (load_s, map_s, wall_s) from the program's own `Total:` line"""
+    t = time.time()
+    r = subprocess.run([str(exe), "--search", "g.fa", *seq_args, *wl.cli_flags(), "-t", str(threads), "-o", out, *extra],
+                       cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+    wall = time.time() - t
+    m = re.search(r"Total:\s+([0-9.]+)\s+([0-9.]+)", r.stderr)
+    if r.returncode != 0 or not m:
+        log(f"[bench] {exe.name} failed: {r.stderr[-500:]}")
         return None
-    n = min(sample_pairs, len(m1))
-    fa, fb = d / f"ref_{n}_1.fq", d / f"ref_{n}_2.fq"
-    if not fa.exists() or not fb.exists():
-        S.write_fastq_matrix(fa, m1[:n], "/1"); S.write_fastq_matrix(fb, m2[:n], "/2")
-    out = []
-    for _ in range(repeats):
-        t = time.time()
-        r = subprocess.run([str(ref), "--search", "g.fa", "--seq1", fa.name, "--seq2", fb.name, "--pe", "-t", str(threads), "-o", "/dev/null"],
-                           cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
-        wall = time.time() - t
-        m = re.search(r"Total:\s+([0-9.]+)\s+([0-9.]+)", r.stderr)
-        if r.returncode != 0 or not m:
-            return None
-        out.append((float(m.group(2)), wall))
-    return n, out
+    return float(m.group(1)), float(m.group(2)), wall
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU per step")
-    ap.add_argument("--scale", type=float, default=1.0, help="genome scale (1.0 = 100 Mbp)")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg4"])
+    ap.add_argument("--reads", "--pairs", dest="units", type=int, default=1_000_000, help="reads (pairs) per GPU per step")
+    ap.add_argument("--scale", type=float, default=None, help="fraction of the workload's full genome (cfg3/cfg4: of 3.087 Gbp)")
     ap.add_argument("--cache", default=os.environ.get("BMBS_BENCH_CACHE", "/tmp/bmbs_bench"))
-    ap.add_argument("--ref-sample", type=int, default=250_000, help="pairs per reference-CPU run")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-sample", type=int, default=500_000, help="reads (pairs) per reference-CPU run")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference runs and the whole-program comparison")
     ap.add_argument("--inflight", type=int, default=3, help="batches in flight in the end-to-end loop")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    scale = a.scale if a.scale is not None else float(os.environ.get("BMBS_BENCH_SCALE", DEFAULT_SCALE[a.workload]))
+    wl = Workload(a.workload, scale)
+    per_unit = 2 if wl.pe else 1
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     cache = Path(a.cache)
     cores = os.cpu_count() or 1
-    workload = f"cfg2: synthetic {100 * a.scale:g} Mbp genome (4 chr, uniform, seed 1002), {a.pairs} x 2 x {READ_LEN} bp paired-end directional bisulfite reads per GPU, --pe fast mode"
+    workload = wl.describe(a.units)
+    REF = ROOT / "oracle/_ref/bitmapperBS"
 
     # ---------------------------------------------------------------- reference arm
     if a.impl == "reference":
         if rank != 0:
             return 0
-        d = ensure_dataset(cache, a.scale, True)
-        m1, m2 = make_reads(d, a.pairs, 2002)
-        r = run_reference(d, m1, m2, a.ref_sample, cores, a.warmup + a.steps)
-        if r is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bitmapperBS missing or failed (built by oracle/build_ref.sh from /root/reference)"}))
+        if not REF.exists():
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bitmapperBS missing (built by oracle/build_ref.sh from /root/reference)"}))
             return 0
-        n, runs = r
+        d = ensure_dataset(cache, wl, True)
+        m1, m2 = make_reads(d, wl, a.units, wl.read_seed)
+        n, seq_args = write_fastq_files(d, wl, m1, m2, a.ref_sample, "ref")
+        runs = []
+        for _ in range(a.warmup + a.steps):
+            r = run_cli(REF, d, wl, seq_args, cores, "/dev/null")
+            if r is None:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bitmapperBS failed on the workload"}))
+                return 0
+            runs.append(r)
         runs = runs[a.warmup:]
-        map_s = sum(x[0] for x in runs)
-        value = 2 * n * len(runs) / map_s
-        sample = f"first {n} pairs of the workload, reference's own mapping timer (index load excluded), -t {cores}"
+        map_s = sum(x[1] for x in runs)
+        value = per_unit * n * len(runs) / map_s
+        sample = (f"first {n} {'pairs' if wl.pe else 'reads'} of rank 0's batch per step, oracle/_ref/bitmapperBS {' '.join(wl.cli_flags())} -t {cores}, "
+                  f"the reference's own mapping timer (index load excluded; covers seeding, verification, CIGAR, MAPQ and SAM text)")
         print(json.dumps({
             "impl": "reference", "metric": "mapped_reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1000 * map_s / len(runs), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload, "sample": sample, "reads_per_step": 2 * n},
+            "config": {"workload": workload, "sample": sample, "reads_per_step": per_unit * n},
             "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "wall_s_per_step": sum(x[1] for x in runs) / len(runs)}))
+            "load_s_per_step": sum(x[0] for x in runs) / len(runs), "wall_s_per_step": sum(x[2] for x in runs) / len(runs)}))
         return 0
 
     # ---------------------------------------------------------------- our arm
@@ -223,15 +306,17 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = local
     torch.cuda.set_device(dev)
-    d = ensure_dataset(cache, a.scale, rank == 0)
+    d = ensure_dataset(cache, wl, rank == 0)
     if dist:
         dist.barrier()
-    from bitmapperbs_b200 import shard
-    m1, m2 = make_reads(d, a.pairs, shard.rank_seed(2002, rank))
-    n_pairs = len(m1); n_reads = 2 * n_pairs
-    from bitmapperbs_b200.simulate import _revcomp_rows
-    mates = np.empty((n_reads, READ_LEN), dtype=np.uint8)
-    mates[0::2] = m1; mates[1::2] = _revcomp_rows(m2)
+    m1, m2 = make_reads(d, wl, a.units, wl.read_seed + rank)     # weak scaling: every rank maps its own reads
+    n_units = len(m1); n_reads = per_unit * n_units
+    if wl.pe:
+        from bitmapperbs_b200.simulate import _revcomp_rows
+        mates = np.empty((n_reads, READ_LEN), dtype=np.uint8)
+        mates[0::2] = m1; mates[1::2] = _revcomp_rows(m2)
+    else:
+        mates = m1
     bases = mates.size
     # pinned host staging (torch is plumbing here: pinned memory, device selection, rendezvous)
     h_flat = torch.empty(bases + 64, dtype=torch.uint8, pin_memory=True); h_flat.numpy()[:bases] = mates.ravel()
@@ -240,12 +325,13 @@ def main():
 
     t0 = time.time()
     index = B.Index(d / "g.fa.index", devices=(dev,))
-    log(f"[bench r{rank}] index resident: {index.device_bytes / 1e9:.2f} GB in {time.time() - t0:.1f}s")
-    prm = capi.default_params()
-    cand_cap = 10 * n_reads
+    load_s = time.time() - t0
+    log(f"[bench r{rank}] index resident: {index.device_bytes / 1e9:.2f} GB in {load_s:.1f}s")
+    prm = capi.default_params(sensitive=1 if wl.sensitive else 0)
+    cand_cap = 16 * n_reads
     while True:
         batch = B.Batch(index, dev, n_reads, bases + 64, cand_cap)
-        batch.upload(flat, offs, pe=True); batch.run(prm)
+        batch.upload(flat, offs, pe=wl.pe); batch.run(prm)
         try:
             batch.sync()
             h_res = torch.empty(n_reads * capi.ReadResult.itemsize, dtype=torch.uint8, pin_memory=True)
@@ -274,7 +360,7 @@ def main():
     batch.sync()
     for i in range(max(a.warmup, NB)):
         bb, rr, cc = outs[i % NB]
-        bb.upload(flat, offs, pe=True); bb.run(prm); bb.download(rr, cc)
+        bb.upload(flat, offs, pe=wl.pe); bb.run(prm); bb.download(rr, cc)
 
     def barrier():
         torch.cuda.synchronize()
@@ -300,13 +386,13 @@ def main():
     counters = batch.counters()
     launches = batch.launches() * a.steps
     # ---- timed: end to end through the C ABI, host buffers in / out
-    # (every step: H2D of the step's reads from pinned host memory, kernels, D2H of its records; two batches in
-    # flight on two streams, as the host mapper drives them)
+    # (every step: H2D of the step's reads from pinned host memory, kernels, D2H of its records; NB batches in
+    # flight on their own streams, as the host mapper drives them)
     barrier()
     e0 = time.perf_counter()
     for i in range(a.steps):
         bb, rr, cc = outs[i % NB]
-        bb.upload(flat, offs, pe=True); bb.run(prm)
+        bb.upload(flat, offs, pe=wl.pe); bb.run(prm)
         if i >= NB - 1:
             pb, pr, pc = outs[(i - (NB - 1)) % NB]
             _, _, used = pb.download(pr, pc)
@@ -330,7 +416,7 @@ def main():
 
     value = n_reads * world * a.steps / (dev_ms / 1000)
     e2e = n_reads * world * a.steps / (e2e_ms / 1000)
-    # ---- roofline of the dominant kernel (SURVEY.md §8d algorithmic bytes per unit)
+    # ---- roofline of the dominant kernel group (SURVEY.md §8d algorithmic bytes per unit)
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -338,63 +424,116 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     per_step = {k: v / a.steps for k, v in stage.items()}
-    # algorithmic bytes per unit: 8 B per table query (one deep-table / 16-mer entry), 32 B per occ-block lookup
-    seed_bytes = 8 * counters["hash_queries"] + 32 * counters["occ_lookups"]
-    # sampled suffix array: 80 B per LF step + 44 B per row; dense suffix array (default): one 4-byte entry per row
-    loc_bytes = counters["locate_lf_steps"] * 80 + counters["located_rows"] * (44 if counters["locate_lf_steps"] else 4)
-    ver_bytes = counters["window_bytes"]
-    kernels = {"seed_first+second+rest": (per_step["seed"], seed_bytes), "expand_locate": (per_step["locate"], loc_bytes), "verify_windows": (per_step["verify"], ver_bytes)}
-    dom = max(kernels, key=lambda k: kernels[k][0])
-    dms, dbytes = kernels[dom]
-    achieved = dbytes / (dms / 1000) / 1e9 if dms > 0 else 0.0
+    c = counters
+    dense = c["locate_lf_steps"] == 0
+    # SURVEY §8d units (the reference's layout): 10 B per 16-mer query, 40 B per occ lookup, (80 B per LF step + 44 B) per located row;
+    # this layout's own units: 8 B per table entry, 32 B per occ block, 4-5 B per located row of the dense suffix array
+    survey = {"seed": 10 * c["hash_queries"] + 40 * c["occ_lookups"], "locate": 80 * c["locate_lf_steps"] + 44 * c["located_rows"], "verify": c["window_bytes"]}
+    layout = {"seed": 8 * c["hash_queries"] + 32 * c["occ_lookups"],
+              "locate": c["located_rows"] * (5 if index.genome_length * 2 >= (1 << 32) else 4) if dense else 80 * c["locate_lf_steps"] + 44 * c["located_rows"],
+              "verify": c["window_bytes"]}
+    names = {"seed": "seed_first+seed_second+seed_rest", "locate": "expand_locate", "verify": "verify_windows"}
+    dom = max(names, key=lambda k: per_step[k])
+    dms = per_step[dom]
+    achieved = survey[dom] / (dms / 1000) / 1e9 if dms > 0 else 0.0
     # DRAM traffic of the same kernels from the committed `ncu --set full` capture (profiles/ncu_traffic.json), per launch
     traffic = None
     try:
-        traffic = json.loads((ROOT / "profiles/ncu_traffic.json").read_text()).get(dom, {}).get("dram_bytes_per_launch")
+        tj = json.loads((ROOT / "profiles/ncu_traffic.json").read_text())
+        traffic = tj.get(wl.name, {}).get(names[dom], {}).get("dram_bytes_per_launch")
     except Exception:
         pass
-    gcups = counters["cells"] / (per_step["verify"] / 1000) / 1e9 if per_step["verify"] > 0 else 0.0
-    # the bound that applies to the seeding kernels: independent random 32-byte sectors per second (measured live)
     try:
-        rs_peak = capi.random_sector_peak(dev)
+        rs_peak = capi.random_sector_peak(dev)      # independent random 32-byte sector loads per second (measured live)
     except Exception:
         rs_peak = None
-    seed_sectors = counters["hash_queries"] + counters["occ_lookups"] + counters["located_rows"]
-    seed_sector_rate = seed_sectors / (per_step["seed"] / 1000) if per_step["seed"] > 0 else 0.0
+    accesses = {"seed": c["hash_queries"] + c["occ_lookups"], "locate": c["located_rows"] + c["locate_lf_steps"] * 2, "verify": None}
+    # ---- integer roofline of verification: GCUPS and word-ops (14 per column per band word; 1 word for k <= 15, 2 above)
+    try:
+        int_peak = capi.int_pipe_peak(dev)
+    except Exception:
+        int_peak = None
+    k_band = int(min(31, int(0.08 * READ_LEN)))
+    words = 1 if k_band <= 15 else 2
+    vms = per_step["verify"]
+    gcups = c["cells"] / (vms / 1000) / 1e9 if vms > 0 else 0.0
+    columns = c["cells"] / (2 * k_band + 1)
+    int_ops = 14 * words * columns
     out = {
         "metric": "mapped_reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": workload, "reads_per_step_per_gpu": n_reads, "l2": "inputs (300 MB of reads, 0.6 GB index) exceed the 126 MB L2; no flush needed",
+        "config": {"workload": workload, "reads_per_step_per_gpu": n_reads,
+                   "l2": f"inputs ({bases / 1e6:.0f} MB of reads, {index.device_bytes / 1e9:.1f} GB index) exceed the 126 MB L2; no flush needed",
                    "read_states": {"none": int(states[0]), "exact_unique": int(states[1]), "multi_exact": int(states[2]), "one_mismatch": int(states[3]), "verify": int(states[4])},
-                   "index_hbm_bytes": index.device_bytes},
-        "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps, "batches_in_flight": NB},
+                   "index_hbm_bytes": index.device_bytes, "index_load_s": load_s, "genome_bases": index.genome_length},
+        "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps, "batches_in_flight": NB,
+                "scope": "C-ABI call: H2D of the reads, kernels, D2H of records + verified candidate lists (host reduction / CIGAR / SAM are in whole_program)"},
         "gpu_launches": launches,
         "clocks": clk,
         "stage_ms_per_step": per_step,
         "wall_ms_per_step": wall_ms / a.steps,
         "verify_gcups": gcups,
         "work_per_step": counters,
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": dbytes, "kernel_ms": dms,
-                     # DRAM bytes the kernels really move (ncu, profiles/ncu_traffic.json) over the live kernel time: random 8-byte table entries and
-                     # 32-byte occ blocks cost a 64-byte DRAM access each, so this -- not the algorithmic figure -- is what loads HBM
+        "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                     "peak_source": peak_src, "kernel_ms": dms,
+                     "algorithmic_bytes_per_launch": survey[dom], "units": "SURVEY 8d: 10 B per table query, 40 B per occ lookup, 80 B per locate LF step + 44 B per located row, window bytes",
+                     "layout_bytes_per_launch": layout[dom], "layout_units": "this layout: 8 B per table entry, 32 B per occ block, 4-5 B per located row (dense suffix array)",
+                     "layout_frac": layout[dom] / (dms / 1000) / 1e9 / peak if dms > 0 and peak else None,
+                     # DRAM bytes the kernels really move (ncu, profiles/ncu_traffic.json) over the live kernel time: every random 8-byte
+                     # table entry / 32-byte occ block costs a whole DRAM line, so this -- not the algorithmic figure -- is what loads HBM
                      "traffic_gbs": traffic / (dms / 1000) / 1e9 if traffic and dms > 0 else None,
                      "traffic_frac_of_peak": traffic / (dms / 1000) / 1e9 / peak if traffic and dms > 0 and peak else None,
-                     "random_sector_peak_gbs": rs_peak * 32 / 1e9 if rs_peak else None, "seed_random_sector_gbs": seed_sector_rate * 32 / 1e9,
-                     "frac_of_random_sector_peak": seed_sector_rate / rs_peak if rs_peak else None,
-                     "note": "after the deep seed table a seed is one 8-byte entry: the seed kernels are bound by dependent random sectors and instruction issue, not by bytes (DESIGN.md 7)",
-                     "all_kernels": {k: {"ms": v[0], "algorithmic_bytes": v[1], "GBps": (v[1] / (v[0] / 1000) / 1e9 if v[0] > 0 else 0.0)} for k, v in kernels.items()}},
+                     "random_access_peak_per_s": rs_peak, "random_accesses_per_s": accesses[dom] / (dms / 1000) if accesses[dom] and dms > 0 else None,
+                     "frac_of_random_access_peak": accesses[dom] / (dms / 1000) / rs_peak if accesses[dom] and dms > 0 and rs_peak else None,
+                     "all_kernels": {names[k]: {"ms": per_step[k], "survey_bytes": survey[k], "layout_bytes": layout[k],
+                                                "GBps": (survey[k] / (per_step[k] / 1000) / 1e9 if per_step[k] > 0 else 0.0)} for k in names}},
+        "roofline_int": {"bound": "int-alu", "kernel": "verify_windows", "gcups": gcups, "cells_per_launch": c["cells"], "windows_per_launch": c["verified"],
+                         "achieved": int_ops / (vms / 1000) / 1e12 if vms > 0 else 0.0, "peak": int_peak / 1e12 if int_peak else None, "unit": "T int32 ops/s",
+                         "frac": int_ops / (vms / 1000) / int_peak if vms > 0 and int_peak else None, "kernel_ms": vms,
+                         "units": f"14 word-ops per column per band word (SURVEY 8d), {words} word(s) for k = {k_band}; peak = measured LOP3+IADD3 rate (bmbs_ubench_int_pipe)"},
     }
-    # ---- reference CPU baseline on this box (rank 0, N == 1 only)
+    # ---- the whole program and the reference on this box's host cores (rank 0, N == 1 only)
     if world == 1 and not a.no_cpu_baseline:
-        r = run_reference(d, m1, m2, a.ref_sample, cores, 2)
-        if r is not None:
-            n, runs = r
-            out["cpu_baseline"] = {"value": 2 * n / runs[-1][0], "unit": "reads/s", "cores": cores, "kind": "reference",
-                                   "sample": f"first {n} pairs of the workload, oracle/_ref/bitmapperBS --pe -t {cores}, its own mapping timer, 2nd of 2 runs",
-                                   "wall_s": runs[-1][1]}
-        else:
+        BMBS = ROOT / "bitmapperbs_b200/_build/bmbs"
+        n, seq_args = write_fastq_files(d, wl, m1, m2, a.units, "wp")
+        wp = {"reads": per_unit * n, "host_cores": cores, "scope": "FASTQ file -> SAM file through the command line, index load and the program's mapping phase timed by its own `Total:` line"}
+        run_cli(BMBS, d, wl, seq_args, cores, "/dev/null")                               # page cache + driver warm-up
+        g = run_cli(BMBS, d, wl, seq_args, cores, "wp_gpu.sam")
+        if g:
+            wp["ours"] = {"load_s": g[0], "map_s": g[1], "wall_s": g[2], "reads_per_s_map": per_unit * n / g[1] if g[1] > 0 else None, "reads_per_s_wall": per_unit * n / g[2]}
+        if REF.exists():
+            r = run_cli(REF, d, wl, seq_args, cores, "wp_ref.sam")
+            if r:
+                wp["reference"] = {"load_s": r[0], "map_s": r[1], "wall_s": r[2], "reads_per_s_map": per_unit * n / r[1] if r[1] > 0 else None, "reads_per_s_wall": per_unit * n / r[2]}
+                if g:
+                    wp["map_speedup"] = r[1] / g[1] if g[1] > 0 else None; wp["wall_speedup"] = r[2] / g[2]
+                    try:      # same records?  (the reference's -t N order is not deterministic: compare sorted bodies)
+                        import hashlib
+
+                        def digest(p):
+                            h = hashlib.sha256()
+                            for line in sorted(x for x in open(p, "rb") if not x.startswith(b"@")):
+                                h.update(line)
+                            return h.hexdigest()
+                        wp["sam_identical"] = digest(d / "wp_gpu.sam") == digest(d / "wp_ref.sam")
+                    except Exception:
+                        pass
+            ns, sargs = write_fastq_files(d, wl, m1, m2, a.ref_sample, "ref")
+            r2 = run_cli(REF, d, wl, sargs, cores, "/dev/null")
+            if r2:
+                out["cpu_baseline"] = {"value": per_unit * ns / r2[1], "unit": "reads/s", "cores": cores, "kind": "reference",
+                                       "sample": f"first {ns} {'pairs' if wl.pe else 'reads'} of the step's batch, oracle/_ref/bitmapperBS {' '.join(wl.cli_flags())} -t {cores}, its own mapping timer (page cache warm)",
+                                       "wall_s": r2[2]}
+        for f in ("wp_gpu.sam", "wp_ref.sam"):
+            try:
+                (d / f).unlink()
+            except OSError:
+                pass
+        out["whole_program"] = wp
+        if "cpu_baseline" not in out:
             out["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref/bitmapperBS unavailable"}
+    elif world > 1:
+        out["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": cores, "kind": "reference", "sample": "measured at N = 1 only (bench contract); see the N = 1 line and --impl reference"}
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(out) + "\n").encode())
     if dist:

@@ -11,6 +11,8 @@
 #include <unistd.h>
 #include <algorithm>
 #include <atomic>
+#include <mutex>
+#include <set>
 #include <string>
 #include <thread>
 #include <vector>
@@ -215,8 +217,16 @@ __global__ void __launch_bounds__(256) densify_sa(DevIndex ix, u32* lo, unsigned
 
 }  // namespace
 
+// every loaded index gets a serial that is never reused: the one-call forms cache their batch contexts per thread and
+// must not mistake a new index that malloc placed at a freed handle's address for the old one
+namespace {
+std::mutex g_live_mu; std::set<u64> g_live_serials; std::atomic<u64> g_next_serial{1};
+bool serial_live(u64 s) { std::lock_guard<std::mutex> l(g_live_mu); return g_live_serials.count(s) != 0; }
+}  // namespace
+
 struct bmbs_index {
   u64 N = 0;
+  u64 serial = 0;
   std::vector<DeviceCopy> copies;
   const DeviceCopy* on(int dev) const { for (auto& c : copies) if (c.dev == dev) return &c; return nullptr; }
 };
@@ -228,6 +238,7 @@ extern "C" uint64_t bmbs_index_device_bytes(const bmbs_index* idx) { return idx 
 
 extern "C" void bmbs_index_free(bmbs_index* idx) {
   if (!idx) return;
+  { std::lock_guard<std::mutex> l(g_live_mu); g_live_serials.erase(idx->serial); }
   for (auto& c : idx->copies) { cudaSetDevice(c.dev); cudaFree(c.occ); cudaFree(c.flag); cudaFree(c.hash); cudaFree(c.ssa); cudaFree(c.planes); cudaFree(c.dsa_lo); cudaFree(c.dsa_hi); cudaFree(c.ktab); }
   delete idx;
 }
@@ -252,6 +263,8 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
 
   bmbs_index* idx = new bmbs_index();
   idx->N = h.N;
+  idx->serial = g_next_serial++;
+  { std::lock_guard<std::mutex> l(g_live_mu); g_live_serials.insert(idx->serial); }
   warm.join();
   lap("(wait for the CUDA context)");
   for (int d = 0; d < n_dev; ++d) {
@@ -298,7 +311,9 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
     lap("upload + device re-layout");
     // ---- dense suffix array (BMBS_SA=sampled keeps the on-disk 1/8 sampling; default: dense when it fits with room to spare)
     const char* mode = getenv("BMBS_SA");
-    const bool wide = h.sa_length > 0xFFFFFFFFull;
+    // texts of 2^32 rows and more keep bits 32..39 of every suffix-array value in a byte array of their own; BMBS_FORCE_WIDE
+    // switches that path on for a small index too (GPU tests: the 5-byte gather and densify's second store run everywhere)
+    const bool wide = h.sa_length > 0xFFFFFFFFull || getenv("BMBS_FORCE_WIDE") != nullptr;
     const size_t need = (size_t)h.sa_length * (wide ? 5 : 4);
     size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
     const bool want = mode ? strcmp(mode, "sampled") != 0 : need + (total_b >> 2) < free_b;
@@ -597,22 +612,29 @@ extern "C" void bmbs_pinned_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ================================================================================================ one-call forms
 namespace {
-struct Cached { bmbs_index* idx; int dev; bmbs_batch* b; };
+struct Cached { bmbs_index* idx; u64 serial; int dev; bmbs_batch* b; };
 thread_local std::vector<Cached> g_cache;
 
 int cached_batch(bmbs_index* idx, int dev, size_t reads, size_t bases, size_t cand_cap, bmbs_batch** out) {
+  // contexts of indexes that have been freed since: their device slabs are still ours to release (bmbs_batch_free does not
+  // touch the index), the entries go
+  for (size_t i = 0; i < g_cache.size();) {
+    if (g_cache[i].b && serial_live(g_cache[i].serial)) { ++i; continue; }
+    if (g_cache[i].b) bmbs_batch_free(g_cache[i].b);
+    g_cache[i] = g_cache.back(); g_cache.pop_back();
+  }
   for (auto& c : g_cache)
-    if (c.idx == idx && c.dev == dev) {
+    if (c.idx == idx && c.serial == idx->serial && c.dev == dev) {
       if (c.b->max_reads >= reads && c.b->max_bases >= bases && c.b->cand_cap >= cand_cap) { *out = c.b; return BMBS_OK; }
       bmbs_batch_free(c.b); c.b = nullptr;
       int rc = bmbs_batch_create(idx, dev, reads, bases, cand_cap, &c.b);
-      if (rc) { c.idx = nullptr; return rc; }
+      if (rc) { c.idx = nullptr; c.serial = 0; return rc; }
       *out = c.b; return BMBS_OK;
     }
   bmbs_batch* b = nullptr;
   int rc = bmbs_batch_create(idx, dev, reads, bases, cand_cap, &b);
   if (rc) return rc;
-  g_cache.push_back({idx, dev, b});
+  g_cache.push_back({idx, idx->serial, dev, b});
   *out = b; return BMBS_OK;
 }
 

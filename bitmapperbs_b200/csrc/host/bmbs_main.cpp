@@ -146,6 +146,9 @@ void parse_batch(RawBatch& rb, bool pe, bool pbat_se, Batch& b) {
     if (!name.empty() && name[0] == '@') name.remove_prefix(1);
     upper_in_place(seq);
     if (qual.size() > seq.size()) qual = qual.substr(0, seq.size());
+    // every later stage indexes the qualities by read position: a record whose quality line is shorter than its sequence
+    // (truncated / malformed input) is refused rather than read past its end
+    if (qual.size() < seq.size()) die("malformed FASTQ record '" + std::string(name) + "': quality line shorter than the sequence");
   };
   for (size_t u = 0; u < rb.n_rec; ++u) {
     if (!pe) {

@@ -172,14 +172,18 @@ inline void cut_name_se(std::string_view& n) { size_t p = n.find_first_of(" /");
 inline void cut_name_pe(std::string_view& a, std::string_view& b) {
   size_t j = 0;
   for (; j < a.size(); ++j) if (j >= b.size() || a[j] != b[j] || a[j] == ' ' || a[j] == '/') break;
-  if (j < a.size()) { a = a.substr(0, j); if (b.size() > j) b = b.substr(0, j); }
+  // the reference's loop also looks at mate 1's terminating NUL (Process_Reads.cpp:392-405): a mate-2 name that merely
+  // continues mate 1's is cut to the same length
+  if (j < a.size()) a = a.substr(0, j);
+  if (b.size() > j) b = b.substr(0, j);
 }
 
 inline void cut_name_se(std::string& n) { size_t p = n.find_first_of(" /"); if (p != std::string::npos) n.resize(p); }
 inline void cut_name_pe(std::string& a, std::string& b) {
   size_t j = 0;
   for (; j < a.size(); ++j) if (j >= b.size() || a[j] != b[j] || a[j] == ' ' || a[j] == '/') break;
-  if (j < a.size()) { a.resize(j); if (b.size() > j) b.resize(j); }
+  if (j < a.size()) a.resize(j);
+  if (b.size() > j) b.resize(j);
 }
 inline std::string revcomp(std::string_view s) {
   std::string r(s.size(), 'N');

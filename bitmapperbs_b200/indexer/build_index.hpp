@@ -43,6 +43,7 @@ void read_fasta(const char* path, std::vector<Chrom>& chroms, std::vector<uint8_
   fclose(f);
   g.reserve(sz);
   size_t i = 0;
+  uint64_t rng = 0x9E3779B97F4A7C15ull, replaced = 0;
   while (i < sz) {
     char c = buf[i];
     if (c == '>') {
@@ -56,9 +57,12 @@ void read_fasta(const char* path, std::vector<Chrom>& chroms, std::vector<uint8_
     } else {
       if (!isspace((unsigned char)c)) {
         char u = toupper(c);
-        if (u != 'A' && u != 'C' && u != 'G' && u != 'T')
-          die("genome contains a base outside ACGT; the reference randomises those with srand(time) "
-              "(Index.cpp:696-729) so no reproducible index exists -- mask them first");
+        if (u != 'A' && u != 'C' && u != 'G' && u != 'T') {
+          // the reference replaces every base outside ACGT by a random one seeded with the time of day (Index.cpp:696-729),
+          // so two of its own builds differ there; here the replacement is a fixed-seed sequence (reproducible builds)
+          rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+          u = "ACGT"[(rng >> 33) & 3]; ++replaced;
+        }
         if (chroms.empty()) die("sequence before first FASTA header");
         g.push_back(u);
       }
@@ -67,6 +71,7 @@ void read_fasta(const char* path, std::vector<Chrom>& chroms, std::vector<uint8_
   }
   if (chroms.empty()) die("no FASTA records");
   chroms.back().len = g.size() - chroms.back().len;
+  if (replaced) fprintf(stderr, "bmbs-index: %llu bases outside ACGT replaced by pseudo-random bases (fixed seed)\n", (unsigned long long)replaced);
 }
 
 }  // namespace indexer

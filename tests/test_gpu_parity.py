@@ -18,11 +18,14 @@ ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
 
 # index residency variants: what the loader picks for a genome this small (dense suffix array, 16-mer table
 # only), the on-disk 1/8 suffix-array sampling with an 18-mer deep seed table, and the 20-mer table a 100 Mbp genome gets
-@pytest.fixture(scope="module", params=["default", "sampled_sa+18mer", "20mer"])
+# and the layout of texts beyond 2^32 rows (bits 32..39 of every suffix-array value in their own byte array) forced onto
+# the small index together with the 20-mer table and the dense suffix array -- what a 3.1 Gbp genome gets
+@pytest.fixture(scope="module", params=["default", "sampled_sa+18mer", "20mer", "wide_sa+20mer"])
 def gidx(golden, request):
     import os
-    env = {"default": {}, "sampled_sa+18mer": {"BMBS_SA": "sampled", "BMBS_KMER": "18"}, "20mer": {"BMBS_KMER": "20"}}[request.param]
-    old = {k: os.environ.get(k) for k in ("BMBS_SA", "BMBS_KMER")}
+    env = {"default": {}, "sampled_sa+18mer": {"BMBS_SA": "sampled", "BMBS_KMER": "18"}, "20mer": {"BMBS_KMER": "20"},
+           "wide_sa+20mer": {"BMBS_FORCE_WIDE": "1", "BMBS_KMER": "20", "BMBS_SA": "dense"}}[request.param]
+    old = {k: os.environ.get(k) for k in ("BMBS_SA", "BMBS_KMER", "BMBS_FORCE_WIDE")}
     os.environ.update(env)
     try:
         ix = B.Index(golden / "genome.fa.index")
@@ -297,6 +300,38 @@ def test_live_reference_binary_agrees_on_fresh_data(built, tmp_path):
                        cwd=tmp_path, check=True, stderr=subprocess.DEVNULL)
         assert sam_body(tmp_path / f"gpu_{tag}.sam") == sam_body(tmp_path / f"cpu_{tag}.sam")
         assert (tmp_path / f"gpu_{tag}.st").read_text() == (tmp_path / f"cpu_{tag}.st").read_text()
+
+
+def test_mapper_wide_suffix_array_gzip_input_and_two_gpus(golden, built, tmp_path):
+    """whole program with (i) the > 2^32-row suffix-array layout forced on, (ii) gzip-compressed FASTQ input and (iii) the
+    batches of one run spread over two GPUs (when the box has two): SAM and mapstats identical to the reference's golden files"""
+    import gzip, os, shutil
+    for f in ("se100.fq", "pe150_1.fq", "pe150_2.fq"):
+        with open(golden / f, "rb") as i, gzip.open(golden / (f + ".gz"), "wb", compresslevel=1) as o:
+            shutil.copyfileobj(i, o)
+    import torch
+    runs = [("wide", {"BMBS_FORCE_WIDE": "1", "BMBS_KMER": "20"}, []), ("gz", {}, [])]
+    if torch.cuda.device_count() >= 2:
+        runs.append(("gpus2", {}, ["--gpus", "2"]))
+    for tag, env, extra in runs:
+        gz = ".gz" if tag == "gz" else ""
+        for name, args in (("se100", ["--seq", "se100.fq" + gz]), ("pe150s", ["--seq1", "pe150_1.fq" + gz, "--seq2", "pe150_2.fq" + gz, "--pe", "--sensitive"])):
+            subprocess.run([str(built["bmbs"]), "--search", "genome.fa", *args, *extra, "-t", "4", "-o", f"{tag}.sam", "--mapstats", f"{tag}.stats", "--batch", "300"],
+                           cwd=golden, check=True, stderr=subprocess.DEVNULL, env={**os.environ, **env})
+            assert sam_body(golden / f"{tag}.sam") == sam_body(golden / f"{name}.sam"), (tag, name)
+            assert (golden / f"{tag}.stats").read_text() == (golden / f"ref_{name}.stats").read_text(), (tag, name)
+
+
+def test_one_call_cache_survives_index_reload(golden, oidx):
+    """the one-call forms keep a batch context per (index, device); a new index that lands on a freed handle's address must
+    not be served the old context: load / map / free / load / map, each result checked against the oracle"""
+    reads = [r[1] for r in read_fastq(golden / "se100.fq")][:400]
+    ores, ocand = oidx.map_se(reads)
+    for _ in range(4):
+        ix = B.Index(golden / "genome.fa.index")
+        gres, gcand = ix.map_batch_se(reads)
+        ix.close()
+        assert_same_records(gres, gcand, ores, ocand)
 
 
 def test_capacity_error_is_reported_with_needed_size(golden, gidx):

@@ -6,21 +6,22 @@ set -u
 TAG=${1:-run}; shift || true
 WHAT=${*:-tests bench launches full}
 O=gpurun_out; mkdir -p $O
-KERNELS='regex:^(pack_reads|seed_first|seed_second|seed_rest|expand_locate|votes_classify|votes_sort|filter_pairs_kernel|gather_work|verify_windows)'
+KERNELS='regex:^(pack_reads|seed_first|seed_second|seed_rest|expand_locate|votes_classify|votes_sort|votes_big|gather_work|verify_windows)'
+BENCH_ARGS=${BENCH_ARGS:-}
 for w in $WHAT; do
   case $w in
     tests)
       timeout 900 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest.log 2>&1; echo "pytest exit $?" | tee -a $O/${TAG}_pytest.log; tail -3 $O/${TAG}_pytest.log ;;
     bench)
-      timeout 600 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.log; echo "bench exit $?"; cat $O/${TAG}_bench.json ;;
+      timeout 900 python bench.py $BENCH_ARGS > $O/${TAG}_bench.json 2> $O/${TAG}_bench.log; echo "bench exit $?"; cat $O/${TAG}_bench.json ;;
     refarm)
-      timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_bench_reference.json 2>> $O/${TAG}_bench.log; cat $O/${TAG}_bench_reference.json ;;
+      timeout 600 python bench.py $BENCH_ARGS --impl reference --steps 2 --warmup 1 > $O/${TAG}_bench_reference.json 2>> $O/${TAG}_bench.log; cat $O/${TAG}_bench_reference.json ;;
     launches)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv \
-        python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_launches_bench.log 2>&1; echo "launch list exit $?" ;;
+        python bench.py $BENCH_ARGS --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_launches_bench.log 2>&1; echo "launch list exit $?" ;;
     full)
-      timeout 900 ncu --set full --clock-control none --import-source on -k "$KERNELS" --launch-skip 36 --launch-count 12 -f -o $O/${TAG}_full \
-        python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_full_bench.log 2>&1; echo "ncu full exit $?" ;;
+      timeout 900 ncu --set full --clock-control none --import-source on -k "$KERNELS" --launch-skip 60 --launch-count 10 -f -o $O/${TAG}_full \
+        python bench.py $BENCH_ARGS --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_full_bench.log 2>&1; echo "ncu full exit $?" ;;
     verify)
       timeout 900 python tools/bench_verify.py > $O/${TAG}_verify.json 2> $O/${TAG}_verify.log; echo "bench_verify exit $?"; tail -c 1500 $O/${TAG}_verify.json ;;
     fullverify)
@@ -29,7 +30,7 @@ for w in $WHAT; do
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:verify_windows --launch-skip 3 --launch-count 1 -f -o $O/${TAG}_fullverify250 \
         python tools/bench_verify.py --lengths 250 --rates 0.02 --reps 2 --no-oracle --cpu-sample-log2 10 >> $O/${TAG}_fullverify.log 2>&1; echo "ncu verify250 exit $?" ;;
     scale2)
-      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 \
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py $BENCH_ARGS --gpus 2 --steps 10 --warmup 3 \
         > $O/${TAG}_scale2.json 2> $O/${TAG}_scale2.log; cat $O/${TAG}_scale2.json ;;
   esac
 done

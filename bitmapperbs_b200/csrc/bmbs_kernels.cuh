@@ -21,7 +21,7 @@ namespace bmbs {
 
 constexpr int MAX_TASKS = 28;       // 25 seeds + first-seed literal + second seed + slack
 constexpr u32 MAX_SEED_HITS = 1000; // Schema.cpp:26826 max_seed_matches
-constexpr u32 MAX_PE_MULTI = 25000; // Schema.cpp:18854 max_candidates_occ (fast pair mode)
+constexpr u32 MAX_PE_MULTI = 10000; // Schema.cpp:21719-21737 max_candidates_occ of Map_Pair_Seq_split_fast: 25 x 1000, then clamped to 10000
 constexpr u32 MAX_PE_MULTI_SENSITIVE = 10000; // Schema.cpp:22713-22716 (sensitive pair mode)
 
 struct SeedTask { u64 sp; u32 hits; unsigned short mlen, off; };  // hits==0: `sp` is a literal site

@@ -3,6 +3,7 @@
 # reference mapper from the sources where they lie under /root/reference.
 #
 #   oracle/_ref/bitmapperBS  the reference CLI (SE / PE / PE --sensitive, SAM text)
+#   oracle/_ref/bitmapperBS_gpu, bitmapperBS_seam_cpu   the reference with its workers calling include/bmbs.h per sub-block
 #   oracle/_ref/psascan      suffix-sorter stand-in the reference shells out to in --index
 #   oracle/_ref/libref_bpm.so, libref_fm.so, libref_ksw.so   C entry points into the reference's own BPM / FM-index / CIGAR functions
 #
@@ -20,7 +21,7 @@ REF="${BMBS_REFERENCE:-/root/reference}"
 OUT="$HERE/_ref"
 [ -d "$REF" ] || { echo "build_ref: $REF absent (GPU box?) - keeping prebuilt $OUT" >&2; exit 0; }
 mkdir -p "$OUT"
-if [ -x "$OUT/bitmapperBS" ] && [ -x "$OUT/psascan" ] && [ -f "$OUT/libref_bpm.so" ] && [ -f "$OUT/libref_fm.so" ] && [ -f "$OUT/libref_ksw.so" ] && [ "${1:-}" != "--force" ]; then
+if [ -x "$OUT/bitmapperBS" ] && [ -x "$OUT/bitmapperBS_gpu" ] && [ -x "$OUT/bitmapperBS_seam_cpu" ] && [ "$OUT/bitmapperBS_gpu" -nt "$HERE/../integration/bmbs_seam.h" ] && [ "$OUT/bitmapperBS_gpu" -nt "$HERE/../integration/patch_reference.py" ] && [ -x "$OUT/psascan" ] && [ -f "$OUT/libref_bpm.so" ] && [ -f "$OUT/libref_fm.so" ] && [ -f "$OUT/libref_ksw.so" ] && [ "${1:-}" != "--force" ]; then
   echo "build_ref: $OUT up to date"; exit 0
 fi
 TMP="$(mktemp -d /tmp/bmbs_refbuild.XXXXXX)"
@@ -34,6 +35,25 @@ gcc -c -O1 "$HERE/hts_stub.c" -o "$TMP/hts_stub.o"
     Process_sam_out.cpp Process_Reads.cpp Ref_Genome.cpp Levenshtein_Cal.cpp SAM_queue.cpp bam_prase.cpp ksw.cpp \
     hts_stub.o -o bitmapperBS -lm -lz -lpthread )
 cp "$TMP/bitmapperBS" "$OUT/bitmapperBS"
+# ---- the same reference with the GPU seam spliced into its workers (integration/patch_reference.py, integration/bmbs_seam.h):
+#   bitmapperBS_gpu       linked against the product library libbmbs_gpu.so (GPU tests diff its SAM with the stock binary's)
+#   bitmapperBS_seam_cpu  linked against the CPU oracle behind the same C ABI (seam_cpu_shim.cpp): tests the splice without a GPU
+ROOT="$(cd "$HERE/.." && pwd)"
+cp "$TMP/Schema.cpp" "$TMP/Schema_seam.cpp"
+python3 "$ROOT/integration/patch_reference.py" "$TMP/Schema_seam.cpp"
+( cd "$TMP" && for f in saca-k bwt Bitmapper_main Process_CommandLines Auxiliary Index Process_sam_out Process_Reads Ref_Genome Levenshtein_Cal SAM_queue bam_prase ksw; do
+    g++ -w -O3 -mavx2 -mpopcnt -fomit-frame-pointer -D__AVX2__ -I "$REF/htslib" -c $f.cpp -o $f.o & done; wait
+  g++ -w -O3 -mavx2 -mpopcnt -fomit-frame-pointer -D__AVX2__ -I "$REF/htslib" -I "$ROOT/include" -I "$ROOT/integration" -c Schema_seam.cpp -o Schema_seam.o )
+OBJS="saca-k.o bwt.o Bitmapper_main.o Process_CommandLines.o Auxiliary.o Index.o Schema_seam.o Process_sam_out.o Process_Reads.o Ref_Genome.o Levenshtein_Cal.o SAM_queue.o bam_prase.o ksw.o hts_stub.o"
+( cd "$TMP" && g++ -O2 -std=c++17 -w -c "$HERE/seam_cpu_shim.cpp" -o seam_cpu_shim.o && g++ -O2 -std=c++17 -w -Wno-sign-compare -c "$HERE/oracle_capi.cpp" -o oracle_capi.o \
+  && g++ $OBJS seam_cpu_shim.o oracle_capi.o -o bitmapperBS_seam_cpu -lm -lz -lpthread )
+cp "$TMP/bitmapperBS_seam_cpu" "$OUT/bitmapperBS_seam_cpu"
+if [ -f "$ROOT/bitmapperbs_b200/libbmbs_gpu.so" ]; then
+  ( cd "$TMP" && g++ $OBJS -o bitmapperBS_gpu -L"$ROOT/bitmapperbs_b200" -lbmbs_gpu -Wl,-rpath,'$ORIGIN/../../bitmapperbs_b200' -lm -lz -lpthread )
+  cp "$TMP/bitmapperBS_gpu" "$OUT/bitmapperBS_gpu"
+else
+  echo "build_ref: libbmbs_gpu.so not built yet -- bitmapperBS_gpu skipped (run bitmapperbs_b200/build.py first)" >&2
+fi
 g++ -O2 -std=c++17 -pthread "$HERE/psascan_shim.cpp" -o "$OUT/psascan"
 # function-level harnesses over the reference's own headers / sources
 g++ -w -O3 -mavx2 -mpopcnt -D__AVX2__ -shared -fPIC -pthread -I "$REF" "$HERE/ref_harness_bpm.cpp" -o "$OUT/libref_bpm.so"

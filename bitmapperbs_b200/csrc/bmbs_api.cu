@@ -377,7 +377,7 @@ struct bmbs_batch {
   u64* d_tile = nullptr;
   u64* h_small = nullptr;        // pinned: totals[2], status, counters[8]
   cudaEvent_t ev[9] = {nullptr};
-  int n_reads = 0, pe = 0, max_len = 0, launches = 0, sm_count = 148;
+  int n_reads = 0, pe = 0, max_len = 0, launches = 0, sm_count = 148, seed_blocks_per_sm = 8; u32 seed_plane_cap = 0;
   bool ran = false;
 };
 
@@ -435,7 +435,7 @@ extern "C" int bmbs_batch_create(bmbs_index* idx, int dev, size_t max_reads, siz
   A(dalloc(b, &v.slot_row, S)); A(dalloc(b, &v.slot_adj, S)); A(dalloc(b, &v.slot_read, S)); A(dalloc(b, &v.cand, S)); A(dalloc(b, &v.vcnt, S));
   A(dalloc(b, &v.nv, R)); A(dalloc(b, &v.voff, R)); A(dalloc(b, &v.keep, S));
   A(dalloc(b, &v.vitems, S)); A(dalloc(b, &v.out_cand, S));
-  A(dalloc(b, &v.out_res, R)); A(dalloc(b, &v.big_list, R)); A(dalloc(b, &v.big_count, 4)); A(dalloc(b, &v.sort32, R)); A(dalloc(b, &v.sort_count, 4));
+  A(dalloc(b, &v.out_res, R)); A(dalloc(b, &v.big_list, R)); A(dalloc(b, &v.big_count, 4)); A(dalloc(b, &v.sort32, R)); A(dalloc(b, &v.sort_count, 4)); A(dalloc(b, &v.mid_list, R)); A(dalloc(b, &v.big1k_list, R));
   v.scratch_cap = 2 * S + 65536;
   A(dalloc(b, &v.scratch, (size_t)v.scratch_cap)); A(dalloc(b, &v.scratch_used, 4));
   A(dalloc(b, &v.counters, 16)); A(dalloc(b, &v.totals, 4)); A(dalloc(b, &v.status, 4));
@@ -500,15 +500,29 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
     // read chunks staged per thread in shared memory: max_len/32 + 2 chunks of 16 bytes, at most 12 (longer reads: the rest from global memory)
     const u32 plane_cap = (u32)std::min(b->max_len / 32 + 2, 12);
     const size_t seed_smem = (size_t)plane_cap * SEED_BLOCK * sizeof(uint4);
-    seed_first<<<(n + 127) / 128, SEED_BLOCK, seed_smem, s>>>(ix, v, plane_cap); ++b->launches;
-    seed_second<<<(n + 127) / 128, SEED_BLOCK, seed_smem, s>>>(ix, v, plane_cap); ++b->launches;
-    seed_rest<<<(n + 127) / 128, SEED_BLOCK, seed_smem, s>>>(ix, v, plane_cap); ++b->launches;
+    if (!getenv("BMBS_SEED_PHASES")) {
+      // one persistent kernel: a lane per read, one dependent access per loop iteration, finished lanes take the next read
+      if (plane_cap != b->seed_plane_cap) {      // resident blocks: registers and the staged read chunks decide
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seed_reads, SEED_BLOCK, seed_smem) == cudaSuccess && per_sm > 0) b->seed_blocks_per_sm = per_sm;
+        if (const char* e = getenv("BMBS_SEED_BLOCKS")) b->seed_blocks_per_sm = std::max(1, atoi(e));
+        b->seed_plane_cap = plane_cap;
+      }
+      const int seed_blocks = std::min((n + SEED_BLOCK - 1) / SEED_BLOCK, b->sm_count * b->seed_blocks_per_sm);
+      seed_reads<<<seed_blocks, SEED_BLOCK, seed_smem, s>>>(ix, v, plane_cap); ++b->launches;
+    } else {      // the three phase kernels (one loop nest per read), kept for comparison
+      seed_first<<<(n + 127) / 128, SEED_BLOCK, seed_smem, s>>>(ix, v, plane_cap); ++b->launches;
+      seed_second<<<(n + 127) / 128, SEED_BLOCK, seed_smem, s>>>(ix, v, plane_cap); ++b->launches;
+      seed_rest<<<(n + 127) / 128, SEED_BLOCK, seed_smem, s>>>(ix, v, plane_cap); ++b->launches;
+    }
     CU(cudaEventRecord(b->ev[2], s));
     run_scan(b, v.ncand, (u32)n, v.coff, v.totals, v.slot_cap, 2u);
     expand_locate<<<(n + 127) / 128, 128, 0, s>>>(ix, v); ++b->launches;
     CU(cudaEventRecord(b->ev[3], s));
     votes_classify<<<(n + 127) / 128, 128, 0, s>>>(v); ++b->launches;
     votes_sort<32><<<b->sm_count * 4, 128, 0, s>>>(v); ++b->launches;
+    votes_mid<<<b->sm_count * 8, 128, 0, s>>>(v); ++b->launches;
+    votes_big1k<<<b->sm_count * 8, 128, 0, s>>>(v); ++b->launches;
     votes_big<<<b->sm_count * 4, 256, 0, s>>>(v); ++b->launches;
     CU(cudaEventRecord(b->ev[4], s));
     if (b->pe && !v.sensitive) { filter_pairs_kernel<<<(n / 2 + 127) / 128, 128, 0, s>>>(v); ++b->launches; }
@@ -532,6 +546,8 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
       expand_locate<<<(n + 127) / 128, 128, 0, s>>>(ix, w); ++b->launches;
       votes_classify<<<(n + 127) / 128, 128, 0, s>>>(w); ++b->launches;
       votes_sort<32><<<b->sm_count * 4, 128, 0, s>>>(w); ++b->launches;
+      votes_mid<<<b->sm_count * 8, 128, 0, s>>>(w); ++b->launches;
+      votes_big1k<<<b->sm_count * 8, 128, 0, s>>>(w); ++b->launches;
       votes_big<<<b->sm_count * 4, 256, 0, s>>>(w); ++b->launches;
       sens_reseed_filter<<<b->sm_count * 4, 128, 0, s>>>(w); ++b->launches;
       run_scan(b, w.nv, (u32)n, w.voff, w.totals + 1, w.slot_cap, 4u, w.totals + 2);

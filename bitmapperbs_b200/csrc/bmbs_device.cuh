@@ -71,29 +71,28 @@ __device__ __forceinline__ u64 rank_in(const DevIndex& ix, const OccBlock& b, u6
   return first_row_of(ix, c) + base + (u64)__popcll(head);
 }
 
-__device__ __forceinline__ u64 adjust_row(const DevIndex& ix, u64 row) { return row > ix.shapline ? row - 1 : row; }
+__device__ __forceinline__ u64 adjust_row(const DevIndex& ix, u64 row) { return row - (u64)(row > ix.shapline); }
 
 // one backward-extension step on [sp, ep): find_occ_fm_index_combine, bwt.h:1473-1596.
 // Returns the number of distinct occ blocks touched (1 or 2) for the work counters.
-// Both ends extend by the same symbol; when they fall into the same 64-row block (the usual case once an interval is
-// narrow) the second end is the first plus the symbol's count between them: one load, one plane select, two POPCs.
+// Straight-line code: both ends always load their block (the second load of an interval inside one block is the same
+// sector again, a hit), and plane / count / first row of the symbol are picked with masks, not branches -- the lanes of a
+// warp extend by different symbols over intervals of different widths, and every branch here splits them three or six ways.
+__device__ __forceinline__ u64 rank_masked(const DevIndex& ix, const OccBlock& b, u64 adj_row, u64 m0, u64 m1, u64 m2) {
+  const unsigned part = (unsigned)adj_row & 63u;
+  const u64 plane = (b.planes.x & m1) | (b.planes.y & m2) | (~(b.planes.x | b.planes.y) & m0);
+  const u64 base = (b.cnt.x & m1) | (b.cnt.y & m2) | (((b.blk << 6) - b.cnt.x - b.cnt.y) & m0);
+  const u64 first = (ix.C[1] & m1) | (ix.C[2] & m2) | (ix.C[0] & m0);
+  const u64 head = (plane >> 1) >> (63u - part);           // plane >> (64 - part), and 0 for part == 0
+  return first + base + (u64)__popcll(head);
+}
 __device__ __forceinline__ int lf_pair(const DevIndex& ix, u64& sp, u64& ep, int c) {
   const u64 a = adjust_row(ix, sp), b = adjust_row(ix, ep);
-  const OccBlock ba = load_occ(ix, a);
-  if ((b >> 6) != ba.blk) {
-    const OccBlock bb = load_occ(ix, b);
-    sp = rank_in(ix, ba, a, c);
-    ep = rank_in(ix, bb, b, c);
-    return 2;
-  }
-  const unsigned pa = (unsigned)a & 63u, pb = (unsigned)b & 63u;
-  const u64 plane = c == 1 ? ba.planes.x : c == 2 ? ba.planes.y : ~(ba.planes.x | ba.planes.y);
-  const u64 base = c == 1 ? ba.cnt.x : c == 2 ? ba.cnt.y : (ba.blk << 6) - ba.cnt.x - ba.cnt.y;
-  const u64 top = first_row_of(ix, c) + base + (u64)(pa ? __popcll(plane >> (64 - pa)) : 0);
-  u64 between = 0;
-  if (pb > pa) between = (u64)__popcll((plane << pa) >> (64 - (pb - pa)));    // rows a .. b-1, row i at bit 63-i
-  sp = top; ep = top + between;
-  return 1;
+  const OccBlock ba = load_occ(ix, a), bb = load_occ(ix, b);
+  const u64 m1 = 0ull - (u64)(c == 1), m2 = 0ull - (u64)(c == 2), m0 = ~(m1 | m2);
+  sp = rank_masked(ix, ba, a, m0, m1, m2);
+  ep = rank_masked(ix, bb, b, m0, m1, m2);
+  return bb.blk != ba.blk ? 2 : 1;
 }
 
 __device__ __forceinline__ void hash_query(const DevIndex& ix, u64 key, u64& sp, u64& ep) {

@@ -6,7 +6,8 @@
 //   seed_rest        kernel 1a, phase 3: the remaining greedy seeds
 //   expand_locate    kernel 1b: seed intervals -> one candidate site per row (dense suffix array gather, or LF-walk to a sampled row)
 //   votes_classify   kernel 2: what a read's candidates turn into; short segments sorted + run-length encoded in registers
-//   votes_sort<32>, votes_big   kernel 2 for segments of 17..32 (a warp) and longer (a CTA)
+//   votes_sort<32>, votes_mid, votes_big1k, votes_big   kernel 2 for segments of 17..32 (a warp, one key per lane), 33..256 (a warp, eight keys
+//                    per lane), 257..1024 (a CTA, eight keys per thread) and longer (a CTA over shared / global memory)
 //   filter_pairs_kernel         kernel 2b (paired end): distance pre-filter of the two mates' lists
 //   gather_work      the surviving windows as one VerifyItem each (resolved reads get their record directly)
 //   verify_windows   kernel 3: banded Myers bit-vector edit distance, read T may face reference C
@@ -61,6 +62,7 @@ struct BatchView {
   VerifyItem* vitems; bmbs_cand* out_cand;      // dense list of the windows that need the bit-vector kernel (count: list_count[3])
   bmbs_read_result* out_res;
   u32* sort32; u32* sort_count;                  // reads whose candidate segment (17..32 entries) is sorted by a warp; count in sort_count[1]
+  u32* mid_list; u32* big1k_list;                // segments of 33..256 (a warp, eight keys per lane; count in sort_count[2]) and 257..1024 (a CTA; sort_count[3])
   u32* big_list; u32* big_count; u64* scratch; u32* scratch_used; u64 scratch_cap;
   u64* counters; u64* totals;   // totals[0] candidate slots, [1] verification work items of this round, [2] out_cand base of this round, [3] out_cand entries in all
   u32* status;                  // bit0 per-read task overflow, bit1 slot capacity, bit2 work capacity, bit3 scratch
@@ -573,6 +575,278 @@ __global__ void __launch_bounds__(128) seed_rest(DevIndex ix, BatchView b, u32 p
   flush_counters(s_cnt, cn, b.counters);
 }
 
+// ---- seeding, one persistent kernel.  Every lane runs the seeding state machine of ONE read (first seed + unique-hit
+// shortcut, the one-mismatch second seed, the remaining greedy seeds: Schema.cpp:27151-27515 / :19586-19906) and takes the
+// next read from a global cursor when its read is finished, so no lane waits for the warp's longest read.  The machine is
+// cut into four kinds of step, each at most one round of dependent memory accesses:
+//   REFILL   take a read, stage its bit-plane chunks in shared memory
+//   START    start a seed: 16-mer key, deep-table / 16-mer-table lookup
+//   LF       one backward-extension step of the seed in progress (greedy or exact)
+//   COMPARE  a single row is left: locate it and compare the rest of the read with the genome directly
+//   DONE     a seed has its answer: the policy of the read's phase (which seeds count, where the next one starts), task records
+// The two that happen between seeds (DONE, then REFILL or START) are run back to back as one TRANSITION, and in every
+// iteration the WARP VOTES for what most of its lanes are waiting for -- TRANSITION, LF or COMPARE -- and executes only that.  A
+// loop nest per read (the phase kernels below) or a loop that runs every kind each iteration keeps 4-6 of 32 lanes busy on
+// a repeat-rich genome: the rare long paths are executed for one or two lanes while the others wait.  Decisions and their
+// order per read are those of seed_first / seed_second / seed_rest.
+enum { SK_FIRST = 0, SK_SECOND = 1, SK_REST = 2 };
+enum { PH_IDLE = 0, PH_REFILL = 1, PH_START = 2, PH_LF = 3, PH_COMPARE = 4, PH_DONE = 5 };
+
+__global__ void __launch_bounds__(128) seed_reads(DevIndex ix, BatchView b, u32 plane_cap) {
+  extern __shared__ uint4 s_planes[];      // [plane_cap][SEED_BLOCK] staged read chunks, one column per lane
+  __shared__ u64 s_cnt[4];
+  __shared__ unsigned char s_lut[256];
+  if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+  build_key_lut(s_lut);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const u32 n_reads = (u32)b.n_reads;
+  SeedCounters cn;
+  ReadPlanes rp; rp.p = nullptr; rp.s = s_planes + threadIdx.x; rp.ns = 0;
+  int ph = PH_REFILL;
+  // What a step of the seed in progress needs stays in registers; the per-read bookkeeping that only the transitions between
+  // seeds touch lives in shared memory, one column per lane (registers decide how many warps an SM holds, and the kernel
+  // lives on warps in flight).
+  __shared__ u32 s_w[21][SEED_BLOCK];
+  __shared__ u64 s_d[4][SEED_BLOCK];
+  const int tx = threadIdx.x;
+  u32 &r = s_w[0][tx], &L = s_w[1][tx], &first_c = s_w[2][tx], &off = s_w[3][tx], &first_len = s_w[4][tx], &max_seeds = s_w[5][tx], &seed_id = s_w[6][tx];
+  u32 &nt = s_w[7][tx], &nc = s_w[8][tx], &bn = s_w[9][tx], &bs0 = s_w[10][tx], &bs1 = s_w[11][tx], &bep = s_w[12][tx], &bel = s_w[13][tx];
+  u32 &first_cands = s_w[14][tx], &g_mlen = s_w[15][tx], &is_multi = s_w[16][tx], &second_ok = s_w[17][tx];
+  int &state = reinterpret_cast<int&>(s_w[18][tx]), &get_error = reinterpret_cast<int&>(s_w[19][tx]), &one_mm = reinterpret_cast<int&>(s_w[20][tx]);
+  u64 &sp = s_d[0][tx], &ep = s_d[1][tx], &site0 = s_d[2][tx], &g_hits = s_d[3][tx];   // g_hits, g_mlen: answer of the first seed, kept across its COMPARE step
+  u32 kind = SK_FIRST;
+  u32 s_off = 0, s_cur = 0, m = 0;                       // the seed in progress: start, bases available, symbols matched
+  u64 top = 0, bot = 0, ptop = 0, pbot = 0, sa_known = 0;
+  bool known_sa = false;
+  u32 ss_base = 0, ss_lo = 0, ss_hi = 0, ss_bad = 0;     // 32 symbols of the read from ss_base on
+  auto emit = [&](u64 a, u32 hits, u32 mlen, u32 o) {
+    if (nt < MAX_TASKS) { SeedTask t; t.sp = a; t.hits = hits; t.mlen = (unsigned short)mlen; t.off = (unsigned short)o; b.tasks[(size_t)nt * b.n_reads + r] = t; }
+    ++nt; nc += hits ? hits : 1u;
+  };
+  auto symbol_at = [&](u32 pos) -> int {                 // pos >= ss_base, non-decreasing within a seed
+    if (pos - ss_base >= 32u) { ss_base = pos; rp.window(pos, ss_lo, ss_hi, ss_bad); }
+    const unsigned sh = pos - ss_base;
+    const u32 l = (ss_lo >> sh) & 1u, h = (ss_hi >> sh) & 1u, bad = (ss_bad >> sh) & 1u;
+    return (int)((l | ((~(l | h) & 1u) << 1)) | (bad * 3u));
+  };
+  // the read is done: its records
+  auto finish = [&]() {
+    b.state[r] = (unsigned char)state;
+    b.flags[r] = (unsigned char)((is_multi ? 1 : 0) | (second_ok ? 2 : 0));
+    b.one_mm[r] = (short)one_mm;
+    b.site0[r] = site0;
+    b.ntask[r] = nt < MAX_TASKS ? nt : MAX_TASKS; b.ncand[r] = nt <= MAX_TASKS ? nc : 0xFFFFFFFFu;
+    if (b.sensitive) {
+      const bool resolved = state == BMBS_EXACT_UNIQUE || state == BMBS_MULTI_EXACT;
+      unsigned short* k5 = b.bk + (size_t)r * 5;
+      k5[0] = (unsigned short)(resolved ? 0 : bn); k5[1] = (unsigned short)bs0; k5[2] = (unsigned short)bs1; k5[3] = (unsigned short)bep;
+      k5[4] = (unsigned short)(resolved ? 0 : bel);
+      b.first_cands[r] = (unsigned short)(resolved ? 0 : first_cands);
+    }
+    ph = PH_REFILL;
+  };
+  // next seed of the greedy phase, or the end of the read (loop condition of Schema.cpp:27434)
+  auto next_rest = [&]() {
+    kind = SK_REST;
+    if (seed_id < max_seeds && off < L) { s_off = off; s_cur = L - off; ph = PH_START; } else finish();
+  };
+  // first seed, after the unique-hit shortcut did not settle the read (Schema.cpp:27203-27330); mlen: the seed length as the
+  // shortcut left it (clamped to the first C, or the index of the single mismatch)
+  auto first_rest = [&](u32 mlen) {
+    one_mm = (int)mlen;
+    if (mlen == L && g_hits > 1 && (!b.pe || g_hits <= b.multi_cap)) {
+      is_multi = 1;
+      if (first_c == L) {
+        state = BMBS_MULTI_EXACT;
+        if (b.pe) emit(sp, (u32)g_hits, mlen, 0);
+        else if (b.amb_out) emit(sp, (u32)(g_hits > MAX_SEED_HITS ? MAX_SEED_HITS : g_hits), mlen, 0);   // output_ambiguous_exact_map_output_buffer walks at most 1000 rows
+        finish();
+        return;
+      }
+    }
+    if (g_hits != 1 && mlen >= b.seed_len && g_hits <= MAX_SEED_HITS && g_hits != 0) emit(sp, (u32)g_hits, mlen, 0);
+    const bool used = g_hits == 1 || (g_mlen >= b.seed_len && g_hits <= MAX_SEED_HITS);
+    bn = used ? 1 : 0; bel = used ? first_len : 0; first_cands = nc;
+    off = mlen == 0 ? next_offset_unmatched(rp, L, 0) : mlen / 2;
+    seed_id = 1;
+    if (get_error == 1 && L - first_len >= 17) { kind = SK_SECOND; s_off = first_len; s_cur = L - first_len; ph = PH_START; }   // one-mismatch rule
+    else next_rest();
+  };
+  // the second seed has its answer (Schema.cpp:27334-27401): known_sa = its single site is in sa_known, else rows [top, bot)
+  auto second_done = [&]() {
+    const u64 hits = known_sa ? 1 : (bot > top ? bot - top : 0);
+    if (hits <= MAX_SEED_HITS) {
+      if (known_sa) emit(sa_known, 0, 0, 0); else if (hits) emit(top, (u32)hits, s_cur, s_off);
+      second_ok = 1; finish();
+    } else next_rest();
+  };
+  // a greedy seed has its answer: m symbols matched, rows [top, bot) (known_sa: one row whose suffix-array value is sa_known)
+  auto greedy_done = [&]() {
+    const u64 hits = known_sa ? 1 : bot - top;
+    const u32 mlen = m;
+    if (!known_sa) { sp = top; ep = bot; }
+    if (kind == SK_FIRST) {
+      g_hits = hits; g_mlen = mlen; first_len = mlen;
+      if (hits == 1) ph = PH_COMPARE;                                            // unique-hit shortcut: locate + direct compare
+      else first_rest(mlen);
+    } else {                                                                     // Schema.cpp:27434-27515
+      bool used = true;
+      if (hits == 1) { if (known_sa) emit(2 * ix.N - sa_known - mlen - off, 0, 0, 0); else emit(sp, 1, mlen, off); }
+      else if (mlen >= b.seed_len && hits <= MAX_SEED_HITS) { if (hits) emit(sp, (u32)hits, mlen, off); }
+      else { used = false; if (s_cur == mlen) { finish(); return; } }
+      if (used) { if (bn == 0) bs0 = off; else if (bn == 1) bs1 = off; bep = bel; bel = off + mlen; ++bn; }
+      off = mlen == 0 ? next_offset_unmatched(rp, L, off) : off + mlen / 2;
+      ++seed_id;
+      next_rest();
+    }
+  };
+  for (;;) {
+    const u32 m_lf = __ballot_sync(0xffffffffu, ph == PH_LF), m_cmp = __ballot_sync(0xffffffffu, ph == PH_COMPARE);
+    const u32 m_tr = __ballot_sync(0xffffffffu, ph == PH_DONE || ph == PH_START || ph == PH_REFILL);
+    if (!(m_lf | m_cmp | m_tr)) break;
+    const int c_lf = __popc(m_lf), c_cmp = __popc(m_cmp), c_tr = __popc(m_tr);
+    const bool do_tr = c_tr >= c_lf && c_tr >= c_cmp, do_lf = !do_tr && c_lf >= c_cmp;
+    if (do_tr) {
+      // ---- a seed has its answer: the policy of the read's phase
+      if (ph == PH_DONE) { if (kind == SK_SECOND) second_done(); else greedy_done(); }
+      const u32 m_refill = __ballot_sync(0xffffffffu, ph == PH_REFILL);
+      const int c_refill = __popc(m_refill);
+      // ---- lanes without a read take the next ones (one atomic per warp)
+      if (m_refill) {
+      u32 base = 0;
+      const int leader = __ffs(m_refill) - 1;
+      if (lane == leader) base = atomicAdd(b.list_count, (u32)c_refill);
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (ph == PH_REFILL) {
+        const u32 i = base + __popc(m_refill & ((1u << lane) - 1u));
+        if (i >= n_reads) ph = PH_IDLE;
+        else {
+          r = i;
+          L = b.len[r]; first_c = b.first_c[r];
+          rp.stage(b.rplanes + plane_chunk_offset(b.offsets, (int)r), L, s_planes + threadIdx.x, plane_cap);
+          { u64 ms = (u64)L / 10 - 1; if (ms > 25) ms = 25; max_seeds = (u32)ms; }   // u64 wrap for L < 10, as in the reference
+          nt = 0; nc = 0; off = 0; first_len = 0; seed_id = 0; sp = 0; ep = 0; site0 = 0;
+          state = BMBS_NONE; get_error = -1; one_mm = 0; is_multi = 0; second_ok = 0;
+          bn = 0; bs0 = 0; bs1 = 0; bep = 0; bel = 0; first_cands = 0;
+          if (max_seeds > 0 && L > 0) { kind = SK_FIRST; s_off = 0; s_cur = L; ph = PH_START; }
+          else finish();                                                     // no seed at all
+        }
+      }
+      }
+      if (ph == PH_START) {
+        // ---- start of a seed: key, table lookup (count_backward_as_much_1_terminate bwt.h:2081 / count_hash_table :1848)
+        const bool exact = kind == SK_SECOND;
+        bool dead = false, answered = false;                   // no hit at all / the table entry already is the answer
+        u32 key;
+        known_sa = false;
+        if (s_cur < (exact ? 17u : 18u) || !key16(rp, s_lut, s_off, key)) { dead = true; m = 0; }
+        else {
+          m = 16;
+          ss_base = s_off + 16; rp.window(ss_base, ss_lo, ss_hi, ss_bad);
+          bool deep = false;
+          if (ix.ktab && s_cur >= 16 + ix.kdepth) {
+            u32 ext;
+            if (kmer_ext(ix, s_lut, ss_lo, ss_hi, ss_bad, ext)) {
+              const u64 e = __ldg(ix.ktab + (u64)key * ix.kpow + ext); ++cn.n_hash;
+              const u64 size = e >> 39; const u32 code = (u32)(e >> 36) & 7u;
+              if (size != KTAB_SAT) {
+                if (code == 0) { dead = true; m = 0; }         // the 16-mer does not occur
+                else {
+                  m = 15 + code; top = e & 0xFFFFFFFFFull; bot = top + size;
+                  if (!exact) {
+                    if (size == 1) { known_sa = true; sa_known = top; answered = true; }   // one row: the entry holds its SA value
+                    else if (m < 16 + ix.kdepth) answered = true;
+                  } else {
+                    if (m < 16 + ix.kdepth && size >= 2) dead = true;      // the next symbol empties the interval
+                    else if (size == 1) { known_sa = true; sa_known = top; }
+                  }
+                  deep = true;
+                }
+              }
+            }
+          }
+          if (!dead && !answered && !deep) {
+            hash_query(ix, key, top, bot); ++cn.n_hash;
+            if (bot <= top) { dead = true; m = 0; }
+          }
+        }
+        if (dead) { top = 0; bot = 0; known_sa = false; ph = PH_DONE; }
+        else if (answered) ph = PH_DONE;
+        else { ph = PH_LF; ptop = ~0ull; pbot = ~0ull; }
+      }
+    } else if (do_lf) {
+      if (ph == PH_LF) {
+        if (kind != SK_SECOND) {
+          // ---- one step of count_backward_as_much_1_terminate's loop (bwt.h:2081-2209)
+          bool stop = true;
+          if (m < s_cur) {
+            ptop = top; pbot = bot;
+            const int c = symbol_at(s_off + m);
+            if (bot - top != 1) {
+              if (c > 2) bot = top;
+              else {
+                cn.n_occ += lf_pair(ix, top, bot, c);
+                if (bot > top) { ++m; stop = m >= s_cur; }
+              }
+            }
+          }
+          if (stop) { if (bot <= top) { top = ptop; bot = pbot; } ph = PH_DONE; }
+        } else {
+          // ---- one step of count_hash_table's loop (bwt.h:1848-1952); a single row left is located and compared directly
+          if (m < s_cur && bot > top) {
+            if (bot - top == 1) ph = PH_COMPARE;
+            else {
+              const int c = symbol_at(s_off + m);
+              if (c > 2) { bot = top; ph = PH_DONE; }
+              else { cn.n_occ += lf_pair(ix, top, bot, c); ++m; }
+            }
+          } else {
+            if (known_sa) sa_known = 2 * ix.N - sa_known - m - s_off;   // the pattern ends where the table entry stands: its site
+            ph = PH_DONE;
+          }
+        }
+      }
+    } else {
+      if (ph == PH_COMPARE) {
+        if (kind == SK_FIRST) {
+          // ---- unique first seed: locate, compare the rest of the read with the genome (try_process_unique_mismatch_end_to_end_*, Schema.cpp:15410)
+          int st = 0; const u64 sa = known_sa ? sa_known : locate_row(ix, sp, st); cn.n_llf += st; ++cn.n_rows;
+          u32 mlen = g_mlen;
+          const u64 site = 2 * ix.N - sa - mlen;
+          emit(site, 0, 0, 0);
+          if (mlen > first_c) mlen = first_c;
+          int errors = 0;
+          if (mlen != L) errors = compare_rest(ix, rp, site, L, mlen);
+          get_error = errors;
+          if (errors == 0) { state = BMBS_EXACT_UNIQUE; site0 = site; finish(); }
+          else first_rest(mlen);
+        } else {
+          // ---- exact seed with one row left: the remaining symbols can only keep that row or empty the interval
+          int st = 0; const u64 sa = known_sa ? sa_known : locate_row(ix, top, st); cn.n_llf += st; ++cn.n_rows;
+          const u64 s0 = 2 * ix.N - sa - m;                 // double-strand coordinate of read[s_off]
+          bool ok = s0 + s_cur <= 2 * ix.N;                 // else the text ends before the pattern does
+          for (u32 p = s_off + m; ok && p < s_off + s_cur; p += 32) {
+            u32 rlo, rhi, rbad; rp.window(p, rlo, rhi, rbad);
+            const u64 g = s0 + (p - s_off);
+            const uint2 w0 = __ldg(ix.planes + (g >> 5)), w1 = __ldg(ix.planes + (g >> 5) + 1);
+            const unsigned sh = (unsigned)g & 31u;
+            const u32 glo = __funnelshift_r(w0.x, w1.x, sh), ghi = __funnelshift_r(w0.y, w1.y, sh);
+            u32 mism = (rlo ^ glo) | (~rlo & (rhi ^ ghi)) | rbad;   // 3-letter equality: lo set (C/T) ignores hi
+            const u32 left = s_off + s_cur - p;
+            if (left < 32u) mism &= (1u << left) - 1u;
+            if (mism) ok = false;
+          }
+          known_sa = ok; sa_known = s0 - s_off;             // the site, or no hit
+          if (!ok) bot = top;
+          ph = PH_DONE;
+        }
+      }
+    }
+  }
+  flush_counters(s_cnt, cn, b.counters);
+}
+
 // ------------------------------------------------------------------------------------------- expand + locate
 // Seed tasks -> candidate sites, one kernel.  A warp owns 32 consecutive reads, i.e. one contiguous range of candidate
 // slots [coff[r0], coff[r0+32]).  Its lanes first lay the reads' tasks out as a table of segments {first slot, first row or
@@ -721,7 +995,7 @@ __global__ void __launch_bounds__(128) votes_classify(BatchView b) {
   int which = -1; u32 beg = 0, n = 0;
   if (r < b.n_reads && !*b.status) {
     beg = b.coff[r]; n = b.coff[r + 1] - beg;
-    if (classify_read(b, r, beg, n, true)) which = n <= 16 ? 0 : n <= 32 ? 1 : 2;
+    if (classify_read(b, r, beg, n, true)) which = n <= 16 ? 0 : n <= 32 ? 1 : n <= 256 ? 2 : n <= 1024 ? 3 : 4;
   }
   const bool small = which == 0;
   if (__any_sync(0xffffffffu, small)) {
@@ -730,7 +1004,9 @@ __global__ void __launch_bounds__(128) votes_classify(BatchView b) {
     else sort_encode_small<16>(b, r, beg, n, small, multi);
   }
   list_append(b.sort32, b.sort_count + 1, which == 1, (u32)r);
-  list_append(b.big_list, b.big_count, which == 2, (u32)r);
+  list_append(b.mid_list, b.sort_count + 2, which == 2, (u32)r);
+  list_append(b.big1k_list, b.sort_count + 3, which == 3, (u32)r);
+  list_append(b.big_list, b.big_count, which == 4, (u32)r);
 }
 
 // W lanes per read (32; segments up to 16 are sorted by their own thread in votes_classify): bitonic sort in registers over shuffles, run-length encode with a ballot, written back in
@@ -770,6 +1046,116 @@ __global__ void __launch_bounds__(128) votes_sort(BatchView b) {
       }
       if (sub == 0) b.nv[r] = __popc(heads);
     }
+  }
+}
+
+// ---- segments of 33..1024 candidates: bitonic sort with E consecutive keys per thread in registers.  Element e = tid * E + i.
+// A compare-exchange stage with partner distance j < E stays inside the thread (compile-time register indices), E <= j < 32 E
+// is one shuffle per key inside the warp, and only j >= 32 E (CTA form, two warps or more) goes through shared memory -- three
+// exchanges for 1024 keys where a plain shared-memory network needs 55 block-wide barriers.  Padding is ~0 (sorts last).
+template <int E, int T>
+__device__ __forceinline__ void bitonic_regs(u64 (&v)[E], const int tid, u64* xch) {
+#pragma unroll
+  for (int k = 2; k <= E * T; k <<= 1) {
+    const bool up = ((tid * E) & k) == 0;                       // for k < E the direction depends on i: handled below
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32 * E) {                                        // partner in another warp
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < E; ++i) xch[i * T + tid] = v[i];
+        __syncthreads();
+        const int pt = tid ^ (j / E);
+        const bool take_min = up == ((tid & (j / E)) == 0);
+#pragma unroll
+        for (int i = 0; i < E; ++i) { const u64 o = xch[i * T + pt]; v[i] = take_min ? (o < v[i] ? o : v[i]) : (o > v[i] ? o : v[i]); }
+      } else if (j >= E) {                                      // partner lane in the same warp
+        const bool take_min = up == ((tid & (j / E)) == 0);
+#pragma unroll
+        for (int i = 0; i < E; ++i) { const u64 o = __shfl_xor_sync(0xffffffffu, v[i], j / E); v[i] = take_min ? (o < v[i] ? o : v[i]) : (o > v[i] ? o : v[i]); }
+      } else {                                                  // both keys in this thread
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+          if ((i & j) == 0) {
+            const bool asc = k < E ? ((i & k) == 0) : up;
+            const u64 a = v[i], c = v[i | j];
+            const bool sw = asc ? (a > c) : (a < c);
+            v[i] = sw ? c : a; v[i | j] = sw ? a : c;
+          }
+        }
+      }
+    }
+  }
+}
+
+// run-length encode the sorted keys a[0..n) (shared memory) of read r into cand[] / vcnt[] by the 32 lanes of a warp
+__device__ __forceinline__ void warp_encode_runs(BatchView& b, int r, u32 beg, u32 n, const u64* a, int lane) {
+  const u64 k = b.kk[r];
+  u32 base = 0;
+  for (u32 c0 = 0; c0 < n; c0 += 32) {
+    const u32 i = c0 + lane;
+    const bool head = i < n && (i == 0 || a[i - 1] != a[i]);
+    const u32 bal = __ballot_sync(0xffffffffu, head);
+    if (head) {
+      u32 e = i + 1; while (e < n && a[e] == a[i]) ++e;
+      const u32 idx = base + __popc(bal & ((1u << lane) - 1u));
+      b.cand[beg + idx] = window_start(a[i], k);                // idx <= i and a[] is a copy: in place is safe
+      b.vcnt[beg + idx] = e - i;
+    }
+    base += __popc(bal);
+  }
+  if (lane == 0) b.nv[r] = base;
+}
+
+// one warp per segment of 33..256 candidates (eight keys per lane)
+__global__ void __launch_bounds__(128) votes_mid(BatchView b) {
+  constexpr int E = 8;
+  __shared__ u64 s_keys[4][32 * E];
+  const u32 nlist = *b.status ? 0u : b.sort_count[2];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const u32 warps = gridDim.x * (blockDim.x >> 5);
+  u64* a = s_keys[wid];
+  for (u32 g = blockIdx.x * (blockDim.x >> 5) + wid; g < nlist; g += warps) {
+    const int r = (int)b.mid_list[g];
+    const u32 beg = b.coff[r], n = b.coff[r + 1] - beg;
+    u64 v[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) { const u32 e = (u32)lane * E + i; v[i] = e < n ? b.cand[beg + e] : ~0ull; }
+    bitonic_regs<E, 32>(v, lane, nullptr);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < E; ++i) a[lane * E + i] = v[i];
+    __syncwarp();
+    if (b.round == 0 && b.state[r] == BMBS_MULTI_EXACT) {
+      for (u32 i = lane; i < n; i += 32) { b.cand[beg + i] = a[i]; b.vcnt[beg + i] = 0; }
+      if (lane == 0) b.nv[r] = n;
+    } else warp_encode_runs(b, r, beg, n, a, lane);
+    __syncwarp();
+  }
+}
+
+// one CTA of 128 threads per segment of 257..1024 candidates (eight keys per thread)
+__global__ void __launch_bounds__(128) votes_big1k(BatchView b) {
+  constexpr int E = 8, T = 128;
+  __shared__ u64 s_keys[E * T];
+  const u32 nlist = *b.status ? 0u : b.sort_count[3];
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (u32 g = blockIdx.x; g < nlist; g += gridDim.x) {
+    const int r = (int)b.big1k_list[g];
+    const u32 beg = b.coff[r], n = b.coff[r + 1] - beg;
+    u64 v[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) { const u32 e = (u32)tid * E + i; v[i] = e < n ? b.cand[beg + e] : ~0ull; }
+    bitonic_regs<E, T>(v, tid, s_keys);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < E; ++i) s_keys[tid * E + i] = v[i];
+    __syncthreads();
+    if (b.round == 0 && b.state[r] == BMBS_MULTI_EXACT) {
+      for (u32 i = tid; i < n; i += T) { b.cand[beg + i] = s_keys[i]; b.vcnt[beg + i] = 0; }
+      if (tid == 0) b.nv[r] = n;
+    } else if (tid < 32) warp_encode_runs(b, r, beg, n, s_keys, lane);     // <= 32 passes of a warp; the sort dominates
+    __syncthreads();
   }
 }
 
@@ -1317,7 +1703,7 @@ __global__ void __launch_bounds__(128) sens_pair(BatchView b) {
 __global__ void reseed_clear(BatchView b) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < b.n_reads) { b.ntask[r] = 0; b.ncand[r] = 0; b.nv[r] = 0; }
-  if (r == 0) { b.totals[2] = b.totals[1]; b.list_count[3] = 0; b.sort_count[0] = 0; b.sort_count[1] = 0; b.big_count[0] = 0; b.scratch_used[0] = 0; }      // the re-seeding round appends to out_cand
+  if (r == 0) { b.totals[2] = b.totals[1]; b.list_count[3] = 0; b.sort_count[0] = 0; b.sort_count[1] = 0; b.sort_count[2] = 0; b.sort_count[3] = 0; b.big_count[0] = 0; b.scratch_used[0] = 0; }      // the re-seeding round appends to out_cand
 }
 
 // reseed_filter_muti_thread, Schema.cpp:16998-17240: up to three exact seeds chosen from the gaps of the seeds used so

@@ -132,6 +132,34 @@ def test_non_default_parameters_match_oracle(golden, gidx, oidx, e_rate, seed_le
         assert np.array_equal(gs[f], os_[f]), f
 
 
+def test_high_copy_repeats_every_candidate_sort_tier(built, tmp_path):
+    """a genome of high-copy repeat families: candidate segments of every size class (registers <= 16, warp <= 32, warp with
+    eight keys per lane <= 256, CTA <= 1024, CTA over shared / global memory above) and long seed chains with wide intervals;
+    single-end and paired records against the oracle"""
+    chroms = S.random_genome([700000, 500000], seed=321, repeat_fraction=0.7, repeat_copies=(40, 1500), repeat_len=(200, 700), repeat_div=(0.005, 0.06))
+    S.write_fasta(tmp_path / "g.fa", chroms)
+    subprocess.run([str(built["indexer"]), "g.fa"], cwd=tmp_path, check=True, stderr=subprocess.DEVNULL)
+    g, st = S.concat_genome(chroms)
+    m1, _ = S.simulate_fast(g, st, 6000, 150, 17, paired=False, indel_reads=0.2)
+    a, b = S.simulate_fast(g, st, 2500, 120, 18)
+    se = [bytes(r) for r in m1]
+    mates = [x for pr in zip((bytes(r) for r in a), (revcomp(bytes(r)) for r in b)) for x in pr]
+    ix = B.Index(tmp_path / "g.fa.index"); ox = OracleIndex(tmp_path / "g.fa.index")
+    try:
+        gres, gcand = ix.map_batch_se(se)
+        ores, ocand = ox.map_se(se, cap=1 << 24)
+        assert_same_records(gres, gcand, ores, ocand)
+        n = gres["n_cand"][gres["state"] == B.VERIFY]
+        assert (n > 16).any() and (n > 256).any(), "the data set no longer reaches the larger sort tiers"
+        gres, gcand = ix.map_batch_pe(mates)
+        ores, ocand = ox.map_pe(mates, cap=1 << 24)
+        v = np.repeat(gres["state"] == B.VERIFY, gres["n_cand"])
+        assert_same_records(gres, gcand, ores, ocand, compare_vote=False)
+        assert np.array_equal(gcand["vote"][v], ocand["vote"][v])
+    finally:
+        ix.close()
+
+
 def test_mixed_lengths_and_unequal_mates(golden, gidx, oidx):
     """reads of many lengths in one batch (ragged input); mates of different lengths in a pair"""
     rng = np.random.default_rng(11)

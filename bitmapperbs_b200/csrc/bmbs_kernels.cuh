@@ -1399,6 +1399,88 @@ __device__ __forceinline__ void bpm_columns(const u64* __restrict__ sm, int stri
   end_out = site; err_out = best;
 }
 
+// ---- 32-bit band (k <= 15): the form the ALU pipe is budgeted for.  Per column: one PRMT takes the read's code out of a
+// byte-spread copy of its nibble word, one IMAD turns it into the shared-memory address of that symbol's match plane, one
+// funnel shift aligns the 64-bit chunk to the column, and the band mask rides in the LOP3 that forms X = (Eq & mask) | VN
+// (written as inline lop3 so that the compiler keeps VN in a register instead of recomputing it inside a second LOP3):
+// 7 LOP3 + 3 SHF + 1 PRMT on the ALU pipe, IMAD + IADD on the FMA pipe, one LDS.64.
+__device__ __forceinline__ void bpm_step32(u32 eq_raw, u32 mask, u32& VP, u32& VN, u32& dbits) {
+  u32 X;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(X) : "r"(eq_raw), "r"(mask), "r"(VN));    // (eq_raw & mask) | VN
+  const u32 D0 = ((VP + (X & VP)) ^ VP) | X;
+  const u32 HN = VP & D0, HP = VN | ~(VP | D0);
+  const u32 X2 = D0 >> 1;
+  VN = X2 & HP; VP = HN | ~(X2 | HP);
+  dbits = __funnelshift_r(dbits, D0, 1);
+}
+template <int J>
+__device__ __forceinline__ u32 eq_raw32(const char* __restrict__ cbytes, u32 pstride8, u32 ev, u32 od, int t0) {
+  const u32 code = __byte_perm((J & 1) ? od : ev, 0u, 0x4440u | (u32)(J >> 1));          // nibble J of the word, as a number
+  const u64 e0 = *reinterpret_cast<const u64*>(cbytes + code * pstride8);
+  return (u32)(e0 >> (t0 + J));
+}
+__device__ __forceinline__ void bpm_columns32(const u64* __restrict__ sm, int stride, int nch2, const u32* __restrict__ rw,
+                                              int L, int k, int& end_out, u32& err_out) {
+  const int band = 2 * k + 1;
+  const u32 mask = band >= 32 ? ~0u : ((1u << band) - 1u);
+  const u32 pstride8 = (u32)(nch2 * stride) * 8u;
+  u32 VP = 0, VN = 0;
+  int err = 0;
+  const int limit = 3 * k;   // err - 2k > k can never recover (Levenshtein_Cal.h:455); checked every eight columns
+  bool dead = false;
+  u32 dbits = 0;
+  u32 next_word = L > 0 ? __ldg(rw) : 0u;     // the read's code words are fetched one group of eight columns ahead
+  for (int ch = 0; ch * 32 < L && !dead; ++ch) {
+    const char* cbytes = reinterpret_cast<const char*>(sm + ch * stride);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int i0 = ch * 32 + g * 8;
+      if (i0 < L && !dead) {
+        const u32 word = next_word;
+        if (i0 + 8 < L) next_word = __ldg(rw + (i0 >> 3) + 1);
+        const u32 ev = word & 0x0F0F0F0Fu, od = (word >> 4) & 0x0F0F0F0Fu;
+        if (i0 + 8 <= L) {
+          bpm_step32(eq_raw32<0>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
+          bpm_step32(eq_raw32<1>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
+          bpm_step32(eq_raw32<2>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
+          bpm_step32(eq_raw32<3>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
+          bpm_step32(eq_raw32<4>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
+          bpm_step32(eq_raw32<5>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
+          bpm_step32(eq_raw32<6>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
+          bpm_step32(eq_raw32<7>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
+          err += 8 - __popc(dbits >> 24);
+        } else {
+          const int n = L - i0;
+          for (int j = 0; j < n; ++j) {
+            const u32 code = (word >> (4 * j)) & 0xFu;
+            const u64 e0 = *reinterpret_cast<const u64*>(cbytes + code * pstride8);
+            bpm_step32((u32)(e0 >> (g * 8 + j)), mask, VP, VN, dbits);
+          }
+          err += n - __popc(dbits >> (32 - n));
+        }
+        if (err > limit) dead = true;
+      }
+    }
+  }
+  end_out = -1; err_out = 0xFFFFFFFFu;
+  if (dead) return;
+  // the last column, walked down the band (Levenshtein_Cal.h:524-563).  err can only fall by one per negative vertical delta:
+  // when even that cannot reach k, no cell of the column does and the walk is skipped
+  if (err - __popc(VN & (mask >> 1)) > k) return;
+  const int last = L - 1;
+  u32 best = 0xFFFFFFFFu; int site = -1;
+  if (err <= k) { best = (u32)err; site = last; }
+  int ungapped = err;
+  for (int i = 0; i < 2 * k; ++i) {
+    err += (int)((VP >> i) & 1) - (int)((VN >> i) & 1);
+    if (err <= k && (u32)err <= best) { best = (u32)err; site = last + i + 1; }
+    if (i + 1 == k) ungapped = err;
+  }
+  if (k == 0) ungapped = err;
+  if (ungapped >= 0 && ungapped <= k && (u32)ungapped == best) site = last + k;
+  end_out = site; err_out = best;
+}
+
 __global__ void verify_windows(DevIndex ix, BatchView b, int nch2) {
   extern __shared__ u64 sm_all[];
   __shared__ u64 s_cnt[3];
@@ -1449,7 +1531,7 @@ __global__ void verify_windows(DevIndex ix, BatchView b, int nch2) {
         for (int c = 0; c <= nch; ++c) for (int p = 0; p < 5; ++p) sm[(p * nch2 + c) * stride] = 0;
       }
       const u32* rw = b.codes + i1.x;
-      if (k <= 15) bpm_columns<u32>(sm, stride, nch2, rw, L, k, end, err);
+      if (k <= 15) bpm_columns32(sm, stride, nch2, rw, L, k, end, err);
       else bpm_columns<u64>(sm, stride, nch2, rw, L, k, end, err);
       ++verified; cells += (u64)L * (u64)(2 * k + 1);
     }

@@ -74,6 +74,80 @@ void read_fasta(const char* path, std::vector<Chrom>& chroms, std::vector<uint8_
   if (replaced) fprintf(stderr, "bmbs-index: %llu bases outside ACGT replaced by pseudo-random bases (fixed seed)\n", (unsigned long long)replaced);
 }
 
+// ---- writers shared by the CPU builder below and the device builder (gpu_index.cu): same bytes from the same arrays
+inline void write_chrom_table(const std::string& fa, const std::vector<Chrom>& chroms, uint64_t N) {
+  FILE* f = fopen((fa + ".index").c_str(), "wb"); if (!f) die("cannot write .index");
+  uint64_t nc = chroms.size(); wr(f, &nc, 8, 1);
+  for (auto& c : chroms) { uint64_t l = c.name.size(); wr(f, &l, 8, 1); wr(f, c.name.data(), 1, l); wr(f, &c.len, 8, 1); }
+  wr(f, &N, 8, 1); fclose(f);
+}
+inline void write_pac(const std::string& fa, const std::vector<uint8_t>& g) {
+  const uint64_t N = g.size();
+  std::vector<uint8_t> pac((N + 3) / 4, 0);
+  for (uint64_t i = 0; i < N; ++i) {
+    uint8_t c = g[i] == 'A' ? 0 : g[i] == 'C' ? 1 : g[i] == 'G' ? 2 : 3;
+    pac[i >> 2] |= c << (6 - 2 * (i & 3));
+  }
+  FILE* f = fopen((fa + ".index.bs.pac").c_str(), "wb"); if (!f) die("cannot write .pac");
+  uint64_t nb = pac.size(); wr(f, &nb, 8, 1); wr(f, pac.data(), 1, nb); fclose(f);
+}
+// kc[h]: occurrences of 16-mer h in the text; tail: codes of the last min(15, n) symbols of the text
+inline void write_bwt_files(const std::string& fa, uint64_t R, uint64_t shapline, uint64_t cnt0, uint64_t cnt1, uint64_t cnt2,
+                            const std::vector<uint64_t>& bwt, uint64_t bwt_words, const std::vector<uint64_t>& high_occ,
+                            const std::vector<uint32_t>& ssa, const std::vector<uint64_t>& flag, uint64_t flag_words,
+                            const std::vector<uint32_t>& kc, const std::vector<uint8_t>& tail, uint64_t n) {
+  const std::string p = fa + ".index.bs.index";
+  {
+    FILE* f = fopen((p + ".occ").c_str(), "wb"); if (!f) die("cannot write .occ");
+    uint64_t l = high_occ.size(); wr(f, &l, 8, 1); wr(f, high_occ.data(), 8, l); fclose(f);
+  }
+  uint64_t nacgt[5] = {1, 1 + cnt0, 1 + cnt0 + cnt1, 1 + cnt0 + cnt1 + cnt2, 1 + cnt0 + cnt1 + cnt2};
+  {
+    FILE* f = fopen(p.c_str(), "wb"); if (!f) die("cannot write .bs.index");
+    wr(f, &R, 8, 1); wr(f, &shapline, 8, 1); wr(f, nacgt, 8, 5);
+    uint32_t prm[3] = {8, 64, 128}; wr(f, prm, 4, 3); fclose(f);
+  }
+  {
+    FILE* f = fopen((p + ".sa").c_str(), "wb"); if (!f) die("cannot write .sa");
+    uint64_t l = ssa.size(); wr(f, &l, 8, 1); wr(f, ssa.data(), 4, l);
+    wr(f, &flag_words, 8, 1); wr(f, flag.data(), 8, flag_words); fclose(f);
+  }
+  // ---- 3^16 table: entry h = first row of 16-mer h; rows of suffixes shorter than 16
+  // symbols that sit between two consecutive 16-mer intervals are recorded as a 4-bit
+  // gap in the top bits of the following entry (bwt.cpp:1893-2007, query bwt.h:284-306).
+  const uint64_t H = 43046721ull;  // 3^16
+  std::vector<uint64_t> short_pad;  // padded keys of the suffixes shorter than 16 (excluding the empty one)
+  for (uint64_t l = 1; l < 16 && l <= n; ++l) {
+    uint64_t v = 0;
+    for (uint64_t i = tail.size() - l; i < tail.size(); ++i) v = v * 3 + tail[i];
+    for (uint64_t i = l; i < 16; ++i) v *= 3;
+    short_pad.push_back(v);
+  }
+  std::sort(short_pad.begin(), short_pad.end());
+  std::vector<uint32_t> hi(H + 1, 0); std::vector<uint8_t> lo(H + 1, 0);
+  {
+    uint64_t rows_before = 1;   // the empty suffix
+    uint64_t chain = 1;         // what the table holds for entry h before it is visited
+    size_t sp_i = 0;
+    for (uint64_t h = 0; h < H; ++h) {
+      while (sp_i < short_pad.size() && short_pad[sp_i] <= h) { ++rows_before; ++sp_i; }
+      uint64_t top, bot; uint32_t diff = 0;
+      if (kc[h] == 0) { top = bot = chain; }
+      else { top = rows_before; bot = top + kc[h]; diff = (uint32_t)(top - chain) << 28; }
+      hi[h] = (uint32_t)(top >> 8) | diff; lo[h] = top & 255;
+      hi[h + 1] = (uint32_t)(bot >> 8); lo[h + 1] = bot & 255;
+      chain = (((uint64_t)(hi[h + 1] & 0x0FFFFFFFu)) << 8) | lo[h + 1];
+      rows_before += kc[h];
+    }
+  }
+  {
+    FILE* f = fopen((p + ".bwt").c_str(), "wb"); if (!f) die("cannot write .bwt");
+    wr(f, &bwt_words, 8, 1); wr(f, bwt.data(), 8, bwt_words);
+    uint64_t hn = H + 1; wr(f, &hn, 8, 1); wr(f, hi.data(), 4, hn); wr(f, lo.data(), 1, hn); fclose(f);
+  }
+  fprintf(stderr, "bmbs-index: wrote %s{,.bwt,.sa,.occ}\n", p.c_str());
+}
+
 }  // namespace indexer
 
 // Builds every index file next to `fa`; returns 0 on success (fatal problems exit with a message).
@@ -85,21 +159,8 @@ inline int build_index(const std::string& fa, int threads = 0) {
   const uint64_t N = g.size(), n = 2 * N;
   fprintf(stderr, "bmbs-index: %zu chromosomes, %llu bases\n", chroms.size(), (unsigned long long)N);
 
-  {  // chromosome table
-    FILE* f = fopen((fa + ".index").c_str(), "wb"); if (!f) die("cannot write .index");
-    uint64_t nc = chroms.size(); wr(f, &nc, 8, 1);
-    for (auto& c : chroms) { uint64_t l = c.name.size(); wr(f, &l, 8, 1); wr(f, c.name.data(), 1, l); wr(f, &c.len, 8, 1); }
-    wr(f, &N, 8, 1); fclose(f);
-  }
-  {  // 2-bit genome
-    std::vector<uint8_t> pac((N + 3) / 4, 0);
-    for (uint64_t i = 0; i < N; ++i) {
-      uint8_t c = g[i] == 'A' ? 0 : g[i] == 'C' ? 1 : g[i] == 'G' ? 2 : 3;
-      pac[i >> 2] |= c << (6 - 2 * (i & 3));
-    }
-    FILE* f = fopen((fa + ".index.bs.pac").c_str(), "wb"); if (!f) die("cannot write .pac");
-    uint64_t nb = pac.size(); wr(f, &nb, 8, 1); wr(f, pac.data(), 1, nb); fclose(f);
-  }
+  write_chrom_table(fa, chroms, N);
+  write_pac(fa, g);
 
   // 3-letter double-strand text, codes G=0 T=1 A=2
   std::vector<uint8_t> t(n);
@@ -153,28 +214,7 @@ inline int build_index(const std::string& fa, int threads = 0) {
   }
   if ((R & 255) == 0) flag[(R >> 8) * 5] = ssa.size();
 
-  const std::string p = fa + ".index.bs.index";
-  {
-    FILE* f = fopen((p + ".occ").c_str(), "wb"); if (!f) die("cannot write .occ");
-    uint64_t l = high_occ.size(); wr(f, &l, 8, 1); wr(f, high_occ.data(), 8, l); fclose(f);
-  }
-  uint64_t nacgt[5] = {1, 1 + cnt[0], 1 + cnt[0] + cnt[1], 1 + cnt[0] + cnt[1] + cnt[2], 1 + cnt[0] + cnt[1] + cnt[2]};
-  {
-    FILE* f = fopen(p.c_str(), "wb"); if (!f) die("cannot write .bs.index");
-    wr(f, &R, 8, 1); wr(f, &shapline, 8, 1); wr(f, nacgt, 8, 5);
-    uint32_t prm[3] = {8, 64, 128}; wr(f, prm, 4, 3); fclose(f);
-  }
-  {
-    FILE* f = fopen((p + ".sa").c_str(), "wb"); if (!f) die("cannot write .sa");
-    uint64_t l = ssa.size(); wr(f, &l, 8, 1); wr(f, ssa.data(), 4, l);
-    wr(f, &flag_words, 8, 1); wr(f, flag.data(), 8, flag_words); fclose(f);
-  }
-  // ---- 3^16 table: entry h = first row of 16-mer h; rows of suffixes shorter than 16
-  // symbols that sit between two consecutive 16-mer intervals are recorded as a 4-bit
-  // gap in the top bits of the following entry (bwt.cpp:1893-2007, query bwt.h:284-306).
-  const uint64_t H = 43046721ull;  // 3^16
-  std::vector<uint32_t> kc(H, 0);
-  std::vector<uint64_t> short_pad;  // padded keys of the suffixes shorter than 16 (excluding the empty one)
+  std::vector<uint32_t> kc(43046721ull, 0);
   if (n >= 16) {
     uint64_t key = 0; const uint64_t P15 = 14348907ull;
     for (int i = 0; i < 16; ++i) key = key * 3 + t[i];
@@ -184,35 +224,8 @@ inline int build_index(const std::string& fa, int threads = 0) {
       key = (key - t[q] * P15) * 3 + t[q + 16];
     }
   }
-  for (uint64_t l = 1; l < 16 && l <= n; ++l) {
-    uint64_t v = 0;
-    for (uint64_t i = n - l; i < n; ++i) v = v * 3 + t[i];
-    for (uint64_t i = l; i < 16; ++i) v *= 3;
-    short_pad.push_back(v);
-  }
-  std::sort(short_pad.begin(), short_pad.end());
-  std::vector<uint32_t> hi(H + 1, 0); std::vector<uint8_t> lo(H + 1, 0);
-  {
-    uint64_t rows_before = 1;   // the empty suffix
-    uint64_t chain = 1;         // what the table holds for entry h before it is visited
-    size_t sp_i = 0;
-    for (uint64_t h = 0; h < H; ++h) {
-      while (sp_i < short_pad.size() && short_pad[sp_i] <= h) { ++rows_before; ++sp_i; }
-      uint64_t top, bot; uint32_t diff = 0;
-      if (kc[h] == 0) { top = bot = chain; }
-      else { top = rows_before; bot = top + kc[h]; diff = (uint32_t)(top - chain) << 28; }
-      hi[h] = (uint32_t)(top >> 8) | diff; lo[h] = top & 255;
-      hi[h + 1] = (uint32_t)(bot >> 8); lo[h + 1] = bot & 255;
-      chain = (((uint64_t)(hi[h + 1] & 0x0FFFFFFFu)) << 8) | lo[h + 1];
-      rows_before += kc[h];
-    }
-  }
-  {
-    FILE* f = fopen((p + ".bwt").c_str(), "wb"); if (!f) die("cannot write .bwt");
-    wr(f, &bwt_words, 8, 1); wr(f, bwt.data(), 8, bwt_words);
-    uint64_t hn = H + 1; wr(f, &hn, 8, 1); wr(f, hi.data(), 4, hn); wr(f, lo.data(), 1, hn); fclose(f);
-  }
-  fprintf(stderr, "bmbs-index: wrote %s{,.bwt,.sa,.occ}\n", p.c_str());
+  std::vector<uint8_t> tail(t.end() - (n >= 15 ? 15 : n), t.end());
+  write_bwt_files(fa, R, shapline, cnt[0], cnt[1], cnt[2], bwt, bwt_words, high_occ, ssa, flag, flag_words, kc, tail, n);
   return 0;
 }
 

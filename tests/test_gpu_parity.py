@@ -13,6 +13,7 @@ from conftest import read_fastq, revcomp, sam_body
 from oracle_binding import OracleIndex
 
 pytestmark = pytest.mark.gpu
+ROOT_DIR = Path(__file__).resolve().parent.parent
 ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
 
 
@@ -158,6 +159,26 @@ def test_high_copy_repeats_every_candidate_sort_tier(built, tmp_path):
         assert np.array_equal(gcand["vote"][v], ocand["vote"][v])
     finally:
         ix.close()
+
+
+def test_device_index_builder_writes_the_same_files(golden, built, tmp_path):
+    """bmbs-index-gpu (suffix sort by library radix sorts + device BWT passes; data prep for the 3.1 Gbp bench genome) must
+    write, byte for byte, the files of the CPU writer -- which are the reference's own (sha256 test in test_oracle_golden.py).
+    Genomes: the golden one, and one of high-copy repeat families (groups of equal 32-symbol keys refined over many rounds)"""
+    import filecmp, shutil
+    gpu_tool = ROOT_DIR / "bitmapperbs_b200/_build/bmbs-index-gpu"
+    if not gpu_tool.exists():
+        pytest.skip("bmbs-index-gpu not built")
+    chroms = S.random_genome([400000, 250000, 777], seed=4321, repeat_fraction=0.6, repeat_copies=(20, 800), repeat_len=(150, 3000), repeat_div=(0.0, 0.05))
+    S.write_fasta(tmp_path / "rep.fa", chroms)
+    shutil.copy(golden / "genome.fa", tmp_path / "gold.fa")
+    for name in ("gold.fa", "rep.fa"):
+        for tool, d in ((built["indexer"], "cpu"), (gpu_tool, "gpu")):
+            (tmp_path / d).mkdir(exist_ok=True)
+            shutil.copy(tmp_path / name, tmp_path / d / name)
+            subprocess.run([str(tool), name], cwd=tmp_path / d, check=True, stderr=subprocess.DEVNULL)
+        for ext in (".index", ".index.bs.pac", ".index.bs.index", ".index.bs.index.bwt", ".index.bs.index.sa", ".index.bs.index.occ"):
+            assert filecmp.cmp(tmp_path / "cpu" / (name + ext), tmp_path / "gpu" / (name + ext), shallow=False), (name, ext)
 
 
 def test_mixed_lengths_and_unequal_mates(golden, gidx, oidx):

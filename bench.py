@@ -43,7 +43,7 @@ sys.path.insert(0, str(ROOT))
 READ_LEN = 150
 HUMAN_MBP = [250, 243, 198, 190, 181, 171, 159, 145, 138, 134, 135, 133, 114, 107, 102, 90, 83, 80, 59, 64, 47, 51, 156, 57]
 REPEATS = dict(repeat_fraction=0.5, repeat_len=(1000, 10000), repeat_copies=(10, 10000), repeat_div=(0.01, 0.15))
-DEFAULT_SCALE = {"cfg3": 0.1, "cfg4": 0.1, "cfg2": 1.0}
+DEFAULT_SCALE = {"cfg3": 1.0, "cfg4": 1.0, "cfg2": 1.0}     # BMBS_BENCH_SCALE=0.1 for quick runs
 
 
 def log(*a):

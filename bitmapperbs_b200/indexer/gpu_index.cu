@@ -288,7 +288,7 @@ int main(int argc, char** argv) {
   // ---- suffix array
   u64* sa = dmalloc<u64>(n);
   {
-    int P = 0; while (P < 3 && (double)n / (double)(1ull << (2 * P)) * 1.6 > 9.0e8) ++P;       // classes of at most ~0.9 G suffixes
+    int P = 0; { double per = (double)n; while (P < 3 && per > 4.0e8) { per /= 3; ++P; } }       // three symbols: classes of ~n / 3^P, at most ~0.4 G suffixes
     u64* d_count = dmalloc<u64>(64); CK(cudaMemset(d_count, 0, 64 * 8));
     class_histogram<<<G, B>>>(tw, n, P, d_count);
     u64 count[64]; CK(cudaMemcpy(count, d_count, 64 * 8, cudaMemcpyDeviceToHost));

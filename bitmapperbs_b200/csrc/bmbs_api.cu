@@ -253,9 +253,12 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
   // CUDA context creation overlaps the file reads and the host re-layout
   int dev0 = 0;
   if (!devices || n_dev <= 0) { devices = &dev0; n_dev = 1; }
-  std::thread warm([=] { for (int d = 0; d < n_dev; ++d) { cudaSetDevice(devices[d]); cudaFree(0); } });
+  // CUDA contexts are created while the files are mapped, one thread per device
+  std::vector<std::thread> warm;
+  for (int d = 0; d < n_dev; ++d) warm.emplace_back([=] { cudaSetDevice(devices[d]); cudaFree(0); });
+  auto warm_join = [&] { for (auto& t : warm) t.join(); };
   int rc = load_files(index_prefix, h);
-  if (rc) { warm.join(); return rc; }
+  if (rc) { warm_join(); return rc; }
   lap("map index files");
   const u64 n = 2 * h.N;                       // text length = BWT symbols
   const u64 nblk = (n >> 6) + 2, nfb = (h.sa_length >> 6) + 2, npw = (n + 31) / 32 + 64;
@@ -265,10 +268,17 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
   idx->N = h.N;
   idx->serial = g_next_serial++;
   { std::lock_guard<std::mutex> l(g_live_mu); g_live_serials.insert(idx->serial); }
-  warm.join();
+  warm_join();
   lap("(wait for the CUDA context)");
-  for (int d = 0; d < n_dev; ++d) {
-    DeviceCopy c; c.dev = devices[d];
+  // every device uploads the raw arrays over its own link and builds its layouts itself: one host thread per device
+  // (the loads of an 8-GPU run overlap instead of queueing behind each other)
+  idx->copies.resize((size_t)n_dev);
+  std::vector<std::string> errors((size_t)n_dev);
+  auto load_on = [&](int d) {
+    std::string& err_out = errors[(size_t)d];
+    DeviceCopy& c = idx->copies[(size_t)d]; c.dev = devices[d];
+    const bool lap_here = d == 0;
+    auto lap = [&](const char* what) { if (verbose && lap_here) { const double t = tnow(); fprintf(stderr, "[bmbs load] %-28s %.3f s\n", what, t - t_prev); t_prev = t; } };
     cudaError_t e = cudaSetDevice(c.dev);
     cudaDeviceProp prop; if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, c.dev);
     const int grid = e == cudaSuccess ? prop.multiProcessorCount * 16 : 1;
@@ -300,9 +310,8 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
     if (e == cudaSuccess) e = cudaMemcpy(c.ssa, h.ssa.p, h.ssa.bytes(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     cudaFree(r_bwt); cudaFree(r_high); cudaFree(r_flag); cudaFree(r_hi); cudaFree(r_lo); cudaFree(r_pac);
-    idx->copies.push_back(c);
-    if (e != cudaSuccess) { std::string m = std::string("index upload: ") + cudaGetErrorString(e); bmbs_index_free(idx); return fail(BMBS_ERR_CUDA, m); }
-    DevIndex& v = idx->copies.back().view;
+    if (e != cudaSuccess) { err_out = std::string("index upload: ") + cudaGetErrorString(e); return; }
+    DevIndex& v = c.view;
     v.occ = (const ulonglong2*)c.occ; v.flag = (const ulonglong2*)c.flag; v.hash = (const u64*)c.hash;
     v.ssa = (const u32*)c.ssa; v.planes = (const uint2*)c.planes;
     v.C[0] = h.nacgt[0]; v.C[1] = h.nacgt[1]; v.C[2] = h.nacgt[2];
@@ -318,7 +327,7 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
     size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
     const bool want = mode ? strcmp(mode, "sampled") != 0 : need + (total_b >> 2) < free_b;
     if (want) {
-      DeviceCopy& cc = idx->copies.back();
+      DeviceCopy& cc = c;
       e = cudaMalloc(&cc.dsa_lo, (size_t)h.sa_length * 4 + 256);
       if (e == cudaSuccess && wide) e = cudaMalloc(&cc.dsa_hi, (size_t)h.sa_length + 256);
       if (e == cudaSuccess) {
@@ -326,7 +335,7 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
         densify_sa<<<prop.multiProcessorCount * 8, 256>>>(v, (u32*)cc.dsa_lo, (unsigned char*)cc.dsa_hi);
         e = cudaDeviceSynchronize();
       }
-      if (e != cudaSuccess) { std::string m = std::string("dense suffix array: ") + cudaGetErrorString(e); bmbs_index_free(idx); return fail(BMBS_ERR_CUDA, m); }
+      if (e != cudaSuccess) { err_out = std::string("dense suffix array: ") + cudaGetErrorString(e); return; }
       v.dsa_lo = (const u32*)cc.dsa_lo; v.dsa_hi = (const unsigned char*)cc.dsa_hi;
       cudaFree(cc.flag); cudaFree(cc.ssa); cc.flag = nullptr; cc.ssa = nullptr; v.flag = nullptr; v.ssa = nullptr;
       cc.bytes += need; cc.bytes -= nfb * 16 + h.ssa.bytes();
@@ -343,7 +352,7 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
       auto bytes_of = [&](int k) { size_t x = nh ? nh - 1 : 0; for (int i = 16; i < k; ++i) x *= 3; return x * 8; };
       if (!getenv("BMBS_KMER")) while (K > 16 && bytes_of(K) > total_b / 4) --K;
       if (K > 16 && nh > 1) {
-        DeviceCopy& cc = idx->copies.back();
+        DeviceCopy& cc = c;
         const int D = K - 16; const size_t kb = bytes_of(K);
         e = cudaMalloc(&cc.ktab, kb + 256);
         if (e == cudaSuccess) {
@@ -355,13 +364,21 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
           else build_ktab<4><<<grid, 128>>>(v, (u64*)cc.ktab, n_keys);
           e = cudaDeviceSynchronize();
         }
-        if (e != cudaSuccess) { std::string m = std::string("deep seed table: ") + cudaGetErrorString(e); bmbs_index_free(idx); return fail(BMBS_ERR_CUDA, m); }
+        if (e != cudaSuccess) { err_out = std::string("deep seed table: ") + cudaGetErrorString(e); return; }
         v.ktab = (const u64*)cc.ktab; v.kdepth = (u32)D; v.kpow = D == 1 ? 3 : D == 2 ? 9 : D == 3 ? 27 : 81;
         cc.bytes += kb;
       }
     }
     lap("deep seed table");
+  };
+  {
+    std::vector<std::thread> th;
+    for (int d = 1; d < n_dev; ++d) th.emplace_back(load_on, d);
+    load_on(0);
+    for (auto& t : th) t.join();
   }
+  for (int d = 0; d < n_dev; ++d)
+    if (!errors[(size_t)d].empty()) { const std::string m = "device " + std::to_string(devices[d]) + ": " + errors[(size_t)d]; bmbs_index_free(idx); return fail(BMBS_ERR_CUDA, m); }
   *out = idx;
   return BMBS_OK;
 }

@@ -585,7 +585,8 @@ __global__ void __launch_bounds__(128) seed_rest(DevIndex ix, BatchView b, u32 p
 //   COMPARE  a single row is left: locate it and compare the rest of the read with the genome directly
 //   DONE     a seed has its answer: the policy of the read's phase (which seeds count, where the next one starts), task records
 // The two that happen between seeds (DONE, then REFILL or START) are run back to back as one TRANSITION, and in every
-// iteration the WARP VOTES for what most of its lanes are waiting for -- TRANSITION, LF or COMPARE -- and executes only that.  A
+// iteration the WARP VOTES for what most of its lanes are waiting for -- TRANSITION, LF or COMPARE -- and executes only that
+// (letting the LF lanes pile up before they run, with hysteresis thresholds, measured slower: 2.1-2.7 ms against 1.86 ms).  A
 // loop nest per read (the phase kernels below) or a loop that runs every kind each iteration keeps 4-6 of 32 lanes busy on
 // a repeat-rich genome: the rare long paths are executed for one or two lanes while the others wait.  Decisions and their
 // order per read are those of seed_first / seed_second / seed_rest.
@@ -1427,56 +1428,60 @@ __device__ __forceinline__ void bpm_columns32(const u64* __restrict__ sm, int st
   u32 VP = 0, VN = 0;
   int err = 0;
   const int limit = 3 * k;   // err - 2k > k can never recover (Levenshtein_Cal.h:455); checked every eight columns
-  bool dead = false;
   u32 dbits = 0;
-  u32 next_word = L > 0 ? __ldg(rw) : 0u;     // the read's code words are fetched one group of eight columns ahead
-  for (int ch = 0; ch * 32 < L && !dead; ++ch) {
-    const char* cbytes = reinterpret_cast<const char*>(sm + ch * stride);
+  end_out = -1; err_out = 0xFFFFFFFFu;
+  // the read's code words are fetched one group of eight columns ahead (a read's words are followed by the next read's or by
+  // slack: the look-ahead past the last group reads something that is never used)
+  const u32* rwp = rw;
+  u32 next_word = __ldg(rwp++);
+  int rem = L;                                              // columns left
+  const char* cbytes = reinterpret_cast<const char*>(sm);
+  const u32 chunk_bytes = (u32)stride * 8u;
+  for (; rem > 0; cbytes += chunk_bytes) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      const int i0 = ch * 32 + g * 8;
-      if (i0 < L && !dead) {
-        const u32 word = next_word;
-        if (i0 + 8 < L) next_word = __ldg(rw + (i0 >> 3) + 1);
-        const u32 ev = word & 0x0F0F0F0Fu, od = (word >> 4) & 0x0F0F0F0Fu;
-        if (i0 + 8 <= L) {
-          bpm_step32(eq_raw32<0>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
-          bpm_step32(eq_raw32<1>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
-          bpm_step32(eq_raw32<2>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
-          bpm_step32(eq_raw32<3>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
-          bpm_step32(eq_raw32<4>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
-          bpm_step32(eq_raw32<5>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
-          bpm_step32(eq_raw32<6>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
-          bpm_step32(eq_raw32<7>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
-          err += 8 - __popc(dbits >> 24);
-        } else {
-          const int n = L - i0;
-          for (int j = 0; j < n; ++j) {
-            const u32 code = (word >> (4 * j)) & 0xFu;
-            const u64 e0 = *reinterpret_cast<const u64*>(cbytes + code * pstride8);
-            bpm_step32((u32)(e0 >> (g * 8 + j)), mask, VP, VN, dbits);
-          }
-          err += n - __popc(dbits >> (32 - n));
+      if (rem <= 0) break;
+      const u32 word = next_word;
+      next_word = __ldg(rwp++);
+      const u32 ev = word & 0x0F0F0F0Fu, od = (word >> 4) & 0x0F0F0F0Fu;
+      if (rem >= 8) {
+        bpm_step32(eq_raw32<0>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
+        bpm_step32(eq_raw32<1>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
+        bpm_step32(eq_raw32<2>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
+        bpm_step32(eq_raw32<3>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
+        bpm_step32(eq_raw32<4>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
+        bpm_step32(eq_raw32<5>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
+        bpm_step32(eq_raw32<6>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
+        bpm_step32(eq_raw32<7>(cbytes, pstride8, ev, od, g * 8), mask, VP, VN, dbits);
+        err += 8 - __popc(dbits >> 24);
+      } else {
+        for (int j = 0; j < rem; ++j) {
+          const u32 code = (word >> (4 * j)) & 0xFu;
+          const u64 e0 = *reinterpret_cast<const u64*>(cbytes + code * pstride8);
+          bpm_step32((u32)(e0 >> (g * 8 + j)), mask, VP, VN, dbits);
         }
-        if (err > limit) dead = true;
+        err += rem - __popc(dbits >> (32 - rem));
       }
+      rem -= 8;
+      if (err > limit) return;
     }
   }
-  end_out = -1; err_out = 0xFFFFFFFFu;
-  if (dead) return;
-  // the last column, walked down the band (Levenshtein_Cal.h:524-563).  err can only fall by one per negative vertical delta:
-  // when even that cannot reach k, no cell of the column does and the walk is skipped
-  if (err - __popc(VN & (mask >> 1)) > k) return;
+  // the last column, walked down the band (Levenshtein_Cal.h:524-563): position p = 0 .. 2k is the cell whose alignment ends
+  // at window position L - 1 + p, value(p) = err + sum over the vertical deltas below it; the answer is the LAST position
+  // that holds the column's minimum (if that is within k), except that the un-gapped end p = k wins a tie.  The value only
+  // changes where VP or VN has a bit, so the walk goes from set bit to set bit instead of cell by cell.
   const int last = L - 1;
   u32 best = 0xFFFFFFFFu; int site = -1;
-  if (err <= k) { best = (u32)err; site = last; }
-  int ungapped = err;
-  for (int i = 0; i < 2 * k; ++i) {
-    err += (int)((VP >> i) & 1) - (int)((VN >> i) & 1);
-    if (err <= k && (u32)err <= best) { best = (u32)err; site = last + i + 1; }
-    if (i + 1 == k) ungapped = err;
+  int ungapped = err, cur = err, lo_p = 0;
+  u32 M = (VP | VN) & (mask >> 1);                          // bits 0 .. 2k-1
+  for (;;) {
+    const int p_end = M ? __ffs(M) - 1 : 2 * k;             // the plateau [lo_p, p_end] holds `cur`
+    if (cur <= k && (u32)cur <= best) { best = (u32)cur; site = last + p_end; }
+    if (lo_p <= k && k <= p_end) ungapped = cur;
+    if (!M) break;
+    cur += ((VP >> p_end) & 1u) ? 1 : -1;
+    M &= M - 1; lo_p = p_end + 1;
   }
-  if (k == 0) ungapped = err;
   if (ungapped >= 0 && ungapped <= k && (u32)ungapped == best) site = last + k;
   end_out = site; err_out = best;
 }

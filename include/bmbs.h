@@ -24,9 +24,11 @@
  * Conventions: plain pointers and sizes, caller-owned in/out buffers (pinned
  * host memory makes the copies faster but is not required), library-owned device
  * memory and streams.  Every function returns 0 on success and a negative code
- * on failure with a message in bmbs_last_error(); nothing calls exit().  One
- * host thread per device may be inside the library at a time; the index handle
- * is immutable after load.
+ * on failure with a message in bmbs_last_error(); nothing calls exit().  The
+ * index handle is immutable after load and may be shared by any number of host
+ * threads; a bmbs_batch / bmbs_refiner (own stream, own device buffers) belongs to
+ * one thread at a time, and the one-call forms keep one such context per calling
+ * thread -- the reference's -t N workers can all be inside the library at once.
  */
 #ifndef BMBS_H
 #define BMBS_H

@@ -222,6 +222,34 @@ class ClockSampler:
                 "window": "timed region" if len(inside) >= 3 else "warm-up + timed region"}
 
 
+def bind_to_gpu_node(dev: int):
+    """run on the cores of the NUMA node the GPU hangs off (page-locked buffers are then allocated there: the copies of an
+    8-GPU run stay off the inter-socket link); returns the node or None when the box has one node / hides the topology"""
+    try:
+        import pynvml as N
+        N.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[dev]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else dev
+        bus = N.nvmlDeviceGetPciInfo(N.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------------ command-line runs
 def run_cli(exe: Path, d: Path, wl: Workload, seq_args, threads: int, out: str, extra=()):
     """`exe --search g.fa <reads> -t threads -o out`; returns (load_s, map_s, wall_s) from the program's own `Total:` line"""
@@ -306,6 +334,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = local
     torch.cuda.set_device(dev)
+    full_affinity = os.sched_getaffinity(0)
+    numa = bind_to_gpu_node(dev)         # pinned staging is first-touched by this process: keep it on the GPU's NUMA node
     d = ensure_dataset(cache, wl, rank == 0)
     if dist:
         dist.barrier()
@@ -344,23 +374,51 @@ def main():
                 raise
             batch.close(); cand_cap *= 2
     states = np.bincount(res["state"], minlength=5)
+    # single end: the device also finishes the reads (reduction in std::sort's order, ungapped CIGAR check, coordinates) and
+    # 32-byte records come back instead of the window lists; pairs still return their lists (pair pick on the host)
+    fin_mode = not wl.pe
+    fin_cap = 32 * n_reads + 64; fb_cap = max(1 << 20, n_reads)
+
+    def final_buffers():
+        hf = torch.empty(n_reads * capi.Final.itemsize, dtype=torch.uint8, pin_memory=True)
+        hm = torch.empty(fin_cap * 2, dtype=torch.uint8, pin_memory=True)
+        hb = torch.empty(fb_cap * capi.Cand.itemsize, dtype=torch.uint8, pin_memory=True)
+        keep.extend([hf, hm, hb])
+        return hf.numpy().view(capi.Final), hm.numpy().view(np.uint16), hb.numpy().view(capi.Cand)
     # more in-flight batches for the end-to-end loop (each with its own stream and pinned result buffers): the H2D copy of
     # one batch overlaps the kernels of the previous one and the D2H copy of the one before
-    outs = [(batch, res, cand)]
     keep = [h_res, h_cand]
+    outs = [(batch, res, cand) + (final_buffers() if fin_mode else ())]
     for _ in range(a.inflight - 1):
-        hr = torch.empty(n_reads * capi.ReadResult.itemsize, dtype=torch.uint8, pin_memory=True)
-        hc = torch.empty(cand_cap * capi.Cand.itemsize, dtype=torch.uint8, pin_memory=True)
-        keep += [hr, hc]
-        outs.append((B.Batch(index, dev, n_reads, bases + 64, cand_cap), hr.numpy().view(capi.ReadResult), hc.numpy().view(capi.Cand)))
+        nb = B.Batch(index, dev, n_reads, bases + 64, cand_cap)
+        if fin_mode:
+            outs.append((nb, None, None) + final_buffers())
+        else:
+            hr = torch.empty(n_reads * capi.ReadResult.itemsize, dtype=torch.uint8, pin_memory=True)
+            hc = torch.empty(cand_cap * capi.Cand.itemsize, dtype=torch.uint8, pin_memory=True)
+            keep += [hr, hc]
+            outs.append((nb, hr.numpy().view(capi.ReadResult), hc.numpy().view(capi.Cand)))
     NB = len(outs)
+
+    def step_run(bb):
+        bb.run(prm)
+        if fin_mode:
+            bb.finish()
+
+    def step_download(o):
+        """-> bytes copied back"""
+        if fin_mode:
+            _, mm, fb = o[0].download_final(o[3], o[4], o[5])
+            return n_reads * capi.Final.itemsize + 2 * len(mm) + capi.Cand.itemsize * len(fb)
+        _, _, u = o[0].download(o[1], o[2])
+        return n_reads * capi.ReadResult.itemsize + u * capi.Cand.itemsize
     clocks = ClockSampler(dev); clocks.start()
     for _ in range(max(0, a.warmup - 1)):
-        batch.run(prm)
+        step_run(batch)
     batch.sync()
     for i in range(max(a.warmup, NB)):
-        bb, rr, cc = outs[i % NB]
-        bb.upload(flat, offs, pe=wl.pe); bb.run(prm); bb.download(rr, cc)
+        o = outs[i % NB]
+        o[0].upload(flat, offs, pe=wl.pe); step_run(o[0]); step_download(o)
 
     def barrier():
         torch.cuda.synchronize()
@@ -375,8 +433,11 @@ def main():
     dev_ms = 0.0
     w0 = time.perf_counter()
     for _ in range(a.steps):
-        batch.run(prm)
+        step_run(batch)
         t = batch.timings()           # waits on the step's last event; CUDA-event times on the launching stream
+        if fin_mode:
+            t["finish"] = batch.finish_counters()["device_us"] / 1000.0
+            t["total"] += t["finish"]
         dev_ms += t["total"]
         for k, v in t.items():
             stage[k] = stage.get(k, 0.0) + v
@@ -385,25 +446,30 @@ def main():
     barrier()
     counters = batch.counters()
     launches = batch.launches() * a.steps
+    fin_counters = batch.finish_counters() if fin_mode else None
     # ---- timed: end to end through the C ABI, host buffers in / out
     # (every step: H2D of the step's reads from pinned host memory, kernels, D2H of its records; NB batches in
     # flight on their own streams, as the host mapper drives them)
     barrier()
     e0 = time.perf_counter()
+    d2h = 0
     for i in range(a.steps):
-        bb, rr, cc = outs[i % NB]
-        bb.upload(flat, offs, pe=wl.pe); bb.run(prm)
+        o = outs[i % NB]
+        o[0].upload(flat, offs, pe=wl.pe); step_run(o[0])
         if i >= NB - 1:
-            pb, pr, pc = outs[(i - (NB - 1)) % NB]
-            _, _, used = pb.download(pr, pc)
+            d2h = step_download(outs[(i - (NB - 1)) % NB])
     for i in range(max(0, a.steps - (NB - 1)), a.steps):
-        pb, pr, pc = outs[i % NB]
-        _, _, used = pb.download(pr, pc)
+        d2h = step_download(outs[i % NB])
     e2e_ms = (time.perf_counter() - e0) * 1000
     barrier()
     clk = clocks.stop(t_begin, time.time())
-    assert all(np.array_equal(outs[0][1]["state"], o[1]["state"]) for o in outs[1:])
-    h2d = int(bases + 8 * (n_reads + 1)); d2h = int(n_reads * capi.ReadResult.itemsize + used * capi.Cand.itemsize)
+    if fin_mode:
+        assert all(np.array_equal(outs[0][3]["status"], o[3]["status"]) and np.array_equal(outs[0][3]["chrom_pos"], o[3]["chrom_pos"]) for o in outs[1:])
+        fin_status = np.bincount(outs[0][3]["status"], minlength=5)
+    else:
+        assert all(np.array_equal(outs[0][1]["state"], o[1]["state"]) for o in outs[1:])
+    h2d = int(bases + 8 * (n_reads + 1)); d2h = int(d2h)
+    os.sched_setaffinity(0, full_affinity)        # the command-line runs below use every core of the box
 
     if dist:
         t = torch.tensor([dev_ms, e2e_ms, wall_ms], dtype=torch.float64, device=f"cuda:{dev}")
@@ -467,13 +533,18 @@ def main():
                    "read_states": {"none": int(states[0]), "exact_unique": int(states[1]), "multi_exact": int(states[2]), "one_mismatch": int(states[3]), "verify": int(states[4])},
                    "index_hbm_bytes": index.device_bytes, "index_load_s": load_s, "genome_bases": index.genome_length},
         "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps, "batches_in_flight": NB,
-                "scope": "C-ABI call: H2D of the reads, kernels, D2H of records + verified candidate lists (host reduction / CIGAR / SAM are in whole_program)"},
+                "numa_node": numa,
+                "scope": ("C-ABI calls bmbs_batch_upload / _run / _finish / _download_final: H2D of the reads, kernels incl. the device finishing (reduction, ungapped CIGAR, "
+                          "coordinates), D2H of one 32-byte record per read + mismatch positions (MAPQ table lookup and SAM text are in whole_program)") if fin_mode else
+                         "C-ABI call: H2D of the reads, kernels, D2H of records + verified candidate lists (pair pick / CIGAR / SAM are in whole_program)"},
         "gpu_launches": launches,
         "clocks": clk,
         "stage_ms_per_step": per_step,
         "wall_ms_per_step": wall_ms / a.steps,
         "verify_gcups": gcups,
         "work_per_step": counters,
+        "finishing": ({"status": {"unmapped": int(fin_status[0]), "unique_ungapped": int(fin_status[1]), "ambiguous": int(fin_status[2]), "needs_dp": int(fin_status[3]),
+                                  "handed_back_to_host": int(fin_status[4])}, **fin_counters} if fin_mode else None),
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                      "peak_source": peak_src, "kernel_ms": dms,
                      "algorithmic_bytes_per_launch": survey[dom], "units": "SURVEY 8d: 10 B per table query, 40 B per occ lookup, 80 B per locate LF step + 44 B per located row, window bytes",

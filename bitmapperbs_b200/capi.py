@@ -13,6 +13,12 @@ ReadResult = np.dtype([("site", "<u8"), ("first_cand", "<u4"), ("n_cand", "<u4")
                        ("state", "u1"), ("is_multiple_map", "u1"), ("reserved", "<u4")])
 Cand = np.dtype([("site", "<u8"), ("vote", "<u4"), ("end_site", "<i2"), ("err", "<u2")])
 assert ReadResult.itemsize == 24 and Cand.itemsize == 16
+# bmbs_final: one finished single-end read (bmbs_batch_finish)
+FIN_UNMAPPED, FIN_UNIQUE, FIN_AMBIGUOUS, FIN_DP, FIN_HOST = 0, 1, 2, 3, 4
+FINF_REVERSE, FINF_AMBIGUOUS = 1, 2
+Final = np.dtype([("site", "<u8"), ("chrom_pos", "<u8"), ("aux_first", "<u4"), ("end_site", "<i2"), ("nm", "u1"), ("sbd", "u1"), ("status", "u1"),
+                  ("flags", "u1"), ("mapq_fixed", "u1"), ("k", "u1"), ("n_aux", "<u4")])
+assert Final.itemsize == 32
 
 
 class Params(C.Structure):
@@ -44,7 +50,7 @@ EXPORTS = ["bmbs_index_load", "bmbs_index_free", "bmbs_index_genome_length", "bm
            "bmbs_params_default", "bmbs_map_batch_se", "bmbs_map_batch_pe", "bmbs_verify", "bmbs_batch_create", "bmbs_batch_free",
            "bmbs_batch_upload", "bmbs_batch_run", "bmbs_batch_download", "bmbs_batch_sync", "bmbs_batch_timings",
            "bmbs_batch_counters", "bmbs_batch_launches", "bmbs_batch_verify", "bmbs_batch_download_verify", "bmbs_ubench_int_pipe", "bmbs_pinned_alloc", "bmbs_pinned_free", "bmbs_ubench_random_sectors",
-           "bmbs_refiner_create", "bmbs_refiner_free", "bmbs_refine"]
+           "bmbs_refiner_create", "bmbs_refiner_free", "bmbs_refine", "bmbs_batch_finish", "bmbs_batch_download_final", "bmbs_batch_finish_counters"]
 
 
 def load_library():
@@ -79,6 +85,9 @@ def load_library():
     L.bmbs_batch_download_verify.argtypes = [vp, vp, vp, C.c_size_t]
     L.bmbs_ubench_int_pipe.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.bmbs_ubench_random_sectors.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_double)]
+    L.bmbs_batch_finish.argtypes = [vp]
+    L.bmbs_batch_download_final.argtypes = [vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t), vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.bmbs_batch_finish_counters.argtypes = [vp, u64p]
     L.bmbs_refiner_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
     L.bmbs_refiner_free.argtypes = [vp]
     L.bmbs_refine.argtypes = [vp, vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(Scoring), vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -212,6 +221,29 @@ class Batch:
         used = C.c_size_t(0)
         _check(self._L.bmbs_batch_download(self._h, res.ctypes.data, cand.ctypes.data, len(cand), C.byref(used)))
         return res, cand, used.value
+
+    def finish(self):
+        """single end: reduction + ungapped CIGAR + coordinates on the device, behind run() on the batch's stream"""
+        _check(self._L.bmbs_batch_finish(self._h))
+
+    def download_final(self, fin=None, mism=None, cand=None):
+        """-> (Final[n_reads], mismatch positions u16[], handed-back windows Cand[])"""
+        fin = np.zeros(self.n_reads, dtype=Final) if fin is None else fin
+        mism = np.zeros(32 * self.n_reads + 64, dtype=np.uint16) if mism is None else mism
+        cand = np.zeros(1 << 16, dtype=Cand) if cand is None else cand
+        while True:
+            nm, nc = C.c_size_t(0), C.c_size_t(0)
+            rc = self._L.bmbs_batch_download_final(self._h, fin.ctypes.data, mism.ctypes.data, len(mism), C.byref(nm), cand.ctypes.data, len(cand), C.byref(nc))
+            if rc == -4 and (nm.value > len(mism) or nc.value > len(cand)):
+                mism = np.zeros(max(len(mism), nm.value + 64), dtype=np.uint16); cand = np.zeros(max(len(cand), nc.value + 64), dtype=Cand)
+                continue
+            _check(rc)
+            return fin, mism[: nm.value], cand[: nc.value]
+
+    def finish_counters(self):
+        c = (C.c_uint64 * 8)()
+        _check(self._L.bmbs_batch_finish_counters(self._h, c))
+        return dict(zip(["mismatch_positions", "handed_back_windows", "reads_sort_replayed", "reads_handed_back", "reads_dp", "order_decides_window", "order_decides_sbd", "device_us"], [int(x) for x in c]))
 
     def verify(self, read_idx, sites, e_rate=0.08):
         """kernel 3 alone over the uploaded reads (async); results via download_verify"""

@@ -63,6 +63,7 @@ struct HostIndex {
   Span<u64> bwt, high_occ, sa_flag;
   Span<u32> hash_hi, ssa;
   Span<uint8_t> hash_lo, pac;
+  std::vector<u64> chrom_start;      // chrom_start[i] = first coordinate of chromosome i, one more entry = N
 };
 
 // u64 count followed by `count` elements at `off`; advances off
@@ -78,8 +79,10 @@ int load_files(const std::string& prefix, HostIndex& h) {
   FILE* f = fopen(prefix.c_str(), "rb");
   if (!f) return fail(BMBS_ERR_IO, "cannot open " + prefix);
   u64 nc = 0; bool ok = fread(&nc, 8, 1, f) == 1;
-  for (u64 i = 0; ok && i < nc; ++i) { u64 l = 0, cl = 0; ok = fread(&l, 8, 1, f) == 1 && fseek(f, (long)l, SEEK_CUR) == 0 && fread(&cl, 8, 1, f) == 1; }
+  u64 at = 0;
+  for (u64 i = 0; ok && i < nc; ++i) { u64 l = 0, cl = 0; ok = fread(&l, 8, 1, f) == 1 && fseek(f, (long)l, SEEK_CUR) == 0 && fread(&cl, 8, 1, f) == 1; h.chrom_start.push_back(at); at += cl; }
   ok = ok && fread(&h.N, 8, 1, f) == 1; fclose(f);
+  h.chrom_start.push_back(at);
   if (!ok) return fail(BMBS_ERR_IO, "short read in " + prefix);
   if (!h.f_pac.open(prefix + ".bs.pac")) return fail(BMBS_ERR_IO, "cannot open " + prefix + ".bs.pac");
   size_t off = 0;
@@ -118,7 +121,7 @@ int load_files(const std::string& prefix, HostIndex& h) {
 
 struct DeviceCopy {
   int dev = 0; DevIndex view{}; size_t bytes = 0;
-  void *occ = nullptr, *flag = nullptr, *hash = nullptr, *ssa = nullptr, *planes = nullptr, *dsa_lo = nullptr, *dsa_hi = nullptr, *ktab = nullptr;
+  void *occ = nullptr, *flag = nullptr, *hash = nullptr, *ssa = nullptr, *planes = nullptr, *dsa_lo = nullptr, *dsa_hi = nullptr, *ktab = nullptr, *chroms = nullptr;
 };
 
 // ---- deep seed table (kmer_entry, bmbs_device.cuh): one thread per 16-mer walks the <= 3^D extensions depth first, sharing
@@ -239,7 +242,7 @@ extern "C" uint64_t bmbs_index_device_bytes(const bmbs_index* idx) { return idx 
 extern "C" void bmbs_index_free(bmbs_index* idx) {
   if (!idx) return;
   { std::lock_guard<std::mutex> l(g_live_mu); g_live_serials.erase(idx->serial); }
-  for (auto& c : idx->copies) { cudaSetDevice(c.dev); cudaFree(c.occ); cudaFree(c.flag); cudaFree(c.hash); cudaFree(c.ssa); cudaFree(c.planes); cudaFree(c.dsa_lo); cudaFree(c.dsa_hi); cudaFree(c.ktab); }
+  for (auto& c : idx->copies) { cudaSetDevice(c.dev); cudaFree(c.occ); cudaFree(c.flag); cudaFree(c.hash); cudaFree(c.ssa); cudaFree(c.planes); cudaFree(c.dsa_lo); cudaFree(c.dsa_hi); cudaFree(c.ktab); cudaFree(c.chroms); }
   delete idx;
 }
 
@@ -308,6 +311,8 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
     if (e == cudaSuccess) { relayout_planes<<<grid, 256>>>((const unsigned char*)r_pac, h.N, (n + 31) / 32, (uint2*)c.planes); e = cudaGetLastError(); }
     if (e == cudaSuccess) { c.bytes += h.ssa.bytes(); e = cudaMalloc(&c.ssa, h.ssa.bytes() + 16); }
     if (e == cudaSuccess) e = cudaMemcpy(c.ssa, h.ssa.p, h.ssa.bytes(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&c.chroms, h.chrom_start.size() * 8 + 16);
+    if (e == cudaSuccess) e = cudaMemcpy(c.chroms, h.chrom_start.data(), h.chrom_start.size() * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     cudaFree(r_bwt); cudaFree(r_high); cudaFree(r_flag); cudaFree(r_hi); cudaFree(r_lo); cudaFree(r_pac);
     if (e != cudaSuccess) { err_out = std::string("index upload: ") + cudaGetErrorString(e); return; }
@@ -316,6 +321,7 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
     v.ssa = (const u32*)c.ssa; v.planes = (const uint2*)c.planes;
     v.C[0] = h.nacgt[0]; v.C[1] = h.nacgt[1]; v.C[2] = h.nacgt[2];
     v.shapline = h.shapline; v.n_rows = h.sa_length; v.N = h.N;
+    v.chrom_start = (const u64*)c.chroms; v.n_chrom = (u32)(h.chrom_start.size() - 1);
     v.dsa_lo = nullptr; v.dsa_hi = nullptr; v.ktab = nullptr; v.kdepth = 0; v.kpow = 1;
     lap("upload + device re-layout");
     // ---- dense suffix array (BMBS_SA=sampled keeps the on-disk 1/8 sampling; default: dense when it fits with room to spare)
@@ -392,8 +398,11 @@ struct bmbs_batch {
   BatchView v{};
   char* d_ascii = nullptr; u64* d_offsets = nullptr;
   u64* d_tile = nullptr;
-  u64* h_small = nullptr;        // pinned: totals[2], status, counters[8]
-  cudaEvent_t ev[9] = {nullptr};
+  u64* h_small = nullptr;        // pinned: totals[2], status, counters[8]; [16..23] finishing counters
+  cudaEvent_t ev[11] = {nullptr};
+  // finishing (bmbs_batch_finish): records, mismatch positions, handed-back window lists, reads to replay the sort for
+  bmbs_final* d_fin = nullptr; unsigned short* d_mism = nullptr; bmbs_cand* d_fb = nullptr; u32* d_sort_list = nullptr; FinCounters* d_fc = nullptr;
+  size_t mism_cap = 0, fb_cap = 0; bool finished = false;
   int n_reads = 0, pe = 0, max_len = 0, launches = 0, sm_count = 148, seed_blocks_per_sm = 8; u32 seed_plane_cap = 0;
   bool ran = false;
 };
@@ -457,6 +466,8 @@ extern "C" int bmbs_batch_create(bmbs_index* idx, int dev, size_t max_reads, siz
   A(dalloc(b, &v.scratch, (size_t)v.scratch_cap)); A(dalloc(b, &v.scratch_used, 4));
   A(dalloc(b, &v.counters, 16)); A(dalloc(b, &v.totals, 4)); A(dalloc(b, &v.status, 4));
   A(dalloc(b, &b->d_tile, R / SCAN_TILE + 8));
+  b->mism_cap = 32 * R;      // a read holds at most 31 mismatch positions b->fb_cap = S;
+  A(dalloc(b, &b->d_fin, R)); A(dalloc(b, &b->d_mism, b->mism_cap)); A(dalloc(b, &b->d_fb, b->fb_cap)); A(dalloc(b, &b->d_sort_list, R)); A(dalloc(b, &b->d_fc, 1));
   A(slab_commit(b));
   A(cudaMallocHost((void**)&b->h_small, 32 * sizeof(u64)));
   for (auto& evt : b->ev) A(cudaEventCreate(&evt));
@@ -480,7 +491,7 @@ extern "C" int bmbs_batch_upload(bmbs_batch* b, const char* seqs, const uint64_t
   CU(cudaSetDevice(b->dev));
   CU(cudaMemcpyAsync(b->d_ascii, seqs, bases, cudaMemcpyHostToDevice, b->stream));
   CU(cudaMemcpyAsync(b->d_offsets, offsets, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, b->stream));
-  b->n_reads = n_reads; b->pe = pe; b->max_len = max_len; b->ran = false;
+  b->n_reads = n_reads; b->pe = pe; b->max_len = max_len; b->ran = false; b->finished = false;
   return BMBS_OK;
 }
 
@@ -583,7 +594,26 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
   CU(cudaMemcpyAsync(b->h_small + 2, v.status, 4, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(b->h_small + 4, v.counters, 8 * 8, cudaMemcpyDeviceToHost, s));
   CU(cudaGetLastError());
-  b->ran = true;
+  b->ran = true; b->finished = false;
+  return BMBS_OK;
+}
+
+extern "C" int bmbs_batch_finish(bmbs_batch* b) {
+  if (!b || !b->ran) return fail(BMBS_ERR_ARG, "bad argument or batch not run");
+  if (b->pe) return fail(BMBS_ERR_ARG, "bmbs_batch_finish: single-end batches only");
+  CU(cudaSetDevice(b->dev));
+  cudaStream_t s = b->stream;
+  const int n = b->n_reads;
+  CU(cudaMemsetAsync(b->d_fc, 0, sizeof(FinCounters), s));
+  CU(cudaEventRecord(b->ev[9], s));
+  if (n > 0) {
+    finish_se<<<(n + 127) / 128, 128, 0, s>>>(b->copy->view, b->v, b->d_fin, b->d_mism, (u32)b->mism_cap, b->d_fb, (u32)b->fb_cap, b->d_sort_list, b->d_fc); ++b->launches;
+    finish_sorted<<<b->sm_count * 4, 128, 0, s>>>(b->copy->view, b->v, b->d_fin, b->d_mism, (u32)b->mism_cap, b->d_fb, (u32)b->fb_cap, b->d_sort_list, b->d_fc); ++b->launches;
+  }
+  CU(cudaEventRecord(b->ev[10], s));
+  CU(cudaMemcpyAsync(b->h_small + 16, b->d_fc, sizeof(FinCounters), cudaMemcpyDeviceToHost, s));
+  CU(cudaGetLastError());
+  b->finished = true;
   return BMBS_OK;
 }
 
@@ -617,6 +647,35 @@ extern "C" int bmbs_batch_download(bmbs_batch* b, bmbs_read_result* res, bmbs_ca
   if (b->n_reads) CU(cudaMemcpyAsync(res, b->v.out_res, (size_t)b->n_reads * sizeof(bmbs_read_result), cudaMemcpyDeviceToHost, b->stream));
   if (work) { if (!cand) return fail(BMBS_ERR_ARG, "cand is null"); CU(cudaMemcpyAsync(cand, b->v.out_cand, work * sizeof(bmbs_cand), cudaMemcpyDeviceToHost, b->stream)); }
   CU(cudaStreamSynchronize(b->stream));
+  return BMBS_OK;
+}
+
+extern "C" int bmbs_batch_download_final(bmbs_batch* b, bmbs_final* fin, uint16_t* mism, size_t mism_cap, size_t* mism_used,
+                                         bmbs_cand* cand, size_t cand_cap, size_t* cand_used) {
+  if (!b || !b->ran || !b->finished || !fin) return fail(BMBS_ERR_ARG, "bad argument or batch not finished");
+  CU(cudaSetDevice(b->dev));
+  CU(cudaStreamSynchronize(b->stream));
+  int rc = check_status(b, cand_used);
+  if (rc) return rc;
+  const size_t nm = (size_t)b->h_small[16], nfb = (size_t)b->h_small[17];
+  if (mism_used) *mism_used = nm;
+  if (cand_used) *cand_used = nfb;
+  if (nm > b->mism_cap || nfb > b->fb_cap) return fail(BMBS_ERR_CAPACITY, "finishing buffers of the batch are too small");
+  if (nm > mism_cap || nfb > cand_cap) return fail(BMBS_ERR_CAPACITY, "caller's mism[] / cand[] too small: " + std::to_string(nm) + " / " + std::to_string(nfb) + " entries needed");
+  if (b->n_reads) CU(cudaMemcpyAsync(fin, b->d_fin, (size_t)b->n_reads * sizeof(bmbs_final), cudaMemcpyDeviceToHost, b->stream));
+  if (nm) { if (!mism) return fail(BMBS_ERR_ARG, "mism is null"); CU(cudaMemcpyAsync(mism, b->d_mism, nm * sizeof(uint16_t), cudaMemcpyDeviceToHost, b->stream)); }
+  if (nfb) { if (!cand) return fail(BMBS_ERR_ARG, "cand is null"); CU(cudaMemcpyAsync(cand, b->d_fb, nfb * sizeof(bmbs_cand), cudaMemcpyDeviceToHost, b->stream)); }
+  CU(cudaStreamSynchronize(b->stream));
+  return BMBS_OK;
+}
+
+extern "C" int bmbs_batch_finish_counters(bmbs_batch* b, uint64_t c[8]) {
+  if (!b || !b->finished || !c) return fail(BMBS_ERR_ARG, "bad argument or batch not finished");
+  CU(cudaSetDevice(b->dev));
+  CU(cudaStreamSynchronize(b->stream));
+  for (int i = 0; i < 8; ++i) c[i] = b->h_small[16 + i];
+  float ms = 0; CU(cudaEventElapsedTime(&ms, b->ev[9], b->ev[10]));
+  c[7] = (uint64_t)(ms * 1000.0f);
   return BMBS_OK;
 }
 

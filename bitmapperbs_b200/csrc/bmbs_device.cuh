@@ -38,6 +38,8 @@ struct DevIndex {
   u64 shapline;    // row whose BWT symbol is '$' (omitted from the planes)
   u64 n_rows;      // text length + 1
   u64 N;           // genome length; text length = 2N
+  const u64* chrom_start;  // first forward-strand coordinate of every chromosome, chrom_start[n_chrom] = N (finishing: place_hit)
+  u32 n_chrom;
 };
 
 // nibble codes of a read base: A0 C1 G2 T3 other 4; FM alphabet G0 T1 A2 with C->T, other 3

@@ -16,6 +16,7 @@
 //   finalize_reads   per-read result records
 #pragma once
 #include "bmbs_device.cuh"
+#include "bmbs_sort_replay.h"
 #include "../../include/bmbs.h"
 
 namespace bmbs {
@@ -1937,6 +1938,279 @@ __global__ void finalize_reads(BatchView b) {
   if (r == 0) b.totals[3] = b.totals[2] + b.totals[1];
   o.one_mismatch_pos = b.one_mm[r]; o.state = b.state[r]; o.is_multiple_map = b.flags[r] & 1; o.reserved = 0;
   b.out_res[r] = o;
+}
+
+// ------------------------------------------------------------------------------------------- finishing (single end)
+// What the reference's worker does after its verification calls, for every read of a single-end batch:
+//   * the vote-ordered reduction (Schema.cpp:7847-8056 / :8325-8745): the hit with the smallest err, "ambiguous" when another
+//     hit with that err ends elsewhere, second_best_diff = what the running minimum stood at before the best hit was met.
+//     The reference walks the windows in the order its unstable std::sort by vote leaves them.  finish_se (a warp per read,
+//     three reductions over the window list) computes the outcome from order-free quantities whenever the order among equal
+//     votes cannot change it, and from the true order when the list has at most 16 windows (libstdc++ then runs a plain,
+//     stable insertion sort).  The other reads go to finish_sorted, which replays the introsort step by step
+//     (bmbs_sort_replay.h) in shared memory; lists beyond its capacity are handed to the host (BMBS_FIN_HOST).
+//   * try_cigar_without_path (ksw.cpp:2515-2570): the best hit's diagonal re-read against the genome; exactly `err` mismatches
+//     on it = an ungapped alignment, CIGAR <L>M, and the mismatch positions go back so that the host can price them by quality
+//     (MismatchPenaltyByQuality; the quality strings never cross the link for such reads).  Otherwise the read is marked
+//     BMBS_FIN_DP: the banded affine DP (refine_dp) decides.
+//   * coordinates (Schema.cpp:12596-12650, :9188-9244): strand, chromosome, 1-based POS, and the drop of hits that run over
+//     the end of their chromosome.
+struct FinCounters { unsigned long long mism_used, fb_used, n_sorted, n_host, n_dp, n_unc_idx, n_unc_sbd, pad; };
+
+struct PlacedDev { u32 chrom; u64 pos; u32 reverse; bool off; };
+__device__ __forceinline__ PlacedDev place_hit(const DevIndex& ix, u64 site, long long start_site, u64 end_site) {
+  PlacedDev p;
+  u64 loc = site;
+  if (loc >= ix.N) { loc = ix.N * 2 - (loc + end_site) - 1; p.reverse = 1; }
+  else { loc = loc + (u64)start_site; p.reverse = 0; }
+  // the chromosome whose [start, end] holds loc (the reference scans the table; chromosomes are contiguous, so the last one
+  // that starts at or before loc is the only candidate); when nothing holds it: the last entry, where the reference's scan ends
+  u32 lo = 0, hi = ix.n_chrom;                   // chrom_start[n_chrom] = N
+  while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (__ldg(ix.chrom_start + mid) <= loc) lo = mid; else hi = mid; }
+  u64 cs = __ldg(ix.chrom_start + lo), ce = __ldg(ix.chrom_start + lo + 1);
+  if (!(loc >= cs && loc < ce)) { lo = ix.n_chrom - 1; cs = __ldg(ix.chrom_start + lo); ce = __ldg(ix.chrom_start + lo + 1); }
+  p.chrom = lo;
+  p.pos = loc + 1 - cs;
+  p.off = p.pos + end_site - (u64)start_site > ce - cs;
+  return p;
+}
+
+constexpr int FIN_MM = 32;           // mismatch positions kept per read (err <= 31)
+constexpr u32 FIN_INF = 0xFFFFu;
+constexpr int FIN_SORT_CAP = 2048;   // longest window list finish_sorted replays (one warp, keys in shared memory)
+
+__device__ __forceinline__ bmbs_final fin_blank(u32 k) {
+  bmbs_final o; o.site = 0; o.chrom_pos = 0; o.aux_first = 0; o.end_site = 0; o.nm = 0; o.sbd = 255; o.status = BMBS_FIN_UNMAPPED;
+  o.flags = 0; o.mapq_fixed = 0; o.k = (uint8_t)k; o.n_aux = 0;
+  return o;
+}
+__device__ __forceinline__ void fin_set_place(bmbs_final& o, const PlacedDev& p) {
+  if (p.off) { o.status = BMBS_FIN_UNMAPPED; return; }
+  o.status = BMBS_FIN_UNIQUE;
+  o.chrom_pos = ((u64)p.chrom << 40) | (p.pos & 0xFFFFFFFFFFull);
+  o.flags |= (uint8_t)p.reverse;
+}
+
+// the diagonal of window `site` that starts at window position `start`, against the read: number of mismatches (read T on
+// genome C is a match) and their read positions, ascending, into mm[] (the first FIN_MM).  The whole warp works on one read.
+__device__ __forceinline__ u32 warp_diagonal_mismatches(const DevIndex& ix, const u32* __restrict__ codes, u64 site, int start, u32 L, unsigned short* mm, int lane) {
+  u32 count = 0;
+  for (u32 base = 0; base < L; base += 32) {
+    const u32 i = base + lane;
+    bool mis = false;
+    if (i < L) {
+      const int t = read_code(codes, (int)i);
+      const int p = strand_base(ix, site + (u64)(long long)start + i);
+      mis = t != p && !(t == 3 && p == 1);
+    }
+    const u32 m = __ballot_sync(0xffffffffu, mis);
+    if (mis) { const u32 at = count + __popc(m & ((1u << lane) - 1u)); if (at < (u32)FIN_MM) mm[at] = (unsigned short)i; }
+    count += __popc(m);
+  }
+  return count;
+}
+
+// The chosen window -> the read's record (every lane computes the same `o`); returns the number of mismatch positions left in mm[].
+__device__ __forceinline__ u32 warp_finish_hit(const DevIndex& ix, const BatchView& b, int r, u32 L, u32 k, const bmbs_cand x, unsigned short* mm, int lane, bmbs_final& o) {
+  o.site = x.site; o.end_site = x.end_site; o.nm = (uint8_t)x.err;
+  const int start = (int)x.end_site - (int)L + 1;
+  u32 mm_n = 0;
+  if (x.err != 0) {
+    bool ok = start >= 0 && window_inside(ix, x.site, (u64)L + 2ull * k);
+    if (ok) { mm_n = warp_diagonal_mismatches(ix, b.codes + code_word_offset(b.offsets, r), x.site, start, L, mm, lane); ok = mm_n == x.err; }
+    if (!ok) { o.status = BMBS_FIN_DP; return 0; }
+  }
+  fin_set_place(o, place_hit(ix, x.site, start, (u64)(long long)x.end_site));
+  return o.status == BMBS_FIN_UNIQUE ? mm_n : 0u;
+}
+
+__global__ void __launch_bounds__(128) finish_se(DevIndex ix, BatchView b, bmbs_final* __restrict__ fin, unsigned short* __restrict__ mism, u32 mism_cap,
+                                                 bmbs_cand* __restrict__ fb_cand, u32 fb_cap, u32* __restrict__ sort_list, FinCounters* __restrict__ fc) {
+  __shared__ unsigned short s_mm[4][32][FIN_MM];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = r < b.n_reads;
+  bmbs_read_result res; res.state = BMBS_NONE; res.first_cand = 0; res.n_cand = 0; res.site = 0; res.one_mismatch_pos = 0; res.is_multiple_map = 0;
+  u32 L = 0, k = 0;
+  if (live) { res = b.out_res[r]; L = b.len[r]; k = b.kk[r]; }
+  bmbs_final o = fin_blank(k);
+  u32 my_mm = 0;                                       // mismatch positions of my read waiting in s_mm[w][lane]
+  bool to_sort = false;
+  if (live) {
+    if (res.state == BMBS_EXACT_UNIQUE) {
+      o.site = res.site; o.end_site = (int16_t)(L - 1); o.mapq_fixed = 42;
+      fin_set_place(o, place_hit(ix, res.site, 0, L - 1));
+    } else if (res.state == BMBS_ONE_MISMATCH) {
+      o.site = res.site; o.end_site = (int16_t)(L - 1); o.nm = 1;
+      fin_set_place(o, place_hit(ix, res.site, 0, L - 1));
+      if (o.status == BMBS_FIN_UNIQUE) { s_mm[w][lane][0] = (unsigned short)res.one_mismatch_pos; my_mm = 1; }
+    } else if (res.state == BMBS_MULTI_EXACT) {
+      if (!b.amb_out) o.status = BMBS_FIN_AMBIGUOUS;
+      else {      // the first located row (suffix-array order) that stays inside a chromosome, MAPQ 1 (Schema.cpp:27216-27245)
+        for (u32 j = 0; j < res.n_cand; ++j) {
+          const u64 site = b.out_cand[res.first_cand + j].site;
+          const PlacedDev p = place_hit(ix, site, 0, L - 1);
+          if (!p.off) { o.site = site; o.end_site = (int16_t)(L - 1); o.mapq_fixed = 1; o.flags |= BMBS_FINF_AMBIGUOUS; fin_set_place(o, p); break; }
+        }
+      }
+    }
+  }
+  u32 todo = __ballot_sync(0xffffffffu, live && res.state == BMBS_VERIFY);
+  while (todo) {
+    const int src = __ffs(todo) - 1; todo &= todo - 1;
+    const u32 first = __shfl_sync(0xffffffffu, res.first_cand, src), n = __shfl_sync(0xffffffffu, res.n_cand, src);
+    const u32 rL = __shfl_sync(0xffffffffu, L, src), rk = __shfl_sync(0xffffffffu, k, src);
+    const int rr = blockIdx.x * blockDim.x + w * 32 + src;
+    const bmbs_cand* __restrict__ c = b.out_cand + first;
+    bmbs_final q = fin_blank(rk);
+    u32 mm_n = 0; bool sort_it = false;
+    // pass 1: smallest err
+    u32 m = FIN_INF;
+    for (u32 j = lane; j < n; j += 32) m = min(m, (u32)c[j].err);
+    m = __reduce_min_sync(0xffffffffu, m);
+    if (m != FIN_INF) {
+      // pass 2: over the hits with that err -- their best vote, the first of them
+      u32 vstar = 0, i_m = 0xFFFFFFFFu;
+      for (u32 j = lane; j < n; j += 32) { const bmbs_cand x = c[j]; if (x.err == m) { vstar = max(vstar, x.vote); i_m = min(i_m, j); } }
+      vstar = __reduce_max_sync(0xffffffffu, vstar); i_m = __reduce_min_sync(0xffffffffu, i_m);
+      const bmbs_cand cm = c[i_m];
+      const u64 e0 = cm.site + (u64)(long long)cm.end_site;
+      // pass 3: do they all end at the same place; the top-voted ones among them; the smallest err above them (A) and beside
+      // them (B: same vote, larger err)
+      u32 amb = 0, cnt_top = 0, i_top = 0xFFFFFFFFu, A = FIN_INF, B = FIN_INF;
+      for (u32 j = lane; j < n; j += 32) {
+        const bmbs_cand x = c[j];
+        if (x.err == m) { amb |= (u32)((x.site + (u64)(long long)x.end_site) != e0); if (x.vote == vstar) { ++cnt_top; i_top = min(i_top, j); } }
+        else if (x.vote > vstar) A = min(A, (u32)x.err);
+        else if (x.vote == vstar) B = min(B, (u32)x.err);
+      }
+      amb = __any_sync(0xffffffffu, amb != 0) ? 1u : 0u;
+      cnt_top = __reduce_add_sync(0xffffffffu, cnt_top); i_top = __reduce_min_sync(0xffffffffu, i_top);
+      A = __reduce_min_sync(0xffffffffu, A); B = __reduce_min_sync(0xffffffffu, B);
+      if (amb && !b.amb_out) q.status = BMBS_FIN_AMBIGUOUS;
+      else {
+        u32 before = A;                                 // the running minimum when the best hit is met
+        if (n <= 16) {                                  // insertion sort: equal votes keep their (site) order
+          u32 Bs = FIN_INF;
+          for (u32 j = lane; j < i_top; j += 32) { const bmbs_cand x = c[j]; if (x.vote == vstar) Bs = min(Bs, (u32)x.err); }
+          Bs = __reduce_min_sync(0xffffffffu, Bs);
+          before = min(A, Bs);
+        } else if (cnt_top > 1 && (m != 0 || amb)) { sort_it = true; if (lane == 0) atomicAdd(&fc->n_unc_idx, 1ull); }   // which of the equal hits comes first decides the window
+        else if (!amb && B < A) { sort_it = true; if (lane == 0) atomicAdd(&fc->n_unc_sbd, 1ull); }                      // a worse hit with the same vote may or may not come first
+        if (!sort_it) {
+          if (amb) { q.sbd = 0; q.flags |= BMBS_FINF_AMBIGUOUS; }
+          else q.sbd = (uint8_t)(before == FIN_INF ? 255u : min(before - m, 255u));
+          mm_n = warp_finish_hit(ix, b, rr, rL, rk, c[i_top], &s_mm[w][src][0], lane, q);
+        }
+      }
+    }
+    if (lane == src) {
+      if (!sort_it) { o = q; my_mm = mm_n; }
+      else if (n <= (u32)FIN_SORT_CAP) to_sort = true;
+      else { o.status = BMBS_FIN_HOST; o.site = res.is_multiple_map; o.n_aux = n; }
+    }
+    __syncwarp();
+  }
+  // reads whose window order has to be replayed: their record comes from finish_sorted
+  {
+    const u32 ms = __ballot_sync(0xffffffffu, to_sort);
+    u32 base = 0;
+    if (lane == 0 && ms) base = (u32)atomicAdd(&fc->n_sorted, (unsigned long long)__popc(ms));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (to_sort) sort_list[base + __popc(ms & ((1u << lane) - 1u))] = (u32)r;
+  }
+  const bool host = live && o.status == BMBS_FIN_HOST;
+  {
+    const u32 mdp = __ballot_sync(0xffffffffu, live && o.status == BMBS_FIN_DP), mh = __ballot_sync(0xffffffffu, host);
+    if (lane == 0) { if (mdp) atomicAdd(&fc->n_dp, (unsigned long long)__popc(mdp)); if (mh) atomicAdd(&fc->n_host, (unsigned long long)__popc(mh)); }
+  }
+  // one reservation per warp for the mismatch positions, one for the window lists handed back to the host
+  u32 inc_mm = my_mm, inc_fb = host ? o.n_aux : 0u;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u32 t = __shfl_up_sync(0xffffffffu, inc_mm, d), u = __shfl_up_sync(0xffffffffu, inc_fb, d);
+    if (lane >= d) { inc_mm += t; inc_fb += u; }
+  }
+  const u32 tot_mm = __shfl_sync(0xffffffffu, inc_mm, 31), tot_fb = __shfl_sync(0xffffffffu, inc_fb, 31);
+  unsigned long long base_mm = 0, base_fb = 0;
+  if (lane == 0) { if (tot_mm) base_mm = atomicAdd(&fc->mism_used, (unsigned long long)tot_mm); if (tot_fb) base_fb = atomicAdd(&fc->fb_used, (unsigned long long)tot_fb); }
+  base_mm = __shfl_sync(0xffffffffu, base_mm, 0); base_fb = __shfl_sync(0xffffffffu, base_fb, 0);
+  if (my_mm) {
+    const unsigned long long at = base_mm + inc_mm - my_mm;
+    o.aux_first = (u32)at; o.n_aux = my_mm;
+    if (at + my_mm <= mism_cap) for (u32 j = 0; j < my_mm; ++j) mism[at + j] = s_mm[w][lane][j];
+  }
+  if (host) {
+    const unsigned long long at = base_fb + inc_fb - o.n_aux;
+    o.aux_first = (u32)at;
+    if (at + o.n_aux <= fb_cap) for (u32 j = 0; j < o.n_aux; ++j) fb_cand[at + j] = b.out_cand[res.first_cand + j];
+  }
+  if (live && !to_sort) fin[r] = o;
+}
+
+// One warp per read of sort_list: the window list as (vote << 16 | position) keys in shared memory, lane 0 replays std::sort,
+// then the reference's walk in that order -- the first window with the smallest err is the hit, the smallest err in front of it
+// is where the running minimum stood (second_best_diff), a later window with the same err and another end makes it ambiguous.
+__global__ void __launch_bounds__(128) finish_sorted(DevIndex ix, BatchView b, bmbs_final* __restrict__ fin, unsigned short* __restrict__ mism, u32 mism_cap,
+                                                     bmbs_cand* __restrict__ fb_cand, u32 fb_cap, const u32* __restrict__ sort_list, FinCounters* __restrict__ fc) {
+  __shared__ u32 s_key[4][FIN_SORT_CAP];
+  __shared__ unsigned short s_mm[4][FIN_MM];
+  __shared__ int s_ok[4];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const u32 n_list = (u32)fc->n_sorted;
+  const u32 warps = gridDim.x * (blockDim.x >> 5);
+  for (u32 i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_list; i += warps) {
+    const int r = (int)sort_list[i];
+    const bmbs_read_result res = b.out_res[r];
+    const u32 n = res.n_cand, L = b.len[r], k = b.kk[r];
+    const bmbs_cand* __restrict__ c = b.out_cand + res.first_cand;
+    u32* key = s_key[w];
+    u32 m = FIN_INF;
+    for (u32 j = lane; j < n; j += 32) { const bmbs_cand x = c[j]; key[j] = (min(x.vote, 0xFFFFu) << 16) | j; m = min(m, (u32)x.err); }
+    m = __reduce_min_sync(0xffffffffu, m);
+    __syncwarp();
+    if (lane == 0) s_ok[w] = sort_replay(key, (int)n) ? 1 : 0;
+    __syncwarp();
+    bmbs_final o = fin_blank(k);
+    u32 mm_n = 0;
+    if (!s_ok[w]) { o.status = BMBS_FIN_HOST; o.site = res.is_multiple_map; o.n_aux = n; }
+    else {
+      u32 p_hit = 0xFFFFFFFFu;
+      for (u32 p = lane; p < n; p += 32) if (c[key[p] & 0xFFFFu].err == m) p_hit = min(p_hit, p);
+      p_hit = __reduce_min_sync(0xffffffffu, p_hit);
+      const bmbs_cand x = c[key[p_hit] & 0xFFFFu];
+      const u64 e0 = x.site + (u64)(long long)x.end_site;
+      u32 before = FIN_INF, amb = 0;
+      for (u32 p = lane; p < n; p += 32) {
+        const bmbs_cand y = c[key[p] & 0xFFFFu];
+        if (p < p_hit) before = min(before, (u32)y.err);
+        else if (y.err == m) amb |= (u32)((y.site + (u64)(long long)y.end_site) != e0);
+      }
+      before = __reduce_min_sync(0xffffffffu, before);
+      amb = __any_sync(0xffffffffu, amb != 0) ? 1u : 0u;
+      if (amb && !b.amb_out) o.status = BMBS_FIN_AMBIGUOUS;
+      else {
+        if (amb) { o.sbd = 0; o.flags |= BMBS_FINF_AMBIGUOUS; }
+        else o.sbd = (uint8_t)(before == FIN_INF ? 255u : min(before - m, 255u));
+        mm_n = warp_finish_hit(ix, b, r, L, k, x, s_mm[w], lane, o);
+      }
+    }
+    if (lane == 0) {
+      if (mm_n) {
+        const unsigned long long at = atomicAdd(&fc->mism_used, (unsigned long long)mm_n);
+        o.aux_first = (u32)at; o.n_aux = mm_n;
+        if (at + mm_n <= mism_cap) for (u32 j = 0; j < mm_n; ++j) mism[at + j] = s_mm[w][j];
+      }
+      if (o.status == BMBS_FIN_HOST) {
+        const unsigned long long at = atomicAdd(&fc->fb_used, (unsigned long long)n);
+        o.aux_first = (u32)at; atomicAdd(&fc->n_host, 1ull);
+        if (at + n <= fb_cap) for (u32 j = 0; j < n; ++j) fb_cand[at + j] = c[j];
+      }
+      if (o.status == BMBS_FIN_DP) atomicAdd(&fc->n_dp, 1ull);
+      fin[r] = o;
+    }
+    __syncwarp();
+  }
 }
 
 // ------------------------------------------------------------------------------------------- scan

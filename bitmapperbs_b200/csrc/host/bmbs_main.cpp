@@ -49,6 +49,7 @@ struct Batch {
   std::vector<std::string_view> name, qual, fq_seq;  // per read / mate; fq_seq: the sequence as it stands in the FASTQ record
   std::string flat; std::vector<uint64_t> offsets;   // sequences as aligned (mate 2 reverse-complemented), back to back
   std::vector<bmbs_read_result> res; std::vector<bmbs_cand> cand;
+  std::vector<bmbs_final> fin; std::vector<uint16_t> mism;   // single end: finished records of the device (cand: handed-back window lists)
   std::string sam; MapStats st;
   std::string_view seq(int i) const { return std::string_view(flat.data() + offsets[i], (size_t)(offsets[i + 1] - offsets[i])); }
 };
@@ -189,7 +190,8 @@ void finish_batch(const HostContext& hc, Batch& b, bool pe, bool unmapped_out, b
   auto one = [&](int u, std::string& out, MapStats& st) {
     if (!pe) {
       ReadView rv{b.name[u], b.seq(u), b.qual[u], b.fq_seq[u]};
-      finish_single(hc, rv, b.res[u], b.cand.data(), out, st, fs.v1, fs.win, &dq);
+      if (!b.fin.empty()) finish_single_final(hc, rv, b.fin[u], b.mism.data(), b.cand.data(), out, st, fs.v1, fs.win, &dq);
+      else finish_single(hc, rv, b.res[u], b.cand.data(), out, st, fs.v1, fs.win, &dq);
     } else {
       finish_pair(hc, b.name[2 * u], b.seq(2 * u), b.qual[2 * u], b.name[2 * u + 1], b.seq(2 * u + 1), b.fq_seq[2 * u + 1], b.qual[2 * u + 1],
                   b.res[2 * u], b.res[2 * u + 1], b.cand.data(), out, st, fs.v1, fs.v2, fs.win, &dq);
@@ -306,6 +308,10 @@ int search(const Options& o, const std::string& cmdline) {
     // one batch context and one set of page-locked result buffers per GPU thread, grown on demand
     bmbs_batch* ctx = nullptr; size_t cap_reads = 0, cap_bases = 0, cap_cand = 0;
     bmbs_read_result* h_res = nullptr; bmbs_cand* h_cand = nullptr; size_t h_res_cap = 0, h_cand_cap = 0;
+    // single end: the device finishes the reads (reduction, ungapped CIGAR, coordinates) and one 32-byte record per read comes
+    // back; BMBS_HOST_FINISH=1 keeps the host reduction over the full window lists
+    const bool dev_finish = !pe && !getenv("BMBS_HOST_FINISH");
+    bmbs_final* h_fin = nullptr; uint16_t* h_mism = nullptr; size_t h_fin_cap = 0;
     auto ensure = [&](size_t reads, size_t bases, size_t cands) {
       if (!ctx || reads > cap_reads || bases > cap_bases || cands > cap_cand) {
         if (ctx) bmbs_batch_free(ctx);
@@ -314,6 +320,11 @@ int search(const Options& o, const std::string& cmdline) {
       }
       if (cap_reads > h_res_cap) { bmbs_pinned_free(h_res); h_res_cap = cap_reads; h_res = (bmbs_read_result*)bmbs_pinned_alloc(h_res_cap * sizeof(bmbs_read_result)); }
       if (cap_cand > h_cand_cap) { bmbs_pinned_free(h_cand); h_cand_cap = cap_cand; h_cand = (bmbs_cand*)bmbs_pinned_alloc(h_cand_cap * sizeof(bmbs_cand)); }
+      if (dev_finish && cap_reads > h_fin_cap) {
+        bmbs_pinned_free(h_fin); bmbs_pinned_free(h_mism); h_fin_cap = cap_reads;
+        h_fin = (bmbs_final*)bmbs_pinned_alloc(h_fin_cap * sizeof(bmbs_final)); h_mism = (uint16_t*)bmbs_pinned_alloc((32 * h_fin_cap + 64) * sizeof(uint16_t));
+        if (!h_fin || !h_mism) die("cannot allocate page-locked result buffers");
+      }
       if (!h_res || !h_cand) die("cannot allocate page-locked result buffers");
     };
     {   // sized for a full batch of typical reads before the first one arrives
@@ -334,20 +345,24 @@ int search(const Options& o, const std::string& cmdline) {
         const double t_c = now();
         if (!rc) rc = bmbs_batch_run(ctx, &o.prm);
         const double t_d = now();
-        if (!rc) rc = bmbs_batch_download(ctx, h_res, h_cand, h_cand_cap, &used);
+        size_t n_mism = 0;
+        if (!rc && dev_finish) rc = bmbs_batch_finish(ctx);
+        if (!rc) rc = dev_finish ? bmbs_batch_download_final(ctx, h_fin, h_mism, 32 * h_fin_cap + 64, &n_mism, h_cand, h_cand_cap, &used)
+                                 : bmbs_batch_download(ctx, h_res, h_cand, h_cand_cap, &used);
         const double t_e = now();
         us_prep += us(t_a, t_b); us_up += us(t_b, t_c); us_run += us(t_c, t_d); us_down += us(t_d, t_e);
         if (!rc) { float ms[8]; if (!bmbs_batch_timings(ctx, ms)) { us_dev += (long long)(ms[0] * 1000); for (int q = 1; q < 8; ++q) us_stage[q] += (long long)(ms[q] * 1000); } }
         if (rc == BMBS_ERR_CAPACITY) { want_cand = std::max(cap_cand * 2, used + (used >> 2) + 1024); ++n_retry; continue; }
         if (rc) die(std::string("gpu batch failed: ") + bmbs_last_error());
-        b->res.assign(h_res, h_res + b->n); b->cand.assign(h_cand, h_cand + used);
+        if (dev_finish) { b->fin.assign(h_fin, h_fin + b->n); b->mism.assign(h_mism, h_mism + n_mism); b->cand.assign(h_cand, h_cand + used); }
+        else { b->res.assign(h_res, h_res + b->n); b->cand.assign(h_cand, h_cand + used); }
         break;
       }
       us_gpu += us(ts, now());
       fin_q.push(std::move(b));
     }
     if (ctx) bmbs_batch_free(ctx);
-    bmbs_pinned_free(h_res); bmbs_pinned_free(h_cand);
+    bmbs_pinned_free(h_res); bmbs_pinned_free(h_cand); bmbs_pinned_free(h_fin); bmbs_pinned_free(h_mism);
     if (--live_gpu == 0) fin_q.close();
   });
   std::atomic<long long> n_dp_total(0);

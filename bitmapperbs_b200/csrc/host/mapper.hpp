@@ -117,6 +117,58 @@ inline void finish_single(const HostContext& hc, const ReadView& rd, const bmbs_
   }
 }
 
+// ---- single end, from the device's finished records (bmbs_batch_finish) --------------------------
+// The reduction, the ungapped CIGAR check and the coordinates were done on the device; what is left here is the score of the
+// returned mismatch positions (MismatchPenaltyByQuality needs the quality string, which stays on the host), MAPQ and the
+// record text.  BMBS_FIN_DP reads take the banded DP (one bmbs_refine call per sub-block through `dq`), BMBS_FIN_HOST reads
+// the host reduction above with the window list that came back.
+inline void finish_single_final(const HostContext& hc, const ReadView& rd, const bmbs_final& f, const uint16_t* mism, const bmbs_cand* fb_cand,
+                                std::string& out, MapStats& st, std::vector<HostHit>& hits, std::vector<char>& win, DpQueue* dq = nullptr) {
+  const std::string_view seq = rd.seq, qual = rd.qual;
+  const int L = (int)seq.size();
+  const uint64_t k = threshold_k(hc.prm.e_rate, L);
+  auto count = [&](unsigned nm) { if (f.flags & BMBS_FINF_AMBIGUOUS) ++st.ambiguous; else { ++st.unique; st.bases += L; st.err_bases += nm; } };
+  auto record = [&](const Placed& p, int mapq, const std::string& cigar, unsigned nm) {
+    if (!hc.pbat) sam_record_se(out, rd.name, seq, qual, hc.chroms, p, mapq, cigar, nm);
+    else sam_record_se_pbat(out, rd.name, seq, rd.raw, qual, hc.chroms, p, mapq, cigar, nm);
+  };
+  switch (f.status) {
+    case BMBS_FIN_UNIQUE: {
+      ++st.reads;
+      int score = 0;
+      for (uint32_t j = 0; j < f.n_aux; ++j) {
+        const int pos = mism[f.aux_first + j];
+        if (seq[pos] == 'N') score -= hc.sc.n_pen; else score -= mismatch_penalty(hc.sc, qual[hc.pbat ? L - 1 - pos : pos]);
+      }
+      const int mapq = f.mapq_fixed ? f.mapq_fixed : mapq_from(f.sbd, (unsigned)k, score, hc.sc);
+      Placed p; p.flag = (f.flags & BMBS_FINF_REVERSE) ? 16 : 0; p.chrom = (size_t)(f.chrom_pos >> 40); p.pos = f.chrom_pos & 0xFFFFFFFFFFull; p.off_chrom = false;
+      record(p, mapq, std::to_string(L) + "M", f.nm);
+      count(f.nm);
+      return;
+    }
+    case BMBS_FIN_AMBIGUOUS: ++st.reads; ++st.ambiguous; return;
+    case BMBS_FIN_DP: {
+      ++st.reads;
+      const int plen = L + 2 * (int)k; win.resize(plen + 8);
+      hc.genome.window(f.site, plen, win.data());
+      Refined rf;
+      refine_alignment(win.data(), plen, seq.data(), L, (int)k, (int)f.end_site, f.nm, f.site < hc.chroms.N, qual.data(), hc.pbat, hc.sc, rf, f.site, dq);
+      const int mapq = mapq_from(f.sbd, (unsigned)k, rf.score, hc.sc);
+      const Placed p = place(hc.chroms, f.site, (uint64_t)(int64_t)rf.start_site, rf.end_site);
+      if (p.off_chrom) return;
+      record(p, mapq, rf.cigar, rf.err);
+      count(rf.err);
+      return;
+    }
+    case BMBS_FIN_HOST: {
+      bmbs_read_result r{}; r.state = BMBS_VERIFY; r.first_cand = f.aux_first; r.n_cand = f.n_aux; r.is_multiple_map = (uint8_t)f.site;
+      finish_single(hc, rd, r, fb_cand, out, st, hits, win, dq);
+      return;
+    }
+    default: ++st.reads; return;
+  }
+}
+
 // ---- paired end -------------------------------------------------------------------------------
 namespace pe {
 // keep hits (err <= k) whose absolute end differs from the candidate right before them

@@ -148,6 +148,47 @@ int bmbs_ubench_random_sectors(int dev, size_t bytes, double* sectors_per_second
 int bmbs_batch_launches(bmbs_batch* b);
 
 
+/* ---- finished single-end records (SURVEY.md 8a V3 + 8f-1): reduction, ungapped CIGAR, coordinates on the device -----
+ * Replaces, for a single-end batch, what Map_Single_Seq_split does after its verification calls: the vote-ordered reduction
+ * (Schema.cpp:27612 std::sort + :7847-8056 / :8325-8745; second_best_diff and the choice among equal hits in exactly the
+ * order libstdc++'s std::sort leaves), try_cigar_without_path (ksw.cpp:2515-2570) and the coordinate conversion with the
+ * end-of-chromosome drop (Schema.cpp:12596-12650).  One 32-byte record per read comes back instead of the read's whole
+ * verified window list.  What stays with the caller: the alignment score of an ungapped hit = sum of
+ * MismatchPenaltyByQuality (ksw.h:148-162) over the returned mismatch positions (the quality strings never go to the
+ * device), MAP_Calculation on (sbd, k, score), the banded DP of BMBS_FIN_DP reads through bmbs_refine, SAM text. */
+enum {
+  BMBS_FIN_UNMAPPED = 0,   /* no hit within k, or the hit runs over the end of its chromosome: no record, not counted   */
+  BMBS_FIN_UNIQUE = 1,     /* hit without indels, CIGAR <L>M: chrom_pos, strand, nm, mismatch positions, sbd            */
+  BMBS_FIN_AMBIGUOUS = 2,  /* equally good hits at different places: counted, no record (without --ambiguous_out)       */
+  BMBS_FIN_DP = 3,         /* the chosen window (site, end_site, nm = the verifier's err, sbd) needs the banded DP      */
+  BMBS_FIN_HOST = 4        /* handed back: cand[aux_first .. +n_aux) is the read's verified window list, site = is_multiple_map */
+};
+#define BMBS_FINF_REVERSE 1u    /* SAM flag 16                                                                          */
+#define BMBS_FINF_AMBIGUOUS 2u  /* --ambiguous_out: the first of several equally good hits; counted as ambiguous        */
+typedef struct {
+  uint64_t site;        /* double-strand coordinate of the chosen window (states 1 / 3: of the read)                    */
+  uint64_t chrom_pos;   /* BMBS_FIN_UNIQUE: chromosome index << 40 | 1-based POS                                        */
+  uint32_t aux_first;   /* BMBS_FIN_UNIQUE: first of n_aux = nm mismatch read positions in mism[]; BMBS_FIN_HOST: in cand[] */
+  int16_t end_site;     /* last window position of the alignment (the verifier's)                                       */
+  uint8_t nm;           /* mismatches (BMBS_FIN_UNIQUE) / the verifier's err (BMBS_FIN_DP)                              */
+  uint8_t sbd;          /* second_best_diff, 255 = none or more (MAP_Calculation only asks whether it exceeds k <= 31)  */
+  uint8_t status;       /* BMBS_FIN_*                                                                                    */
+  uint8_t flags;        /* BMBS_FINF_*                                                                                   */
+  uint8_t mapq_fixed;   /* non-zero: MAPQ is this (42: unique exact first seed, 1: multi-exact with --ambiguous_out)    */
+  uint8_t k;            /* the read's error threshold                                                                    */
+  uint32_t n_aux;
+} bmbs_final;           /* 32 bytes */
+/* Enqueue the finishing kernels behind bmbs_batch_run on the batch's stream (single-end batches only). */
+int bmbs_batch_finish(bmbs_batch* b);
+/* Wait, then copy back fin[n_reads], the mismatch positions and the window lists of handed-back reads.
+ * BMBS_ERR_CAPACITY with the needed sizes in *mism_used / *cand_used when a caller buffer is too small. */
+int bmbs_batch_download_final(bmbs_batch* b, bmbs_final* fin, uint16_t* mism, size_t mism_cap, size_t* mism_used,
+                              bmbs_cand* cand, size_t cand_cap, size_t* cand_used);
+/* counters of the last bmbs_batch_finish: [0] mismatch positions [1] handed-back windows [2] reads whose window order was
+ * replayed on the device [3] reads handed back [4] reads marked BMBS_FIN_DP [5] / [6] replayed because the chosen window /
+ * second_best_diff depended on the order [7] device time of the finishing kernels, us */
+int bmbs_batch_finish_counters(bmbs_batch* b, uint64_t c[8]);
+
 /* ---- CIGAR refinement: the banded affine-gap DP with traceback -----------------------------------
  * Replaces ksw_semi_global_quality_back (ksw.cpp:1850-2045) as fast_recalculate_bs_Cigar calls it (ksw.cpp:2578-3148,
  * through try_cigar_without_path :2515-2570) for the one hit per read / mate that the host reduction picked and whose

@@ -124,6 +124,78 @@ int orc_map_pe_sensitive(void* h, const char* seqs, const uint64_t* offs, int n_
   return w <= cap ? 0 : BMBS_ERR_CAPACITY;
 }
 
+// CPU restatement of the device finishing (finish_se / finish_sorted, include/bmbs.h bmbs_final) the way the reference does it:
+// std::sort by vote (Schema.cpp:27612, comparator :560-563), the walk of Map_candidate_votes_mutiple_* (:7847-8056 / :8325-8745,
+// early exit of the is_multiple_map variant included), try_cigar_without_path (ksw.cpp:2515-2570) on the chosen window, and the
+// coordinate conversion (Schema.cpp:12596-12650).  Never returns BMBS_FIN_HOST.
+int orc_finish_se(void* h, const char* seqs, const uint64_t* offs, int n, double e_rate, int ambiguous_out, const bmbs_read_result* res,
+                  const bmbs_cand* cand, bmbs_final* fin, uint16_t* mism, size_t mism_cap, size_t* mism_used) {
+  const Index& ix = *(Index*)h;
+  size_t w = 0; std::vector<char> win;
+  struct Hit { u64 site, vote; uint32_t err; u64 end_site; };
+  std::vector<Hit> hits;
+  for (int r = 0; r < n; ++r) {
+    const char* read = seqs + offs[r]; const int L = (int)(offs[r + 1] - offs[r]);
+    const u64 k = u64_k(e_rate, L);
+    bmbs_final& o = fin[r]; memset(&o, 0, sizeof o); o.sbd = 255; o.k = (uint8_t)k;
+    const bmbs_read_result& rs = res[r];
+    auto placed = [&](u64 site, int start, u64 end_site) {
+      const bmbs::Placed p = bmbs::place(ix.chroms, site, (u64)(long long)start, end_site);
+      if (p.off_chrom) { o.status = BMBS_FIN_UNMAPPED; return false; }
+      o.status = BMBS_FIN_UNIQUE; o.chrom_pos = ((u64)p.chrom << 40) | p.pos; if (p.flag) o.flags |= BMBS_FINF_REVERSE;
+      return true;
+    };
+    if (rs.state == BMBS_EXACT_UNIQUE) { o.site = rs.site; o.end_site = (int16_t)(L - 1); o.mapq_fixed = 42; placed(rs.site, 0, L - 1); continue; }
+    if (rs.state == BMBS_ONE_MISMATCH) {
+      o.site = rs.site; o.end_site = (int16_t)(L - 1); o.nm = 1;
+      if (placed(rs.site, 0, L - 1)) { o.aux_first = (uint32_t)w; o.n_aux = 1; if (w < mism_cap) mism[w] = (uint16_t)rs.one_mismatch_pos; ++w; }
+      continue;
+    }
+    if (rs.state == BMBS_MULTI_EXACT) {
+      if (!ambiguous_out) { o.status = BMBS_FIN_AMBIGUOUS; continue; }
+      for (uint32_t j = 0; j < rs.n_cand; ++j) {
+        const u64 site = cand[rs.first_cand + j].site;
+        if (!bmbs::place(ix.chroms, site, 0, L - 1).off_chrom) { o.site = site; o.end_site = (int16_t)(L - 1); o.mapq_fixed = 1; o.flags |= BMBS_FINF_AMBIGUOUS; placed(site, 0, L - 1); break; }
+      }
+      continue;
+    }
+    if (rs.state != BMBS_VERIFY) continue;
+    hits.resize(rs.n_cand);
+    for (uint32_t j = 0; j < rs.n_cand; ++j) { const bmbs_cand& c = cand[rs.first_cand + j]; hits[j] = {c.site, c.vote, c.err == 0xFFFF ? 0xFFFFFFFFu : c.err, (u64)(int64_t)c.end_site}; }
+    std::sort(hits.begin(), hits.end(), [](const Hit& a, const Hit& b) { return a.vote > b.vote; });
+    uint32_t min_err = 0xFFFFFFFEu, sbd = 0; long idx = -1; u64 best_end = ~0ull;
+    for (size_t i = 0; i < hits.size(); ++i) {
+      const uint32_t e = hits[i].err; const u64 end_abs = hits[i].site + hits[i].end_site;
+      if (!rs.is_multiple_map) {
+        if (e == min_err && best_end != end_abs && idx >= 0) { sbd = 0; idx = -2 - idx; }
+        else if (e < min_err) { sbd = min_err - e; min_err = e; idx = (long)i; best_end = end_abs; }
+      } else {
+        if (e == min_err && best_end != end_abs) { sbd = 0; if (idx >= 0) idx = -2 - idx; if (min_err == 0) break; }
+        else if (e < min_err) { sbd = min_err - e; min_err = e; idx = (long)i; best_end = end_abs; }
+      }
+    }
+    const bool ambiguous = idx <= -2;
+    if (ambiguous) { if (!ambiguous_out) { o.status = BMBS_FIN_AMBIGUOUS; continue; } idx = -2 - idx; o.flags |= BMBS_FINF_AMBIGUOUS; }
+    if (idx < 0) continue;
+    const Hit& b = hits[idx];
+    o.site = b.site; o.end_site = (int16_t)(int64_t)b.end_site; o.nm = (uint8_t)b.err; o.sbd = (uint8_t)(sbd > 255 ? 255 : sbd);
+    const int start = (int)(int64_t)b.end_site - L + 1;
+    if (b.err != 0) {
+      const int plen = L + 2 * (int)k; win.resize(plen + 8);
+      ix.genome.window(b.site, plen, win.data());
+      bool ok = start >= 0; size_t w0 = w; unsigned mis = 0;
+      for (int i = 0; ok && i < L; ++i) {
+        const char t = read[i], p = win[i + start];
+        if (t != p && !(t == 'T' && p == 'C')) { if (++mis > b.err) { ok = false; break; } if (w < mism_cap) mism[w] = (uint16_t)i; ++w; }
+      }
+      if (!(ok && mis == b.err)) { w = w0; o.status = BMBS_FIN_DP; continue; }
+      if (placed(b.site, start, b.end_site)) { o.aux_first = (uint32_t)w0; o.n_aux = mis; } else w = w0;
+    } else placed(b.site, start, b.end_site);
+  }
+  *mism_used = w;
+  return w <= mism_cap ? 0 : BMBS_ERR_CAPACITY;
+}
+
 int orc_verify(void* h, const char* seqs, const uint64_t* offs, int n_reads, const uint32_t* read_idx, const uint64_t* sites, size_t n,
                double e_rate, int32_t* end_site, uint32_t* err, int threads) {
   const Index& ix = *(Index*)h;

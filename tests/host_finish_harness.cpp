@@ -2,7 +2,9 @@
 // pair pick, CIGAR refinement with the DP on the CPU, MAPQ, SAM text) fed with the per-read records of the ORACLE instead of
 // the GPU library -- both produce the same bmbs_read_result / bmbs_cand arrays (tests/test_gpu_parity.py checks that on the
 // GPU box).  The SAM it writes must equal the reference's golden SAM: that pins the host glue without a GPU.
-//   host_finish_harness se|pe|pes <genome.fa> <out.sam> <reads.fq> [<mates.fq>] [--unmapped_out] [--ambiguous_out] [--pbat]
+// Mode sef: single end through the finished records (bmbs_final) -- the oracle's restatement of the device finishing
+// (orc_finish_se) feeds mapper.hpp's finish_single_final, the consumer the mapper uses behind bmbs_batch_finish.
+//   host_finish_harness se|sef|pe|pes <genome.fa> <out.sam> <reads.fq> [<mates.fq>] [--unmapped_out] [--ambiguous_out] [--pbat]
 // (--ambiguous_out: paired end only here -- the single-end multi-exact case needs the located rows in row order, which only the
 // device path returns; --pbat as in bmbs_main.cpp: single end aligns the reverse complement, paired end swaps the files)
 #include <cstdio>
@@ -16,7 +18,8 @@
 int main(int argc, char** argv) {
   if (argc < 5) return 2;
   const std::string mode = argv[1], fa = argv[2], out_path = argv[3];
-  const bool pe = mode != "se", sens = mode == "pes";
+  const bool fin_mode = mode == "sef";
+  const bool pe = mode != "se" && !fin_mode, sens = mode == "pes";
   bool unmapped_out = false, ambiguous_out = false, pbat = false;
   std::vector<std::string> files;
   for (int i = 4; i < argc; ++i) { if (!strcmp(argv[i], "--unmapped_out")) unmapped_out = true; else if (!strcmp(argv[i], "--ambiguous_out")) ambiguous_out = true; else if (!strcmp(argv[i], "--pbat")) pbat = true; else files.push_back(argv[i]); }
@@ -52,6 +55,11 @@ int main(int argc, char** argv) {
     if (rc == 0) break;
     cand.resize(used + 1024);
   }
+  std::vector<bmbs_final> fin; std::vector<uint16_t> mism;
+  if (fin_mode) {
+    fin.resize(n + 1); mism.resize((size_t)n * 32 + 64); size_t mused = 0;
+    if (orc_finish_se(h, flat.data(), offs.data(), n, 0.08, ambiguous_out ? 1 : 0, res.data(), cand.data(), fin.data(), mism.data(), mism.size(), &mused)) return 1;
+  }
   std::string out; bmbs::sam_header(out, hc.chroms, "host_finish_harness");
   bmbs::MapStats st; std::vector<bmbs::HostHit> v1, v2; std::vector<char> win;
   auto seq = [&](int i) { return std::string_view(flat.data() + offs[i], (size_t)(offs[i + 1] - offs[i])); };
@@ -59,7 +67,8 @@ int main(int argc, char** argv) {
   const auto t_begin = std::chrono::steady_clock::now();
   for (int u = 0; u < units; ++u) {
     bmbs::MapStats t;
-    if (!pe) { bmbs::ReadView rv{recs[u].name, seq(u), recs[u].qual, raw1[u]}; bmbs::finish_single(hc, rv, res[u], cand.data(), out, t, v1, win); }
+    if (fin_mode) { bmbs::ReadView rv{recs[u].name, seq(u), recs[u].qual, raw1[u]}; bmbs::finish_single_final(hc, rv, fin[u], mism.data(), cand.data(), out, t, v1, win); }
+    else if (!pe) { bmbs::ReadView rv{recs[u].name, seq(u), recs[u].qual, raw1[u]}; bmbs::finish_single(hc, rv, res[u], cand.data(), out, t, v1, win); }
     else bmbs::finish_pair(hc, recs[2 * u].name, seq(2 * u), recs[2 * u].qual, recs[2 * u + 1].name, seq(2 * u + 1), raw2[u], recs[2 * u + 1].qual,
                            res[2 * u], res[2 * u + 1], cand.data(), out, t, v1, v2, win);
     if (unmapped_out && !t.unique && !t.ambiguous) {

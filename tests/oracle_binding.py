@@ -4,7 +4,7 @@ from pathlib import Path
 
 import numpy as np
 
-from bitmapperbs_b200.capi import Cand, ReadResult, flatten
+from bitmapperbs_b200.capi import Cand, Final, ReadResult, flatten
 
 ROOT = Path(__file__).resolve().parent.parent
 _lib = None
@@ -28,6 +28,7 @@ def lib():
         L.orc_map_pe.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.orc_map_pe_sensitive.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_size_t), vp]
         L.orc_verify.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_size_t, C.c_double, vp, vp, C.c_int]
+        L.orc_finish_se.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_int, vp, vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.orc_banded_align.argtypes = [vp, C.c_uint64, C.c_char_p, C.c_char_p] + [C.c_int] * 8 + [C.POINTER(C.c_int)] * 3 + [vp, C.c_int]
         _lib = L
     return _lib
@@ -52,6 +53,17 @@ class OracleIndex:
         rc = lib().orc_map_se(self.h, flat.ctypes.data, offs.ctypes.data, n, e_rate, seed_len, res.ctypes.data, cand.ctypes.data, cap, C.byref(used))
         assert rc == 0
         return res, cand[: used.value]
+
+    def finish_se(self, reads, res, cand, e_rate=0.08, ambiguous_out=False):
+        """the reference's reduction + ungapped CIGAR check + coordinates over (res, cand) -> (Final[n], mismatch positions)"""
+        flat, offs = reads if isinstance(reads, tuple) else flatten(reads)
+        n = len(offs) - 1
+        fin = np.zeros(n, dtype=Final); mism = np.zeros(32 * n + 64, dtype=np.uint16); used = C.c_size_t(0)
+        res = np.ascontiguousarray(res); cand = np.ascontiguousarray(cand)
+        rc = lib().orc_finish_se(self.h, flat.ctypes.data, offs.ctypes.data, n, e_rate, 1 if ambiguous_out else 0, res.ctypes.data, cand.ctypes.data,
+                                 fin.ctypes.data, mism.ctypes.data, len(mism), C.byref(used))
+        assert rc == 0
+        return fin, mism[: used.value]
 
     def map_pe(self, mates, e_rate=0.08, seed_len=30, min_ins=0, max_ins=500, cap=None):
         flat, offs = mates if isinstance(mates, tuple) else flatten(mates)

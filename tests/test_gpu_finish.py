@@ -1,0 +1,93 @@
+"""GPU (-m gpu): the device finishing of single-end batches (bmbs_batch_finish: vote-ordered reduction in std::sort's order,
+ungapped CIGAR check, coordinates) against the oracle's restatement of the reference's walk (orc_finish_se: std::sort + the
+literal loop + try_cigar_without_path + place), record by record; the introsort replay on lists of every size class."""
+import subprocess
+
+import numpy as np
+import pytest
+
+import bitmapperbs_b200 as B
+from bitmapperbs_b200 import capi, simulate as S
+from conftest import read_fastq
+from oracle_binding import OracleIndex
+
+pytestmark = pytest.mark.gpu
+
+
+def device_finish(ix, reads, params=None):
+    flat, offs = capi.flatten(reads)
+    b = B.Batch(ix, 0, len(reads) + 1, len(flat) + 64, max(1 << 18, 64 * len(reads)))
+    p = params or capi.default_params()
+    b.upload(flat, offs); b.run(p); b.finish()
+    res, cand, used = b.download()
+    fin, mism, fb = b.download_final()
+    c = b.finish_counters()
+    b.close()
+    return res, cand[:used], fin, mism, fb, c
+
+
+def assert_same_final(gfin, gmism, ofin, omism, res, cand, allow_host=0):
+    host = gfin["status"] == capi.FIN_HOST
+    assert host.sum() <= allow_host, f"{host.sum()} reads handed back to the host"
+    m = ~host
+    for f in ("status", "flags", "sbd", "nm", "mapq_fixed", "k", "chrom_pos"):
+        assert np.array_equal(gfin[f][m], ofin[f][m]), f
+    # the window may differ among equally voted windows that end at the same place (same alignment): compare where it ends
+    hit = m & np.isin(gfin["status"], [capi.FIN_UNIQUE, capi.FIN_DP])
+    assert np.array_equal(gfin["site"][hit] + gfin["end_site"][hit].astype(np.uint64), ofin["site"][hit] + ofin["end_site"][hit].astype(np.uint64))
+    dp = m & (gfin["status"] == capi.FIN_DP)
+    assert np.array_equal(gfin["site"][dp], ofin["site"][dp]) and np.array_equal(gfin["end_site"][dp], ofin["end_site"][dp])
+    uq = np.nonzero(m & (gfin["status"] == capi.FIN_UNIQUE))[0]
+    assert np.array_equal(gfin["n_aux"][uq], ofin["n_aux"][uq])
+    for r in uq:
+        a, n = int(gfin["aux_first"][r]), int(gfin["n_aux"][r]); b = int(ofin["aux_first"][r])
+        assert np.array_equal(gmism[a:a + n], omism[b:b + n]), r
+    # handed-back reads carry their whole window list
+    for r in np.nonzero(host)[0]:
+        a, n = int(gfin["aux_first"][r]), int(gfin["n_aux"][r])
+        assert n == res["n_cand"][r]
+
+
+@pytest.fixture(scope="module")
+def idx_pair(golden):
+    ix = B.Index(golden / "genome.fa.index"); ox = OracleIndex(golden / "genome.fa.index")
+    yield ix, ox
+    ix.close()
+
+
+@pytest.mark.parametrize("amb_out", [0, 1])
+def test_finished_records_match_oracle_golden_reads(golden, idx_pair, amb_out):
+    ix, ox = idx_pair
+    reads = [r[1] for r in read_fastq(golden / "se100.fq")] + [r[1] for r in read_fastq(golden / "se250.fq")]
+    genome = b"".join(l.strip() for l in open(golden / "genome.fa", "rb") if not l.startswith(b">"))
+    N = len(genome)
+    reads += [b"ACGT" * 4, b"N" * 100, genome[:100], genome[N - 100:], genome[119950:120050], genome[119900:120000], genome[120000:120100],
+              genome[5000:5050] + b"N" + genome[5051:5100], genome[7000:7017] + b"R" + genome[7018:7100], b"T" * 60, b"TG" * 40, genome[9000:9999]]
+    p = capi.default_params(ambiguous_out=amb_out)
+    res, cand, fin, mism, fb, c = device_finish(ix, reads, p)
+    ofin, omism = ox.finish_se(reads, res, cand, ambiguous_out=bool(amb_out))
+    assert_same_final(fin, mism, ofin, omism, res, cand)
+    st = fin["status"]
+    assert (st == capi.FIN_UNIQUE).sum() > 1000 and (st == capi.FIN_DP).sum() > 20 and c["reads_dp"] == (st == capi.FIN_DP).sum()
+
+
+@pytest.mark.parametrize("amb_out", [0, 1])
+def test_finished_records_on_high_copy_repeats(built, tmp_path, amb_out):
+    """window lists of every size: <= 16 (stable insertion sort), longer ones whose outcome does not depend on the order, and
+    the ones finish_sorted replays std::sort for (the counters must show that each class occurred)"""
+    chroms = S.random_genome([700000, 500000], seed=321, repeat_fraction=0.7, repeat_copies=(40, 1500), repeat_len=(200, 700), repeat_div=(0.005, 0.06))
+    S.write_fasta(tmp_path / "g.fa", chroms)
+    subprocess.run([str(built["indexer"]), "g.fa"], cwd=tmp_path, check=True, stderr=subprocess.DEVNULL)
+    g, st = S.concat_genome(chroms)
+    m1, _ = S.simulate_fast(g, st, 8000, 150, 17, paired=False, indel_reads=0.2)
+    reads = [bytes(r) for r in m1]
+    ix = B.Index(tmp_path / "g.fa.index"); ox = OracleIndex(tmp_path / "g.fa.index")
+    try:
+        res, cand, fin, mism, fb, c = device_finish(ix, reads, capi.default_params(ambiguous_out=amb_out))
+        ofin, omism = ox.finish_se(reads, res, cand, ambiguous_out=bool(amb_out))
+        n = res["n_cand"][res["state"] == B.VERIFY]
+        assert (n > 16).sum() > 100 and (n > 256).any()
+        assert c["reads_sort_replayed"] > 10, c
+        assert_same_final(fin, mism, ofin, omism, res, cand, allow_host=(n > 2048).sum())
+    finally:
+        ix.close()

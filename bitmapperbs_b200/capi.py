@@ -50,7 +50,7 @@ EXPORTS = ["bmbs_index_load", "bmbs_index_free", "bmbs_index_genome_length", "bm
            "bmbs_params_default", "bmbs_map_batch_se", "bmbs_map_batch_pe", "bmbs_verify", "bmbs_batch_create", "bmbs_batch_free",
            "bmbs_batch_upload", "bmbs_batch_run", "bmbs_batch_download", "bmbs_batch_sync", "bmbs_batch_timings",
            "bmbs_batch_counters", "bmbs_batch_launches", "bmbs_batch_verify", "bmbs_batch_download_verify", "bmbs_ubench_int_pipe", "bmbs_pinned_alloc", "bmbs_pinned_free", "bmbs_ubench_random_sectors",
-           "bmbs_refiner_create", "bmbs_refiner_free", "bmbs_refine", "bmbs_batch_finish", "bmbs_batch_download_final", "bmbs_batch_finish_counters"]
+           "bmbs_refiner_create", "bmbs_refiner_free", "bmbs_refine", "bmbs_batch_finish", "bmbs_batch_download_final", "bmbs_batch_finish_counters", "bmbs_debug_sort_order"]
 
 
 def load_library():
@@ -88,6 +88,7 @@ def load_library():
     L.bmbs_batch_finish.argtypes = [vp]
     L.bmbs_batch_download_final.argtypes = [vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t), vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.bmbs_batch_finish_counters.argtypes = [vp, u64p]
+    L.bmbs_debug_sort_order.argtypes = [C.c_int, vp, vp, C.c_uint32, vp, vp]
     L.bmbs_refiner_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
     L.bmbs_refiner_free.argtypes = [vp]
     L.bmbs_refine.argtypes = [vp, vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(Scoring), vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -112,6 +113,17 @@ def random_sector_peak(dev=0, nbytes=8 << 30) -> float:
     v = C.c_double(0)
     _check(load_library().bmbs_ubench_random_sectors(dev, nbytes, C.byref(v)))
     return v.value
+
+
+def debug_sort_order(vote_lists, dev=0):
+    """the order std::sort by vote (descending) leaves each list in, replayed by the device finishing's warp routine
+    -> (list of position arrays, ok flags)"""
+    offs = np.zeros(len(vote_lists) + 1, dtype=np.uint32)
+    offs[1:] = np.cumsum([len(v) for v in vote_lists], dtype=np.uint32)
+    votes = np.concatenate([np.asarray(v, dtype=np.uint32) for v in vote_lists]) if vote_lists else np.zeros(0, np.uint32)
+    order = np.zeros(len(votes) + 8, dtype=np.uint16); ok = np.zeros(len(vote_lists) + 4, dtype=np.int32)
+    _check(load_library().bmbs_debug_sort_order(dev, votes.ctypes.data, offs.ctypes.data, len(vote_lists), order.ctypes.data, ok.ctypes.data))
+    return [order[offs[i]:offs[i + 1]] for i in range(len(vote_lists))], ok[: len(vote_lists)]
 
 
 def default_params(**kw) -> Params:

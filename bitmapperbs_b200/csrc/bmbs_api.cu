@@ -401,7 +401,7 @@ struct bmbs_batch {
   u64* h_small = nullptr;        // pinned: totals[2], status, counters[8]; [16..23] finishing counters
   cudaEvent_t ev[11] = {nullptr};
   // finishing (bmbs_batch_finish): records, mismatch positions, handed-back window lists, reads to replay the sort for
-  bmbs_final* d_fin = nullptr; unsigned short* d_mism = nullptr; bmbs_cand* d_fb = nullptr; u32* d_sort_list = nullptr; FinCounters* d_fc = nullptr;
+  bmbs_final* d_fin = nullptr; unsigned short* d_mism = nullptr; bmbs_cand* d_fb = nullptr; u32* d_sort_list = nullptr; u32* d_long_list = nullptr; u32* d_huge_list = nullptr; FinCounters* d_fc = nullptr;
   size_t mism_cap = 0, fb_cap = 0; bool finished = false;
   int n_reads = 0, pe = 0, max_len = 0, launches = 0, sm_count = 148, seed_blocks_per_sm = 8; u32 seed_plane_cap = 0;
   bool ran = false;
@@ -467,9 +467,9 @@ extern "C" int bmbs_batch_create(bmbs_index* idx, int dev, size_t max_reads, siz
   A(dalloc(b, &v.counters, 16)); A(dalloc(b, &v.totals, 4)); A(dalloc(b, &v.status, 4));
   A(dalloc(b, &b->d_tile, R / SCAN_TILE + 8));
   b->mism_cap = 32 * R;      // a read holds at most 31 mismatch positions b->fb_cap = S;
-  A(dalloc(b, &b->d_fin, R)); A(dalloc(b, &b->d_mism, b->mism_cap)); A(dalloc(b, &b->d_fb, b->fb_cap)); A(dalloc(b, &b->d_sort_list, R)); A(dalloc(b, &b->d_fc, 1));
+  A(dalloc(b, &b->d_fin, R)); A(dalloc(b, &b->d_mism, b->mism_cap)); A(dalloc(b, &b->d_fb, b->fb_cap)); A(dalloc(b, &b->d_sort_list, R)); A(dalloc(b, &b->d_long_list, R)); A(dalloc(b, &b->d_huge_list, R)); A(dalloc(b, &b->d_fc, 1));
   A(slab_commit(b));
-  A(cudaMallocHost((void**)&b->h_small, 32 * sizeof(u64)));
+  A(cudaMallocHost((void**)&b->h_small, 48 * sizeof(u64)));
   for (auto& evt : b->ev) A(cudaEventCreate(&evt));
   if (e != cudaSuccess) { std::string m = std::string("batch allocation: ") + cudaGetErrorString(e); bmbs_batch_free(b); return fail(BMBS_ERR_CUDA, m); }
   v.slot_cap = cand_cap;
@@ -607,8 +607,10 @@ extern "C" int bmbs_batch_finish(bmbs_batch* b) {
   CU(cudaMemsetAsync(b->d_fc, 0, sizeof(FinCounters), s));
   CU(cudaEventRecord(b->ev[9], s));
   if (n > 0) {
-    finish_se<<<(n + 127) / 128, 128, 0, s>>>(b->copy->view, b->v, b->d_fin, b->d_mism, (u32)b->mism_cap, b->d_fb, (u32)b->fb_cap, b->d_sort_list, b->d_fc); ++b->launches;
-    finish_sorted<<<b->sm_count * 4, 128, 0, s>>>(b->copy->view, b->v, b->d_fin, b->d_mism, (u32)b->mism_cap, b->d_fb, (u32)b->fb_cap, b->d_sort_list, b->d_fc); ++b->launches;
+    finish_se<<<(n + 127) / 128, 128, 0, s>>>(b->copy->view, b->v, b->d_fin, b->d_mism, (u32)b->mism_cap, b->d_long_list, b->d_huge_list, b->d_sort_list, b->d_fc); ++b->launches;
+    finish_huge<<<b->sm_count * 2, 256, 0, s>>>(b->copy->view, b->v, b->d_fin, b->d_mism, (u32)b->mism_cap, b->d_fb, (u32)b->fb_cap, b->d_huge_list, b->d_sort_list, b->d_fc); ++b->launches;
+    finish_long<<<b->sm_count * 12, 128, 0, s>>>(b->copy->view, b->v, b->d_fin, b->d_mism, (u32)b->mism_cap, b->d_fb, (u32)b->fb_cap, b->d_long_list, b->d_sort_list, b->d_fc); ++b->launches;
+    finish_sorted<<<b->sm_count * 6, 32 * FIN_SORT_WARPS, 0, s>>>(b->copy->view, b->v, b->d_fin, b->d_mism, (u32)b->mism_cap, b->d_fb, (u32)b->fb_cap, b->d_sort_list, b->d_fc); ++b->launches;
   }
   CU(cudaEventRecord(b->ev[10], s));
   CU(cudaMemcpyAsync(b->h_small + 16, b->d_fc, sizeof(FinCounters), cudaMemcpyDeviceToHost, s));
@@ -701,6 +703,23 @@ extern "C" int bmbs_batch_launches(bmbs_batch* b) { return b ? b->launches : 0; 
 
 extern "C" void* bmbs_pinned_alloc(size_t bytes) { void* p = nullptr; return cudaMallocHost(&p, bytes ? bytes : 1) == cudaSuccess ? p : nullptr; }
 extern "C" void bmbs_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+
+// test entry: the order std::sort by vote (descending) leaves lists of <= 2048 votes (each < 32) in, by the warp routine of
+// the device finishing (warp_replay_partitions + stable final pass); ok[i] = 0 when the replay gave up (depth limit)
+extern "C" int bmbs_debug_sort_order(int dev, const uint32_t* votes, const uint32_t* offsets, uint32_t n_lists, uint16_t* order, int* ok) {
+  if (!votes || !offsets || !order || !ok) return fail(BMBS_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(dev));
+  const size_t total = offsets[n_lists];
+  for (uint32_t i = 0; i < n_lists; ++i) if (offsets[i + 1] - offsets[i] > (uint32_t)FIN_SORT_CAP) return fail(BMBS_ERR_ARG, "list longer than the replay capacity");
+  u32 *d_v = nullptr, *d_o = nullptr; unsigned short* d_ord = nullptr; int* d_ok = nullptr;
+  CU(cudaMalloc(&d_v, total * 4 + 16)); CU(cudaMalloc(&d_o, (size_t)(n_lists + 1) * 4)); CU(cudaMalloc(&d_ord, total * 2 + 16)); CU(cudaMalloc(&d_ok, (size_t)n_lists * 4 + 16));
+  CU(cudaMemcpy(d_v, votes, total * 4, cudaMemcpyHostToDevice)); CU(cudaMemcpy(d_o, offsets, (size_t)(n_lists + 1) * 4, cudaMemcpyHostToDevice));
+  debug_sort_order<<<148 * 2, 32 * FIN_SORT_WARPS>>>(d_v, d_o, n_lists, d_ord, d_ok);
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(order, d_ord, total * 2, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(ok, d_ok, (size_t)n_lists * 4, cudaMemcpyDeviceToHost));
+  cudaFree(d_v); cudaFree(d_o); cudaFree(d_ord); cudaFree(d_ok);
+  return BMBS_OK;
+}
 
 // ================================================================================================ one-call forms
 namespace {

@@ -1955,7 +1955,7 @@ __global__ void finalize_reads(BatchView b) {
 //     BMBS_FIN_DP: the banded affine DP (refine_dp) decides.
 //   * coordinates (Schema.cpp:12596-12650, :9188-9244): strand, chromosome, 1-based POS, and the drop of hits that run over
 //     the end of their chromosome.
-struct FinCounters { unsigned long long mism_used, fb_used, n_sorted, n_host, n_dp, n_unc_idx, n_unc_sbd, pad; };
+struct FinCounters { unsigned long long mism_used, fb_used, n_sorted, n_host, n_dp, n_unc_idx, n_unc_sbd, n_long, cursor_long, cursor_sorted, n_huge, cursor_huge, pad[4]; };
 
 struct PlacedDev { u32 chrom; u64 pos; u32 reverse; bool off; };
 __device__ __forceinline__ PlacedDev place_hit(const DevIndex& ix, u64 site, long long start_site, u64 end_site) {
@@ -1978,6 +1978,10 @@ __device__ __forceinline__ PlacedDev place_hit(const DevIndex& ix, u64 site, lon
 constexpr int FIN_MM = 32;           // mismatch positions kept per read (err <= 31)
 constexpr u32 FIN_INF = 0xFFFFu;
 constexpr int FIN_SORT_CAP = 2048;   // longest window list finish_sorted replays (one warp, keys in shared memory)
+constexpr int FIN_SORT_WARPS = 3;    // warps per block there: 12 KB of shared memory each
+constexpr u32 FIN_SHORT = 16;        // window lists up to this long are finished by their own thread (std::sort = stable insertion sort)
+constexpr u32 FIN_THREAD_MAX = 64;    // up to here the read's own thread reduces the list (finish_se)
+constexpr u32 FIN_WARP_MAX = 1024;   // up to here a warp reduces the list (finish_long), beyond a block (finish_huge)
 
 __device__ __forceinline__ bmbs_final fin_blank(u32 k) {
   bmbs_final o; o.site = 0; o.chrom_pos = 0; o.aux_first = 0; o.end_site = 0; o.nm = 0; o.sbd = 255; o.status = BMBS_FIN_UNMAPPED;
@@ -1990,52 +1994,60 @@ __device__ __forceinline__ void fin_set_place(bmbs_final& o, const PlacedDev& p)
   o.chrom_pos = ((u64)p.chrom << 40) | (p.pos & 0xFFFFFFFFFFull);
   o.flags |= (uint8_t)p.reverse;
 }
+__device__ __forceinline__ u64 end_abs(const bmbs_cand& x) { return x.site + (u64)(long long)x.end_site; }
 
-// the diagonal of window `site` that starts at window position `start`, against the read: number of mismatches (read T on
-// genome C is a match) and their read positions, ascending, into mm[] (the first FIN_MM).  The whole warp works on one read.
-__device__ __forceinline__ u32 warp_diagonal_mismatches(const DevIndex& ix, const u32* __restrict__ codes, u64 site, int start, u32 L, unsigned short* mm, int lane) {
-  u32 count = 0;
-  for (u32 base = 0; base < L; base += 32) {
-    const u32 i = base + lane;
-    bool mis = false;
-    if (i < L) {
-      const int t = read_code(codes, (int)i);
-      const int p = strand_base(ix, site + (u64)(long long)start + i);
-      mis = t != p && !(t == 3 && p == 1);
-    }
-    const u32 m = __ballot_sync(0xffffffffu, mis);
-    if (mis) { const u32 at = count + __popc(m & ((1u << lane) - 1u)); if (at < (u32)FIN_MM) mm[at] = (unsigned short)i; }
-    count += __popc(m);
-  }
-  return count;
+// Mismatches of read bases [32 ch, 32 ch + 32) against the double-strand sequence from `pos` on, one bit per base: the read's
+// bit-planes (pack_reads) against two funnel-shifted words of the genome planes; read T on genome C is a match, a read base
+// that is not A/C/G/T matches nothing.
+__device__ __forceinline__ u32 diagonal_mismatch_bits(const DevIndex& ix, const uint4* __restrict__ rpl, u64 pos, u32 ch, u32 L) {
+  const uint4 r = rpl[ch];
+  const u64 p = pos + 32ull * ch;
+  const uint2 g0 = __ldg(ix.planes + (p >> 5)), g1 = __ldg(ix.planes + (p >> 5) + 1);
+  const unsigned sh = (unsigned)p & 31u;
+  const u32 glo = __funnelshift_r(g0.x, g1.x, sh), ghi = __funnelshift_r(g0.y, g1.y, sh);
+  const u32 same = ~(r.x ^ glo) & ~(r.y ^ ghi), t_on_c = r.x & r.y & glo & ~ghi;
+  const u32 left = L - 32u * ch, valid = left >= 32u ? 0xFFFFFFFFu : (1u << left) - 1u;
+  return ~((same | t_on_c) & ~r.z) & valid;
 }
 
-// The chosen window -> the read's record (every lane computes the same `o`); returns the number of mismatch positions left in mm[].
-__device__ __forceinline__ u32 warp_finish_hit(const DevIndex& ix, const BatchView& b, int r, u32 L, u32 k, const bmbs_cand x, unsigned short* mm, int lane, bmbs_final& o) {
+// The chosen window -> the read's record, by one thread: try_cigar_without_path on the window's diagonal that ends at end_site
+// (exactly err mismatches = ungapped, their read positions into mm[]), then the coordinates.  Returns the number of positions.
+__device__ __forceinline__ u32 finish_hit(const DevIndex& ix, const BatchView& b, int r, u32 L, u32 k, const bmbs_cand x, unsigned short* mm, bmbs_final& o) {
   o.site = x.site; o.end_site = x.end_site; o.nm = (uint8_t)x.err;
   const int start = (int)x.end_site - (int)L + 1;
   u32 mm_n = 0;
   if (x.err != 0) {
     bool ok = start >= 0 && window_inside(ix, x.site, (u64)L + 2ull * k);
-    if (ok) { mm_n = warp_diagonal_mismatches(ix, b.codes + code_word_offset(b.offsets, r), x.site, start, L, mm, lane); ok = mm_n == x.err; }
+    if (ok) {
+      const uint4* rpl = b.rplanes + plane_chunk_offset(b.offsets, r);
+      for (u32 ch = 0; ch * 32u < L && mm_n <= x.err; ++ch) {
+        u32 mis = diagonal_mismatch_bits(ix, rpl, x.site + (u64)(long long)start, ch, L);
+        while (mis) { const u32 bit = (u32)__ffs(mis) - 1u; mis &= mis - 1u; if (mm_n < (u32)FIN_MM) mm[mm_n] = (unsigned short)(32u * ch + bit); ++mm_n; }
+      }
+      ok = mm_n == x.err;
+    }
     if (!ok) { o.status = BMBS_FIN_DP; return 0; }
   }
   fin_set_place(o, place_hit(ix, x.site, start, (u64)(long long)x.end_site));
   return o.status == BMBS_FIN_UNIQUE ? mm_n : 0u;
 }
 
+// One thread per read.  Reads that seeding resolved and window lists of up to FIN_THREAD_MAX entries are finished here (two
+// passes over the list; up to FIN_SHORT windows in std::sort's stable order, beyond that when the order cannot matter, else
+// the read goes to finish_sorted); longer lists go to finish_long / finish_huge.
 __global__ void __launch_bounds__(128) finish_se(DevIndex ix, BatchView b, bmbs_final* __restrict__ fin, unsigned short* __restrict__ mism, u32 mism_cap,
-                                                 bmbs_cand* __restrict__ fb_cand, u32 fb_cap, u32* __restrict__ sort_list, FinCounters* __restrict__ fc) {
-  __shared__ unsigned short s_mm[4][32][FIN_MM];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+                                                 u32* __restrict__ long_list, u32* __restrict__ huge_list, u32* __restrict__ sort_list, FinCounters* __restrict__ fc) {
+  __shared__ unsigned short s_mm[128][FIN_MM + 1];
+  const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = r < b.n_reads;
   bmbs_read_result res; res.state = BMBS_NONE; res.first_cand = 0; res.n_cand = 0; res.site = 0; res.one_mismatch_pos = 0; res.is_multiple_map = 0;
   u32 L = 0, k = 0;
   if (live) { res = b.out_res[r]; L = b.len[r]; k = b.kk[r]; }
   bmbs_final o = fin_blank(k);
-  u32 my_mm = 0;                                       // mismatch positions of my read waiting in s_mm[w][lane]
-  bool to_sort = false;
+  unsigned short* mm = s_mm[threadIdx.x];
+  u32 my_mm = 0;
+  bool is_long = false, to_sort = false;
   if (live) {
     if (res.state == BMBS_EXACT_UNIQUE) {
       o.site = res.site; o.end_site = (int16_t)(L - 1); o.mapq_fixed = 42;
@@ -2043,7 +2055,7 @@ __global__ void __launch_bounds__(128) finish_se(DevIndex ix, BatchView b, bmbs_
     } else if (res.state == BMBS_ONE_MISMATCH) {
       o.site = res.site; o.end_site = (int16_t)(L - 1); o.nm = 1;
       fin_set_place(o, place_hit(ix, res.site, 0, L - 1));
-      if (o.status == BMBS_FIN_UNIQUE) { s_mm[w][lane][0] = (unsigned short)res.one_mismatch_pos; my_mm = 1; }
+      if (o.status == BMBS_FIN_UNIQUE) { mm[0] = (unsigned short)res.one_mismatch_pos; my_mm = 1; }
     } else if (res.state == BMBS_MULTI_EXACT) {
       if (!b.amb_out) o.status = BMBS_FIN_AMBIGUOUS;
       else {      // the first located row (suffix-array order) that stays inside a chromosome, MAPQ 1 (Schema.cpp:27216-27245)
@@ -2053,138 +2065,350 @@ __global__ void __launch_bounds__(128) finish_se(DevIndex ix, BatchView b, bmbs_
           if (!p.off) { o.site = site; o.end_site = (int16_t)(L - 1); o.mapq_fixed = 1; o.flags |= BMBS_FINF_AMBIGUOUS; fin_set_place(o, p); break; }
         }
       }
-    }
-  }
-  u32 todo = __ballot_sync(0xffffffffu, live && res.state == BMBS_VERIFY);
-  while (todo) {
-    const int src = __ffs(todo) - 1; todo &= todo - 1;
-    const u32 first = __shfl_sync(0xffffffffu, res.first_cand, src), n = __shfl_sync(0xffffffffu, res.n_cand, src);
-    const u32 rL = __shfl_sync(0xffffffffu, L, src), rk = __shfl_sync(0xffffffffu, k, src);
-    const int rr = blockIdx.x * blockDim.x + w * 32 + src;
-    const bmbs_cand* __restrict__ c = b.out_cand + first;
-    bmbs_final q = fin_blank(rk);
-    u32 mm_n = 0; bool sort_it = false;
-    // pass 1: smallest err
-    u32 m = FIN_INF;
-    for (u32 j = lane; j < n; j += 32) m = min(m, (u32)c[j].err);
-    m = __reduce_min_sync(0xffffffffu, m);
-    if (m != FIN_INF) {
-      // pass 2: over the hits with that err -- their best vote, the first of them
-      u32 vstar = 0, i_m = 0xFFFFFFFFu;
-      for (u32 j = lane; j < n; j += 32) { const bmbs_cand x = c[j]; if (x.err == m) { vstar = max(vstar, x.vote); i_m = min(i_m, j); } }
-      vstar = __reduce_max_sync(0xffffffffu, vstar); i_m = __reduce_min_sync(0xffffffffu, i_m);
-      const bmbs_cand cm = c[i_m];
-      const u64 e0 = cm.site + (u64)(long long)cm.end_site;
-      // pass 3: do they all end at the same place; the top-voted ones among them; the smallest err above them (A) and beside
-      // them (B: same vote, larger err)
-      u32 amb = 0, cnt_top = 0, i_top = 0xFFFFFFFFu, A = FIN_INF, B = FIN_INF;
-      for (u32 j = lane; j < n; j += 32) {
-        const bmbs_cand x = c[j];
-        if (x.err == m) { amb |= (u32)((x.site + (u64)(long long)x.end_site) != e0); if (x.vote == vstar) { ++cnt_top; i_top = min(i_top, j); } }
-        else if (x.vote > vstar) A = min(A, (u32)x.err);
-        else if (x.vote == vstar) B = min(B, (u32)x.err);
-      }
-      amb = __any_sync(0xffffffffu, amb != 0) ? 1u : 0u;
-      cnt_top = __reduce_add_sync(0xffffffffu, cnt_top); i_top = __reduce_min_sync(0xffffffffu, i_top);
-      A = __reduce_min_sync(0xffffffffu, A); B = __reduce_min_sync(0xffffffffu, B);
-      if (amb && !b.amb_out) q.status = BMBS_FIN_AMBIGUOUS;
+    } else if (res.state == BMBS_VERIFY) {
+      const u32 n = res.n_cand;
+      if (n > FIN_THREAD_MAX) is_long = true;
       else {
-        u32 before = A;                                 // the running minimum when the best hit is met
-        if (n <= 16) {                                  // insertion sort: equal votes keep their (site) order
-          u32 Bs = FIN_INF;
-          for (u32 j = lane; j < i_top; j += 32) { const bmbs_cand x = c[j]; if (x.vote == vstar) Bs = min(Bs, (u32)x.err); }
-          Bs = __reduce_min_sync(0xffffffffu, Bs);
-          before = min(A, Bs);
-        } else if (cnt_top > 1 && (m != 0 || amb)) { sort_it = true; if (lane == 0) atomicAdd(&fc->n_unc_idx, 1ull); }   // which of the equal hits comes first decides the window
-        else if (!amb && B < A) { sort_it = true; if (lane == 0) atomicAdd(&fc->n_unc_sbd, 1ull); }                      // a worse hit with the same vote may or may not come first
-        if (!sort_it) {
-          if (amb) { q.sbd = 0; q.flags |= BMBS_FINF_AMBIGUOUS; }
-          else q.sbd = (uint8_t)(before == FIN_INF ? 255u : min(before - m, 255u));
-          mm_n = warp_finish_hit(ix, b, rr, rL, rk, c[i_top], &s_mm[w][src][0], lane, q);
+        const bmbs_cand* __restrict__ c = b.out_cand + res.first_cand;
+        // pass 1: smallest err and, among the hits that have it, the largest vote -- one minimum over (err, ~vote)
+        u32 key = 0xFFFFFFFFu;
+        for (u32 j = 0; j < n; ++j) { const bmbs_cand x = c[j]; key = min(key, (u32)x.err << 16 | (0xFFFFu - min(x.vote, 0xFFFFu))); }
+        const u32 m = key >> 16, vstar = 0xFFFFu - (key & 0xFFFFu);
+        if (n && m != FIN_INF) {
+          // pass 2: the first top-voted hit with that err and how many there are, whether all hits with that err end at the same
+          // place, the smallest err voted higher (A), voted the same (B) and voted the same ahead of the hit (Bs)
+          u32 i_top = 0xFFFFFFFFu, cnt_top = 0, A = FIN_INF, B = FIN_INF, Bs = FIN_INF;
+          u64 e_min = ~0ull, e_max = 0;
+          for (u32 j = 0; j < n; ++j) {
+            const bmbs_cand y = c[j];
+            if (y.err == m) { const u64 e = end_abs(y); e_min = min(e_min, e); e_max = max(e_max, e); if (y.vote == vstar) { ++cnt_top; if (i_top == 0xFFFFFFFFu) i_top = j; } }
+            else if (y.vote > vstar) A = min(A, (u32)y.err);
+            else if (y.vote == vstar) { B = min(B, (u32)y.err); if (i_top == 0xFFFFFFFFu) Bs = min(Bs, (u32)y.err); }
+          }
+          const bool amb = e_min != e_max;
+          if (amb && !b.amb_out) o.status = BMBS_FIN_AMBIGUOUS;
+          else {
+            u32 before = A;
+            bool sort_it = false;
+            if (n <= FIN_SHORT) before = min(A, Bs);          // std::sort is a stable insertion sort: equal votes stay in site order
+            else if (cnt_top > 1 && (m != 0 || amb)) { sort_it = true; atomicAdd(&fc->n_unc_idx, 1ull); }
+            else if (!amb && B < A) { sort_it = true; atomicAdd(&fc->n_unc_sbd, 1ull); }
+            if (sort_it) to_sort = true;
+            else {
+              if (amb) { o.sbd = 0; o.flags |= BMBS_FINF_AMBIGUOUS; }
+              else o.sbd = (uint8_t)(before == FIN_INF ? 255u : min(before - m, 255u));
+              my_mm = finish_hit(ix, b, r, L, k, c[i_top], mm, o);
+            }
+          }
         }
       }
     }
-    if (lane == src) {
-      if (!sort_it) { o = q; my_mm = mm_n; }
-      else if (n <= (u32)FIN_SORT_CAP) to_sort = true;
-      else { o.status = BMBS_FIN_HOST; o.site = res.is_multiple_map; o.n_aux = n; }
-    }
-    __syncwarp();
   }
-  // reads whose window order has to be replayed: their record comes from finish_sorted
-  {
+  {   // window lists whose order decides: finish_sorted
     const u32 ms = __ballot_sync(0xffffffffu, to_sort);
     u32 base = 0;
     if (lane == 0 && ms) base = (u32)atomicAdd(&fc->n_sorted, (unsigned long long)__popc(ms));
     base = __shfl_sync(0xffffffffu, base, 0);
     if (to_sort) sort_list[base + __popc(ms & ((1u << lane) - 1u))] = (u32)r;
   }
-  const bool host = live && o.status == BMBS_FIN_HOST;
+  {   // longer lists: one warp each in finish_long, one block each in finish_huge
+    const bool is_huge = is_long && res.n_cand > FIN_WARP_MAX;
+    const u32 ml = __ballot_sync(0xffffffffu, is_long && !is_huge), mh = __ballot_sync(0xffffffffu, is_huge);
+    u32 base = 0, hbase = 0;
+    if (lane == 0 && ml) base = (u32)atomicAdd(&fc->n_long, (unsigned long long)__popc(ml));
+    if (lane == 0 && mh) hbase = (u32)atomicAdd(&fc->n_huge, (unsigned long long)__popc(mh));
+    base = __shfl_sync(0xffffffffu, base, 0); hbase = __shfl_sync(0xffffffffu, hbase, 0);
+    if (is_long && !is_huge) long_list[base + __popc(ml & ((1u << lane) - 1u))] = (u32)r;
+    if (is_huge) huge_list[hbase + __popc(mh & ((1u << lane) - 1u))] = (u32)r;
+  }
   {
-    const u32 mdp = __ballot_sync(0xffffffffu, live && o.status == BMBS_FIN_DP), mh = __ballot_sync(0xffffffffu, host);
-    if (lane == 0) { if (mdp) atomicAdd(&fc->n_dp, (unsigned long long)__popc(mdp)); if (mh) atomicAdd(&fc->n_host, (unsigned long long)__popc(mh)); }
+    const u32 mdp = __ballot_sync(0xffffffffu, live && o.status == BMBS_FIN_DP);
+    if (lane == 0 && mdp) atomicAdd(&fc->n_dp, (unsigned long long)__popc(mdp));
   }
-  // one reservation per warp for the mismatch positions, one for the window lists handed back to the host
-  u32 inc_mm = my_mm, inc_fb = host ? o.n_aux : 0u;
+  // one reservation per warp for the mismatch positions
+  u32 inc_mm = my_mm;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const u32 t = __shfl_up_sync(0xffffffffu, inc_mm, d), u = __shfl_up_sync(0xffffffffu, inc_fb, d);
-    if (lane >= d) { inc_mm += t; inc_fb += u; }
-  }
-  const u32 tot_mm = __shfl_sync(0xffffffffu, inc_mm, 31), tot_fb = __shfl_sync(0xffffffffu, inc_fb, 31);
-  unsigned long long base_mm = 0, base_fb = 0;
-  if (lane == 0) { if (tot_mm) base_mm = atomicAdd(&fc->mism_used, (unsigned long long)tot_mm); if (tot_fb) base_fb = atomicAdd(&fc->fb_used, (unsigned long long)tot_fb); }
-  base_mm = __shfl_sync(0xffffffffu, base_mm, 0); base_fb = __shfl_sync(0xffffffffu, base_fb, 0);
+  for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, inc_mm, d); if (lane >= d) inc_mm += t; }
+  const u32 tot_mm = __shfl_sync(0xffffffffu, inc_mm, 31);
+  unsigned long long base_mm = 0;
+  if (lane == 0 && tot_mm) base_mm = atomicAdd(&fc->mism_used, (unsigned long long)tot_mm);
+  base_mm = __shfl_sync(0xffffffffu, base_mm, 0);
   if (my_mm) {
     const unsigned long long at = base_mm + inc_mm - my_mm;
     o.aux_first = (u32)at; o.n_aux = my_mm;
-    if (at + my_mm <= mism_cap) for (u32 j = 0; j < my_mm; ++j) mism[at + j] = s_mm[w][lane][j];
+    if (at + my_mm <= mism_cap) for (u32 j = 0; j < my_mm; ++j) mism[at + j] = mm[j];
   }
-  if (host) {
-    const unsigned long long at = base_fb + inc_fb - o.n_aux;
-    o.aux_first = (u32)at;
-    if (at + o.n_aux <= fb_cap) for (u32 j = 0; j < o.n_aux; ++j) fb_cand[at + j] = b.out_cand[res.first_cand + j];
-  }
-  if (live && !to_sort) fin[r] = o;
+  if (live && !is_long && !to_sort) fin[r] = o;
 }
 
-// One warp per read of sort_list: the window list as (vote << 16 | position) keys in shared memory, lane 0 replays std::sort,
-// then the reference's walk in that order -- the first window with the smallest err is the hit, the smallest err in front of it
-// is where the running minimum stood (second_best_diff), a later window with the same err and another end makes it ambiguous.
-__global__ void __launch_bounds__(128) finish_sorted(DevIndex ix, BatchView b, bmbs_final* __restrict__ fin, unsigned short* __restrict__ mism, u32 mism_cap,
+// what a warp leaves behind for its read: the record, its mismatch positions, or the whole window list for the host
+__device__ __forceinline__ void fin_store(const BatchView& b, int r, bmbs_final o, u32 mm_n, const unsigned short* mm, const bmbs_cand* __restrict__ c, u32 n,
+                                          bmbs_final* __restrict__ fin, unsigned short* __restrict__ mism, u32 mism_cap, bmbs_cand* __restrict__ fb_cand, u32 fb_cap,
+                                          FinCounters* __restrict__ fc, int lane) {
+  unsigned long long at = 0;
+  if (o.status == BMBS_FIN_HOST) {
+    if (lane == 0) { at = atomicAdd(&fc->fb_used, (unsigned long long)n); atomicAdd(&fc->n_host, 1ull); }
+    at = __shfl_sync(0xffffffffu, at, 0);
+    o.aux_first = (u32)at; o.n_aux = n;
+    if (at + n <= fb_cap) for (u32 j = lane; j < n; j += 32) fb_cand[at + j] = c[j];
+  } else if (mm_n) {
+    if (lane == 0) at = atomicAdd(&fc->mism_used, (unsigned long long)mm_n);
+    at = __shfl_sync(0xffffffffu, at, 0);
+    o.aux_first = (u32)at; o.n_aux = mm_n;
+    if (at + mm_n <= mism_cap && (u32)lane < mm_n) mism[at + lane] = mm[lane];
+  }
+  if (lane == 0) { if (o.status == BMBS_FIN_DP) atomicAdd(&fc->n_dp, 1ull); fin[r] = o; }
+}
+
+// The group of threads that works on one long window list: a warp (lists of up to FIN_WARP_MAX windows) or a whole block.
+struct WarpGroup {
+  static constexpr u32 SIZE = 32;
+  __device__ __forceinline__ static u32 id() { return threadIdx.x & 31u; }
+  __device__ __forceinline__ static u32 rmin(u32 v, u32*) { return __reduce_min_sync(0xffffffffu, v); }
+  __device__ __forceinline__ static u32 rmax(u32 v, u32*) { return __reduce_max_sync(0xffffffffu, v); }
+  __device__ __forceinline__ static u32 radd(u32 v, u32*) { return __reduce_add_sync(0xffffffffu, v); }
+  __device__ __forceinline__ static void sync() { __syncwarp(); }
+};
+struct BlockGroup {      // 256 threads
+  static constexpr u32 SIZE = 256;
+  __device__ __forceinline__ static u32 id() { return threadIdx.x; }
+  template <int OP> __device__ __forceinline__ static u32 red(u32 v, u32* sh) {
+    v = OP == 0 ? __reduce_min_sync(0xffffffffu, v) : OP == 1 ? __reduce_max_sync(0xffffffffu, v) : __reduce_add_sync(0xffffffffu, v);
+    __syncthreads();
+    if ((threadIdx.x & 31u) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    u32 t = sh[threadIdx.x & 7u];
+    t = OP == 0 ? __reduce_min_sync(0xffffffffu, t) : OP == 1 ? __reduce_max_sync(0xffffffffu, t) : __reduce_add_sync(0xffffffffu, (threadIdx.x & 31u) < 8u ? t : 0u);
+    return t;
+  }
+  __device__ __forceinline__ static u32 rmin(u32 v, u32* sh) { return red<0>(v, sh); }
+  __device__ __forceinline__ static u32 rmax(u32 v, u32* sh) { return red<1>(v, sh); }
+  __device__ __forceinline__ static u32 radd(u32 v, u32* sh) { return red<2>(v, sh); }
+  __device__ __forceinline__ static void sync() { __syncthreads(); }
+};
+
+// Order-free part of the reduction over one window list, by a group of threads: four passes of reductions say what the
+// outcome is whenever the order among equal votes cannot change it -- it cannot when the best hit is the only top-voted one
+// with its err (or err 0: every such window is the same alignment) and no hit of the same vote has an err below everything
+// voted higher.  Returns 0: o is the read's record up to the chosen window `xt` (caller finishes the hit when o.status is
+// BMBS_FIN_UNIQUE), 1: the order decides.
+template <class G>
+__device__ __forceinline__ int reduce_order_free(const BatchView& b, const bmbs_cand* __restrict__ c, u32 n, bmbs_final& o, bmbs_cand& xt, u32* sh, FinCounters* fc) {
+  const u32 id = G::id();
+  u32 m = FIN_INF;
+  for (u32 j = id; j < n; j += G::SIZE) m = min(m, (u32)c[j].err);
+  m = G::rmin(m, sh);
+  if (m == FIN_INF) return 0;                                      // nothing within k: unmapped
+  u32 vstar = 0;
+  for (u32 j = id; j < n; j += G::SIZE) { const bmbs_cand x = c[j]; if (x.err == m) vstar = max(vstar, x.vote); }
+  vstar = G::rmax(vstar, sh);
+  // the top-voted hits with that err and the first of them; the smallest err voted higher (A) and voted the same (B)
+  u32 cnt_top = 0, i_top = 0xFFFFFFFFu, A = FIN_INF, B = FIN_INF;
+  for (u32 j = id; j < n; j += G::SIZE) {
+    const bmbs_cand x = c[j];
+    if (x.err == m) { if (x.vote == vstar) { ++cnt_top; i_top = min(i_top, j); } }
+    else if (x.vote > vstar) A = min(A, (u32)x.err);
+    else if (x.vote == vstar) B = min(B, (u32)x.err);
+  }
+  cnt_top = G::radd(cnt_top, sh); i_top = G::rmin(i_top, sh); A = G::rmin(A, sh); B = G::rmin(B, sh);
+  xt = c[i_top];
+  const u64 e0 = end_abs(xt);
+  u32 amb = 0;
+  for (u32 j = id; j < n; j += G::SIZE) { const bmbs_cand x = c[j]; if (x.err == m) amb |= (u32)(end_abs(x) != e0); }
+  amb = G::rmax(amb, sh);
+  if (amb && !b.amb_out) { o.status = BMBS_FIN_AMBIGUOUS; return 0; }
+  if (cnt_top > 1 && (m != 0 || amb)) { if (id == 0) atomicAdd(&fc->n_unc_idx, 1ull); return 1; }   // which of the equal hits comes first decides the window
+  if (!amb && B < A) { if (id == 0) atomicAdd(&fc->n_unc_sbd, 1ull); return 1; }                    // a worse hit with the same vote may or may not come first
+  if (amb) { o.sbd = 0; o.flags |= BMBS_FINF_AMBIGUOUS; }
+  else o.sbd = (uint8_t)(A == FIN_INF ? 255u : min(A - m, 255u));
+  o.status = BMBS_FIN_UNIQUE;                                      // provisional: finish_hit decides
+  return 0;
+}
+
+// One warp per read of long_list (window lists of FIN_SHORT+1 .. FIN_WARP_MAX entries; reads taken from a shared cursor).
+// Reads whose outcome the order cannot change are finished here, the others go to finish_sorted.
+__global__ void __launch_bounds__(128) finish_long(DevIndex ix, BatchView b, bmbs_final* __restrict__ fin, unsigned short* __restrict__ mism, u32 mism_cap,
+                                                   bmbs_cand* __restrict__ fb_cand, u32 fb_cap, const u32* __restrict__ long_list, u32* __restrict__ sort_list,
+                                                   FinCounters* __restrict__ fc) {
+  __shared__ unsigned short s_mm[4][FIN_MM + 1];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const u32 n_list = (u32)fc->n_long;
+  for (;;) {
+    u32 i = 0;
+    if (lane == 0) i = (u32)atomicAdd(&fc->cursor_long, 1ull);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= n_list) break;
+    const int r = (int)long_list[i];
+    const bmbs_read_result res = b.out_res[r];
+    const u32 n = res.n_cand, L = b.len[r], k = b.kk[r];
+    const bmbs_cand* __restrict__ c = b.out_cand + res.first_cand;
+    bmbs_final o = fin_blank(k);
+    bmbs_cand xt; xt.site = 0; xt.vote = 0; xt.end_site = 0; xt.err = 0;
+    u32 mm_n = 0;
+    const int sort_it = reduce_order_free<WarpGroup>(b, c, n, o, xt, nullptr, fc);
+    if (sort_it) {
+      if (lane == 0) sort_list[atomicAdd(&fc->n_sorted, 1ull)] = (u32)r;       // n <= FIN_WARP_MAX <= FIN_SORT_CAP
+    } else {
+      if (o.status == BMBS_FIN_UNIQUE) {
+        if (lane == 0) mm_n = finish_hit(ix, b, r, L, k, xt, s_mm[w], o);       // lane 0 holds the record; the others help with the copies
+        mm_n = __shfl_sync(0xffffffffu, mm_n, 0);
+        o.status = (uint8_t)__shfl_sync(0xffffffffu, (u32)o.status, 0);
+      }
+      __syncwarp();
+      fin_store(b, r, o, mm_n, s_mm[w], c, n, fin, mism, mism_cap, fb_cand, fb_cap, fc, lane);
+    }
+    __syncwarp();
+  }
+}
+
+// One block per read of huge_list (more than FIN_WARP_MAX windows -- reads out of high-copy repeats, up to 25 x 1000).  Such a
+// list is beyond the sort replay: when the order decides, the read goes back to the host with its list.
+__global__ void __launch_bounds__(256) finish_huge(DevIndex ix, BatchView b, bmbs_final* __restrict__ fin, unsigned short* __restrict__ mism, u32 mism_cap,
+                                                   bmbs_cand* __restrict__ fb_cand, u32 fb_cap, const u32* __restrict__ huge_list, u32* __restrict__ sort_list, FinCounters* __restrict__ fc) {
+  __shared__ unsigned short s_mm[FIN_MM + 1];
+  __shared__ u32 s_red[8];
+  __shared__ u32 s_i;
+  const u32 n_list = (u32)fc->n_huge;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_i = (u32)atomicAdd(&fc->cursor_huge, 1ull);
+    __syncthreads();
+    const u32 i = s_i;
+    if (i >= n_list) break;
+    const int r = (int)huge_list[i];
+    const bmbs_read_result res = b.out_res[r];
+    const u32 n = res.n_cand, L = b.len[r], k = b.kk[r];
+    const bmbs_cand* __restrict__ c = b.out_cand + res.first_cand;
+    bmbs_final o = fin_blank(k);
+    bmbs_cand xt; xt.site = 0; xt.vote = 0; xt.end_site = 0; xt.err = 0;
+    const int sort_it = reduce_order_free<BlockGroup>(b, c, n, o, xt, s_red, fc);
+    if (sort_it && n <= (u32)FIN_SORT_CAP) {
+      if (threadIdx.x == 0) sort_list[atomicAdd(&fc->n_sorted, 1ull)] = (u32)r;
+    } else if (threadIdx.x < 32) {      // the first warp writes the record
+      const int lane = threadIdx.x;
+      u32 mm_n = 0;
+      if (sort_it) { o = fin_blank(k); o.status = BMBS_FIN_HOST; o.site = res.is_multiple_map; }
+      else if (o.status == BMBS_FIN_UNIQUE) {
+        if (lane == 0) mm_n = finish_hit(ix, b, r, L, k, xt, s_mm, o);
+        mm_n = __shfl_sync(0xffffffffu, mm_n, 0);
+        o.status = (uint8_t)__shfl_sync(0xffffffffu, (u32)o.status, 0);
+      }
+      __syncwarp();
+      fin_store(b, r, o, mm_n, s_mm, c, n, fin, mism, mism_cap, fb_cand, fb_cap, fc, lane);
+    }
+  }
+}
+
+// std::sort's partition phase on key[0..n) (u16: vote << 11 | position in the list), by a whole warp, step for step what
+// bmbs_sort_replay.h does sequentially (that header is checked against std::sort on the CPU; this routine against std::sort
+// through bmbs_debug_sort_order on the GPU).  One unguarded Hoare partition = the t-th element from the left that is not
+// before the pivot swaps with the t-th element from the right that is not after it, for as long as the two have not met
+// (positions untouched by earlier swaps are all the scan ever stops at, so the pairs can be formed up front): both stopper
+// lists are compacted with ballots, the number of swaps T is where the lists cross, the T swaps are independent, and the cut is
+// the first stopper the left scan would meet next.  Ranges of <= 16 are left as they are: the final insertion sort is stable,
+// i.e. equal votes stay in the order the partitions left them, which is all the callers need.
+__device__ __forceinline__ u32 key_vote(unsigned short k) { return (u32)k >> 11; }
+__device__ bool warp_replay_partitions(unsigned short* key, int n, unsigned short* posL, unsigned short* posR, u32* stack, int lane) {
+  if (n <= 16) return true;
+  const u32 lt = (1u << lane) - 1u;
+  int sp = 1;
+  if (lane == 0) stack[0] = (u32)n << 12 | (u32)(2 * (31 - __clz(n))) << 24;
+  __syncwarp();
+  while (sp) {
+    --sp;
+    const u32 e = stack[sp];
+    int first = (int)(e & 0xFFFu), last = (int)((e >> 12) & 0xFFFu), depth = (int)(e >> 24);
+    __syncwarp();
+    while (last - first > 16) {
+      if (depth == 0 || sp >= 31) return false;
+      --depth;
+      const int ia = first + 1, ib = first + (last - first) / 2, ic = last - 1;       // __move_median_to_first
+      const u32 va = key_vote(key[ia]), vb = key_vote(key[ib]), vc = key_vote(key[ic]);
+      int pick;
+      if (va > vb) { if (vb > vc) pick = ib; else if (va > vc) pick = ic; else pick = ia; }
+      else if (va > vc) pick = ia;
+      else if (vb > vc) pick = ic;
+      else pick = ib;
+      __syncwarp();
+      if (lane == 0) { const unsigned short t = key[first]; key[first] = key[pick]; key[pick] = t; }
+      __syncwarp();
+      const u32 vp = key_vote(key[first]);
+      const int lo0 = first + 1, s = last - lo0;
+      int nL = 0, nR = 0;
+      for (int base = 0; base < s; base += 32) {
+        const int o = base + lane;
+        bool isL = false, isR = false;
+        if (o < s) { isL = key_vote(key[lo0 + o]) <= vp; isR = key_vote(key[last - 1 - o]) >= vp; }
+        const u32 mL = __ballot_sync(0xffffffffu, isL), mR = __ballot_sync(0xffffffffu, isR);
+        if (isL) posL[nL + __popc(mL & lt)] = (unsigned short)(lo0 + o);
+        if (isR) posR[nR + __popc(mR & lt)] = (unsigned short)(last - 1 - o);
+        nL += __popc(mL); nR += __popc(mR);
+      }
+      __syncwarp();
+      int T = 0; const int nmin = min(nL, nR);
+      for (int base = 0; base < nmin; base += 32) {
+        const int t = base + lane;
+        const u32 m = __ballot_sync(0xffffffffu, t < nmin && posL[t] < posR[t]);
+        T += __popc(m);
+        if (m != 0xffffffffu) break;
+      }
+      for (int t = lane; t < T; t += 32) { const int i = posL[t], j = posR[t]; const unsigned short x = key[i]; key[i] = key[j]; key[j] = x; }
+      const int cut = min(T < nL ? (int)posL[T] : 0x7fffffff, T >= 1 ? (int)posR[T - 1] : 0x7fffffff);
+      __syncwarp();
+      if (lane == 0) stack[sp] = (u32)cut | (u32)last << 12 | (u32)depth << 24;
+      ++sp;
+      last = cut;
+      __syncwarp();
+    }
+  }
+  return true;
+}
+
+// One warp per read of sort_list: the window list as (vote << 11 | position) keys in shared memory, the partition phase of
+// std::sort replayed, then the reference's walk in the resulting order -- among the hits with the smallest err the one that
+// comes first (largest vote, then earliest place after the partitions) is the hit, the smallest err in front of it is where
+// the running minimum stood (second_best_diff), a hit with the same err and another end makes it ambiguous.
+__global__ void __launch_bounds__(32 * FIN_SORT_WARPS) finish_sorted(DevIndex ix, BatchView b, bmbs_final* __restrict__ fin, unsigned short* __restrict__ mism, u32 mism_cap,
                                                      bmbs_cand* __restrict__ fb_cand, u32 fb_cap, const u32* __restrict__ sort_list, FinCounters* __restrict__ fc) {
-  __shared__ u32 s_key[4][FIN_SORT_CAP];
-  __shared__ unsigned short s_mm[4][FIN_MM];
-  __shared__ int s_ok[4];
+  __shared__ unsigned short s_key[FIN_SORT_WARPS][FIN_SORT_CAP], s_posL[FIN_SORT_WARPS][FIN_SORT_CAP], s_posR[FIN_SORT_WARPS][FIN_SORT_CAP];
+  __shared__ u32 s_stack[FIN_SORT_WARPS][32];
+  __shared__ unsigned short s_mm[FIN_SORT_WARPS][FIN_MM + 1];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const u32 n_list = (u32)fc->n_sorted;
-  const u32 warps = gridDim.x * (blockDim.x >> 5);
-  for (u32 i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_list; i += warps) {
+  for (;;) {
+    u32 i = 0;
+    if (lane == 0) i = (u32)atomicAdd(&fc->cursor_sorted, 1ull);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= n_list) break;
     const int r = (int)sort_list[i];
     const bmbs_read_result res = b.out_res[r];
     const u32 n = res.n_cand, L = b.len[r], k = b.kk[r];
     const bmbs_cand* __restrict__ c = b.out_cand + res.first_cand;
-    u32* key = s_key[w];
-    u32 m = FIN_INF;
-    for (u32 j = lane; j < n; j += 32) { const bmbs_cand x = c[j]; key[j] = (min(x.vote, 0xFFFFu) << 16) | j; m = min(m, (u32)x.err); }
-    m = __reduce_min_sync(0xffffffffu, m);
+    unsigned short* key = s_key[w];
+    u32 m = FIN_INF, vmax = 0;
+    for (u32 j = lane; j < n; j += 32) { const bmbs_cand x = c[j]; key[j] = (unsigned short)((x.vote & 31u) << 11 | j); m = min(m, (u32)x.err); vmax = max(vmax, x.vote); }
+    m = __reduce_min_sync(0xffffffffu, m); vmax = __reduce_max_sync(0xffffffffu, vmax);
     __syncwarp();
-    if (lane == 0) s_ok[w] = sort_replay(key, (int)n) ? 1 : 0;
+    const bool ok = vmax < 32u && warp_replay_partitions(key, (int)n, s_posL[w], s_posR[w], s_stack[w], lane);
     __syncwarp();
     bmbs_final o = fin_blank(k);
     u32 mm_n = 0;
-    if (!s_ok[w]) { o.status = BMBS_FIN_HOST; o.site = res.is_multiple_map; o.n_aux = n; }
+    if (!ok) { o.status = BMBS_FIN_HOST; o.site = res.is_multiple_map; }
     else {
+      // the hit: smallest err, largest vote, earliest place; ahead of it: every larger vote, and the equal votes placed before it
+      u32 vstar = 0;
+      for (u32 j = lane; j < n; j += 32) { const bmbs_cand x = c[j]; if (x.err == m) vstar = max(vstar, x.vote); }
+      vstar = __reduce_max_sync(0xffffffffu, vstar);
       u32 p_hit = 0xFFFFFFFFu;
-      for (u32 p = lane; p < n; p += 32) if (c[key[p] & 0xFFFFu].err == m) p_hit = min(p_hit, p);
+      for (u32 p = lane; p < n; p += 32) { const bmbs_cand x = c[key[p] & 0x7FFu]; if (x.err == m && x.vote == vstar) p_hit = min(p_hit, p); }
       p_hit = __reduce_min_sync(0xffffffffu, p_hit);
-      const bmbs_cand x = c[key[p_hit] & 0xFFFFu];
-      const u64 e0 = x.site + (u64)(long long)x.end_site;
+      const bmbs_cand x = c[key[p_hit] & 0x7FFu];
+      const u64 e0 = end_abs(x);
       u32 before = FIN_INF, amb = 0;
       for (u32 p = lane; p < n; p += 32) {
-        const bmbs_cand y = c[key[p] & 0xFFFFu];
-        if (p < p_hit) before = min(before, (u32)y.err);
-        else if (y.err == m) amb |= (u32)((y.site + (u64)(long long)y.end_site) != e0);
+        const bmbs_cand y = c[key[p] & 0x7FFu];
+        if (y.err == m) amb |= (u32)(end_abs(y) != e0);
+        else if (y.vote > vstar || (y.vote == vstar && p < p_hit)) before = min(before, (u32)y.err);
       }
       before = __reduce_min_sync(0xffffffffu, before);
       amb = __any_sync(0xffffffffu, amb != 0) ? 1u : 0u;
@@ -2192,22 +2416,51 @@ __global__ void __launch_bounds__(128) finish_sorted(DevIndex ix, BatchView b, b
       else {
         if (amb) { o.sbd = 0; o.flags |= BMBS_FINF_AMBIGUOUS; }
         else o.sbd = (uint8_t)(before == FIN_INF ? 255u : min(before - m, 255u));
-        mm_n = warp_finish_hit(ix, b, r, L, k, x, s_mm[w], lane, o);
+        if (lane == 0) mm_n = finish_hit(ix, b, r, L, k, x, s_mm[w], o);
+        mm_n = __shfl_sync(0xffffffffu, mm_n, 0);
+        o.status = (uint8_t)__shfl_sync(0xffffffffu, (u32)o.status, 0);
       }
     }
-    if (lane == 0) {
-      if (mm_n) {
-        const unsigned long long at = atomicAdd(&fc->mism_used, (unsigned long long)mm_n);
-        o.aux_first = (u32)at; o.n_aux = mm_n;
-        if (at + mm_n <= mism_cap) for (u32 j = 0; j < mm_n; ++j) mism[at + j] = s_mm[w][j];
+    __syncwarp();
+    fin_store(b, r, o, mm_n, s_mm[w], c, n, fin, mism, mism_cap, fb_cand, fb_cap, fc, lane);
+    __syncwarp();
+  }
+}
+
+// Test entry (bmbs_debug_sort_order): the order std::sort by vote leaves each list in, through the same warp routine -- the
+// partition phase, then the stable final pass as a counting sort by vote (rank = larger votes + equal votes placed earlier).
+__global__ void __launch_bounds__(32 * FIN_SORT_WARPS) debug_sort_order(const u32* __restrict__ votes, const u32* __restrict__ offsets, u32 n_lists, unsigned short* __restrict__ order, int* __restrict__ okflag) {
+  __shared__ unsigned short s_key[FIN_SORT_WARPS][FIN_SORT_CAP], s_posL[FIN_SORT_WARPS][FIN_SORT_CAP], s_posR[FIN_SORT_WARPS][FIN_SORT_CAP];
+  __shared__ u32 s_stack[FIN_SORT_WARPS][32];
+  __shared__ u32 s_base[FIN_SORT_WARPS][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const u32 warps = gridDim.x * (blockDim.x >> 5);
+  for (u32 i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_lists; i += warps) {
+    const u32 off = offsets[i], n = offsets[i + 1] - off;
+    unsigned short* key = s_key[w];
+    for (u32 j = lane; j < n; j += 32) key[j] = (unsigned short)((votes[off + j] & 31u) << 11 | j);
+    __syncwarp();
+    const bool ok = warp_replay_partitions(key, (int)n, s_posL[w], s_posR[w], s_stack[w], lane);
+    if (lane == 0) okflag[i] = ok ? 1 : 0;
+    // histogram of the votes, first rank of every vote (descending)
+    u32 cnt = 0;
+    for (u32 p = 0; p < n; ++p) cnt += key_vote(key[p]) == (u32)lane;
+    u32 above = 0;
+    for (int v = 31; v >= 0; --v) { const u32 t = __shfl_sync(0xffffffffu, cnt, v); if (v > lane) above += t; }
+    s_base[w][lane] = above;
+    __syncwarp();
+    for (u32 base = 0; base < n; base += 32) {
+      const u32 p = base + lane;
+      const bool live = p < n;
+      const u32 v = live ? key_vote(key[p]) : 32u + (u32)lane;
+      const u32 peers = __match_any_sync(0xffffffffu, v);
+      if (live) {
+        const u32 dest = s_base[w][v] + __popc(peers & ((1u << lane) - 1u));
+        order[off + dest] = key[p] & 0x7FFu;
       }
-      if (o.status == BMBS_FIN_HOST) {
-        const unsigned long long at = atomicAdd(&fc->fb_used, (unsigned long long)n);
-        o.aux_first = (u32)at; atomicAdd(&fc->n_host, 1ull);
-        if (at + n <= fb_cap) for (u32 j = 0; j < n; ++j) fb_cand[at + j] = c[j];
-      }
-      if (o.status == BMBS_FIN_DP) atomicAdd(&fc->n_dp, 1ull);
-      fin[r] = o;
+      __syncwarp();
+      if (live && (peers & ((1u << lane) - 1u)) == 0) s_base[w][v] += __popc(peers);
+      __syncwarp();
     }
     __syncwarp();
   }

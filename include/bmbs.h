@@ -188,6 +188,10 @@ int bmbs_batch_download_final(bmbs_batch* b, bmbs_final* fin, uint16_t* mism, si
  * replayed on the device [3] reads handed back [4] reads marked BMBS_FIN_DP [5] / [6] replayed because the chosen window /
  * second_best_diff depended on the order [7] device time of the finishing kernels, us */
 int bmbs_batch_finish_counters(bmbs_batch* b, uint64_t c[8]);
+/* test entry: the order libstdc++'s std::sort by vote (descending, Schema.cpp:27612) leaves each list
+ * votes[offsets[i] .. offsets[i+1]) in (<= 2048 votes per list, each < 32), computed by the warp routine the finishing uses;
+ * order[] receives original positions, ok[i] = 0 when the replay declined (introsort depth limit) */
+int bmbs_debug_sort_order(int dev, const uint32_t* votes, const uint32_t* offsets, uint32_t n_lists, uint16_t* order, int* ok);
 
 /* ---- CIGAR refinement: the banded affine-gap DP with traceback -----------------------------------
  * Replaces ksw_semi_global_quality_back (ksw.cpp:1850-2045) as fast_recalculate_bs_Cigar calls it (ksw.cpp:2578-3148,

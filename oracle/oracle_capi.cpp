@@ -196,6 +196,16 @@ int orc_finish_se(void* h, const char* seqs, const uint64_t* offs, int n, double
   return w <= mism_cap ? 0 : BMBS_ERR_CAPACITY;
 }
 
+// The order std::sort leaves the reference's 32-byte vote records in (Schema.cpp:27612, comparator :560-563): order[] receives
+// the original positions.  What the device's sort replay (bmbs_debug_sort_order) is compared with.
+void orc_std_sort_order(const uint32_t* votes, uint32_t n, uint32_t* order) {
+  struct Rec { u64 site, vote; uint32_t err; u64 end_site; };
+  std::vector<Rec> v(n);
+  for (uint32_t i = 0; i < n; ++i) v[i] = {i, votes[i], 0, 0};
+  std::sort(v.begin(), v.end(), [](const Rec& a, const Rec& b) { return a.vote > b.vote; });
+  for (uint32_t i = 0; i < n; ++i) order[i] = (uint32_t)v[i].site;
+}
+
 int orc_verify(void* h, const char* seqs, const uint64_t* offs, int n_reads, const uint32_t* read_idx, const uint64_t* sites, size_t n,
                double e_rate, int32_t* end_site, uint32_t* err, int threads) {
   const Index& ix = *(Index*)h;

@@ -28,10 +28,18 @@ def lib():
         L.orc_map_pe.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.orc_map_pe_sensitive.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_size_t), vp]
         L.orc_verify.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_size_t, C.c_double, vp, vp, C.c_int]
+        L.orc_std_sort_order.argtypes = [vp, C.c_uint32, vp]
         L.orc_finish_se.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_int, vp, vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.orc_banded_align.argtypes = [vp, C.c_uint64, C.c_char_p, C.c_char_p] + [C.c_int] * 8 + [C.POINTER(C.c_int)] * 3 + [vp, C.c_int]
         _lib = L
     return _lib
+
+
+def std_sort_order(votes):
+    """positions in the order std::sort (by vote, descending) leaves the reference's vote records in"""
+    votes = np.ascontiguousarray(votes, dtype=np.uint32); order = np.zeros(len(votes), dtype=np.uint32)
+    lib().orc_std_sort_order(votes.ctypes.data, len(votes), order.ctypes.data)
+    return order
 
 
 class OracleIndex:

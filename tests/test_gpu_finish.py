@@ -9,7 +9,7 @@ import pytest
 import bitmapperbs_b200 as B
 from bitmapperbs_b200 import capi, simulate as S
 from conftest import read_fastq
-from oracle_binding import OracleIndex
+from oracle_binding import OracleIndex, std_sort_order
 
 pytestmark = pytest.mark.gpu
 
@@ -91,3 +91,31 @@ def test_finished_records_on_high_copy_repeats(built, tmp_path, amb_out):
         assert_same_final(fin, mism, ofin, omism, res, cand, allow_host=(n > 2048).sum())
     finally:
         ix.close()
+
+
+def test_device_sort_replay_equals_std_sort():
+    """the warp routine that replays std::sort's partitions (finish_sorted) against std::sort itself: 6000 vote lists of 1..2048
+    entries -- random, few distinct values, periodic, sparse, ramps, all equal"""
+    rng = np.random.default_rng(5)
+    lists = []
+    for it in range(6000):
+        n = int(rng.integers(1, 2049)) if it % 10 == 0 else int(rng.integers(1, 200))
+        vr = int(rng.integers(1, 29))
+        mode = it % 6
+        if mode == 0:
+            v = rng.integers(1, vr + 1, size=n)
+        elif mode == 1:
+            v = 1 + (np.arange(n) % vr)
+        elif mode == 2:
+            v = np.where(rng.random(n) < 0.1, rng.integers(1, vr + 1, size=n), 1)
+        elif mode == 3:
+            v = 1 + (vr * np.arange(n) // n)
+        elif mode == 4:
+            v = np.full(n, vr)
+        else:
+            v = 1 + ((vr * np.arange(n)[::-1]) // n)
+        lists.append(v.astype(np.uint32))
+    orders, ok = capi.debug_sort_order(lists)
+    assert ok.all()
+    for v, o in zip(lists, orders):
+        assert np.array_equal(o.astype(np.uint32), std_sort_order(v)), len(v)

@@ -31,7 +31,7 @@ class Scoring(C.Structure):
 
 
 RefineItem = np.dtype([("site", "<u8"), ("seq_off", "<u4"), ("len", "<u2"), ("k", "u1"), ("pad", "u1")])
-RefineResult = np.dtype([("score", "<i4"), ("qb", "<i4"), ("qe", "<i4"), ("n_ops", "<u4"), ("ops_off", "<u4")])
+RefineResult = np.dtype([("score", "<i4"), ("qb", "<i4"), ("qe", "<i4"), ("n_ops", "<u4"), ("ops_off", "<u4"), ("nm", "<u4")])
 
 
 class BmbsError(RuntimeError):
@@ -50,7 +50,7 @@ EXPORTS = ["bmbs_index_load", "bmbs_index_free", "bmbs_index_genome_length", "bm
            "bmbs_params_default", "bmbs_map_batch_se", "bmbs_map_batch_pe", "bmbs_verify", "bmbs_batch_create", "bmbs_batch_free",
            "bmbs_batch_upload", "bmbs_batch_run", "bmbs_batch_download", "bmbs_batch_sync", "bmbs_batch_timings",
            "bmbs_batch_counters", "bmbs_batch_launches", "bmbs_batch_verify", "bmbs_batch_download_verify", "bmbs_ubench_int_pipe", "bmbs_pinned_alloc", "bmbs_pinned_free", "bmbs_ubench_random_sectors",
-           "bmbs_refiner_create", "bmbs_refiner_free", "bmbs_refine", "bmbs_batch_finish", "bmbs_batch_download_final", "bmbs_batch_finish_counters", "bmbs_debug_sort_order"]
+           "bmbs_refiner_create", "bmbs_refiner_free", "bmbs_refine", "bmbs_batch_finish", "bmbs_batch_download_final", "bmbs_batch_finish_counters", "bmbs_debug_sort_order", "bmbs_refiner_kernel_ms"]
 
 
 def load_library():
@@ -91,6 +91,7 @@ def load_library():
     L.bmbs_debug_sort_order.argtypes = [C.c_int, vp, vp, C.c_uint32, vp, vp]
     L.bmbs_refiner_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
     L.bmbs_refiner_free.argtypes = [vp]
+    L.bmbs_refiner_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.bmbs_refine.argtypes = [vp, vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(Scoring), vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     _lib = L
     return L
@@ -311,6 +312,12 @@ class Refiner:
         items = np.ascontiguousarray(items)
         _check(self.L.bmbs_refine(self.h, seqs, quals, len(seqs), items.ctypes.data, n, C.byref(sc), res.ctypes.data, ops.ctypes.data, cap, C.byref(used)))
         return res, ops[: used.value]
+
+    def kernel_ms(self) -> float:
+        """device time of the last refine() call's kernels"""
+        v = C.c_float(0)
+        _check(self.L.bmbs_refiner_kernel_ms(self.h, C.byref(v)))
+        return v.value
 
     def close(self):
         if self.h:

@@ -868,6 +868,8 @@ struct bmbs_refiner {
   unsigned long long* d_total = nullptr;
   // page-locked staging for the offsets and the counter
   u64* h_off = nullptr; size_t cap_h_off = 0; unsigned long long* h_total = nullptr;
+  int sm_count = 148;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool timed = false;
 };
 
 extern "C" int bmbs_refiner_create(bmbs_index* idx, int dev, bmbs_refiner** out) {
@@ -879,8 +881,11 @@ extern "C" int bmbs_refiner_create(bmbs_index* idx, int dev, bmbs_refiner** out)
   bmbs_refiner* r = new bmbs_refiner();
   r->idx = idx; r->copy = copy; r->dev = dev;
   CU(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+  { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) r->sm_count = prop.multiProcessorCount; }
+  cudaFuncSetAttribute(refine_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, RW_WARPS * 1000 * (int)sizeof(uint4));
   CU(cudaMalloc(&r->d_total, 8));
   CU(cudaMallocHost(&r->h_total, 8));
+  CU(cudaEventCreate(&r->ev0)); CU(cudaEventCreate(&r->ev1));
   *out = r;
   return BMBS_OK;
 }
@@ -892,6 +897,7 @@ extern "C" void bmbs_refiner_free(bmbs_refiner* r) {
   cudaFree(r->d_seq); cudaFree(r->d_qual); cudaFree(r->d_items); cudaFree(r->d_res); cudaFree(r->d_dir_off); cudaFree(r->d_ops_off);
   cudaFree(r->d_dir); cudaFree(r->d_ops_scratch); cudaFree(r->d_ops_out); cudaFree(r->d_total);
   cudaFreeHost(r->h_off); cudaFreeHost(r->h_total);
+  if (r->ev0) cudaEventDestroy(r->ev0); if (r->ev1) cudaEventDestroy(r->ev1);
   cudaStreamDestroy(r->stream);
   delete r;
 }
@@ -906,12 +912,19 @@ extern "C" int bmbs_refine(bmbs_refiner* r, const char* seqs, const char* quals,
   if (2 * (n + 1) > r->cap_h_off) { cudaFreeHost(r->h_off); r->cap_h_off = 2 * (n + 1) + 1024; CU(cudaMallocHost(&r->h_off, r->cap_h_off * 8)); }
   u64* dir_off = r->h_off; u64* ops_off = r->h_off + (n + 1);
   u64 dir_total = 0, ops_total = 0;
+  // bands of up to 32 cells go to the warp kernel (directions in shared memory), wider ones to the thread kernel
+  const int all_thread = getenv("BMBS_REFINE_THREAD") ? 1 : 0;      // tests: every item through the thread kernel
+  size_t n_warp = 0, n_thread = 0; u32 max_len = 1;
   for (size_t i = 0; i < n; ++i) {
     const bmbs_refine_item& q = items[i];
     if (q.k > 31) return fail(BMBS_ERR_ARG, "k > 31");
+    if (q.len == 0 || q.len > 1000) return fail(BMBS_ERR_ARG, "read length outside 1..1000");
     if ((size_t)q.seq_off + q.len > bytes) return fail(BMBS_ERR_ARG, "item reaches past the end of seqs[]");
+    const bool warp_item = !all_thread && 2 * q.k + 1 <= 32;
+    if (warp_item) { ++n_warp; if (q.len > max_len) max_len = q.len; } else ++n_thread;
     dir_off[i] = dir_total; ops_off[i] = ops_total;
-    dir_total += (u64)(2 * q.k + 1) * q.len; ops_total += 2ull * q.len + 2ull * q.k + 2;
+    if (!warp_item) dir_total += (u64)(2 * q.k + 1) * q.len;
+    ops_total += 2ull * q.len + 2ull * q.k + 2;
   }
   dir_off[n] = dir_total; ops_off[n] = ops_total;
   if (ops_total > 0xFFFFFFFFull) return fail(BMBS_ERR_CAPACITY, "too many alignments in one bmbs_refine call");
@@ -941,8 +954,17 @@ extern "C" int bmbs_refine(bmbs_refiner* r, const char* seqs, const char* quals,
   CU(cudaMemcpyAsync(r->d_ops_off, ops_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
   CU(cudaMemsetAsync(r->d_total, 0, 8, s));
   RefineScoring rs{sc->mp_max, sc->mp_min, sc->n_pen, sc->gap_open, sc->gap_ext, sc->q_base};
-  refine_dp<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(r->copy->view, r->d_items, (u32)n, r->d_seq, r->d_qual, rs, r->d_dir, r->d_dir_off,
-                                                      r->d_ops_scratch, r->d_ops_off, r->d_res, r->d_ops_out, r->d_total, (u64)r->cap_ops);
+  CU(cudaEventRecord(r->ev0, s));
+  if (n_warp) {
+    const size_t smem = (size_t)RW_WARPS * max_len * sizeof(uint4);
+    const unsigned blocks = (unsigned)std::min<size_t>((n + RW_WARPS - 1) / RW_WARPS, (size_t)r->sm_count * 16);
+    refine_warp<<<blocks, 32 * RW_WARPS, smem, s>>>(r->copy->view, r->d_items, (u32)n, r->d_seq, r->d_qual, rs, r->d_ops_scratch, r->d_ops_off, r->d_res,
+                                                   r->d_ops_out, r->d_total, (u64)r->cap_ops, max_len);
+  }
+  if (n_thread)
+    refine_dp<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(r->copy->view, r->d_items, (u32)n, r->d_seq, r->d_qual, rs, r->d_dir, r->d_dir_off,
+                                                        r->d_ops_scratch, r->d_ops_off, r->d_res, r->d_ops_out, r->d_total, (u64)r->cap_ops, all_thread);
+  CU(cudaEventRecord(r->ev1, s)); r->timed = true;
   CU(cudaMemcpyAsync(r->h_total, r->d_total, 8, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(res, r->d_res, n * sizeof(bmbs_refine_result), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
@@ -951,6 +973,14 @@ extern "C" int bmbs_refine(bmbs_refiner* r, const char* seqs, const char* quals,
   if (ops_used) *ops_used = used;
   if (used > ops_cap) return fail(BMBS_ERR_CAPACITY, "ops[] holds " + std::to_string(ops_cap) + " entries, " + std::to_string(used) + " needed");
   if (used) { if (!ops) return fail(BMBS_ERR_ARG, "ops is null"); CU(cudaMemcpyAsync(ops, r->d_ops_out, used * 4, cudaMemcpyDeviceToHost, s)); CU(cudaStreamSynchronize(s)); }
+  return BMBS_OK;
+}
+
+extern "C" int bmbs_refiner_kernel_ms(bmbs_refiner* r, float* ms) {
+  if (!r || !ms || !r->timed) return fail(BMBS_ERR_ARG, "bad argument or nothing refined yet");
+  CU(cudaSetDevice(r->dev));
+  CU(cudaEventSynchronize(r->ev1));
+  CU(cudaEventElapsedTime(ms, r->ev0, r->ev1));
   return BMBS_OK;
 }
 

@@ -1551,12 +1551,47 @@ __global__ void verify_windows(DevIndex ix, BatchView b, int nch2) {
 
 
 // ------------------------------------------------------------------------------------------- CIGAR refinement
-// ksw_semi_global_quality_back (ksw.cpp:1850-2045) as fast_recalculate_bs_Cigar uses it: semi-global banded (2k+1)
-// affine-gap alignment of the read against its window with traceback.  One thread per alignment -- the row recurrence
-// is a serial chain (h -> f -> h), alignments are independent, and a sub-block sends thousands of them; the H / E rows
-// live in a 128-entry ring per thread, the direction bytes (band x L) in global scratch.  Values and tie-breaks are the
-// reference's, cell by cell (every comparison below is written as it is there).
+// fast_recalculate_bs_Cigar (ksw.cpp:2578-3148) for alignments with indels: ksw_semi_global_quality_back (:1850-2045), the
+// semi-global banded (2k+1) affine-gap alignment of the read against its window with traceback, then the end fix-ups
+// (leading / trailing insertions become matches, :2894-2990) and the NM recount over the final operations (:2990-3143).
+// Values and tie-breaks are the reference's, cell by cell (every comparison below is written as it is there).
+//   refine_warp   bands of up to 32 cells (k <= 15): one warp per alignment, one band cell per lane.  Within a row the match
+//                 score m and the vertical gap e only depend on the row above (m: the lane's own h, e: the neighbour lane's),
+//                 and the horizontal gap opens from m alone, f[j+1] = max(f[j] - ext, m[j] - open - ext): a max-plus prefix
+//                 scan over the lanes.  The four direction bits of a row are four ballots, kept in shared memory (16 bytes
+//                 per row), so the DP touches global memory only for the read, its qualities and the window.
+//   refine_dp     wider bands (k 16..31): one thread per alignment, H / E rows in a 128-entry ring, direction bytes in global
+//                 scratch.
 struct RefineScoring { int mp_max, mp_min, n_pen, gap_open, gap_ext, q_base; };
+
+// End fix-ups of the traceback in ops[0..n) (read order, (len << 4) | op, 0 = M, 1 = D, 2 = I): the read is aligned end to end,
+// so insertions at either end become matches and the window span grows with them.  Returns the first / last op that stays.
+__device__ __forceinline__ void refine_fix_ends(u32* ops, int n, int& qb, int& qe, int& cb, int& ce) {
+  int i = 0; u32 ins = 0;
+  for (; i < n && (ops[i] & 0xfu) == 2u; ++i) ins += ops[i] >> 4;
+  if (i != 0) {
+    u32 op = ops[i] & 0xfu, len = ops[i] >> 4;
+    if (op == 0) len += ins; else { op = 0; len = ins; --i; }
+    ops[i] = len << 4 | op;
+    qb -= (int)ins;
+  }
+  cb = i;
+  ins = 0;
+  for (i = n - 1; i >= cb && (ops[i] & 0xfu) == 2u; --i) ins += ops[i] >> 4;
+  if (i != n - 1) {
+    u32 op = ops[i] & 0xfu, len = ops[i] >> 4;
+    if (op == 0) len += ins; else { op = 0; len = ins; ++i; }
+    ops[i] = len << 4 | op;
+    qe += (int)ins;
+  }
+  ce = i;
+}
+// read character against the window base at double-strand position pos (an out-of-strand window matches nothing)
+__device__ __forceinline__ u32 refine_mismatch(const DevIndex& ix, bool inside, u64 pos, char rc) {
+  if (!inside) return 1u;
+  const int g = strand_base(ix, pos);
+  return (u32)!(rc == "ACGT"[g] || (g == 1 && rc == 'T'));
+}
 
 __device__ __forceinline__ int refine_nt4(char c) {
   switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; }
@@ -1565,10 +1600,11 @@ __device__ __forceinline__ int refine_nt4(char c) {
 __global__ void __launch_bounds__(64) refine_dp(DevIndex ix, const bmbs_refine_item* __restrict__ items, u32 n, const char* __restrict__ seqs,
                                                 const char* __restrict__ quals, RefineScoring sc, unsigned char* __restrict__ dir_all,
                                                 const u64* __restrict__ dir_off, u32* __restrict__ ops_scratch, const u64* __restrict__ ops_off,
-                                                bmbs_refine_result* __restrict__ res, u32* __restrict__ ops_out, unsigned long long* ops_total, u64 ops_cap) {
+                                                bmbs_refine_result* __restrict__ res, u32* __restrict__ ops_out, unsigned long long* ops_total, u64 ops_cap, int all_items) {
   const u32 it = blockIdx.x * blockDim.x + threadIdx.x;
   if (it >= n) return;
   const bmbs_refine_item q = items[it];
+  if (2 * (int)q.k + 1 <= 32 && !all_items) return;      // refine_warp's
   const int rlen = q.len, k = q.k, band = 2 * k + 1, wlen = rlen + 2 * k;
   const char* read = seqs + q.seq_off; const char* qual = quals + q.seq_off;
   const int NEG = -0x40000000, goe = sc.gap_open + sc.gap_ext, ge = sc.gap_ext;
@@ -1642,11 +1678,148 @@ __global__ void __launch_bounds__(64) refine_dp(DevIndex ix, const bmbs_refine_i
   }
   if (i >= 0) push(2, (u32)(i + 1));
   if (n_ops) ops[cap - n_ops] = cur;
-  const u64 at = atomicAdd(ops_total, (unsigned long long)n_ops);
-  if (at + n_ops <= ops_cap) for (u32 x = 0; x < n_ops; ++x) ops_out[at + x] = ops[cap - n_ops + x];
-  bmbs_refine_result r; r.score = score; r.qb = j + 1; r.qe = best - 1; r.n_ops = n_ops; r.ops_off = (u32)at;
+  int qb = j + 1, qe = best - 1, cb = 0, ce = -1;
+  u32* fo = ops + (cap - n_ops);
+  if (n_ops) refine_fix_ends(fo, (int)n_ops, qb, qe, cb, ce);
+  u32 nm = 0;
+  {
+    int wi = qb, ri = 0;
+    for (int x = cb; x <= ce; ++x) {
+      const u32 op = fo[x] & 0xfu, len = fo[x] >> 4;
+      if (op == 0) { for (u32 y = 0; y < len; ++y) nm += refine_mismatch(ix, inside, q.site + (u64)(long long)(wi + (int)y), read[ri + (int)y]); wi += (int)len; ri += (int)len; }
+      else if (op == 1) { wi += (int)len; nm += len; }
+      else { ri += (int)len; nm += len; }
+    }
+  }
+  const u32 n_fin = ce >= cb ? (u32)(ce - cb + 1) : 0u;
+  const u64 at = atomicAdd(ops_total, (unsigned long long)n_fin);
+  if (at + n_fin <= ops_cap) for (u32 x = 0; x < n_fin; ++x) ops_out[at + x] = fo[cb + (int)x];
+  bmbs_refine_result r; r.score = score; r.qb = qb; r.qe = qe; r.n_ops = n_fin; r.ops_off = (u32)at; r.nm = nm;
   res[it] = r;
 }
+
+constexpr int RW_WARPS = 4;
+__global__ void __launch_bounds__(32 * RW_WARPS) refine_warp(DevIndex ix, const bmbs_refine_item* __restrict__ items, u32 n, const char* __restrict__ seqs,
+                                                             const char* __restrict__ quals, RefineScoring sc, u32* __restrict__ ops_scratch, const u64* __restrict__ ops_off,
+                                                             bmbs_refine_result* __restrict__ res, u32* __restrict__ ops_out, unsigned long long* ops_total, u64 ops_cap, u32 max_len) {
+  extern __shared__ uint4 s_dirs[];                     // [RW_WARPS][max_len]: bit jj of .x/.y = h source, .z = e extended, .w = f extended
+  __shared__ int s_fin[RW_WARPS][8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint4* dir = s_dirs + (size_t)w * max_len;
+  const u32 warps = gridDim.x * RW_WARPS;
+  const int NEG = -0x40000000, goe = sc.gap_open + sc.gap_ext, ge = sc.gap_ext;
+  for (u32 it = blockIdx.x * RW_WARPS + w; it < n; it += warps) {
+    const bmbs_refine_item q = items[it];
+    const int rlen = q.len, k = q.k, band = 2 * k + 1, wlen = rlen + 2 * k;
+    if (band > 32) continue;                            // refine_dp's
+    const char* read = seqs + q.seq_off; const char* qual = quals + q.seq_off;
+    const bool inside = window_inside(ix, q.site, (u64)wlen);
+    const bool act = lane < band;
+    int hd = 0, e_prev = -goe;                          // row 0: H = 0, E = -(open + ext) over the band
+    int my_t = 4, my_mism = 0; u32 wlo = 0, whi = 0;
+    for (int i = 0; i < rlen; ++i) {
+      const int ph = i & 31;
+      if (ph == 0) {
+        // every 32 rows: lane l prepares row i + l (base code, quality-scaled mismatch penalty) and its own diagonal's next
+        // 32 window bases (window position i + lane + 0..31)
+        const int ri = i + lane;
+        my_t = 4; my_mism = 0;
+        if (ri < rlen) {
+          my_t = refine_nt4(read[ri]);
+          double phred = (double)((int)qual[ri] - sc.q_base);
+          if (phred > 40) phred = 40;
+          phred = phred / 40;
+          my_mism = -sc.mp_min - (int)((double)(signed char)(sc.mp_max - sc.mp_min) * phred);
+        }
+        if (inside) {
+          const u64 p = q.site + (u64)(i + lane);
+          const uint2 g0 = __ldg(ix.planes + (p >> 5)), g1 = __ldg(ix.planes + (p >> 5) + 1);
+          const unsigned sh = (unsigned)p & 31u;
+          wlo = __funnelshift_r(g0.x, g1.x, sh); whi = __funnelshift_r(g0.y, g1.y, sh);
+        }
+      }
+      const int t = __shfl_sync(0xffffffffu, my_t, ph), mism = __shfl_sync(0xffffffffu, my_mism, ph);
+      const int qb = inside ? (int)(((wlo >> ph) & 1u) | (((whi >> ph) & 1u) << 1)) : 4;
+      int sco;
+      if (t == 4 || qb == 4) sco = -sc.n_pen;
+      else if (t == qb || (t == 3 && qb == 1)) sco = 0;
+      else sco = mism;
+      const int m = hd + sco;
+      int e = __shfl_down_sync(0xffffffffu, e_prev, 1);
+      if (i == 0) e = -goe; else if (lane == band - 1) e = NEG;
+      u32 d = m >= e ? 0u : 1u;
+      int h = m >= e ? m : e;
+      const int open = m - goe;
+      // f entering cell jj: NEG at the band start, then f[jj+1] = max(f[jj] - ge, open[jj]) -- a prefix maximum of open[q] + q ge
+      int a = act ? open + lane * ge : (int)0x80000000;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, a, o); if (lane >= o) a = max(a, v); }
+      const int ex = __shfl_up_sync(0xffffffffu, a, 1);
+      const int f = lane == 0 ? NEG : max(NEG - lane * ge, ex - (lane - 1) * ge);
+      d = h >= f ? d : 2u;
+      h = h >= f ? h : f;
+      e -= ge;
+      const bool e_ext = e > open;
+      if (!e_ext) e = open;
+      const bool f_ext = f - ge > open;
+      const u32 b0 = __ballot_sync(0xffffffffu, act && (d & 1u)), b1 = __ballot_sync(0xffffffffu, act && (d & 2u));
+      const u32 be = __ballot_sync(0xffffffffu, act && e_ext), bf = __ballot_sync(0xffffffffu, act && f_ext);
+      if (lane == 0) dir[i] = make_uint4(b0, b1, be, bf);
+      hd = h; e_prev = e;
+    }
+    // best end in the last row: the middle of the band unless another cell is strictly better, then the rightmost best one
+    const int hv = act ? hd : (int)0x80000000;
+    const int vmax = __reduce_max_sync(0xffffffffu, hv);
+    const u32 at_max = __ballot_sync(0xffffffffu, act && hd == vmax);
+    const int best_lane = ((at_max >> k) & 1u) ? k : 31 - __clz((int)at_max);
+    __syncwarp();
+    if (lane == 0) {
+      u32* ops = ops_scratch + ops_off[it];
+      const u32 cap = (u32)(ops_off[it + 1] - ops_off[it]);
+      u32 n_ops = 0, cur = 0;
+      auto push = [&](u32 op, u32 len) {
+        if (n_ops == 0 || (cur & 0xfu) != op) { if (n_ops) ops[cap - n_ops] = cur; cur = len << 4 | op; ++n_ops; } else cur += len << 4;
+      };
+      int i = rlen - 1, j = rlen - 1 + best_lane, state = 0;
+      while (i >= 0 && j >= 0) {
+        const uint4 dd = dir[i]; const int jj = j - i;
+        if (state == 0) state = (int)(((dd.x >> jj) & 1u) | (((dd.y >> jj) & 1u) << 1));
+        else if (state == 1) state = (int)((dd.z >> jj) & 1u);
+        else state = (int)(((dd.w >> jj) & 1u) << 1);
+        if (state == 0) { push(0, 1); --i; --j; }
+        else if (state == 1) { push(2, 1); --i; }
+        else { push(1, 1); --j; }
+      }
+      if (i >= 0) push(2, (u32)(i + 1));
+      if (n_ops) ops[cap - n_ops] = cur;
+      int qb = j + 1, qe = rlen - 1 + best_lane, cb = 0, ce = -1;
+      if (n_ops) refine_fix_ends(ops + (cap - n_ops), (int)n_ops, qb, qe, cb, ce);
+      s_fin[w][0] = qb; s_fin[w][1] = qe; s_fin[w][2] = (int)(cap - n_ops) + cb; s_fin[w][3] = ce - cb + 1;
+    }
+    __syncwarp();
+    const int qb = s_fin[w][0], qe = s_fin[w][1], first = s_fin[w][2], n_fin = max(s_fin[w][3], 0);
+    const u32* fo = ops_scratch + ops_off[it] + first;
+    // NM over the final operations: the lanes share the bases of every match run
+    u32 nm = 0;
+    {
+      int wi = qb, ri = 0;
+      for (int x = 0; x < n_fin; ++x) {
+        const u32 op = fo[x] & 0xfu, len = fo[x] >> 4;
+        if (op == 0) { for (u32 y = lane; y < len; y += 32) nm += refine_mismatch(ix, inside, q.site + (u64)(long long)(wi + (int)y), read[ri + (int)y]); wi += (int)len; ri += (int)len; }
+        else if (op == 1) { wi += (int)len; if (lane == 0) nm += len; }
+        else { ri += (int)len; if (lane == 0) nm += len; }
+      }
+      nm = __reduce_add_sync(0xffffffffu, nm);
+    }
+    unsigned long long at = 0;
+    if (lane == 0) at = atomicAdd(ops_total, (unsigned long long)n_fin);
+    at = __shfl_sync(0xffffffffu, at, 0);
+    if (at + (u64)n_fin <= ops_cap) for (int x = lane; x < n_fin; x += 32) ops_out[at + x] = fo[x];
+    if (lane == 0) { bmbs_refine_result r; r.score = vmax; r.qb = qb; r.qe = qe; r.n_ops = (u32)n_fin; r.ops_off = (u32)at; r.nm = nm; res[it] = r; }
+    __syncwarp();
+  }
+}
+
 
 // ------------------------------------------------------------------------------------------- sensitive pairing
 // select_suit_candidates (Schema.cpp:4775-4824): a verified hit of the mate within [dmin, dmax] of `site`?

@@ -149,10 +149,19 @@ inline void finish_single_final(const HostContext& hc, const ReadView& rd, const
     case BMBS_FIN_AMBIGUOUS: ++st.reads; ++st.ambiguous; return;
     case BMBS_FIN_DP: {
       ++st.reads;
-      const int plen = L + 2 * (int)k; win.resize(plen + 8);
-      hc.genome.window(f.site, plen, win.data());
       Refined rf;
-      refine_alignment(win.data(), plen, seq.data(), L, (int)k, (int)f.end_site, f.nm, f.site < hc.chroms.N, qual.data(), hc.pbat, hc.sc, rf, f.site, dq);
+      const bool forward = f.site < hc.chroms.N;
+      if (dq && dq->mode == DpQueue::COLLECT) {        // the ungapped check already failed on the device: straight to the DP queue
+        if (!hc.pbat) dq->request(f.site, seq.data(), qual.data(), L, (int)k);
+        else { std::string rq(qual.rbegin(), qual.rend()); dq->request(f.site, seq.data(), rq.data(), L, (int)k); }
+        return;
+      }
+      if (dq) dq->take(forward, rf);
+      else {                                           // no device queue (tests): the whole refinement on the CPU
+        const int plen = L + 2 * (int)k; win.resize(plen + 8);
+        hc.genome.window(f.site, plen, win.data());
+        refine_alignment(win.data(), plen, seq.data(), L, (int)k, (int)f.end_site, f.nm, forward, qual.data(), hc.pbat, hc.sc, rf, f.site, nullptr);
+      }
       const int mapq = mapq_from(f.sbd, (unsigned)k, rf.score, hc.sc);
       const Placed p = place(hc.chroms, f.site, (uint64_t)(int64_t)rf.start_site, rf.end_site);
       if (p.off_chrom) return;

@@ -256,7 +256,62 @@ struct DpQueue {
   std::string seqs, quals; std::vector<bmbs_refine_item> items; size_t ops_bound = 0;
   std::vector<bmbs_refine_result> res; std::vector<uint32_t> ops; size_t next = 0;   // REPLAY
   void clear() { mode = COLLECT; pending = false; seqs.clear(); quals.clear(); items.clear(); ops_bound = 0; res.clear(); ops.clear(); next = 0; }
+  // COLLECT: one alignment for the device (read as aligned, qualities in the DP's order)
+  void request(uint64_t site, const char* read, const char* qual, int rlen, int k) {
+    bmbs_refine_item it; it.site = site; it.seq_off = (uint32_t)seqs.size(); it.len = (uint16_t)rlen; it.k = (uint8_t)k; it.pad = 0;
+    seqs.append(read, (size_t)rlen); quals.append(qual, (size_t)rlen); items.push_back(it);
+    ops_bound += 2 * (size_t)rlen + 2 * (size_t)k + 2;
+    pending = true;
+  }
+  // REPLAY: the next result as the reference's (start, end, NM, score, CIGAR); a reverse-strand hit prints its operations last to first
+  template <class R> void take(bool forward, R& out) {
+    const bmbs_refine_result& r = res[next++];
+    out.score = r.score; out.start_site = r.qb; out.end_site = (uint64_t)(int64_t)r.qe; out.err = r.nm;
+    out.cigar.clear();
+    char buf[16];
+    for (uint32_t x = 0; x < r.n_ops; ++x) {
+      const uint32_t o = ops[r.ops_off + (forward ? x : r.n_ops - 1 - x)];
+      uint32_t len = o >> 4; int p = 16; buf[--p] = "MDISH"[o & 0xf];
+      do { buf[--p] = (char)('0' + len % 10); len /= 10; } while (len);
+      out.cigar.append(buf + p, (size_t)(16 - p));
+    }
+  }
 };
+
+// End fix-ups of fast_recalculate_bs_Cigar (ksw.cpp:2894-2990): the read is aligned end to end, so insertions at either end of
+// the traceback become matches and the window span grows with them.  ops[cb..ce] is what stays.
+inline void fix_ends(std::vector<uint32_t>& ops, int& qb, int& qe, int& cb, int& ce) {
+  const int n = (int)ops.size();
+  int i = 0, ins = 0;
+  for (; i < n && (ops[i] & 0xf) == 2; ++i) ins += ops[i] >> 4;
+  if (i != 0) {
+    uint32_t op = ops[i] & 0xf, len = ops[i] >> 4;   // (i == n cannot happen for a non-empty read with a match)
+    if (op == 0) len += ins; else { op = 0; len = ins; --i; }
+    ops[i] = len << 4 | op;
+    qb -= ins;
+  }
+  cb = i;
+  ins = 0;
+  for (i = n - 1; i >= cb && (ops[i] & 0xf) == 2; --i) ins += ops[i] >> 4;
+  if (i != n - 1) {
+    uint32_t op = ops[i] & 0xf, len = ops[i] >> 4;
+    if (op == 0) len += ins; else { op = 0; len = ins; ++i; }
+    ops[i] = len << 4 | op;
+    qe += ins;
+  }
+  ce = i;
+}
+// NM over the final operations (ksw.cpp:2990-3143): mismatches of the match runs (read T on window C is none) + gap lengths
+inline unsigned recount_nm(const char* win, const char* read, const std::vector<uint32_t>& ops, int cb, int ce, int qb) {
+  unsigned nm = 0; int wi = qb, ri = 0;
+  for (int i = cb; i <= ce; ++i) {
+    const uint32_t op = ops[i] & 0xf, len = ops[i] >> 4;
+    if (op == 0) { for (uint32_t x = 0; x < len; ++x, ++wi, ++ri) nm += win[wi] != read[ri] && !(win[wi] == 'C' && read[ri] == 'T'); }
+    else if (op == 1) { wi += len; nm += len; }
+    else { ri += len; nm += len; }
+  }
+  return nm;
+}
 
 // CIGAR / NM / score / start / end of the best hit, given the verifier's
 // (end_site, err).  `qual` is the quality string in FASTQ order; mate 2 of a
@@ -291,58 +346,15 @@ inline void refine_alignment(const char* win, int wlen, const char* read, int rl
   }
   int score, qb, qe; std::vector<uint32_t> ops;
   if (!dq) banded_affine_align(win, wlen, read, rlen, k, qual.data(), sc, score, qb, qe, ops);
-  else if (dq->mode == DpQueue::COLLECT) {
-    bmbs_refine_item it; it.site = site; it.seq_off = (uint32_t)dq->seqs.size(); it.len = (uint16_t)rlen; it.k = (uint8_t)k; it.pad = 0;
-    dq->seqs.append(read, (size_t)rlen); dq->quals.append(qual.data(), (size_t)rlen); dq->items.push_back(it);
-    dq->ops_bound += 2 * (size_t)rlen + 2 * (size_t)k + 2;
-    dq->pending = true;
-    out.score = 0; out.start_site = end_site - rlen + 1; out.end_site = end_site; out.err = err; out.cigar = "*";   // placeholder, the unit is redone
-    return;
-  } else {
-    const bmbs_refine_result& r = dq->res[dq->next++];
-    score = r.score; qb = r.qb; qe = r.qe; ops.assign(dq->ops.begin() + r.ops_off, dq->ops.begin() + r.ops_off + r.n_ops);
-  }
-  const int n = (int)ops.size();
-  // leading / trailing insertions become matches (the read is end-to-end)
-  int i = 0, ins = 0;
-  for (; i < n && (ops[i] & 0xf) == 2; ++i) ins += ops[i] >> 4;
-  if (i != 0) {
-    uint32_t op = ops[i] & 0xf, len = ops[i] >> 4;   // (i == n cannot happen for a non-empty read with a match)
-    if (op == 0) len += ins; else { op = 0; len = ins; --i; }
-    ops[i] = len << 4 | op;
-    qb -= ins;
-  }
-  const int cb = i;
-  ins = 0;
-  for (i = n - 1; i >= cb && (ops[i] & 0xf) == 2; --i) ins += ops[i] >> 4;
-  if (i != n - 1) {
-    uint32_t op = ops[i] & 0xf, len = ops[i] >> 4;
-    if (op == 0) len += ins; else { op = 0; len = ins; ++i; }
-    ops[i] = len << 4 | op;
-    qe += ins;
-  }
-  const int ce = i;
-  unsigned nm = 0;
+  else if (dq->mode == DpQueue::COLLECT) { dq->request(site, read, qual.data(), rlen, k); out.score = 0; out.start_site = end_site - rlen + 1; out.end_site = end_site; out.err = err; out.cigar = "*"; return; }   // placeholder, the unit is redone
+  else { dq->take(forward, out); return; }       // the device returns the final operations: fix-ups and NM recount included
+  int cb, ce;
+  fix_ends(ops, qb, qe, cb, ce);
+  const unsigned nm = recount_nm(win, read, ops, cb, ce, qb);
   char buf[32];
-  auto mismatch = [&](int wi, int ri) { return win[wi] != read[ri] && !(win[wi] == 'C' && read[ri] == 'T'); };
-  if (forward) {
-    int wi = qb, ri = 0;
-    for (i = cb; i <= ce; ++i) {
-      uint32_t op = ops[i] & 0xf, len = ops[i] >> 4;
-      snprintf(buf, sizeof buf, "%u%c", len, "MDISH"[op]); out.cigar += buf;
-      if (op == 0) { for (uint32_t x = 0; x < len; ++x) nm += mismatch(wi++, ri++); }
-      else if (op == 1) { wi += len; nm += len; }
-      else { ri += len; nm += len; }
-    }
-  } else {
-    int wi = qe, ri = rlen - 1;
-    for (i = ce; i >= cb; --i) {
-      uint32_t op = ops[i] & 0xf, len = ops[i] >> 4;
-      snprintf(buf, sizeof buf, "%u%c", len, "MDISH"[op]); out.cigar += buf;
-      if (op == 0) { for (uint32_t x = 0; x < len; ++x) nm += mismatch(wi--, ri--); }
-      else if (op == 1) { wi -= len; nm += len; }
-      else { ri -= len; nm += len; }
-    }
+  for (int x = cb; x <= ce; ++x) {
+    const uint32_t o = ops[forward ? x : ce - (x - cb)];
+    snprintf(buf, sizeof buf, "%u%c", o >> 4, "MDISH"[o & 0xf]); out.cigar += buf;
   }
   out.score = score; out.start_site = qb; out.end_site = qe; out.err = nm;
 }

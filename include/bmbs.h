@@ -193,18 +193,19 @@ int bmbs_batch_finish_counters(bmbs_batch* b, uint64_t c[8]);
  * order[] receives original positions, ok[i] = 0 when the replay declined (introsort depth limit) */
 int bmbs_debug_sort_order(int dev, const uint32_t* votes, const uint32_t* offsets, uint32_t n_lists, uint16_t* order, int* ok);
 
-/* ---- CIGAR refinement: the banded affine-gap DP with traceback -----------------------------------
- * Replaces ksw_semi_global_quality_back (ksw.cpp:1850-2045) as fast_recalculate_bs_Cigar calls it (ksw.cpp:2578-3148,
- * through try_cigar_without_path :2515-2570) for the one hit per read / mate that the host reduction picked and whose
- * ungapped re-check failed, i.e. alignments with indels.  One call refines a whole sub-block's worth of alignments.
+/* ---- CIGAR refinement: the banded affine-gap DP with traceback, end fix-ups and NM recount ----------
+ * Replaces fast_recalculate_bs_Cigar (ksw.cpp:2578-3148) for the alignments whose ungapped re-check (try_cigar_without_path,
+ * :2515-2570 -- done by bmbs_batch_finish for single-end reads, by the caller otherwise) failed, i.e. alignments with indels:
+ * ksw_semi_global_quality_back (:1850-2045), then the leading / trailing insertions turned into matches (:2894-2990) and the NM
+ * recount over the final operations (:2990-3143).  One call refines a whole sub-block's worth of alignments.
  * The window is read from the index on the device (get_actuall_genome / _rc_genome, Schema.cpp:4998-5115: L + 2k bases
  * at `site`, all-N when it leaves the strand); the caller sends the read as aligned and its qualities in the order the
  * reference's DP sees them (reversed for mate 2, calculate_best_map_cigar_end_to_end_return need_reverse_quality=1).
  * Scores: read T on reference C is a match; mismatch = -(mp_min + (int)((mp_max - mp_min) * min(q - q_base, 40) / 40));
  * N on either side = -n_pen; gap of length g = -(gap_open + g * gap_ext)  (ksw.h:148-162, ksw.cpp:1917-1950).
- * Result: best score in the last row, first / last window position used (qb, qe) and the traceback as run-length ops
- * in read order, (len << 4) | op with op 0 = M, 1 = D (window only), 2 = I (read only); the caller applies the
- * reference's end fix-ups and recounts NM (ksw.cpp:2894-3143), which need no DP. */
+ * Result: best score in the last row, first / last window position of the final alignment (qb, qe), NM, and the final
+ * operations as run-length ops in read order, (len << 4) | op with op 0 = M, 1 = D (window only), 2 = I (read only); the
+ * CIGAR string is these ops printed first to last for a forward-strand hit and last to first for a reverse-strand one. */
 typedef struct bmbs_refiner bmbs_refiner;              /* one per host thread: own stream and device buffers          */
 typedef struct { int mp_max, mp_min, n_pen, gap_open, gap_ext, q_base; } bmbs_scoring;   /* defaults 6 2 1 5 3 33 */
 typedef struct {
@@ -214,13 +215,15 @@ typedef struct {
   uint8_t  k;           /* error threshold: band = 2k + 1, window = L + 2k                                             */
   uint8_t  pad;
 } bmbs_refine_item;
-typedef struct { int32_t score, qb, qe; uint32_t n_ops; uint32_t ops_off; } bmbs_refine_result;   /* ops[ops_off .. +n_ops) */
+typedef struct { int32_t score, qb, qe; uint32_t n_ops; uint32_t ops_off; uint32_t nm; } bmbs_refine_result;   /* ops[ops_off .. +n_ops) */
 int bmbs_refiner_create(bmbs_index* idx, int dev, bmbs_refiner** out);
 void bmbs_refiner_free(bmbs_refiner* r);
 /* seqs / quals: `bytes` bytes each; res[n]; ops[ops_cap] receives every item's ops back to back (*ops_used entries);
  * BMBS_ERR_CAPACITY with the needed size in *ops_used when ops_cap is too small (2 * len + 2 * k + 2 per item always fits). */
 int bmbs_refine(bmbs_refiner* r, const char* seqs, const char* quals, size_t bytes, const bmbs_refine_item* items, size_t n,
                 const bmbs_scoring* sc, bmbs_refine_result* res, uint32_t* ops, size_t ops_cap, size_t* ops_used);
+/* device time of the kernels of the last bmbs_refine call (CUDA events on the refiner's stream), ms */
+int bmbs_refiner_kernel_ms(bmbs_refiner* r, float* ms);
 
 #ifdef __cplusplus
 }

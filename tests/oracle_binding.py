@@ -28,6 +28,7 @@ def lib():
         L.orc_map_pe.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.orc_map_pe_sensitive.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_size_t), vp]
         L.orc_verify.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_size_t, C.c_double, vp, vp, C.c_int]
+        L.orc_refine_final.argtypes = [vp, C.c_uint64, C.c_char_p, C.c_char_p] + [C.c_int] * 8 + [C.POINTER(C.c_int)] * 3 + [C.POINTER(C.c_uint), vp, C.c_int]
         L.orc_std_sort_order.argtypes = [vp, C.c_uint32, vp]
         L.orc_finish_se.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_int, vp, vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.orc_banded_align.argtypes = [vp, C.c_uint64, C.c_char_p, C.c_char_p] + [C.c_int] * 8 + [C.POINTER(C.c_int)] * 3 + [vp, C.c_int]
@@ -100,6 +101,16 @@ class OracleIndex:
         end = np.zeros(n, dtype=np.int32); err = np.zeros(n, dtype=np.uint32)
         lib().orc_verify(self.h, flat.ctypes.data, offs.ctypes.data, len(offs) - 1, read_idx.ctypes.data, sites.ctypes.data, n, e_rate, end.ctypes.data, err.ctypes.data, threads)
         return end, err
+
+
+def refine_final(oidx, site, read: bytes, qual: bytes, k, scoring=(6, 2, 1, 5, 3, 33)):
+    """the reference's whole refinement of an alignment with indels on the CPU (DP, end fix-ups, NM recount):
+    (score, qb, qe, nm, final ops in read order) -- what bmbs_refine must return value for value"""
+    score, qb, qe, nm = C.c_int(), C.c_int(), C.c_int(), C.c_uint()
+    ops = np.zeros(2 * len(read) + 2 * k + 2, dtype=np.uint32)
+    n = lib().orc_refine_final(oidx.h, int(site), read, qual, len(read), int(k), *scoring, C.byref(score), C.byref(qb), C.byref(qe), C.byref(nm), ops.ctypes.data, len(ops))
+    assert n >= 0
+    return score.value, qb.value, qe.value, nm.value, ops[:n].copy()
 
 
 def banded_align(oidx, site, read: bytes, qual: bytes, k, scoring=(6, 2, 1, 5, 3, 33)):

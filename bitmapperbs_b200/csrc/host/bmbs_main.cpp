@@ -60,6 +60,9 @@ template <class T> class Channel {
   void push(T v) { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return q_.size() < cap_; }); q_.push_back(std::move(v)); cv_.notify_all(); }
   bool pop(T& v) { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return !q_.empty() || closed_; }); if (q_.empty()) return false; v = std::move(q_.front()); q_.pop_front(); cv_.notify_all(); return true; }
   void close() { std::lock_guard<std::mutex> l(m_); closed_ = true; cv_.notify_all(); }
+  // without waiting: used for the pool of written-out batches whose buffers the parsers take over
+  bool try_push(T& v) { std::lock_guard<std::mutex> l(m_); if (q_.size() >= cap_) return false; q_.push_back(std::move(v)); return true; }
+  bool try_pop(T& v) { std::lock_guard<std::mutex> l(m_); if (q_.empty()) return false; v = std::move(q_.front()); q_.pop_front(); return true; }
  private:
   std::mutex m_; std::condition_variable cv_; std::deque<T> q_; size_t cap_; bool closed_ = false;
 };
@@ -206,6 +209,24 @@ void finish_batch(const HostContext& hc, Batch& b, bool pe, bool unmapped_out, b
     else { sam_record_unmapped(out, b.name[2 * u], 77, b.fq_seq[2 * u], b.qual[2 * u]); sam_record_unmapped(out, b.name[2 * u + 1], 141, b.fq_seq[2 * u + 1], b.qual[2 * u + 1]); }
   };
   auto add = [&](const MapStats& t) { b.st.reads += t.reads; b.st.unique += t.unique; b.st.ambiguous += t.ambiguous; b.st.bases += t.bases; b.st.err_bases += t.err_bases; };
+  if (!pe && !b.fin.empty()) {
+    // single end behind the device finishing: which reads need the banded DP is already known, so their requests are collected
+    // first, one bmbs_refine call answers them, and the records are then written once, in order
+    fs.side.clear();
+    for (int u = 0; u < units; ++u)      // (a read handed back to the host may ask for a DP too: its trial text goes to a scratch buffer)
+      if (b.fin[u].status == BMBS_FIN_DP || b.fin[u].status == BMBS_FIN_HOST) { MapStats t; one(u, fs.side, t); }
+    if (!dq.items.empty()) {
+      n_dp += (long long)dq.items.size();
+      dq.res.resize(dq.items.size()); dq.ops.resize(dq.ops_bound);
+      const bmbs_scoring sc{hc.sc.mp_max, hc.sc.mp_min, hc.sc.n_pen, hc.sc.gap_open, hc.sc.gap_ext, hc.sc.q_base};
+      size_t used = 0;
+      if (bmbs_refine(refiner, dq.seqs.data(), dq.quals.data(), dq.seqs.size(), dq.items.data(), dq.items.size(), &sc, dq.res.data(), dq.ops.data(), dq.ops.size(), &used))
+        die(std::string("gpu CIGAR refinement failed: ") + bmbs_last_error());
+    }
+    dq.mode = DpQueue::REPLAY; dq.next = 0;
+    for (int u = 0; u < units; ++u) { MapStats t; one(u, b.sam, t); add(t); unmapped(u, b.sam, t); }
+    return;
+  }
   for (int u = 0; u < units; ++u) {
     const size_t mark = b.sam.size();
     MapStats t; dq.pending = false;
@@ -280,6 +301,9 @@ int search(const Options& o, const std::string& cmdline) {
   auto us = [](double a, double b) { return (long long)((b - a) * 1e6); };
   Channel<std::unique_ptr<RawBatch>> raw_q(2 * n_parse);
   Channel<std::unique_ptr<Batch>> gpu_q(2 * n_gpu), fin_q(2 * n_finish), out_q(4 * n_finish);
+  // batches that have been written out go back to the parsers with their buffers (a fresh 25 MB text buffer per sub-block costs
+  // more in page faults than the text that goes into it)
+  Channel<std::unique_ptr<Batch>> spare((size_t)(2 * n_gpu + 6 * n_finish + 2 * n_parse));
   std::thread splitter([&] {
     size_t seq_no = 0;
     for (;;) {
@@ -300,7 +324,13 @@ int search(const Options& o, const std::string& cmdline) {
   std::vector<std::thread> pool;
   for (int t = 0; t < n_parse; ++t) pool.emplace_back([&] {
     std::unique_ptr<RawBatch> rb;
-    while (raw_q.pop(rb)) { const double ts = now(); std::unique_ptr<Batch> b(new Batch()); parse_batch(*rb, pe, o.pbat && !pe, *b); us_parse += us(ts, now()); gpu_q.push(std::move(b)); }
+    while (raw_q.pop(rb)) {
+      const double ts = now();
+      std::unique_ptr<Batch> b;
+      if (!spare.try_pop(b)) b.reset(new Batch());
+      parse_batch(*rb, pe, o.pbat && !pe, *b);
+      us_parse += us(ts, now()); gpu_q.push(std::move(b));
+    }
     if (--live_parse == 0) gpu_q.close();
   });
   for (int g = 0; g < n_gpu; ++g) pool.emplace_back([&, g] {
@@ -401,7 +431,10 @@ int search(const Options& o, const std::string& cmdline) {
         write_all(x.sam.data(), x.sam.size());
         us_write += us(ts, now());
         total.reads += x.st.reads; total.unique += x.st.unique; total.ambiguous += x.st.ambiguous; total.bases += x.st.bases; total.err_bases += x.st.err_bases;
+        std::unique_ptr<Batch> done = std::move(pending.begin()->second);
         pending.erase(pending.begin()); ++next;
+        done->sam.clear(); done->st = MapStats(); done->fin.clear(); done->mism.clear(); done->res.clear(); done->cand.clear();
+        spare.try_push(done);
       }
     }
   }

@@ -128,7 +128,7 @@ inline void finish_single_final(const HostContext& hc, const ReadView& rd, const
   const int L = (int)seq.size();
   const uint64_t k = threshold_k(hc.prm.e_rate, L);
   auto count = [&](unsigned nm) { if (f.flags & BMBS_FINF_AMBIGUOUS) ++st.ambiguous; else { ++st.unique; st.bases += L; st.err_bases += nm; } };
-  auto record = [&](const Placed& p, int mapq, const std::string& cigar, unsigned nm) {
+  auto record = [&](const Placed& p, int mapq, std::string_view cigar, unsigned nm) {
     if (!hc.pbat) sam_record_se(out, rd.name, seq, qual, hc.chroms, p, mapq, cigar, nm);
     else sam_record_se_pbat(out, rd.name, seq, rd.raw, qual, hc.chroms, p, mapq, cigar, nm);
   };
@@ -142,7 +142,9 @@ inline void finish_single_final(const HostContext& hc, const ReadView& rd, const
       }
       const int mapq = f.mapq_fixed ? f.mapq_fixed : mapq_from(f.sbd, (unsigned)k, score, hc.sc);
       Placed p; p.flag = (f.flags & BMBS_FINF_REVERSE) ? 16 : 0; p.chrom = (size_t)(f.chrom_pos >> 40); p.pos = f.chrom_pos & 0xFFFFFFFFFFull; p.off_chrom = false;
-      record(p, mapq, std::to_string(L) + "M", f.nm);
+      char cg[16]; int cp = 16; cg[--cp] = 'M';
+      { unsigned v = (unsigned)L; do { cg[--cp] = (char)('0' + v % 10); v /= 10; } while (v); }
+      record(p, mapq, std::string_view(cg + cp, (size_t)(16 - cp)), f.nm);
       count(f.nm);
       return;
     }

@@ -7,6 +7,9 @@
 #include <cstdio>
 #include <string>
 #include <string_view>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include "postprocess.hpp"
 
 namespace bmbs {
@@ -19,8 +22,30 @@ inline void append_uint(std::string& out, uint64_t v) {
   for (int i = 0; i < n; ++i) out[at + (size_t)i] = buf[n - 1 - i];
 }
 inline void append_int(std::string& out, long long v) { if (v < 0) { out += '-'; append_uint(out, (uint64_t)(-(v + 1)) + 1u); } else append_uint(out, (uint64_t)v); }
+// dst[i] = src[n-1-i], sixteen bytes at a time (byte shuffle) where the CPU has SSSE3; complement: A<->T, C<->G, anything else stays
+#if defined(__x86_64__)
+__attribute__((target("ssse3"))) inline void reverse_bytes_ssse3(char* dst, const char* src, size_t n, bool complement) {
+  const __m128i rev = _mm_set_epi8(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+  const __m128i cA = _mm_set1_epi8('A'), cC = _mm_set1_epi8('C'), cG = _mm_set1_epi8('G'), cT = _mm_set1_epi8('T');
+  const __m128i xAT = _mm_set1_epi8('A' ^ 'T'), xCG = _mm_set1_epi8('C' ^ 'G');
+  size_t i = 0;
+  for (; i + 16 <= n; i += 16) {
+    __m128i v = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i*)(src + n - 16 - i)), rev);
+    if (complement) {
+      const __m128i at = _mm_or_si128(_mm_cmpeq_epi8(v, cA), _mm_cmpeq_epi8(v, cT)), cg = _mm_or_si128(_mm_cmpeq_epi8(v, cC), _mm_cmpeq_epi8(v, cG));
+      v = _mm_xor_si128(v, _mm_or_si128(_mm_and_si128(at, xAT), _mm_and_si128(cg, xCG)));
+    }
+    _mm_storeu_si128((__m128i*)(dst + i), v);
+  }
+  for (; i < n; ++i) { const char c = src[n - 1 - i]; dst[i] = complement ? (c == 'A' ? 'T' : c == 'T' ? 'A' : c == 'C' ? 'G' : c == 'G' ? 'C' : c) : c; }
+}
+inline bool cpu_has_ssse3() { static const bool v = __builtin_cpu_supports("ssse3"); return v; }
+#endif
 inline void append_reversed(std::string& out, std::string_view s) {
   const size_t at = out.size(), n = s.size(); out.resize(at + n);
+#if defined(__x86_64__)
+  if (cpu_has_ssse3()) { reverse_bytes_ssse3(&out[at], s.data(), n, false); return; }
+#endif
   for (size_t i = 0; i < n; ++i) out[at + i] = s[n - 1 - i];
 }
 inline char complement_base(char c) { return c == 'A' ? 'T' : c == 'T' ? 'A' : c == 'C' ? 'G' : c == 'G' ? 'C' : c; }
@@ -29,6 +54,9 @@ inline const char* complement_table() { static const ComplementTable c; return c
 inline void append_revcomp(std::string& out, std::string_view s) {
   const char* t = complement_table();
   const size_t at = out.size(), n = s.size(); out.resize(at + n);
+#if defined(__x86_64__)
+  if (cpu_has_ssse3()) { reverse_bytes_ssse3(&out[at], s.data(), n, true); return; }
+#endif
   for (size_t i = 0; i < n; ++i) out[at + i] = t[(unsigned char)s[n - 1 - i]];
 }
 
@@ -41,7 +69,7 @@ inline void sam_header(std::string& out, const ChromTable& ct, const std::string
 // Single-end record.  `seq`/`qual` as in the FASTQ; reverse-strand hits print
 // the reverse complement and the reversed qualities.
 inline void sam_record_se(std::string& out, std::string_view name, std::string_view seq, std::string_view qual,
-                          const ChromTable& ct, const Placed& p, int mapq, const std::string& cigar, unsigned nm) {
+                          const ChromTable& ct, const Placed& p, int mapq, std::string_view cigar, unsigned nm) {
   out += name; out += '\t';
   append_uint(out, (uint64_t)p.flag); out += '\t';
   out += ct.name[p.chrom]; out += '\t';
@@ -56,7 +84,7 @@ inline void sam_record_se(std::string& out, std::string_view name, std::string_v
 // --pbat single-end record (output_sam_end_to_end_pbat_output_buffer, Schema.cpp:13215-13450): `seq` is what was aligned (the
 // reverse complement of the FASTQ record `raw`), `qual` in FASTQ order
 inline void sam_record_se_pbat(std::string& out, std::string_view name, std::string_view seq, std::string_view raw, std::string_view qual,
-                               const ChromTable& ct, const Placed& p, int mapq, const std::string& cigar, unsigned nm) {
+                               const ChromTable& ct, const Placed& p, int mapq, std::string_view cigar, unsigned nm) {
   out += name; out += '\t';
   append_uint(out, (uint64_t)p.flag); out += '\t';
   out += ct.name[p.chrom]; out += '\t';

@@ -498,7 +498,7 @@ def main():
     layout = {"seed": 8 * c["hash_queries"] + 32 * c["occ_lookups"],
               "locate": c["located_rows"] * (5 if index.genome_length * 2 >= (1 << 32) else 4) if dense else 80 * c["locate_lf_steps"] + 44 * c["located_rows"],
               "verify": c["window_bytes"]}
-    names = {"seed": "seed_first+seed_second+seed_rest", "locate": "expand_locate", "verify": "verify_windows"}
+    names = {"seed": "seed_reads", "locate": "expand_locate", "verify": "verify_windows"}
     dom = max(names, key=lambda k: per_step[k])
     dms = per_step[dom]
     achieved = survey[dom] / (dms / 1000) / 1e9 if dms > 0 else 0.0

@@ -258,7 +258,10 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
   if (!devices || n_dev <= 0) { devices = &dev0; n_dev = 1; }
   // CUDA contexts are created while the files are mapped, one thread per device
   std::vector<std::thread> warm;
-  for (int d = 0; d < n_dev; ++d) warm.emplace_back([=] { cudaSetDevice(devices[d]); cudaFree(0); });
+  // (host threads that wait for the device sleep instead of spinning -- the mapper runs more threads than cores; BMBS_SPIN=1 keeps
+  // the driver's default.  No effect when the process already has a context on the device.)
+  const bool spin = getenv("BMBS_SPIN") != nullptr;
+  for (int d = 0; d < n_dev; ++d) warm.emplace_back([=] { cudaSetDevice(devices[d]); if (!spin) { cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync); cudaGetLastError(); } cudaFree(0); });
   auto warm_join = [&] { for (auto& t : warm) t.join(); };
   int rc = load_files(index_prefix, h);
   if (rc) { warm_join(); return rc; }

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <string_view>
 #if defined(__x86_64__)
@@ -68,17 +69,42 @@ inline void sam_header(std::string& out, const ChromTable& ct, const std::string
 
 // Single-end record.  `seq`/`qual` as in the FASTQ; reverse-strand hits print
 // the reverse complement and the reversed qualities.
+// raw field writers for the hot single-end record: the record's text is written through a pointer into space reserved once
+inline char* put_bytes(char* w, std::string_view s) { memcpy(w, s.data(), s.size()); return w + s.size(); }
+inline char* put_uint(char* w, uint64_t v) {
+  char buf[24]; int n = 0;
+  do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+  while (n) *w++ = buf[--n];
+  return w;
+}
 inline void sam_record_se(std::string& out, std::string_view name, std::string_view seq, std::string_view qual,
                           const ChromTable& ct, const Placed& p, int mapq, std::string_view cigar, unsigned nm) {
-  out += name; out += '\t';
-  append_uint(out, (uint64_t)p.flag); out += '\t';
-  out += ct.name[p.chrom]; out += '\t';
-  append_uint(out, p.pos); out += '\t';
-  append_int(out, mapq); out += '\t';
-  out += cigar; out += "\t*\t0\t0\t";
-  if (p.flag == 0) { out += seq; out += '\t'; out += qual; }
-  else { append_revcomp(out, seq); out += '\t'; append_reversed(out, qual); }
-  out += "\tNM:i:"; append_uint(out, nm); out += '\n';
+  const std::string& cn = ct.name[p.chrom];
+  const size_t at = out.size();
+  out.resize(at + name.size() + cn.size() + cigar.size() + seq.size() + qual.size() + 96);
+  char* const w0 = &out[at]; char* w = w0;
+  w = put_bytes(w, name); *w++ = '\t';
+  w = put_uint(w, (uint64_t)p.flag); *w++ = '\t';
+  w = put_bytes(w, cn); *w++ = '\t';
+  w = put_uint(w, p.pos); *w++ = '\t';
+  if (mapq < 0) { *w++ = '-'; w = put_uint(w, (uint64_t)(-(long long)mapq)); } else w = put_uint(w, (uint64_t)mapq);
+  *w++ = '\t';
+  w = put_bytes(w, cigar); w = put_bytes(w, "\t*\t0\t0\t");
+  if (p.flag == 0) { w = put_bytes(w, seq); *w++ = '\t'; w = put_bytes(w, qual); }
+  else {
+#if defined(__x86_64__)
+    if (cpu_has_ssse3()) { reverse_bytes_ssse3(w, seq.data(), seq.size(), true); w += seq.size(); *w++ = '\t'; reverse_bytes_ssse3(w, qual.data(), qual.size(), false); w += qual.size(); }
+    else
+#endif
+    {
+      const char* t = complement_table();
+      for (size_t i = 0, n = seq.size(); i < n; ++i) *w++ = t[(unsigned char)seq[n - 1 - i]];
+      *w++ = '\t';
+      for (size_t i = 0, n = qual.size(); i < n; ++i) *w++ = qual[n - 1 - i];
+    }
+  }
+  w = put_bytes(w, "\tNM:i:"); w = put_uint(w, nm); *w++ = '\n';
+  out.resize(at + (size_t)(w - w0));
 }
 
 // --pbat single-end record (output_sam_end_to_end_pbat_output_buffer, Schema.cpp:13215-13450): `seq` is what was aligned (the

@@ -1,12 +1,12 @@
 #!/usr/bin/env bash
 # One gpurun call's worth of evidence: GPU parity tests, the bench line, the ncu launch list of the same command and
 # one `ncu --set full` capture of the main kernels.  Everything lands in gpurun_out/ (copied into profiles/ by hand).
-#   gpurun --timeout 1700 -- 'bash tools/gpu_round.sh [tag] [what...]'      what: tests bench launches full verify
+#   gpurun --timeout 1700 -- 'bash tools/gpu_round.sh [tag] [what...]'      what: tests bench refarm launches traffic full cliscale verify fullverify scale2
 set -u
 TAG=${1:-run}; shift || true
 WHAT=${*:-tests bench launches full}
 O=gpurun_out; mkdir -p $O
-KERNELS='regex:^(pack_reads|seed_first|seed_second|seed_rest|expand_locate|votes_classify|votes_sort|votes_big|gather_work|verify_windows)'
+KERNELS='regex:^(pack_reads|seed_reads|expand_locate|votes_classify|votes_sort|votes_mid|votes_big1k|votes_big|gather_work|verify_windows|finish_se|finish_long|finish_huge|finish_sorted)'
 BENCH_ARGS=${BENCH_ARGS:-}
 for w in $WHAT; do
   case $w in
@@ -20,8 +20,15 @@ for w in $WHAT; do
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv \
         python bench.py $BENCH_ARGS --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_launches_bench.log 2>&1; echo "launch list exit $?" ;;
     full)
-      timeout 900 ncu --set full --clock-control none --import-source on -k "$KERNELS" --launch-skip 60 --launch-count 10 -f -o $O/${TAG}_full \
+      timeout 900 ncu --set full --clock-control none --import-source on -k "$KERNELS" --launch-skip ${NCU_SKIP:-80} --launch-count ${NCU_COUNT:-14} -f -o $O/${TAG}_full \
         python bench.py $BENCH_ARGS --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_full_bench.log 2>&1; echo "ncu full exit $?" ;;
+    traffic)
+      # DRAM bytes and duration of one launch of every step kernel at the bench's own scale (one pass: nothing is replayed)
+      timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k "$KERNELS" \
+        --launch-skip ${NCU_SKIP:-80} --launch-count ${NCU_COUNT:-14} --csv --log-file $O/${TAG}_traffic.csv \
+        python bench.py $BENCH_ARGS --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_traffic_bench.log 2>&1; echo "traffic exit $?" ;;
+    cliscale)
+      timeout 900 python tools/cli_scale.py --out $O/${TAG}_cli_scale.json > $O/${TAG}_cli_scale.log 2>&1; echo "cli_scale exit $?"; tail -5 $O/${TAG}_cli_scale.log ;;
     verify)
       timeout 900 python tools/bench_verify.py > $O/${TAG}_verify.json 2> $O/${TAG}_verify.log; echo "bench_verify exit $?"; tail -c 1500 $O/${TAG}_verify.json ;;
     fullverify)

@@ -81,12 +81,49 @@ if rep.exists():
     for n, r in zip(names, data):
         b = float(r[ir]) * mult[units[ir]] + float(r[iw]) * mult[units[iw]]
         traffic[n] = {"dram_bytes_per_launch": b, "duration_us": float(r[it]) * {"us": 1, "ms": 1e3, "ns": 1e-3}.get(units[it], 1), "capture": f"profiles/{tag}_ncu_summary.md"}
-    groups = {"seed_first+second+rest": ["seed_first", "seed_second", "seed_rest"]}
-    for g, ks in groups.items():
-        if all(k in traffic for k in ks):
-            traffic[g] = {"dram_bytes_per_launch": sum(traffic[k]["dram_bytes_per_launch"] for k in ks), "duration_us": sum(traffic[k]["duration_us"] for k in ks),
-                          "capture": f"profiles/{tag}_ncu_summary.md"}
-    (P / "ncu_traffic.json").write_text(json.dumps(traffic, indent=1) + "\n")
+    # keyed by workload (bench.py looks up ncu_traffic[workload][kernel]); other workloads' entries are kept
+    wl_name = "cfg3"
+    if bf.exists() and bf.stat().st_size:
+        wl_name = json.loads([l for l in open(bf) if l.startswith("{")][-1])["config"]["workload"].split(":")[0]
+    allt = {}
+    try:
+        allt = json.loads((P / "ncu_traffic.json").read_text())
+        if not all(isinstance(v, dict) and all(isinstance(x, dict) for x in v.values()) for v in allt.values()):
+            allt = {}
+    except Exception:
+        allt = {}
+    allt[wl_name] = traffic
+    (P / "ncu_traffic.json").write_text(json.dumps(allt, indent=1) + "\n")
+# ---- DRAM traffic at the bench's own scale (tools/gpu_round.sh traffic: one pass, metrics only)
+tf = G / f"{tag}_traffic.csv"
+if tf.exists():
+    rows = [r for r in csv.reader(l for l in open(tf) if l.startswith('"'))]
+    h = rows[0]; ki, mi, vi, ui = h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Value"), h.index("Metric Unit")
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}
+    per = collections.OrderedDict()
+    for r in rows[1:]:
+        k = short(r[ki]); v = float(r[vi].replace(",", "")) * mult.get(r[ui], 1)
+        e = per.setdefault(k, {"dram_bytes_per_launch": 0.0, "duration_us": 0.0, "capture": f"profiles/{tag}_traffic.csv"})
+        if r[mi].startswith("dram__bytes"):
+            e["dram_bytes_per_launch"] += v
+        elif r[mi].startswith("gpu__time_duration"):
+            e["duration_us"] += v
+    wl_name = "cfg3"
+    if bf.exists() and bf.stat().st_size:
+        wl_name = json.loads([l for l in open(bf) if l.startswith("{")][-1])["config"]["workload"].split(":")[0]
+    try:
+        allt = json.loads((P / "ncu_traffic.json").read_text())
+        if not all(isinstance(v, dict) and all(isinstance(x, dict) for x in v.values()) for v in allt.values()):
+            allt = {}
+    except Exception:
+        allt = {}
+    allt[wl_name] = per
+    (P / "ncu_traffic.json").write_text(json.dumps(allt, indent=1) + "\n")
+    shutil.copy(tf, P / f"{tag}_traffic.csv")
+    out += ["", f"## DRAM traffic per launch at the bench's scale (`ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum`, one pass; `profiles/{tag}_traffic.csv`)\n",
+            "| kernel | DRAM bytes | us | GB/s |", "|---|---|---|---|"]
+    for k, e in per.items():
+        out.append(f"| {k} | {e['dram_bytes_per_launch'] / 1e6:.1f} MB | {e['duration_us']:.1f} | {e['dram_bytes_per_launch'] / max(e['duration_us'], 1e-9) / 1e3:.0f} |")
 notes = G / f"{tag}_notes.md"
 if notes.exists():
     out += ["", notes.read_text()]

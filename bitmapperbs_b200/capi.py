@@ -50,7 +50,7 @@ EXPORTS = ["bmbs_index_load", "bmbs_index_free", "bmbs_index_genome_length", "bm
            "bmbs_params_default", "bmbs_map_batch_se", "bmbs_map_batch_pe", "bmbs_verify", "bmbs_batch_create", "bmbs_batch_free",
            "bmbs_batch_upload", "bmbs_batch_run", "bmbs_batch_download", "bmbs_batch_sync", "bmbs_batch_timings",
            "bmbs_batch_counters", "bmbs_batch_launches", "bmbs_batch_verify", "bmbs_batch_download_verify", "bmbs_ubench_int_pipe", "bmbs_pinned_alloc", "bmbs_pinned_free", "bmbs_ubench_random_sectors",
-           "bmbs_refiner_create", "bmbs_refiner_free", "bmbs_refine", "bmbs_batch_finish", "bmbs_batch_download_final", "bmbs_batch_finish_counters", "bmbs_debug_sort_order", "bmbs_refiner_kernel_ms"]
+           "bmbs_refiner_create", "bmbs_refiner_free", "bmbs_refine", "bmbs_batch_finish", "bmbs_batch_download_final", "bmbs_batch_finish_counters", "bmbs_debug_sort_order", "bmbs_refiner_kernel_ms", "bmbs_batch_output_sizes"]
 
 
 def load_library():
@@ -78,6 +78,7 @@ def load_library():
     L.bmbs_batch_run.argtypes = [vp, C.POINTER(Params)]
     L.bmbs_batch_download.argtypes = [vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.bmbs_batch_sync.argtypes = [vp]
+    L.bmbs_batch_output_sizes.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.bmbs_batch_timings.argtypes = [vp, C.POINTER(C.c_float)]
     L.bmbs_batch_counters.argtypes = [vp, u64p]
     L.bmbs_batch_launches.argtypes = [vp]
@@ -234,6 +235,12 @@ class Batch:
         used = C.c_size_t(0)
         _check(self._L.bmbs_batch_download(self._h, res.ctypes.data, cand.ctypes.data, len(cand), C.byref(used)))
         return res, cand, used.value
+
+    def output_sizes(self):
+        """waits for the batch -> (entries of cand[], mismatch positions) the download call will write"""
+        nc, nm = C.c_size_t(0), C.c_size_t(0)
+        _check(self._L.bmbs_batch_output_sizes(self._h, C.byref(nc), C.byref(nm)))
+        return nc.value, nm.value
 
     def finish(self):
         """single end: reduction + ungapped CIGAR + coordinates on the device, behind run() on the batch's stream"""

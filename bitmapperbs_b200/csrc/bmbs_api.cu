@@ -641,6 +641,17 @@ int check_status(bmbs_batch* b, size_t* used) {
 }
 }  // namespace
 
+extern "C" int bmbs_batch_output_sizes(bmbs_batch* b, size_t* n_cand, size_t* n_mism) {
+  if (!b || !b->ran) return fail(BMBS_ERR_ARG, "bad argument or batch not run");
+  CU(cudaSetDevice(b->dev));
+  CU(cudaStreamSynchronize(b->stream));
+  if (n_mism) *n_mism = 0;
+  int rc = check_status(b, n_cand);
+  if (rc) return rc;
+  if (b->finished) { if (n_mism) *n_mism = (size_t)b->h_small[16]; if (n_cand) *n_cand = (size_t)b->h_small[17]; }
+  return BMBS_OK;
+}
+
 extern "C" int bmbs_batch_download(bmbs_batch* b, bmbs_read_result* res, bmbs_cand* cand, size_t cand_cap, size_t* cand_used) {
   if (!b || !b->ran || !res) return fail(BMBS_ERR_ARG, "bad argument or batch not run");
   CU(cudaSetDevice(b->dev));

@@ -43,13 +43,28 @@ struct Options {
 
 struct RawBatch { size_t seq_no = 0; size_t n_rec = 0; std::string_view raw1, raw2; std::string own1, own2; };   // views into the mapped files (own*: gzip input)
 
+// What one device launch returned.  Several sub-blocks go to the device together (a 32 k-read sub-block does not fill a B200);
+// they share the launch's page-locked result buffers and each looks at its own range of reads.  Recycled through a pool:
+// page-locking memory costs more than the copies into it.
+struct GpuResult {
+  bmbs_final* fin = nullptr; uint16_t* mism = nullptr; bmbs_read_result* res = nullptr; bmbs_cand* cand = nullptr;
+  size_t fin_cap = 0, mism_cap = 0, res_cap = 0, cand_cap = 0;
+  template <class T> static void grow(T*& p, size_t& cap, size_t need) {
+    if (need <= cap) return;
+    bmbs_pinned_free(p); cap = need + need / 4 + 1024; p = (T*)bmbs_pinned_alloc(cap * sizeof(T));
+    if (!p) { fprintf(stderr, "bmbs: cannot allocate page-locked result buffers\n"); exit(1); }
+  }
+  ~GpuResult() { bmbs_pinned_free(fin); bmbs_pinned_free(mism); bmbs_pinned_free(res); bmbs_pinned_free(cand); }
+};
+
 struct Batch {
   size_t seq_no = 0; int n = 0;                      // n reads (SE) or mates (PE, even)
   std::string_view raw1, raw2; std::string own1, own2; // FASTQ text the views below point into (bases upper-cased in place)
   std::vector<std::string_view> name, qual, fq_seq;  // per read / mate; fq_seq: the sequence as it stands in the FASTQ record
   std::string flat; std::vector<uint64_t> offsets;   // sequences as aligned (mate 2 reverse-complemented), back to back
-  std::vector<bmbs_read_result> res; std::vector<bmbs_cand> cand;
-  std::vector<bmbs_final> fin; std::vector<uint16_t> mism;   // single end: finished records of the device (cand: handed-back window lists)
+  // results of the launch this sub-block was part of: read u of the sub-block is read r0 + u of the launch; slices of cand[] and
+  // mism[] are addressed by the records themselves.  final: single end, finished records of the device (cand: handed-back lists)
+  std::shared_ptr<GpuResult> gr; size_t r0 = 0; bool final = false;
   std::string sam; MapStats st;
   std::string_view seq(int i) const { return std::string_view(flat.data() + offsets[i], (size_t)(offsets[i + 1] - offsets[i])); }
 };
@@ -62,7 +77,7 @@ template <class T> class Channel {
   void close() { std::lock_guard<std::mutex> l(m_); closed_ = true; cv_.notify_all(); }
   // without waiting: used for the pool of written-out batches whose buffers the parsers take over
   bool try_push(T& v) { std::lock_guard<std::mutex> l(m_); if (q_.size() >= cap_) return false; q_.push_back(std::move(v)); return true; }
-  bool try_pop(T& v) { std::lock_guard<std::mutex> l(m_); if (q_.empty()) return false; v = std::move(q_.front()); q_.pop_front(); return true; }
+  bool try_pop(T& v) { std::lock_guard<std::mutex> l(m_); if (q_.empty()) return false; v = std::move(q_.front()); q_.pop_front(); cv_.notify_all(); return true; }
  private:
   std::mutex m_; std::condition_variable cv_; std::deque<T> q_; size_t cap_; bool closed_ = false;
 };
@@ -183,21 +198,24 @@ void parse_batch(RawBatch& rb, bool pe, bool pbat_se, Batch& b) {
 // Finishing of one sub-block.  The banded DPs (alignments with indels) of the whole sub-block run on the GPU in one
 // bmbs_refine call: the first pass writes the SAM text of every unit that needs none and collects the requests of the
 // others, the second pass redoes only those units with the results, and their text is spliced back in input order.
-struct FinishScratch { std::vector<HostHit> v1, v2; std::vector<char> win; DpQueue dq; std::string side; std::vector<uint32_t> unit; std::vector<size_t> at, side_end; };
+struct FinishScratch { std::vector<HostHit> v1, v2; std::vector<char> win; DpQueue dq; std::string side; std::vector<uint32_t> unit; std::vector<size_t> at, side_end; double refine_s = 0; };
 
 void finish_batch(const HostContext& hc, Batch& b, bool pe, bool unmapped_out, bmbs_refiner* refiner, FinishScratch& fs, long long& n_dp) {
   const int units = pe ? b.n / 2 : b.n;
   b.sam.clear(); b.sam.reserve((size_t)units * (pe ? 900 : 400));
   DpQueue& dq = fs.dq; dq.clear();
   fs.unit.clear(); fs.at.clear();
+  const GpuResult& gr = *b.gr;
+  const bmbs_final* fin = b.final ? gr.fin + b.r0 : nullptr;
+  const bmbs_read_result* res = b.final ? nullptr : gr.res + b.r0;
   auto one = [&](int u, std::string& out, MapStats& st) {
     if (!pe) {
       ReadView rv{b.name[u], b.seq(u), b.qual[u], b.fq_seq[u]};
-      if (!b.fin.empty()) finish_single_final(hc, rv, b.fin[u], b.mism.data(), b.cand.data(), out, st, fs.v1, fs.win, &dq);
-      else finish_single(hc, rv, b.res[u], b.cand.data(), out, st, fs.v1, fs.win, &dq);
+      if (fin) finish_single_final(hc, rv, fin[u], gr.mism, gr.cand, out, st, fs.v1, fs.win, &dq);
+      else finish_single(hc, rv, res[u], gr.cand, out, st, fs.v1, fs.win, &dq);
     } else {
       finish_pair(hc, b.name[2 * u], b.seq(2 * u), b.qual[2 * u], b.name[2 * u + 1], b.seq(2 * u + 1), b.fq_seq[2 * u + 1], b.qual[2 * u + 1],
-                  b.res[2 * u], b.res[2 * u + 1], b.cand.data(), out, st, fs.v1, fs.v2, fs.win, &dq);
+                  res[2 * u], res[2 * u + 1], gr.cand, out, st, fs.v1, fs.v2, fs.win, &dq);
     }
   };
   // --unmapped_out: a read (pair) that was counted neither as unique nor as ambiguous gets flag-4 (77 / 141) records where its
@@ -209,19 +227,21 @@ void finish_batch(const HostContext& hc, Batch& b, bool pe, bool unmapped_out, b
     else { sam_record_unmapped(out, b.name[2 * u], 77, b.fq_seq[2 * u], b.qual[2 * u]); sam_record_unmapped(out, b.name[2 * u + 1], 141, b.fq_seq[2 * u + 1], b.qual[2 * u + 1]); }
   };
   auto add = [&](const MapStats& t) { b.st.reads += t.reads; b.st.unique += t.unique; b.st.ambiguous += t.ambiguous; b.st.bases += t.bases; b.st.err_bases += t.err_bases; };
-  if (!pe && !b.fin.empty()) {
+  if (!pe && fin) {
     // single end behind the device finishing: which reads need the banded DP is already known, so their requests are collected
     // first, one bmbs_refine call answers them, and the records are then written once, in order
     fs.side.clear();
     for (int u = 0; u < units; ++u)      // (a read handed back to the host may ask for a DP too: its trial text goes to a scratch buffer)
-      if (b.fin[u].status == BMBS_FIN_DP || b.fin[u].status == BMBS_FIN_HOST) { MapStats t; one(u, fs.side, t); }
+      if (fin[u].status == BMBS_FIN_DP || fin[u].status == BMBS_FIN_HOST) { MapStats t; one(u, fs.side, t); }
     if (!dq.items.empty()) {
       n_dp += (long long)dq.items.size();
       dq.res.resize(dq.items.size()); dq.ops.resize(dq.ops_bound);
       const bmbs_scoring sc{hc.sc.mp_max, hc.sc.mp_min, hc.sc.n_pen, hc.sc.gap_open, hc.sc.gap_ext, hc.sc.q_base};
       size_t used = 0;
+      const double tr = now();
       if (bmbs_refine(refiner, dq.seqs.data(), dq.quals.data(), dq.seqs.size(), dq.items.data(), dq.items.size(), &sc, dq.res.data(), dq.ops.data(), dq.ops.size(), &used))
         die(std::string("gpu CIGAR refinement failed: ") + bmbs_last_error());
+      fs.refine_s += now() - tr;
     }
     dq.mode = DpQueue::REPLAY; dq.next = 0;
     for (int u = 0; u < units; ++u) { MapStats t; one(u, b.sam, t); add(t); unmapped(u, b.sam, t); }
@@ -238,8 +258,10 @@ void finish_batch(const HostContext& hc, Batch& b, bool pe, bool unmapped_out, b
   dq.res.resize(dq.items.size()); dq.ops.resize(dq.ops_bound);
   const bmbs_scoring sc{hc.sc.mp_max, hc.sc.mp_min, hc.sc.n_pen, hc.sc.gap_open, hc.sc.gap_ext, hc.sc.q_base};
   size_t used = 0;
+  const double tr = now();
   if (bmbs_refine(refiner, dq.seqs.data(), dq.quals.data(), dq.seqs.size(), dq.items.data(), dq.items.size(), &sc, dq.res.data(), dq.ops.data(), dq.ops.size(), &used))
     die(std::string("gpu CIGAR refinement failed: ") + bmbs_last_error());
+  fs.refine_s += now() - tr;
   dq.mode = DpQueue::REPLAY; dq.next = 0;
   fs.side.clear(); fs.side_end.clear();
   for (uint32_t u : fs.unit) { MapStats t; one((int)u, fs.side, t); add(t); unmapped((int)u, fs.side, t); fs.side_end.push_back(fs.side.size()); }
@@ -290,20 +312,37 @@ int search(const Options& o, const std::string& cmdline) {
     while (n) { const ssize_t w = ::write(fileno(fo), p, n); if (w <= 0) die("write failed on " + o.out); p += w; n -= (size_t)w; }
   };
 
-  // splitter -> parse workers -> GPU threads (two batches in flight per device) -> finish workers -> ordered writer
+  // splitter -> parse workers -> GPU threads (three launches in flight per device) -> finish workers -> ordered writer
   const double t1 = now();
-  // batches in flight per device: a sub-block of 32 k reads does not fill a B200 (and its slowest reads set the pace of
-  // every kernel), so three of them share the device on their own streams while their copies overlap (BMBS_INFLIGHT to change)
-  const int inflight = getenv("BMBS_INFLIGHT") ? std::max(1, atoi(getenv("BMBS_INFLIGHT"))) : 3;
-  const int n_parse = std::max(1, o.threads / 2), n_finish = std::max(1, o.threads), n_gpu = inflight * (int)devs.size();
-  std::atomic<long long> us_split(0), us_parse(0), us_gpu(0), us_finish(0), us_write(0), n_retry(0), n_batches(0), us_dev(0), us_up(0), us_run(0), us_down(0), us_prep(0);
+  // Launches in flight per device: while one launch computes, the next one's reads go up and the previous one's records come down
+  // (BMBS_INFLIGHT to change).  A launch takes every sub-block that is waiting, up to BMBS_GROUP of them: a 32 k-read sub-block
+  // does not fill a B200 and its slowest reads set the pace of every kernel, so the device runs 5 x faster on 256 k reads at a
+  // time -- and when the host is the slower side the queue is short and a launch is one or two sub-blocks, with no added latency.
+  auto env_int = [](const char* k, int d) { const char* e = getenv(k); return e ? std::max(1, atoi(e)) : d; };
+  const int inflight = env_int("BMBS_INFLIGHT", 3), group_max = env_int("BMBS_GROUP", 8);
+  // host threads: -t counts the workers that do the per-read work; the splitter, the writer and the GPU threads mostly wait.
+  // Parsing is a sixth of the per-read host work, finishing the rest.
+  const int n_parse = env_int("BMBS_PARSE_THREADS", std::max(1, (o.threads + 2) / 5)), n_finish = env_int("BMBS_FINISH_THREADS", std::max(1, o.threads - n_parse));
+  const int n_gpu = inflight * (int)devs.size();
+  std::atomic<long long> us_split(0), us_parse(0), us_gpu(0), us_finish(0), us_write(0), n_retry(0), n_batches(0), n_launches(0), us_dev(0), us_up(0), us_run(0), us_down(0), us_prep(0), us_refine(0);
   std::atomic<long long> us_stage[8] = {};
   auto us = [](double a, double b) { return (long long)((b - a) * 1e6); };
+  // result buffers of finished launches, handed back by the last sub-block that drops its reference (declared before the queues: it outlives every batch)
+  struct ResultPool {
+    std::mutex m; std::vector<GpuResult*> idle;
+    ~ResultPool() { for (GpuResult* g : idle) delete g; }
+    std::shared_ptr<GpuResult> take() {
+      GpuResult* g = nullptr;
+      { std::lock_guard<std::mutex> l(m); if (!idle.empty()) { g = idle.back(); idle.pop_back(); } }
+      if (!g) g = new GpuResult();
+      return std::shared_ptr<GpuResult>(g, [this](GpuResult* x) { std::lock_guard<std::mutex> l(m); idle.push_back(x); });
+    }
+  } result_pool;
   Channel<std::unique_ptr<RawBatch>> raw_q(2 * n_parse);
-  Channel<std::unique_ptr<Batch>> gpu_q(2 * n_gpu), fin_q(2 * n_finish), out_q(4 * n_finish);
+  Channel<std::unique_ptr<Batch>> gpu_q((size_t)(n_gpu * group_max)), fin_q((size_t)(2 * n_finish + n_gpu * group_max)), out_q(4 * n_finish);
   // batches that have been written out go back to the parsers with their buffers (a fresh 25 MB text buffer per sub-block costs
   // more in page faults than the text that goes into it)
-  Channel<std::unique_ptr<Batch>> spare((size_t)(2 * n_gpu + 6 * n_finish + 2 * n_parse));
+  Channel<std::unique_ptr<Batch>> spare((size_t)(2 * n_gpu * group_max + 8 * n_finish + 2 * n_parse));
   std::thread splitter([&] {
     size_t seq_no = 0;
     for (;;) {
@@ -335,64 +374,80 @@ int search(const Options& o, const std::string& cmdline) {
   });
   for (int g = 0; g < n_gpu; ++g) pool.emplace_back([&, g] {
     const int dev = devs[g % devs.size()];
-    // one batch context and one set of page-locked result buffers per GPU thread, grown on demand
+    // one batch context and one page-locked staging area for the reads per GPU thread, grown on demand
     bmbs_batch* ctx = nullptr; size_t cap_reads = 0, cap_bases = 0, cap_cand = 0;
-    bmbs_read_result* h_res = nullptr; bmbs_cand* h_cand = nullptr; size_t h_res_cap = 0, h_cand_cap = 0;
+    char* h_seq = nullptr; uint64_t* h_off = nullptr; size_t h_seq_cap = 0, h_off_cap = 0;
     // single end: the device finishes the reads (reduction, ungapped CIGAR, coordinates) and one 32-byte record per read comes
     // back; BMBS_HOST_FINISH=1 keeps the host reduction over the full window lists
     const bool dev_finish = !pe && !getenv("BMBS_HOST_FINISH");
-    bmbs_final* h_fin = nullptr; uint16_t* h_mism = nullptr; size_t h_fin_cap = 0;
     auto ensure = [&](size_t reads, size_t bases, size_t cands) {
       if (!ctx || reads > cap_reads || bases > cap_bases || cands > cap_cand) {
         if (ctx) bmbs_batch_free(ctx);
         cap_reads = std::max(cap_reads, reads); cap_bases = std::max(cap_bases, bases); cap_cand = std::max(cap_cand, cands);
         if (bmbs_batch_create(idx, dev, cap_reads, cap_bases, cap_cand, &ctx)) die(std::string("batch create: ") + bmbs_last_error());
       }
-      if (cap_reads > h_res_cap) { bmbs_pinned_free(h_res); h_res_cap = cap_reads; h_res = (bmbs_read_result*)bmbs_pinned_alloc(h_res_cap * sizeof(bmbs_read_result)); }
-      if (cap_cand > h_cand_cap) { bmbs_pinned_free(h_cand); h_cand_cap = cap_cand; h_cand = (bmbs_cand*)bmbs_pinned_alloc(h_cand_cap * sizeof(bmbs_cand)); }
-      if (dev_finish && cap_reads > h_fin_cap) {
-        bmbs_pinned_free(h_fin); bmbs_pinned_free(h_mism); h_fin_cap = cap_reads;
-        h_fin = (bmbs_final*)bmbs_pinned_alloc(h_fin_cap * sizeof(bmbs_final)); h_mism = (uint16_t*)bmbs_pinned_alloc((32 * h_fin_cap + 64) * sizeof(uint16_t));
-        if (!h_fin || !h_mism) die("cannot allocate page-locked result buffers");
-      }
-      if (!h_res || !h_cand) die("cannot allocate page-locked result buffers");
+      if (bases > h_seq_cap) { bmbs_pinned_free(h_seq); h_seq_cap = bases + bases / 8; h_seq = (char*)bmbs_pinned_alloc(h_seq_cap); }
+      if (reads + 1 > h_off_cap) { bmbs_pinned_free(h_off); h_off_cap = reads + reads / 8 + 1; h_off = (uint64_t*)bmbs_pinned_alloc(h_off_cap * sizeof(uint64_t)); }
+      if (!h_seq || !h_off) die("cannot allocate page-locked staging buffers");
     };
-    {   // sized for a full batch of typical reads before the first one arrives
-      const size_t r0 = o.batch_reads * (pe ? 2 : 1);
+    {   // sized for a typical launch before the first sub-block arrives (a short input never grows it)
+      const size_t r0 = o.batch_reads * (pe ? 2 : 1) * (size_t)std::min(group_max, 2);
       ensure(r0, r0 * 160 + 64, r0 * 24 + (1u << 20));
     }
+    std::vector<std::unique_ptr<Batch>> grp;
     std::unique_ptr<Batch> b;
     while (gpu_q.pop(b)) {
-      const double ts = now(); ++n_batches;
-      const size_t bases = b->flat.size() + 64;
-      size_t want_cand = std::max<size_t>(cap_cand, (size_t)b->n * 24 + (1u << 20));
+      const double ts = now();
+      grp.clear(); grp.push_back(std::move(b));
+      while ((int)grp.size() < group_max) { std::unique_ptr<Batch> x; if (!gpu_q.try_pop(x)) break; grp.push_back(std::move(x)); }
+      n_batches += (long long)grp.size(); ++n_launches;
+      size_t reads = 0, bases = 0;
+      for (auto& x : grp) { reads += (size_t)x->n; bases += x->flat.size(); }
+      size_t want_cand = std::max<size_t>(cap_cand, reads * 24 + (1u << 20));
+      std::shared_ptr<GpuResult> gr = result_pool.take();
       for (;;) {
         const double t_a = now();
-        ensure((size_t)b->n, bases, want_cand);
-        size_t used = 0;
+        ensure(reads, bases + 64, want_cand);
+        {   // the sub-blocks' reads back to back in the staging area
+          size_t r = 0, at = 0;
+          for (auto& x : grp) {
+            memcpy(h_seq + at, x->flat.data(), x->flat.size());
+            for (int i = 0; i < x->n; ++i) h_off[r + (size_t)i] = at + x->offsets[(size_t)i];
+            r += (size_t)x->n; at += x->flat.size();
+          }
+          h_off[r] = at;
+        }
         const double t_b = now();
-        int rc = bmbs_batch_upload(ctx, b->flat.data(), b->offsets.data(), b->n, pe ? 1 : 0);
+        int rc = bmbs_batch_upload(ctx, h_seq, h_off, (int)reads, pe ? 1 : 0);
         const double t_c = now();
         if (!rc) rc = bmbs_batch_run(ctx, &o.prm);
-        const double t_d = now();
-        size_t n_mism = 0;
         if (!rc && dev_finish) rc = bmbs_batch_finish(ctx);
-        if (!rc) rc = dev_finish ? bmbs_batch_download_final(ctx, h_fin, h_mism, 32 * h_fin_cap + 64, &n_mism, h_cand, h_cand_cap, &used)
-                                 : bmbs_batch_download(ctx, h_res, h_cand, h_cand_cap, &used);
+        const double t_d = now();
+        size_t n_cand = 0, n_mism = 0, got_cand = 0, got_mism = 0;
+        if (!rc) rc = bmbs_batch_output_sizes(ctx, &n_cand, &n_mism);
+        if (!rc) {
+          GpuResult::grow(gr->cand, gr->cand_cap, n_cand + 64);
+          if (dev_finish) {
+            GpuResult::grow(gr->fin, gr->fin_cap, reads); GpuResult::grow(gr->mism, gr->mism_cap, n_mism + 64);
+            rc = bmbs_batch_download_final(ctx, gr->fin, gr->mism, gr->mism_cap, &got_mism, gr->cand, gr->cand_cap, &got_cand);
+          } else {
+            GpuResult::grow(gr->res, gr->res_cap, reads);
+            rc = bmbs_batch_download(ctx, gr->res, gr->cand, gr->cand_cap, &got_cand);
+          }
+        }
         const double t_e = now();
         us_prep += us(t_a, t_b); us_up += us(t_b, t_c); us_run += us(t_c, t_d); us_down += us(t_d, t_e);
         if (!rc) { float ms[8]; if (!bmbs_batch_timings(ctx, ms)) { us_dev += (long long)(ms[0] * 1000); for (int q = 1; q < 8; ++q) us_stage[q] += (long long)(ms[q] * 1000); } }
-        if (rc == BMBS_ERR_CAPACITY) { want_cand = std::max(cap_cand * 2, used + (used >> 2) + 1024); ++n_retry; continue; }
+        if (rc == BMBS_ERR_CAPACITY) { want_cand = std::max(cap_cand * 2, n_cand + (n_cand >> 2) + 1024); ++n_retry; continue; }
         if (rc) die(std::string("gpu batch failed: ") + bmbs_last_error());
-        if (dev_finish) { b->fin.assign(h_fin, h_fin + b->n); b->mism.assign(h_mism, h_mism + n_mism); b->cand.assign(h_cand, h_cand + used); }
-        else { b->res.assign(h_res, h_res + b->n); b->cand.assign(h_cand, h_cand + used); }
         break;
       }
       us_gpu += us(ts, now());
-      fin_q.push(std::move(b));
+      size_t r = 0;
+      for (auto& x : grp) { x->gr = gr; x->r0 = r; x->final = dev_finish; r += (size_t)x->n; fin_q.push(std::move(x)); }
     }
     if (ctx) bmbs_batch_free(ctx);
-    bmbs_pinned_free(h_res); bmbs_pinned_free(h_cand); bmbs_pinned_free(h_fin); bmbs_pinned_free(h_mism);
+    bmbs_pinned_free(h_seq); bmbs_pinned_free(h_off);
     if (--live_gpu == 0) fin_q.close();
   });
   std::atomic<long long> n_dp_total(0);
@@ -415,7 +470,7 @@ int search(const Options& o, const std::string& cmdline) {
       us_finish += us(ts, now()); out_q.push(std::move(b));
     }
     bmbs_refiner_free(refiner);
-    n_dp_total += n_dp;
+    n_dp_total += n_dp; us_refine += (long long)(fs.refine_s * 1e6);
     if (--live_finish == 0) out_q.close();
   });
 
@@ -433,7 +488,7 @@ int search(const Options& o, const std::string& cmdline) {
         total.reads += x.st.reads; total.unique += x.st.unique; total.ambiguous += x.st.ambiguous; total.bases += x.st.bases; total.err_bases += x.st.err_bases;
         std::unique_ptr<Batch> done = std::move(pending.begin()->second);
         pending.erase(pending.begin()); ++next;
-        done->sam.clear(); done->st = MapStats(); done->fin.clear(); done->mism.clear(); done->res.clear(); done->cand.clear();
+        done->sam.clear(); done->st = MapStats(); done->gr.reset();
         spare.try_push(done);
       }
     }
@@ -445,8 +500,8 @@ int search(const Options& o, const std::string& cmdline) {
             us_prep / 1e6, us_up / 1e6, us_run / 1e6, us_down / 1e6, us_dev / 1e6, us_stage[1] / 1e6, us_stage[2] / 1e6, us_stage[3] / 1e6, us_stage[4] / 1e6, us_stage[5] / 1e6, us_stage[6] / 1e6, us_stage[7] / 1e6);
   }
   if (getenv("BMBS_TIMING"))
-    fprintf(stderr, "[bmbs timing] busy seconds summed over threads: split %.2f  parse %.2f (%d thr)  gpu %.2f (%d thr, %lld batches, %lld capacity retries)  finish %.2f (%d thr, %lld banded DPs on the GPU)  write %.2f\n",
-            us_split / 1e6, us_parse / 1e6, n_parse, us_gpu / 1e6, n_gpu, (long long)n_batches, (long long)n_retry, us_finish / 1e6, n_finish, (long long)n_dp_total, us_write / 1e6);
+    fprintf(stderr, "[bmbs timing] busy seconds summed over threads: split %.2f  parse %.2f (%d thr)  gpu %.2f (%d thr, %lld sub-blocks in %lld launches, %lld capacity retries)  finish %.2f (%d thr, %.2f of it waiting for %lld banded DPs on the GPU)  write %.2f\n",
+            us_split / 1e6, us_parse / 1e6, n_parse, us_gpu / 1e6, n_gpu, (long long)n_batches, (long long)n_launches, (long long)n_retry, us_finish / 1e6, n_finish, us_refine / 1e6, (long long)n_dp_total, us_write / 1e6);
   fclose(fo);
   const double t_map = now() - t1;
   bmbs_index_free(idx);

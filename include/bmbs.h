@@ -122,6 +122,11 @@ int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm);
 /* async D2H of results into the caller's buffers, then wait; returns BMBS_ERR_CAPACITY like above */
 int bmbs_batch_download(bmbs_batch* b, bmbs_read_result* res, bmbs_cand* cand, size_t cand_cap, size_t* cand_used);
 int bmbs_batch_sync(bmbs_batch* b);
+/* Wait for the batch, then say how many entries the download call will write, so that the caller can size its buffers first:
+ * *n_cand entries of cand[] (bmbs_batch_download: the verified windows of every read; bmbs_batch_download_final after
+ * bmbs_batch_finish: the window lists of handed-back reads) and *n_mism mismatch positions (0 unless finished).  Returns what
+ * the download would return for the batch itself (BMBS_ERR_CAPACITY with the candidate slots needed in *n_cand). */
+int bmbs_batch_output_sizes(bmbs_batch* b, size_t* n_cand, size_t* n_mism);
 /* device time of the last bmbs_batch_run in ms (CUDA events on the batch stream), per stage:
  * [0] total [1] pack [2] seed [3] locate [4] votes [5] pair filter [6] verify [7] sensitive pairing + re-seeding round */
 int bmbs_batch_timings(bmbs_batch* b, float ms[8]);

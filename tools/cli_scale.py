@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--reads", type=int, default=10_000_000); ap.add_argument("--scale", type=float, default=None)
 ap.add_argument("--workload", default="cfg3"); ap.add_argument("--out", default="gpurun_out/cli_scale.json"); ap.add_argument("--no-reference", action="store_true")
 ap.add_argument("--threads", type=int, default=os.cpu_count() or 16)
+ap.add_argument("--variants", default="", help="extra runs of our mapper to /dev/null and to a file under environment settings: 'name:K=V,K=V;name2:K=V'")
 a = ap.parse_args()
 scale = a.scale if a.scale is not None else float(os.environ.get("BMBS_BENCH_SCALE", 1.0))
 wl = BN.Workload(a.workload, scale)
@@ -49,6 +50,11 @@ run(EXE, "/dev/null")                                                      # pag
 out["ours_devnull"] = run(EXE, "/dev/null", {"BMBS_TIMING": "1"})
 out["ours"] = run(EXE, "scale_gpu.sam", {"BMBS_TIMING": "1"})
 out["ours_host_finish"] = run(EXE, "/dev/null", {"BMBS_TIMING": "1", "BMBS_HOST_FINISH": "1"})
+for spec in filter(None, a.variants.split(";")):
+    name, _, kv = spec.partition(":")
+    env = {"BMBS_TIMING": "1", **dict(x.split("=", 1) for x in kv.split(",") if x)}
+    out["runs"].append({"name": name, "env": env, "devnull": run(EXE, "/dev/null", env), "file": run(EXE, "scale_var.sam", env)})
+    (d / "scale_var.sam").unlink()
 if REF.exists() and not a.no_reference:
     out["reference"] = run(REF, "scale_ref.sam")
     g, r = digest(d / "scale_gpu.sam"), digest(d / "scale_ref.sam")

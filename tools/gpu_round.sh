@@ -28,7 +28,7 @@ for w in $WHAT; do
         --launch-skip ${NCU_SKIP:-80} --launch-count ${NCU_COUNT:-14} --csv --log-file $O/${TAG}_traffic.csv \
         python bench.py $BENCH_ARGS --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_traffic_bench.log 2>&1; echo "traffic exit $?" ;;
     cliscale)
-      timeout 900 python tools/cli_scale.py --out $O/${TAG}_cli_scale.json > $O/${TAG}_cli_scale.log 2>&1; echo "cli_scale exit $?"; tail -5 $O/${TAG}_cli_scale.log ;;
+      timeout 1500 python tools/cli_scale.py ${CLI_SCALE_ARGS:-} --out $O/${TAG}_cli_scale.json > $O/${TAG}_cli_scale.log 2>&1; echo "cli_scale exit $?"; tail -5 $O/${TAG}_cli_scale.log ;;
     verify)
       timeout 900 python tools/bench_verify.py > $O/${TAG}_verify.json 2> $O/${TAG}_verify.log; echo "bench_verify exit $?"; tail -c 1500 $O/${TAG}_verify.json ;;
     fullverify)

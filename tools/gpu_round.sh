@@ -18,15 +18,15 @@ for w in $WHAT; do
       timeout 600 python bench.py $BENCH_ARGS --impl reference --steps 2 --warmup 1 > $O/${TAG}_bench_reference.json 2>> $O/${TAG}_bench.log; cat $O/${TAG}_bench_reference.json ;;
     launches)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv \
-        python bench.py $BENCH_ARGS --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_launches_bench.log 2>&1; echo "launch list exit $?" ;;
+        python bench.py $BENCH_ARGS --steps 2 --warmup 3 --no-cpu-baseline --no-cfg4 > $O/${TAG}_launches_bench.log 2>&1; echo "launch list exit $?" ;;
     full)
       timeout 900 ncu --set full --clock-control none --import-source on -k "$KERNELS" --launch-skip ${NCU_SKIP:-80} --launch-count ${NCU_COUNT:-14} -f -o $O/${TAG}_full \
-        python bench.py $BENCH_ARGS --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_full_bench.log 2>&1; echo "ncu full exit $?" ;;
+        python bench.py $BENCH_ARGS --steps 2 --warmup 3 --no-cpu-baseline --no-cfg4 > $O/${TAG}_full_bench.log 2>&1; echo "ncu full exit $?" ;;
     traffic)
       # DRAM bytes and duration of one launch of every step kernel at the bench's own scale (one pass: nothing is replayed)
       timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k "$KERNELS" \
         --launch-skip ${NCU_SKIP:-80} --launch-count ${NCU_COUNT:-14} --csv --log-file $O/${TAG}_traffic.csv \
-        python bench.py $BENCH_ARGS --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_traffic_bench.log 2>&1; echo "traffic exit $?" ;;
+        python bench.py $BENCH_ARGS --steps 2 --warmup 3 --no-cpu-baseline --no-cfg4 > $O/${TAG}_traffic_bench.log 2>&1; echo "traffic exit $?" ;;
     cliscale)
       timeout 1500 python tools/cli_scale.py ${CLI_SCALE_ARGS:-} --out $O/${TAG}_cli_scale.json > $O/${TAG}_cli_scale.log 2>&1; echo "cli_scale exit $?"; tail -5 $O/${TAG}_cli_scale.log ;;
     verify)

@@ -603,13 +603,14 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
 
 extern "C" int bmbs_batch_finish(bmbs_batch* b) {
   if (!b || !b->ran) return fail(BMBS_ERR_ARG, "bad argument or batch not run");
-  if (b->pe) return fail(BMBS_ERR_ARG, "bmbs_batch_finish: single-end batches only");
   CU(cudaSetDevice(b->dev));
   cudaStream_t s = b->stream;
   const int n = b->n_reads;
   CU(cudaMemsetAsync(b->d_fc, 0, sizeof(FinCounters), s));
   CU(cudaEventRecord(b->ev[9], s));
-  if (n > 0) {
+  if (n > 0 && b->pe) {
+    finish_pe<<<(n / 2 + 127) / 128, 128, 0, s>>>(b->copy->view, b->v, b->d_fin, b->d_mism, (u32)b->mism_cap, b->d_fc); ++b->launches;
+  } else if (n > 0) {
     finish_se<<<(n + 127) / 128, 128, 0, s>>>(b->copy->view, b->v, b->d_fin, b->d_mism, (u32)b->mism_cap, b->d_long_list, b->d_huge_list, b->d_sort_list, b->d_fc); ++b->launches;
     finish_huge<<<b->sm_count * 2, 256, 0, s>>>(b->copy->view, b->v, b->d_fin, b->d_mism, (u32)b->mism_cap, b->d_fb, (u32)b->fb_cap, b->d_huge_list, b->d_sort_list, b->d_fc); ++b->launches;
     finish_long<<<b->sm_count * 12, 128, 0, s>>>(b->copy->view, b->v, b->d_fin, b->d_mism, (u32)b->mism_cap, b->d_fb, (u32)b->fb_cap, b->d_long_list, b->d_sort_list, b->d_fc); ++b->launches;

@@ -1,0 +1,168 @@
+// Paired-end finishing on the device: what Map_Pair_Seq_split_fast / Map_Pair_Seq_split do after their
+// verification calls, for every pair of a paired batch -- included by bmbs_kernels.cuh.
+//   * hit compaction (map_candidate_votes_mutiple_cut_end_to_end_*_for_paired_end, Schema.cpp:7502-7608): hits within k whose
+//     absolute end differs from the entry before them, in site order;
+//   * filter_pairs_single_side (:16186-16288): the longer list keeps the windows within [dmin, dmax] of a hit of the shorter one;
+//   * new_faster_verify_pairs (:15773-15959): the pair with the smallest err sum, how many pairs share it, second_best_diff as
+//     the running best stood before the winner (first winner kept);
+//   * per chosen mate: try_cigar_without_path (ksw.cpp:2515-2570) and the coordinates, as finish_hit does for single-end reads.
+// One thread per pair walks the lists literally, in the reference's order (the walks carry `first`, a skip pointer whose
+// value depends on every earlier step; lists are a handful of entries outside repeats).  Two bmbs_final records per pair come
+// back (mates 2p, 2p+1) instead of both mates' window lists:
+//   mate 1's record carries the pair's outcome: status BMBS_FIN_UNMAPPED (no pair: both records blank), BMBS_FIN_AMBIGUOUS
+//   (several equally good pairs, not reported), else both mates are BMBS_FIN_UNIQUE (ungapped: chrom_pos, strand, nm, mismatch
+//   positions) or BMBS_FIN_DP (site, end_site, nm = the verifier's err); sbd = second_best_diff of the pair (both records),
+//   BMBS_FINF_AMBIGUOUS = reported although several pairs tie (--ambiguous_out).  A mate that runs over the end of its
+//   chromosome keeps its coordinates: the pair is dropped by the caller's span check (Schema.cpp:22310-22330), as in the reference.
+#pragma once
+
+namespace pe_fin {
+// within [dmin, dmax]?  `first` skips entries that are too far below a; stop: b is too far above (Schema.cpp:15800-15840)
+__device__ __forceinline__ bool in_range(u64 a, u64 b, int dmax, int dmin, long long j, long long& first, bool& stop) {
+  stop = false;
+  if (a > b) { const long long d = (long long)(a - b); if (d > dmax) { first = j + 1; return false; } return d >= dmin; }
+  const long long d = (long long)(b - a);
+  if (d > dmax) { stop = true; return false; }
+  return d >= dmin;
+}
+__device__ __forceinline__ int keep_hits(bmbs_cand* v, int n, u32 k) {
+  int kept = 0; u64 prev = ~0ull;
+  for (int i = 0; i < n; ++i) {
+    const bmbs_cand x = v[i];
+    const u64 e = x.site + (u64)(long long)x.end_site;
+    if ((u32)x.err <= k && prev != e) v[kept++] = x;          // err 0xFFFF (none within k) never passes: k <= 31
+    prev = e;
+  }
+  return kept;
+}
+// b keeps the entries within range of one of a[0..na), each at most once, in order; returns how many
+__device__ __forceinline__ int single_side(const bmbs_cand* a, int na, bmbs_cand* b, int nb, int dmax, int dmin) {
+  long long first = 0; int kept = 0;
+  for (long long i = 0; i < na; ++i) {
+    const u64 as = a[i].site;
+    for (long long j = first; j < nb; ++j) {
+      bool stop; const bool in = in_range(as, b[j].site, dmax, dmin, j, first, stop);
+      if (stop) break;
+      if (in) { b[kept++] = b[j]; first = j + 1; }
+    }
+  }
+  return na > 0 ? kept : 0;
+}
+}  // namespace pe_fin
+
+// finish_hit for a mate: the chromosome-end test is left to the caller (it needs the final span of both mates)
+__device__ __forceinline__ u32 finish_mate_hit(const DevIndex& ix, const BatchView& b, int r, u32 L, u32 k, const bmbs_cand x, unsigned short* mm, bmbs_final& o) {
+  o.site = x.site; o.end_site = x.end_site; o.nm = (uint8_t)x.err;
+  const int start = (int)x.end_site - (int)L + 1;
+  u32 mm_n = 0;
+  if (x.err != 0) {
+    bool ok = start >= 0 && window_inside(ix, x.site, (u64)L + 2ull * k);
+    if (ok) {
+      const uint4* rpl = b.rplanes + plane_chunk_offset(b.offsets, r);
+      for (u32 ch = 0; ch * 32u < L && mm_n <= x.err; ++ch) {
+        u32 mis = diagonal_mismatch_bits(ix, rpl, x.site + (u64)(long long)start, ch, L);
+        while (mis) { const u32 bit = (u32)__ffs(mis) - 1u; mis &= mis - 1u; if (mm_n < (u32)FIN_MM) mm[mm_n] = (unsigned short)(32u * ch + bit); ++mm_n; }
+      }
+      ok = mm_n == x.err;
+    }
+    if (!ok) { o.status = BMBS_FIN_DP; return 0; }
+  }
+  const PlacedDev p = place_hit(ix, x.site, start, (u64)(long long)x.end_site);
+  o.status = BMBS_FIN_UNIQUE;
+  o.chrom_pos = ((u64)p.chrom << 40) | (p.pos & 0xFFFFFFFFFFull);
+  o.flags |= (uint8_t)p.reverse;
+  return mm_n;
+}
+
+__global__ void __launch_bounds__(128) finish_pe(DevIndex ix, BatchView b, bmbs_final* __restrict__ fin, unsigned short* __restrict__ mism, u32 mism_cap,
+                                                 FinCounters* __restrict__ fc) {
+  __shared__ unsigned short s_mm[128][2 * FIN_MM + 2];
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = 2 * p + 1 < b.n_reads;
+  const int r1 = 2 * p, r2 = r1 + 1;
+  bmbs_final o1 = fin_blank(0), o2 = fin_blank(0);
+  unsigned short* mm1 = s_mm[threadIdx.x]; unsigned short* mm2 = mm1 + FIN_MM + 1;
+  u32 n_mm1 = 0, n_mm2 = 0;
+  if (live) {
+    const bmbs_read_result q1 = b.out_res[r1], q2 = b.out_res[r2];
+    const u32 L1 = b.len[r1], L2 = b.len[r2], k1 = b.kk[r1], k2 = b.kk[r2], kl = k1 > k2 ? k1 : k2;
+    o1.k = (uint8_t)k1; o2.k = (uint8_t)k2;
+    int dmax, dmin; pair_bounds(b, r1, r2, dmax, dmin);
+    if (q1.n_cand != 0 && q2.n_cand != 0) {                    // else: a mate without candidates, or nothing survived the distance filter
+      bmbs_cand* v1 = b.out_cand + q1.first_cand; bmbs_cand* v2 = b.out_cand + q2.first_cand;
+      const bool res1 = is_resolved(q1.state), res2 = is_resolved(q2.state);
+      int occ1 = (int)q1.n_cand, occ2 = (int)q2.n_cand;
+      bool none = false;
+      // --pe --sensitive: sens_pair / sens_reseed_finish already left each mate's final hits
+      if (!(b.sensitive || (res1 && res2))) {
+        if (!res1 && !res2) {
+          if (q1.n_cand <= q2.n_cand) {
+            occ1 = pe_fin::keep_hits(v1, occ1, k1);
+            if (occ1 == 0) none = true;
+            else { occ2 = pe_fin::single_side(v1, occ1, v2, occ2, dmax, dmin); occ2 = pe_fin::keep_hits(v2, occ2, k2); }
+          } else {
+            occ2 = pe_fin::keep_hits(v2, occ2, k2);
+            if (occ2 == 0) none = true;
+            else { occ1 = pe_fin::single_side(v2, occ2, v1, occ1, dmax, dmin); occ1 = pe_fin::keep_hits(v1, occ1, k1); }
+          }
+        } else if (res1) occ2 = pe_fin::keep_hits(v2, occ2, k2);
+        else occ1 = pe_fin::keep_hits(v1, occ1, k1);
+      }
+      if (!none) {
+        // the pair pick: smallest err sum, the first such pair, how many, and what the best stood at before it
+        int best = 4 * (int)kl + 2, n_best = 0; long long second = 2LL * best, first = 0, i1 = 0, i2 = 0;
+        bool done = false;
+        if (occ1 > 0 && occ2 > 0)
+          for (int i = 0; i < occ1 && !done; ++i) {
+            const bmbs_cand a = v1[i];
+            for (int j = (int)first; j < occ2; ++j) {
+              const bmbs_cand c = v2[j];
+              bool stop; const bool in = pe_fin::in_range(a.site, c.site, dmax, dmin, j, first, stop);
+              if (stop) break;
+              if (!in) continue;
+              const long long sum = (long long)a.err + c.err;
+              if (sum < best) { second = best; best = (int)sum; i1 = i; i2 = j; n_best = 1; }
+              else if (sum == best) { second = best; ++n_best; if (best == 0) { done = true; break; } }
+            }
+          }
+        u32 sbd = 0;
+        if (n_best && !done) sbd = (u32)(second - best);
+        if (n_best > 1 && !b.amb_out) o1.status = BMBS_FIN_AMBIGUOUS;
+        else if (n_best >= 1) {
+          const uint8_t s8 = (uint8_t)(sbd > 255u ? 255u : sbd);
+          o1.sbd = s8; o2.sbd = s8;
+          if (n_best > 1) { o1.flags |= BMBS_FINF_AMBIGUOUS; o2.flags |= BMBS_FINF_AMBIGUOUS; }
+          n_mm1 = finish_mate_hit(ix, b, r1, L1, k1, v1[i1], mm1, o1);
+          n_mm2 = finish_mate_hit(ix, b, r2, L2, k2, v2[i2], mm2, o2);
+        }
+      }
+    }
+  }
+  {
+    const u32 ndp = (live && o1.status == BMBS_FIN_DP ? 1u : 0u) + (live && o2.status == BMBS_FIN_DP ? 1u : 0u);
+    u32 tot = ndp;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
+    if (lane == 0 && tot) atomicAdd(&fc->n_dp, (unsigned long long)tot);
+  }
+  // one reservation per warp for the mismatch positions
+  const u32 my_mm = n_mm1 + n_mm2;
+  u32 inc_mm = my_mm;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, inc_mm, d); if (lane >= d) inc_mm += t; }
+  const u32 tot_mm = __shfl_sync(0xffffffffu, inc_mm, 31);
+  unsigned long long base_mm = 0;
+  if (lane == 0 && tot_mm) base_mm = atomicAdd(&fc->mism_used, (unsigned long long)tot_mm);
+  base_mm = __shfl_sync(0xffffffffu, base_mm, 0);
+  if (my_mm) {
+    const unsigned long long at = base_mm + inc_mm - my_mm;
+    if (n_mm1) { o1.aux_first = (u32)at; o1.n_aux = n_mm1; }
+    if (n_mm2) { o2.aux_first = (u32)(at + n_mm1); o2.n_aux = n_mm2; }
+    if (at + my_mm <= mism_cap) {
+      for (u32 j = 0; j < n_mm1; ++j) mism[at + j] = mm1[j];
+      for (u32 j = 0; j < n_mm2; ++j) mism[at + n_mm1 + j] = mm2[j];
+    }
+  }
+  if (live) { fin[r1] = o1; fin[r2] = o2; }
+}

@@ -2600,6 +2600,8 @@ __global__ void __launch_bounds__(32 * FIN_SORT_WARPS) finish_sorted(DevIndex ix
   }
 }
 
+#include "bmbs_finish_pe.cuh"
+
 // Test entry (bmbs_debug_sort_order): the order std::sort by vote leaves each list in, through the same warp routine -- the
 // partition phase, then the stable final pass as a counting sort by vote (rank = larger votes + equal votes placed earlier).
 __global__ void __launch_bounds__(32 * FIN_SORT_WARPS) debug_sort_order(const u32* __restrict__ votes, const u32* __restrict__ offsets, u32 n_lists, unsigned short* __restrict__ order, int* __restrict__ okflag) {

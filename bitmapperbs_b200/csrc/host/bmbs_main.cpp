@@ -49,6 +49,7 @@ struct RawBatch { size_t seq_no = 0; size_t n_rec = 0; std::string_view raw1, ra
 struct GpuResult {
   bmbs_final* fin = nullptr; uint16_t* mism = nullptr; bmbs_read_result* res = nullptr; bmbs_cand* cand = nullptr;
   size_t fin_cap = 0, mism_cap = 0, res_cap = 0, cand_cap = 0;
+  std::vector<bmbs_refine_result> dp_res; std::vector<uint32_t> dp_ops;   // the launch's banded DPs (BMBS_FIN_DP reads), in read order
   template <class T> static void grow(T*& p, size_t& cap, size_t need) {
     if (need <= cap) return;
     bmbs_pinned_free(p); cap = need + need / 4 + 1024; p = (T*)bmbs_pinned_alloc(cap * sizeof(T));
@@ -64,7 +65,7 @@ struct Batch {
   std::string flat; std::vector<uint64_t> offsets;   // sequences as aligned (mate 2 reverse-complemented), back to back
   // results of the launch this sub-block was part of: read u of the sub-block is read r0 + u of the launch; slices of cand[] and
   // mism[] are addressed by the records themselves.  final: single end, finished records of the device (cand: handed-back lists)
-  std::shared_ptr<GpuResult> gr; size_t r0 = 0; bool final = false;
+  std::shared_ptr<GpuResult> gr; size_t r0 = 0, dp_first = 0; bool final = false;   // dp_first: the sub-block's first entry of gr->dp_res
   std::string sam; MapStats st;
   std::string_view seq(int i) const { return std::string_view(flat.data() + offsets[i], (size_t)(offsets[i + 1] - offsets[i])); }
 };
@@ -213,6 +214,9 @@ void finish_batch(const HostContext& hc, Batch& b, bool pe, bool unmapped_out, b
       ReadView rv{b.name[u], b.seq(u), b.qual[u], b.fq_seq[u]};
       if (fin) finish_single_final(hc, rv, fin[u], gr.mism, gr.cand, out, st, fs.v1, fs.win, &dq);
       else finish_single(hc, rv, res[u], gr.cand, out, st, fs.v1, fs.win, &dq);
+    } else if (fin) {
+      finish_pair_final(hc, b.name[2 * u], b.seq(2 * u), b.qual[2 * u], b.name[2 * u + 1], b.seq(2 * u + 1), b.fq_seq[2 * u + 1], b.qual[2 * u + 1],
+                        fin[2 * u], fin[2 * u + 1], gr.mism, out, st, fs.win, &dq);
     } else {
       finish_pair(hc, b.name[2 * u], b.seq(2 * u), b.qual[2 * u], b.name[2 * u + 1], b.seq(2 * u + 1), b.fq_seq[2 * u + 1], b.qual[2 * u + 1],
                   res[2 * u], res[2 * u + 1], gr.cand, out, st, fs.v1, fs.v2, fs.win, &dq);
@@ -227,23 +231,10 @@ void finish_batch(const HostContext& hc, Batch& b, bool pe, bool unmapped_out, b
     else { sam_record_unmapped(out, b.name[2 * u], 77, b.fq_seq[2 * u], b.qual[2 * u]); sam_record_unmapped(out, b.name[2 * u + 1], 141, b.fq_seq[2 * u + 1], b.qual[2 * u + 1]); }
   };
   auto add = [&](const MapStats& t) { b.st.reads += t.reads; b.st.unique += t.unique; b.st.ambiguous += t.ambiguous; b.st.bases += t.bases; b.st.err_bases += t.err_bases; };
-  if (!pe && fin) {
-    // single end behind the device finishing: which reads need the banded DP is already known, so their requests are collected
-    // first, one bmbs_refine call answers them, and the records are then written once, in order
-    fs.side.clear();
-    for (int u = 0; u < units; ++u)      // (a read handed back to the host may ask for a DP too: its trial text goes to a scratch buffer)
-      if (fin[u].status == BMBS_FIN_DP || fin[u].status == BMBS_FIN_HOST) { MapStats t; one(u, fs.side, t); }
-    if (!dq.items.empty()) {
-      n_dp += (long long)dq.items.size();
-      dq.res.resize(dq.items.size()); dq.ops.resize(dq.ops_bound);
-      const bmbs_scoring sc{hc.sc.mp_max, hc.sc.mp_min, hc.sc.n_pen, hc.sc.gap_open, hc.sc.gap_ext, hc.sc.q_base};
-      size_t used = 0;
-      const double tr = now();
-      if (bmbs_refine(refiner, dq.seqs.data(), dq.quals.data(), dq.seqs.size(), dq.items.data(), dq.items.size(), &sc, dq.res.data(), dq.ops.data(), dq.ops.size(), &used))
-        die(std::string("gpu CIGAR refinement failed: ") + bmbs_last_error());
-      fs.refine_s += now() - tr;
-    }
-    dq.mode = DpQueue::REPLAY; dq.next = 0;
+  if (fin) {
+    // behind the device finishing: the GPU thread already ran the banded DPs of the whole launch (it knows which reads need one
+    // from their records), so the records are written once, in order, and nothing here waits for the device
+    dq.replay_from(gr.dp_res.data(), gr.dp_ops.data(), b.dp_first);
     for (int u = 0; u < units; ++u) { MapStats t; one(u, b.sam, t); add(t); unmapped(u, b.sam, t); }
     return;
   }
@@ -325,7 +316,7 @@ int search(const Options& o, const std::string& cmdline) {
   const int n_parse = env_int("BMBS_PARSE_THREADS", std::max(1, (o.threads + 2) / 5)), n_finish = env_int("BMBS_FINISH_THREADS", std::max(1, o.threads - n_parse));
   const int n_gpu = inflight * (int)devs.size();
   std::atomic<long long> us_split(0), us_parse(0), us_gpu(0), us_finish(0), us_write(0), n_retry(0), n_batches(0), n_launches(0), us_dev(0), us_up(0), us_run(0), us_down(0), us_prep(0), us_refine(0);
-  std::atomic<long long> us_stage[8] = {};
+  std::atomic<long long> us_stage[8] = {}; std::atomic<long long> n_dp_total(0);
   auto us = [](double a, double b) { return (long long)((b - a) * 1e6); };
   // result buffers of finished launches, handed back by the last sub-block that drops its reference (declared before the queues: it outlives every batch)
   struct ResultPool {
@@ -377,9 +368,10 @@ int search(const Options& o, const std::string& cmdline) {
     // one batch context and one page-locked staging area for the reads per GPU thread, grown on demand
     bmbs_batch* ctx = nullptr; size_t cap_reads = 0, cap_bases = 0, cap_cand = 0;
     char* h_seq = nullptr; uint64_t* h_off = nullptr; size_t h_seq_cap = 0, h_off_cap = 0;
-    // single end: the device finishes the reads (reduction, ungapped CIGAR, coordinates) and one 32-byte record per read comes
-    // back; BMBS_HOST_FINISH=1 keeps the host reduction over the full window lists
-    const bool dev_finish = !pe && !getenv("BMBS_HOST_FINISH");
+    // the device finishes the reads (single end: reduction in the reference's order; pairs: hit compaction, single-side filter, pair
+    // pick; both: ungapped CIGAR check, coordinates) and one 32-byte record per read comes back; BMBS_HOST_FINISH=1 keeps the
+    // host reduction / pair pick over the full window lists
+    const bool dev_finish = !getenv("BMBS_HOST_FINISH");
     auto ensure = [&](size_t reads, size_t bases, size_t cands) {
       if (!ctx || reads > cap_reads || bases > cap_bases || cands > cap_cand) {
         if (ctx) bmbs_batch_free(ctx);
@@ -394,6 +386,11 @@ int search(const Options& o, const std::string& cmdline) {
       const size_t r0 = o.batch_reads * (pe ? 2 : 1) * (size_t)std::min(group_max, 2);
       ensure(r0, r0 * 160 + 64, r0 * 24 + (1u << 20));
     }
+    // the banded DPs of a launch (reads whose ungapped check failed on the device) go to the device in one call from here
+    bmbs_refiner* refiner = nullptr;
+    if (dev_finish && bmbs_refiner_create(idx, dev, &refiner)) die(std::string("refiner create: ") + bmbs_last_error());
+    DpQueue gdq; std::string rq; long long n_dp = 0;
+    const bmbs_scoring bsc{hc.sc.mp_max, hc.sc.mp_min, hc.sc.n_pen, hc.sc.gap_open, hc.sc.gap_ext, hc.sc.q_base};
     std::vector<std::unique_ptr<Batch>> grp;
     std::unique_ptr<Batch> b;
     while (gpu_q.pop(b)) {
@@ -442,19 +439,46 @@ int search(const Options& o, const std::string& cmdline) {
         if (rc) die(std::string("gpu batch failed: ") + bmbs_last_error());
         break;
       }
+      if (dev_finish) {
+        const double tr = now();
+        gdq.clear();
+        size_t r = 0;
+        for (auto& x : grp) {
+          x->dp_first = gdq.items.size();
+          for (int u = 0; u < x->n; ++u) {
+            const bmbs_final& f = gr->fin[r + (size_t)u];
+            if (f.status != BMBS_FIN_DP) continue;
+            const std::string_view sq = x->seq(u), ql = x->qual[(size_t)u];
+            // the DP sees the qualities in the order of the aligned sequence: reversed for mate 2 and for --pbat single-end reads
+            if (pe ? (u & 1) != 0 : hc.pbat) { rq.assign(ql.rbegin(), ql.rend()); gdq.request(f.site, sq.data(), rq.data(), (int)sq.size(), (int)f.k); }
+            else gdq.request(f.site, sq.data(), ql.data(), (int)sq.size(), (int)f.k);
+          }
+          r += (size_t)x->n;
+        }
+        gr->dp_res.resize(gdq.items.size()); gr->dp_ops.resize(gdq.ops_bound);
+        if (!gdq.items.empty()) {
+          n_dp += (long long)gdq.items.size();
+          size_t used = 0;
+          if (bmbs_refine(refiner, gdq.seqs.data(), gdq.quals.data(), gdq.seqs.size(), gdq.items.data(), gdq.items.size(), &bsc, gr->dp_res.data(), gr->dp_ops.data(), gr->dp_ops.size(), &used))
+            die(std::string("gpu CIGAR refinement failed: ") + bmbs_last_error());
+        }
+        us_refine += us(tr, now());
+      }
       us_gpu += us(ts, now());
       size_t r = 0;
       for (auto& x : grp) { x->gr = gr; x->r0 = r; x->final = dev_finish; r += (size_t)x->n; fin_q.push(std::move(x)); }
     }
+    n_dp_total += n_dp;
+    if (refiner) bmbs_refiner_free(refiner);
     if (ctx) bmbs_batch_free(ctx);
     bmbs_pinned_free(h_seq); bmbs_pinned_free(h_off);
     if (--live_gpu == 0) fin_q.close();
   });
-  std::atomic<long long> n_dp_total(0);
   for (int t = 0; t < n_finish; ++t) pool.emplace_back([&, t] {
-    // each finishing thread owns a refiner (stream + device buffers) on one of the GPUs
+    // host finishing (BMBS_HOST_FINISH=1): each finishing thread owns a refiner (stream + device buffers) on one of the GPUs and
+    // sends its sub-block's DPs itself; behind the device finishing the GPU threads have done that already
     bmbs_refiner* refiner = nullptr;
-    if (bmbs_refiner_create(idx, devs[t % devs.size()], &refiner)) die(std::string("refiner create: ") + bmbs_last_error());
+    if (getenv("BMBS_HOST_FINISH") && bmbs_refiner_create(idx, devs[t % devs.size()], &refiner)) die(std::string("refiner create: ") + bmbs_last_error());
     FinishScratch fs; long long n_dp = 0;
     std::unique_ptr<Batch> b;
     std::string raw;
@@ -469,7 +493,7 @@ int search(const Options& o, const std::string& cmdline) {
       }
       us_finish += us(ts, now()); out_q.push(std::move(b));
     }
-    bmbs_refiner_free(refiner);
+    if (refiner) bmbs_refiner_free(refiner);
     n_dp_total += n_dp; us_refine += (long long)(fs.refine_s * 1e6);
     if (--live_finish == 0) out_q.close();
   });
@@ -500,7 +524,7 @@ int search(const Options& o, const std::string& cmdline) {
             us_prep / 1e6, us_up / 1e6, us_run / 1e6, us_down / 1e6, us_dev / 1e6, us_stage[1] / 1e6, us_stage[2] / 1e6, us_stage[3] / 1e6, us_stage[4] / 1e6, us_stage[5] / 1e6, us_stage[6] / 1e6, us_stage[7] / 1e6);
   }
   if (getenv("BMBS_TIMING"))
-    fprintf(stderr, "[bmbs timing] busy seconds summed over threads: split %.2f  parse %.2f (%d thr)  gpu %.2f (%d thr, %lld sub-blocks in %lld launches, %lld capacity retries)  finish %.2f (%d thr, %.2f of it waiting for %lld banded DPs on the GPU)  write %.2f\n",
+    fprintf(stderr, "[bmbs timing] busy seconds summed over threads: split %.2f  parse %.2f (%d thr)  gpu %.2f (%d thr, %lld sub-blocks in %lld launches, %lld capacity retries)  finish %.2f (%d thr)  banded DPs %.2f (%lld on the GPU)  write %.2f\n",
             us_split / 1e6, us_parse / 1e6, n_parse, us_gpu / 1e6, n_gpu, (long long)n_batches, (long long)n_launches, (long long)n_retry, us_finish / 1e6, n_finish, us_refine / 1e6, (long long)n_dp_total, us_write / 1e6);
   fclose(fo);
   const double t_map = now() - t1;

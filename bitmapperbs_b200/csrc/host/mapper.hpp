@@ -173,7 +173,7 @@ inline void finish_single_final(const HostContext& hc, const ReadView& rd, const
     }
     case BMBS_FIN_HOST: {
       bmbs_read_result r{}; r.state = BMBS_VERIFY; r.first_cand = f.aux_first; r.n_cand = f.n_aux; r.is_multiple_map = (uint8_t)f.site;
-      finish_single(hc, rd, r, fb_cand, out, st, hits, win, dq);
+      finish_single(hc, rd, r, fb_cand, out, st, hits, win, dq && dq->external ? nullptr : dq);   // (no queue to ask: the DP on the CPU)
       return;
     }
     default: ++st.reads; return;
@@ -287,6 +287,67 @@ inline void finish_pair(const HostContext& hc, std::string_view name1, std::stri
   if (pk.n == 1) ++st.unique; else ++st.ambiguous;
   st.bases += L1 + L2; st.err_bases += m1.err + m2.err;
   const int mapq = mapq_from(pk.sbd, (unsigned)(k1 + k2), m1.score + m2.score, hc.sc);
+  sam_record_pe(out, true, name1, seq1, std::string_view(), qual1, hc.chroms, m1.flag, m1.chrom, m1.pos, mapq, m1.cigar, m2.pos, tlen, m1.err);
+  sam_record_pe(out, false, name2, seq2, raw2, qual2, hc.chroms, m2.flag, m2.chrom, m2.pos, mapq, m2.cigar, m1.pos, tlen, m2.err);
+}
+
+// ---- paired end, from the device's finished records (bmbs_batch_finish on a paired batch) -----------------------
+// Hit compaction, the single-side filter and the pair pick ran on the device (finish_pe), and so did the ungapped CIGAR check
+// and the coordinates of the two chosen hits; what is left here mirrors the tail of finish_pair: the score of the returned
+// mismatch positions (mate 2's qualities are read from the other end: it was aligned as its reverse complement), the banded DP
+// of BMBS_FIN_DP mates through `dq`, TLEN and its limits, the chromosome-end check, MAPQ, the two records.
+inline void finish_pair_final(const HostContext& hc, std::string_view name1, std::string_view seq1, std::string_view qual1,
+                              std::string_view name2, std::string_view seq2, std::string_view raw2, std::string_view qual2,
+                              const bmbs_final& f1, const bmbs_final& f2, const uint16_t* mism,
+                              std::string& out, MapStats& st, std::vector<char>& win, DpQueue* dq = nullptr) {
+  ++st.reads;
+  if (f1.status == BMBS_FIN_AMBIGUOUS) { ++st.ambiguous; return; }
+  if (f1.status == BMBS_FIN_UNMAPPED) return;
+  const int L1 = (int)seq1.size(), L2 = (int)seq2.size();
+  const uint64_t k1 = threshold_k(hc.prm.e_rate, L1), k2 = threshold_k(hc.prm.e_rate, L2);
+  if (dq && dq->mode == DpQueue::COLLECT) {          // the requests of this pair, mate 1 first; the records are written in the replay pass
+    if (f1.status == BMBS_FIN_DP) dq->request(f1.site, seq1.data(), qual1.data(), L1, (int)k1);
+    if (f2.status == BMBS_FIN_DP) { std::string rq(qual2.rbegin(), qual2.rend()); dq->request(f2.site, seq2.data(), rq.data(), L2, (int)k2); }
+    return;
+  }
+  auto mate = [&](const bmbs_final& f, std::string_view seq, std::string_view qual, uint64_t k, bool reverse_quality, pe::Mate& m) {
+    const int L = (int)seq.size();
+    if (f.status == BMBS_FIN_UNIQUE) {
+      int score = 0;
+      for (uint32_t j = 0; j < f.n_aux; ++j) {
+        const int pos = mism[f.aux_first + j];
+        if (seq[pos] == 'N') score -= hc.sc.n_pen; else score -= mismatch_penalty(hc.sc, qual[reverse_quality ? L - 1 - pos : pos]);
+      }
+      m.err = f.nm; m.score = score; m.span = L;
+      char cg[16]; int cp = 16; cg[--cp] = 'M';
+      { unsigned v = (unsigned)L; do { cg[--cp] = (char)('0' + v % 10); v /= 10; } while (v); }
+      m.cigar.assign(cg + cp, (size_t)(16 - cp));
+      m.flag = (f.flags & BMBS_FINF_REVERSE) ? 16 : 0; m.chrom = (size_t)(f.chrom_pos >> 40); m.pos = f.chrom_pos & 0xFFFFFFFFFFull;
+      return;
+    }
+    Refined rf;
+    const bool forward = f.site < hc.chroms.N;
+    if (dq) dq->take(forward, rf);
+    else {                                             // no device queue (tests): the whole refinement on the CPU
+      const int plen = L + 2 * (int)k; win.resize(plen + 8);
+      hc.genome.window(f.site, plen, win.data());
+      refine_alignment(win.data(), plen, seq.data(), L, (int)k, (int)f.end_site, f.nm, forward, qual.data(), reverse_quality, hc.sc, rf, f.site, nullptr);
+    }
+    m.err = rf.err; m.score = rf.score; m.cigar = rf.cigar; m.span = (int)(rf.end_site - rf.start_site + 1);
+    const Placed p = place(hc.chroms, f.site, (uint64_t)(int64_t)rf.start_site, rf.end_site);
+    m.flag = p.flag; m.chrom = p.chrom; m.pos = p.pos;
+  };
+  pe::Mate m1, m2;
+  mate(f1, seq1, qual1, k1, false, m1);
+  mate(f2, seq2, qual2, k2, true, m2);
+  long long lo = (long long)std::min(m1.pos, m2.pos), hi = std::max((long long)m1.pos + m1.span - 1, (long long)m2.pos + m2.span - 1);
+  const int tlen = (int)(hi - lo + 1);                     // calculate_TLEN, Schema.h:1587-1600
+  if (!(tlen <= hc.prm.max_ins && tlen >= hc.prm.min_ins)) return;
+  if (!(m1.pos + m1.span <= hc.chroms.len[m1.chrom] + 1 && m2.pos + m2.span <= hc.chroms.len[m2.chrom] + 1)) return;
+  if (f1.flags & BMBS_FINF_AMBIGUOUS) ++st.ambiguous; else ++st.unique;
+  st.bases += L1 + L2; st.err_bases += m1.err + m2.err;
+  const unsigned sbd = f1.sbd == 255 ? 0xFFFFu : f1.sbd;
+  const int mapq = mapq_from(sbd, (unsigned)(k1 + k2), m1.score + m2.score, hc.sc);
   sam_record_pe(out, true, name1, seq1, std::string_view(), qual1, hc.chroms, m1.flag, m1.chrom, m1.pos, mapq, m1.cigar, m2.pos, tlen, m1.err);
   sam_record_pe(out, false, name2, seq2, raw2, qual2, hc.chroms, m2.flag, m2.chrom, m2.pos, mapq, m2.cigar, m1.pos, tlen, m2.err);
 }

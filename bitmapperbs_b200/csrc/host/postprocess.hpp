@@ -255,7 +255,11 @@ struct DpQueue {
   bool pending = false;                                 // COLLECT: the current unit asked for a DP
   std::string seqs, quals; std::vector<bmbs_refine_item> items; size_t ops_bound = 0;
   std::vector<bmbs_refine_result> res; std::vector<uint32_t> ops; size_t next = 0;   // REPLAY
-  void clear() { mode = COLLECT; pending = false; seqs.clear(); quals.clear(); items.clear(); ops_bound = 0; res.clear(); ops.clear(); next = 0; }
+  // REPLAY from results that live elsewhere (the mapper refines a whole launch's alignments in one call and every sub-block
+  // replays its own range); reads handed back to the host reduction then run their DP on the CPU
+  const bmbs_refine_result* xres = nullptr; const uint32_t* xops = nullptr; bool external = false;
+  void clear() { mode = COLLECT; pending = false; seqs.clear(); quals.clear(); items.clear(); ops_bound = 0; res.clear(); ops.clear(); next = 0; xres = nullptr; xops = nullptr; external = false; }
+  void replay_from(const bmbs_refine_result* r, const uint32_t* o, size_t first) { mode = REPLAY; external = true; xres = r; xops = o; next = first; }
   // COLLECT: one alignment for the device (read as aligned, qualities in the DP's order)
   void request(uint64_t site, const char* read, const char* qual, int rlen, int k) {
     bmbs_refine_item it; it.site = site; it.seq_off = (uint32_t)seqs.size(); it.len = (uint16_t)rlen; it.k = (uint8_t)k; it.pad = 0;
@@ -265,7 +269,8 @@ struct DpQueue {
   }
   // REPLAY: the next result as the reference's (start, end, NM, score, CIGAR); a reverse-strand hit prints its operations last to first
   template <class R> void take(bool forward, R& out) {
-    const bmbs_refine_result& r = res[next++];
+    const bmbs_refine_result& r = external ? xres[next++] : res[next++];
+    const uint32_t* ops = external ? xops : this->ops.data();
     out.score = r.score; out.start_site = r.qb; out.end_site = (uint64_t)(int64_t)r.qe; out.err = r.nm;
     out.cigar.clear();
     char buf[16];

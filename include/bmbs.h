@@ -183,7 +183,16 @@ typedef struct {
   uint8_t k;            /* the read's error threshold                                                                    */
   uint32_t n_aux;
 } bmbs_final;           /* 32 bytes */
-/* Enqueue the finishing kernels behind bmbs_batch_run on the batch's stream (single-end batches only). */
+/* Enqueue the finishing kernels behind bmbs_batch_run on the batch's stream.
+ * Paired batches: what Map_Pair_Seq_split_fast / Map_Pair_Seq_split do after their verification calls --
+ * hit compaction (Schema.cpp:7502-7608), filter_pairs_single_side (:16186-16288), the pair pick new_faster_verify_pairs
+ * (:15773-15959: smallest err sum, the first such pair, how many, second_best_diff), then try_cigar_without_path and the
+ * coordinates of the two chosen hits.  fin[2p], fin[2p+1] are the mates of pair p: fin[2p].status = BMBS_FIN_UNMAPPED (no pair),
+ * BMBS_FIN_AMBIGUOUS (several equally good pairs, not reported), else each mate is BMBS_FIN_UNIQUE (ungapped: chrom_pos,
+ * strand, nm, mismatch positions) or BMBS_FIN_DP (site, end_site, nm = the verifier's err); sbd = the pair's second_best_diff
+ * (255 = more); BMBS_FINF_AMBIGUOUS = reported although several pairs tie (--ambiguous_out).  A mate that runs over the end of
+ * its chromosome keeps its coordinates (the caller's span check drops the pair, Schema.cpp:22310-22330).  The window lists of
+ * the batch are compacted in place: bmbs_batch_download is not meaningful after this call.  No window lists come back. */
 int bmbs_batch_finish(bmbs_batch* b);
 /* Wait, then copy back fin[n_reads], the mismatch positions and the window lists of handed-back reads.
  * BMBS_ERR_CAPACITY with the needed sizes in *mism_used / *cand_used when a caller buffer is too small. */

@@ -298,10 +298,14 @@ def test_verify_error_rate_other_than_default(gidx, oidx):
     ("pe100h", ["--seq1", "pe100h_1.fq", "--seq2", "pe100h_2.fq", "--pe"]),
     ("pe100hs", ["--seq1", "pe100h_1.fq", "--seq2", "pe100h_2.fq", "--pe", "--sensitive"]),
 ])
-def test_mapper_sam_identical_to_reference_golden(golden, built, name, args):
-    """whole program: FASTQ -> GPU seed-and-verify through the C ABI -> host CIGAR/MAPQ -> SAM, vs the reference's SAM"""
+@pytest.mark.parametrize("finish", ["device", "host"])
+def test_mapper_sam_identical_to_reference_golden(golden, built, name, args, finish):
+    """whole program: FASTQ -> GPU seed-and-verify through the C ABI -> finishing (device: reduction / pair pick, ungapped CIGAR,
+    coordinates, banded DP per launch; host: the same from the window lists) -> MAPQ -> SAM, vs the reference's SAM"""
+    import os
+    env = {**os.environ, **({"BMBS_HOST_FINISH": "1"} if finish == "host" else {})}
     subprocess.run([str(built["bmbs"]), "--search", "genome.fa", *args, "-t", "4", "-o", "gpu.sam", "--mapstats", "gpu.stats", "--batch", "700"],
-                   cwd=golden, check=True, stderr=subprocess.DEVNULL)
+                   cwd=golden, check=True, stderr=subprocess.DEVNULL, env=env)
     assert sam_body(golden / "gpu.sam") == sam_body(golden / f"{name}.sam")
     assert (golden / "gpu.stats").read_text() == (golden / f"ref_{name}.stats").read_text()
 

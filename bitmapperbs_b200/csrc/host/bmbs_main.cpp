@@ -23,6 +23,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <sys/stat.h>
 #include <unistd.h>
 #include "../../../include/bmbs.h"
 #include "../../indexer/build_index.hpp"
@@ -52,7 +53,7 @@ struct GpuResult {
   std::vector<bmbs_refine_result> dp_res; std::vector<uint32_t> dp_ops;   // the launch's banded DPs (BMBS_FIN_DP reads), in read order
   template <class T> static void grow(T*& p, size_t& cap, size_t need) {
     if (need <= cap) return;
-    bmbs_pinned_free(p); cap = need + need / 4 + 1024; p = (T*)bmbs_pinned_alloc(cap * sizeof(T));
+    bmbs_pinned_free(p); cap = 2 * need + 1024; p = (T*)bmbs_pinned_alloc(cap * sizeof(T));
     if (!p) { fprintf(stderr, "bmbs: cannot allocate page-locked result buffers\n"); exit(1); }
   }
   ~GpuResult() { bmbs_pinned_free(fin); bmbs_pinned_free(mism); bmbs_pinned_free(res); bmbs_pinned_free(cand); }
@@ -154,6 +155,11 @@ void parse_batch(RawBatch& rb, bool pe, bool pbat_se, Batch& b) {
   const bool o1 = rb.raw1.data() == rb.own1.data(), o2 = rb.raw2.data() == rb.own2.data();
   b.own1 = std::move(rb.own1); b.own2 = std::move(rb.own2);
   b.raw1 = o1 ? std::string_view(b.own1) : rb.raw1; b.raw2 = o2 ? std::string_view(b.own2) : rb.raw2;
+  if (rb.n_rec == SIZE_MAX) {      // a block cut by bytes (single end, mapped input): its records are counted here
+    size_t lines = count_newlines(b.raw1.data(), b.raw1.size());
+    if (!b.raw1.empty() && b.raw1.back() != '\n') ++lines;
+    rb.n_rec = lines / 4;
+  }
   const size_t n = rb.n_rec * (pe ? 2 : 1);
   b.n = (int)n;
   b.name.resize(n); b.qual.resize(n); b.fq_seq.resize(n);
@@ -334,6 +340,10 @@ int search(const Options& o, const std::string& cmdline) {
   // batches that have been written out go back to the parsers with their buffers (a fresh 25 MB text buffer per sub-block costs
   // more in page faults than the text that goes into it)
   Channel<std::unique_ptr<Batch>> spare((size_t)(2 * n_gpu * group_max + 8 * n_finish + 2 * n_parse));
+  // a plain single-end file is cut into blocks by size at record boundaries (no pass over the text in this one thread); pairs
+  // and gzip input are cut by counting lines, the two files of a pair side by side (BMBS_SPLIT_SCAN=1: always by lines)
+  const bool by_bytes = !pe && q1.mapped() && !getenv("BMBS_SPLIT_SCAN");
+  const size_t block_bytes = by_bytes ? o.batch_reads * q1.bytes_per_record() : 0;
   std::thread splitter([&] {
     size_t seq_no = 0;
     for (;;) {
@@ -342,7 +352,8 @@ int search(const Options& o, const std::string& cmdline) {
       size_t n2 = 0;
       std::thread second;                              // the two files of a pair are split side by side
       if (pe) second = std::thread([&] { n2 = q2.next(o.batch_reads, rb->raw2, rb->own2); });
-      rb->n_rec = q1.next(o.batch_reads, rb->raw1, rb->own1);
+      if (by_bytes) rb->n_rec = q1.next_bytes(block_bytes, rb->raw1) ? SIZE_MAX : 0;      // records counted by the parse worker
+      else rb->n_rec = q1.next(o.batch_reads, rb->raw1, rb->own1);
       if (pe) { second.join(); if (n2 < rb->n_rec) rb->n_rec = n2; }   // the shorter file ends the run, as in the reference's paired reader
       us_split += us(ts, now());
       if (rb->n_rec == 0) break;
@@ -372,19 +383,26 @@ int search(const Options& o, const std::string& cmdline) {
     // pick; both: ungapped CIGAR check, coordinates) and one 32-byte record per read comes back; BMBS_HOST_FINISH=1 keeps the
     // host reduction / pair pick over the full window lists
     const bool dev_finish = !getenv("BMBS_HOST_FINISH");
+    // (re-creating a context or re-locking host memory costs milliseconds and serialises the GPU threads in the driver: the first
+    // launch that outgrows the initial two sub-blocks gets room for a full group at once)
+    const size_t full_reads = o.batch_reads * (pe ? 2 : 1) * (size_t)group_max;
     auto ensure = [&](size_t reads, size_t bases, size_t cands) {
       if (!ctx || reads > cap_reads || bases > cap_bases || cands > cap_cand) {
-        if (ctx) bmbs_batch_free(ctx);
+        if (ctx) {
+          bmbs_batch_free(ctx);
+          const size_t per_read = reads ? bases / reads + 1 : 160;
+          reads = std::max(reads, full_reads + full_reads / 16); bases = std::max(bases, reads * per_read + 64); cands = std::max(cands, reads * 24 + (1u << 20));
+        }
         cap_reads = std::max(cap_reads, reads); cap_bases = std::max(cap_bases, bases); cap_cand = std::max(cap_cand, cands);
         if (bmbs_batch_create(idx, dev, cap_reads, cap_bases, cap_cand, &ctx)) die(std::string("batch create: ") + bmbs_last_error());
       }
-      if (bases > h_seq_cap) { bmbs_pinned_free(h_seq); h_seq_cap = bases + bases / 8; h_seq = (char*)bmbs_pinned_alloc(h_seq_cap); }
-      if (reads + 1 > h_off_cap) { bmbs_pinned_free(h_off); h_off_cap = reads + reads / 8 + 1; h_off = (uint64_t*)bmbs_pinned_alloc(h_off_cap * sizeof(uint64_t)); }
+      if (cap_bases > h_seq_cap) { bmbs_pinned_free(h_seq); h_seq_cap = cap_bases; h_seq = (char*)bmbs_pinned_alloc(h_seq_cap); }
+      if (cap_reads + 1 > h_off_cap) { bmbs_pinned_free(h_off); h_off_cap = cap_reads + 1; h_off = (uint64_t*)bmbs_pinned_alloc(h_off_cap * sizeof(uint64_t)); }
       if (!h_seq || !h_off) die("cannot allocate page-locked staging buffers");
     };
-    {   // sized for a typical launch before the first sub-block arrives (a short input never grows it)
+    {   // sized for two sub-blocks before the first one arrives (a short input never grows it)
       const size_t r0 = o.batch_reads * (pe ? 2 : 1) * (size_t)std::min(group_max, 2);
-      ensure(r0, r0 * 160 + 64, r0 * 24 + (1u << 20));
+      ensure(r0 + r0 / 16, r0 * 160 + 64, r0 * 24 + (1u << 20));
     }
     // the banded DPs of a launch (reads whose ungapped check failed on the device) go to the device in one call from here
     bmbs_refiner* refiner = nullptr;
@@ -498,26 +516,54 @@ int search(const Options& o, const std::string& cmdline) {
     if (--live_finish == 0) out_q.close();
   });
 
+  // Output.  This thread puts the finished sub-blocks back in input order.  Into a regular file their text is then written by a
+  // few writer threads, each block at the offset its predecessors' sizes give it (one thread copying 350 bytes per read into
+  // the page cache would be the slowest stage of the program); anything else (a pipe, /dev/null) is written here, in order.
   MapStats total;
+  struct stat ost; const int ofd = fileno(fo);
+  const bool positioned = fstat(ofd, &ost) == 0 && S_ISREG(ost.st_mode);
+  const int n_write = positioned ? env_int("BMBS_WRITE_THREADS", 3) : 0;
+  off_t out_off = positioned ? lseek(ofd, 0, SEEK_CUR) : 0;
+  struct WriteJob { std::unique_ptr<Batch> b; off_t off = 0; };
+  Channel<WriteJob> write_q((size_t)(4 * std::max(1, n_write)));
+  auto recycle = [&](std::unique_ptr<Batch>& done) { done->sam.clear(); done->st = MapStats(); done->gr.reset(); spare.try_push(done); };
+  std::vector<std::thread> writers;
+  for (int t = 0; t < n_write; ++t) writers.emplace_back([&] {
+    WriteJob j;
+    while (write_q.pop(j)) {
+      const double ts = now();
+      const char* p = j.b->sam.data(); size_t n = j.b->sam.size(); off_t at = j.off;
+      while (n) { const ssize_t w = ::pwrite(ofd, p, n, at); if (w <= 0) die("write failed on " + o.out); p += w; n -= (size_t)w; at += w; }
+      us_write += us(ts, now());
+      recycle(j.b);
+    }
+  });
   {
     std::map<size_t, std::unique_ptr<Batch>> pending; size_t next = 0;
     std::unique_ptr<Batch> b;
     while (out_q.pop(b)) {
       pending[b->seq_no] = std::move(b);
       while (!pending.empty() && pending.begin()->first == next) {
-        Batch& x = *pending.begin()->second;
-        const double ts = now();
-        write_all(x.sam.data(), x.sam.size());
-        us_write += us(ts, now());
-        total.reads += x.st.reads; total.unique += x.st.unique; total.ambiguous += x.st.ambiguous; total.bases += x.st.bases; total.err_bases += x.st.err_bases;
         std::unique_ptr<Batch> done = std::move(pending.begin()->second);
         pending.erase(pending.begin()); ++next;
-        done->sam.clear(); done->st = MapStats(); done->gr.reset();
-        spare.try_push(done);
+        const Batch& x = *done;
+        total.reads += x.st.reads; total.unique += x.st.unique; total.ambiguous += x.st.ambiguous; total.bases += x.st.bases; total.err_bases += x.st.err_bases;
+        if (n_write) { WriteJob j; j.off = out_off; out_off += (off_t)x.sam.size(); j.b = std::move(done); write_q.push(std::move(j)); }
+        else {
+          const double ts = now();
+          write_all(x.sam.data(), x.sam.size());
+          us_write += us(ts, now());
+          recycle(done);
+        }
       }
     }
   }
-  if (o.bam) { std::string z; BamWriter::eof_marker(z); write_all(z.data(), z.size()); }
+  write_q.close(); for (auto& w : writers) w.join();
+  if (o.bam) {
+    std::string z; BamWriter::eof_marker(z);
+    if (n_write) { if (::pwrite(ofd, z.data(), z.size(), out_off) != (ssize_t)z.size()) die("write failed on " + o.out); }
+    else write_all(z.data(), z.size());
+  }
   splitter.join(); for (auto& w : pool) w.join();
   if (getenv("BMBS_TIMING")) {
     fprintf(stderr, "[bmbs timing] gpu threads: prepare %.2f  upload %.2f  run(enqueue) %.2f  download(wait+copy) %.2f  | device %.3f s: pack %.3f seed %.3f locate %.3f votes %.3f pairfilter %.3f verify %.3f sensitive %.3f\n",

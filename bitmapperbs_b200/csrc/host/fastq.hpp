@@ -123,7 +123,38 @@ class FastqBlockReader {
     pos_ = end;
     return rec;
   }
+  bool mapped() const { return map_ != nullptr; }
+  // Plain (mapped) input of 4-line records: the next ~target bytes as a view, cut at a record boundary that is found by looking
+  // at the lines around the cut -- the text is not scanned here (the parse workers count the records of their block).  A record
+  // starts at a line that begins with '@' and whose next line but one begins with '+'; a quality line may begin with '@' as
+  // well, but two lines below it stands a sequence.  Returns the number of bytes, 0 at end of input.
+  size_t next_bytes(size_t target, std::string_view& view) {
+    if (pos_ >= map_size_) return 0;
+    size_t end = pos_ + (target ? target : 1);
+    end = end >= map_size_ ? map_size_ : record_start_after(end);
+    view = std::string_view(map_ + pos_, end - pos_);
+    pos_ = end;
+    return view.size();
+  }
+  // bytes per record over the first (up to) 64 records of the input: sizes the blocks of next_bytes
+  size_t bytes_per_record() const {
+    size_t at = 0, lines = 0;
+    while (lines < 256 && at < map_size_) { const char* nl = (const char*)memchr(map_ + at, '\n', map_size_ - at); at = nl ? (size_t)(nl - map_) + 1 : map_size_; ++lines; }
+    return lines >= 4 ? at / (lines / 4) : (at ? at : 1);
+  }
  private:
+  size_t record_start_after(size_t at) const {
+    size_t p = at, l[6];
+    if (p > 0 && map_[p - 1] != '\n') { const char* nl = (const char*)memchr(map_ + p, '\n', map_size_ - p); if (!nl) return map_size_; p = (size_t)(nl - map_) + 1; }
+    for (int i = 0; i < 6; ++i) {
+      if (p >= map_size_) return map_size_;              // fewer than six lines left: the tail goes out with this block
+      l[i] = p;
+      const char* nl = (const char*)memchr(map_ + p, '\n', map_size_ - p);
+      p = nl ? (size_t)(nl - map_) + 1 : map_size_;
+    }
+    for (int i = 0; i < 4; ++i) if (map_[l[i]] == '@' && map_[l[i + 2]] == '+') return l[i];
+    return map_size_;                                    // not 4-line FASTQ: one block, the parser reports what it finds
+  }
   // gzip path: up to max_rec records -> out (ends with '\n')
   size_t next_copy(size_t max_rec, std::string& out) {
     out.clear();

@@ -50,3 +50,25 @@ def test_block_reader(harness, tmp_path, n, per, variant):
     total, got = run(harness, p, per)
     assert total == n
     assert got == [tuple(x) for x in expect]
+
+
+@pytest.mark.parametrize("n", [1, 5, 1000])
+@pytest.mark.parametrize("target", [1, 7, 50, 333, 4096, 10 ** 9])
+@pytest.mark.parametrize("variant", ["plain", "no_final_newline", "crlf", "truncated", "at_quality"])
+def test_blocks_cut_by_size_hold_whole_records(harness, tmp_path, n, target, variant):
+    """the single-end splitter cuts a mapped file every `target` bytes at the next record boundary without scanning the text:
+    every record comes out once, in order, whatever the block size -- also when quality lines begin with '@' or '+'"""
+    recs, text = records(n, crlf=variant == "crlf")
+    if variant == "at_quality":      # qualities that look like header / separator lines
+        recs = [(r[0], r[1], r[2], ("@+"[i % 2] + r[3][1:])) for i, r in enumerate(recs)]
+        text = "".join("\n".join(r) + "\n" for r in recs)
+    expect = [(r[0], r[1], r[3]) for r in recs]
+    if variant == "no_final_newline":
+        text = text[:-1]
+    if variant == "truncated":
+        text += "@partial\nACGT\n"
+    p = tmp_path / "r.fq"
+    p.write_text(text)
+    out = subprocess.run([str(harness), str(p), "1", str(target)], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert int(out[-1].split()[1]) == n
+    assert [tuple(l.split("\t")) for l in out[:-1]] == [tuple(x) for x in expect]

@@ -1109,10 +1109,23 @@ __device__ __forceinline__ void warp_encode_runs(BatchView& b, int r, u32 beg, u
   if (lane == 0) b.nv[r] = base;
 }
 
-// one warp per segment of 33..256 candidates (eight keys per lane)
+// a warp sorts the n <= 32 E keys of a segment (E consecutive keys per lane) and leaves them, ascending, in a[0 .. 32 E)
+template <int E>
+__device__ __forceinline__ void warp_sort_keys(const u64* __restrict__ src, u32 n, u64* a, int lane) {
+  u64 v[E];
+#pragma unroll
+  for (int i = 0; i < E; ++i) { const u32 e = (u32)lane * E + i; v[i] = e < n ? src[e] : ~0ull; }
+  bitonic_regs<E, 32>(v, lane, nullptr);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < E; ++i) a[lane * E + i] = v[i];
+  __syncwarp();
+}
+
+// one warp per segment of 33..256 candidates: two, four or eight keys per lane -- the network over 64 keys is a seventh of the
+// work of the one over 256, and most of these segments are short
 __global__ void __launch_bounds__(128) votes_mid(BatchView b) {
-  constexpr int E = 8;
-  __shared__ u64 s_keys[4][32 * E];
+  __shared__ u64 s_keys[4][32 * 8];
   const u32 nlist = *b.status ? 0u : b.sort_count[2];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const u32 warps = gridDim.x * (blockDim.x >> 5);
@@ -1120,14 +1133,9 @@ __global__ void __launch_bounds__(128) votes_mid(BatchView b) {
   for (u32 g = blockIdx.x * (blockDim.x >> 5) + wid; g < nlist; g += warps) {
     const int r = (int)b.mid_list[g];
     const u32 beg = b.coff[r], n = b.coff[r + 1] - beg;
-    u64 v[E];
-#pragma unroll
-    for (int i = 0; i < E; ++i) { const u32 e = (u32)lane * E + i; v[i] = e < n ? b.cand[beg + e] : ~0ull; }
-    bitonic_regs<E, 32>(v, lane, nullptr);
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < E; ++i) a[lane * E + i] = v[i];
-    __syncwarp();
+    if (n <= 64) warp_sort_keys<2>(b.cand + beg, n, a, lane);
+    else if (n <= 128) warp_sort_keys<4>(b.cand + beg, n, a, lane);
+    else warp_sort_keys<8>(b.cand + beg, n, a, lane);
     if (b.round == 0 && b.state[r] == BMBS_MULTI_EXACT) {
       for (u32 i = lane; i < n; i += 32) { b.cand[beg + i] = a[i]; b.vcnt[beg + i] = 0; }
       if (lane == 0) b.nv[r] = n;
@@ -1136,23 +1144,30 @@ __global__ void __launch_bounds__(128) votes_mid(BatchView b) {
   }
 }
 
-// one CTA of 128 threads per segment of 257..1024 candidates (eight keys per thread)
+// a CTA of T threads sorts the n <= T E keys of a segment and leaves them, ascending, in keys[0 .. T E)
+template <int E, int T>
+__device__ __forceinline__ void block_sort_keys(const u64* __restrict__ src, u32 n, u64* keys, int tid) {
+  u64 v[E];
+#pragma unroll
+  for (int i = 0; i < E; ++i) { const u32 e = (u32)tid * E + i; v[i] = e < n ? src[e] : ~0ull; }
+  bitonic_regs<E, T>(v, tid, keys);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < E; ++i) keys[tid * E + i] = v[i];
+  __syncthreads();
+}
+
+// one CTA of 128 threads per segment of 257..1024 candidates (four keys per thread up to 512, eight beyond)
 __global__ void __launch_bounds__(128) votes_big1k(BatchView b) {
-  constexpr int E = 8, T = 128;
-  __shared__ u64 s_keys[E * T];
+  constexpr int T = 128;
+  __shared__ u64 s_keys[8 * T];
   const u32 nlist = *b.status ? 0u : b.sort_count[3];
   const int tid = threadIdx.x, lane = tid & 31;
   for (u32 g = blockIdx.x; g < nlist; g += gridDim.x) {
     const int r = (int)b.big1k_list[g];
     const u32 beg = b.coff[r], n = b.coff[r + 1] - beg;
-    u64 v[E];
-#pragma unroll
-    for (int i = 0; i < E; ++i) { const u32 e = (u32)tid * E + i; v[i] = e < n ? b.cand[beg + e] : ~0ull; }
-    bitonic_regs<E, T>(v, tid, s_keys);
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < E; ++i) s_keys[tid * E + i] = v[i];
-    __syncthreads();
+    if (n <= 4 * T) block_sort_keys<4, T>(b.cand + beg, n, s_keys, tid);
+    else block_sort_keys<8, T>(b.cand + beg, n, s_keys, tid);
     if (b.round == 0 && b.state[r] == BMBS_MULTI_EXACT) {
       for (u32 i = tid; i < n; i += T) { b.cand[beg + i] = s_keys[i]; b.vcnt[beg + i] = 0; }
       if (tid == 0) b.nv[r] = n;

@@ -285,12 +285,11 @@ def measure_cfg4(B, capi, torch, index, dev, d, scale, pairs, rank, steps, warmu
         batches = [B.Batch(index, dev, n_reads, bases + 64, cand_cap) for _ in range(2)]
         try:
             batches[0].upload(flat, offs, pe=True); batches[0].run(prm); batches[0].sync()
-            bufs = []
-            for _ in batches:
-                hr = torch.empty(n_reads * capi.ReadResult.itemsize, dtype=torch.uint8, pin_memory=True)
-                hc = torch.empty(cand_cap * capi.Cand.itemsize, dtype=torch.uint8, pin_memory=True)
-                bufs.append((hr, hc, hr.numpy().view(capi.ReadResult), hc.numpy().view(capi.Cand)))
-            _, _, used = batches[0].download(bufs[0][2], bufs[0][3])
+            hr = torch.empty(n_reads * capi.ReadResult.itemsize, dtype=torch.uint8, pin_memory=True)
+            hc = torch.empty(cand_cap * capi.Cand.itemsize, dtype=torch.uint8, pin_memory=True)
+            res, _, used = batches[0].download(hr.numpy().view(capi.ReadResult), hc.numpy().view(capi.Cand))
+            states = np.bincount(res["state"], minlength=5)
+            del hr, hc
             break
         except B.BmbsError as e:
             for x in batches:
@@ -298,31 +297,44 @@ def measure_cfg4(B, capi, torch, index, dev, d, scale, pairs, rank, steps, warmu
             if e.code != -4:
                 raise
             cand_cap *= 2
-    res = bufs[0][2]
-    states = np.bincount(res["state"], minlength=5)
+    # the pairs are finished on the device too (hit compaction, pair pick, ungapped CIGAR check, coordinates): two 32-byte records
+    # per pair and the mismatch positions come back instead of the mates' hit lists
+    bufs = []
+    for _ in batches:
+        hf = torch.empty(n_reads * capi.Final.itemsize, dtype=torch.uint8, pin_memory=True)
+        hm = torch.empty((32 * n_reads + 64) * 2, dtype=torch.uint8, pin_memory=True)
+        hb = torch.empty((1 << 16) * capi.Cand.itemsize, dtype=torch.uint8, pin_memory=True)
+        bufs.append((hf, hm, hb, hf.numpy().view(capi.Final), hm.numpy().view(np.uint16), hb.numpy().view(capi.Cand)))
+
+    def down(i):
+        _, mm, fb = batches[i].download_final(bufs[i][3], bufs[i][4], bufs[i][5])
+        return n_reads * capi.Final.itemsize + 2 * len(mm) + capi.Cand.itemsize * len(fb)
     for i in range(max(warmup, 2)):
-        b = batches[i % 2]; b.upload(flat, offs, pe=True); b.run(prm); b.download(bufs[i % 2][2], bufs[i % 2][3])
+        b = batches[i % 2]; b.upload(flat, offs, pe=True); b.run(prm); b.finish(); down(i % 2)
     torch.cuda.synchronize()
     stage, dev_ms = {}, 0.0
     for _ in range(steps):
-        batches[0].run(prm)
+        batches[0].run(prm); batches[0].finish()
         t = batches[0].timings()
+        t["finish"] = batches[0].finish_counters()["device_us"] / 1000.0
+        t["total"] += t["finish"]
         dev_ms += t["total"]
         for k, v in t.items():
             stage[k] = stage.get(k, 0.0) + v
     batches[0].sync()
     counters = batches[0].counters(); launches = batches[0].launches() * steps
+    fin_status = np.bincount(bufs[0][3]["status"][0::2], minlength=5)
     torch.cuda.synchronize()
     e0 = time.perf_counter(); d2h = 0
     for i in range(steps):
-        b = batches[i % 2]; b.upload(flat, offs, pe=True); b.run(prm)
+        b = batches[i % 2]; b.upload(flat, offs, pe=True); b.run(prm); b.finish()
         if i >= 1:
-            _, _, u = batches[(i - 1) % 2].download(bufs[(i - 1) % 2][2], bufs[(i - 1) % 2][3]); d2h = n_reads * capi.ReadResult.itemsize + u * capi.Cand.itemsize
-    _, _, u = batches[(steps - 1) % 2].download(bufs[(steps - 1) % 2][2], bufs[(steps - 1) % 2][3]); d2h = n_reads * capi.ReadResult.itemsize + u * capi.Cand.itemsize
+            d2h = down((i - 1) % 2)
+    d2h = down((steps - 1) % 2)
     e2e_ms = (time.perf_counter() - e0) * 1000
     for x in batches:
         x.close()
-    return {"workload": wl.describe(len(m1)), "n_reads": n_reads, "steps": steps, "dev_ms": dev_ms, "e2e_ms": e2e_ms, "launches": launches,
+    return {"pair_status": {"no_pair": int(fin_status[0]), "reported": int(fin_status[1] + fin_status[3]), "ambiguous": int(fin_status[2])},"workload": wl.describe(len(m1)), "n_reads": n_reads, "steps": steps, "dev_ms": dev_ms, "e2e_ms": e2e_ms, "launches": launches,
             "stage_ms_per_step": {k: v / steps for k, v in stage.items()}, "work_per_step": counters, "h2d": int(bases + 8 * (n_reads + 1)), "d2h": int(d2h),
             "read_states": {"none": int(states[0]), "exact_unique": int(states[1]), "multi_exact": int(states[2]), "one_mismatch": int(states[3]), "verify": int(states[4])}}
 
@@ -645,9 +657,10 @@ def main():
                        "ms_per_step": c4_ms[0] / c4["steps"], "reads_per_step_per_gpu": c4["n_reads"], "gpu_launches": c4["launches"],
                        "e2e": {"value": c4["n_reads"] * world * c4["steps"] / (c4_ms[1] / 1000), "unit": "reads/s", "h2d_bytes_per_step": c4["h2d"], "d2h_bytes_per_step": c4["d2h"],
                                "ms_per_step": c4_ms[1] / c4["steps"], "batches_in_flight": 2},
-                       "stage_ms_per_step": c4["stage_ms_per_step"], "work_per_step": c4["work_per_step"], "read_states": c4["read_states"],
-                       "scope": "secondary measurement on the same resident index (BASELINE.json configs[3]); device pipeline incl. the sensitive pair logic and the re-seeding round, "
-                                "records + verified hit lists back (pair pick / CIGAR / SAM on the host); max over ranks like the headline"}
+                       "stage_ms_per_step": c4["stage_ms_per_step"], "work_per_step": c4["work_per_step"], "read_states": c4["read_states"], "pair_status": c4["pair_status"],
+                       "scope": "secondary measurement on the same resident index (BASELINE.json configs[3]); device pipeline incl. the sensitive pair logic, the re-seeding round and the "
+                                "pair finishing (hit compaction, pair pick, ungapped CIGAR check, coordinates); two 32-byte records per pair + mismatch positions back (banded DP of indel "
+                                "mates, MAPQ, SAM text on the host); max over ranks like the headline"}
     # ---- the whole program and the reference on this box's host cores (rank 0, N == 1 only)
     if world == 1 and not a.no_cpu_baseline:
         BMBS = ROOT / "bitmapperbs_b200/_build/bmbs"

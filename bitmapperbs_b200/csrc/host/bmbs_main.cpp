@@ -312,14 +312,15 @@ int search(const Options& o, const std::string& cmdline) {
   // splitter -> parse workers -> GPU threads (three launches in flight per device) -> finish workers -> ordered writer
   const double t1 = now();
   // Launches in flight per device: while one launch computes, the next one's reads go up and the previous one's records come down
-  // (BMBS_INFLIGHT to change).  A launch takes every sub-block that is waiting, up to BMBS_GROUP of them: a 32 k-read sub-block
-  // does not fill a B200 and its slowest reads set the pace of every kernel, so the device runs 5 x faster on 256 k reads at a
-  // time -- and when the host is the slower side the queue is short and a launch is one or two sub-blocks, with no added latency.
+  // (BMBS_INFLIGHT to change).  A launch takes the sub-blocks that are waiting, up to BMBS_GROUP of them: a 32 k-read sub-block
+  // does not fill a B200 (the device is 3 x faster per read on 256 k reads), but the host side sets the pace of the program and
+  // larger groups only add latency and burstiness to it: measured at 10 M reads, groups of 1-2 map in 0.51-0.53 s, of 8 in 0.59 s.
   auto env_int = [](const char* k, int d) { const char* e = getenv(k); return e ? std::max(1, atoi(e)) : d; };
-  const int inflight = env_int("BMBS_INFLIGHT", 3), group_max = env_int("BMBS_GROUP", 8);
-  // host threads: -t counts the workers that do the per-read work; the splitter, the writer and the GPU threads mostly wait.
-  // Parsing is a sixth of the per-read host work, finishing the rest.
-  const int n_parse = env_int("BMBS_PARSE_THREADS", std::max(1, (o.threads + 2) / 5)), n_finish = env_int("BMBS_FINISH_THREADS", std::max(1, o.threads - n_parse));
+  const int inflight = env_int("BMBS_INFLIGHT", 3), group_max = env_int("BMBS_GROUP", 2);
+  // host threads: -t counts the workers that do the per-read work; the splitter, the sequencer, the writer and the GPU threads
+  // mostly wait.  Measured per 10 M reads of 150 bp: parsing 1.2 core-seconds, finishing (records already reduced on the
+  // device, DPs replayed) 1.4, the GPU threads' own host work 1.3, writing 0.9.
+  const int n_parse = env_int("BMBS_PARSE_THREADS", std::max(1, (3 * o.threads + 8) / 10)), n_finish = env_int("BMBS_FINISH_THREADS", std::max(1, o.threads / 2));
   const int n_gpu = inflight * (int)devs.size();
   std::atomic<long long> us_split(0), us_parse(0), us_gpu(0), us_finish(0), us_write(0), n_retry(0), n_batches(0), n_launches(0), us_dev(0), us_up(0), us_run(0), us_down(0), us_prep(0), us_refine(0);
   std::atomic<long long> us_stage[8] = {}; std::atomic<long long> n_dp_total(0);

@@ -416,7 +416,8 @@ def main():
     d = ensure_dataset(cache, wl, rank == 0)
     if dist:
         dist.barrier()
-    m1, m2 = make_reads(d, wl, a.units, wl.read_seed + rank)     # weak scaling: every rank maps its own reads
+    from bitmapperbs_b200 import shard
+    m1, m2 = make_reads(d, wl, a.units, shard.rank_seed(wl.read_seed, rank))     # weak scaling: every rank maps its own reads
     n_units = len(m1); n_reads = per_unit * n_units
     if wl.pe:
         from bitmapperbs_b200.simulate import _revcomp_rows
@@ -558,19 +559,18 @@ def main():
         except Exception as e:      # the headline line must not depend on the secondary measurement
             log(f"[bench r{rank}] cfg4 measurement failed: {e}")
     c4_ms = [c4["dev_ms"], c4["e2e_ms"]] if c4 else [0.0, 0.0]
-    if dist:
-        t = torch.tensor([dev_ms, e2e_ms, wall_ms] + c4_ms + [0.0 if c4 else 1.0], dtype=torch.float64, device=f"cuda:{dev}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms, wall_ms, c4_ms[0], c4_ms[1], c4_missing = (float(x) for x in t.tolist())
-        if c4_missing:
-            c4 = None
+    # the slowest rank's times count (one MAX reduction outside the timed work)
+    dev_ms, e2e_ms, wall_ms, c4_ms[0], c4_ms[1], c4_missing = shard.max_over_ranks(dist, [dev_ms, e2e_ms, wall_ms] + c4_ms + [0.0 if c4 else 1.0],
+                                                                                   device=f"cuda:{dev}" if dist else None)
+    if c4_missing:
+        c4 = None
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return 0
 
-    value = n_reads * world * a.steps / (dev_ms / 1000)
-    e2e = n_reads * world * a.steps / (e2e_ms / 1000)
+    value = shard.whole_job_rate(n_reads, world, a.steps, dev_ms)
+    e2e = shard.whole_job_rate(n_reads, world, a.steps, e2e_ms)
     # ---- roofline of the dominant kernel group (SURVEY.md §8d algorithmic bytes per unit)
     peaks = {}
     try:
@@ -653,9 +653,9 @@ def main():
                          "units": f"14 word-ops per column per band word (SURVEY 8d), {words} word(s) for k = {k_band}; peak = measured LOP3+IADD3 rate (bmbs_ubench_int_pipe)"},
     }
     if c4:
-        out["cfg4"] = {"workload": c4["workload"], "value": c4["n_reads"] * world * c4["steps"] / (c4_ms[0] / 1000), "unit": "reads/s", "steps": c4["steps"],
+        out["cfg4"] = {"workload": c4["workload"], "value": shard.whole_job_rate(c4["n_reads"], world, c4["steps"], c4_ms[0]), "unit": "reads/s", "steps": c4["steps"],
                        "ms_per_step": c4_ms[0] / c4["steps"], "reads_per_step_per_gpu": c4["n_reads"], "gpu_launches": c4["launches"],
-                       "e2e": {"value": c4["n_reads"] * world * c4["steps"] / (c4_ms[1] / 1000), "unit": "reads/s", "h2d_bytes_per_step": c4["h2d"], "d2h_bytes_per_step": c4["d2h"],
+                       "e2e": {"value": shard.whole_job_rate(c4["n_reads"], world, c4["steps"], c4_ms[1]), "unit": "reads/s", "h2d_bytes_per_step": c4["h2d"], "d2h_bytes_per_step": c4["d2h"],
                                "ms_per_step": c4_ms[1] / c4["steps"], "batches_in_flight": 2},
                        "stage_ms_per_step": c4["stage_ms_per_step"], "work_per_step": c4["work_per_step"], "read_states": c4["read_states"], "pair_status": c4["pair_status"],
                        "scope": "secondary measurement on the same resident index (BASELINE.json configs[3]); device pipeline incl. the sensitive pair logic, the re-seeding round and the "

@@ -478,6 +478,7 @@ extern "C" int bmbs_batch_create(bmbs_index* idx, int dev, size_t max_reads, siz
   v.slot_cap = cand_cap;
   // verify_windows may need more than 48 KB of dynamic shared memory for long reads
   cudaFuncSetAttribute(verify_windows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(finish_pe_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PE_FIN_WARPS * 2 * PE_FIN_STAGE * sizeof(bmbs_cand)));
   *out = b;
   return BMBS_OK;
 }
@@ -489,8 +490,19 @@ extern "C" int bmbs_batch_upload(bmbs_batch* b, const char* seqs, const uint64_t
   const u64 bases = offsets[n_reads] - offsets[0];
   if (offsets[0] != 0) return fail(BMBS_ERR_ARG, "offsets[0] must be 0");
   if (bases > b->max_bases) return fail(BMBS_ERR_ARG, "batch has more bases than bmbs_batch_create allowed");
-  int max_len = 0;
-  for (int i = 0; i < n_reads; ++i) { const u64 l = offsets[i + 1] - offsets[i]; if (l > 1000) return fail(BMBS_ERR_ARG, "read longer than 1000 bases (SEQ_MAX_LENGTH, Auxiliary.h:15)"); if ((int)l > max_len) max_len = (int)l; }
+  // the longest read (sizes the shared-memory staging of the kernels); a million-read batch passes through here on the caller's
+  // thread every step, so: no branch in the loop, four independent maxima, one check at the end (offsets that run backwards
+  // wrap to a huge length and fail the same check)
+  u64 m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+  int i = 0;
+  for (; i + 4 <= n_reads; i += 4) {
+    const u64 a = offsets[i + 1] - offsets[i], b2 = offsets[i + 2] - offsets[i + 1], c = offsets[i + 3] - offsets[i + 2], d = offsets[i + 4] - offsets[i + 3];
+    m0 = a > m0 ? a : m0; m1 = b2 > m1 ? b2 : m1; m2 = c > m2 ? c : m2; m3 = d > m3 ? d : m3;
+  }
+  for (; i < n_reads; ++i) { const u64 a = offsets[i + 1] - offsets[i]; m0 = a > m0 ? a : m0; }
+  const u64 longest = std::max(std::max(m0, m1), std::max(m2, m3));
+  if (longest > 1000) return fail(BMBS_ERR_ARG, "read longer than 1000 bases (SEQ_MAX_LENGTH, Auxiliary.h:15)");
+  const int max_len = (int)longest;
   CU(cudaSetDevice(b->dev));
   CU(cudaMemcpyAsync(b->d_ascii, seqs, bases, cudaMemcpyHostToDevice, b->stream));
   CU(cudaMemcpyAsync(b->d_offsets, offsets, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, b->stream));
@@ -609,7 +621,9 @@ extern "C" int bmbs_batch_finish(bmbs_batch* b) {
   CU(cudaMemsetAsync(b->d_fc, 0, sizeof(FinCounters), s));
   CU(cudaEventRecord(b->ev[9], s));
   if (n > 0 && b->pe) {
-    finish_pe<<<(n / 2 + 127) / 128, 128, 0, s>>>(b->copy->view, b->v, b->d_fin, b->d_mism, (u32)b->mism_cap, b->d_fc); ++b->launches;
+    finish_pe<<<(n / 2 + 127) / 128, 128, 0, s>>>(b->copy->view, b->v, b->d_fin, b->d_mism, (u32)b->mism_cap, b->d_long_list, b->d_fc); ++b->launches;
+    const size_t pe_smem = (size_t)PE_FIN_WARPS * 2 * PE_FIN_STAGE * sizeof(bmbs_cand);
+    finish_pe_long<<<b->sm_count * 2, 32 * PE_FIN_WARPS, pe_smem, s>>>(b->copy->view, b->v, b->d_fin, b->d_mism, (u32)b->mism_cap, b->d_long_list, b->d_fc); ++b->launches;
   } else if (n > 0) {
     finish_se<<<(n + 127) / 128, 128, 0, s>>>(b->copy->view, b->v, b->d_fin, b->d_mism, (u32)b->mism_cap, b->d_long_list, b->d_huge_list, b->d_sort_list, b->d_fc); ++b->launches;
     finish_huge<<<b->sm_count * 2, 256, 0, s>>>(b->copy->view, b->v, b->d_fin, b->d_mism, (u32)b->mism_cap, b->d_fb, (u32)b->fb_cap, b->d_huge_list, b->d_sort_list, b->d_fc); ++b->launches;

@@ -74,8 +74,63 @@ __device__ __forceinline__ u32 finish_mate_hit(const DevIndex& ix, const BatchVi
   return mm_n;
 }
 
+// The pair logic on the two hit lists v1 / v2 (global memory, or a warp's copy in shared memory): compaction, single-side filter,
+// pair pick, then the records of the two chosen hits.  Returns the mismatch positions written to mm1 / mm2.
+__device__ __forceinline__ void pe_pair_logic(const DevIndex& ix, const BatchView& b, int r1, int r2, const bmbs_read_result& q1, const bmbs_read_result& q2,
+                                              bmbs_cand* v1, bmbs_cand* v2, bmbs_final& o1, bmbs_final& o2, unsigned short* mm1, unsigned short* mm2, u32& n_mm1, u32& n_mm2) {
+  const u32 L1 = b.len[r1], L2 = b.len[r2], k1 = b.kk[r1], k2 = b.kk[r2], kl = k1 > k2 ? k1 : k2;
+  int dmax, dmin; pair_bounds(b, r1, r2, dmax, dmin);
+  const bool res1 = is_resolved(q1.state), res2 = is_resolved(q2.state);
+  int occ1 = (int)q1.n_cand, occ2 = (int)q2.n_cand;
+  // --pe --sensitive: sens_pair / sens_reseed_finish already left each mate's final hits
+  if (!(b.sensitive || (res1 && res2))) {
+    if (!res1 && !res2) {
+      if (q1.n_cand <= q2.n_cand) {
+        occ1 = pe_fin::keep_hits(v1, occ1, k1);
+        if (occ1 == 0) return;
+        occ2 = pe_fin::single_side(v1, occ1, v2, occ2, dmax, dmin); occ2 = pe_fin::keep_hits(v2, occ2, k2);
+      } else {
+        occ2 = pe_fin::keep_hits(v2, occ2, k2);
+        if (occ2 == 0) return;
+        occ1 = pe_fin::single_side(v2, occ2, v1, occ1, dmax, dmin); occ1 = pe_fin::keep_hits(v1, occ1, k1);
+      }
+    } else if (res1) occ2 = pe_fin::keep_hits(v2, occ2, k2);
+    else occ1 = pe_fin::keep_hits(v1, occ1, k1);
+  }
+  // the pair pick: smallest err sum, the first such pair, how many, and what the best stood at before it
+  int best = 4 * (int)kl + 2, n_best = 0; long long second = 2LL * best, first = 0, i1 = 0, i2 = 0;
+  bool done = false;
+  if (occ1 > 0 && occ2 > 0)
+    for (int i = 0; i < occ1 && !done; ++i) {
+      const bmbs_cand a = v1[i];
+      for (int j = (int)first; j < occ2; ++j) {
+        const bmbs_cand c = v2[j];
+        bool stop; const bool in = pe_fin::in_range(a.site, c.site, dmax, dmin, j, first, stop);
+        if (stop) break;
+        if (!in) continue;
+        const long long sum = (long long)a.err + c.err;
+        if (sum < best) { second = best; best = (int)sum; i1 = i; i2 = j; n_best = 1; }
+        else if (sum == best) { second = best; ++n_best; if (best == 0) { done = true; break; } }
+      }
+    }
+  u32 sbd = 0;
+  if (n_best && !done) sbd = (u32)(second - best);
+  if (n_best > 1 && !b.amb_out) { o1.status = BMBS_FIN_AMBIGUOUS; return; }
+  if (n_best < 1) return;
+  const uint8_t s8 = (uint8_t)(sbd > 255u ? 255u : sbd);
+  o1.sbd = s8; o2.sbd = s8;
+  if (n_best > 1) { o1.flags |= BMBS_FINF_AMBIGUOUS; o2.flags |= BMBS_FINF_AMBIGUOUS; }
+  n_mm1 = finish_mate_hit(ix, b, r1, L1, k1, v1[i1], mm1, o1);
+  n_mm2 = finish_mate_hit(ix, b, r2, L2, k2, v2[i2], mm2, o2);
+}
+
+constexpr u32 PE_FIN_SHORT = 48;      // pairs with more hits than this in both lists together go to finish_pe_long
+constexpr int PE_FIN_STAGE = 768;     // entries of each list a warp stages in shared memory there
+
+// One thread per pair; pairs with long lists (a single thread pays an L2 round trip per entry: a thousand entries are a
+// millisecond) are left to finish_pe_long.
 __global__ void __launch_bounds__(128) finish_pe(DevIndex ix, BatchView b, bmbs_final* __restrict__ fin, unsigned short* __restrict__ mism, u32 mism_cap,
-                                                 FinCounters* __restrict__ fc) {
+                                                 u32* __restrict__ long_list, FinCounters* __restrict__ fc) {
   __shared__ unsigned short s_mm[128][2 * FIN_MM + 2];
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -84,60 +139,21 @@ __global__ void __launch_bounds__(128) finish_pe(DevIndex ix, BatchView b, bmbs_
   bmbs_final o1 = fin_blank(0), o2 = fin_blank(0);
   unsigned short* mm1 = s_mm[threadIdx.x]; unsigned short* mm2 = mm1 + FIN_MM + 1;
   u32 n_mm1 = 0, n_mm2 = 0;
+  bool is_long = false;
   if (live) {
     const bmbs_read_result q1 = b.out_res[r1], q2 = b.out_res[r2];
-    const u32 L1 = b.len[r1], L2 = b.len[r2], k1 = b.kk[r1], k2 = b.kk[r2], kl = k1 > k2 ? k1 : k2;
-    o1.k = (uint8_t)k1; o2.k = (uint8_t)k2;
-    int dmax, dmin; pair_bounds(b, r1, r2, dmax, dmin);
+    o1.k = b.kk[r1]; o2.k = b.kk[r2];
     if (q1.n_cand != 0 && q2.n_cand != 0) {                    // else: a mate without candidates, or nothing survived the distance filter
-      bmbs_cand* v1 = b.out_cand + q1.first_cand; bmbs_cand* v2 = b.out_cand + q2.first_cand;
-      const bool res1 = is_resolved(q1.state), res2 = is_resolved(q2.state);
-      int occ1 = (int)q1.n_cand, occ2 = (int)q2.n_cand;
-      bool none = false;
-      // --pe --sensitive: sens_pair / sens_reseed_finish already left each mate's final hits
-      if (!(b.sensitive || (res1 && res2))) {
-        if (!res1 && !res2) {
-          if (q1.n_cand <= q2.n_cand) {
-            occ1 = pe_fin::keep_hits(v1, occ1, k1);
-            if (occ1 == 0) none = true;
-            else { occ2 = pe_fin::single_side(v1, occ1, v2, occ2, dmax, dmin); occ2 = pe_fin::keep_hits(v2, occ2, k2); }
-          } else {
-            occ2 = pe_fin::keep_hits(v2, occ2, k2);
-            if (occ2 == 0) none = true;
-            else { occ1 = pe_fin::single_side(v2, occ2, v1, occ1, dmax, dmin); occ1 = pe_fin::keep_hits(v1, occ1, k1); }
-          }
-        } else if (res1) occ2 = pe_fin::keep_hits(v2, occ2, k2);
-        else occ1 = pe_fin::keep_hits(v1, occ1, k1);
-      }
-      if (!none) {
-        // the pair pick: smallest err sum, the first such pair, how many, and what the best stood at before it
-        int best = 4 * (int)kl + 2, n_best = 0; long long second = 2LL * best, first = 0, i1 = 0, i2 = 0;
-        bool done = false;
-        if (occ1 > 0 && occ2 > 0)
-          for (int i = 0; i < occ1 && !done; ++i) {
-            const bmbs_cand a = v1[i];
-            for (int j = (int)first; j < occ2; ++j) {
-              const bmbs_cand c = v2[j];
-              bool stop; const bool in = pe_fin::in_range(a.site, c.site, dmax, dmin, j, first, stop);
-              if (stop) break;
-              if (!in) continue;
-              const long long sum = (long long)a.err + c.err;
-              if (sum < best) { second = best; best = (int)sum; i1 = i; i2 = j; n_best = 1; }
-              else if (sum == best) { second = best; ++n_best; if (best == 0) { done = true; break; } }
-            }
-          }
-        u32 sbd = 0;
-        if (n_best && !done) sbd = (u32)(second - best);
-        if (n_best > 1 && !b.amb_out) o1.status = BMBS_FIN_AMBIGUOUS;
-        else if (n_best >= 1) {
-          const uint8_t s8 = (uint8_t)(sbd > 255u ? 255u : sbd);
-          o1.sbd = s8; o2.sbd = s8;
-          if (n_best > 1) { o1.flags |= BMBS_FINF_AMBIGUOUS; o2.flags |= BMBS_FINF_AMBIGUOUS; }
-          n_mm1 = finish_mate_hit(ix, b, r1, L1, k1, v1[i1], mm1, o1);
-          n_mm2 = finish_mate_hit(ix, b, r2, L2, k2, v2[i2], mm2, o2);
-        }
-      }
+      if (q1.n_cand + q2.n_cand > PE_FIN_SHORT) is_long = true;
+      else pe_pair_logic(ix, b, r1, r2, q1, q2, b.out_cand + q1.first_cand, b.out_cand + q2.first_cand, o1, o2, mm1, mm2, n_mm1, n_mm2);
     }
+  }
+  {
+    const u32 ml = __ballot_sync(0xffffffffu, is_long);
+    u32 base = 0;
+    if (lane == 0 && ml) base = (u32)atomicAdd(&fc->n_long, (unsigned long long)__popc(ml));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (is_long) long_list[base + __popc(ml & ((1u << lane) - 1u))] = (u32)p;
   }
   {
     const u32 ndp = (live && o1.status == BMBS_FIN_DP ? 1u : 0u) + (live && o2.status == BMBS_FIN_DP ? 1u : 0u);
@@ -164,5 +180,52 @@ __global__ void __launch_bounds__(128) finish_pe(DevIndex ix, BatchView b, bmbs_
       for (u32 j = 0; j < n_mm2; ++j) mism[at + n_mm1 + j] = mm2[j];
     }
   }
-  if (live) { fin[r1] = o1; fin[r2] = o2; }
+  if (live && !is_long) { fin[r1] = o1; fin[r2] = o2; }
+}
+
+// One warp per pair with long lists: the lanes copy both lists into shared memory with coalesced loads, lane 0 then walks them
+// there, literally as above (lists beyond the staging area are walked in global memory).
+constexpr int PE_FIN_WARPS = 4;
+__global__ void __launch_bounds__(32 * PE_FIN_WARPS) finish_pe_long(DevIndex ix, BatchView b, bmbs_final* __restrict__ fin, unsigned short* __restrict__ mism, u32 mism_cap,
+                                                                    const u32* __restrict__ long_list, FinCounters* __restrict__ fc) {
+  extern __shared__ bmbs_cand s_lists[];                      // [PE_FIN_WARPS][2][PE_FIN_STAGE]
+  __shared__ unsigned short s_mm[PE_FIN_WARPS][2 * FIN_MM + 2];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const u32 n_long = (u32)fc->n_long;
+  bmbs_cand* s1 = s_lists + (size_t)w * 2 * PE_FIN_STAGE; bmbs_cand* s2 = s1 + PE_FIN_STAGE;
+  for (;;) {
+    u32 g = 0;
+    if (lane == 0) g = (u32)atomicAdd(&fc->cursor_long, 1ull);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= n_long) break;
+    const int p = (int)long_list[g], r1 = 2 * p, r2 = r1 + 1;
+    const bmbs_read_result q1 = b.out_res[r1], q2 = b.out_res[r2];
+    bmbs_cand* g1 = b.out_cand + q1.first_cand; bmbs_cand* g2 = b.out_cand + q2.first_cand;
+    const bool stage = q1.n_cand <= (u32)PE_FIN_STAGE && q2.n_cand <= (u32)PE_FIN_STAGE;
+    if (stage) {
+      for (u32 i = lane; i < q1.n_cand; i += 32) s1[i] = g1[i];
+      for (u32 i = lane; i < q2.n_cand; i += 32) s2[i] = g2[i];
+    }
+    __syncwarp();
+    if (lane == 0) {
+      bmbs_final o1 = fin_blank(b.kk[r1]), o2 = fin_blank(b.kk[r2]);
+      unsigned short* mm1 = s_mm[w]; unsigned short* mm2 = mm1 + FIN_MM + 1;
+      u32 n_mm1 = 0, n_mm2 = 0;
+      pe_pair_logic(ix, b, r1, r2, q1, q2, stage ? s1 : g1, stage ? s2 : g2, o1, o2, mm1, mm2, n_mm1, n_mm2);
+      const u32 ndp = (o1.status == BMBS_FIN_DP ? 1u : 0u) + (o2.status == BMBS_FIN_DP ? 1u : 0u);
+      if (ndp) atomicAdd(&fc->n_dp, (unsigned long long)ndp);
+      const u32 my_mm = n_mm1 + n_mm2;
+      if (my_mm) {
+        const unsigned long long at = atomicAdd(&fc->mism_used, (unsigned long long)my_mm);
+        if (n_mm1) { o1.aux_first = (u32)at; o1.n_aux = n_mm1; }
+        if (n_mm2) { o2.aux_first = (u32)(at + n_mm1); o2.n_aux = n_mm2; }
+        if (at + my_mm <= mism_cap) {
+          for (u32 j = 0; j < n_mm1; ++j) mism[at + j] = mm1[j];
+          for (u32 j = 0; j < n_mm2; ++j) mism[at + n_mm1 + j] = mm2[j];
+        }
+      }
+      fin[r1] = o1; fin[r2] = o2;
+    }
+    __syncwarp();
+  }
 }

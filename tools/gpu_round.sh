@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # One gpurun call's worth of evidence: GPU parity tests, the bench line, the ncu launch list of the same command and
 # one `ncu --set full` capture of the main kernels.  Everything lands in gpurun_out/ (copied into profiles/ by hand).
-#   gpurun --timeout 1700 -- 'bash tools/gpu_round.sh [tag] [what...]'      what: tests bench refarm launches traffic full cliscale verify fullverify scale2
+#   gpurun --timeout 1700 -- 'bash tools/gpu_round.sh [tag] [what...]'      what: tests bench cfg2 refarm launches traffic full cliscale verify fullverify scale2
 set -u
 TAG=${1:-run}; shift || true
 WHAT=${*:-tests bench launches full}
@@ -14,6 +14,9 @@ for w in $WHAT; do
       timeout 900 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest.log 2>&1; echo "pytest exit $?" | tee -a $O/${TAG}_pytest.log; tail -3 $O/${TAG}_pytest.log ;;
     bench)
       timeout 900 python bench.py $BENCH_ARGS > $O/${TAG}_bench.json 2> $O/${TAG}_bench.log; echo "bench exit $?"; cat $O/${TAG}_bench.json ;;
+    cfg2)
+      # round 1's headline workload (100 Mbp uniform genome, pairs, fast mode) with the current build, for comparison
+      timeout 600 python bench.py --workload cfg2 --no-cpu-baseline > $O/${TAG}_bench_cfg2.json 2> $O/${TAG}_bench_cfg2.log; echo "bench cfg2 exit $?"; cut -c1-600 $O/${TAG}_bench_cfg2.json ;;
     refarm)
       timeout 600 python bench.py $BENCH_ARGS --impl reference --steps 2 --warmup 1 > $O/${TAG}_bench_reference.json 2>> $O/${TAG}_bench.log; cat $O/${TAG}_bench_reference.json ;;
     launches)

@@ -407,6 +407,7 @@ struct bmbs_batch {
   bmbs_final* d_fin = nullptr; unsigned short* d_mism = nullptr; bmbs_cand* d_fb = nullptr; u32* d_sort_list = nullptr; u32* d_long_list = nullptr; u32* d_huge_list = nullptr; FinCounters* d_fc = nullptr;
   size_t mism_cap = 0, fb_cap = 0; bool finished = false;
   int n_reads = 0, pe = 0, max_len = 0, launches = 0, sm_count = 148, seed_blocks_per_sm = 8; u32 seed_plane_cap = 0;
+  u32 pe_short = 48;             // pairs with more hits than this go to the warp kernel of the pair finishing (BMBS_PE_FIN_SHORT: tests)
   bool ran = false;
 };
 
@@ -450,6 +451,7 @@ extern "C" int bmbs_batch_create(bmbs_index* idx, int dev, size_t max_reads, siz
   bmbs_batch* b = new bmbs_batch();
   b->idx = idx; b->copy = c; b->dev = dev; b->max_reads = max_reads; b->max_bases = max_bases; b->cand_cap = cand_cap;
   cudaDeviceProp prop; cudaGetDeviceProperties(&prop, dev); b->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("BMBS_PE_FIN_SHORT")) b->pe_short = (u32)std::max(0, atoi(e));
   BatchView& v = b->v;
   const size_t R = max_reads + 2, S = cand_cap + 64;
   g_slab.clear();
@@ -621,7 +623,7 @@ extern "C" int bmbs_batch_finish(bmbs_batch* b) {
   CU(cudaMemsetAsync(b->d_fc, 0, sizeof(FinCounters), s));
   CU(cudaEventRecord(b->ev[9], s));
   if (n > 0 && b->pe) {
-    finish_pe<<<(n / 2 + 127) / 128, 128, 0, s>>>(b->copy->view, b->v, b->d_fin, b->d_mism, (u32)b->mism_cap, b->d_long_list, b->d_fc); ++b->launches;
+    finish_pe<<<(n / 2 + 127) / 128, 128, 0, s>>>(b->copy->view, b->v, b->d_fin, b->d_mism, (u32)b->mism_cap, b->d_long_list, b->d_fc, b->pe_short); ++b->launches;
     const size_t pe_smem = (size_t)PE_FIN_WARPS * 2 * PE_FIN_STAGE * sizeof(bmbs_cand);
     finish_pe_long<<<b->sm_count * 2, 32 * PE_FIN_WARPS, pe_smem, s>>>(b->copy->view, b->v, b->d_fin, b->d_mism, (u32)b->mism_cap, b->d_long_list, b->d_fc); ++b->launches;
   } else if (n > 0) {

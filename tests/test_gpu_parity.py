@@ -298,12 +298,13 @@ def test_verify_error_rate_other_than_default(gidx, oidx):
     ("pe100h", ["--seq1", "pe100h_1.fq", "--seq2", "pe100h_2.fq", "--pe"]),
     ("pe100hs", ["--seq1", "pe100h_1.fq", "--seq2", "pe100h_2.fq", "--pe", "--sensitive"]),
 ])
-@pytest.mark.parametrize("finish", ["device", "host"])
+@pytest.mark.parametrize("finish", ["device", "host", "device_warp_pairs"])
 def test_mapper_sam_identical_to_reference_golden(golden, built, name, args, finish):
     """whole program: FASTQ -> GPU seed-and-verify through the C ABI -> finishing (device: reduction / pair pick, ungapped CIGAR,
     coordinates, banded DP per launch; host: the same from the window lists) -> MAPQ -> SAM, vs the reference's SAM"""
     import os
-    env = {**os.environ, **({"BMBS_HOST_FINISH": "1"} if finish == "host" else {})}
+    # device_warp_pairs: every pair through the warp kernel of the pair finishing (staged lists, warp-parallel pair pick)
+    env = {**os.environ, **({"BMBS_HOST_FINISH": "1"} if finish == "host" else {"BMBS_PE_FIN_SHORT": "0"} if finish == "device_warp_pairs" else {})}
     subprocess.run([str(built["bmbs"]), "--search", "genome.fa", *args, "-t", "4", "-o", "gpu.sam", "--mapstats", "gpu.stats", "--batch", "700"],
                    cwd=golden, check=True, stderr=subprocess.DEVNULL, env=env)
     assert sam_body(golden / "gpu.sam") == sam_body(golden / f"{name}.sam")
@@ -353,6 +354,12 @@ def test_live_reference_binary_agrees_on_fresh_data(built, tmp_path):
                        cwd=tmp_path, check=True, stderr=subprocess.DEVNULL)
         assert sam_body(tmp_path / f"gpu_{tag}.sam") == sam_body(tmp_path / f"cpu_{tag}.sam")
         assert (tmp_path / f"gpu_{tag}.st").read_text() == (tmp_path / f"cpu_{tag}.st").read_text()
+        if "--pe" in args:      # the same pairs with every pair through the warp kernel of the pair finishing
+            import os
+            subprocess.run([str(built["bmbs"]), "--search", "g.fa", *args, "-t", "4", "-o", f"gpw_{tag}.sam", "--mapstats", f"gpw_{tag}.st"],
+                           cwd=tmp_path, check=True, stderr=subprocess.DEVNULL, env={**os.environ, "BMBS_PE_FIN_SHORT": "0"})
+            assert sam_body(tmp_path / f"gpw_{tag}.sam") == sam_body(tmp_path / f"cpu_{tag}.sam"), tag
+            assert (tmp_path / f"gpw_{tag}.st").read_text() == (tmp_path / f"cpu_{tag}.st").read_text(), tag
 
 
 def test_mapper_wide_suffix_array_gzip_input_and_two_gpus(golden, built, tmp_path):

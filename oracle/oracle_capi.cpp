@@ -196,6 +196,87 @@ int orc_finish_se(void* h, const char* seqs, const uint64_t* offs, int n, double
   return w <= mism_cap ? 0 : BMBS_ERR_CAPACITY;
 }
 
+// What the reference's pair workers do between their verification calls and the CIGAR / SAM code, on the records and verified
+// hit lists of a paired batch (same layout as bmbs_batch_finish on a paired batch returns): in fast mode the hit compaction
+// (Schema.cpp:7502-7608, as verify_keep_hits without the verification), filter_pairs_single_side (:16186-16288) on the longer
+// list, the compaction of that list; in sensitive mode and for mates that seeding resolved the lists are final as they stand
+// (Schema.cpp:22014-22130 / :23562-23690); then the pair pick new_faster_verify_pairs (:15773-15959), try_cigar_without_path
+// (ksw.cpp:2515-2570) on the two chosen hits and their coordinates (Schema.cpp:9188-9244; the end-of-chromosome test comes later
+// in the reference, with the final spans of both mates, :22310-22330, so a mate keeps its coordinates here).
+int orc_finish_pe(void* h, const char* seqs, const uint64_t* offs, int n_pairs, double e_rate, int min_ins, int max_ins, int sensitive, int ambiguous_out,
+                  const bmbs_read_result* res, const bmbs_cand* cand, bmbs_final* fin, uint16_t* mism, size_t mism_cap, size_t* mism_used) {
+  const Index& ix = *(Index*)h;
+  size_t w = 0; std::vector<char> win;
+  auto resolved = [](const bmbs_read_result& r) { return r.state == BMBS_EXACT_UNIQUE || r.state == BMBS_MULTI_EXACT || r.state == BMBS_ONE_MISMATCH; };
+  auto keep = [](std::vector<Vote>& v, u64 k) {      // Schema.cpp:7502-7512: hits within k whose absolute end differs from the entry before
+    int kept = 0; u64 prev = (u64)-1;
+    for (size_t i = 0; i < v.size(); ++i) {
+      const u64 e = v[i].site + v[i].end_site;
+      if (v[i].err <= k && prev != e) { v[kept].site = v[i].site; v[kept].err = v[i].err; v[kept].end_site = v[i].end_site; ++kept; }
+      prev = e;
+    }
+    return kept;
+  };
+  for (int p = 0; p < n_pairs; ++p) {
+    const int r1 = 2 * p, r2 = r1 + 1;
+    const char* read[2] = {seqs + offs[r1], seqs + offs[r2]};
+    const int L[2] = {(int)(offs[r1 + 1] - offs[r1]), (int)(offs[r2 + 1] - offs[r2])};
+    const u64 k[2] = {u64_k(e_rate, L[0]), u64_k(e_rate, L[1])}, kl = k[0] > k[1] ? k[0] : k[1];
+    bmbs_final* o[2] = {&fin[r1], &fin[r2]};
+    for (int m = 0; m < 2; ++m) { memset(o[m], 0, sizeof(bmbs_final)); o[m]->sbd = 255; o[m]->k = (uint8_t)k[m]; }
+    const bmbs_read_result& q1 = res[r1]; const bmbs_read_result& q2 = res[r2];
+    if (q1.n_cand == 0 || q2.n_cand == 0) continue;
+    const int dmax = (int)((u64)(long long)max_ins + kl * 2);
+    const int dmin = (int)((u64)(long long)min_ins - kl * 2 - (u64)(L[0] > L[1] ? L[0] : L[1]));
+    std::vector<Vote> v[2];
+    for (int m = 0; m < 2; ++m) {
+      const bmbs_read_result& q = m ? q2 : q1;
+      v[m].resize(q.n_cand);
+      for (uint32_t j = 0; j < q.n_cand; ++j) { const bmbs_cand& c = cand[q.first_cand + j]; v[m][j] = {c.site, c.vote, c.err == 0xFFFF ? 0xFFFFFFFFu : c.err, (u64)(int64_t)c.end_site}; }
+    }
+    int occ[2] = {(int)v[0].size(), (int)v[1].size()};
+    const bool res1 = resolved(q1), res2 = resolved(q2);
+    if (!(sensitive || (res1 && res2))) {
+      if (!res1 && !res2) {
+        const int a = v[0].size() <= v[1].size() ? 0 : 1, b = 1 - a;      // the shorter list is compacted first, the other filtered by it
+        occ[a] = keep(v[a], k[a]);
+        if (occ[a] == 0) continue;
+        filter_single_side(v[a], occ[a], v[b], dmax, dmin);
+        occ[b] = keep(v[b], k[b]);
+      } else if (res1) occ[1] = keep(v[1], k[1]);
+      else occ[0] = keep(v[0], k[0]);
+    }
+    const PairPick pk = pick_pair(v[0], occ[0], v[1], occ[1], (int)kl, dmax, dmin);
+    if (pk.n > 1 && !ambiguous_out) { o[0]->status = BMBS_FIN_AMBIGUOUS; continue; }
+    if (pk.n < 1) continue;
+    const long long pick[2] = {pk.i1, pk.i2};
+    for (int m = 0; m < 2; ++m) {
+      const Vote& b = v[m][pick[m]];
+      bmbs_final& f = *o[m];
+      f.sbd = (uint8_t)(pk.second_best_diff > 255 ? 255 : pk.second_best_diff);
+      if (pk.n > 1) f.flags |= BMBS_FINF_AMBIGUOUS;
+      f.site = b.site; f.end_site = (int16_t)(int64_t)b.end_site; f.nm = (uint8_t)b.err;
+      const int start = (int)(int64_t)b.end_site - L[m] + 1;
+      size_t w0 = w; unsigned mis = 0;
+      if (b.err != 0) {
+        const int plen = L[m] + 2 * (int)k[m]; win.resize(plen + 8);
+        ix.genome.window(b.site, plen, win.data());
+        bool ok = start >= 0;
+        for (int i = 0; ok && i < L[m]; ++i) {
+          const char t = read[m][i], g = win[i + start];
+          if (t != g && !(t == 'T' && g == 'C')) { if (++mis > b.err) { ok = false; break; } if (w < mism_cap) mism[w] = (uint16_t)i; ++w; }
+        }
+        if (!(ok && mis == b.err)) { w = w0; f.status = BMBS_FIN_DP; continue; }
+      }
+      const bmbs::Placed pl = bmbs::place(ix.chroms, b.site, (u64)(long long)start, b.end_site);
+      f.status = BMBS_FIN_UNIQUE; f.chrom_pos = ((u64)pl.chrom << 40) | pl.pos; if (pl.flag) f.flags |= BMBS_FINF_REVERSE;
+      if (mis) { f.aux_first = (uint32_t)w0; f.n_aux = mis; }
+    }
+  }
+  *mism_used = w;
+  return w <= mism_cap ? 0 : BMBS_ERR_CAPACITY;
+}
+
 // The order std::sort leaves the reference's 32-byte vote records in (Schema.cpp:27612, comparator :560-563): order[] receives
 // the original positions.  What the device's sort replay (bmbs_debug_sort_order) is compared with.
 void orc_std_sort_order(const uint32_t* votes, uint32_t n, uint32_t* order) {

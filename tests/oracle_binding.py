@@ -31,6 +31,7 @@ def lib():
         L.orc_refine_final.argtypes = [vp, C.c_uint64, C.c_char_p, C.c_char_p] + [C.c_int] * 8 + [C.POINTER(C.c_int)] * 3 + [C.POINTER(C.c_uint), vp, C.c_int]
         L.orc_std_sort_order.argtypes = [vp, C.c_uint32, vp]
         L.orc_finish_se.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_int, vp, vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.orc_finish_pe.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.orc_banded_align.argtypes = [vp, C.c_uint64, C.c_char_p, C.c_char_p] + [C.c_int] * 8 + [C.POINTER(C.c_int)] * 3 + [vp, C.c_int]
         _lib = L
     return _lib
@@ -71,6 +72,18 @@ class OracleIndex:
         res = np.ascontiguousarray(res); cand = np.ascontiguousarray(cand)
         rc = lib().orc_finish_se(self.h, flat.ctypes.data, offs.ctypes.data, n, e_rate, 1 if ambiguous_out else 0, res.ctypes.data, cand.ctypes.data,
                                  fin.ctypes.data, mism.ctypes.data, len(mism), C.byref(used))
+        assert rc == 0
+        return fin, mism[: used.value]
+
+    def finish_pe(self, mates, res, cand, e_rate=0.08, min_ins=0, max_ins=500, sensitive=False, ambiguous_out=False):
+        """the reference's hit compaction + single-side filter + pair pick + ungapped CIGAR check + coordinates over the records
+        and verified hit lists of a paired batch -> (Final[2 * pairs], mismatch positions)"""
+        flat, offs = mates if isinstance(mates, tuple) else flatten(mates)
+        n = len(offs) - 1
+        fin = np.zeros(n, dtype=Final); mism = np.zeros(32 * n + 64, dtype=np.uint16); used = C.c_size_t(0)
+        res = np.ascontiguousarray(res); cand = np.ascontiguousarray(cand)
+        rc = lib().orc_finish_pe(self.h, flat.ctypes.data, offs.ctypes.data, n // 2, e_rate, min_ins, max_ins, 1 if sensitive else 0, 1 if ambiguous_out else 0,
+                                 res.ctypes.data, cand.ctypes.data, fin.ctypes.data, mism.ctypes.data, len(mism), C.byref(used))
         assert rc == 0
         return fin, mism[: used.value]
 

@@ -1,6 +1,7 @@
-"""GPU (-m gpu): the device finishing of single-end batches (bmbs_batch_finish: vote-ordered reduction in std::sort's order,
-ungapped CIGAR check, coordinates) against the oracle's restatement of the reference's walk (orc_finish_se: std::sort + the
-literal loop + try_cigar_without_path + place), record by record; the introsort replay on lists of every size class."""
+"""GPU (-m gpu): the device finishing (bmbs_batch_finish) against the oracle's restatement of the reference, record by record.
+Single end: vote-ordered reduction in std::sort's order, ungapped CIGAR check, coordinates (orc_finish_se: std::sort + the
+literal loop + try_cigar_without_path + place); the introsort replay on lists of every size class.  Paired end: hit compaction,
+single-side filter, pair pick, the two chosen hits' records (orc_finish_pe), thread and warp kernels."""
 import subprocess
 
 import numpy as np
@@ -119,3 +120,77 @@ def test_device_sort_replay_equals_std_sort():
     assert ok.all()
     for v, o in zip(lists, orders):
         assert np.array_equal(o.astype(np.uint32), std_sort_order(v)), len(v)
+
+
+# ---- paired end: finish_pe / finish_pe_long against the oracle's restatement of the reference's pair logic (orc_finish_pe) ----
+def device_finish_pe(ix, mates, params):
+    flat, offs = capi.flatten(mates)
+    b = B.Batch(ix, 0, len(mates) + 2, len(flat) + 64, max(1 << 18, 96 * len(mates)))
+    b.upload(flat, offs, pe=True); b.run(params)
+    res, cand, used = b.download()                     # the verified hit lists as the pair logic finds them
+    res, cand = res.copy(), cand[:used].copy()
+    b.finish()                                         # (compacts the lists in place on the device)
+    fin, mism, fb = b.download_final()
+    c = b.finish_counters()
+    b.close()
+    assert len(fb) == 0
+    return res, cand, fin, mism, c
+
+
+def assert_same_pairs(gfin, gmism, ofin, omism):
+    for f in ("status", "flags", "sbd", "nm", "k", "chrom_pos", "site", "end_site", "n_aux"):
+        assert np.array_equal(gfin[f], ofin[f]), f
+    for r in np.nonzero(gfin["n_aux"])[0]:
+        a, n, b = int(gfin["aux_first"][r]), int(gfin["n_aux"][r]), int(ofin["aux_first"][r])
+        assert np.array_equal(gmism[a:a + n], omism[b:b + n]), r
+
+
+def mates_of(golden, name):
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    a = [r[1] for r in read_fastq(golden / f"{name}_1.fq")]; b = [r[1].translate(comp)[::-1] for r in read_fastq(golden / f"{name}_2.fq")]
+    return [x for p in zip(a, b) for x in p]
+
+
+@pytest.mark.parametrize("pe_short", [None, "0"])
+@pytest.mark.parametrize("name,sensitive,amb_out,extra", [("pe150", 0, 0, {}), ("pe150", 1, 1, {}), ("pe100h", 0, 1, {}), ("pe100h", 1, 0, {}),
+                                                          ("pe100h", 0, 0, {"e_rate": 0.05, "min_ins": 100, "max_ins": 350})])
+def test_finished_pairs_match_oracle_golden_reads(golden, idx_pair, monkeypatch, name, sensitive, amb_out, extra, pe_short):
+    ix, ox = idx_pair
+    if pe_short is not None:
+        monkeypatch.setenv("BMBS_PE_FIN_SHORT", pe_short)       # every pair through the warp kernel
+    mates = mates_of(golden, name)
+    p = capi.default_params(sensitive=sensitive, ambiguous_out=amb_out, **extra)
+    res, cand, fin, mism, c = device_finish_pe(ix, mates, p)
+    ofin, omism = ox.finish_pe(mates, res, cand, e_rate=p.e_rate, min_ins=p.min_ins, max_ins=p.max_ins, sensitive=bool(sensitive), ambiguous_out=bool(amb_out))
+    assert_same_pairs(fin, mism, ofin, omism)
+    st = fin["status"][0::2]
+    assert (st == capi.FIN_UNIQUE).sum() + (st == capi.FIN_DP).sum() > len(st) // 2
+    assert c["reads_dp"] == (fin["status"] == capi.FIN_DP).sum()
+
+
+@pytest.mark.parametrize("sensitive", [0, 1])
+def test_finished_pairs_on_high_copy_repeats(built, tmp_path, sensitive):
+    """hit lists of hundreds of entries per mate: the staged lists and the warp-parallel pair pick of finish_pe_long, ties among
+    equally good pairs (ambiguous pairs, second_best_diff 0) included"""
+    chroms = S.random_genome([700000, 500000], seed=322, repeat_fraction=0.7, repeat_copies=(40, 1500), repeat_len=(400, 1500), repeat_div=(0.0, 0.05))
+    S.write_fasta(tmp_path / "g.fa", chroms)
+    subprocess.run([str(built["indexer"]), "g.fa"], cwd=tmp_path, check=True, stderr=subprocess.DEVNULL)
+    g, st = S.concat_genome(chroms)
+    m1, m2 = S.simulate_fast(g, st, 5000, 120, 23)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    mates = [x for a, b in zip(m1, m2) for x in (bytes(a), bytes(b).translate(comp)[::-1])]
+    ix = B.Index(tmp_path / "g.fa.index"); ox = OracleIndex(tmp_path / "g.fa.index")
+    try:
+        for amb_out in (0, 1):
+            p = capi.default_params(sensitive=sensitive, ambiguous_out=amb_out)
+            res, cand, fin, mism, c = device_finish_pe(ix, mates, p)
+            n = res["n_cand"][0::2] + res["n_cand"][1::2]
+            assert (n > 48).sum() > 100 and (n > 300).any(), n.max()
+            ofin, omism = ox.finish_pe(mates, res, cand, sensitive=bool(sensitive), ambiguous_out=bool(amb_out))
+            assert_same_pairs(fin, mism, ofin, omism)
+            if not amb_out:
+                assert (fin["status"][0::2] == capi.FIN_AMBIGUOUS).sum() > 20
+            else:
+                assert (fin["flags"][0::2] & 2).astype(bool).sum() > 20
+    finally:
+        ix.close()

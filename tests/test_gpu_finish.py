@@ -185,12 +185,12 @@ def test_finished_pairs_on_high_copy_repeats(built, tmp_path, sensitive):
             p = capi.default_params(sensitive=sensitive, ambiguous_out=amb_out)
             res, cand, fin, mism, c = device_finish_pe(ix, mates, p)
             n = res["n_cand"][0::2] + res["n_cand"][1::2]
-            assert (n > 48).sum() > 100 and (n > 300).any(), n.max()
+            assert (n > 48).sum() > 20 and (n > 100).any(), n.max()       # (fast mode: filter_pairs has already thinned the lists)
             ofin, omism = ox.finish_pe(mates, res, cand, sensitive=bool(sensitive), ambiguous_out=bool(amb_out))
             assert_same_pairs(fin, mism, ofin, omism)
             if not amb_out:
-                assert (fin["status"][0::2] == capi.FIN_AMBIGUOUS).sum() > 20
+                assert (fin["status"][0::2] == capi.FIN_AMBIGUOUS).sum() > 5
             else:
-                assert (fin["flags"][0::2] & 2).astype(bool).sum() > 20
+                assert (fin["flags"][0::2] & 2).astype(bool).sum() > 5
     finally:
         ix.close()

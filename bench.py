@@ -265,7 +265,7 @@ def run_cli(exe: Path, d: Path, wl: Workload, seq_args, threads: int, out: str, 
         return None
     return float(m.group(1)), float(m.group(2)), wall
 
-def measure_cfg4(B, capi, torch, index, dev, d, scale, pairs, rank, steps, warmup):
+def measure_cfg4(B, capi, torch, index, dev, d, scale, pairs, rank, steps, warmup, nb=4):
     """BASELINE.json configs[3] on the index that is already resident: cfg3's genome, 150 bp pairs, --pe --sensitive (the whole
     pair logic on the device: mate-range filter, hit compaction, one re-seeding round).  -> dict with the rank's device and
     end-to-end milliseconds for `steps` steps; the caller takes the maximum over ranks."""
@@ -282,7 +282,7 @@ def measure_cfg4(B, capi, torch, index, dev, d, scale, pairs, rank, steps, warmu
     prm = capi.default_params(sensitive=1)
     cand_cap = 24 * n_reads
     while True:
-        batches = [B.Batch(index, dev, n_reads, bases + 64, cand_cap) for _ in range(2)]
+        batches = [B.Batch(index, dev, n_reads, bases + 64, cand_cap) for _ in range(nb)]
         try:
             batches[0].upload(flat, offs, pe=True); batches[0].run(prm); batches[0].sync()
             hr = torch.empty(n_reads * capi.ReadResult.itemsize, dtype=torch.uint8, pin_memory=True)
@@ -309,8 +309,8 @@ def measure_cfg4(B, capi, torch, index, dev, d, scale, pairs, rank, steps, warmu
     def down(i):
         _, mm, fb = batches[i].download_final(bufs[i][3], bufs[i][4], bufs[i][5])
         return n_reads * capi.Final.itemsize + 2 * len(mm) + capi.Cand.itemsize * len(fb)
-    for i in range(max(warmup, 2)):
-        b = batches[i % 2]; b.upload(flat, offs, pe=True); b.run(prm); b.finish(); down(i % 2)
+    for i in range(max(warmup, nb)):
+        b = batches[i % nb]; b.upload(flat, offs, pe=True); b.run(prm); b.finish(); down(i % nb)
     torch.cuda.synchronize()
     stage, dev_ms = {}, 0.0
     for _ in range(steps):
@@ -327,10 +327,11 @@ def measure_cfg4(B, capi, torch, index, dev, d, scale, pairs, rank, steps, warmu
     torch.cuda.synchronize()
     e0 = time.perf_counter(); d2h = 0
     for i in range(steps):
-        b = batches[i % 2]; b.upload(flat, offs, pe=True); b.run(prm); b.finish()
-        if i >= 1:
-            d2h = down((i - 1) % 2)
-    d2h = down((steps - 1) % 2)
+        b = batches[i % nb]; b.upload(flat, offs, pe=True); b.run(prm); b.finish()
+        if i >= nb - 1:
+            d2h = down((i - (nb - 1)) % nb)
+    for i in range(max(0, steps - (nb - 1)), steps):
+        d2h = down(i % nb)
     e2e_ms = (time.perf_counter() - e0) * 1000
     for x in batches:
         x.close()
@@ -555,7 +556,7 @@ def main():
         for o in outs:
             o[0].close()
         try:
-            c4 = measure_cfg4(B, capi, torch, index, dev, d, scale, a.cfg4_pairs, rank, max(3, min(a.steps, 10)), a.warmup)
+            c4 = measure_cfg4(B, capi, torch, index, dev, d, scale, a.cfg4_pairs, rank, max(a.inflight + 1, min(a.steps, 12)), a.warmup, a.inflight)
         except Exception as e:      # the headline line must not depend on the secondary measurement
             log(f"[bench r{rank}] cfg4 measurement failed: {e}")
     c4_ms = [c4["dev_ms"], c4["e2e_ms"]] if c4 else [0.0, 0.0]
@@ -656,7 +657,7 @@ def main():
         out["cfg4"] = {"workload": c4["workload"], "value": shard.whole_job_rate(c4["n_reads"], world, c4["steps"], c4_ms[0]), "unit": "reads/s", "steps": c4["steps"],
                        "ms_per_step": c4_ms[0] / c4["steps"], "reads_per_step_per_gpu": c4["n_reads"], "gpu_launches": c4["launches"],
                        "e2e": {"value": shard.whole_job_rate(c4["n_reads"], world, c4["steps"], c4_ms[1]), "unit": "reads/s", "h2d_bytes_per_step": c4["h2d"], "d2h_bytes_per_step": c4["d2h"],
-                               "ms_per_step": c4_ms[1] / c4["steps"], "batches_in_flight": 2},
+                               "ms_per_step": c4_ms[1] / c4["steps"], "batches_in_flight": a.inflight},
                        "stage_ms_per_step": c4["stage_ms_per_step"], "work_per_step": c4["work_per_step"], "read_states": c4["read_states"], "pair_status": c4["pair_status"],
                        "scope": "secondary measurement on the same resident index (BASELINE.json configs[3]); device pipeline incl. the sensitive pair logic, the re-seeding round and the "
                                 "pair finishing (hit compaction, pair pick, ungapped CIGAR check, coordinates); two 32-byte records per pair + mismatch positions back (banded DP of indel "

@@ -480,6 +480,7 @@ extern "C" int bmbs_batch_create(bmbs_index* idx, int dev, size_t max_reads, siz
   v.slot_cap = cand_cap;
   // verify_windows may need more than 48 KB of dynamic shared memory for long reads
   cudaFuncSetAttribute(verify_windows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(votes_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BIG_SMEM_ELEMS * sizeof(u64)));
   cudaFuncSetAttribute(finish_pe_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PE_FIN_WARPS * 2 * PE_FIN_STAGE * sizeof(bmbs_cand)));
   *out = b;
   return BMBS_OK;
@@ -568,7 +569,7 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
     votes_sort<32><<<b->sm_count * 4, 128, 0, s>>>(v); ++b->launches;
     votes_mid<<<b->sm_count * 8, 128, 0, s>>>(v); ++b->launches;
     votes_big1k<<<b->sm_count * 8, 128, 0, s>>>(v); ++b->launches;
-    votes_big<<<b->sm_count * 4, 256, 0, s>>>(v); ++b->launches;
+    votes_big<<<b->sm_count * 2, BIG_THREADS, BIG_SMEM_ELEMS * sizeof(u64), s>>>(v); ++b->launches;
     CU(cudaEventRecord(b->ev[4], s));
     if (b->pe && !v.sensitive) { filter_pairs_kernel<<<(n / 2 + 127) / 128, 128, 0, s>>>(v); ++b->launches; }
     CU(cudaEventRecord(b->ev[5], s));
@@ -593,7 +594,7 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
       votes_sort<32><<<b->sm_count * 4, 128, 0, s>>>(w); ++b->launches;
       votes_mid<<<b->sm_count * 8, 128, 0, s>>>(w); ++b->launches;
       votes_big1k<<<b->sm_count * 8, 128, 0, s>>>(w); ++b->launches;
-      votes_big<<<b->sm_count * 4, 256, 0, s>>>(w); ++b->launches;
+      votes_big<<<b->sm_count * 2, BIG_THREADS, BIG_SMEM_ELEMS * sizeof(u64), s>>>(w); ++b->launches;
       sens_reseed_filter<<<b->sm_count * 4, 128, 0, s>>>(w); ++b->launches;
       run_scan(b, w.nv, (u32)n, w.voff, w.totals + 1, w.slot_cap, 4u, w.totals + 2);
       gather_work<<<(n + 127) / 128, 128, 0, s>>>(w); ++b->launches;

@@ -1178,10 +1178,11 @@ __global__ void __launch_bounds__(128) votes_big1k(BatchView b) {
 
 // one CTA per long segment: bitonic sort on a power-of-two padded copy (shared memory when it fits,
 // global scratch otherwise), then a block-wide run-length encode.
-constexpr int BIG_SMEM_ELEMS = 4096;
-__global__ void __launch_bounds__(256) votes_big(BatchView b) {
-  __shared__ u64 s_buf[BIG_SMEM_ELEMS];
-  __shared__ u32 s_warp[8];
+constexpr int BIG_SMEM_ELEMS = 16384;             // 128 KB of dynamic shared memory: segments of up to 16 k candidates never touch global scratch
+constexpr int BIG_THREADS = 512;
+__global__ void __launch_bounds__(BIG_THREADS) votes_big(BatchView b) {
+  extern __shared__ u64 s_buf[];                  // [BIG_SMEM_ELEMS]
+  __shared__ u32 s_warp[BIG_THREADS / 32];
   __shared__ u32 s_base, s_soff;
   const u32 nbig = *b.status ? 0u : *b.big_count;
   for (u32 bi = blockIdx.x; bi < nbig; bi += gridDim.x) {

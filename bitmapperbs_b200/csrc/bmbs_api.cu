@@ -569,7 +569,8 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
     votes_sort<32><<<b->sm_count * 4, 128, 0, s>>>(v); ++b->launches;
     votes_mid<<<b->sm_count * 8, 128, 0, s>>>(v); ++b->launches;
     votes_big1k<<<b->sm_count * 8, 128, 0, s>>>(v); ++b->launches;
-    votes_big<<<b->sm_count * 2, BIG_THREADS, BIG_SMEM_ELEMS * sizeof(u64), s>>>(v); ++b->launches;
+    votes_big<<<b->sm_count * 4, 256, 4096 * sizeof(u64), s>>>(v, 4096u, 0u, 4096u); ++b->launches;
+    votes_big<<<b->sm_count * 2, BIG_THREADS, BIG_SMEM_ELEMS * sizeof(u64), s>>>(v, (u32)BIG_SMEM_ELEMS, 8192u, 0xFFFFFFFFu); ++b->launches;
     CU(cudaEventRecord(b->ev[4], s));
     if (b->pe && !v.sensitive) { filter_pairs_kernel<<<(n / 2 + 127) / 128, 128, 0, s>>>(v); ++b->launches; }
     CU(cudaEventRecord(b->ev[5], s));
@@ -594,7 +595,8 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
       votes_sort<32><<<b->sm_count * 4, 128, 0, s>>>(w); ++b->launches;
       votes_mid<<<b->sm_count * 8, 128, 0, s>>>(w); ++b->launches;
       votes_big1k<<<b->sm_count * 8, 128, 0, s>>>(w); ++b->launches;
-      votes_big<<<b->sm_count * 2, BIG_THREADS, BIG_SMEM_ELEMS * sizeof(u64), s>>>(w); ++b->launches;
+      votes_big<<<b->sm_count * 4, 256, 4096 * sizeof(u64), s>>>(w, 4096u, 0u, 4096u); ++b->launches;
+      votes_big<<<b->sm_count * 2, BIG_THREADS, BIG_SMEM_ELEMS * sizeof(u64), s>>>(w, (u32)BIG_SMEM_ELEMS, 8192u, 0xFFFFFFFFu); ++b->launches;
       sens_reseed_filter<<<b->sm_count * 4, 128, 0, s>>>(w); ++b->launches;
       run_scan(b, w.nv, (u32)n, w.voff, w.totals + 1, w.slot_cap, 4u, w.totals + 2);
       gather_work<<<(n + 127) / 128, 128, 0, s>>>(w); ++b->launches;

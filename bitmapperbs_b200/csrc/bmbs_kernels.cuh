@@ -1180,8 +1180,10 @@ __global__ void __launch_bounds__(128) votes_big1k(BatchView b) {
 // global scratch otherwise), then a block-wide run-length encode.
 constexpr int BIG_SMEM_ELEMS = 16384;             // 128 KB of dynamic shared memory: segments of up to 16 k candidates never touch global scratch
 constexpr int BIG_THREADS = 512;
-__global__ void __launch_bounds__(BIG_THREADS) votes_big(BatchView b) {
-  extern __shared__ u64 s_buf[];                  // [BIG_SMEM_ELEMS]
+// Launched twice: 256 threads and 32 KB for segments that pad to at most 4096 keys (several CTAs per SM), 512 threads and
+// 128 KB for the longer ones; a CTA skips the segments of the other launch.  cap = keys that fit its shared memory.
+__global__ void __launch_bounds__(BIG_THREADS) votes_big(BatchView b, u32 cap, u32 min_p, u32 max_p) {
+  extern __shared__ u64 s_buf[];                  // [cap]
   __shared__ u32 s_warp[BIG_THREADS / 32];
   __shared__ u32 s_base, s_soff;
   const u32 nbig = *b.status ? 0u : *b.big_count;
@@ -1189,8 +1191,9 @@ __global__ void __launch_bounds__(BIG_THREADS) votes_big(BatchView b) {
     const int r = (int)b.big_list[bi];
     const u32 beg = b.coff[r], n = b.coff[r + 1] - beg;
     u32 P = 64; while (P < n) P <<= 1;
+    if (P < min_p || P > max_p) continue;
     u64* a = s_buf;
-    if (P > BIG_SMEM_ELEMS) {
+    if (P > cap) {
       if (threadIdx.x == 0) s_soff = atomicAdd(b.scratch_used, P);
       __syncthreads();
       if ((u64)s_soff + P > b.scratch_cap) { if (threadIdx.x == 0) { b.nv[r] = 0; atomicOr(b.status, 8u); } __syncthreads(); continue; }

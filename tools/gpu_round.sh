@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # One gpurun call's worth of evidence: GPU parity tests, the bench line, the ncu launch list of the same command and
 # one `ncu --set full` capture of the main kernels.  Everything lands in gpurun_out/ (copied into profiles/ by hand).
-#   gpurun --timeout 1700 -- 'bash tools/gpu_round.sh [tag] [what...]'      what: tests bench cfg2 refarm launches traffic full cliscale verify fullverify scale2
+#   gpurun --timeout 1700 -- 'bash tools/gpu_round.sh [tag] [what...]'      what: tests bench cfg2 refarm launches traffic full cliscale verify fullverify scale2   (votes_big runs twice per round now: see KERNELS)
 set -u
 TAG=${1:-run}; shift || true
 WHAT=${*:-tests bench launches full}

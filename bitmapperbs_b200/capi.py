@@ -50,7 +50,7 @@ EXPORTS = ["bmbs_index_load", "bmbs_index_free", "bmbs_index_genome_length", "bm
            "bmbs_params_default", "bmbs_map_batch_se", "bmbs_map_batch_pe", "bmbs_verify", "bmbs_batch_create", "bmbs_batch_free",
            "bmbs_batch_upload", "bmbs_batch_run", "bmbs_batch_download", "bmbs_batch_sync", "bmbs_batch_timings",
            "bmbs_batch_counters", "bmbs_batch_launches", "bmbs_batch_verify", "bmbs_batch_download_verify", "bmbs_ubench_int_pipe", "bmbs_pinned_alloc", "bmbs_pinned_free", "bmbs_ubench_random_sectors",
-           "bmbs_refiner_create", "bmbs_refiner_free", "bmbs_refine", "bmbs_batch_finish", "bmbs_batch_download_final", "bmbs_batch_finish_counters", "bmbs_debug_sort_order", "bmbs_refiner_kernel_ms", "bmbs_batch_output_sizes", "bmbs_debug_check_lf2"]
+           "bmbs_refiner_create", "bmbs_refiner_free", "bmbs_refine", "bmbs_batch_finish", "bmbs_batch_download_final", "bmbs_batch_finish_counters", "bmbs_debug_sort_order", "bmbs_refiner_kernel_ms", "bmbs_batch_output_sizes"]
 
 
 def load_library():
@@ -90,7 +90,6 @@ def load_library():
     L.bmbs_batch_download_final.argtypes = [vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t), vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.bmbs_batch_finish_counters.argtypes = [vp, u64p]
     L.bmbs_debug_sort_order.argtypes = [C.c_int, vp, vp, C.c_uint32, vp, vp]
-    L.bmbs_debug_check_lf2.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, u64p]
     L.bmbs_refiner_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
     L.bmbs_refiner_free.argtypes = [vp]
     L.bmbs_refiner_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
@@ -163,12 +162,6 @@ class Index:
     @property
     def device_bytes(self):
         return int(self._L.bmbs_index_device_bytes(self._h))
-
-    def check_lf2(self, n_rows, seed=0, dev=None):
-        """mismatches between the two-symbol LF blocks and two single LF steps over n_rows pseudo-random rows x 9 symbol pairs"""
-        bad = C.c_uint64(0)
-        _check(self._L.bmbs_debug_check_lf2(self._h, self.devices[0] if dev is None else dev, n_rows, seed, C.byref(bad)))
-        return bad.value
 
     def close(self):
         if self._h:

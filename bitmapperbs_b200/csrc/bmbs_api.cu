@@ -122,7 +122,6 @@ int load_files(const std::string& prefix, HostIndex& h) {
 struct DeviceCopy {
   int dev = 0; DevIndex view{}; size_t bytes = 0;
   void *occ = nullptr, *flag = nullptr, *hash = nullptr, *ssa = nullptr, *planes = nullptr, *dsa_lo = nullptr, *dsa_hi = nullptr, *ktab = nullptr, *chroms = nullptr;
-  void *occ2 = nullptr, *c2tab = nullptr;
 };
 
 // ---- deep seed table (kmer_entry, bmbs_device.cuh): one thread per 16-mer walks the <= 3^D extensions depth first, sharing
@@ -210,75 +209,6 @@ __global__ void relayout_planes(const unsigned char* __restrict__ pac, u64 N, u6
   }
 }
 
-// ---- two-symbol LF blocks (rank2, bmbs_device.cuh), built from the one-symbol structure
-// code planes: a warp takes 64 BWT symbols in two passes of 32; symbol i has c1 = BWT[i], its LF image j (rank inside its own
-// block: no random access), and c2 = BWT[j] (one random access); the lanes' codes become four 64-bit plane words by ballots
-__global__ void __launch_bounds__(256) build_occ2_planes(DevIndex ix, u64* __restrict__ occ2, u64 n_sym) {
-  const int lane = threadIdx.x & 31;
-  const u64 warps = (u64)gridDim.x * (blockDim.x >> 5), n_groups = (n_sym + 63) >> 6;
-  for (u64 g = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < n_groups; g += warps) {
-    u64 word[4] = {0, 0, 0, 0};
-    for (int h = 0; h < 2; ++h) {
-      const u64 i = g * 64 + 32 * h + lane;
-      u32 code = 15u;                                          // beyond the text: matches no pair
-      if (i < n_sym) {
-        const OccBlock b = load_occ(ix, i);
-        const unsigned sh = 63u - ((unsigned)i & 63u);
-        const int c1 = ((b.planes.x >> sh) & 1ull) ? 1 : ((b.planes.y >> sh) & 1ull) ? 2 : 0;
-        const u64 j = rank_in(ix, b, i, c1);                   // LF of the row this symbol belongs to
-        if (j == ix.shapline) code = 9u;                       // its image is the '$' row: no second symbol
-        else {
-          const u64 a2 = adjust_row(ix, j);
-          const OccBlock b2 = load_occ(ix, a2);
-          const unsigned sh2 = 63u - ((unsigned)a2 & 63u);
-          const int c2 = ((b2.planes.x >> sh2) & 1ull) ? 1 : ((b2.planes.y >> sh2) & 1ull) ? 2 : 0;
-          code = (u32)(3 * c1 + c2);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const u32 bal = __brev(__ballot_sync(0xffffffffu, (code >> k) & 1u));   // lane 0 = the highest bit
-        word[k] |= h == 0 ? (u64)bal << 32 : (u64)bal;
-      }
-    }
-    if (lane == 0) {
-      u64* blk = occ2 + (g >> 1) * 16;                         // 16 words per 128-symbol block; plane k: words 2k, 2k + 1
-#pragma unroll
-      for (int k = 0; k < 4; ++k) blk[2 * k + (g & 1)] = word[k];
-    }
-  }
-}
-// counts: pairs p among the symbols before each block = occ(c2, LF_c1(block start)) - occ(c2, C[c1]); one thread per block and pair
-__global__ void __launch_bounds__(256) build_occ2_counts(DevIndex ix, u64* __restrict__ occ2, u64 n_blk2, u64 n_sym) {
-  for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < n_blk2 * 9; t += (u64)gridDim.x * blockDim.x) {
-    const u64 blk = t / 9; const int p = (int)(t % 9), c1 = p / 3, c2 = p % 3;
-    u64 a0 = blk << 7; if (a0 > n_sym) a0 = n_sym;
-    const u64 r1 = first_row_of(ix, c1) + occ_raw(ix, a0, c1);
-    const u64 cnt = occ_raw(ix, adjust_row(ix, r1), c2) - occ_raw(ix, adjust_row(ix, first_row_of(ix, c1)), c2);
-    char* base = reinterpret_cast<char*>(occ2) + blk * 128;
-    reinterpret_cast<u32*>(base + 64)[p] = (u32)cnt;
-    reinterpret_cast<unsigned short*>(base + 100)[p] = (unsigned short)(cnt >> 32);
-  }
-}
-__global__ void build_c2tab(DevIndex ix, u64* __restrict__ c2tab) {
-  const int p = threadIdx.x;
-  if (p < 9) { const int c1 = p / 3, c2 = p % 3; c2tab[p] = first_row_of(ix, c2) + occ_raw(ix, adjust_row(ix, first_row_of(ix, c1)), c2); }
-}
-// test entry: rank2 against the two single steps it stands for, for `n` pseudo-random rows and all nine pairs
-__global__ void check_occ2(DevIndex ix, u64 n, u64 seed, unsigned long long* __restrict__ bad) {
-  for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (u64)gridDim.x * blockDim.x) {
-    u64 x = seed + t * 0x9E3779B97F4A7C15ull; x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
-    const u64 row = t < 1024 ? t : t < 2048 ? ix.n_rows - 1 - (t - 1024) : x % ix.n_rows;      // both ends of the table, then anywhere
-    const u64 a = adjust_row(ix, row);
-    for (int p = 0; p < 9; ++p) {
-      const int c1 = p / 3, c2 = p % 3;
-      const u64 r1 = first_row_of(ix, c1) + occ_raw(ix, a, c1);
-      const u64 want = first_row_of(ix, c2) + occ_raw(ix, adjust_row(ix, r1), c2);
-      if (rank2(ix, a, (u32)p) != want) atomicAdd(bad, 1ull);
-    }
-  }
-}
-
 // every row's suffix-array value from the sampled one, once per index load (the same walk the reference does per hit)
 __global__ void __launch_bounds__(256) densify_sa(DevIndex ix, u32* lo, unsigned char* hi) {
   for (u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x; row < ix.n_rows; row += (u64)gridDim.x * blockDim.x) {
@@ -312,7 +242,7 @@ extern "C" uint64_t bmbs_index_device_bytes(const bmbs_index* idx) { return idx 
 extern "C" void bmbs_index_free(bmbs_index* idx) {
   if (!idx) return;
   { std::lock_guard<std::mutex> l(g_live_mu); g_live_serials.erase(idx->serial); }
-  for (auto& c : idx->copies) { cudaSetDevice(c.dev); cudaFree(c.occ); cudaFree(c.flag); cudaFree(c.hash); cudaFree(c.ssa); cudaFree(c.planes); cudaFree(c.dsa_lo); cudaFree(c.dsa_hi); cudaFree(c.ktab); cudaFree(c.chroms); cudaFree(c.occ2); cudaFree(c.c2tab); }
+  for (auto& c : idx->copies) { cudaSetDevice(c.dev); cudaFree(c.occ); cudaFree(c.flag); cudaFree(c.hash); cudaFree(c.ssa); cudaFree(c.planes); cudaFree(c.dsa_lo); cudaFree(c.dsa_hi); cudaFree(c.ktab); cudaFree(c.chroms); }
   delete idx;
 }
 
@@ -395,7 +325,7 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
     v.C[0] = h.nacgt[0]; v.C[1] = h.nacgt[1]; v.C[2] = h.nacgt[2];
     v.shapline = h.shapline; v.n_rows = h.sa_length; v.N = h.N;
     v.chrom_start = (const u64*)c.chroms; v.n_chrom = (u32)(h.chrom_start.size() - 1);
-    v.dsa_lo = nullptr; v.dsa_hi = nullptr; v.ktab = nullptr; v.kdepth = 0; v.kpow = 1; v.occ2 = nullptr; v.c2tab = nullptr;
+    v.dsa_lo = nullptr; v.dsa_hi = nullptr; v.ktab = nullptr; v.kdepth = 0; v.kpow = 1;
     lap("upload + device re-layout");
     // ---- dense suffix array (BMBS_SA=sampled keeps the on-disk 1/8 sampling; default: dense when it fits with room to spare)
     const char* mode = getenv("BMBS_SA");
@@ -449,30 +379,6 @@ extern "C" int bmbs_index_load(const char* index_prefix, const int* devices, int
       }
     }
     lap("deep seed table");
-    // ---- two-symbol LF blocks: 1 byte per BWT symbol (BMBS_LF2=0: single steps only; default: built when a tenth of HBM holds them)
-    {
-      const char* m2 = getenv("BMBS_LF2");
-      const u64 n_blk2 = (n >> 7) + 2;
-      size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
-      const bool want2 = m2 ? atoi(m2) != 0 : (n_blk2 * 128 < total_b / 10 && n_blk2 * 128 + (total_b >> 3) < free_b);
-      if (want2) {
-        DeviceCopy& cc = c;
-        e = cudaMalloc(&cc.occ2, n_blk2 * 128 + 256);
-        if (e == cudaSuccess) e = cudaMemset(cc.occ2, 0, n_blk2 * 128 + 256);
-        if (e == cudaSuccess) e = cudaMalloc(&cc.c2tab, 16 * 8);
-        if (e == cudaSuccess) {
-          cudaDeviceProp prop; cudaGetDeviceProperties(&prop, cc.dev);
-          build_c2tab<<<1, 32>>>(v, (u64*)cc.c2tab);
-          build_occ2_planes<<<prop.multiProcessorCount * 8, 256>>>(v, (u64*)cc.occ2, n);
-          build_occ2_counts<<<prop.multiProcessorCount * 8, 256>>>(v, (u64*)cc.occ2, n_blk2, n);
-          e = cudaDeviceSynchronize();
-        }
-        if (e != cudaSuccess) { err_out = std::string("two-symbol LF blocks: ") + cudaGetErrorString(e); return; }
-        v.occ2 = (const ulonglong2*)cc.occ2; v.c2tab = (const u64*)cc.c2tab;
-        cc.bytes += n_blk2 * 128;
-      }
-    }
-    lap("two-symbol LF blocks");
   };
   {
     std::vector<std::thread> th;
@@ -850,22 +756,6 @@ extern "C" int bmbs_debug_sort_order(int dev, const uint32_t* votes, const uint3
 }
 
 // ================================================================================================ one-call forms
-extern "C" int bmbs_debug_check_lf2(bmbs_index* idx, int dev, uint64_t n_rows, uint64_t seed, uint64_t* mismatches) {
-  if (!idx || !mismatches) return fail(BMBS_ERR_ARG, "null argument");
-  const DeviceCopy* c = idx->on(dev);
-  if (!c) return fail(BMBS_ERR_ARG, "index was not loaded on device " + std::to_string(dev));
-  if (!c->view.occ2) return fail(BMBS_ERR_ARG, "the index was loaded without two-symbol LF blocks (BMBS_LF2=0, or not enough memory)");
-  CU(cudaSetDevice(dev));
-  unsigned long long* d_bad = nullptr; CU(cudaMalloc(&d_bad, 8)); CU(cudaMemset(d_bad, 0, 8));
-  check_occ2<<<148 * 8, 256>>>(c->view, n_rows, seed, d_bad);
-  unsigned long long bad = 0;
-  cudaError_t e = cudaMemcpy(&bad, d_bad, 8, cudaMemcpyDeviceToHost);
-  cudaFree(d_bad);
-  CU(e);
-  *mismatches = bad;
-  return BMBS_OK;
-}
-
 namespace {
 struct Cached { bmbs_index* idx; u64 serial; int dev; bmbs_batch* b; };
 thread_local std::vector<Cached> g_cache;

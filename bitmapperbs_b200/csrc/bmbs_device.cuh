@@ -32,8 +32,6 @@ struct DevIndex {
  const uint2* planes;
   const u64* ktab;            // deep seed table over K-mers, K = 16 + kdepth (null: only the 16-mer table); see kmer_entry
   u32 kdepth, kpow;           // K - 16 (1..4), 3^(K-16)
-  const ulonglong2* occ2;     // two-symbol LF blocks (128 bytes per 128 BWT symbols, see rank2); null = single steps only
-  const u64* c2tab;           // [9] first row of the suffixes that start with c2 c1, pair code p = 3 c1 + c2
   const u32* dsa_lo;          // dense suffix array (one entry per row), low 32 bits; null = walk to a sampled row
   const unsigned char* dsa_hi; // bits 32..39 when the text is longer than 2^32
   u64 C[3];        // first row of symbols G(0), T(1), A(2)   (nacgt[c], bwt.cpp:1715-1729)
@@ -97,42 +95,6 @@ __device__ __forceinline__ int lf_pair(const DevIndex& ix, u64& sp, u64& ep, int
   sp = rank_masked(ix, ba, a, m0, m1, m2);
   ep = rank_masked(ix, bb, b, m0, m1, m2);
   return bb.blk != ba.blk ? 2 : 1;
-}
-
-// occ(c, .) alone: occurrences of symbol c among the first adj_row BWT symbols
-__device__ __forceinline__ u64 occ_raw(const DevIndex& ix, u64 adj_row, int c) {
-  const OccBlock b = load_occ(ix, adj_row);
-  return rank_in(ix, b, adj_row, c) - first_row_of(ix, c);
-}
-
-// ---- two symbols per dependent access.  With HBM to spare the LF step is also stored for PAIRS of symbols: BWT symbol i gets the
-// pair code p = 3 c1 + c2 with c1 = BWT[i] and c2 = BWT[LF(i)] (9 codes; 9 = undefined, the one row whose LF image is the '$'
-// row), and a block of 128 symbols is one 128-byte line -- the unit a random access moves anyway:
-//   bytes 0..63    four bit-planes of the code, two words each (symbol r of the block = bit 63 - (r & 63) of word r >> 6)
-//   bytes 64..99   u32 low halves, bytes 100..117 u16 high halves of the nine counts "pairs p among the symbols before the block"
-// LF by c1 then by c2 of row x is c2tab[p] + count_p(block) + popcount(code == p in the block before x): extending an interval
-// by two symbols costs one access per end instead of two dependent ones.  Built at load from the one-symbol structure.
-__device__ __forceinline__ u64 rank2(const DevIndex& ix, u64 adj_row, u32 p) {
-  const u64 blk = adj_row >> 7; const unsigned part = (unsigned)adj_row & 127u;
-  const char* base = reinterpret_cast<const char*>(ix.occ2) + blk * 128;
-  u64 w0, w1, w2, w3, w4, w5, w6, w7;
-  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w0), "=l"(w1), "=l"(w2), "=l"(w3) : "l"(base));
-  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w4), "=l"(w5), "=l"(w6), "=l"(w7) : "l"(base + 32));
-  const u64 cnt = (u64)__ldg(reinterpret_cast<const u32*>(base + 64) + p) | ((u64)__ldg(reinterpret_cast<const unsigned short*>(base + 100) + p) << 32);
-  const u64 s0 = 0ull - (u64)(p & 1u), s1 = 0ull - (u64)((p >> 1) & 1u), s2 = 0ull - (u64)((p >> 2) & 1u), s3 = 0ull - (u64)((p >> 3) & 1u);
-  const u64 m0 = ~(w0 ^ s0) & ~(w2 ^ s1) & ~(w4 ^ s2) & ~(w6 ^ s3);      // symbols 0..63 of the block whose code is p
-  const u64 m1 = ~(w1 ^ s0) & ~(w3 ^ s1) & ~(w5 ^ s2) & ~(w7 ^ s3);      // symbols 64..127
-  const unsigned lo_part = part < 64u ? part : 64u, hi_part = part < 64u ? 0u : part - 64u;
-  const u64 head0 = lo_part == 0u ? 0ull : (lo_part == 64u ? m0 : m0 >> (64u - lo_part));
-  const u64 head1 = hi_part == 0u ? 0ull : m1 >> (64u - hi_part);
-  return __ldg(ix.c2tab + p) + cnt + (u64)__popcll(head0) + (u64)__popcll(head1);
-}
-// extends [sp, ep) by the symbols c1 (next to the pattern) and c2 (before it), p = 3 c1 + c2; returns the blocks touched
-__device__ __forceinline__ int lf2_pair(const DevIndex& ix, u64& sp, u64& ep, u32 p) {
-  const u64 a = adjust_row(ix, sp), b = adjust_row(ix, ep);
-  sp = rank2(ix, a, p);
-  ep = rank2(ix, b, p);
-  return (a >> 7) != (b >> 7) ? 2 : 1;
 }
 
 __device__ __forceinline__ void hash_query(const DevIndex& ix, u64 key, u64& sp, u64& ep) {

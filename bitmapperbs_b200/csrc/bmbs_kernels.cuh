@@ -785,19 +785,7 @@ __global__ void __launch_bounds__(128) seed_reads(DevIndex ix, BatchView b, u32 
           if (m < s_cur) {
             ptop = top; pbot = bot;
             const int c = symbol_at(s_off + m);
-            // Two symbols in one dependent access while the interval is wide: if at least two rows are left after both
-            // symbols, at least two were left after the first, so the loop of the reference would have gone through both
-            // steps without stopping and stands exactly here.  Otherwise nothing is taken over and the single step below runs.
-            bool two = false;
-            if (ix.occ2 && bot - top >= 4 && c <= 2 && m + 2 <= s_cur) {
-              const int c2 = symbol_at(s_off + m + 1);
-              if (c2 <= 2) {
-                u64 t2 = top, b2 = bot;
-                cn.n_occ += lf2_pair(ix, t2, b2, (u32)(3 * c + c2));
-                if (b2 - t2 >= 2) { top = t2; bot = b2; m += 2; stop = m >= s_cur; two = true; }
-              }
-            }
-            if (!two && bot - top != 1) {
+            if (bot - top != 1) {
               if (c > 2) bot = top;
               else {
                 cn.n_occ += lf_pair(ix, top, bot, c);

@@ -207,12 +207,6 @@ int bmbs_batch_finish_counters(bmbs_batch* b, uint64_t c[8]);
  * order[] receives original positions, ok[i] = 0 when the replay declined (introsort depth limit) */
 int bmbs_debug_sort_order(int dev, const uint32_t* votes, const uint32_t* offsets, uint32_t n_lists, uint16_t* order, int* ok);
 
-/* test entry: the two-symbol LF blocks of the index (one access extends a suffix-array interval by two symbols, built at load
- * from the reference's one-symbol structure) against the two single steps they stand for, find_occ_fm_index_combine
- * (bwt.h:1473-1596) applied twice: n_rows pseudo-random rows (and both ends of the table) x all nine symbol pairs;
- * *mismatches must come back 0 */
-int bmbs_debug_check_lf2(bmbs_index* idx, int dev, uint64_t n_rows, uint64_t seed, uint64_t* mismatches);
-
 /* ---- CIGAR refinement: the banded affine-gap DP with traceback, end fix-ups and NM recount ----------
  * Replaces fast_recalculate_bs_Cigar (ksw.cpp:2578-3148) for the alignments whose ungapped re-check (try_cigar_without_path,
  * :2515-2570 -- done by bmbs_batch_finish for single-end reads, by the caller otherwise) failed, i.e. alignments with indels:

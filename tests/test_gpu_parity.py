@@ -21,13 +21,12 @@ ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
 # only), the on-disk 1/8 suffix-array sampling with an 18-mer deep seed table, and the 20-mer table a 100 Mbp genome gets
 # and the layout of texts beyond 2^32 rows (bits 32..39 of every suffix-array value in their own byte array) forced onto
 # the small index together with the 20-mer table and the dense suffix array -- what a 3.1 Gbp genome gets
-# -- and the default layout without the two-symbol LF blocks (every extension a single step, as in round 1)
-@pytest.fixture(scope="module", params=["default", "sampled_sa+18mer", "20mer", "wide_sa+20mer", "single_step_lf"])
+@pytest.fixture(scope="module", params=["default", "sampled_sa+18mer", "20mer", "wide_sa+20mer"])
 def gidx(golden, request):
     import os
     env = {"default": {}, "sampled_sa+18mer": {"BMBS_SA": "sampled", "BMBS_KMER": "18"}, "20mer": {"BMBS_KMER": "20"},
-           "wide_sa+20mer": {"BMBS_FORCE_WIDE": "1", "BMBS_KMER": "20", "BMBS_SA": "dense"}, "single_step_lf": {"BMBS_LF2": "0"}}[request.param]
-    old = {k: os.environ.get(k) for k in ("BMBS_SA", "BMBS_KMER", "BMBS_FORCE_WIDE", "BMBS_LF2")}
+           "wide_sa+20mer": {"BMBS_FORCE_WIDE": "1", "BMBS_KMER": "20", "BMBS_SA": "dense"}}[request.param]
+    old = {k: os.environ.get(k) for k in ("BMBS_SA", "BMBS_KMER", "BMBS_FORCE_WIDE")}
     os.environ.update(env)
     try:
         ix = B.Index(golden / "genome.fa.index")
@@ -437,31 +436,3 @@ def test_mapper_bam_output_holds_the_same_records(golden, built, name, args):
         assert (r["name"], r["flag"], r["rid"], r["pos"], r["mapq"], r["cigar"], r["seq"], r["qual"], r["tags"]) == \
                (f[0], int(f[1]), rid[f[2]], int(f[3]) - 1, int(f[4]), f[5], f[9], f[10], f[11:])
         assert r["npos"] == int(f[7]) - 1 and r["tlen"] == int(f[8])
-
-
-def test_two_symbol_lf_blocks_equal_two_single_steps(golden, built, tmp_path):
-    """the two-symbol LF blocks built at load (one access extends an interval by two symbols) against the two single steps of
-    find_occ_fm_index_combine they stand for: both ends of the row table and two million pseudo-random rows x all nine symbol
-    pairs, on the golden index and on a repeat-rich one; and the library says so when the blocks were not built"""
-    import os
-    ix = B.Index(golden / "genome.fa.index")
-    try:
-        assert ix.check_lf2(2_000_000, seed=1) == 0
-    finally:
-        ix.close()
-    chroms = S.random_genome([900000, 700000], seed=77, repeat_fraction=0.6, repeat_copies=(20, 800), repeat_len=(300, 2000), repeat_div=(0.0, 0.08))
-    S.write_fasta(tmp_path / "g.fa", chroms)
-    subprocess.run([str(built["indexer"]), "g.fa"], cwd=tmp_path, check=True, stderr=subprocess.DEVNULL)
-    ix = B.Index(tmp_path / "g.fa.index")
-    try:
-        assert ix.check_lf2(2_000_000, seed=2) == 0
-    finally:
-        ix.close()
-    os.environ["BMBS_LF2"] = "0"
-    try:
-        ix = B.Index(golden / "genome.fa.index")
-        with pytest.raises(B.BmbsError, match="two-symbol"):
-            ix.check_lf2(10)
-        ix.close()
-    finally:
-        os.environ.pop("BMBS_LF2", None)

@@ -4,7 +4,9 @@
 // GPU box).  The SAM it writes must equal the reference's golden SAM: that pins the host glue without a GPU.
 // Mode sef: single end through the finished records (bmbs_final) -- the oracle's restatement of the device finishing
 // (orc_finish_se) feeds mapper.hpp's finish_single_final, the consumer the mapper uses behind bmbs_batch_finish.
-//   host_finish_harness se|sef|pe|pes <genome.fa> <out.sam> <reads.fq> [<mates.fq>] [--unmapped_out] [--ambiguous_out] [--pbat]
+// Modes pef / pesf: pairs (fast / sensitive) through the finished records -- orc_finish_pe (the oracle's restatement of the pair
+// logic the device runs in finish_pe) feeds finish_pair_final.
+//   host_finish_harness se|sef|pe|pes|pef|pesf <genome.fa> <out.sam> <reads.fq> [<mates.fq>] [--unmapped_out] [--ambiguous_out] [--pbat]
 // (--ambiguous_out: paired end only here -- the single-end multi-exact case needs the located rows in row order, which only the
 // device path returns; --pbat as in bmbs_main.cpp: single end aligns the reverse complement, paired end swaps the files)
 #include <cstdio>
@@ -18,8 +20,8 @@
 int main(int argc, char** argv) {
   if (argc < 5) return 2;
   const std::string mode = argv[1], fa = argv[2], out_path = argv[3];
-  const bool fin_mode = mode == "sef";
-  const bool pe = mode != "se" && !fin_mode, sens = mode == "pes";
+  const bool fin_mode = mode == "sef" || mode == "pef" || mode == "pesf";      // through finished records (bmbs_final)
+  const bool pe = mode == "pe" || mode == "pes" || mode == "pef" || mode == "pesf", sens = mode == "pes" || mode == "pesf";
   bool unmapped_out = false, ambiguous_out = false, pbat = false;
   std::vector<std::string> files;
   for (int i = 4; i < argc; ++i) { if (!strcmp(argv[i], "--unmapped_out")) unmapped_out = true; else if (!strcmp(argv[i], "--ambiguous_out")) ambiguous_out = true; else if (!strcmp(argv[i], "--pbat")) pbat = true; else files.push_back(argv[i]); }
@@ -58,7 +60,8 @@ int main(int argc, char** argv) {
   std::vector<bmbs_final> fin; std::vector<uint16_t> mism;
   if (fin_mode) {
     fin.resize(n + 1); mism.resize((size_t)n * 32 + 64); size_t mused = 0;
-    if (orc_finish_se(h, flat.data(), offs.data(), n, 0.08, ambiguous_out ? 1 : 0, res.data(), cand.data(), fin.data(), mism.data(), mism.size(), &mused)) return 1;
+    if (!pe) { if (orc_finish_se(h, flat.data(), offs.data(), n, 0.08, ambiguous_out ? 1 : 0, res.data(), cand.data(), fin.data(), mism.data(), mism.size(), &mused)) return 1; }
+    else if (orc_finish_pe(h, flat.data(), offs.data(), n / 2, 0.08, 0, 500, sens ? 1 : 0, ambiguous_out ? 1 : 0, res.data(), cand.data(), fin.data(), mism.data(), mism.size(), &mused)) return 1;
   }
   std::string out; bmbs::sam_header(out, hc.chroms, "host_finish_harness");
   bmbs::MapStats st; std::vector<bmbs::HostHit> v1, v2; std::vector<char> win;
@@ -67,7 +70,9 @@ int main(int argc, char** argv) {
   const auto t_begin = std::chrono::steady_clock::now();
   for (int u = 0; u < units; ++u) {
     bmbs::MapStats t;
-    if (fin_mode) { bmbs::ReadView rv{recs[u].name, seq(u), recs[u].qual, raw1[u]}; bmbs::finish_single_final(hc, rv, fin[u], mism.data(), cand.data(), out, t, v1, win); }
+    if (fin_mode && pe) bmbs::finish_pair_final(hc, recs[2 * u].name, seq(2 * u), recs[2 * u].qual, recs[2 * u + 1].name, seq(2 * u + 1), raw2[u], recs[2 * u + 1].qual,
+                                                fin[2 * u], fin[2 * u + 1], mism.data(), out, t, win);
+    else if (fin_mode) { bmbs::ReadView rv{recs[u].name, seq(u), recs[u].qual, raw1[u]}; bmbs::finish_single_final(hc, rv, fin[u], mism.data(), cand.data(), out, t, v1, win); }
     else if (!pe) { bmbs::ReadView rv{recs[u].name, seq(u), recs[u].qual, raw1[u]}; bmbs::finish_single(hc, rv, res[u], cand.data(), out, t, v1, win); }
     else bmbs::finish_pair(hc, recs[2 * u].name, seq(2 * u), recs[2 * u].qual, recs[2 * u + 1].name, seq(2 * u + 1), raw2[u], recs[2 * u + 1].qual,
                            res[2 * u], res[2 * u + 1], cand.data(), out, t, v1, v2, win);

@@ -609,17 +609,13 @@ __global__ void __launch_bounds__(128) seed_reads(DevIndex ix, BatchView b, u32 
   // What a step of the seed in progress needs stays in registers; the per-read bookkeeping that only the transitions between
   // seeds touch lives in shared memory, one column per lane (registers decide how many warps an SM holds, and the kernel
   // lives on warps in flight).
-  // (read positions, seed counts and flags as 16-bit words: with 23.5 KB of shared memory per block instead of 27 KB a ninth
-  // block fits on the SM)
-  __shared__ u32 s_w[6][SEED_BLOCK];
-  __shared__ unsigned short s_h[15][SEED_BLOCK];
+  __shared__ u32 s_w[21][SEED_BLOCK];
   __shared__ u64 s_d[4][SEED_BLOCK];
   const int tx = threadIdx.x;
-  u32 &r = s_w[0][tx], &nc = s_w[1][tx], &first_cands = s_w[2][tx];
-  int &state = reinterpret_cast<int&>(s_w[3][tx]), &get_error = reinterpret_cast<int&>(s_w[4][tx]), &one_mm = reinterpret_cast<int&>(s_w[5][tx]);
-  unsigned short &L = s_h[0][tx], &first_c = s_h[1][tx], &off = s_h[2][tx], &first_len = s_h[3][tx], &max_seeds = s_h[4][tx], &seed_id = s_h[5][tx];
-  unsigned short &nt = s_h[6][tx], &bn = s_h[7][tx], &bs0 = s_h[8][tx], &bs1 = s_h[9][tx], &bep = s_h[10][tx], &bel = s_h[11][tx];
-  unsigned short &g_mlen = s_h[12][tx], &is_multi = s_h[13][tx], &second_ok = s_h[14][tx];
+  u32 &r = s_w[0][tx], &L = s_w[1][tx], &first_c = s_w[2][tx], &off = s_w[3][tx], &first_len = s_w[4][tx], &max_seeds = s_w[5][tx], &seed_id = s_w[6][tx];
+  u32 &nt = s_w[7][tx], &nc = s_w[8][tx], &bn = s_w[9][tx], &bs0 = s_w[10][tx], &bs1 = s_w[11][tx], &bep = s_w[12][tx], &bel = s_w[13][tx];
+  u32 &first_cands = s_w[14][tx], &g_mlen = s_w[15][tx], &is_multi = s_w[16][tx], &second_ok = s_w[17][tx];
+  int &state = reinterpret_cast<int&>(s_w[18][tx]), &get_error = reinterpret_cast<int&>(s_w[19][tx]), &one_mm = reinterpret_cast<int&>(s_w[20][tx]);
   u64 &sp = s_d[0][tx], &ep = s_d[1][tx], &site0 = s_d[2][tx], &g_hits = s_d[3][tx];   // g_hits, g_mlen: answer of the first seed, kept across its COMPARE step
   u32 kind = SK_FIRST;
   u32 s_off = 0, s_cur = 0, m = 0;                       // the seed in progress: start, bases available, symbols matched

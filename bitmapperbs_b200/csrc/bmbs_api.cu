@@ -550,15 +550,12 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
       // one persistent kernel: a lane per read, one dependent access per loop iteration, finished lanes take the next read
       if (plane_cap != b->seed_plane_cap) {      // resident blocks: registers and the staged read chunks decide
         int per_sm = 0;
-        const bool fused = getenv("BMBS_SEED_FUSED") != nullptr;
-        if ((fused ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seed_reads_fused, SEED_BLOCK, seed_smem)
-                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seed_reads, SEED_BLOCK, seed_smem)) == cudaSuccess && per_sm > 0) b->seed_blocks_per_sm = per_sm;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seed_reads, SEED_BLOCK, seed_smem) == cudaSuccess && per_sm > 0) b->seed_blocks_per_sm = per_sm;
         if (const char* e = getenv("BMBS_SEED_BLOCKS")) b->seed_blocks_per_sm = std::max(1, atoi(e));
         b->seed_plane_cap = plane_cap;
       }
       const int seed_blocks = std::min((n + SEED_BLOCK - 1) / SEED_BLOCK, b->sm_count * b->seed_blocks_per_sm);
-      if (getenv("BMBS_SEED_FUSED")) { seed_reads_fused<<<seed_blocks, SEED_BLOCK, seed_smem, s>>>(ix, v, plane_cap); ++b->launches; }
-      else { seed_reads<<<seed_blocks, SEED_BLOCK, seed_smem, s>>>(ix, v, plane_cap); ++b->launches; }
+      seed_reads<<<seed_blocks, SEED_BLOCK, seed_smem, s>>>(ix, v, plane_cap); ++b->launches;
     } else {      // the three phase kernels (one loop nest per read), kept for comparison
       seed_first<<<(n + 127) / 128, SEED_BLOCK, seed_smem, s>>>(ix, v, plane_cap); ++b->launches;
       seed_second<<<(n + 127) / 128, SEED_BLOCK, seed_smem, s>>>(ix, v, plane_cap); ++b->launches;

@@ -849,288 +849,6 @@ __global__ void __launch_bounds__(128) seed_reads(DevIndex ix, BatchView b, u32 
   flush_counters(s_cnt, cn, b.counters);
 }
 
-// The same machine with another loop: in every iteration every lane that has an LF step or the start of a seed to do prepares it
-// (stops, policy, key, address -- no memory access), then ALL accesses of the iteration are issued back to back, then every lane
-// takes what came back.  No lane waits for a vote (with the vote a warp runs one kind of step per iteration and a third of its
-// lanes take part), and an iteration costs one memory round trip however many kinds of step it holds.  COMPARE keeps its own turn.
-__global__ void __launch_bounds__(128, 8) seed_reads_fused(DevIndex ix, BatchView b, u32 plane_cap) {
-  extern __shared__ uint4 s_planes[];      // [plane_cap][SEED_BLOCK] staged read chunks, one column per lane
-  __shared__ u64 s_cnt[4];
-  __shared__ unsigned char s_lut[256];
-  if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
-  build_key_lut(s_lut);
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const u32 n_reads = (u32)b.n_reads;
-  SeedCounters cn;
-  ReadPlanes rp; rp.p = nullptr; rp.s = s_planes + threadIdx.x; rp.ns = 0;
-  int ph = PH_REFILL;
-  // What a step of the seed in progress needs stays in registers; the per-read bookkeeping that only the transitions between
-  // seeds touch lives in shared memory, one column per lane (registers decide how many warps an SM holds, and the kernel
-  // lives on warps in flight).
-  __shared__ u32 s_w[21][SEED_BLOCK];
-  __shared__ u64 s_d[4][SEED_BLOCK];
-  const int tx = threadIdx.x;
-  u32 &r = s_w[0][tx], &L = s_w[1][tx], &first_c = s_w[2][tx], &off = s_w[3][tx], &first_len = s_w[4][tx], &max_seeds = s_w[5][tx], &seed_id = s_w[6][tx];
-  u32 &nt = s_w[7][tx], &nc = s_w[8][tx], &bn = s_w[9][tx], &bs0 = s_w[10][tx], &bs1 = s_w[11][tx], &bep = s_w[12][tx], &bel = s_w[13][tx];
-  u32 &first_cands = s_w[14][tx], &g_mlen = s_w[15][tx], &is_multi = s_w[16][tx], &second_ok = s_w[17][tx];
-  int &state = reinterpret_cast<int&>(s_w[18][tx]), &get_error = reinterpret_cast<int&>(s_w[19][tx]), &one_mm = reinterpret_cast<int&>(s_w[20][tx]);
-  u64 &sp = s_d[0][tx], &ep = s_d[1][tx], &site0 = s_d[2][tx], &g_hits = s_d[3][tx];   // g_hits, g_mlen: answer of the first seed, kept across its COMPARE step
-  u32 kind = SK_FIRST;
-  u32 s_off = 0, s_cur = 0, m = 0;                       // the seed in progress: start, bases available, symbols matched
-  u64 top = 0, bot = 0, ptop = 0, pbot = 0, sa_known = 0;
-  bool known_sa = false;
-  u32 ss_base = 0, ss_lo = 0, ss_hi = 0, ss_bad = 0;     // 32 symbols of the read from ss_base on
-  auto emit = [&](u64 a, u32 hits, u32 mlen, u32 o) {
-    if (nt < MAX_TASKS) { SeedTask t; t.sp = a; t.hits = hits; t.mlen = (unsigned short)mlen; t.off = (unsigned short)o; b.tasks[(size_t)nt * b.n_reads + r] = t; }
-    ++nt; nc += hits ? hits : 1u;
-  };
-  auto symbol_at = [&](u32 pos) -> int {                 // pos >= ss_base, non-decreasing within a seed
-    if (pos - ss_base >= 32u) { ss_base = pos; rp.window(pos, ss_lo, ss_hi, ss_bad); }
-    const unsigned sh = pos - ss_base;
-    const u32 l = (ss_lo >> sh) & 1u, h = (ss_hi >> sh) & 1u, bad = (ss_bad >> sh) & 1u;
-    return (int)((l | ((~(l | h) & 1u) << 1)) | (bad * 3u));
-  };
-  // the read is done: its records
-  auto finish = [&]() {
-    b.state[r] = (unsigned char)state;
-    b.flags[r] = (unsigned char)((is_multi ? 1 : 0) | (second_ok ? 2 : 0));
-    b.one_mm[r] = (short)one_mm;
-    b.site0[r] = site0;
-    b.ntask[r] = nt < MAX_TASKS ? nt : MAX_TASKS; b.ncand[r] = nt <= MAX_TASKS ? nc : 0xFFFFFFFFu;
-    if (b.sensitive) {
-      const bool resolved = state == BMBS_EXACT_UNIQUE || state == BMBS_MULTI_EXACT;
-      unsigned short* k5 = b.bk + (size_t)r * 5;
-      k5[0] = (unsigned short)(resolved ? 0 : bn); k5[1] = (unsigned short)bs0; k5[2] = (unsigned short)bs1; k5[3] = (unsigned short)bep;
-      k5[4] = (unsigned short)(resolved ? 0 : bel);
-      b.first_cands[r] = (unsigned short)(resolved ? 0 : first_cands);
-    }
-    ph = PH_REFILL;
-  };
-  // next seed of the greedy phase, or the end of the read (loop condition of Schema.cpp:27434)
-  auto next_rest = [&]() {
-    kind = SK_REST;
-    if (seed_id < max_seeds && off < L) { s_off = off; s_cur = L - off; ph = PH_START; } else finish();
-  };
-  // first seed, after the unique-hit shortcut did not settle the read (Schema.cpp:27203-27330); mlen: the seed length as the
-  // shortcut left it (clamped to the first C, or the index of the single mismatch)
-  auto first_rest = [&](u32 mlen) {
-    one_mm = (int)mlen;
-    if (mlen == L && g_hits > 1 && (!b.pe || g_hits <= b.multi_cap)) {
-      is_multi = 1;
-      if (first_c == L) {
-        state = BMBS_MULTI_EXACT;
-        if (b.pe) emit(sp, (u32)g_hits, mlen, 0);
-        else if (b.amb_out) emit(sp, (u32)(g_hits > MAX_SEED_HITS ? MAX_SEED_HITS : g_hits), mlen, 0);   // output_ambiguous_exact_map_output_buffer walks at most 1000 rows
-        finish();
-        return;
-      }
-    }
-    if (g_hits != 1 && mlen >= b.seed_len && g_hits <= MAX_SEED_HITS && g_hits != 0) emit(sp, (u32)g_hits, mlen, 0);
-    const bool used = g_hits == 1 || (g_mlen >= b.seed_len && g_hits <= MAX_SEED_HITS);
-    bn = used ? 1 : 0; bel = used ? first_len : 0; first_cands = nc;
-    off = mlen == 0 ? next_offset_unmatched(rp, L, 0) : mlen / 2;
-    seed_id = 1;
-    if (get_error == 1 && L - first_len >= 17) { kind = SK_SECOND; s_off = first_len; s_cur = L - first_len; ph = PH_START; }   // one-mismatch rule
-    else next_rest();
-  };
-  // the second seed has its answer (Schema.cpp:27334-27401): known_sa = its single site is in sa_known, else rows [top, bot)
-  auto second_done = [&]() {
-    const u64 hits = known_sa ? 1 : (bot > top ? bot - top : 0);
-    if (hits <= MAX_SEED_HITS) {
-      if (known_sa) emit(sa_known, 0, 0, 0); else if (hits) emit(top, (u32)hits, s_cur, s_off);
-      second_ok = 1; finish();
-    } else next_rest();
-  };
-  // a greedy seed has its answer: m symbols matched, rows [top, bot) (known_sa: one row whose suffix-array value is sa_known)
-  auto greedy_done = [&]() {
-    const u64 hits = known_sa ? 1 : bot - top;
-    const u32 mlen = m;
-    if (!known_sa) { sp = top; ep = bot; }
-    if (kind == SK_FIRST) {
-      g_hits = hits; g_mlen = mlen; first_len = mlen;
-      if (hits == 1) ph = PH_COMPARE;                                            // unique-hit shortcut: locate + direct compare
-      else first_rest(mlen);
-    } else {                                                                     // Schema.cpp:27434-27515
-      bool used = true;
-      if (hits == 1) { if (known_sa) emit(2 * ix.N - sa_known - mlen - off, 0, 0, 0); else emit(sp, 1, mlen, off); }
-      else if (mlen >= b.seed_len && hits <= MAX_SEED_HITS) { if (hits) emit(sp, (u32)hits, mlen, off); }
-      else { used = false; if (s_cur == mlen) { finish(); return; } }
-      if (used) { if (bn == 0) bs0 = off; else if (bn == 1) bs1 = off; bep = bel; bel = off + mlen; ++bn; }
-      off = mlen == 0 ? next_offset_unmatched(rp, L, off) : off + mlen / 2;
-      ++seed_id;
-      next_rest();
-    }
-  };
-  bool force_hash = false;                               // the deep-table entry was saturated: the seed starts from the 16-mer table
-  u32 iter = 0;
-  for (;;) {
-    const u32 m_work = __ballot_sync(0xffffffffu, ph != PH_IDLE);
-    if (!m_work) break;
-    // ---- COMPARE has two dependent round trips of its own (locate, then the genome words): it runs when a quarter of the warp
-    // waits for it, every sixteenth iteration, or when nothing else is left
-    {
-      const u32 m_cmp = __ballot_sync(0xffffffffu, ph == PH_COMPARE);
-      const int c_cmp = __popc(m_cmp), c_other = __popc(m_work) - c_cmp;
-      const bool do_cmp = c_cmp > 0 && (c_cmp >= 8 || c_other == 0 || (iter & 15u) == 15u);
-      ++iter;
-      if (do_cmp && ph == PH_COMPARE) {
-        if (kind == SK_FIRST) {
-          // ---- unique first seed: locate, compare the rest of the read with the genome (try_process_unique_mismatch_end_to_end_*, Schema.cpp:15410)
-          int st = 0; const u64 sa = known_sa ? sa_known : locate_row(ix, sp, st); cn.n_llf += st; ++cn.n_rows;
-          u32 mlen = g_mlen;
-          const u64 site = 2 * ix.N - sa - mlen;
-          emit(site, 0, 0, 0);
-          if (mlen > first_c) mlen = first_c;
-          int errors = 0;
-          if (mlen != L) errors = compare_rest(ix, rp, site, L, mlen);
-          get_error = errors;
-          if (errors == 0) { state = BMBS_EXACT_UNIQUE; site0 = site; finish(); }
-          else first_rest(mlen);
-        } else {
-          // ---- exact seed with one row left: the remaining symbols can only keep that row or empty the interval
-          int st = 0; const u64 sa = known_sa ? sa_known : locate_row(ix, top, st); cn.n_llf += st; ++cn.n_rows;
-          const u64 s0 = 2 * ix.N - sa - m;                 // double-strand coordinate of read[s_off]
-          bool ok = s0 + s_cur <= 2 * ix.N;                 // else the text ends before the pattern does
-          for (u32 p = s_off + m; ok && p < s_off + s_cur; p += 32) {
-            u32 rlo, rhi, rbad; rp.window(p, rlo, rhi, rbad);
-            const u64 g = s0 + (p - s_off);
-            const uint2 w0 = __ldg(ix.planes + (g >> 5)), w1 = __ldg(ix.planes + (g >> 5) + 1);
-            const unsigned sh = (unsigned)g & 31u;
-            const u32 glo = __funnelshift_r(w0.x, w1.x, sh), ghi = __funnelshift_r(w0.y, w1.y, sh);
-            u32 mism = (rlo ^ glo) | (~rlo & (rhi ^ ghi)) | rbad;   // 3-letter equality: lo set (C/T) ignores hi
-            const u32 left = s_off + s_cur - p;
-            if (left < 32u) mism &= (1u << left) - 1u;
-            if (mism) ok = false;
-          }
-          known_sa = ok; sa_known = s0 - s_off;             // the site, or no hit
-          if (!ok) bot = top;
-          ph = PH_DONE;
-        }
-      }
-    }
-    // ---- (A) LF lanes: what the step needs, or why the seed stops here -- no memory access yet
-    bool lf_load = false; u64 adj_a = 0, adj_b = 0; int lf_c = 0;
-    if (ph == PH_LF) {
-      if (kind != SK_SECOND) {                             // count_backward_as_much_1_terminate's loop (bwt.h:2081-2209)
-        bool stop = true;
-        if (m < s_cur) {
-          ptop = top; pbot = bot;
-          const int c = symbol_at(s_off + m);
-          if (bot - top != 1) {
-            if (c > 2) bot = top;
-            else { lf_load = true; lf_c = c; stop = false; }
-          }
-        }
-        if (stop) { if (bot <= top) { top = ptop; bot = pbot; } ph = PH_DONE; }
-      } else {                                             // count_hash_table's loop (bwt.h:1848-1952)
-        if (m < s_cur && bot > top) {
-          if (bot - top == 1) ph = PH_COMPARE;
-          else {
-            const int c = symbol_at(s_off + m);
-            if (c > 2) { bot = top; ph = PH_DONE; }
-            else { lf_load = true; lf_c = c; }
-          }
-        } else {
-          if (known_sa) sa_known = 2 * ix.N - sa_known - m - s_off;   // the pattern ends where the table entry stands: its site
-          ph = PH_DONE;
-        }
-      }
-      if (lf_load) { adj_a = adjust_row(ix, top); adj_b = adjust_row(ix, bot); }
-    }
-    // ---- (B) a seed has its answer: the policy of the read's phase (lanes that stopped in (A) go on right away)
-    if (ph == PH_DONE) { if (kind == SK_SECOND) second_done(); else greedy_done(); force_hash = false; }
-    // ---- (C) lanes without a read take the next ones (one atomic per warp)
-    {
-      const u32 m_refill = __ballot_sync(0xffffffffu, ph == PH_REFILL);
-      if (m_refill) {
-        const int c_refill = __popc(m_refill);
-        u32 base = 0;
-        const int leader = __ffs(m_refill) - 1;
-        if (lane == leader) base = atomicAdd(b.list_count, (u32)c_refill);
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (ph == PH_REFILL) {
-          const u32 i = base + __popc(m_refill & ((1u << lane) - 1u));
-          if (i >= n_reads) ph = PH_IDLE;
-          else {
-            r = i;
-            L = b.len[r]; first_c = b.first_c[r];
-            rp.stage(b.rplanes + plane_chunk_offset(b.offsets, (int)r), L, s_planes + threadIdx.x, plane_cap);
-            { u64 ms = (u64)L / 10 - 1; if (ms > 25) ms = 25; max_seeds = (u32)ms; }   // u64 wrap for L < 10, as in the reference
-            nt = 0; nc = 0; off = 0; first_len = 0; seed_id = 0; sp = 0; ep = 0; site0 = 0;
-            state = BMBS_NONE; get_error = -1; one_mm = 0; is_multi = 0; second_ok = 0;
-            bn = 0; bs0 = 0; bs1 = 0; bep = 0; bel = 0; first_cands = 0; force_hash = false;
-            if (max_seeds > 0 && L > 0) { kind = SK_FIRST; s_off = 0; s_cur = L; ph = PH_START; }
-            else finish();                                                     // no seed at all (its REFILL is taken next iteration)
-          }
-        }
-      }
-    }
-    // ---- (D) start of a seed: the key and the address of its table entry (count_backward_as_much_1_terminate bwt.h:2081 /
-    // count_hash_table :1848)
-    int st_load = 0; const u64* st_adr = nullptr;          // 1: deep-table entry, 2: the two words of the 16-mer table
-    if (ph == PH_START) {
-      const bool exact = kind == SK_SECOND;
-      u32 key;
-      known_sa = false;
-      if (s_cur < (exact ? 17u : 18u) || !key16(rp, s_lut, s_off, key)) { m = 0; top = 0; bot = 0; ph = PH_DONE; }   // no hit at all
-      else {
-        m = 16;
-        ss_base = s_off + 16; rp.window(ss_base, ss_lo, ss_hi, ss_bad);
-        u32 ext;
-        if (!force_hash && ix.ktab && s_cur >= 16 + ix.kdepth && kmer_ext(ix, s_lut, ss_lo, ss_hi, ss_bad, ext)) { st_load = 1; st_adr = ix.ktab + (u64)key * ix.kpow + ext; }
-        else { st_load = 2; st_adr = ix.hash + key; }
-      }
-    }
-    // ---- (E) every lane's access of this iteration, issued back to back: they are in flight together
-    OccBlock ba, bb; u64 e0 = 0, e1 = 0;
-    ba.planes = make_ulonglong2(0, 0); ba.cnt = make_ulonglong2(0, 0); ba.blk = 0; bb = ba;
-    if (lf_load) { ba = load_occ(ix, adj_a); bb = load_occ(ix, adj_b); }
-    if (st_load) { e0 = __ldg(st_adr); if (st_load == 2) e1 = __ldg(st_adr + 1); }
-    // ---- (F) what came back
-    if (lf_load) {
-      const u64 m1 = 0ull - (u64)(lf_c == 1), m2 = 0ull - (u64)(lf_c == 2), m0 = ~(m1 | m2);
-      top = rank_masked(ix, ba, adj_a, m0, m1, m2);
-      bot = rank_masked(ix, bb, adj_b, m0, m1, m2);
-      cn.n_occ += bb.blk != ba.blk ? 2 : 1;
-      if (kind != SK_SECOND) {
-        bool stop = true;
-        if (bot > top) { ++m; stop = m >= s_cur; }
-        if (stop) { if (bot <= top) { top = ptop; bot = pbot; } ph = PH_DONE; }
-      } else ++m;
-    }
-    if (st_load) {
-      const bool exact = kind == SK_SECOND;
-      bool dead = false, answered = false;
-      ++cn.n_hash;
-      if (st_load == 1) {
-        const u64 size = e0 >> 39; const u32 code = (u32)(e0 >> 36) & 7u;
-        if (size == KTAB_SAT) { force_hash = true; }                           // too many rows to store: the 16-mer table next iteration
-        else if (code == 0) { dead = true; m = 0; }                            // the 16-mer does not occur
-        else {
-          m = 15 + code; top = e0 & 0xFFFFFFFFFull; bot = top + size;
-          if (!exact) {
-            if (size == 1) { known_sa = true; sa_known = top; answered = true; }   // one row: the entry holds its SA value
-            else if (m < 16 + ix.kdepth) answered = true;
-          } else {
-            if (m < 16 + ix.kdepth && size >= 2) dead = true;                  // the next symbol empties the interval
-            else if (size == 1) { known_sa = true; sa_known = top; }
-          }
-        }
-      } else {
-        top = e0 & 0xFFFFFFFFFull; bot = (e1 & 0xFFFFFFFFFull) - (e1 >> 60);   // hash_query
-        force_hash = false;
-        if (bot <= top) { dead = true; m = 0; }
-      }
-      if (force_hash && st_load == 1) { /* stays PH_START */ }
-      else if (dead) { top = 0; bot = 0; known_sa = false; ph = PH_DONE; }
-      else if (answered) ph = PH_DONE;
-      else { ph = PH_LF; ptop = ~0ull; pbot = ~0ull; }
-    }
-  }
-  flush_counters(s_cnt, cn, b.counters);
-}
-
 // ------------------------------------------------------------------------------------------- expand + locate
 // Seed tasks -> candidate sites, one kernel.  A warp owns 32 consecutive reads, i.e. one contiguous range of candidate
 // slots [coff[r0], coff[r0+32]).  Its lanes first lay the reads' tasks out as a table of segments {first slot, first row or

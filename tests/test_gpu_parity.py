@@ -436,3 +436,10 @@ def test_mapper_bam_output_holds_the_same_records(golden, built, name, args):
         assert (r["name"], r["flag"], r["rid"], r["pos"], r["mapq"], r["cigar"], r["seq"], r["qual"], r["tags"]) == \
                (f[0], int(f[1]), rid[f[2]], int(f[3]) - 1, int(f[4]), f[5], f[9], f[10], f[11:])
         assert r["npos"] == int(f[7]) - 1 and r["tlen"] == int(f[8])
+    # and byte for byte what the reference's own writer (the stock reference linked with its vendored, patched htslib) puts out
+    ref = ROOT_DIR / "oracle/_ref/bitmapperBS_bam"
+    if ref.exists():
+        from test_host_bam import bam_payload
+        subprocess.run([str(ref), "--search", "genome.fa", *args, "-t", "1", "--bam", "-o", "ref.bam"], cwd=golden, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        gt, gd, gr = bam_payload(golden / "gpu.bam"); rt, rd, rr = bam_payload(golden / "ref.bam")
+        assert gd == rd and gr == rr

@@ -1,7 +1,7 @@
 """Host BAM writer (bitmapperbs_b200/csrc/host/bam.hpp, behind `bmbs --bam`): the golden SAM files of the real reference are
 turned into BAM by the same calls the mapper makes, decoded here with nothing but gzip + struct, and compared with the SAM
-text field by field (the reference writes its BAM through a patched htslib, bam_prase.cpp:248-274, which this build of the
-reference stubs out -- so the container is checked against the specification, the content against the reference's SAM)."""
+text field by field; and the record bytes are compared with what the reference's own writer produces (the stock reference linked
+with its vendored, patched htslib: bam_prase.cpp:248-274 -> chhy_bam_write1_pure; oracle/_ref/bitmapperBS_bam)."""
 import gzip
 import struct
 import subprocess
@@ -108,3 +108,36 @@ def test_bam_matches_sam(harness, tmp_path, name):
         import re
         ref_len = sum(int(n) for n, op in re.findall(r"(\d+)([MIDNSHP=X])", f[5]) if op in "MDN=X")
         assert r["bin"] == reg2bin(r["pos"], r["pos"] + (ref_len or 1))
+
+
+# ---- against the reference's own BAM writer: oracle/_ref/bitmapperBS_bam is the stock reference linked with its vendored, patched
+# htslib (chhy_bam_write1_pure, bam_prase.cpp:248-274; built by oracle/build_ref.sh from the sources under /root/reference)
+def bam_payload(path):
+    """-> (header text, reference dictionary bytes, the records exactly as they stand in the decompressed stream)"""
+    d = gzip.decompress(open(path, "rb").read())
+    assert d[:4] == b"BAM\x01"
+    l_text = struct.unpack_from("<i", d, 4)[0]
+    p = 8 + l_text
+    n_ref = struct.unpack_from("<i", d, p)[0]; q = p + 4
+    for _ in range(n_ref):
+        q += 4 + struct.unpack_from("<i", d, q)[0] + 4
+    return d[8:8 + l_text].decode(), d[p:q], d[q:]
+
+
+@pytest.mark.parametrize("name,args", [("se100", ["--seq", "se100.fq"]), ("se250", ["--seq", "se250.fq", "--unmapped_out"]),
+                                       ("pe150", ["--seq1", "pe150_1.fq", "--seq2", "pe150_2.fq", "--pe"]),
+                                       ("pe100hs", ["--seq1", "pe100h_1.fq", "--seq2", "pe100h_2.fq", "--pe", "--sensitive", "--unmapped_out"])])
+def test_bam_records_identical_to_the_reference_writer(harness, golden, name, args):
+    """the reference writes the same alignments once as SAM and once as BAM; the product's writer turns that SAM into a BAM whose
+    reference dictionary and record bytes (every field, bin, packed sequence, tags) equal the reference's own"""
+    ref = ROOT / "oracle/_ref/bitmapperBS_bam"
+    if not ref.exists():
+        pytest.skip("reference with its BAM writer absent (oracle/build_ref.sh builds it where /root/reference exists)")
+    for out, fmt in ((f"refw_{name}.bam", ["--bam"]), (f"refw_{name}.sam", [])):
+        subprocess.run([str(ref), "--search", "genome.fa", *args, *fmt, "-t", "1", "-o", out], cwd=golden, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([str(harness), str(golden / f"refw_{name}.sam"), str(golden / f"ours_{name}.bam")], check=True)
+    rt, rd, rr = bam_payload(golden / f"refw_{name}.bam")
+    ot, od, orr = bam_payload(golden / f"ours_{name}.bam")
+    assert od == rd and len(rr) > 10000 and orr == rr
+    strip = lambda t: [l for l in t.splitlines() if not l.startswith("@PG")]      # the @PG line carries each run's command line
+    assert strip(ot) == strip(rt)

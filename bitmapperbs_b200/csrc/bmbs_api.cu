@@ -408,10 +408,19 @@ struct bmbs_batch {
   size_t mism_cap = 0, fb_cap = 0; bool finished = false;
   int n_reads = 0, pe = 0, max_len = 0, launches = 0, sm_count = 148, seed_blocks_per_sm = 8; u32 seed_plane_cap = 0;
   u32 pe_short = 48;             // pairs with more hits than this go to the warp kernel of the pair finishing (BMBS_PE_FIN_SHORT: tests)
+  int verify_variant = 2;        // which pipe the shifts of the 32-bit band run on (bpm_col32; BMBS_VERIFY_VARIANT = 0 .. 3)
   bool ran = false;
 };
 
 namespace {
+void launch_verify(bmbs_batch* b, int per_sm, int bd, size_t smem, cudaStream_t s, const DevIndex& ix, const BatchView& v, int nch2) {
+  const int grid = b->sm_count * per_sm;
+  if (b->verify_variant == 0) verify_windows<0><<<grid, bd, smem, s>>>(ix, v, nch2, 2u);
+  else if (b->verify_variant == 1) verify_windows<1><<<grid, bd, smem, s>>>(ix, v, nch2, 2u);
+  else if (b->verify_variant == 2) verify_windows<2><<<grid, bd, smem, s>>>(ix, v, nch2, 2u);
+  else verify_windows<3><<<grid, bd, smem, s>>>(ix, v, nch2, 2u);
+  ++b->launches;
+}
 // device arrays of a batch are carved out of one slab (one cudaMalloc per batch context): requests are recorded first
 struct SlabRequest { void** slot; size_t bytes; };
 thread_local std::vector<SlabRequest> g_slab;
@@ -479,7 +488,11 @@ extern "C" int bmbs_batch_create(bmbs_index* idx, int dev, size_t max_reads, siz
   if (e != cudaSuccess) { std::string m = std::string("batch allocation: ") + cudaGetErrorString(e); bmbs_batch_free(b); return fail(BMBS_ERR_CUDA, m); }
   v.slot_cap = cand_cap;
   // verify_windows may need more than 48 KB of dynamic shared memory for long reads
-  cudaFuncSetAttribute(verify_windows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(verify_windows<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(verify_windows<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(verify_windows<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(verify_windows<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (const char* e = getenv("BMBS_VERIFY_VARIANT")) b->verify_variant = std::min(3, std::max(0, atoi(e)));
   cudaFuncSetAttribute(votes_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BIG_SMEM_ELEMS * sizeof(u64)));
   cudaFuncSetAttribute(finish_pe_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PE_FIN_WARPS * 2 * PE_FIN_STAGE * sizeof(bmbs_cand)));
   *out = b;
@@ -581,7 +594,7 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
     int per_sm = (int)((226 * 1024) / (smem + 1024)); if (per_sm > 12) per_sm = 12; if (per_sm < 1) per_sm = 1;
     run_scan(b, v.nv, (u32)n, v.voff, v.totals + 1, v.slot_cap, 4u);
     gather_work<<<(n + 127) / 128, 128, 0, s>>>(v); ++b->launches;
-    verify_windows<<<b->sm_count * per_sm, bd, smem, s>>>(ix, v, nch2); ++b->launches;
+    launch_verify(b, per_sm, bd, smem, s, ix, v, nch2);
     CU(cudaEventRecord(b->ev[6], s));
     if (v.sensitive) {
       // --pe --sensitive: pair logic on the verified lists, then one re-seeding round for the mates left without a hit
@@ -600,7 +613,7 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
       sens_reseed_filter<<<b->sm_count * 4, 128, 0, s>>>(w); ++b->launches;
       run_scan(b, w.nv, (u32)n, w.voff, w.totals + 1, w.slot_cap, 4u, w.totals + 2);
       gather_work<<<(n + 127) / 128, 128, 0, s>>>(w); ++b->launches;
-      verify_windows<<<b->sm_count * per_sm, bd, smem, s>>>(ix, w, nch2); ++b->launches;
+      launch_verify(b, per_sm, bd, smem, s, ix, w, nch2);
       sens_reseed_finish<<<b->sm_count * 4, 128, 0, s>>>(w); ++b->launches;
     }
     CU(cudaEventRecord(b->ev[7], s));
@@ -854,7 +867,7 @@ extern "C" int bmbs_batch_verify(bmbs_batch* b, const uint32_t* read_idx, const 
   while (bd > 32 && (size_t)5 * nch2 * bd * 8 > 96 * 1024) bd >>= 1;
   const size_t smem = (size_t)5 * nch2 * bd * 8;
   int per_sm = (int)((226 * 1024) / (smem + 1024)); if (per_sm > 12) per_sm = 12; if (per_sm < 1) per_sm = 1;
-  verify_windows<<<b->sm_count * per_sm, bd, smem, s>>>(b->copy->view, v, nch2); ++b->launches;
+  launch_verify(b, per_sm, bd, smem, s, b->copy->view, v, nch2);
   CU(cudaEventRecord(b->ev[6], s)); CU(cudaEventRecord(b->ev[7], s)); CU(cudaEventRecord(b->ev[8], s));
   CU(cudaMemcpyAsync(b->h_small + 4, v.counters, 8 * 8, cudaMemcpyDeviceToHost, s));
   CU(cudaGetLastError());

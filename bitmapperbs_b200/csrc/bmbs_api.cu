@@ -408,18 +408,12 @@ struct bmbs_batch {
   size_t mism_cap = 0, fb_cap = 0; bool finished = false;
   int n_reads = 0, pe = 0, max_len = 0, launches = 0, sm_count = 148, seed_blocks_per_sm = 8; u32 seed_plane_cap = 0;
   u32 pe_short = 48;             // pairs with more hits than this go to the warp kernel of the pair finishing (BMBS_PE_FIN_SHORT: tests)
-  int verify_variant = 2;        // which pipe the shifts of the 32-bit band run on (bpm_col32; BMBS_VERIFY_VARIANT = 0 .. 3)
   bool ran = false;
 };
 
 namespace {
 void launch_verify(bmbs_batch* b, int per_sm, int bd, size_t smem, cudaStream_t s, const DevIndex& ix, const BatchView& v, int nch2) {
-  const int grid = b->sm_count * per_sm;
-  if (b->verify_variant == 0) verify_windows<0><<<grid, bd, smem, s>>>(ix, v, nch2, 2u);
-  else if (b->verify_variant == 1) verify_windows<1><<<grid, bd, smem, s>>>(ix, v, nch2, 2u);
-  else if (b->verify_variant == 2) verify_windows<2><<<grid, bd, smem, s>>>(ix, v, nch2, 2u);
-  else verify_windows<3><<<grid, bd, smem, s>>>(ix, v, nch2, 2u);
-  ++b->launches;
+  verify_windows<<<b->sm_count * per_sm, bd, smem, s>>>(ix, v, nch2); ++b->launches;
 }
 // device arrays of a batch are carved out of one slab (one cudaMalloc per batch context): requests are recorded first
 struct SlabRequest { void** slot; size_t bytes; };
@@ -488,11 +482,7 @@ extern "C" int bmbs_batch_create(bmbs_index* idx, int dev, size_t max_reads, siz
   if (e != cudaSuccess) { std::string m = std::string("batch allocation: ") + cudaGetErrorString(e); bmbs_batch_free(b); return fail(BMBS_ERR_CUDA, m); }
   v.slot_cap = cand_cap;
   // verify_windows may need more than 48 KB of dynamic shared memory for long reads
-  cudaFuncSetAttribute(verify_windows<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(verify_windows<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(verify_windows<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(verify_windows<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  if (const char* e = getenv("BMBS_VERIFY_VARIANT")) b->verify_variant = std::min(3, std::max(0, atoi(e)));
+  cudaFuncSetAttribute(verify_windows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(votes_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BIG_SMEM_ELEMS * sizeof(u64)));
   cudaFuncSetAttribute(finish_pe_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PE_FIN_WARPS * 2 * PE_FIN_STAGE * sizeof(bmbs_cand)));
   *out = b;

@@ -1442,82 +1442,48 @@ __device__ __forceinline__ void bpm_step32(u32 eq_raw, u32 mask, u32& VP, u32& V
   VN = X2 & HP; VP = HN | ~(X2 | HP);
   dbits = __funnelshift_r(dbits, D0, 1);
 }
-// The same column with its two shifts on the FMA pipe (the ALU pipe is what bounds the kernel, the FMA pipe idles): one
-// IMAD.WIDE.U32 D0 * 2^31 yields D0 >> 1 in its high word and the diagonal bit (bit 0 of D0) as bit 31 of its low word; a
-// IMAD.HI.U32 by 2 turns that word into 0 / 1, which is added to the count of matched diagonal cells (`two` = 2 arrives as a
-// kernel argument: a literal 2 is strength-reduced into shifts on the ALU pipe).  7 LOP3 on the ALU pipe, 3-4 IMAD on the FMA pipe.
-__device__ __forceinline__ void bpm_step32_fma(u32 eq_raw, u32 mask, u32& VP, u32& VN, u32& matched, u32 two) {
-  u32 X;
-  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(X) : "r"(eq_raw), "r"(mask), "r"(VN));    // (eq_raw & mask) | VN
-  const u32 D0 = ((VP + (X & VP)) ^ VP) | X;
-  const u32 HN = VP & D0, HP = VN | ~(VP | D0);
-  u32 dbit, X2;
-  asm("{ .reg .u64 t; mul.wide.u32 t, %2, 0x80000000; mov.b64 {%0, %1}, t; }" : "=r"(dbit), "=r"(X2) : "r"(D0));
-  VN = X2 & HP; VP = HN | ~(X2 | HP);
-  u32 one; asm("mul.hi.u32 %0, %1, %2;" : "=r"(one) : "r"(dbit), "r"(two));
-  matched += one;
-}
-// (u32)(e0 >> C) for a constant C on the FMA pipe: IMAD.HI.U32 by 2^(32-C) is the low word shifted right, an IMAD by the same
-// constant adds the high word's low bits above it (the two parts do not overlap, so the sum is the OR)
-template <int C>
-__device__ __forceinline__ u32 shr64_fma(u64 e0) {
-  const u32 lo = (u32)e0, hi = (u32)(e0 >> 32);
-  if (C == 0) return lo;
-  constexpr u32 M = 1u << ((32 - C) & 31);
-  u32 t, r;
-  asm("mul.hi.u32 %0, %1, %2;" : "=r"(t) : "r"(lo), "n"(M));
-  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(hi), "n"(M), "r"(t));
-  return r;
-}
-// eight columns of group G (window bits 8G .. 8G+7 of the chunk) on one word of read codes; V: 0 = shifts on the ALU pipe
-// (bpm_step32), 1 = the band shift and the diagonal bit on the FMA pipe (bpm_step32_fma), 2 = the Eq alignment there as well,
-// 3 = and the read's code: `ev` holds the word with its nibbles in reverse order, the codes still to come on top, and one
-// IMAD.WIDE.U32 by 16 splits it into the next code (high word) and the rest (low word)
-template <int V, int G, int J>
-__device__ __forceinline__ void bpm_col32(const char* __restrict__ cbytes, u32 pstride8, u32& ev, u32 od, u32 mask, u32& VP, u32& VN, u32& acc, u32& matched, u32 two) {
-  u32 code;
-  if (V == 3) asm("{ .reg .u64 t; mul.wide.u32 t, %2, 16; mov.b64 {%0, %1}, t; }" : "=r"(ev), "=r"(code) : "r"(ev));
-  else code = __byte_perm((J & 1) ? od : ev, 0u, 0x4440u | (u32)(J >> 1));                // nibble J of the word, as a number
+// eight columns of group G (window bits 8G .. 8G+7 of the chunk) on one word of read codes
+template <int G, int J>
+__device__ __forceinline__ void bpm_col32(const char* __restrict__ cbytes, u32 pstride8, u32 ev, u32 od, u32 mask, u32& VP, u32& VN, u32& dbits) {
+  const u32 code = __byte_perm((J & 1) ? od : ev, 0u, 0x4440u | (u32)(J >> 1));          // nibble J of the word, as a number
   const u64 e0 = *reinterpret_cast<const u64*>(cbytes + code * pstride8);
-  if (V == 0) bpm_step32((u32)(e0 >> (G * 8 + J)), mask, VP, VN, acc);
-  else if (V == 1) bpm_step32_fma((u32)(e0 >> (G * 8 + J)), mask, VP, VN, matched, two);
-  else bpm_step32_fma(shr64_fma<G * 8 + J>(e0), mask, VP, VN, matched, two);
+  bpm_step32((u32)(e0 >> (G * 8 + J)), mask, VP, VN, dbits);
 }
-// eight columns of group G on one word of read codes
-template <int V, int G>
-__device__ __forceinline__ void bpm_group32(const char* __restrict__ cbytes, u32 pstride8, u32 word, u32 mask, u32& VP, u32& VN, u32& acc, u32& matched, u32 two) {
-  u32 ev = word & 0x0F0F0F0Fu, od = (word >> 4) & 0x0F0F0F0Fu;
-  if (V == 3) { const u32 r = __byte_perm(word, 0u, 0x0123u); ev = ((r & 0x0F0F0F0Fu) << 4) | ((r >> 4) & 0x0F0F0F0Fu); }
-  bpm_col32<V, G, 0>(cbytes, pstride8, ev, od, mask, VP, VN, acc, matched, two);
-  bpm_col32<V, G, 1>(cbytes, pstride8, ev, od, mask, VP, VN, acc, matched, two);
-  bpm_col32<V, G, 2>(cbytes, pstride8, ev, od, mask, VP, VN, acc, matched, two);
-  bpm_col32<V, G, 3>(cbytes, pstride8, ev, od, mask, VP, VN, acc, matched, two);
-  bpm_col32<V, G, 4>(cbytes, pstride8, ev, od, mask, VP, VN, acc, matched, two);
-  bpm_col32<V, G, 5>(cbytes, pstride8, ev, od, mask, VP, VN, acc, matched, two);
-  bpm_col32<V, G, 6>(cbytes, pstride8, ev, od, mask, VP, VN, acc, matched, two);
-  bpm_col32<V, G, 7>(cbytes, pstride8, ev, od, mask, VP, VN, acc, matched, two);
+template <int G>
+__device__ __forceinline__ void bpm_group32(const char* __restrict__ cbytes, u32 pstride8, u32 word, u32 mask, u32& VP, u32& VN, u32& dbits) {
+  const u32 ev = word & 0x0F0F0F0Fu, od = (word >> 4) & 0x0F0F0F0Fu;
+  bpm_col32<G, 0>(cbytes, pstride8, ev, od, mask, VP, VN, dbits);
+  bpm_col32<G, 1>(cbytes, pstride8, ev, od, mask, VP, VN, dbits);
+  bpm_col32<G, 2>(cbytes, pstride8, ev, od, mask, VP, VN, dbits);
+  bpm_col32<G, 3>(cbytes, pstride8, ev, od, mask, VP, VN, dbits);
+  bpm_col32<G, 4>(cbytes, pstride8, ev, od, mask, VP, VN, dbits);
+  bpm_col32<G, 5>(cbytes, pstride8, ev, od, mask, VP, VN, dbits);
+  bpm_col32<G, 6>(cbytes, pstride8, ev, od, mask, VP, VN, dbits);
+  bpm_col32<G, 7>(cbytes, pstride8, ev, od, mask, VP, VN, dbits);
 }
 // the last n < 8 columns of a read, in group G of the chunk
-template <int V, int G>
-__device__ __forceinline__ void bpm_tail32(const char* __restrict__ cbytes, u32 pstride8, u32 word, int n, u32 mask, u32& VP, u32& VN, u32& acc, u32& matched, u32 two) {
+template <int G>
+__device__ __forceinline__ void bpm_tail32(const char* __restrict__ cbytes, u32 pstride8, u32 word, int n, u32 mask, u32& VP, u32& VN, u32& dbits) {
   for (int j = 0; j < n; ++j) {
     const u32 code = (word >> (4 * j)) & 0xFu;
     const u64 e0 = *reinterpret_cast<const u64*>(cbytes + code * pstride8);
-    if (V == 0) bpm_step32((u32)(e0 >> (G * 8 + j)), mask, VP, VN, acc);
-    else bpm_step32_fma((u32)(e0 >> (G * 8 + j)), mask, VP, VN, matched, two);
+    bpm_step32((u32)(e0 >> (G * 8 + j)), mask, VP, VN, dbits);
   }
 }
-template <int V>
+// What was measured and left out (profiles/r02X_verify_variant*.jsonl): the band shift D0 >> 1 and the diagonal bit from one
+// IMAD.WIDE.U32 by 2^31 (high word / bit 31 of the low word), the diagonal count by IMAD.HI.U32, the Eq alignment as IMAD.HI.U32 +
+// IMAD by 2^(32-c), the code extraction as a chain of IMAD.WIDE.U32 by 16 -- 8.6 / 7.7 instead of 11.5 ALU-pipe instructions per
+// column, every result identical, and 3 / 3 / 6 % SLOWER at L = 150: the kernel's time follows its instruction count
+// (15.1 -> 15.4 / 16.7 / 16.6 per column), not the ALU pipe's share of it.
 __device__ __forceinline__ void bpm_columns32(const u64* __restrict__ sm, int stride, int nch2, const u32* __restrict__ rw,
-                                              int L, int k, int& end_out, u32& err_out, u32 two) {
+                                              int L, int k, int& end_out, u32& err_out) {
   const int band = 2 * k + 1;
   const u32 mask = band >= 32 ? ~0u : ((1u << band) - 1u);
   const u32 pstride8 = (u32)(nch2 * stride) * 8u;
   u32 VP = 0, VN = 0;
   int err = 0;
   const int limit = 3 * k;   // err - 2k > k can never recover (Levenshtein_Cal.h:455); checked every 32 columns
-  u32 acc = 0;               // V = 0: the diagonal bits of the last 32 columns
-  u32 matched = 0;           // V > 0: the count of matched diagonal cells
+  u32 dbits = 0;             // the diagonal bits of the last 32 columns
   end_out = -1; err_out = 0xFFFFFFFFu;
   // a read's code words start on a 16-byte boundary (code_word_offset): the 32 columns of a chunk are one 128-bit load, fetched
   // one chunk ahead (a read's words are followed by the next read's or by slack: the look-ahead past the last chunk reads
@@ -1529,23 +1495,22 @@ __device__ __forceinline__ void bpm_columns32(const u64* __restrict__ sm, int st
   const u32 chunk_bytes = (u32)stride * 8u;
   for (; rem >= 32; rem -= 32, cbytes += chunk_bytes) {
     const uint4 q = nextq; nextq = __ldg(rq++);
-    bpm_group32<V, 0>(cbytes, pstride8, q.x, mask, VP, VN, acc, matched, two);
-    bpm_group32<V, 1>(cbytes, pstride8, q.y, mask, VP, VN, acc, matched, two);
-    bpm_group32<V, 2>(cbytes, pstride8, q.z, mask, VP, VN, acc, matched, two);
-    bpm_group32<V, 3>(cbytes, pstride8, q.w, mask, VP, VN, acc, matched, two);
-    if (V == 0) err += 32 - __popc(acc);
-    if (V == 0 ? err > limit : (L - rem + 32) - (int)matched > limit) return;
+    bpm_group32<0>(cbytes, pstride8, q.x, mask, VP, VN, dbits);
+    bpm_group32<1>(cbytes, pstride8, q.y, mask, VP, VN, dbits);
+    bpm_group32<2>(cbytes, pstride8, q.z, mask, VP, VN, dbits);
+    bpm_group32<3>(cbytes, pstride8, q.w, mask, VP, VN, dbits);
+    err += 32 - __popc(dbits);
+    if (err > limit) return;
   }
   if (rem > 0) {                                            // the last, partial chunk
     const uint4 q = nextq;
-    if (rem >= 8) bpm_group32<V, 0>(cbytes, pstride8, q.x, mask, VP, VN, acc, matched, two); else bpm_tail32<V, 0>(cbytes, pstride8, q.x, rem, mask, VP, VN, acc, matched, two);
-    if (rem >= 16) bpm_group32<V, 1>(cbytes, pstride8, q.y, mask, VP, VN, acc, matched, two); else if (rem > 8) bpm_tail32<V, 1>(cbytes, pstride8, q.y, rem - 8, mask, VP, VN, acc, matched, two);
-    if (rem >= 24) bpm_group32<V, 2>(cbytes, pstride8, q.z, mask, VP, VN, acc, matched, two); else if (rem > 16) bpm_tail32<V, 2>(cbytes, pstride8, q.z, rem - 16, mask, VP, VN, acc, matched, two);
-    if (rem > 24) bpm_tail32<V, 3>(cbytes, pstride8, q.w, rem - 24, mask, VP, VN, acc, matched, two);
-    if (V == 0) err += rem - __popc(acc >> (32 - rem));
+    if (rem >= 8) bpm_group32<0>(cbytes, pstride8, q.x, mask, VP, VN, dbits); else bpm_tail32<0>(cbytes, pstride8, q.x, rem, mask, VP, VN, dbits);
+    if (rem >= 16) bpm_group32<1>(cbytes, pstride8, q.y, mask, VP, VN, dbits); else if (rem > 8) bpm_tail32<1>(cbytes, pstride8, q.y, rem - 8, mask, VP, VN, dbits);
+    if (rem >= 24) bpm_group32<2>(cbytes, pstride8, q.z, mask, VP, VN, dbits); else if (rem > 16) bpm_tail32<2>(cbytes, pstride8, q.z, rem - 16, mask, VP, VN, dbits);
+    if (rem > 24) bpm_tail32<3>(cbytes, pstride8, q.w, rem - 24, mask, VP, VN, dbits);
+    err += rem - __popc(dbits >> (32 - rem));
+    if (err > limit) return;
   }
-  if (V != 0) err = L - (int)matched;
-  if (err > limit) return;
   // the last column, down the band (Levenshtein_Cal.h:524-563): position p = 0 .. 2k is the cell whose alignment ends at window
   // position L - 1 + p, S(p) = err + (VP bits below p) - (VN bits below p); the answer is the LAST position that holds the
   // column's minimum (if that is within k), except that the un-gapped end p = k wins a tie.  S only falls on VN bits, so the
@@ -1573,8 +1538,7 @@ __device__ __forceinline__ void bpm_columns32(const u64* __restrict__ sm, int st
   end_out = site; err_out = best;
 }
 
-template <int V>
-__global__ void verify_windows(DevIndex ix, BatchView b, int nch2, u32 two) {
+__global__ void verify_windows(DevIndex ix, BatchView b, int nch2) {
   extern __shared__ u64 sm_all[];
   __shared__ u64 s_cnt[3];
   if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
@@ -1624,7 +1588,7 @@ __global__ void verify_windows(DevIndex ix, BatchView b, int nch2, u32 two) {
         for (int c = 0; c <= nch; ++c) for (int p = 0; p < 5; ++p) sm[(p * nch2 + c) * stride] = 0;
       }
       const u32* rw = b.codes + i1.x;
-      if (k <= 15) bpm_columns32<V>(sm, stride, nch2, rw, L, k, end, err, two);
+      if (k <= 15) bpm_columns32(sm, stride, nch2, rw, L, k, end, err);
       else bpm_columns<u64>(sm, stride, nch2, rw, L, k, end, err);
       ++verified; cells += (u64)L * (u64)(2 * k + 1);
     }

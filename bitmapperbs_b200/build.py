@@ -34,7 +34,7 @@ def _run(cmd):
 
 
 def build_library(force=False) -> Path:
-    src = [PKG / "csrc/bmbs_api.cu", PKG / "csrc/bmbs_kernels.cuh", PKG / "csrc/bmbs_device.cuh", PKG / "csrc/bmbs_sort_replay.h", PKG / "csrc/bmbs_finish_pe.cuh", ROOT / "include/bmbs.h"]
+    src = [PKG / "csrc/bmbs_api.cu", PKG / "csrc/bmbs_kernels.cuh", PKG / "csrc/bmbs_device.cuh", PKG / "csrc/bmbs_sort_replay.h", PKG / "csrc/bmbs_band_walk.h", PKG / "csrc/bmbs_finish_pe.cuh", ROOT / "include/bmbs.h"]
     if force or _newer(LIB, src):
         _run([NVCC, *NVCC_FLAGS, "-shared", src[0], "-o", LIB])
     return LIB

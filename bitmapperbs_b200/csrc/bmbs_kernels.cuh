@@ -17,6 +17,7 @@
 #pragma once
 #include "bmbs_device.cuh"
 #include "bmbs_sort_replay.h"
+#include "bmbs_band_walk.h"
 #include "../../include/bmbs.h"
 
 namespace bmbs {
@@ -1406,26 +1407,7 @@ __device__ __forceinline__ void bpm_columns(const u64* __restrict__ sm, int stri
   }
   end_out = -1; err_out = 0xFFFFFFFFu;
   if (dead) return;
-  // the last column, from VN run to VN run (see bpm_columns32)
-  const int last = L - 1;
-  const u64 bm = (u64)(mask >> 1);                          // bits 0 .. 2k-1
-  const u64 vp = (u64)VP & bm, vn = (u64)VN & bm, any = vp | vn;
-  if (err - __popcll(vn) > k) return;
-  u32 best = 0xFFFFFFFFu; int site = -1;
-  if (err <= k) { best = (u32)err; site = last + (any ? __ffsll((long long)any) - 1 : 2 * k); }
-  for (u64 rest = vn; rest;) {
-    const int a = __ffsll((long long)rest) - 1;             // a run of VN bits [a, b)
-    const int b = a + __ffsll((long long)~(vn >> a)) - 1;
-    const u64 below = (1ull << b) - 1ull;
-    const int cur = err + __popcll(vp & below) - __popcll(vn & below);     // S(b)
-    const u64 above = any >> b;
-    if (cur <= k && (u32)cur <= best) { best = (u32)cur; site = last + (above ? b + __ffsll((long long)above) - 1 : 2 * k); }
-    rest &= ~below;
-  }
-  const u64 below_k = (1ull << k) - 1ull;
-  const int ungapped = err + __popcll(vp & below_k) - __popcll(vn & below_k);   // S(k)
-  if (ungapped <= k && (u32)ungapped == best) site = last + k;
-  end_out = site; err_out = best;
+  band_last_column<W>(VP, VN, err, k, L, end_out, err_out);     // the last column, from VN run to VN run (bmbs_band_walk.h)
 }
 
 // ---- 32-bit band (k <= 15): the form the ALU pipe is budgeted for.  Per column: one PRMT takes the read's code out of a
@@ -1511,31 +1493,7 @@ __device__ __forceinline__ void bpm_columns32(const u64* __restrict__ sm, int st
     err += rem - __popc(dbits >> (32 - rem));
     if (err > limit) return;
   }
-  // the last column, down the band (Levenshtein_Cal.h:524-563): position p = 0 .. 2k is the cell whose alignment ends at window
-  // position L - 1 + p, S(p) = err + (VP bits below p) - (VN bits below p); the answer is the LAST position that holds the
-  // column's minimum (if that is within k), except that the un-gapped end p = k wins a tie.  S only falls on VN bits, so the
-  // minimum stands either on the first plateau (from p = 0 to the first set bit) or on the plateau that follows a run of VN
-  // bits: the walk goes from run to run (two or three per window) instead of cell by cell, and a window whose smallest
-  // possible value err - popc(VN) is beyond k is not walked at all.
-  const int last = L - 1;
-  const u32 bm = mask >> 1;                                 // bits 0 .. 2k-1
-  const u32 vp = VP & bm, vn = VN & bm, any = vp | vn;
-  if (err - __popc(vn) > k) return;
-  u32 best = 0xFFFFFFFFu; int site = -1;
-  if (err <= k) { best = (u32)err; site = last + (any ? __ffs(any) - 1 : 2 * k); }
-  for (u32 rest = vn; rest;) {
-    const int a = __ffs(rest) - 1;                          // a run of VN bits [a, b)
-    const int b = a + __ffs(~(vn >> a)) - 1;
-    const u32 below = (1u << b) - 1u;
-    const int cur = err + __popc(vp & below) - __popc(vn & below);     // S(b)
-    const u32 above = any >> b;
-    if (cur <= k && (u32)cur <= best) { best = (u32)cur; site = last + (above ? b + __ffs(above) - 1 : 2 * k); }
-    rest &= ~below;
-  }
-  const u32 below_k = (1u << k) - 1u;
-  const int ungapped = err + __popc(vp & below_k) - __popc(vn & below_k);   // S(k)
-  if (ungapped <= k && (u32)ungapped == best) site = last + k;
-  end_out = site; err_out = best;
+  band_last_column<u32>(VP, VN, err, k, L, end_out, err_out);   // the last column, from VN run to VN run (bmbs_band_walk.h)
 }
 
 __global__ void verify_windows(DevIndex ix, BatchView b, int nch2) {

@@ -412,8 +412,20 @@ struct bmbs_batch {
 };
 
 namespace {
-void launch_verify(bmbs_batch* b, int per_sm, int bd, size_t smem, cudaStream_t s, const DevIndex& ix, const BatchView& v, int nch2) {
-  verify_windows<<<b->sm_count * per_sm, bd, smem, s>>>(ix, v, nch2); ++b->launches;
+// verify_windows over the work list.  Shared memory: five match planes of nch2 overlapping 64-bit chunks per thread; the 32-bit
+// band (every k <= 15) reads the chunk of its column only, the 64-bit band the one after it as well.  The grid is what is
+// resident at once (the kernel is a grid-stride loop over windows of equal cost: blocks beyond that would run alone at the end).
+void launch_verify(bmbs_batch* b, double e_rate, cudaStream_t s, const DevIndex& ix, const BatchView& v) {
+  const double kd = e_rate * (double)b->max_len;                       // k of the longest read, as pack_reads computes it
+  const int kmax = kd >= 31.0 ? 31 : (int)(u64)kd;
+  const int nch2 = (b->max_len + 31) / 32 + (kmax <= 15 ? 0 : 1);
+  int bd = 128;
+  while (bd > 32 && (size_t)5 * nch2 * bd * 8 > 96 * 1024) bd >>= 1;
+  const size_t smem = (size_t)5 * std::max(nch2, 1) * bd * 8;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, verify_windows, bd, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  if (per_sm > 12) per_sm = 12;
+  verify_windows<<<b->sm_count * per_sm, bd, smem, s>>>(ix, v, std::max(nch2, 1)); ++b->launches;
 }
 // device arrays of a batch are carved out of one slab (one cudaMalloc per batch context): requests are recorded first
 struct SlabRequest { void** slot; size_t bytes; };
@@ -577,14 +589,9 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
     CU(cudaEventRecord(b->ev[4], s));
     if (b->pe && !v.sensitive) { filter_pairs_kernel<<<(n / 2 + 127) / 128, 128, 0, s>>>(v); ++b->launches; }
     CU(cudaEventRecord(b->ev[5], s));
-    const int nch2 = (b->max_len + 31) / 32 + 2;
-    int bd = 128;
-    while (bd > 32 && (size_t)5 * nch2 * bd * 8 > 96 * 1024) bd >>= 1;
-    const size_t smem = (size_t)5 * nch2 * bd * 8;
-    int per_sm = (int)((226 * 1024) / (smem + 1024)); if (per_sm > 12) per_sm = 12; if (per_sm < 1) per_sm = 1;
     run_scan(b, v.nv, (u32)n, v.voff, v.totals + 1, v.slot_cap, 4u);
     gather_work<<<(n + 127) / 128, 128, 0, s>>>(v); ++b->launches;
-    launch_verify(b, per_sm, bd, smem, s, ix, v, nch2);
+    launch_verify(b, v.e_rate, s, ix, v);
     CU(cudaEventRecord(b->ev[6], s));
     if (v.sensitive) {
       // --pe --sensitive: pair logic on the verified lists, then one re-seeding round for the mates left without a hit
@@ -603,7 +610,7 @@ extern "C" int bmbs_batch_run(bmbs_batch* b, const bmbs_params* prm) {
       sens_reseed_filter<<<b->sm_count * 4, 128, 0, s>>>(w); ++b->launches;
       run_scan(b, w.nv, (u32)n, w.voff, w.totals + 1, w.slot_cap, 4u, w.totals + 2);
       gather_work<<<(n + 127) / 128, 128, 0, s>>>(w); ++b->launches;
-      launch_verify(b, per_sm, bd, smem, s, ix, w, nch2);
+      launch_verify(b, w.e_rate, s, ix, w);
       sens_reseed_finish<<<b->sm_count * 4, 128, 0, s>>>(w); ++b->launches;
     }
     CU(cudaEventRecord(b->ev[7], s));
@@ -852,12 +859,7 @@ extern "C" int bmbs_batch_verify(bmbs_batch* b, const uint32_t* read_idx, const 
   const u32 m = (u32)(n > (size_t)n_reads ? n : (size_t)n_reads);
   if (m) { verify_setup<<<(m + 255) / 256, 256, 0, s>>>(v, v.slot_read, v.slot_row, (u32)n); ++b->launches; }
   for (int i = 1; i <= 5; ++i) CU(cudaEventRecord(b->ev[i], s));
-  const int nch2 = (b->max_len + 31) / 32 + 2;
-  int bd = 128;
-  while (bd > 32 && (size_t)5 * nch2 * bd * 8 > 96 * 1024) bd >>= 1;
-  const size_t smem = (size_t)5 * nch2 * bd * 8;
-  int per_sm = (int)((226 * 1024) / (smem + 1024)); if (per_sm > 12) per_sm = 12; if (per_sm < 1) per_sm = 1;
-  launch_verify(b, per_sm, bd, smem, s, b->copy->view, v, nch2);
+  launch_verify(b, v.e_rate, s, b->copy->view, v);
   CU(cudaEventRecord(b->ev[6], s)); CU(cudaEventRecord(b->ev[7], s)); CU(cudaEventRecord(b->ev[8], s));
   CU(cudaMemcpyAsync(b->h_small + 4, v.counters, 8 * 8, cudaMemcpyDeviceToHost, s));
   CU(cudaGetLastError());

@@ -1496,7 +1496,7 @@ __device__ __forceinline__ void bpm_columns32(const u64* __restrict__ sm, int st
   band_last_column<u32>(VP, VN, err, k, L, end_out, err_out);   // the last column, from VN run to VN run (bmbs_band_walk.h)
 }
 
-__global__ void verify_windows(DevIndex ix, BatchView b, int nch2) {
+__global__ void __launch_bounds__(128, 7) verify_windows(DevIndex ix, BatchView b, int nch2) {
   extern __shared__ u64 sm_all[];
   __shared__ u64 s_cnt[3];
   if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
@@ -1515,21 +1515,22 @@ __global__ void verify_windows(DevIndex ix, BatchView b, int nch2) {
     int end = -1; u32 err = 0xFFFFFFFFu;
     {
       const int plen = L + 2 * k;
-      const int nch = (L + 31) >> 5;           // chunks addressed by the column loop (+1 for 64-bit bands)
+      const int nch = (L + 31) >> 5;           // chunks addressed by the column loop
+      const int nst = k <= 15 ? nch : nch + 1;  // chunks staged: the 64-bit band also reads the chunk after the column's (nst <= nch2, see launch_verify)
       const bool inside = window_inside(ix, site, (u64)plen);
       if (inside) {
         // window words gp[0 .. nch+2]: eight chunks per pass, their ten words loaded back to back (independent loads in
         // flight together instead of one dependent round trip per chunk)
         const uint2* gp = ix.planes + (site >> 5);
         const unsigned sh = (unsigned)site & 31u;
-        for (int c0 = 0; c0 <= nch; c0 += 8) {
+        for (int c0 = 0; c0 < nst; c0 += 8) {
           uint2 w[10];
 #pragma unroll
           for (int j = 0; j < 10; ++j) w[j] = c0 + j <= nch + 2 ? __ldg(gp + c0 + j) : make_uint2(0u, 0u);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int c = c0 + j;
-            if (c <= nch) {
+            if (c < nst) {
               const u32 lo0 = __funnelshift_r(w[j].x, w[j + 1].x, sh), hi0 = __funnelshift_r(w[j].y, w[j + 1].y, sh);
               const u32 lo1 = __funnelshift_r(w[j + 1].x, w[j + 2].x, sh), hi1 = __funnelshift_r(w[j + 1].y, w[j + 2].y, sh);
               const u64 lo = (u64)lo0 | ((u64)lo1 << 32), hi = (u64)hi0 | ((u64)hi1 << 32);
@@ -1543,7 +1544,7 @@ __global__ void verify_windows(DevIndex ix, BatchView b, int nch2) {
         }
         wbytes += (u64)(nch + 3) * 8;
       } else {
-        for (int c = 0; c <= nch; ++c) for (int p = 0; p < 5; ++p) sm[(p * nch2 + c) * stride] = 0;
+        for (int c = 0; c < nst; ++c) for (int p = 0; p < 5; ++p) sm[(p * nch2 + c) * stride] = 0;
       }
       const u32* rw = b.codes + i1.x;
       if (k <= 15) bpm_columns32(sm, stride, nch2, rw, L, k, end, err);
